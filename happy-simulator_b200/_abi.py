@@ -1,0 +1,105 @@
+"""ctypes mirror of include/hs_b200.h (the C-ABI structs and constants)."""
+from __future__ import annotations
+
+import ctypes as C
+
+HS_ABI_VERSION = 1
+
+HS_OK, HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_NO_DEVICE, HS_ERR_STATE, HS_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
+
+HS_ENT_SOURCE, HS_ENT_SERVER, HS_ENT_SINK, HS_ENT_COUNTER, HS_ENT_LB = 1, 2, 3, 4, 5
+HS_ARR_CONSTANT, HS_ARR_POISSON = 0, 1
+HS_SVC_CONSTANT, HS_SVC_EXPONENTIAL = 0, 1
+HS_Q_FIFO, HS_Q_LIFO = 0, 1
+HS_LB_ROUND_ROBIN, HS_LB_KEY_TABLE = 0, 1
+
+(HS_EV_SOURCE_TICK, HS_EV_REQ_LB, HS_EV_REQ_ENQUEUE, HS_EV_NOTIFY, HS_EV_POLL, HS_EV_DELIVER,
+ HS_EV_REQ_WORKER, HS_EV_CONTINUATION, HS_EV_REQ_SINK, HS_EV_LB_RESPONSE, HS_EV_REQ_COUNTER) = range(11)
+
+EVENT_KIND_NAMES = ["SOURCE_TICK", "REQ_LB", "REQ_ENQUEUE", "NOTIFY", "POLL", "DELIVER",
+                    "REQ_WORKER", "CONTINUATION", "REQ_SINK", "LB_RESPONSE", "REQ_COUNTER"]
+
+HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH = 1, 2, 4
+
+HS_STREAM_ARRIVAL, HS_STREAM_SERVICE, HS_STREAM_ROUTING = 0, 1, 2
+
+HS_TOTALS_I64, HS_TOTALS_F64_SUM = 8, 3
+
+
+class EntityDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("target", C.c_int32), ("i0", C.c_int32), ("i1", C.c_int32),
+                ("i2", C.c_int32), ("i3", C.c_int32), ("l0", C.c_int64), ("d0", C.c_double),
+                ("d1", C.c_double)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("n_entities", C.c_uint32),
+                ("entities", C.POINTER(EntityDesc)),
+                ("n_backends", C.c_uint32), ("key_population", C.c_uint32),
+                ("backends", C.POINTER(C.c_int32)), ("key_table", C.POINTER(C.c_int32)),
+                ("n_cells", C.c_uint32), ("reserved", C.c_uint32),
+                ("cell_d0", C.POINTER(C.c_double)), ("cell_i0", C.POINTER(C.c_int32))]
+
+
+class RunParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("seed_stride", C.c_uint64),
+                ("rid_base", C.c_uint32), ("rid_stride", C.c_uint32),
+                ("end_ns", C.c_int64),
+                ("n_replicas", C.c_uint32), ("replica_index_base", C.c_uint32),
+                ("replicas_per_cell", C.c_uint32), ("record_cap", C.c_uint32),
+                ("sample_cap", C.c_uint32), ("service_cap", C.c_uint32),
+                ("queue_ring", C.c_uint32), ("engine", C.c_uint32)]
+
+
+class ReplicaSummary(C.Structure):
+    _fields_ = [("events_processed", C.c_int64), ("final_time_ns", C.c_int64),
+                ("order_hash", C.c_uint64), ("next_sort_index", C.c_uint64),
+                ("heap_left", C.c_int32), ("status", C.c_uint32)]
+
+
+class EntityStats(C.Structure):
+    _fields_ = [("c0", C.c_int64), ("c1", C.c_int64), ("c2", C.c_int64), ("c3", C.c_int64),
+                ("f0", C.c_double), ("f1", C.c_double), ("f2", C.c_double), ("f3", C.c_double)]
+
+
+class EventRecord(C.Structure):
+    _fields_ = [("time_ns", C.c_int64), ("sort_index", C.c_uint32), ("kind", C.c_uint8),
+                ("pad", C.c_uint8), ("entity", C.c_uint16)]
+
+
+class SinkSample(C.Structure):
+    _fields_ = [("completion_ns", C.c_int64), ("latency_s", C.c_double)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("summaries", C.POINTER(ReplicaSummary)), ("entity_stats", C.POINTER(EntityStats)),
+                ("records", C.POINTER(EventRecord)), ("sink_samples", C.POINTER(SinkSample)),
+                ("service_samples", C.POINTER(C.c_double))]
+
+
+class Totals(C.Structure):
+    _fields_ = [("i", C.c_int64 * HS_TOTALS_I64), ("fsum", C.c_double * HS_TOTALS_F64_SUM),
+                ("fmin", C.c_double), ("fmax", C.c_double)]
+
+
+assert C.sizeof(EntityDesc) == 48
+assert C.sizeof(ReplicaSummary) == 40
+assert C.sizeof(EntityStats) == 64
+assert C.sizeof(EventRecord) == 16
+assert C.sizeof(SinkSample) == 16
+assert C.sizeof(RunParams) == 64
+
+# numpy views of the same layouts (host buffers are numpy structured arrays)
+import numpy as _np
+
+SUMMARY_DTYPE = _np.dtype([("events_processed", "<i8"), ("final_time_ns", "<i8"), ("order_hash", "<u8"),
+                           ("next_sort_index", "<u8"), ("heap_left", "<i4"), ("status", "<u4")])
+STATS_DTYPE = _np.dtype([("c0", "<i8"), ("c1", "<i8"), ("c2", "<i8"), ("c3", "<i8"),
+                         ("f0", "<f8"), ("f1", "<f8"), ("f2", "<f8"), ("f3", "<f8")])
+RECORD_DTYPE = _np.dtype([("time_ns", "<i8"), ("sort_index", "<u4"), ("kind", "u1"), ("pad", "u1"),
+                          ("entity", "<u2")])
+SAMPLE_DTYPE = _np.dtype([("completion_ns", "<i8"), ("latency_s", "<f8")])
+ENTITY_DTYPE = _np.dtype([("kind", "<i4"), ("target", "<i4"), ("i0", "<i4"), ("i1", "<i4"), ("i2", "<i4"),
+                          ("i3", "<i4"), ("l0", "<i8"), ("d0", "<f8"), ("d1", "<f8")])
+assert SUMMARY_DTYPE.itemsize == 40 and STATS_DTYPE.itemsize == 64 and RECORD_DTYPE.itemsize == 16
+assert ENTITY_DTYPE.itemsize == 48

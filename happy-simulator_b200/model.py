@@ -1,0 +1,171 @@
+"""Flat model table: the data format the engine (and the CPU oracle) consume.
+
+A ``FlatModel`` is the lowered form of what ``Simulation.__init__`` receives as
+``sources=`` / ``entities=`` (reference: happysimulator/core/simulation.py:66-102):
+one ``hs_entity_desc`` row per Source / Server / Sink / Counter / LoadBalancer,
+the LoadBalancer backend lists, an optional routing-key -> backend table (the
+host-side evaluation of ConsistentHash.select, strategies.py:411-433) and an
+optional per-cell parameter override for sweeps.  See include/hs_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi as A
+
+
+@dataclass
+class FlatModel:
+    entities: np.ndarray                      # ENTITY_DTYPE[n]
+    names: list[str] = field(default_factory=list)
+    backends: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    key_table: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    cell_d0: np.ndarray | None = None         # float64[n_cells, n]
+    cell_i0: np.ndarray | None = None         # int32[n_cells, n]
+
+    @property
+    def n_entities(self) -> int:
+        return int(self.entities.shape[0])
+
+    @property
+    def n_cells(self) -> int:
+        return 0 if self.cell_d0 is None else int(self.cell_d0.shape[0])
+
+    def ids_of(self, kind: int) -> list[int]:
+        return [i for i in range(self.n_entities) if int(self.entities["kind"][i]) == kind]
+
+    def desc(self) -> A.ModelDesc:
+        """ctypes view; keeps references to the numpy buffers on the returned struct."""
+        ents = np.ascontiguousarray(self.entities)
+        be = np.ascontiguousarray(self.backends, dtype=np.int32)
+        kt = np.ascontiguousarray(self.key_table, dtype=np.int32)
+        d = A.ModelDesc()
+        d.abi_version = A.HS_ABI_VERSION
+        d.n_entities = self.n_entities
+        d.entities = ents.ctypes.data_as(C.POINTER(A.EntityDesc))
+        d.n_backends = be.shape[0]
+        d.key_population = kt.shape[0]
+        d.backends = be.ctypes.data_as(C.POINTER(C.c_int32)) if be.size else None
+        d.key_table = kt.ctypes.data_as(C.POINTER(C.c_int32)) if kt.size else None
+        keep = [ents, be, kt]
+        if self.cell_d0 is not None:
+            cd = np.ascontiguousarray(self.cell_d0, dtype=np.float64)
+            ci = np.ascontiguousarray(self.cell_i0, dtype=np.int32)
+            assert cd.shape == ci.shape == (cd.shape[0], self.n_entities)
+            d.n_cells = cd.shape[0]
+            d.cell_d0 = cd.ctypes.data_as(C.POINTER(C.c_double))
+            d.cell_i0 = ci.ctypes.data_as(C.POINTER(C.c_int32))
+            keep += [cd, ci]
+        d._keep = keep
+        return d
+
+
+class ModelBuilder:
+    """Incremental construction of a FlatModel (entity ids are creation order)."""
+
+    def __init__(self):
+        self._rows: list[tuple] = []
+        self._names: list[str] = []
+        self._backends: list[int] = []
+        self._key_table = np.zeros(0, np.int32)
+
+    def _add(self, name, kind, target=-1, i0=0, i1=0, i2=0, l0=-1, d0=0.0):
+        self._rows.append((kind, target, i0, i1, i2, 0, l0, d0, 0.0))
+        self._names.append(name)
+        return len(self._rows) - 1
+
+    def source(self, name="Source", *, rate, target=-1, poisson=True, stop_after_ns=-1, key_population=0):
+        return self._add(name, A.HS_ENT_SOURCE, target, A.HS_ARR_POISSON if poisson else A.HS_ARR_CONSTANT,
+                         key_population, 0, stop_after_ns, float(rate))
+
+    def server(self, name="Server", *, concurrency=1, mean_service_s=0.01, exponential=True,
+               downstream=-1, capacity=-1, lifo=False):
+        return self._add(name, A.HS_ENT_SERVER, downstream, int(concurrency),
+                         A.HS_Q_LIFO if lifo else A.HS_Q_FIFO,
+                         A.HS_SVC_EXPONENTIAL if exponential else A.HS_SVC_CONSTANT,
+                         int(capacity), float(mean_service_s))
+
+    def sink(self, name="Sink"):
+        return self._add(name, A.HS_ENT_SINK)
+
+    def counter(self, name="Counter"):
+        return self._add(name, A.HS_ENT_COUNTER)
+
+    def load_balancer(self, name="LB", *, backends, key_table=None):
+        off = len(self._backends)
+        self._backends += [int(b) for b in backends]
+        strat = A.HS_LB_ROUND_ROBIN
+        if key_table is not None:
+            strat = A.HS_LB_KEY_TABLE
+            self._key_table = np.asarray(key_table, dtype=np.int32)
+        return self._add(name, A.HS_ENT_LB, -1, strat, off, len(backends))
+
+    def set_target(self, ent, target):
+        r = list(self._rows[ent]); r[1] = int(target); self._rows[ent] = tuple(r)
+
+    def build(self) -> FlatModel:
+        ents = np.array(self._rows, dtype=A.ENTITY_DTYPE)
+        return FlatModel(entities=ents, names=list(self._names),
+                         backends=np.asarray(self._backends, dtype=np.int32),
+                         key_table=self._key_table)
+
+
+# ---- the BASELINE.json configurations ------------------------------------
+
+def mm1(rate=8.0, mean_service_s=0.1, *, poisson=True, exponential=True, capacity=-1,
+        concurrency=1, lifo=False) -> FlatModel:
+    """configs[0]/[1]: Source.poisson(rate) -> Server(Exponential(mean)) -> Sink."""
+    b = ModelBuilder()
+    src = b.source(rate=rate, poisson=poisson)
+    srv = b.server(concurrency=concurrency, mean_service_s=mean_service_s, exponential=exponential,
+                   capacity=capacity, lifo=lifo)
+    snk = b.sink()
+    b.set_target(src, srv)
+    b.set_target(srv, snk)
+    return b.build()
+
+
+def lb_round_robin(n_servers=64, rate=512.0, mean_service_s=0.1) -> FlatModel:
+    """configs[2]: Source.poisson(rate) -> LoadBalancer(RoundRobin) -> n x Server(1, Exp) -> Sink."""
+    b = ModelBuilder()
+    src = b.source(rate=rate)
+    servers = [b.server(f"S{i}", mean_service_s=mean_service_s) for i in range(n_servers)]
+    snk = b.sink()
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb)
+    for s in servers:
+        b.set_target(s, snk)
+    return b.build()
+
+
+def lb_key_table(key_table, n_servers, rate, mean_service_s=0.1) -> FlatModel:
+    """configs[3]: Source.poisson(rate) with client_id ~ Uniform{0..K-1} ->
+    LoadBalancer(ConsistentHash) -> n x Server -> Sink; key_table[k] = backend slot
+    (use lowering.consistent_hash_table to evaluate the MD5 ring on the host)."""
+    b = ModelBuilder()
+    src = b.source(rate=rate, key_population=len(key_table))
+    servers = [b.server(f"S{i}", mean_service_s=mean_service_s) for i in range(n_servers)]
+    snk = b.sink()
+    lb = b.load_balancer(backends=servers, key_table=key_table)
+    b.set_target(src, lb)
+    for s in servers:
+        b.set_target(s, snk)
+    return b.build()
+
+
+def mmc_sweep(cs=range(1, 33), rhos=(0.5, 0.6, 0.7, 0.8, 0.85, 0.9, 0.95, 0.99), mu=10.0) -> FlatModel:
+    """configs[4]: M/M/c cells, c x rho grid, lambda = rho * c * mu."""
+    m = mm1(rate=1.0, mean_service_s=1.0 / mu)
+    cells = [(c, rho) for c in cs for rho in rhos]
+    n = m.n_entities
+    cd = np.tile(m.entities["d0"].astype(np.float64), (len(cells), 1))
+    ci = np.tile(m.entities["i0"].astype(np.int32), (len(cells), 1))
+    for k, (c, rho) in enumerate(cells):
+        cd[k, 0] = rho * c * mu
+        ci[k, 1] = c
+    m.cell_d0, m.cell_i0 = cd, ci
+    m.cells = cells
+    return m

@@ -1,0 +1,233 @@
+/* hs_b200.h -- C-ABI of the B200 discrete-event engine (libhs_b200.so).
+ *
+ * The reference (adamfilli/happy-simulator) is pure Python and has NO FFI or
+ * plugin registry for its run loop: the boundary it
+ * offers is the Python object protocol
+ *     Simulation(sources=, entities=, end_time=|duration=).run() -> SimulationSummary
+ *     (happysimulator/core/simulation.py:66-76,230-288)
+ *     ParallelRunner.run_replicas(build_fn, n, base_seed)
+ *     (happysimulator/parallel/runner.py:115-142)
+ * with results read back off the entity objects.  The entry points below are
+ * what a ctypes binding of that boundary needs: upload a flattened model
+ * (the object graph Simulation.__init__ receives), run N replicas of
+ * Simulation.run()'s pop-invoke-push loop on the device, read per-replica
+ * summaries / entity statistics / event records back.  Plain pointers and
+ * sizes only; no torch types.  Every function returns 0 on success or a
+ * negative hs_status; hs_last_error() gives the message of the calling
+ * thread's last failure.  One host thread per engine handle.
+ *
+ * The same structs are the input/output format of the CPU oracle
+ * (oracle/hs_oracle.c), so parity tests feed identical bytes to both sides.
+ */
+#ifndef HS_B200_H
+#define HS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_ABI_VERSION 1u
+
+typedef enum hs_status {
+    HS_OK = 0,
+    HS_ERR_INVALID = -1,     /* bad argument / unsupported model             */
+    HS_ERR_CUDA = -2,        /* CUDA runtime failure (message has details)   */
+    HS_ERR_NO_DEVICE = -3,   /* no CUDA device: the engine never falls back  */
+    HS_ERR_STATE = -4,       /* call out of order (e.g. run before upload)   */
+    HS_ERR_OVERFLOW = -5     /* a replica overflowed a fixed-size structure  */
+} hs_status;
+
+/* ---- model ------------------------------------------------------------- */
+
+/* Entity kinds: the reference classes the engine lowers. */
+enum {
+    HS_ENT_SOURCE = 1,   /* load/source.py:92  Source (+SimpleEventProvider, ArrivalTimeProvider) */
+    HS_ENT_SERVER = 2,   /* components/server/server.py:43 Server = Queue + QueueDriver + worker    */
+    HS_ENT_SINK = 3,     /* components/common.py:18 Sink                                            */
+    HS_ENT_COUNTER = 4,  /* components/common.py:79 Counter                                         */
+    HS_ENT_LB = 5        /* components/load_balancer/load_balancer.py:60 LoadBalancer               */
+};
+enum { HS_ARR_CONSTANT = 0, HS_ARR_POISSON = 1 };       /* load/providers/{constant,poisson}_arrival.py */
+enum { HS_SVC_CONSTANT = 0, HS_SVC_EXPONENTIAL = 1 };   /* distributions/{constant,exponential}.py      */
+enum { HS_Q_FIFO = 0, HS_Q_LIFO = 1 };                  /* components/queue_policy.py:75,117            */
+enum { HS_LB_ROUND_ROBIN = 0, HS_LB_KEY_TABLE = 1 };    /* strategies.py:50 RoundRobin, :336 ConsistentHash
+                                                           (ring lookup precomputed per key on the host) */
+
+/* Processed-event kinds (what Simulation._execute_until pops). */
+enum {
+    HS_EV_SOURCE_TICK = 0,  /* SourceEvent -> Source                 load/source.py:142           */
+    HS_EV_REQ_LB = 1,       /* Request -> LoadBalancer               load_balancer.py:347         */
+    HS_EV_REQ_ENQUEUE = 2,  /* Request -> Server (Queue enqueue)     queue.py:122                 */
+    HS_EV_NOTIFY = 3,       /* QueueNotifyEvent -> driver            queue_driver.py:92           */
+    HS_EV_POLL = 4,         /* QueuePollEvent -> queue               queue.py:149                 */
+    HS_EV_DELIVER = 5,      /* QueueDeliverEvent -> driver           queue_driver.py:66           */
+    HS_EV_REQ_WORKER = 6,   /* Request -> worker (service start)     server/server.py:202         */
+    HS_EV_CONTINUATION = 7, /* ProcessContinuation (service end)     core/event.py:465            */
+    HS_EV_REQ_SINK = 8,     /* Request -> Sink                       common.py:36                 */
+    HS_EV_LB_RESPONSE = 9,  /* _lb_response -> LoadBalancer          load_balancer.py:435         */
+    HS_EV_REQ_COUNTER = 10  /* Request -> Counter                    common.py:92                 */
+};
+
+typedef struct hs_entity_desc {
+    int32_t kind;      /* HS_ENT_*                                                              */
+    int32_t target;    /* SOURCE: entity receiving payloads; SERVER: downstream or -1           */
+    int32_t i0;        /* SOURCE: HS_ARR_*; SERVER: concurrency (FixedConcurrency); LB: HS_LB_* */
+    int32_t i1;        /* SOURCE: key population (0 = no routing key); SERVER: HS_Q_*;
+                          LB: offset of its backend list in hs_model_desc.backends              */
+    int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends                              */
+    int32_t i3;        /* reserved, 0                                                           */
+    int64_t l0;        /* SOURCE: stop_after in ns or -1; SERVER: queue capacity or -1 (= inf)  */
+    double d0;         /* SOURCE: rate (events/s); SERVER: mean / constant service time (s)     */
+    double d1;         /* reserved, 0                                                           */
+} hs_entity_desc;      /* 48 bytes */
+
+typedef struct hs_model_desc {
+    uint32_t abi_version;          /* HS_ABI_VERSION */
+    uint32_t n_entities;
+    const hs_entity_desc *entities;
+    uint32_t n_backends;           /* total length of backends[]                               */
+    uint32_t key_population;       /* length of key_table[] (0 if unused)                      */
+    const int32_t *backends;       /* entity ids, LB backend lists concatenated                */
+    const int32_t *key_table;      /* routing key -> index into the LB's backend list          */
+    /* Parameter sweep ("cells"): replica r belongs to cell r / replicas_per_cell; a cell
+     * overrides d0 / i0 of every entity.  NULL = no override.                                 */
+    uint32_t n_cells;
+    uint32_t reserved;
+    const double *cell_d0;         /* [n_cells][n_entities] or NULL */
+    const int32_t *cell_i0;        /* [n_cells][n_entities] or NULL */
+} hs_model_desc;
+
+/* ---- run --------------------------------------------------------------- */
+
+typedef struct hs_run_params {
+    uint64_t seed;             /* Philox key of replica r = seed + r * seed_stride             */
+    uint64_t seed_stride;      /* 1 mirrors ParallelRunner (base_seed + i), 0 for ensembles    */
+    uint32_t rid_base;         /* Philox replica word of replica r = rid_base + r * rid_stride */
+    uint32_t rid_stride;
+    int64_t end_ns;            /* Simulation end_time; the loop processes while now <= end_ns  */
+    uint32_t n_replicas;       /* replicas run by THIS call                                    */
+    uint32_t replica_index_base; /* global index of this call's replica 0 (multi-GPU shards)   */
+    uint32_t replicas_per_cell;  /* cell = global index / replicas_per_cell (>=1)              */
+    uint32_t record_cap;       /* event records kept per replica (first record_cap events)     */
+    uint32_t sample_cap;       /* Sink samples kept per replica (first sample_cap)             */
+    uint32_t service_cap;      /* service-time samples kept per replica                        */
+    uint32_t queue_ring;       /* device queue ring entries per server (power of two), 0 = default */
+    uint32_t engine;           /* 0 auto, 1 warp engine (general), 2 lane engine (single server) */
+} hs_run_params;
+
+/* Replica status bits. */
+#define HS_ST_QUEUE_OVERFLOW 1u   /* a server's device queue ring filled up  */
+#define HS_ST_FEL_OVERFLOW 2u     /* future-event list slots exhausted       */
+#define HS_ST_REJECT_PATH 4u      /* Server acquire failed (server.py:223)   */
+
+typedef struct hs_replica_summary {
+    int64_t events_processed;  /* SimulationSummary.total_events_processed (simulation.py:553) */
+    int64_t final_time_ns;     /* clock after the last processed event (simulation.py:503)     */
+    uint64_t order_hash;       /* hs_hash_step over every processed event, in order            */
+    uint64_t next_sort_index;  /* value of the per-heap creation counter at the end            */
+    int32_t heap_left;         /* events still pending                                         */
+    uint32_t status;           /* HS_ST_* bits, 0 = clean                                      */
+} hs_replica_summary;          /* 40 bytes */
+
+typedef struct hs_entity_stats {
+    int64_t c0; /* SOURCE generated_count | SERVER stats_accepted | SINK events_received
+                   | COUNTER total | LB requests_received                                      */
+    int64_t c1; /* SOURCE payloads created | SERVER stats_dropped | LB requests_forwarded       */
+    int64_t c2; /* SERVER requests_completed | LB in-flight entries left                        */
+    int64_t c3; /* SERVER requests_rejected | SERVER (after run) -- ; LB responses handled      */
+    double f0;  /* SERVER total_service_time (sequential sum) | SINK sum of latencies (sequential) */
+    double f1;  /* SINK sum of squared latencies                                                */
+    double f2;  /* SINK min latency (+inf if none)                                              */
+    double f3;  /* SINK max latency (-inf if none)                                              */
+} hs_entity_stats;             /* 64 bytes */
+
+typedef struct hs_event_record {   /* 16 bytes per processed event            */
+    int64_t time_ns;
+    uint32_t sort_index;           /* low 32 bits of Event._sort_index                         */
+    uint8_t kind;                  /* HS_EV_*                                                  */
+    uint8_t pad;
+    uint16_t entity;               /* entity id (hidden queue/driver/worker -> their Server)    */
+} hs_event_record;
+
+typedef struct hs_sink_sample {    /* Sink.completion_times[i], Sink.latencies_s[i]            */
+    int64_t completion_ns;
+    double latency_s;
+} hs_sink_sample;
+
+typedef struct hs_outputs {        /* caller-owned HOST buffers; any pointer may be NULL        */
+    hs_replica_summary *summaries; /* [n_replicas]                                             */
+    hs_entity_stats *entity_stats; /* [n_replicas][n_entities]                                 */
+    hs_event_record *records;      /* [n_replicas][record_cap]                                 */
+    hs_sink_sample *sink_samples;  /* [n_replicas][sample_cap], all sinks, arrival order       */
+    double *service_samples;       /* [n_replicas][service_cap], service-start order           */
+} hs_outputs;
+
+/* Ensemble totals: what the single end-of-run NCCL allreduce carries.
+ * Sums are over replicas; extrema are min/max.  Fixed layout so ranks can reduce it as
+ * int64[HS_TOTALS_I64] (sum), double[HS_TOTALS_F64_SUM] (sum) and two extrema (min, max). */
+#define HS_TOTALS_I64 8
+#define HS_TOTALS_F64_SUM 3
+typedef struct hs_totals {
+    int64_t i[HS_TOTALS_I64];  /* 0 events_processed, 1 sink events, 2 server completions,
+                                  3 source ticks, 4 dropped, 5 replicas, 6 replicas with
+                                  status != 0, 7 sum of final_time_ns / 1000 (us)              */
+    double fsum[HS_TOTALS_F64_SUM]; /* 0 sum latency, 1 sum latency^2, 2 sum service time      */
+    double fmin;               /* min sink latency */
+    double fmax;               /* max sink latency */
+} hs_totals;
+
+/* ---- entry points ------------------------------------------------------ */
+
+typedef struct hs_engine hs_engine;
+
+/* Library / ABI version (HS_ABI_VERSION of the build). */
+uint32_t hs_version(void);
+
+/* Message of the calling thread's last error; returns its length. */
+int hs_last_error(char *buf, int len);
+
+/* Create an engine on CUDA device `device`, launching on `stream` (a cudaStream_t
+ * cast to void*, NULL = a private non-blocking stream).  Replaces
+ * Simulation.__init__'s heap/clock construction (core/simulation.py:93-106).
+ * Fails with HS_ERR_NO_DEVICE when no GPU is present: there is no CPU path. */
+int hs_engine_create(int device, void *stream, hs_engine **out);
+int hs_engine_destroy(hs_engine *e);
+
+/* Validate and upload the flattened model (what Simulation.__init__ receives
+ * as sources=/entities=, core/simulation.py:95-102). */
+int hs_model_upload(hs_engine *e, const hs_model_desc *model);
+
+/* Validate a model without a device (used by host-side tests). */
+int hs_model_validate(const hs_model_desc *model);
+
+/* Simulation.run() for params->n_replicas replicas (core/simulation.py:230,
+ * 449-505).  Asynchronous on the engine's stream; results stay on the device
+ * until hs_read_outputs / hs_read_totals. */
+int hs_run(hs_engine *e, const hs_run_params *params);
+
+/* Wait for the stream; returns HS_ERR_CUDA on a device fault. */
+int hs_sync(hs_engine *e);
+
+/* Device milliseconds of the last hs_run's kernels (CUDA events on the engine stream). */
+int hs_last_run_ms(hs_engine *e, float *ms);
+
+/* Number of kernels hs_run launched since engine creation. */
+int hs_launch_count(hs_engine *e, uint64_t *n);
+
+/* Copy results of the last run to caller-owned host buffers (synchronises). */
+int hs_read_outputs(hs_engine *e, const hs_outputs *out);
+
+/* Reduce the last run's per-replica results on the device and copy the totals
+ * (SimulationSummary-level aggregates) to the host (synchronises). */
+int hs_read_totals(hs_engine *e, hs_totals *out);
+
+/* Device pointer/size of the last run's totals (for the NCCL allreduce done by
+ * the host layer on torch.distributed; layout = hs_totals). */
+int hs_totals_device_ptr(hs_engine *e, void **ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS_B200_H */

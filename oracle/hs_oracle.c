@@ -1,0 +1,501 @@
+/* hs_oracle.c -- CPU restatement of the reference's Simulation.run() hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (happy-simulator_b200/,
+ * include/) may import, link or execute this file; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do,
+ * and only as the checker.  The product path is the CUDA engine and fails
+ * loudly without it.
+ *
+ * Parity pinning: this restatement is checked, event by event, against the
+ * UNMODIFIED reference (imported from /root/reference, driven through its own
+ * LatencyDistribution / ArrivalTimeProvider plug-in points by the Philox
+ * sampler of happy-simulator_b200/csrc/hs_sampler.h) by
+ * tests/golden/gen_golden.py; the fixtures it wrote are committed under
+ * tests/golden/ and tests/test_oracle_golden.py replays them.  The reference's
+ * own deterministic known-answer tests for this path are
+ * restated in tests/test_oracle_reference_kats.py.
+ *
+ * The structure follows the reference one to one (paths under /root/reference):
+ *   run loop            happysimulator/core/simulation.py:449-505 (_execute_until)
+ *   heap                happysimulator/core/event_heap.py:54-113 + CPython heapq
+ *   order key           happysimulator/core/event.py:337-344 (time, _sort_index)
+ *   creation counters   happysimulator/core/event.py:53-77, event_heap.py:48,
+ *                       core/sim_future.py:64-73 (global at bootstrap, per heap in run)
+ *   completion hooks    happysimulator/core/event.py:277-311
+ *   generators          happysimulator/core/event.py:313-325,465-533
+ *   Source              happysimulator/load/source.py:67-86,120-180
+ *   arrival providers   happysimulator/load/arrival_time_provider.py:57-82
+ *   Queue/Driver/Worker happysimulator/components/queue.py:115-166,
+ *                       queue_driver.py:57-99, queued_resource.py:38-49,138-143
+ *   Server              happysimulator/components/server/server.py:202-273,
+ *                       server/concurrency.py:66-140
+ *   Sink / Counter      happysimulator/components/common.py:36-44,92-95
+ *   LoadBalancer        happysimulator/components/load_balancer/load_balancer.py:347-473,
+ *                       strategies.py:61-68 (RoundRobin), :411-433 (ConsistentHash.select,
+ *                       as a host-precomputed key -> backend table)
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../include/hs_b200.h"
+#include "../happy-simulator_b200/csrc/hs_sampler.h"
+
+/* ---- one pending Event object ------------------------------------------ */
+typedef struct oev {
+    int64_t time;        /* Event.time (ns)                                       */
+    uint64_t idx;        /* Event._sort_index                                     */
+    int32_t kind;        /* HS_EV_*                                               */
+    int32_t ent;         /* target entity id                                      */
+    /* request context (Event.context): shared by forward()/LB copies            */
+    int64_t created_at;  /* context["created_at"]                                 */
+    uint32_t req_id;     /* context["request_id"]                                 */
+    int32_t key;         /* context["metadata"]["client_id"], -1 if none          */
+    int32_t lb_hook;     /* LoadBalancer on_complete hook: LB entity id, -1 none  */
+    int32_t poll_hook;   /* QueueDriver schedule_poll hook: server id, -1 none    */
+    double svc_s;        /* CONTINUATION: the service time the generator yielded  */
+    uint64_t payload_idx;/* DELIVER: _sort_index of the payload Event it carries  */
+} oev;
+
+/* ---- CPython heapq (Lib/heapq.py: heappush/_siftdown, heappop/_siftup) -- */
+typedef struct { oev *a; size_t n, cap; } oheap;
+
+static int ev_lt(const oev *x, const oev *y)    /* Event.__lt__, event.py:337-344 */
+{
+    if (x->time != y->time) return x->time < y->time;
+    return x->idx < y->idx;
+}
+
+static void heap_siftdown(oheap *h, size_t start, size_t pos)
+{
+    oev item = h->a[pos];
+    while (pos > start) {
+        size_t parent = (pos - 1) >> 1;
+        if (ev_lt(&item, &h->a[parent])) { h->a[pos] = h->a[parent]; pos = parent; continue; }
+        break;
+    }
+    h->a[pos] = item;
+}
+
+static void heap_siftup(oheap *h, size_t pos)
+{
+    size_t end = h->n, start = pos;
+    oev item = h->a[pos];
+    size_t child = 2 * pos + 1;
+    while (child < end) {
+        size_t right = child + 1;
+        if (right < end && !ev_lt(&h->a[child], &h->a[right])) child = right;
+        h->a[pos] = h->a[child];
+        pos = child;
+        child = 2 * pos + 1;
+    }
+    h->a[pos] = item;
+    heap_siftdown(h, start, pos);
+}
+
+static void heap_push(oheap *h, const oev *e)
+{
+    if (h->n == h->cap) {
+        h->cap = h->cap ? h->cap * 2 : 64;
+        h->a = (oev *)realloc(h->a, h->cap * sizeof(oev));
+    }
+    h->a[h->n++] = *e;
+    heap_siftdown(h, 0, h->n - 1);
+}
+
+static oev heap_pop(oheap *h)
+{
+    oev last = h->a[--h->n];
+    if (h->n) { oev ret = h->a[0]; h->a[0] = last; heap_siftup(h, 0); return ret; }
+    return last;
+}
+
+/* ---- entity state ------------------------------------------------------ */
+typedef struct { int64_t created_at; uint64_t idx; uint32_t req_id; int32_t key; } oreq;
+
+typedef struct oent {
+    hs_entity_desc d;        /* with the cell override applied                    */
+    /* SOURCE */
+    int64_t cur_ns;          /* ArrivalTimeProvider.current_time                  */
+    uint64_t arr_draws;      /* arrival draws consumed                            */
+    uint64_t key_draws;      /* routing-key draws consumed                        */
+    int64_t generated_count; /* Source._generated_count                           */
+    int64_t provider_count;  /* SimpleEventProvider._generated                    */
+    /* SERVER */
+    oreq *q; size_t q_head, q_len, q_cap;   /* FIFOQueue / LIFOQueue deque        */
+    int32_t active;          /* FixedConcurrency._active                          */
+    uint64_t svc_draws;
+    double lambda;           /* ExponentialLatency._lambda = 1 / mean             */
+    int64_t accepted, dropped, completed, rejected;
+    double total_service;    /* Server._total_service_time                        */
+    /* SINK / COUNTER */
+    int64_t received;
+    double sum, sumsq, mn, mx;
+    /* LB */
+    uint64_t rr_index;       /* RoundRobin._index                                 */
+    int64_t lb_received, lb_forwarded, lb_in_flight, lb_responses;
+    uint32_t lb_next_request_id;
+} oent;
+
+typedef struct orun {
+    const hs_model_desc *m;
+    const hs_run_params *p;
+    oent *ents;
+    oheap heap;
+    uint64_t counter;        /* active creation counter                           */
+    uint64_t seed; uint32_t rid;
+    int64_t now;
+    uint32_t status;
+    /* outputs of this replica */
+    hs_event_record *rec; uint32_t n_rec;
+    hs_sink_sample *smp; uint32_t n_smp;
+    double *svc; uint32_t n_svc;
+} orun;
+
+static void q_push(oent *s, const oreq *r)
+{
+    if (s->q_len == s->q_cap) {
+        size_t ncap = s->q_cap ? s->q_cap * 2 : 16;
+        oreq *nq = (oreq *)malloc(ncap * sizeof(oreq));
+        for (size_t i = 0; i < s->q_len; ++i) nq[i] = s->q[(s->q_head + i) % s->q_cap];
+        free(s->q); s->q = nq; s->q_cap = ncap; s->q_head = 0;
+    }
+    s->q[(s->q_head + s->q_len) % s->q_cap] = *r;
+    s->q_len++;
+}
+
+static oreq q_pop(oent *s)
+{
+    oreq r;
+    if (s->d.i1 == HS_Q_LIFO) {          /* LIFOQueue.pop: deque.pop() (right)   */
+        r = s->q[(s->q_head + s->q_len - 1) % s->q_cap];
+    } else {                              /* FIFOQueue.pop: deque.popleft()       */
+        r = s->q[s->q_head];
+        s->q_head = (s->q_head + 1) % s->q_cap;
+    }
+    s->q_len--;
+    return r;
+}
+
+static oev new_event(orun *R, int64_t time, int kind, int ent)   /* Event.__init__ */
+{
+    oev e; memset(&e, 0, sizeof e);
+    e.time = time; e.kind = kind; e.ent = ent;
+    e.idx = R->counter++;                 /* _next_sort_index(), event.py:62-67   */
+    e.key = -1; e.lb_hook = -1; e.poll_hook = -1;
+    return e;
+}
+
+static int request_kind_for(const orun *R, int ent)
+{
+    switch (R->ents[ent].d.kind) {
+    case HS_ENT_SERVER: return HS_EV_REQ_ENQUEUE;
+    case HS_ENT_SINK: return HS_EV_REQ_SINK;
+    case HS_ENT_COUNTER: return HS_EV_REQ_COUNTER;
+    case HS_ENT_LB: return HS_EV_REQ_LB;
+    default: return -1;
+    }
+}
+
+/* ArrivalTimeProvider.next_arrival_time, constant-rate fast path
+ * (arrival_time_provider.py:66-82). */
+static int64_t next_arrival(orun *R, int sid, oent *s)
+{
+    double target;
+    if (s->d.i0 == HS_ARR_POISSON) {
+        double u = hs_uniform(R->seed, R->rid, HS_STREAM_ARRIVAL | ((uint32_t)sid << 8), s->arr_draws++);
+        target = hs_exp1(u);              /* poisson_arrival.py:31                */
+    } else {
+        target = 1.0;                     /* constant_arrival.py:21-23            */
+    }
+    s->cur_ns = hs_next_arrival_ns(s->cur_ns, target, s->d.d0);
+    return s->cur_ns;
+}
+
+/* QueueDriver._handle_work_payload.schedule_poll (queue_driver.py:79-85). */
+static void run_poll_hook(orun *R, int server)
+{
+    oent *s = &R->ents[server];
+    if (s->active < s->d.i0) {            /* target.has_capacity()                */
+        oev p = new_event(R, R->now, HS_EV_POLL, server);
+        heap_push(&R->heap, &p);
+    }
+}
+
+/* Event._run_completion_hooks for a request whose non-generator handler just
+ * returned (event.py:277-283): only the LoadBalancer on_complete hook can be
+ * attached at that point (load_balancer.py:414-427). */
+static void run_request_hooks(orun *R, oev *e)
+{
+    if (e->lb_hook >= 0) {
+        oev r = new_event(R, R->now, HS_EV_LB_RESPONSE, e->lb_hook);
+        heap_push(&R->heap, &r);
+        e->lb_hook = -1;                  /* on_complete.clear()                  */
+    }
+}
+
+static void handle(orun *R, oev *e)
+{
+    oent *E = &R->ents[e->ent];
+    switch (e->kind) {
+    case HS_EV_SOURCE_TICK: {             /* Source.handle_event, source.py:142-180 */
+        int have_payload = 0; oev pay;
+        if (!(E->d.l0 >= 0 && R->now > E->d.l0)) {   /* stop_after, source.py:68 */
+            E->provider_count++;
+            pay = new_event(R, R->now, request_kind_for(R, E->d.target), E->d.target);
+            pay.created_at = R->now;
+            pay.req_id = (uint32_t)E->provider_count;
+            if (E->d.i1 > 0) {            /* routing key: client_id ~ Uniform{0..pop-1}   */
+                double u = hs_uniform(R->seed, R->rid, HS_STREAM_ROUTING | ((uint32_t)e->ent << 8), E->key_draws++);
+                pay.key = (int32_t)HS_D2LL(HS_MUL(u, (double)E->d.i1));
+            }
+            have_payload = 1;
+        }
+        E->generated_count++;
+        int64_t nt = next_arrival(R, e->ent, E);
+        oev tick = new_event(R, nt, HS_EV_SOURCE_TICK, e->ent);
+        if (have_payload) heap_push(&R->heap, &pay);
+        heap_push(&R->heap, &tick);
+        break;
+    }
+    case HS_EV_REQ_LB: {                  /* LoadBalancer._forward_request, :347-433 */
+        E->lb_received++;
+        int nb = E->d.i2;
+        if (nb <= 0) break;               /* no healthy backends -> rejected     */
+        int slot;
+        if (E->d.i0 == HS_LB_KEY_TABLE && e->key >= 0)
+            slot = R->m->key_table[e->key];                 /* ConsistentHash.select    */
+        else { slot = (int)(E->rr_index % (uint64_t)nb); E->rr_index++; } /* RoundRobin  */
+        int backend = R->m->backends[E->d.i1 + slot];
+        E->lb_next_request_id++;
+        E->lb_in_flight++;
+        E->lb_forwarded++;
+        oev f = new_event(R, R->now, request_kind_for(R, backend), backend);
+        f.created_at = e->created_at; f.req_id = e->req_id; f.key = e->key;
+        f.lb_hook = e->ent;
+        heap_push(&R->heap, &f);
+        run_request_hooks(R, e);          /* hooks of the original (none from a Source) */
+        break;
+    }
+    case HS_EV_REQ_ENQUEUE: {             /* Queue._handle_enqueue, queue.py:122-147 */
+        int was_empty = (E->q_len == 0);
+        int accepted = !(E->d.l0 >= 0 && (int64_t)E->q_len >= E->d.l0);  /* queue_policy.py:94-98 */
+        if (!accepted) {
+            E->dropped++;
+        } else {
+            oreq r; r.created_at = e->created_at; r.idx = e->idx; r.req_id = e->req_id; r.key = e->key;
+            q_push(E, &r);
+            E->accepted++;
+            if (was_empty) {
+                oev n = new_event(R, R->now, HS_EV_NOTIFY, e->ent);
+                heap_push(&R->heap, &n);
+            }
+        }
+        run_request_hooks(R, e);          /* _lb_response fires at ENQUEUE time  */
+        break;
+    }
+    case HS_EV_NOTIFY:                    /* QueueDriver._handle_notify, :92-99  */
+        if (E->active < E->d.i0) {
+            oev p = new_event(R, R->now, HS_EV_POLL, e->ent);
+            heap_push(&R->heap, &p);
+        }
+        break;
+    case HS_EV_POLL:                      /* Queue._handle_poll, queue.py:149-166 */
+        if (E->q_len > 0) {
+            oreq r = q_pop(E);
+            oev d = new_event(R, R->now, HS_EV_DELIVER, e->ent);
+            d.created_at = r.created_at; d.req_id = r.req_id; d.key = r.key;
+            d.payload_idx = r.idx;       /* QueueDeliverEvent.payload is the queued Event object */
+            heap_push(&R->heap, &d);
+        }
+        break;
+    case HS_EV_DELIVER: {                 /* _handle_work_payload, queue_driver.py:78-90 */
+        oev w; memset(&w, 0, sizeof w);
+        w.time = R->now; w.kind = HS_EV_REQ_WORKER; w.ent = e->ent;
+        w.idx = e->payload_idx;           /* the payload keeps its OLD _sort_index */
+        w.created_at = e->created_at; w.req_id = e->req_id; w.key = e->key;
+        w.lb_hook = -1; w.poll_hook = e->ent;
+        heap_push(&R->heap, &w);
+        break;
+    }
+    case HS_EV_REQ_WORKER: {              /* Server.handle_queued_event first step */
+        R->counter++;                     /* inline ProcessContinuation, event.py:314-325 */
+        if (E->active >= E->d.i0) {       /* acquire failed, server.py:223-234   */
+            E->rejected++;
+            R->status |= HS_ST_REJECT_PATH;
+            run_poll_hook(R, e->ent);     /* StopIteration -> hooks, event.py:522-533 */
+            break;
+        }
+        E->active++;
+        int64_t dur_ns;
+        if (E->d.i2 == HS_SVC_EXPONENTIAL) {
+            double u = hs_uniform(R->seed, R->rid, HS_STREAM_SERVICE | ((uint32_t)e->ent << 8), E->svc_draws++);
+            dur_ns = hs_exp_latency_ns(u, E->lambda);     /* exponential.py:41-45 */
+        } else {
+            dur_ns = hs_seconds_to_ns(E->d.d0);           /* constant.py:33-35    */
+        }
+        double service_time_s = hs_ns_to_seconds(dur_ns); /* server.py:246-247    */
+        if (R->svc && R->n_svc < R->p->service_cap) R->svc[R->n_svc] = service_time_s;
+        R->n_svc++;
+        oev c = new_event(R, hs_resume_ns(R->now, service_time_s), HS_EV_CONTINUATION, e->ent);
+        c.created_at = e->created_at; c.req_id = e->req_id; c.key = e->key;
+        c.poll_hook = e->poll_hook; c.svc_s = service_time_s;
+        heap_push(&R->heap, &c);
+        break;
+    }
+    case HS_EV_CONTINUATION: {            /* generator resumes, server.py:255-273 */
+        E->active = E->active > 0 ? E->active - 1 : 0;    /* FixedConcurrency.release */
+        E->completed++;
+        E->total_service += e->svc_s;
+        if (E->d.target >= 0) {           /* Entity.forward, entity.py:83-105     */
+            oev f = new_event(R, R->now, request_kind_for(R, E->d.target), E->d.target);
+            f.created_at = e->created_at; f.req_id = e->req_id; f.key = e->key;
+            heap_push(&R->heap, &f);
+        }
+        if (e->poll_hook >= 0) run_poll_hook(R, e->poll_hook);
+        break;
+    }
+    case HS_EV_REQ_SINK: {                /* Sink.handle_event, common.py:36-44   */
+        E->received++;
+        double lat = hs_ns_to_seconds(R->now - e->created_at);
+        E->sum += lat; E->sumsq += lat * lat;
+        if (lat < E->mn) E->mn = lat;
+        if (lat > E->mx) E->mx = lat;
+        if (R->smp && R->n_smp < R->p->sample_cap) {
+            R->smp[R->n_smp].completion_ns = R->now; R->smp[R->n_smp].latency_s = lat;
+        }
+        R->n_smp++;
+        run_request_hooks(R, e);
+        break;
+    }
+    case HS_EV_REQ_COUNTER:               /* Counter.handle_event, common.py:92-95 */
+        E->received++;
+        run_request_hooks(R, e);
+        break;
+    case HS_EV_LB_RESPONSE:               /* LoadBalancer._handle_response, :435-473 */
+        if (E->lb_in_flight > 0) E->lb_in_flight--;
+        E->lb_responses++;
+        break;
+    default: break;
+    }
+}
+
+static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t r,
+                        const hs_outputs *out)
+{
+    orun R; memset(&R, 0, sizeof R);
+    R.m = m; R.p = p;
+    uint32_t ne = m->n_entities;
+    uint32_t gidx = p->replica_index_base + r;
+    uint32_t cell = p->replicas_per_cell ? gidx / p->replicas_per_cell : 0;
+    if (m->n_cells) cell %= m->n_cells;
+    R.seed = p->seed + (uint64_t)gidx * p->seed_stride;
+    R.rid = p->rid_base + gidx * p->rid_stride;
+    R.ents = (oent *)calloc(ne, sizeof(oent));
+    for (uint32_t i = 0; i < ne; ++i) {
+        oent *E = &R.ents[i];
+        E->d = m->entities[i];
+        if (m->n_cells && m->cell_d0) E->d.d0 = m->cell_d0[(size_t)cell * ne + i];
+        if (m->n_cells && m->cell_i0) E->d.i0 = m->cell_i0[(size_t)cell * ne + i];
+        E->mn = INFINITY; E->mx = -INFINITY;
+        if (E->d.kind == HS_ENT_SERVER && E->d.i2 == HS_SVC_EXPONENTIAL) E->lambda = 1.0 / E->d.d0;
+    }
+    if (out->records) R.rec = out->records + (size_t)r * p->record_cap;
+    if (out->sink_samples) R.smp = out->sink_samples + (size_t)r * p->sample_cap;
+    if (out->service_samples) R.svc = out->service_samples + (size_t)r * p->service_cap;
+
+    /* Simulation.__init__: reset_event_counter(); source.start() for each source
+     * in order; the SourceEvent takes its index from the GLOBAL counter
+     * (simulation.py:77,145-154; source.py:120-140). */
+    R.counter = 0;
+    R.now = 0;
+    for (uint32_t i = 0; i < ne; ++i) {
+        oent *E = &R.ents[i];
+        if (E->d.kind != HS_ENT_SOURCE) continue;
+        E->cur_ns = 0;                    /* provider.current_time = start_time   */
+        int64_t first = next_arrival(&R, (int)i, E);
+        oev tick = new_event(&R, first, HS_EV_SOURCE_TICK, (int)i);
+        heap_push(&R.heap, &tick);
+    }
+    /* run(): _active_sim_context installs the per-heap counter, again from 0
+     * (event_heap.py:48, sim_future.py:64-73). */
+    R.counter = 0;
+
+    int64_t processed = 0;
+    uint64_t h = HS_HASH_INIT;
+    /* _execute_until, simulation.py:472: the test is on the LAST processed time. */
+    while (R.heap.n && R.now <= p->end_ns) {
+        oev e = heap_pop(&R.heap);
+        R.now = e.time;
+        uint64_t w1 = hs_record_word1(e.idx, (uint32_t)e.kind, (uint32_t)e.ent);
+        h = hs_hash_step(h, e.time, w1);
+        if (R.rec && processed < (int64_t)p->record_cap) {
+            hs_event_record *rc = &R.rec[processed];
+            rc->time_ns = e.time; rc->sort_index = (uint32_t)e.idx;
+            rc->kind = (uint8_t)e.kind; rc->pad = 0; rc->entity = (uint16_t)e.ent;
+        }
+        processed++;
+        handle(&R, &e);
+    }
+
+    if (out->summaries) {
+        hs_replica_summary *s = &out->summaries[r];
+        s->events_processed = processed; s->final_time_ns = R.now; s->order_hash = h;
+        s->next_sort_index = R.counter; s->heap_left = (int32_t)R.heap.n; s->status = R.status;
+    }
+    if (out->entity_stats) {
+        for (uint32_t i = 0; i < ne; ++i) {
+            hs_entity_stats *st = &out->entity_stats[(size_t)r * ne + i];
+            oent *E = &R.ents[i];
+            memset(st, 0, sizeof *st);
+            switch (E->d.kind) {
+            case HS_ENT_SOURCE: st->c0 = E->generated_count; st->c1 = E->provider_count; break;
+            case HS_ENT_SERVER:
+                st->c0 = E->accepted; st->c1 = E->dropped; st->c2 = E->completed; st->c3 = E->rejected;
+                st->f0 = E->total_service; break;
+            case HS_ENT_SINK:
+                st->c0 = E->received; st->f0 = E->sum; st->f1 = E->sumsq; st->f2 = E->mn; st->f3 = E->mx; break;
+            case HS_ENT_COUNTER: st->c0 = E->received; break;
+            case HS_ENT_LB:
+                st->c0 = E->lb_received; st->c1 = E->lb_forwarded; st->c2 = E->lb_in_flight; st->c3 = E->lb_responses; break;
+            }
+        }
+    }
+    for (uint32_t i = 0; i < ne; ++i) free(R.ents[i].q);
+    free(R.ents); free(R.heap.a);
+}
+
+/* ---- exported --------------------------------------------------------- */
+
+int hs_oracle_run(const hs_model_desc *m, const hs_run_params *p, const hs_outputs *out)
+{
+    if (!m || !p || !out || m->abi_version != HS_ABI_VERSION) return HS_ERR_INVALID;
+    for (uint32_t r = 0; r < p->n_replicas; ++r) run_replica(m, p, r, out);
+    return HS_OK;
+}
+
+/* Run replicas [r0, r1) only: lets Python spread a batch over host processes/threads. */
+int hs_oracle_run_range(const hs_model_desc *m, const hs_run_params *p, const hs_outputs *out,
+                        uint32_t r0, uint32_t r1)
+{
+    if (!m || !p || !out || m->abi_version != HS_ABI_VERSION) return HS_ERR_INVALID;
+    for (uint32_t r = r0; r < r1 && r < p->n_replicas; ++r) run_replica(m, p, r, out);
+    return HS_OK;
+}
+
+/* CPU twins of the shared sampler, called by the Philox plug-ins that
+ * tests/golden/gen_golden.py injects into the unmodified reference. */
+double hs_cpu_uniform(uint64_t seed, uint32_t replica, uint32_t sid, uint64_t draw)
+{ return hs_uniform(seed, replica, sid, draw); }
+double hs_cpu_log(double x) { return hs_log(x); }
+double hs_cpu_exp1(double u) { return hs_exp1(u); }
+int64_t hs_cpu_seconds_to_ns(double s) { return hs_seconds_to_ns(s); }
+double hs_cpu_ns_to_seconds(int64_t ns) { return hs_ns_to_seconds(ns); }
+int64_t hs_cpu_next_arrival_ns(int64_t cur, double target, double rate) { return hs_next_arrival_ns(cur, target, rate); }
+int64_t hs_cpu_exp_latency_ns(double u, double lambda) { return hs_exp_latency_ns(u, lambda); }
+uint64_t hs_cpu_hash_step(uint64_t h, int64_t t, uint64_t idx, uint32_t kind, uint32_t ent)
+{ return hs_hash_step(h, t, hs_record_word1(idx, kind, ent)); }
+void hs_cpu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4)
+{ hs_u32x4 r = hs_philox4x32_10(c0, c1, c2, c3, k0, k1); out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w; }

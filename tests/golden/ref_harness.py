@@ -1,0 +1,298 @@
+"""Drive the UNMODIFIED reference (imported from /root/reference) on a FlatModel.
+
+Only tests/golden/gen_golden.py (and ad-hoc checks in the build container) use
+this module: /root/reference does not exist on the GPU box.  It
+
+  * rebuilds the reference object graph (Source / Server / Sink / Counter /
+    LoadBalancer) that a FlatModel describes,
+  * injects the shared Philox sampler through the reference's own plug-in points
+    (ArrivalTimeProvider._get_target_integral_value,
+    LatencyDistribution.get_latency, SimpleEventProvider(context_fn=)),
+    SURVEY.md section 8(c),
+  * taps EventHeap.pop to capture the processed-event
+    sequence as (time_ns, sort_index, kind, entity) records,
+  * returns the same arrays the oracle / the CUDA engine produce.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("HS_REFERENCE_ROOT", "/root/reference")
+
+
+def _import_reference():
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import happysimulator  # noqa: F401
+    return happysimulator
+
+
+def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, stock_rng=False,
+                  max_records=None):
+    """Run the reference on ``model`` (a happysim_b200.FlatModel); replica word ``rid``.
+
+    stock_rng=True leaves the reference's own MT19937 streams in place (seeded
+    random.seed(seed); np.random.seed(seed)) instead of the Philox plug-ins.
+    """
+    _import_reference()
+    import oracle_lib as O
+    from happysim_b200 import _abi as A
+
+    from happysimulator.components.common import Counter, Sink
+    from happysimulator.components.load_balancer.load_balancer import LoadBalancer
+    from happysimulator.components.load_balancer.strategies import ConsistentHash, RoundRobin
+    from happysimulator.components.queue_policy import FIFOQueue, LIFOQueue
+    from happysimulator.components.queued_resource import _QueuedResourceWorkerAdapter
+    from happysimulator.components.server.server import Server
+    from happysimulator.core.event import ProcessContinuation
+    from happysimulator.core.simulation import Simulation
+    from happysimulator.core.temporal import Duration, Instant
+    from happysimulator.distributions.constant import ConstantLatency
+    from happysimulator.distributions.exponential import ExponentialLatency
+    from happysimulator.distributions.latency_distribution import LatencyDistribution
+    from happysimulator.load.arrival_time_provider import ArrivalTimeProvider
+    from happysimulator.load.profile import ConstantRateProfile
+    from happysimulator.load.providers.constant_arrival import ConstantArrivalTimeProvider
+    from happysimulator.load.providers.poisson_arrival import PoissonArrivalTimeProvider
+    from happysimulator.load.source import SimpleEventProvider, Source
+    from happysimulator.load.source_event import SourceEvent
+
+    L = O.lib()
+    ents = model.entities
+    n = model.n_entities
+    names = names or model.names or [f"e{i}" for i in range(n)]
+
+    class PhiloxPoissonArrival(ArrivalTimeProvider):
+        def __init__(self, profile, start_time, sid):
+            super().__init__(profile, start_time)
+            self._sid, self._n = sid, 0
+
+        def _get_target_integral_value(self):
+            u = L.hs_cpu_uniform(seed, rid, A.HS_STREAM_ARRIVAL | (self._sid << 8), self._n)
+            self._n += 1
+            return L.hs_cpu_exp1(u)
+
+    class PhiloxExponentialLatency(LatencyDistribution):
+        def __init__(self, mean, sid):
+            super().__init__(mean)
+            self._lambda = 1 / self._mean_latency
+            self._sid, self._n = sid, 0
+
+        def get_latency(self, current_time):
+            u = L.hs_cpu_uniform(seed, rid, A.HS_STREAM_SERVICE | (self._sid << 8), self._n)
+            self._n += 1
+            return Duration.from_seconds(L.hs_cpu_exp1(u) / self._lambda)
+
+    objs = [None] * n
+    # leaves first: sinks / counters, then servers, then LBs, then sources
+    for i in range(n):
+        k = int(ents["kind"][i])
+        if k == A.HS_ENT_SINK:
+            objs[i] = Sink(names[i])
+        elif k == A.HS_ENT_COUNTER:
+            objs[i] = Counter(names[i])
+    for i in range(n):
+        if int(ents["kind"][i]) != A.HS_ENT_SERVER:
+            continue
+        e = ents[i]
+        mean = float(e["d0"])
+        if int(e["i2"]) == A.HS_SVC_EXPONENTIAL:
+            dist = ExponentialLatency(mean) if stock_rng else PhiloxExponentialLatency(mean, i)
+        else:
+            dist = ConstantLatency(mean)
+        cap = int(e["l0"])
+        pol_cls = LIFOQueue if int(e["i1"]) == A.HS_Q_LIFO else FIFOQueue
+        policy = pol_cls(capacity=cap) if cap >= 0 else pol_cls()
+        objs[i] = Server(names[i], concurrency=int(e["i0"]), service_time=dist, queue_policy=policy)
+    for i in range(n):          # server downstreams (may point at servers: tandem queues)
+        if int(ents["kind"][i]) == A.HS_ENT_SERVER and int(ents["target"][i]) >= 0:
+            objs[i].downstream = objs[int(ents["target"][i])]
+    for i in range(n):
+        if int(ents["kind"][i]) != A.HS_ENT_LB:
+            continue
+        e = ents[i]
+        be = [objs[int(b)] for b in model.backends[int(e["i1"]): int(e["i1"]) + int(e["i2"])]]
+        if int(e["i0"]) == A.HS_LB_KEY_TABLE:
+            strat = ConsistentHash(virtual_nodes=chash_vnodes or 100)
+        else:
+            strat = RoundRobin()
+        objs[i] = LoadBalancer(names[i], backends=be, strategy=strat)
+    sources = []
+    for i in range(n):
+        if int(ents["kind"][i]) != A.HS_ENT_SOURCE:
+            continue
+        e = ents[i]
+        target = objs[int(e["target"])]
+        stop = Instant(int(e["l0"])) if int(e["l0"]) >= 0 else None
+        pop = int(e["i1"])
+        ctx_fn = None
+        if pop > 0:
+            def ctx_fn(time, count, _sid=i, _pop=pop):
+                u = L.hs_cpu_uniform(seed, rid, A.HS_STREAM_ROUTING | (_sid << 8), count - 1)
+                return {"created_at": time, "request_id": count, "metadata": {"client_id": int(u * _pop)}}
+        prov = SimpleEventProvider(target, "Request", stop, ctx_fn)
+        profile = ConstantRateProfile(rate=float(e["d0"]))
+        if int(e["i0"]) == A.HS_ARR_POISSON:
+            atp = (PoissonArrivalTimeProvider(profile, Instant.Epoch) if stock_rng
+                   else PhiloxPoissonArrival(profile, Instant.Epoch, i))
+        else:
+            atp = ConstantArrivalTimeProvider(profile, Instant.Epoch)
+        objs[i] = Source(names[i], prov, atp)
+        sources.append(objs[i])
+
+    if stock_rng:
+        import random
+        random.seed(seed)
+        np.random.seed(seed)
+
+    entities = [o for i, o in enumerate(objs) if int(ents["kind"][i]) != A.HS_ENT_SOURCE]
+    sim = Simulation(end_time=Instant(int(end_ns)), sources=sources, entities=entities)
+
+    # ---- object -> entity id, for the pop tap
+    oid = {}
+    for i, o in enumerate(objs):
+        oid[id(o)] = i
+        if int(ents["kind"][i]) == A.HS_ENT_SERVER:
+            oid[id(o.queue)] = i
+            oid[id(o.driver)] = i
+            oid[id(o.worker)] = i
+
+    recs = []
+    heap = sim._event_heap
+    orig_pop = heap.pop
+
+    def classify(ev):
+        t = ev.target
+        if isinstance(ev, SourceEvent):
+            return A.HS_EV_SOURCE_TICK
+        if isinstance(ev, ProcessContinuation):
+            return A.HS_EV_CONTINUATION
+        et = ev.event_type
+        if et == "QUEUE_NOTIFY":
+            return A.HS_EV_NOTIFY
+        if et == "QUEUE_POLL":
+            return A.HS_EV_POLL
+        if et == "QUEUE_DELIVER":
+            return A.HS_EV_DELIVER
+        if et == "_lb_response":
+            return A.HS_EV_LB_RESPONSE
+        if isinstance(t, _QueuedResourceWorkerAdapter):
+            return A.HS_EV_REQ_WORKER
+        if isinstance(t, Server):
+            return A.HS_EV_REQ_ENQUEUE
+        if isinstance(t, Sink):
+            return A.HS_EV_REQ_SINK
+        if isinstance(t, Counter):
+            return A.HS_EV_REQ_COUNTER
+        if isinstance(t, LoadBalancer):
+            return A.HS_EV_REQ_LB
+        raise AssertionError(f"unclassified event {ev!r}")
+
+    def tap():
+        ev = orig_pop()
+        recs.append((ev.time.nanoseconds, ev._sort_index, classify(ev), oid[id(ev.target)]))
+        return ev
+
+    heap.pop = tap
+    summary = sim.run()
+
+    rec = np.zeros(len(recs), A.RECORD_DTYPE)
+    if recs:
+        arr = np.array(recs, dtype=np.int64)
+        rec["time_ns"], rec["sort_index"], rec["kind"], rec["entity"] = arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3]
+    h = 0xcbf29ce484222325
+    for t, idx, kind, ent in recs:
+        h = L.hs_cpu_hash_step(h, t, idx, kind, ent)
+
+    summ = np.zeros(1, A.SUMMARY_DTYPE)
+    summ["events_processed"] = summary.total_events_processed
+    summ["final_time_ns"] = sim._current_time.nanoseconds
+    summ["order_hash"] = h
+    summ["heap_left"] = heap.size()
+    stats = np.zeros(n, A.STATS_DTYPE)
+    sink_samples = []
+    per_server_service = {}
+    for i, o in enumerate(objs):
+        k = int(ents["kind"][i])
+        if k == A.HS_ENT_SOURCE:
+            stats[i]["c0"], stats[i]["c1"] = o.generated_count, o._event_provider._generated
+        elif k == A.HS_ENT_SERVER:
+            st = o.stats
+            stats[i]["c0"], stats[i]["c1"] = o.stats_accepted, o.stats_dropped
+            stats[i]["c2"], stats[i]["c3"], stats[i]["f0"] = st.requests_completed, st.requests_rejected, st.total_service_time
+            per_server_service[i] = list(o._service_times)
+        elif k == A.HS_ENT_SINK:
+            stats[i]["c0"] = o.events_received
+            s = 0.0
+            s2 = 0.0
+            for v in o.latencies_s:
+                s += v
+                s2 += v * v
+            stats[i]["f0"], stats[i]["f1"] = s, s2
+            stats[i]["f2"] = min(o.latencies_s) if o.latencies_s else np.inf
+            stats[i]["f3"] = max(o.latencies_s) if o.latencies_s else -np.inf
+            sink_samples.append((i, [t.nanoseconds for t in o.completion_times], list(o.latencies_s)))
+        elif k == A.HS_ENT_COUNTER:
+            stats[i]["c0"] = o.total
+        elif k == A.HS_ENT_LB:
+            s = o.stats
+            stats[i]["c0"], stats[i]["c1"], stats[i]["c2"] = s.requests_received, s.requests_forwarded, len(o._in_flight)
+            stats[i]["c3"] = sum(1 for r in recs if r[2] == A.HS_EV_LB_RESPONSE and r[3] == i)
+
+    # all sinks' samples merged in arrival order (= order of REQ_SINK records)
+    cursors = {i: 0 for i, _, _ in sink_samples}
+    by_id = {i: (ct, ls) for i, ct, ls in sink_samples}
+    merged = []
+    svc_cursor = {i: 0 for i in per_server_service}
+    svc_merged = []
+    for t, idx, kind, ent in recs:
+        if kind == A.HS_EV_REQ_SINK:
+            c = cursors[ent]
+            merged.append((by_id[ent][0][c], by_id[ent][1][c]))
+            cursors[ent] = c + 1
+        elif kind == A.HS_EV_REQ_WORKER:
+            c = svc_cursor[ent]
+            if c < len(per_server_service[ent]):
+                svc_merged.append(per_server_service[ent][c])
+                svc_cursor[ent] = c + 1
+    smp = np.zeros(len(merged), A.SAMPLE_DTYPE)
+    if merged:
+        smp["completion_ns"] = [m[0] for m in merged]
+        smp["latency_s"] = [m[1] for m in merged]
+    out = {
+        "summaries": summ, "entity_stats": stats[None, :], "records": rec, "sink_samples": smp,
+        "service_samples": np.array(svc_merged, dtype=np.float64), "objects": objs, "sim": sim,
+        "summary": summary,
+    }
+    if max_records is not None:
+        out["records"] = rec[:max_records]
+    return out
+
+
+def ring_table_from_reference(names, vnodes, population):
+    """key -> backend slot by asking the reference's ConsistentHash itself."""
+    _import_reference()
+    from happysimulator.components.load_balancer.strategies import ConsistentHash
+    from happysimulator.core.entity import Entity
+
+    class _B(Entity):
+        def handle_event(self, event):
+            return None
+
+    bes = [_B(nm) for nm in names]
+    ch = ConsistentHash(virtual_nodes=vnodes)
+    for b in bes:
+        ch.add_backend(b)
+    ring = sorted(ch._ring)
+    import bisect
+    hashes = [h for h, _ in ring]
+    slot = {nm: i for i, nm in enumerate(names)}
+    tab = np.zeros(population, np.int32)
+    for k in range(population):
+        hv = ch._hash(str(k))
+        j = bisect.bisect_left(hashes, hv)
+        tab[k] = slot[ring[j][1]] if j < len(ring) else slot[ring[0][1]]
+    return tab

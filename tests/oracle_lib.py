@@ -1,0 +1,88 @@
+"""ctypes binding of the CPU oracle (oracle/libhs_oracle.so).  Test infrastructure."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import happysim_b200
+from happysim_b200 import _abi as A
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "libhs_oracle.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        L = C.CDLL(_SO)
+        L.hs_oracle_run.argtypes = [C.POINTER(A.ModelDesc), C.POINTER(A.RunParams), C.POINTER(A.Outputs)]
+        L.hs_oracle_run.restype = C.c_int
+        L.hs_oracle_run_range.argtypes = [C.POINTER(A.ModelDesc), C.POINTER(A.RunParams), C.POINTER(A.Outputs),
+                                          C.c_uint32, C.c_uint32]
+        L.hs_oracle_run_range.restype = C.c_int
+        L.hs_cpu_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
+        L.hs_cpu_uniform.restype = C.c_double
+        for n in ("hs_cpu_log", "hs_cpu_exp1"):
+            getattr(L, n).argtypes = [C.c_double]; getattr(L, n).restype = C.c_double
+        L.hs_cpu_seconds_to_ns.argtypes = [C.c_double]; L.hs_cpu_seconds_to_ns.restype = C.c_int64
+        L.hs_cpu_ns_to_seconds.argtypes = [C.c_int64]; L.hs_cpu_ns_to_seconds.restype = C.c_double
+        L.hs_cpu_next_arrival_ns.argtypes = [C.c_int64, C.c_double, C.c_double]
+        L.hs_cpu_next_arrival_ns.restype = C.c_int64
+        L.hs_cpu_exp_latency_ns.argtypes = [C.c_double, C.c_double]; L.hs_cpu_exp_latency_ns.restype = C.c_int64
+        L.hs_cpu_hash_step.argtypes = [C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.hs_cpu_hash_step.restype = C.c_uint64
+        L.hs_cpu_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
+        L.hs_cpu_philox.restype = None
+        _lib = L
+    return _lib
+
+
+def make_params(*, seed=1234, end_ns, n_replicas=1, seed_stride=0, rid_base=0, rid_stride=1,
+                replica_index_base=0, replicas_per_cell=1, record_cap=0, sample_cap=0, service_cap=0,
+                queue_ring=0, engine=0) -> A.RunParams:
+    p = A.RunParams()
+    p.seed, p.seed_stride, p.rid_base, p.rid_stride = seed, seed_stride, rid_base, rid_stride
+    p.end_ns = int(end_ns)
+    p.n_replicas, p.replica_index_base, p.replicas_per_cell = n_replicas, replica_index_base, max(1, replicas_per_cell)
+    p.record_cap, p.sample_cap, p.service_cap = record_cap, sample_cap, service_cap
+    p.queue_ring, p.engine = queue_ring, engine
+    return p
+
+
+def alloc_outputs(n_entities: int, p: A.RunParams):
+    """Host buffers (numpy) + the hs_outputs struct pointing at them."""
+    n = p.n_replicas
+    bufs = {
+        "summaries": np.zeros(n, A.SUMMARY_DTYPE),
+        "entity_stats": np.zeros((n, n_entities), A.STATS_DTYPE),
+        "records": np.zeros((n, p.record_cap), A.RECORD_DTYPE) if p.record_cap else None,
+        "sink_samples": np.zeros((n, p.sample_cap), A.SAMPLE_DTYPE) if p.sample_cap else None,
+        "service_samples": np.zeros((n, p.service_cap), np.float64) if p.service_cap else None,
+    }
+    o = A.Outputs()
+    o.summaries = bufs["summaries"].ctypes.data_as(C.POINTER(A.ReplicaSummary))
+    o.entity_stats = bufs["entity_stats"].ctypes.data_as(C.POINTER(A.EntityStats))
+    if p.record_cap:
+        o.records = bufs["records"].ctypes.data_as(C.POINTER(A.EventRecord))
+    if p.sample_cap:
+        o.sink_samples = bufs["sink_samples"].ctypes.data_as(C.POINTER(A.SinkSample))
+    if p.service_cap:
+        o.service_samples = bufs["service_samples"].ctypes.data_as(C.POINTER(C.c_double))
+    return bufs, o
+
+
+def oracle_run(model: happysim_b200.FlatModel, p: A.RunParams, r0=None, r1=None):
+    d = model.desc()
+    bufs, o = alloc_outputs(model.n_entities, p)
+    if r0 is None:
+        rc = lib().hs_oracle_run(C.byref(d), C.byref(p), C.byref(o))
+    else:
+        rc = lib().hs_oracle_run_range(C.byref(d), C.byref(p), C.byref(o), r0, r1)
+    assert rc == 0, rc
+    return bufs

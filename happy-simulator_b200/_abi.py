@@ -48,7 +48,8 @@ class RunParams(C.Structure):
                 ("n_replicas", C.c_uint32), ("replica_index_base", C.c_uint32),
                 ("replicas_per_cell", C.c_uint32), ("record_cap", C.c_uint32),
                 ("sample_cap", C.c_uint32), ("service_cap", C.c_uint32),
-                ("queue_ring", C.c_uint32), ("engine", C.c_uint32)]
+                ("queue_ring", C.c_uint32), ("engine", C.c_uint32),
+                ("window_end_ns", C.c_int64), ("resume", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class ReplicaSummary(C.Structure):
@@ -87,7 +88,8 @@ assert C.sizeof(ReplicaSummary) == 40
 assert C.sizeof(EntityStats) == 64
 assert C.sizeof(EventRecord) == 16
 assert C.sizeof(SinkSample) == 16
-assert C.sizeof(RunParams) == 64
+assert C.sizeof(RunParams) == 80
+HS_RUN_ORDER_HASH = 1
 
 # numpy views of the same layouts (host buffers are numpy structured arrays)
 import numpy as _np

@@ -1,0 +1,433 @@
+/* hs_engine.cu -- C-ABI of the B200 discrete-event engine (include/hs_b200.h).
+ *
+ * Host side of the boundary: validates and uploads the flat model, owns the
+ * device buffers (replica state, queue rings, per-replica outputs), picks the
+ * kernel (lane engine for the single-server topology, warp engine otherwise),
+ * launches on the engine's CUDA stream and times the launches with CUDA events
+ * recorded on that same stream.  No torch types, no CPU fallback.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hs_b200.h"
+#include "hs_lane_engine.cuh"
+#include "hs_warp_engine.cuh"
+#include "hs_totals.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(HS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),    \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+struct dev_buf {
+    void *p = nullptr; size_t n = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= n && p) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        if (bytes == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(HS_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        n = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct hs_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    int sm_count = 148;
+
+    /* model (host copy + device copy) */
+    bool have_model = false;
+    std::vector<hs_entity_desc> ents;
+    std::vector<int32_t> backends, key_table;
+    std::vector<double> cell_d0; std::vector<int32_t> cell_i0;
+    uint32_t n_cells = 0;
+    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0;
+    bool lane_ok = false;
+    hs_lane_model lane_model;
+
+    /* last run */
+    bool have_run = false;
+    hs_run_params last;
+    int last_engine = 0;
+    dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals;
+};
+
+/* ---- validation ----------------------------------------------------------- */
+
+static int validate_model(const hs_model_desc *m)
+{
+    if (!m) return fail(HS_ERR_INVALID, "model is NULL");
+    if (m->abi_version != HS_ABI_VERSION) return fail(HS_ERR_INVALID, "abi_version %u != %u", m->abi_version, HS_ABI_VERSION);
+    if (m->n_entities == 0 || m->n_entities > 65535 || !m->entities) return fail(HS_ERR_INVALID, "n_entities must be 1..65535");
+    uint32_t n = m->n_entities;
+    int n_src = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const hs_entity_desc &e = m->entities[i];
+        switch (e.kind) {
+        case HS_ENT_SOURCE:
+            n_src++;
+            if (e.target < 0 || (uint32_t)e.target >= n) return fail(HS_ERR_INVALID, "entity %u: source target %d out of range", i, e.target);
+            if (m->entities[e.target].kind == HS_ENT_SOURCE) return fail(HS_ERR_INVALID, "entity %u: source targets a source", i);
+            if (!(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: source rate must be > 0 (arrival_time_provider.py:75)", i);
+            if (e.i0 != HS_ARR_CONSTANT && e.i0 != HS_ARR_POISSON) return fail(HS_ERR_INVALID, "entity %u: bad arrival kind", i);
+            if (e.i1 < 0 || (e.i1 > 0 && (uint32_t)e.i1 != m->key_population)) return fail(HS_ERR_INVALID, "entity %u: key population %d != key_table length %u", i, e.i1, m->key_population);
+            break;
+        case HS_ENT_SERVER:
+            if (e.target >= (int32_t)n) return fail(HS_ERR_INVALID, "entity %u: downstream out of range", i);
+            if (e.target >= 0 && m->entities[e.target].kind == HS_ENT_SOURCE) return fail(HS_ERR_INVALID, "entity %u: downstream is a source", i);
+            if (e.i0 < 1) return fail(HS_ERR_INVALID, "entity %u: max_concurrent must be >= 1, got %d (concurrency.py:86)", i, e.i0);
+            if (e.i1 != HS_Q_FIFO && e.i1 != HS_Q_LIFO) return fail(HS_ERR_INVALID, "entity %u: bad queue policy", i);
+            if (e.i2 != HS_SVC_CONSTANT && e.i2 != HS_SVC_EXPONENTIAL) return fail(HS_ERR_INVALID, "entity %u: bad service kind", i);
+            if (e.i2 == HS_SVC_EXPONENTIAL && !(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: exponential mean must be > 0", i);
+            if (e.d0 < 0.0) return fail(HS_ERR_INVALID, "entity %u: negative service time", i);
+            break;
+        case HS_ENT_SINK: case HS_ENT_COUNTER: break;
+        case HS_ENT_LB:
+            if (e.i0 != HS_LB_ROUND_ROBIN && e.i0 != HS_LB_KEY_TABLE) return fail(HS_ERR_INVALID, "entity %u: bad LB strategy", i);
+            if (e.i2 < 0 || e.i1 < 0 || (uint32_t)(e.i1 + e.i2) > m->n_backends) return fail(HS_ERR_INVALID, "entity %u: backend list out of range", i);
+            if (e.i2 > 0 && !m->backends) return fail(HS_ERR_INVALID, "backends is NULL");
+            for (int b = 0; b < e.i2; ++b) {
+                int be = m->backends[e.i1 + b];
+                if (be < 0 || (uint32_t)be >= n) return fail(HS_ERR_INVALID, "entity %u: backend %d out of range", i, be);
+                int bk = m->entities[be].kind;
+                if (bk != HS_ENT_SERVER && bk != HS_ENT_SINK && bk != HS_ENT_COUNTER) return fail(HS_ERR_INVALID, "entity %u: backend %d must be a Server, Sink or Counter", i, be);
+            }
+            if (e.i0 == HS_LB_KEY_TABLE) {
+                if (!m->key_table || m->key_population == 0) return fail(HS_ERR_INVALID, "entity %u: key table missing", i);
+                for (uint32_t k = 0; k < m->key_population; ++k)
+                    if (m->key_table[k] < 0 || m->key_table[k] >= e.i2) return fail(HS_ERR_INVALID, "key_table[%u] = %d out of range", k, m->key_table[k]);
+            }
+            break;
+        default: return fail(HS_ERR_INVALID, "entity %u: unknown kind %d", i, e.kind);
+        }
+    }
+    if (m->n_cells && (!m->cell_d0 || !m->cell_i0)) return fail(HS_ERR_INVALID, "cells without tables");
+    for (uint32_t c = 0; c < m->n_cells; ++c)
+        for (uint32_t i = 0; i < n; ++i) {
+            const hs_entity_desc &e = m->entities[i];
+            double d = m->cell_d0[(size_t)c * n + i]; int32_t v = m->cell_i0[(size_t)c * n + i];
+            if (e.kind == HS_ENT_SOURCE && !(d > 0.0)) return fail(HS_ERR_INVALID, "cell %u: source rate must be > 0", c);
+            if (e.kind == HS_ENT_SERVER && (v < 1 || d < 0.0)) return fail(HS_ERR_INVALID, "cell %u: bad server override", c);
+            if (e.kind != HS_ENT_SERVER && v != e.i0) return fail(HS_ERR_INVALID, "cell %u: i0 override only applies to servers", c);
+        }
+    return HS_OK;
+}
+
+/* Lane engine eligibility: exactly Source -> Server(c=1) -> Sink|Counter|none. */
+static bool classify_lane(hs_engine *E)
+{
+    const auto &en = E->ents;
+    size_t n = en.size();
+    if (n < 2 || n > 3) return false;
+    int src = -1, srv = -1, dst = -1;
+    for (size_t i = 0; i < n; ++i) {
+        if (en[i].kind == HS_ENT_SOURCE) { if (src >= 0) return false; src = (int)i; }
+        else if (en[i].kind == HS_ENT_SERVER) { if (srv >= 0) return false; srv = (int)i; }
+        else if (en[i].kind == HS_ENT_SINK || en[i].kind == HS_ENT_COUNTER) { if (dst >= 0) return false; dst = (int)i; }
+        else return false;
+    }
+    if (src < 0 || srv < 0) return false;
+    if (en[src].target != srv || en[src].i1 != 0) return false;
+    if (en[srv].i0 != 1) return false;
+    if (en[srv].target != dst) { if (!(en[srv].target < 0 && dst < 0)) return false; }
+    for (uint32_t c = 0; c < E->n_cells; ++c) if (E->cell_i0[(size_t)c * n + srv] != 1) return false;
+    hs_lane_model &L = E->lane_model;
+    memset(&L, 0, sizeof L);
+    L.src_id = src; L.srv_id = srv; L.dst_id = en[srv].target;
+    L.dst_kind = L.dst_id >= 0 ? en[L.dst_id].kind : 0;
+    L.arr_kind = en[src].i0; L.svc_kind = en[srv].i2; L.policy = en[srv].i1; L.n_entities = (int32_t)n;
+    L.capacity = en[srv].l0; L.stop_after = en[src].l0;
+    L.rate = en[src].d0; L.mean = en[srv].d0;
+    L.n_cells = E->n_cells;
+    L.cell_d0 = (const double *)E->d_cell_d0.p;
+    return true;
+}
+
+/* ---- entry points ------------------------------------------------------- */
+
+extern "C" {
+
+uint32_t hs_version(void) { return HS_ABI_VERSION; }
+
+int hs_last_error(char *buf, int len)
+{
+    int n = (int)strlen(g_err);
+    if (buf && len > 0) { strncpy(buf, g_err, (size_t)len - 1); buf[len - 1] = 0; }
+    return n;
+}
+
+int hs_model_validate(const hs_model_desc *model) { return validate_model(model); }
+
+int hs_engine_create(int device, void *stream, hs_engine **out)
+{
+    if (!out) return fail(HS_ERR_INVALID, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(HS_ERR_NO_DEVICE, "no CUDA device (%s); the engine has no CPU path", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(HS_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    hs_engine *E = new hs_engine();
+    E->device = device;
+    if (stream) { E->stream = (cudaStream_t)stream; E->own_stream = false; }
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking)); E->own_stream = true; }
+    CUDA_TRY(cudaEventCreate(&E->ev0));
+    CUDA_TRY(cudaEventCreate(&E->ev1));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    E->sm_count = prop.multiProcessorCount;
+    *out = E;
+    return HS_OK;
+}
+
+int hs_engine_destroy(hs_engine *E)
+{
+    if (!E) return HS_OK;
+    cudaSetDevice(E->device);
+    cudaStreamSynchronize(E->stream);
+    dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
+                       &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals};
+    for (dev_buf *b : bufs) b->release();
+    if (E->ev0) cudaEventDestroy(E->ev0);
+    if (E->ev1) cudaEventDestroy(E->ev1);
+    if (E->own_stream && E->stream) cudaStreamDestroy(E->stream);
+    delete E;
+    return HS_OK;
+}
+
+int hs_model_upload(hs_engine *E, const hs_model_desc *m)
+{
+    if (!E) return fail(HS_ERR_INVALID, "engine is NULL");
+    int rc = validate_model(m);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(E->device));
+    uint32_t n = m->n_entities;
+    E->ents.assign(m->entities, m->entities + n);
+    E->backends.assign(m->backends, m->backends + (m->backends ? m->n_backends : 0));
+    E->key_table.assign(m->key_table, m->key_table + (m->key_table ? m->key_population : 0));
+    E->n_cells = m->n_cells;
+    E->cell_d0.clear(); E->cell_i0.clear();
+    if (m->n_cells) {
+        E->cell_d0.assign(m->cell_d0, m->cell_d0 + (size_t)m->n_cells * n);
+        E->cell_i0.assign(m->cell_i0, m->cell_i0 + (size_t)m->n_cells * n);
+    }
+    auto up = [&](dev_buf &b, const void *src, size_t bytes) -> int {
+        int r = b.ensure(bytes ? bytes : 16);
+        if (r) return r;
+        if (bytes) {
+            cudaError_t e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, E->stream);
+            if (e != cudaSuccess) return fail(HS_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e));
+        }
+        return 0;
+    };
+    if ((rc = up(E->d_ents, E->ents.data(), n * sizeof(hs_entity_desc)))) return rc;
+    if ((rc = up(E->d_backends, E->backends.data(), E->backends.size() * 4))) return rc;
+    if ((rc = up(E->d_key_table, E->key_table.data(), E->key_table.size() * 4))) return rc;
+    if ((rc = up(E->d_cell_d0, E->cell_d0.data(), E->cell_d0.size() * 8))) return rc;
+    if ((rc = up(E->d_cell_i0, E->cell_i0.data(), E->cell_i0.size() * 4))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(E->stream));   /* host vectors may be reused by the caller's next upload */
+    E->lane_ok = classify_lane(E);
+    E->have_model = true;
+    E->have_run = false;
+    return HS_OK;
+}
+
+static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+int hs_run(hs_engine *E, const hs_run_params *p)
+{
+    if (!E || !p) return fail(HS_ERR_INVALID, "NULL argument");
+    if (!E->have_model) return fail(HS_ERR_STATE, "hs_run before hs_model_upload");
+    if (p->n_replicas == 0) return fail(HS_ERR_INVALID, "n_replicas must be > 0");
+    if (p->end_ns < 0) return fail(HS_ERR_INVALID, "end_ns must be >= 0 (an explicit end_time is required)");
+    if (p->replicas_per_cell == 0) return fail(HS_ERR_INVALID, "replicas_per_cell must be >= 1");
+    CUDA_TRY(cudaSetDevice(E->device));
+
+    int engine = (int)p->engine;
+    if (engine == 0) engine = E->lane_ok ? 2 : 1;
+    if (engine == 2 && !E->lane_ok) return fail(HS_ERR_INVALID, "lane engine needs Source -> Server(concurrency 1) -> Sink|Counter");
+    if (engine != 1 && engine != 2) return fail(HS_ERR_INVALID, "unknown engine %d", engine);
+
+    if (p->resume) {
+        if (!E->have_run) return fail(HS_ERR_STATE, "resume without a previous run");
+        const hs_run_params &q = E->last;
+        if (q.n_replicas != p->n_replicas || q.seed != p->seed || q.seed_stride != p->seed_stride ||
+            q.rid_base != p->rid_base || q.rid_stride != p->rid_stride || q.record_cap != p->record_cap ||
+            q.sample_cap != p->sample_cap || q.service_cap != p->service_cap ||
+            q.replica_index_base != p->replica_index_base || q.replicas_per_cell != p->replicas_per_cell ||
+            engine != E->last_engine)
+            return fail(HS_ERR_STATE, "resume must repeat the replica set, seeds and capacities of the paused run");
+    }
+
+    const uint32_t n = p->n_replicas;
+    const uint32_t ne = (uint32_t)E->ents.size();
+    uint32_t ring = p->queue_ring ? pow2_at_least(p->queue_ring) : 0;
+    int rc;
+    if ((rc = E->d_summ.ensure((size_t)n * sizeof(hs_replica_summary)))) return rc;
+    if ((rc = E->d_stats.ensure((size_t)n * ne * sizeof(hs_entity_stats)))) return rc;
+    if ((rc = E->d_rec.ensure((size_t)n * p->record_cap * sizeof(hs_event_record)))) return rc;
+    if ((rc = E->d_smp.ensure((size_t)n * p->sample_cap * sizeof(hs_sink_sample)))) return rc;
+    if ((rc = E->d_svc.ensure((size_t)n * p->service_cap * sizeof(double)))) return rc;
+    if (!p->resume) {
+        CUDA_TRY(cudaMemsetAsync(E->d_stats.p, 0, (size_t)n * ne * sizeof(hs_entity_stats), E->stream));
+        if (p->record_cap) CUDA_TRY(cudaMemsetAsync(E->d_rec.p, 0, (size_t)n * p->record_cap * sizeof(hs_event_record), E->stream));
+        if (p->sample_cap) CUDA_TRY(cudaMemsetAsync(E->d_smp.p, 0, (size_t)n * p->sample_cap * sizeof(hs_sink_sample), E->stream));
+        if (p->service_cap) CUDA_TRY(cudaMemsetAsync(E->d_svc.p, 0, (size_t)n * p->service_cap * sizeof(double), E->stream));
+    }
+
+    const bool want_hash = (p->flags & HS_RUN_ORDER_HASH) != 0;
+    const bool want_rec = (p->record_cap | p->sample_cap | p->service_cap) != 0;
+
+    if (engine == 2) {
+        if (!ring) ring = 256;
+        if (p->resume && E->d_rings.n != (size_t)n * ring * sizeof(hs_ring_entry))
+            return fail(HS_ERR_STATE, "resume must keep queue_ring");
+        if ((rc = E->d_state.ensure((size_t)n * sizeof(hs_lane_state)))) return rc;
+        if ((rc = E->d_rings.ensure((size_t)n * ring * sizeof(hs_ring_entry)))) return rc;
+        hs_lane_model M = E->lane_model;
+        M.cell_d0 = (const double *)E->d_cell_d0.p;
+        hs_lane_run R;
+        R.seed = p->seed; R.seed_stride = p->seed_stride; R.rid_base = p->rid_base; R.rid_stride = p->rid_stride;
+        R.end_ns = p->end_ns; R.window_end_ns = p->window_end_ns;
+        R.n_replicas = n; R.index_base = p->replica_index_base; R.replicas_per_cell = p->replicas_per_cell;
+        R.record_cap = p->record_cap; R.sample_cap = p->sample_cap; R.service_cap = p->service_cap;
+        R.ring = ring; R.resume = p->resume;
+        hs_lane_out O;
+        O.summaries = (hs_replica_summary *)E->d_summ.p; O.stats = (hs_entity_stats *)E->d_stats.p;
+        O.records = p->record_cap ? (hs_event_record *)E->d_rec.p : nullptr;
+        O.samples = p->sample_cap ? (hs_sink_sample *)E->d_smp.p : nullptr;
+        O.service = p->service_cap ? (double *)E->d_svc.p : nullptr;
+        const int threads = 64;
+        const int blocks = (int)((n + threads - 1) / threads);
+        CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
+        hs_lane_state *st = (hs_lane_state *)E->d_state.p;
+        hs_ring_entry *rg = (hs_ring_entry *)E->d_rings.p;
+        if (want_rec) hs_lane_kernel<HS_LF_HASH | HS_LF_REC><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
+        else if (want_hash) hs_lane_kernel<HS_LF_HASH><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
+        else hs_lane_kernel<0><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
+        E->launches += 1;
+    } else {
+        rc = hs_warp_launch(E, p, ring, want_hash, want_rec);
+        if (rc) return rc;
+    }
+    E->last = *p;
+    E->last_engine = engine;
+    E->have_run = true;
+    return HS_OK;
+}
+
+int hs_sync(hs_engine *E)
+{
+    if (!E) return fail(HS_ERR_INVALID, "engine is NULL");
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    return HS_OK;
+}
+
+int hs_last_run_ms(hs_engine *E, float *ms)
+{
+    if (!E || !ms) return fail(HS_ERR_INVALID, "NULL argument");
+    if (!E->have_run) return fail(HS_ERR_STATE, "no run yet");
+    CUDA_TRY(cudaEventSynchronize(E->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, E->ev0, E->ev1));
+    return HS_OK;
+}
+
+int hs_launch_count(hs_engine *E, uint64_t *n)
+{
+    if (!E || !n) return fail(HS_ERR_INVALID, "NULL argument");
+    *n = E->launches;
+    return HS_OK;
+}
+
+int hs_read_outputs(hs_engine *E, const hs_outputs *out)
+{
+    if (!E || !out) return fail(HS_ERR_INVALID, "NULL argument");
+    if (!E->have_run) return fail(HS_ERR_STATE, "no run yet");
+    CUDA_TRY(cudaSetDevice(E->device));
+    const hs_run_params &p = E->last;
+    const size_t n = p.n_replicas, ne = E->ents.size();
+    if (out->summaries) CUDA_TRY(cudaMemcpyAsync(out->summaries, E->d_summ.p, n * sizeof(hs_replica_summary), cudaMemcpyDeviceToHost, E->stream));
+    if (out->entity_stats) CUDA_TRY(cudaMemcpyAsync(out->entity_stats, E->d_stats.p, n * ne * sizeof(hs_entity_stats), cudaMemcpyDeviceToHost, E->stream));
+    if (out->records && p.record_cap) CUDA_TRY(cudaMemcpyAsync(out->records, E->d_rec.p, n * p.record_cap * sizeof(hs_event_record), cudaMemcpyDeviceToHost, E->stream));
+    if (out->sink_samples && p.sample_cap) CUDA_TRY(cudaMemcpyAsync(out->sink_samples, E->d_smp.p, n * p.sample_cap * sizeof(hs_sink_sample), cudaMemcpyDeviceToHost, E->stream));
+    if (out->service_samples && p.service_cap) CUDA_TRY(cudaMemcpyAsync(out->service_samples, E->d_svc.p, n * p.service_cap * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    return HS_OK;
+}
+
+static int compute_totals(hs_engine *E)
+{
+    const hs_run_params &p = E->last;
+    int rc;
+    const int blocks = 256;
+    if ((rc = E->d_partials.ensure((size_t)blocks * sizeof(hs_totals)))) return rc;
+    if ((rc = E->d_totals.ensure(sizeof(hs_totals)))) return rc;
+    hs_totals_partial_kernel<<<blocks, 256, 0, E->stream>>>(
+        (const hs_replica_summary *)E->d_summ.p, (const hs_entity_stats *)E->d_stats.p,
+        (const hs_entity_desc *)E->d_ents.p, p.n_replicas, (uint32_t)E->ents.size(), (hs_totals *)E->d_partials.p);
+    CUDA_TRY(cudaGetLastError());
+    hs_totals_final_kernel<<<1, 32, 0, E->stream>>>((const hs_totals *)E->d_partials.p, blocks, (hs_totals *)E->d_totals.p);
+    CUDA_TRY(cudaGetLastError());
+    E->launches += 2;
+    return HS_OK;
+}
+
+int hs_read_totals(hs_engine *E, hs_totals *out)
+{
+    if (!E || !out) return fail(HS_ERR_INVALID, "NULL argument");
+    if (!E->have_run) return fail(HS_ERR_STATE, "no run yet");
+    CUDA_TRY(cudaSetDevice(E->device));
+    int rc = compute_totals(E);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, E->d_totals.p, sizeof(hs_totals), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    return HS_OK;
+}
+
+int hs_totals_device_ptr(hs_engine *E, void **ptr)
+{
+    if (!E || !ptr) return fail(HS_ERR_INVALID, "NULL argument");
+    if (!E->have_run) return fail(HS_ERR_STATE, "no run yet");
+    CUDA_TRY(cudaSetDevice(E->device));
+    int rc = compute_totals(E);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    *ptr = E->d_totals.p;
+    return HS_OK;
+}
+
+} /* extern "C" */
+
+static int hs_warp_launch(hs_engine *, const hs_run_params *, uint32_t, bool, bool)
+{
+    return fail(HS_ERR_INVALID, "warp engine not built yet");
+}

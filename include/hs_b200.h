@@ -115,7 +115,18 @@ typedef struct hs_run_params {
     uint32_t service_cap;      /* service-time samples kept per replica                        */
     uint32_t queue_ring;       /* device queue ring entries per server (power of two), 0 = default */
     uint32_t engine;           /* 0 auto, 1 warp engine (general), 2 lane engine (single server) */
+    /* Windowed execution (reference: Simulation._run_window, core/simulation.py:527-541):
+     * when 0 <= window_end_ns < end_ns the call pauses every replica before the first
+     * event later than window_end_ns and keeps its state on the device; a following
+     * call with resume = 1 continues from there.  The processed-event sequence of a
+     * run cut into windows is identical to the uncut run.  window_end_ns < 0: run to
+     * end_ns. */
+    int64_t window_end_ns;
+    uint32_t resume;           /* 1 = continue the replicas of the previous call          */
+    uint32_t flags;            /* HS_RUN_* bits                                           */
 } hs_run_params;
+
+#define HS_RUN_ORDER_HASH 1u   /* maintain hs_replica_summary.order_hash (off: hash = 0)  */
 
 /* Replica status bits. */
 #define HS_ST_QUEUE_OVERFLOW 1u   /* a server's device queue ring filled up  */

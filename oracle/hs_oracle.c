@@ -426,8 +426,14 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
     int64_t processed = 0;
     uint64_t h = HS_HASH_INIT;
     /* _execute_until, simulation.py:472: the test is on the LAST processed time. */
+    int windowed = (p->window_end_ns >= 0 && p->window_end_ns < p->end_ns);
     while (R.heap.n && R.now <= p->end_ns) {
+        /* windowed run (core/simulation.py:527-541 cut at event boundaries): pause
+         * before the first event later than the window end; resume is not modelled
+         * here -- a paused prefix is compared against the device's paused prefix. */
+        if (windowed && R.heap.a[0].time > p->window_end_ns) break;
         oev e = heap_pop(&R.heap);
+        if (e.time < R.now) continue;     /* "time travel": skipped, not counted (simulation.py:479-489) */
         R.now = e.time;
         uint64_t w1 = hs_record_word1(e.idx, (uint32_t)e.kind, (uint32_t)e.ent);
         h = hs_hash_step(h, e.time, w1);
@@ -436,6 +442,7 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
             rc->time_ns = e.time; rc->sort_index = (uint32_t)e.idx;
             rc->kind = (uint8_t)e.kind; rc->pad = 0; rc->entity = (uint16_t)e.ent;
         }
+        if (!(p->flags & HS_RUN_ORDER_HASH)) h = 0;
         processed++;
         handle(&R, &e);
     }

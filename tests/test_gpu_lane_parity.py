@@ -1,0 +1,138 @@
+"""GPU parity of the lane engine (single-server topology) against the CPU oracle.
+
+Bit-exact: event counts, the (time_ns, sort_index, kind, entity) sequence of every
+processed event, the order hash, per-entity statistics (the floating-point sums are
+accumulated in the reference's order, so they are compared bitwise too), Sink samples
+and service-time samples.  All calls go through the C-ABI (happysim_b200.engine)."""
+import numpy as np
+import pytest
+
+import happysim_b200 as hs
+from happysim_b200 import engine
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("summaries", "entity_stats", "records", "sink_samples", "service_samples")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = engine.Engine(0)
+    yield e
+    e.close()
+
+
+def run_both(eng, model, **kw):
+    eng.upload(model)
+    eng.run(engine.make_params(**kw))
+    got = eng.read_outputs()
+    want = O.oracle_run(model, O.make_params(**kw))
+    return got, want
+
+
+def assert_same(got, want):
+    for k in KEYS:
+        if want[k] is None:
+            continue
+        if got[k].tobytes() != want[k].tobytes():
+            g, w = got[k], want[k]
+            bad = np.argwhere((g != w).reshape(g.shape[0], -1).any(axis=1)).ravel()
+            r = int(bad[0])
+            detail = ""
+            if g.ndim == 2:
+                c = int(np.argwhere(g[r] != w[r]).ravel()[0])
+                detail = f" first at [{r},{c}]: got {g[r][max(0, c - 2):c + 3]} want {w[r][max(0, c - 2):c + 3]}"
+            raise AssertionError(f"{k}: {len(bad)} replicas differ;{detail or f' replica {r}: {g[r]} vs {w[r]}'}")
+
+
+CASES = {
+    "mm1_config1": (dict(), 60),
+    "mm1_heavy": (dict(rate=9.5), 200),
+    "md1_constant": (dict(poisson=False, exponential=False, rate=10, mean_service_s=0.05), 20),
+    "dm1": (dict(poisson=False, rate=7.0), 60),
+    "mm1_capacity5": (dict(rate=50, mean_service_s=0.1, capacity=5), 20),
+    "mm1_capacity0": (dict(rate=5, mean_service_s=0.1, capacity=0), 20),
+    "mm1_lifo": (dict(rate=9, mean_service_s=0.1, lifo=True), 60),
+    "overload": (dict(rate=20, mean_service_s=0.1), 10),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_lane_matches_oracle(eng, name):
+    kw, end_s = CASES[name]
+    model = hs.mm1(**kw)
+    got, want = run_both(eng, model, seed=7, end_ns=int(end_s * 1e9), n_replicas=96, record_cap=6000,
+                         sample_cap=800, service_cap=800)
+    assert int(want["summaries"]["events_processed"].min()) > 50
+    assert_same(got, want)
+
+
+def test_seed_stride_mirrors_parallel_runner(eng):
+    model = hs.mm1()
+    got, want = run_both(eng, model, seed=42, seed_stride=1, rid_stride=0, end_ns=30 * 10**9, n_replicas=40,
+                         record_cap=2500)
+    assert_same(got, want)
+    # replica i of base seed 42 == replica 0 of base seed 42 + i
+    g2, _ = run_both(eng, model, seed=45, seed_stride=1, rid_stride=0, end_ns=30 * 10**9, n_replicas=1, record_cap=2500)
+    assert g2["records"][0].tobytes() == got["records"][3].tobytes()
+
+
+def test_no_hash_mode_same_counts(eng):
+    model = hs.mm1()
+    kw = dict(seed=3, end_ns=120 * 10**9, n_replicas=256)
+    eng.upload(model)
+    eng.run(engine.make_params(**kw))
+    a = eng.read_outputs()
+    eng.run(engine.make_params(flags=0, **kw))
+    b = eng.read_outputs()
+    assert np.array_equal(a["summaries"]["events_processed"], b["summaries"]["events_processed"])
+    assert np.array_equal(a["summaries"]["final_time_ns"], b["summaries"]["final_time_ns"])
+    assert (b["summaries"]["order_hash"] == 0).all()
+    assert a["entity_stats"].tobytes() == b["entity_stats"].tobytes()
+    want = O.oracle_run(model, O.make_params(**kw))
+    assert a["summaries"].tobytes() == want["summaries"].tobytes()
+
+
+def test_windowed_run_equals_uncut_run(eng):
+    """Simulation._run_window semantics: cutting a run into windows must not change the
+    processed-event sequence (order hash, counts, statistics)."""
+    model = hs.mm1(rate=9.0)
+    end = 100 * 10**9
+    kw = dict(seed=11, n_replicas=128, record_cap=3000, sample_cap=500)
+    want = O.oracle_run(model, O.make_params(end_ns=end, **kw))
+    eng.upload(model)
+    cuts = [13 * 10**9, 13 * 10**9 + 1, 50 * 10**9, 99_999_999_999]
+    eng.run(engine.make_params(end_ns=end, window_end_ns=cuts[0], **kw))
+    paused = eng.read_outputs()
+    pw = O.oracle_run(model, O.make_params(end_ns=end, window_end_ns=cuts[0], **kw))
+    assert paused["summaries"].tobytes() == pw["summaries"].tobytes()
+    assert paused["entity_stats"].tobytes() == pw["entity_stats"].tobytes()
+    for c in cuts[1:]:
+        eng.run(engine.make_params(end_ns=end, window_end_ns=c, resume=1, **kw))
+    eng.run(engine.make_params(end_ns=end, window_end_ns=-1, resume=1, **kw))
+    got = eng.read_outputs()
+    assert_same(got, want)
+
+
+def test_queue_overflow_is_flagged_not_silent(eng):
+    model = hs.mm1(rate=200.0, mean_service_s=0.1)      # rho = 20: queue grows without bound
+    eng.upload(model)
+    eng.run(engine.make_params(seed=1, end_ns=10 * 10**9, n_replicas=32, queue_ring=64))
+    got = eng.read_outputs()
+    assert (got["summaries"]["status"] & hs._abi.HS_ST_QUEUE_OVERFLOW).all()
+
+
+def test_totals_match_per_replica_sums(eng):
+    model = hs.mm1()
+    eng.upload(model)
+    eng.run(engine.make_params(seed=5, end_ns=60 * 10**9, n_replicas=1000))
+    got = eng.read_outputs()
+    t = engine.totals_to_dict(eng.read_totals())
+    assert t["events_processed"] == int(got["summaries"]["events_processed"].sum())
+    assert t["replicas"] == 1000 and t["replicas_flagged"] == 0
+    sink = got["entity_stats"][:, 2]
+    assert t["sink_events"] == int(sink["c0"].sum())
+    assert t["min_latency"] == float(sink["f2"].min()) and t["max_latency"] == float(sink["f3"].max())
+    assert abs(t["sum_latency"] - float(sink["f0"].sum())) <= 1e-9 * abs(t["sum_latency"])
+    assert t["server_completions"] == int(got["entity_stats"][:, 1]["c2"].sum())

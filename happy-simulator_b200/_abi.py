@@ -55,6 +55,7 @@ class RunParams(C.Structure):
 class ReplicaSummary(C.Structure):
     _fields_ = [("events_processed", C.c_int64), ("final_time_ns", C.c_int64),
                 ("order_hash", C.c_uint64), ("next_sort_index", C.c_uint64),
+                ("n_sink_samples", C.c_int64), ("n_service_samples", C.c_int64),
                 ("heap_left", C.c_int32), ("status", C.c_uint32)]
 
 
@@ -84,7 +85,7 @@ class Totals(C.Structure):
 
 
 assert C.sizeof(EntityDesc) == 48
-assert C.sizeof(ReplicaSummary) == 40
+assert C.sizeof(ReplicaSummary) == 56
 assert C.sizeof(EntityStats) == 64
 assert C.sizeof(EventRecord) == 16
 assert C.sizeof(SinkSample) == 16
@@ -95,7 +96,8 @@ HS_RUN_ORDER_HASH = 1
 import numpy as _np
 
 SUMMARY_DTYPE = _np.dtype([("events_processed", "<i8"), ("final_time_ns", "<i8"), ("order_hash", "<u8"),
-                           ("next_sort_index", "<u8"), ("heap_left", "<i4"), ("status", "<u4")])
+                           ("next_sort_index", "<u8"), ("n_sink_samples", "<i8"), ("n_service_samples", "<i8"),
+                           ("heap_left", "<i4"), ("status", "<u4")])
 STATS_DTYPE = _np.dtype([("c0", "<i8"), ("c1", "<i8"), ("c2", "<i8"), ("c3", "<i8"),
                          ("f0", "<f8"), ("f1", "<f8"), ("f2", "<f8"), ("f3", "<f8")])
 RECORD_DTYPE = _np.dtype([("time_ns", "<i8"), ("sort_index", "<u4"), ("kind", "u1"), ("pad", "u1"),
@@ -103,5 +105,14 @@ RECORD_DTYPE = _np.dtype([("time_ns", "<i8"), ("sort_index", "<u4"), ("kind", "u
 SAMPLE_DTYPE = _np.dtype([("completion_ns", "<i8"), ("latency_s", "<f8")])
 ENTITY_DTYPE = _np.dtype([("kind", "<i4"), ("target", "<i4"), ("i0", "<i4"), ("i1", "<i4"), ("i2", "<i4"),
                           ("i3", "<i4"), ("l0", "<i8"), ("d0", "<f8"), ("d1", "<f8")])
-assert SUMMARY_DTYPE.itemsize == 40 and STATS_DTYPE.itemsize == 64 and RECORD_DTYPE.itemsize == 16
+assert SUMMARY_DTYPE.itemsize == 56 and STATS_DTYPE.itemsize == 64 and RECORD_DTYPE.itemsize == 16
 assert ENTITY_DTYPE.itemsize == 48
+
+
+def unroll_ring(buf, count: int, cap: int):
+    """Items of a flight-recorder ring in stream order (oldest retained first)."""
+    count = int(count)
+    if count <= cap:
+        return buf[:count]
+    h = count % cap
+    return _np.concatenate([buf[h:cap], buf[:h]])

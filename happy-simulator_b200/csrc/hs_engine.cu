@@ -75,6 +75,7 @@ struct hs_engine {
     bool have_run = false;
     hs_run_params last;
     int last_engine = 0;
+    uint32_t last_ring = 0;
     dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals;
 };
 
@@ -306,8 +307,8 @@ int hs_run(hs_engine *E, const hs_run_params *p)
 
     if (engine == 2) {
         if (!ring) ring = 256;
-        if (p->resume && E->d_rings.n != (size_t)n * ring * sizeof(hs_ring_entry))
-            return fail(HS_ERR_STATE, "resume must keep queue_ring");
+        if (p->resume && E->last_ring != ring) return fail(HS_ERR_STATE, "resume must keep queue_ring");
+        E->last_ring = ring;
         if ((rc = E->d_state.ensure((size_t)n * sizeof(hs_lane_state)))) return rc;
         if ((rc = E->d_rings.ensure((size_t)n * ring * sizeof(hs_ring_entry)))) return rc;
         hs_lane_model M = E->lane_model;

@@ -63,8 +63,8 @@ struct __align__(16) hs_lane_state {   /* persisted between windows (512 B)  */
     uint64_t svc_draws; int64_t accepted, dropped, completed, rejected; double total_service;
     int64_t received; double sum, sumsq, mn, mx;
     uint32_t q_head, q_len; int32_t active; uint32_t status;
-    uint32_t n_smp, n_svc; int32_t now_n; int32_t has_c;
-    int32_t done; int32_t pad0; int64_t pad1;
+    int64_t n_smp, n_svc; int32_t now_n; int32_t has_c;
+    int32_t done; uint32_t rec_pos; double comp; uint32_t smp_pos, svc_pos; int64_t pad1;
     hs_now_ev nowq[HS_NOW_CAP];
 };
 
@@ -133,8 +133,9 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     int64_t now, processed, tT, tC, c_created, gen_count, prov_count;
     uint64_t ctr, hash, iT, iC, arr_draws, svc_draws;
     int64_t accepted, dropped, completed, rejected, received;
-    double svc_s, total_service, sum, sumsq, mn, mx;
-    uint32_t q_head, q_len, status, n_smp, n_svc;
+    double svc_s, total_service, sum, comp, sumsq, mn, mx;
+    uint32_t q_head, q_len, status, rec_pos, smp_pos, svc_pos;
+    int64_t n_smp, n_svc;
     int32_t active, now_n, has_c;
     hs_now_ev nowq[HS_NOW_CAP];
     double arr_cache = 0.0, svc_cache = 0.0;
@@ -147,9 +148,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         tC = S->tC; iC = S->iC; svc_s = S->svc_s; c_created = S->c_created;
         svc_draws = S->svc_draws; accepted = S->accepted; dropped = S->dropped; completed = S->completed;
         rejected = S->rejected; total_service = S->total_service;
-        received = S->received; sum = S->sum; sumsq = S->sumsq; mn = S->mn; mx = S->mx;
+        received = S->received; sum = S->sum; comp = S->comp; sumsq = S->sumsq; mn = S->mn; mx = S->mx;
         q_head = S->q_head; q_len = S->q_len; active = S->active; status = S->status;
         n_smp = S->n_smp; n_svc = S->n_svc; now_n = S->now_n; has_c = S->has_c;
+        rec_pos = S->rec_pos; smp_pos = S->smp_pos; svc_pos = S->svc_pos;
         for (int i = 0; i < HS_NOW_CAP; ++i) nowq[i] = S->nowq[i];
         double u0, u1;
         if (arr_draws & 1) { hs_uniform_pair(seed, rid, sid_arr, arr_draws >> 1, &u0, &u1); arr_cache = u1; }
@@ -159,9 +161,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         arr_draws = 0; svc_draws = 0; gen_count = 0; prov_count = 0;
         tC = 0; iC = 0; svc_s = 0.0; c_created = 0;
         accepted = dropped = completed = rejected = received = 0;
-        total_service = 0.0; sum = 0.0; sumsq = 0.0;
+        total_service = 0.0; sum = 0.0; comp = 0.0; sumsq = 0.0;
         mn = __longlong_as_double(0x7ff0000000000000LL); mx = __longlong_as_double(0xfff0000000000000LL);
         q_head = 0; q_len = 0; active = 0; status = 0; n_smp = 0; n_svc = 0; now_n = 0; has_c = 0;
+        rec_pos = 0; smp_pos = 0; svc_pos = 0;
         for (int i = 0; i < HS_NOW_CAP; ++i) { nowq[i].idx = 0; nowq[i].created = 0; nowq[i].payload_idx = 0; nowq[i].kind = 0; nowq[i].pad = 0; }
         /* Simulation.__init__: source.start() draws the first arrival and the
          * SourceEvent takes index 0 of the GLOBAL counter (simulation.py:77,145-154);
@@ -178,10 +181,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
 #define HS_EMIT(KIND, IDX, ENT)                                                              \
     do {                                                                                     \
         if (FLAGS & HS_LF_HASH) hash = hs_hash_step(hash, now, hs_record_word1((IDX), (KIND), (uint32_t)(ENT))); \
-        if ((FLAGS & HS_LF_REC) && rec && processed < (int64_t)P.record_cap) {               \
+        if ((FLAGS & HS_LF_REC) && rec) {                                                    \
             hs_event_record rc_; rc_.time_ns = now; rc_.sort_index = (uint32_t)(IDX);        \
             rc_.kind = (uint8_t)(KIND); rc_.pad = 0; rc_.entity = (uint16_t)(ENT);           \
-            rec[processed] = rc_;                                                            \
+            rec[rec_pos] = rc_; rec_pos = (rec_pos + 1 == P.record_cap) ? 0u : rec_pos + 1;  \
         }                                                                                    \
         processed++;                                                                         \
     } while (0)
@@ -214,7 +217,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         if (expo) { double u_; HS_DRAW(u_, sid_svc, svc_draws, svc_cache); dur_ = hs_exp_latency_ns(u_, lambda); } \
         else dur_ = const_dur_ns;                                                            \
         svc_s = hs_ns_to_seconds(dur_);                                                      \
-        if ((FLAGS & HS_LF_REC) && svc_out && n_svc < P.service_cap) svc_out[n_svc] = svc_s; \
+        if ((FLAGS & HS_LF_REC) && svc_out) { svc_out[svc_pos] = svc_s; svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
         n_svc++;                                                                             \
         tC = hs_resume_ns(now, svc_s); iC = ctr++; c_created = (CREATED); has_c = 1;         \
     } while (0)
@@ -224,10 +227,11 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         received++;                                                                          \
         if (M.dst_kind == HS_ENT_SINK) {                                                     \
             double lat_ = hs_ns_to_seconds(now - (CREATED));                                 \
-            sum = HS_ADD(sum, lat_); sumsq = HS_ADD(sumsq, HS_MUL(lat_, lat_));              \
+            hs_neumaier_add(&sum, &comp, lat_); sumsq = HS_ADD(sumsq, HS_MUL(lat_, lat_));              \
             if (lat_ < mn) mn = lat_;                                                        \
             if (lat_ > mx) mx = lat_;                                                        \
-            if ((FLAGS & HS_LF_REC) && smp && n_smp < P.sample_cap) { smp[n_smp].completion_ns = now; smp[n_smp].latency_s = lat_; } \
+            if ((FLAGS & HS_LF_REC) && smp) { hs_sink_sample q_; q_.completion_ns = now; q_.latency_s = lat_; smp[smp_pos] = q_; \
+                smp_pos = (smp_pos + 1 == P.sample_cap) ? 0u : smp_pos + 1; }                \
             n_smp++;                                                                         \
         }                                                                                    \
     } while (0)
@@ -414,9 +418,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     S->tC = tC; S->iC = iC; S->svc_s = svc_s; S->c_created = c_created;
     S->svc_draws = svc_draws; S->accepted = accepted; S->dropped = dropped; S->completed = completed;
     S->rejected = rejected; S->total_service = total_service;
-    S->received = received; S->sum = sum; S->sumsq = sumsq; S->mn = mn; S->mx = mx;
+    S->received = received; S->sum = sum; S->comp = comp; S->sumsq = sumsq; S->mn = mn; S->mx = mx;
     S->q_head = q_head; S->q_len = q_len; S->active = active; S->status = status;
     S->n_smp = n_smp; S->n_svc = n_svc; S->now_n = now_n; S->has_c = has_c;
+    S->rec_pos = rec_pos; S->smp_pos = smp_pos; S->svc_pos = svc_pos;
     S->done = paused ? 0 : 1;
     for (int i = 0; i < HS_NOW_CAP; ++i) S->nowq[i] = nowq[i];
 
@@ -424,7 +429,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         hs_replica_summary s;
         s.events_processed = processed; s.final_time_ns = now;
         s.order_hash = (FLAGS & HS_LF_HASH) ? hash : 0ULL;
-        s.next_sort_index = ctr; s.heap_left = (tT != INT64_MAX) + has_c + now_n; s.status = status;
+        s.next_sort_index = ctr; s.n_sink_samples = n_smp; s.n_service_samples = n_svc; s.heap_left = (tT != INT64_MAX) + has_c + now_n; s.status = status;
         O.summaries[r] = s;
     }
     if (O.stats) {
@@ -435,7 +440,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         st[M.srv_id] = a;
         if (M.dst_id >= 0) {
             a.c0 = received; a.c1 = a.c2 = a.c3 = 0;
-            if (M.dst_kind == HS_ENT_SINK) { a.f0 = sum; a.f1 = sumsq; a.f2 = mn; a.f3 = mx; }
+            if (M.dst_kind == HS_ENT_SINK) { a.f0 = hs_neumaier_result(sum, comp); a.f1 = sumsq; a.f2 = mn; a.f3 = mx; }
             else { a.f0 = a.f1 = a.f2 = a.f3 = 0.0; }
             st[M.dst_id] = a;
         }

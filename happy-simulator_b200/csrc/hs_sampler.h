@@ -208,6 +208,29 @@ HS_HD int64_t hs_resume_ns(int64_t now_ns, double delay_s)
 { return now_ns + hs_seconds_to_ns(delay_s); }
 
 /* ------------------------------------------------------------------------ */
+/* Sink.average_latency() is sum(latencies_s) / n (components/common.py:46-50) and
+ * CPython >= 3.12 (the reference requires >= 3.13, pyproject.toml:11) evaluates
+ * float sum() with Neumaier compensation (Python/bltinmodule.c, builtin_sum):
+ *     t = s + x;  c += |s| >= |x| ? (s - t) + x : (x - t) + s;  s = t
+ * and returns s + c when c is non-zero and finite.  Same steps here.          */
+HS_HD void hs_neumaier_add(double *s, double *c, double x)
+{
+    double t = HS_ADD(*s, x);
+    double as = *s < 0.0 ? -*s : *s, ax = x < 0.0 ? -x : x;
+    if (as >= ax) *c = HS_ADD(*c, HS_ADD(HS_SUB(*s, t), x));
+    else          *c = HS_ADD(*c, HS_ADD(HS_SUB(x, t), *s));
+    *s = t;
+}
+
+HS_HD double hs_neumaier_result(double s, double c)
+{
+    /* "if (c && Py_IS_FINITE(c)) f_result += c" */
+    uint64_t b = HS_D2BITS(c) & 0x7fffffffffffffffULL;
+    if (b != 0 && b < 0x7ff0000000000000ULL) return HS_ADD(s, c);
+    return s;
+}
+
+/* ------------------------------------------------------------------------ */
 /* Order hash over the processed-event sequence: FNV-1a style over the two
  * 64-bit words of the 16-byte event record (time_ns, idx | kind<<32 | ent<<40). */
 #define HS_HASH_INIT 0xcbf29ce484222325ULL

@@ -110,9 +110,12 @@ typedef struct hs_run_params {
     uint32_t n_replicas;       /* replicas run by THIS call                                    */
     uint32_t replica_index_base; /* global index of this call's replica 0 (multi-GPU shards)   */
     uint32_t replicas_per_cell;  /* cell = global index / replicas_per_cell (>=1)              */
-    uint32_t record_cap;       /* event records kept per replica (first record_cap events)     */
-    uint32_t sample_cap;       /* Sink samples kept per replica (first sample_cap)             */
-    uint32_t service_cap;      /* service-time samples kept per replica                        */
+    /* Flight-recorder rings, per replica: item i of a stream lives at slot i % cap, so the
+     * buffers hold the LAST cap items (everything when cap >= count).  Every item is written
+     * to HBM: 16 B per processed event, 16 B per Sink sample, 8 B per service start.          */
+    uint32_t record_cap;       /* event-record ring entries per replica (0 = no trace)         */
+    uint32_t sample_cap;       /* Sink-sample ring entries per replica                         */
+    uint32_t service_cap;      /* service-time ring entries per replica                        */
     uint32_t queue_ring;       /* device queue ring entries per server (power of two), 0 = default */
     uint32_t engine;           /* 0 auto, 1 warp engine (general), 2 lane engine (single server) */
     /* Windowed execution (reference: Simulation._run_window, core/simulation.py:527-541):
@@ -138,9 +141,11 @@ typedef struct hs_replica_summary {
     int64_t final_time_ns;     /* clock after the last processed event (simulation.py:503)     */
     uint64_t order_hash;       /* hs_hash_step over every processed event, in order            */
     uint64_t next_sort_index;  /* value of the per-heap creation counter at the end            */
+    int64_t n_sink_samples;    /* Sink samples produced (all sinks); ring position = n % cap   */
+    int64_t n_service_samples; /* service starts (Server._service_times appends)               */
     int32_t heap_left;         /* events still pending                                         */
     uint32_t status;           /* HS_ST_* bits, 0 = clean                                      */
-} hs_replica_summary;          /* 40 bytes */
+} hs_replica_summary;          /* 56 bytes */
 
 typedef struct hs_entity_stats {
     int64_t c0; /* SOURCE generated_count | SERVER stats_accepted | SINK events_received
@@ -148,7 +153,8 @@ typedef struct hs_entity_stats {
     int64_t c1; /* SOURCE payloads created | SERVER stats_dropped | LB requests_forwarded       */
     int64_t c2; /* SERVER requests_completed | LB in-flight entries left                        */
     int64_t c3; /* SERVER requests_rejected | SERVER (after run) -- ; LB responses handled      */
-    double f0;  /* SERVER total_service_time (sequential sum) | SINK sum of latencies (sequential) */
+    double f0;  /* SERVER total_service_time (sequential +=) | SINK sum(latencies_s) as CPython's
+                   float sum() computes it (Neumaier-compensated), so f0 / c0 == average_latency() */
     double f1;  /* SINK sum of squared latencies                                                */
     double f2;  /* SINK min latency (+inf if none)                                              */
     double f3;  /* SINK max latency (-inf if none)                                              */
@@ -170,7 +176,7 @@ typedef struct hs_sink_sample {    /* Sink.completion_times[i], Sink.latencies_s
 typedef struct hs_outputs {        /* caller-owned HOST buffers; any pointer may be NULL        */
     hs_replica_summary *summaries; /* [n_replicas]                                             */
     hs_entity_stats *entity_stats; /* [n_replicas][n_entities]                                 */
-    hs_event_record *records;      /* [n_replicas][record_cap]                                 */
+    hs_event_record *records;      /* [n_replicas][record_cap] ring, slot = event number % cap */
     hs_sink_sample *sink_samples;  /* [n_replicas][sample_cap], all sinks, arrival order       */
     double *service_samples;       /* [n_replicas][service_cap], service-start order           */
 } hs_outputs;

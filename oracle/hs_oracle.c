@@ -132,7 +132,7 @@ typedef struct oent {
     double total_service;    /* Server._total_service_time                        */
     /* SINK / COUNTER */
     int64_t received;
-    double sum, sumsq, mn, mx;
+    double sum, comp, sumsq, mn, mx;   /* sum/comp: Neumaier state of sum(latencies_s) */
     /* LB */
     uint64_t rr_index;       /* RoundRobin._index                                 */
     int64_t lb_received, lb_forwarded, lb_in_flight, lb_responses;
@@ -148,10 +148,14 @@ typedef struct orun {
     uint64_t seed; uint32_t rid;
     int64_t now;
     uint32_t status;
+    /* optional externally supplied draws (hs_oracle_run_trace): the reference's own
+     * RNG outputs, so the restatement can be checked against a STOCK-seed run */
+    const double *trace_targets; uint64_t n_trace_targets;   /* -log(1-U) per arrival  */
+    const double *trace_service; uint64_t n_trace_service;   /* expovariate() samples   */
     /* outputs of this replica */
-    hs_event_record *rec; uint32_t n_rec;
-    hs_sink_sample *smp; uint32_t n_smp;
-    double *svc; uint32_t n_svc;
+    hs_event_record *rec;
+    hs_sink_sample *smp; int64_t n_smp;
+    double *svc; int64_t n_svc;
 } orun;
 
 static void q_push(oent *s, const oreq *r)
@@ -204,7 +208,10 @@ static int request_kind_for(const orun *R, int ent)
 static int64_t next_arrival(orun *R, int sid, oent *s)
 {
     double target;
-    if (s->d.i0 == HS_ARR_POISSON) {
+    if (s->d.i0 == HS_ARR_POISSON && R->trace_targets) {
+        target = s->arr_draws < R->n_trace_targets ? R->trace_targets[s->arr_draws] : 1e300;
+        s->arr_draws++;
+    } else if (s->d.i0 == HS_ARR_POISSON) {
         double u = hs_uniform(R->seed, R->rid, HS_STREAM_ARRIVAL | ((uint32_t)sid << 8), s->arr_draws++);
         target = hs_exp1(u);              /* poisson_arrival.py:31                */
     } else {
@@ -330,14 +337,18 @@ static void handle(orun *R, oev *e)
         }
         E->active++;
         int64_t dur_ns;
-        if (E->d.i2 == HS_SVC_EXPONENTIAL) {
+        if (E->d.i2 == HS_SVC_EXPONENTIAL && R->trace_service) {
+            double sample = E->svc_draws < R->n_trace_service ? R->trace_service[E->svc_draws] : 1e300;
+            E->svc_draws++;
+            dur_ns = hs_seconds_to_ns(sample);            /* Duration.from_seconds(sample) */
+        } else if (E->d.i2 == HS_SVC_EXPONENTIAL) {
             double u = hs_uniform(R->seed, R->rid, HS_STREAM_SERVICE | ((uint32_t)e->ent << 8), E->svc_draws++);
             dur_ns = hs_exp_latency_ns(u, E->lambda);     /* exponential.py:41-45 */
         } else {
             dur_ns = hs_seconds_to_ns(E->d.d0);           /* constant.py:33-35    */
         }
         double service_time_s = hs_ns_to_seconds(dur_ns); /* server.py:246-247    */
-        if (R->svc && R->n_svc < R->p->service_cap) R->svc[R->n_svc] = service_time_s;
+        if (R->svc && R->p->service_cap) R->svc[R->n_svc % R->p->service_cap] = service_time_s;
         R->n_svc++;
         oev c = new_event(R, hs_resume_ns(R->now, service_time_s), HS_EV_CONTINUATION, e->ent);
         c.created_at = e->created_at; c.req_id = e->req_id; c.key = e->key;
@@ -360,11 +371,12 @@ static void handle(orun *R, oev *e)
     case HS_EV_REQ_SINK: {                /* Sink.handle_event, common.py:36-44   */
         E->received++;
         double lat = hs_ns_to_seconds(R->now - e->created_at);
-        E->sum += lat; E->sumsq += lat * lat;
+        hs_neumaier_add(&E->sum, &E->comp, lat); E->sumsq += lat * lat;
         if (lat < E->mn) E->mn = lat;
         if (lat > E->mx) E->mx = lat;
-        if (R->smp && R->n_smp < R->p->sample_cap) {
-            R->smp[R->n_smp].completion_ns = R->now; R->smp[R->n_smp].latency_s = lat;
+        if (R->smp && R->p->sample_cap) {
+            hs_sink_sample *q = &R->smp[R->n_smp % R->p->sample_cap];
+            q->completion_ns = R->now; q->latency_s = lat;
         }
         R->n_smp++;
         run_request_hooks(R, e);
@@ -382,11 +394,15 @@ static void handle(orun *R, oev *e)
     }
 }
 
+typedef struct { const double *targets; uint64_t n_targets; const double *service; uint64_t n_service; } otrace;
+
 static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t r,
-                        const hs_outputs *out)
+                        const hs_outputs *out, const otrace *tr)
 {
     orun R; memset(&R, 0, sizeof R);
     R.m = m; R.p = p;
+    if (tr) { R.trace_targets = tr->targets; R.n_trace_targets = tr->n_targets;
+              R.trace_service = tr->service; R.n_trace_service = tr->n_service; }
     uint32_t ne = m->n_entities;
     uint32_t gidx = p->replica_index_base + r;
     uint32_t cell = p->replicas_per_cell ? gidx / p->replicas_per_cell : 0;
@@ -437,8 +453,8 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
         R.now = e.time;
         uint64_t w1 = hs_record_word1(e.idx, (uint32_t)e.kind, (uint32_t)e.ent);
         h = hs_hash_step(h, e.time, w1);
-        if (R.rec && processed < (int64_t)p->record_cap) {
-            hs_event_record *rc = &R.rec[processed];
+        if (R.rec && p->record_cap) {
+            hs_event_record *rc = &R.rec[processed % (int64_t)p->record_cap];
             rc->time_ns = e.time; rc->sort_index = (uint32_t)e.idx;
             rc->kind = (uint8_t)e.kind; rc->pad = 0; rc->entity = (uint16_t)e.ent;
         }
@@ -450,7 +466,7 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
     if (out->summaries) {
         hs_replica_summary *s = &out->summaries[r];
         s->events_processed = processed; s->final_time_ns = R.now; s->order_hash = h;
-        s->next_sort_index = R.counter; s->heap_left = (int32_t)R.heap.n; s->status = R.status;
+        s->next_sort_index = R.counter; s->n_sink_samples = R.n_smp; s->n_service_samples = R.n_svc; s->heap_left = (int32_t)R.heap.n; s->status = R.status;
     }
     if (out->entity_stats) {
         for (uint32_t i = 0; i < ne; ++i) {
@@ -463,7 +479,7 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
                 st->c0 = E->accepted; st->c1 = E->dropped; st->c2 = E->completed; st->c3 = E->rejected;
                 st->f0 = E->total_service; break;
             case HS_ENT_SINK:
-                st->c0 = E->received; st->f0 = E->sum; st->f1 = E->sumsq; st->f2 = E->mn; st->f3 = E->mx; break;
+                st->c0 = E->received; st->f0 = hs_neumaier_result(E->sum, E->comp); st->f1 = E->sumsq; st->f2 = E->mn; st->f3 = E->mx; break;
             case HS_ENT_COUNTER: st->c0 = E->received; break;
             case HS_ENT_LB:
                 st->c0 = E->lb_received; st->c1 = E->lb_forwarded; st->c2 = E->lb_in_flight; st->c3 = E->lb_responses; break;
@@ -479,7 +495,7 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
 int hs_oracle_run(const hs_model_desc *m, const hs_run_params *p, const hs_outputs *out)
 {
     if (!m || !p || !out || m->abi_version != HS_ABI_VERSION) return HS_ERR_INVALID;
-    for (uint32_t r = 0; r < p->n_replicas; ++r) run_replica(m, p, r, out);
+    for (uint32_t r = 0; r < p->n_replicas; ++r) run_replica(m, p, r, out, NULL);
     return HS_OK;
 }
 
@@ -488,7 +504,19 @@ int hs_oracle_run_range(const hs_model_desc *m, const hs_run_params *p, const hs
                         uint32_t r0, uint32_t r1)
 {
     if (!m || !p || !out || m->abi_version != HS_ABI_VERSION) return HS_ERR_INVALID;
-    for (uint32_t r = r0; r < r1 && r < p->n_replicas; ++r) run_replica(m, p, r, out);
+    for (uint32_t r = r0; r < r1 && r < p->n_replicas; ++r) run_replica(m, p, r, out, NULL);
+    return HS_OK;
+}
+
+/* One replica driven by externally supplied draws: arrival target areas
+ * (-log(1-U), poisson_arrival.py:31) and service samples (random.expovariate,
+ * exponential.py:43) captured from the reference's stock generators. */
+int hs_oracle_run_trace(const hs_model_desc *m, const hs_run_params *p, const hs_outputs *out,
+                        const double *targets, uint64_t n_targets, const double *service, uint64_t n_service)
+{
+    if (!m || !p || !out || m->abi_version != HS_ABI_VERSION || p->n_replicas != 1) return HS_ERR_INVALID;
+    otrace tr = { targets, n_targets, service, n_service };
+    run_replica(m, p, 0, out, &tr);
     return HS_OK;
 }
 

@@ -1,0 +1,138 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container).
+
+    python tests/golden/gen_golden.py          # needs /root/reference
+
+Two families of fixtures, both produced by the reference's own Simulation.run():
+
+  philox_<case>.npz   the reference driven through its plug-in points by the shared
+                      Philox sampler (ref_harness.run_reference): the full processed-event
+                      sequence hash, counts, per-entity statistics, the first records and
+                      samples.  The oracle and the CUDA engine must reproduce these bit for bit.
+  stock_<case>.npz    the reference with its STOCK generators (random.seed(s);
+                      np.random.seed(s)) -- the README quick-start known answers of
+                      SURVEY.md 8(c) -- together with the generators' outputs, so the oracle's
+                      state machine and time arithmetic can be replayed against a run that
+                      never saw our sampler (oracle_lib.oracle_run_trace).
+
+The fixtures are small (first MAX_REC records / MAX_SMP samples; the order hash covers the
+whole run) and committed; nothing on the GPU box reads /root/reference.
+"""
+from __future__ import annotations
+
+import math
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), HERE]
+
+import happysim_b200 as hs  # noqa: E402
+import ref_harness as RH  # noqa: E402
+
+MAX_REC = 4000
+MAX_SMP = 1500
+
+
+def names_for(model):
+    return list(model.names)
+
+
+def chash_case(n_servers, vnodes, population, rate):
+    names = [f"S{i}" for i in range(n_servers)]
+    tab = RH.ring_table_from_reference(names, vnodes, population)
+    return hs.lb_key_table(tab, n_servers, rate), vnodes
+
+
+def tandem():
+    b = hs.ModelBuilder()
+    src = b.source(rate=6.0)
+    s1 = b.server("A", mean_service_s=0.08)
+    s2 = b.server("B", concurrency=2, mean_service_s=0.2)
+    snk = b.sink()
+    b.set_target(src, s1); b.set_target(s1, s2); b.set_target(s2, snk)
+    return b.build()
+
+
+def source_to_counter():
+    b = hs.ModelBuilder()
+    src = b.source("PingSource", rate=1.0, poisson=False)
+    c = b.counter("pingcounter")
+    b.set_target(src, c)
+    return b.build()
+
+
+def two_sources():
+    b = hs.ModelBuilder()
+    a = b.source("A", rate=3.0)
+    c = b.source("B", rate=4.0, poisson=False, stop_after_ns=20 * 10**9)
+    srv = b.server(concurrency=2, mean_service_s=0.1)
+    snk = b.sink()
+    b.set_target(a, srv); b.set_target(c, srv); b.set_target(srv, snk)
+    return b.build()
+
+
+def philox_cases():
+    c = {}
+    c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
+    c["mm1_seed1"] = (hs.mm1(), dict(seed=1, rid=0, end_s=60))
+    c["mm1_seed42"] = (hs.mm1(), dict(seed=42, rid=0, end_s=60))
+    c["mm1_rid77_long"] = (hs.mm1(rate=9.5), dict(seed=1234, rid=77, end_s=400))
+    c["dd1_constant"] = (hs.mm1(poisson=False, exponential=False, rate=10, mean_service_s=0.05), dict(seed=1, rid=0, end_s=20))
+    c["mm1_capacity5"] = (hs.mm1(rate=50, capacity=5), dict(seed=3, rid=2, end_s=20))
+    c["mm1_lifo"] = (hs.mm1(rate=9, lifo=True), dict(seed=3, rid=5, end_s=60))
+    c["mmc4"] = (hs.mm1(rate=32, concurrency=4), dict(seed=9, rid=1, end_s=30))
+    c["mmc32"] = (hs.mm1(rate=256, concurrency=32), dict(seed=9, rid=3, end_s=10))
+    c["lb_rr8"] = (hs.lb_round_robin(n_servers=8, rate=64.0), dict(seed=5, rid=0, end_s=10))
+    c["lb_rr64"] = (hs.lb_round_robin(n_servers=64, rate=512.0), dict(seed=7, rid=9, end_s=5))
+    m, v = chash_case(16, 20, 500, 128.0)
+    c["lb_chash16"] = (m, dict(seed=11, rid=4, end_s=5, chash_vnodes=v))
+    c["tandem"] = (tandem(), dict(seed=13, rid=0, end_s=60))
+    c["source_to_counter"] = (source_to_counter(), dict(seed=0, rid=0, end_s=60))
+    c["two_sources"] = (two_sources(), dict(seed=21, rid=6, end_s=40))
+    return c
+
+
+def save_case(path, model, ref, meta):
+    rec = ref["records"]
+    np.savez_compressed(
+        path,
+        entities=model.entities, backends=model.backends, key_table=model.key_table,
+        names=np.array(model.names), meta=np.array([meta["seed"], meta["rid"], int(meta["end_s"] * 1e9)], dtype=np.int64),
+        summaries=ref["summaries"], entity_stats=ref["entity_stats"],
+        n_records=np.int64(len(rec)), records=rec[:MAX_REC],
+        n_samples=np.int64(len(ref["sink_samples"])), sink_samples=ref["sink_samples"][:MAX_SMP],
+        n_service=np.int64(len(ref["service_samples"])), service_samples=ref["service_samples"][:MAX_SMP],
+        **{k: v for k, v in meta.items() if isinstance(v, np.ndarray)},
+    )
+
+
+def main():
+    for name, (model, kw) in philox_cases().items():
+        ref = RH.run_reference(model, seed=kw["seed"], rid=kw["rid"], end_ns=int(kw["end_s"] * 1e9),
+                               chash_vnodes=kw.get("chash_vnodes"))
+        save_case(os.path.join(HERE, f"philox_{name}.npz"), model, ref, kw)
+        print(f"philox_{name}: {len(ref['records'])} events, hash {int(ref['summaries']['order_hash'][0]):#x}")
+
+    # ---- stock generators: the README quick-start known answers ----
+    for seed, end_s in ((42, 60), (7, 200)):
+        model = hs.mm1()
+        ref = RH.run_reference(model, seed=seed, end_ns=int(end_s * 1e9), stock_rng=True)
+        n_draw = len(ref["records"])
+        u = np.random.RandomState(seed).random_sample(n_draw)          # numpy legacy global stream
+        targets = np.array([-math.log(1.0 - x) for x in u])            # poisson_arrival.py:31
+        rnd = random.Random(seed)
+        service = np.array([rnd.expovariate(1 / 0.1) for _ in range(n_draw)])   # exponential.py:36,43
+        meta = dict(seed=seed, rid=0, end_s=end_s, trace_targets=targets, trace_service=service)
+        save_case(os.path.join(HERE, f"stock_mm1_seed{seed}.npz"), model, ref, meta)
+        sink = ref["objects"][2]
+        print(f"stock_mm1_seed{seed}: events={ref['summary'].total_events_processed} "
+              f"sink={sink.events_received} avg_latency={sink.average_latency()!r} "
+              f"final_ns={int(ref['summaries']['final_time_ns'][0])} heap_left={int(ref['summaries']['heap_left'][0])}")
+
+
+if __name__ == "__main__":
+    main()

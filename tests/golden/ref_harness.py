@@ -226,12 +226,11 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             per_server_service[i] = list(o._service_times)
         elif k == A.HS_ENT_SINK:
             stats[i]["c0"] = o.events_received
-            s = 0.0
             s2 = 0.0
             for v in o.latencies_s:
-                s += v
                 s2 += v * v
-            stats[i]["f0"], stats[i]["f1"] = s, s2
+            # exactly what Sink.average_latency() divides by n (common.py:46-50)
+            stats[i]["f0"], stats[i]["f1"] = sum(o.latencies_s), s2
             stats[i]["f2"] = min(o.latencies_s) if o.latencies_s else np.inf
             stats[i]["f3"] = max(o.latencies_s) if o.latencies_s else -np.inf
             sink_samples.append((i, [t.nanoseconds for t in o.completion_times], list(o.latencies_s)))
@@ -262,6 +261,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     if merged:
         smp["completion_ns"] = [m[0] for m in merged]
         smp["latency_s"] = [m[1] for m in merged]
+    summ["n_sink_samples"] = len(merged)
+    summ["n_service_samples"] = len(svc_merged)
     out = {
         "summaries": summ, "entity_stats": stats[None, :], "records": rec, "sink_samples": smp,
         "service_samples": np.array(svc_merged, dtype=np.float64), "objects": objs, "sim": sim,

@@ -1,0 +1,43 @@
+"""Load the committed reference fixtures (tests/golden/*.npz)."""
+import glob
+import os
+
+import numpy as np
+
+import happysim_b200 as hs
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def case_names(prefix):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, prefix + "*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    model = hs.FlatModel(entities=z["entities"], names=[str(s) for s in z["names"]], backends=z["backends"],
+                         key_table=z["key_table"])
+    seed, rid, end_ns = (int(v) for v in z["meta"])
+    return model, dict(seed=seed, rid_base=rid, end_ns=end_ns), z
+
+
+def caps(z):
+    """Ring capacities that retain the whole run, so the fixture's prefix can be compared."""
+    return dict(record_cap=int(z["n_records"]) + 1, sample_cap=int(z["n_samples"]) + 1,
+                service_cap=int(z["n_service"]) + 1)
+
+
+def check_against(z, got, r=0):
+    """Compare replica ``r`` of an oracle/engine result with a reference fixture."""
+    s, ws = got["summaries"][r], z["summaries"][0]
+    for f in ("events_processed", "final_time_ns", "order_hash", "heap_left", "n_sink_samples", "n_service_samples"):
+        assert int(s[f]) == int(ws[f]), (f, int(s[f]), int(ws[f]))
+    assert got["entity_stats"][r].tobytes() == z["entity_stats"][0].tobytes(), "entity statistics differ"
+    n = len(z["records"])
+    assert got["records"][r][:n].tobytes() == z["records"].tobytes(), "event records differ"
+    n = len(z["sink_samples"])
+    if n:
+        assert got["sink_samples"][r][:n].tobytes() == z["sink_samples"].tobytes(), "sink samples differ"
+    n = len(z["service_samples"])
+    if n:
+        assert got["service_samples"][r][:n].tobytes() == z["service_samples"].tobytes(), "service samples differ"

@@ -26,6 +26,9 @@ def lib():
         L.hs_oracle_run_range.argtypes = [C.POINTER(A.ModelDesc), C.POINTER(A.RunParams), C.POINTER(A.Outputs),
                                           C.c_uint32, C.c_uint32]
         L.hs_oracle_run_range.restype = C.c_int
+        L.hs_oracle_run_trace.argtypes = [C.POINTER(A.ModelDesc), C.POINTER(A.RunParams), C.POINTER(A.Outputs),
+                                          C.POINTER(C.c_double), C.c_uint64, C.POINTER(C.c_double), C.c_uint64]
+        L.hs_oracle_run_trace.restype = C.c_int
         L.hs_cpu_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
         L.hs_cpu_uniform.restype = C.c_double
         for n in ("hs_cpu_log", "hs_cpu_exp1"):
@@ -86,5 +89,18 @@ def oracle_run(model: happysim_b200.FlatModel, p: A.RunParams, r0=None, r1=None)
         rc = lib().hs_oracle_run(C.byref(d), C.byref(p), C.byref(o))
     else:
         rc = lib().hs_oracle_run_range(C.byref(d), C.byref(p), C.byref(o), r0, r1)
+    assert rc == 0, rc
+    return bufs
+
+
+def oracle_run_trace(model, p: A.RunParams, targets, service):
+    """One replica fed with externally captured draws (the reference's stock RNG outputs)."""
+    d = model.desc()
+    bufs, o = alloc_outputs(model.n_entities, p)
+    t = np.ascontiguousarray(targets, dtype=np.float64)
+    s = np.ascontiguousarray(service, dtype=np.float64)
+    rc = lib().hs_oracle_run_trace(C.byref(d), C.byref(p), C.byref(o),
+                                   t.ctypes.data_as(C.POINTER(C.c_double)), len(t),
+                                   s.ctypes.data_as(C.POINTER(C.c_double)), len(s))
     assert rc == 0, rc
     return bufs

@@ -1,0 +1,82 @@
+"""The shared sampler (happy-simulator_b200/csrc/hs_sampler.h) through its CPU twins."""
+import ctypes as C
+import math
+import random
+
+import numpy as np
+
+import oracle_lib as O
+
+
+def philox(ctr, key):
+    out = (C.c_uint32 * 4)()
+    O.lib().hs_cpu_philox(*ctr, *key, out)
+    return [int(x) for x in out]
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors for philox4x32-10 (Salmon et al., SC'11)."""
+    assert philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_uniform_is_genrand_res53_of_the_block():
+    L = O.lib()
+    for seed, rid, sid, n in [(0, 0, 0, 0), (42, 7, 1 | (3 << 8), 5), (2**40 + 3, 65535, 2, 123456789012)]:
+        x = philox([(n >> 1) & 0xffffffff, (n >> 1) >> 32, rid, sid], [seed & 0xffffffff, seed >> 32])
+        a, b = (x[2], x[3]) if n & 1 else (x[0], x[1])
+        want = ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0
+        assert L.hs_cpu_uniform(seed, rid, sid, n) == want
+        assert 0.0 <= want < 1.0
+
+
+def test_log_within_one_ulp_of_libm():
+    L = O.lib()
+    rnd = random.Random(5)
+    worst = 0.0
+    for _ in range(100000):
+        x = 1.0 - rnd.random()
+        a, b = L.hs_cpu_log(x), math.log(x)
+        if b != 0.0:
+            worst = max(worst, abs(a - b) / math.ulp(b))
+    assert worst <= 1.0
+    assert L.hs_cpu_log(1.0) == 0.0
+    assert L.hs_cpu_log(2.0 ** -53) == math.log(2.0 ** -53)
+    for x in (0.5, 0.25, 0.7071067811865476, 0.7071067811865475, 1e-300, 5e-324):
+        assert abs(L.hs_cpu_log(x) - math.log(x)) <= math.ulp(math.log(x))
+
+
+def test_time_arithmetic_matches_python_semantics():
+    """T1-T3 / L2 / D1 of SURVEY.md 8(a) against the reference's Python expressions."""
+    L = O.lib()
+    rnd = random.Random(9)
+    for _ in range(20000):
+        ns = rnd.randrange(0, 10**15)
+        s = rnd.random() * 10 ** rnd.randrange(-9, 6)
+        assert L.hs_cpu_seconds_to_ns(s) == int(s * 1_000_000_000)            # temporal.py:58-62
+        assert L.hs_cpu_ns_to_seconds(ns) == float(ns) / 1_000_000_000        # temporal.py:66-68
+        target, rate = rnd.expovariate(1.0), rnd.choice([8.0, 10.0, 50.0, 512.0, 0.37])
+        t_next = float(ns) / 1_000_000_000 + target / rate                    # arrival_time_provider.py:70-78
+        assert L.hs_cpu_next_arrival_ns(ns, target, rate) == int(t_next * 1_000_000_000)
+        u, lam = rnd.random(), 1 / rnd.choice([0.1, 0.01, 0.25])
+        sample = L.hs_cpu_exp1(u) / lam                                       # exponential.py:43-45
+        assert L.hs_cpu_exp_latency_ns(u, lam) == int(sample * 1_000_000_000)
+
+
+def test_constant_rate_tick_drift_golden_vector():
+    """tests/regression/test_arrival_time_regression.py:20-31 of the reference: rate 50 ticks."""
+    L = O.lib()
+    t, got = 0, []
+    for _ in range(10):
+        t = L.hs_cpu_next_arrival_ns(t, 1.0, 50.0)
+        got.append(t / 1e9)
+    want = [0.02, 0.04, 0.06, 0.08, 0.1, 0.12, 0.14, 0.16, 0.18, 0.199999999]
+    assert all(abs(a - b) < 1e-8 for a, b in zip(got, want))
+    assert got[-1] == 0.199999999
+    t, got = 0, []
+    for _ in range(10):
+        t = L.hs_cpu_next_arrival_ns(t, 1.0, 100.0)
+        got.append(t)
+    assert got[-1] == 99999999

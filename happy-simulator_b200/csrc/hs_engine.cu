@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -19,6 +20,9 @@
 #include "hs_lane_engine.cuh"
 #include "hs_warp_engine.cuh"
 #include "hs_totals.cuh"
+
+struct hs_engine;
+static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec);
 
 static thread_local char g_err[512] = "";
 
@@ -76,7 +80,7 @@ struct hs_engine {
     hs_run_params last;
     int last_engine = 0;
     uint32_t last_ring = 0;
-    dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals;
+    dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals, d_srv_index, d_counter;
 };
 
 /* ---- validation ----------------------------------------------------------- */
@@ -170,6 +174,86 @@ static bool classify_lane(hs_engine *E)
     return true;
 }
 
+/* ---- warp engine launch ------------------------------------------------- */
+
+static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec)
+{
+    const uint32_t n = p->n_replicas;
+    const uint32_t ne = (uint32_t)E->ents.size();
+    if (!ring) ring = 128;
+    /* FEL slots: one pending SourceEvent per source, one ProcessContinuation per busy
+     * server slot, plus the same-timestamp protocol events in flight. */
+    uint64_t live = 24;
+    uint32_t n_servers = 0;
+    std::vector<int32_t> srv_index(ne, -1);
+    for (uint32_t i = 0; i < ne; ++i) {
+        const hs_entity_desc &e = E->ents[i];
+        if (e.kind == HS_ENT_SOURCE) live += 2;
+        if (e.kind == HS_ENT_SERVER) {
+            int32_t c = e.i0;
+            for (uint32_t k = 0; k < E->n_cells; ++k) c = std::max(c, E->cell_i0[(size_t)k * ne + i]);
+            live += (uint64_t)c + 1;
+            srv_index[i] = (int32_t)n_servers++;
+        }
+    }
+    const uint32_t S = (uint32_t)((live + 31) / 32) * 32;
+    const uint32_t block_bytes = (uint32_t)((sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + (size_t)S * 44 + 15) / 16 * 16);
+    const uint32_t per_warp = 16 + block_bytes;
+    const uint32_t smem_budget = 200 * 1024;
+    if (per_warp > 227 * 1024 - 1024) return fail(HS_ERR_INVALID, "model too large for the warp engine (%u B of state per replica)", per_warp);
+    uint32_t warps = std::min<uint32_t>(8, std::max<uint32_t>(1, (smem_budget / 2) / per_warp));
+    if (per_warp * warps > 227 * 1024 - 1024) warps = 1;
+    const uint32_t smem = per_warp * warps;
+    uint32_t blocks_per_sm = std::max<uint32_t>(1, std::min<uint32_t>((227 * 1024) / (smem + 1024), 64 / warps));
+    if (blocks_per_sm * warps * 32 > 2048) blocks_per_sm = 2048 / (warps * 32);
+    uint32_t grid = std::min<uint32_t>((n + warps - 1) / warps, (uint32_t)E->sm_count * blocks_per_sm);
+
+    if (p->resume && (E->last_ring != ring)) return fail(HS_ERR_STATE, "resume must keep queue_ring");
+    E->last_ring = ring;
+    int rc;
+    if ((rc = E->d_state.ensure((size_t)n * block_bytes))) return rc;
+    if ((rc = E->d_rings.ensure(std::max<size_t>(16, (size_t)n * n_servers * ring * sizeof(hs_wring_entry))))) return rc;
+    if ((rc = E->d_srv_index.ensure(ne * 4 + 16))) return rc;
+    if ((rc = E->d_counter.ensure(16))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(E->d_srv_index.p, srv_index.data(), ne * 4, cudaMemcpyHostToDevice, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));     /* srv_index is a local */
+    CUDA_TRY(cudaMemsetAsync(E->d_counter.p, 0, 16, E->stream));
+
+    hs_warp_model M;
+    M.ents = (const hs_entity_desc *)E->d_ents.p;
+    M.backends = (const int32_t *)E->d_backends.p; M.key_table = (const int32_t *)E->d_key_table.p;
+    M.srv_index = (const int32_t *)E->d_srv_index.p;
+    M.cell_d0 = (const double *)E->d_cell_d0.p; M.cell_i0 = (const int32_t *)E->d_cell_i0.p;
+    M.n_entities = ne; M.n_cells = E->n_cells; M.n_servers = n_servers; M.fel_slots = S; M.block_bytes = block_bytes;
+    hs_warp_run R;
+    R.seed = p->seed; R.seed_stride = p->seed_stride; R.rid_base = p->rid_base; R.rid_stride = p->rid_stride;
+    R.end_ns = p->end_ns; R.window_end_ns = p->window_end_ns;
+    R.n_replicas = n; R.index_base = p->replica_index_base; R.replicas_per_cell = p->replicas_per_cell;
+    R.record_cap = p->record_cap; R.sample_cap = p->sample_cap; R.service_cap = p->service_cap;
+    R.ring = ring; R.resume = p->resume;
+    hs_warp_out O;
+    O.summaries = (hs_replica_summary *)E->d_summ.p; O.stats = (hs_entity_stats *)E->d_stats.p;
+    O.records = p->record_cap ? (hs_event_record *)E->d_rec.p : nullptr;
+    O.samples = p->sample_cap ? (hs_sink_sample *)E->d_smp.p : nullptr;
+    O.service = p->service_cap ? (double *)E->d_svc.p : nullptr;
+
+    auto launch = [&](auto kern) -> int {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
+        kern<<<grid, warps * 32, smem, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O,
+                                                   (unsigned int *)E->d_counter.p);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
+        return 0;
+    };
+    if (want_rec) rc = launch(hs_warp_kernel<HS_WF_HASH | HS_WF_REC>);
+    else if (want_hash) rc = launch(hs_warp_kernel<HS_WF_HASH>);
+    else rc = launch(hs_warp_kernel<0>);
+    if (rc) return rc;
+    E->launches += 1;
+    return HS_OK;
+}
+
 /* ---- entry points ------------------------------------------------------- */
 
 extern "C" {
@@ -213,7 +297,8 @@ int hs_engine_destroy(hs_engine *E)
     cudaSetDevice(E->device);
     cudaStreamSynchronize(E->stream);
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
-                       &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals};
+                       &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
+                       &E->d_srv_index, &E->d_counter};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
@@ -427,8 +512,3 @@ int hs_totals_device_ptr(hs_engine *E, void **ptr)
 }
 
 } /* extern "C" */
-
-static int hs_warp_launch(hs_engine *, const hs_run_params *, uint32_t, bool, bool)
-{
-    return fail(HS_ERR_INVALID, "warp engine not built yet");
-}

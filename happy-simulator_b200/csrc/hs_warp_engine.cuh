@@ -1,5 +1,474 @@
+/* hs_warp_engine.cuh -- "warp engine": one WARP per replica, any lowered model
+ * (sources, servers with concurrency c, sinks, counters, load balancers).
+ *
+ * Layout of one replica (contiguous block in HBM, staged into the warp's slice
+ * of shared memory with TMA bulk copies -- cp.async.bulk + mbarrier -- when a
+ * paused window is resumed, and written back with cp.async.bulk when the window
+ * ends):
+ *     [ header 128 B | entity state n x 96 B | future-event list, SoA, S slots x 44 B ]
+ * The future-event list (FEL) has S = 32 k slots; lane l owns slots l, l+32, ...
+ * Popping the next event is a lane-parallel scan of the (time, sort_index) keys
+ * followed by a 5-step __shfl_xor_sync min-reduction; the handler of the popped
+ * event is the reference's handler, restated statement by statement, executed
+ * by lane 0 (it is scalar control flow over one entity's state); queue contents
+ * (FIFOQueue / LIFOQueue items) live in per-server rings in HBM.
+ *
+ * This is the pop-invoke-push loop of happysimulator/core/simulation.py:449-505;
+ * handlers: see oracle/hs_oracle.c for the one-to-one citations (identical
+ * structure), and include/hs_b200.h for the event kinds.
+ */
 #ifndef HS_WARP_ENGINE_CUH
 #define HS_WARP_ENGINE_CUH
-struct hs_engine;
-static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec);
-#endif
+
+#include "hs_sampler.h"
+#include "../../include/hs_b200.h"
+
+#define HS_WF_HASH 1
+#define HS_WF_REC 2
+
+struct __align__(16) hs_warp_hdr {      /* 128 B */
+    int64_t now; uint64_t ctr; int64_t processed; uint64_t hash;
+    int64_t n_smp, n_svc;
+    uint32_t rec_pos, smp_pos, svc_pos, status;
+    int32_t fel_n, done; uint32_t pad[14];
+};
+
+struct __align__(16) hs_went {          /* 96 B per entity */
+    double d0;          /* effective rate / mean (cell override applied)          */
+    double lambda;      /* SERVER: 1 / mean (exponential.py:36)                   */
+    int32_t i0;         /* effective concurrency / arrival kind / strategy        */
+    int32_t pad0; int64_t pad1;
+    union {
+        struct { int64_t cur_ns; uint64_t arr_draws, key_draws; int64_t generated, provider; } src;
+        struct { uint32_t q_head, q_len; int32_t active, pad; uint64_t svc_draws;
+                 int64_t accepted, dropped, completed, rejected; double total_service; } srv;
+        struct { int64_t received; double sum, comp, sumsq, mn, mx; } snk;
+        struct { uint64_t rr_index; int64_t received, forwarded, in_flight, responses; } lb;
+        uint64_t raw[8];
+    } u;
+};
+
+struct hs_wring_entry { int64_t created; uint64_t idx; int64_t key; };   /* 24 B */
+
+struct hs_warp_model {
+    const hs_entity_desc *ents;     /* device */
+    const int32_t *backends, *key_table, *srv_index;
+    const double *cell_d0; const int32_t *cell_i0;
+    uint32_t n_entities, n_cells, n_servers, fel_slots;   /* fel_slots = S, multiple of 32 */
+    uint32_t block_bytes;           /* bytes of one replica block (multiple of 16)          */
+};
+
+struct hs_warp_run {
+    uint64_t seed, seed_stride;
+    uint32_t rid_base, rid_stride;
+    int64_t end_ns, window_end_ns;
+    uint32_t n_replicas, index_base, replicas_per_cell;
+    uint32_t record_cap, sample_cap, service_cap, ring, resume;
+};
+
+struct hs_warp_out {
+    hs_replica_summary *summaries;
+    hs_entity_stats *stats;
+    hs_event_record *records;
+    hs_sink_sample *samples;
+    double *service;
+};
+
+/* ---- PTX helpers: mbarrier + TMA 1-D bulk copies ------------------------- */
+__device__ __forceinline__ uint32_t hs_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void hs_mbar_init(uint64_t *bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(hs_smem_u32(bar)), "r"(count) : "memory"); }
+
+__device__ __forceinline__ void hs_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    uint64_t state;
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;"
+                 : "=l"(state) : "r"(hs_smem_u32(bar)), "r"(bytes) : "memory");
+    (void)state;
+}
+
+__device__ __forceinline__ void hs_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(hs_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void hs_tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(hs_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(hs_smem_u32(bar)) : "memory");
+}
+
+/* every thread that wrote the staged block through the generic proxy fences it
+ * towards the async proxy before the (single-thread) bulk store is issued */
+__device__ __forceinline__ void hs_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void hs_tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(hs_smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+/* ---- the kernel --------------------------------------------------------- */
+
+#define HS_W_EMPTY 0x7fffffffffffffffLL
+
+template <int FLAGS>
+__global__ void __launch_bounds__(256)
+hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blocks,
+               hs_wring_entry *__restrict__ rings, hs_warp_out O, unsigned int *__restrict__ next_replica)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t S = M.fel_slots;
+    const uint32_t ne = M.n_entities;
+    const uint32_t per_warp = 16u + M.block_bytes;          /* mbarrier slot + block */
+    unsigned char *base = smem_raw + (size_t)warp * per_warp;
+    uint64_t *mbar = (uint64_t *)base;
+    unsigned char *blk = base + 16;
+    hs_warp_hdr *H = (hs_warp_hdr *)blk;
+    hs_went *E = (hs_went *)(blk + sizeof(hs_warp_hdr));
+    unsigned char *felp = blk + sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went);
+    int64_t *f_time = (int64_t *)felp;
+    uint64_t *f_idx = (uint64_t *)(felp + (size_t)S * 8);
+    int64_t *f_created = (int64_t *)(felp + (size_t)S * 16);
+    uint64_t *f_aux = (uint64_t *)(felp + (size_t)S * 24);
+    uint32_t *f_m0 = (uint32_t *)(felp + (size_t)S * 32);   /* kind | ent << 8              */
+    int32_t *f_key = (int32_t *)(felp + (size_t)S * 36);
+    uint32_t *f_hook = (uint32_t *)(felp + (size_t)S * 40); /* (lb_hook + 1) | poll << 31   */
+
+    if (lane == 0) hs_mbar_init(mbar, 1);
+    __syncwarp();
+    uint32_t phase = 0;
+    const bool windowed = (P.window_end_ns >= 0 && P.window_end_ns < P.end_ns);
+
+    while (true) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(next_replica, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= P.n_replicas) break;
+
+        const uint32_t gidx = P.index_base + r;
+        const uint64_t seed = P.seed + (uint64_t)gidx * P.seed_stride;
+        const uint32_t rid = P.rid_base + gidx * P.rid_stride;
+        unsigned char *gblk = blocks + (size_t)r * M.block_bytes;
+        hs_wring_entry *ring0 = rings + (size_t)r * M.n_servers * P.ring;
+        const uint32_t ring_mask = P.ring - 1u;
+
+        /* ---- stage the replica into shared memory -------------------------- */
+        if (P.resume) {
+            if (lane == 0) {
+                hs_mbar_expect_tx(mbar, M.block_bytes);
+                hs_tma_load_1d(blk, gblk, M.block_bytes, mbar);
+            }
+            hs_mbar_wait(mbar, phase);
+            phase ^= 1u;
+            __syncwarp();
+            if (H->done) continue;                      /* finished in an earlier window */
+        } else {
+            for (uint32_t i = lane; i < M.block_bytes / 8; i += 32) ((uint64_t *)blk)[i] = 0ull;
+            __syncwarp();
+            for (uint32_t i = lane; i < S; i += 32) f_time[i] = HS_W_EMPTY;
+            const uint32_t cell = M.n_cells ? (gidx / P.replicas_per_cell) % M.n_cells : 0u;
+            for (uint32_t i = lane; i < ne; i += 32) {
+                const hs_entity_desc d = M.ents[i];
+                hs_went *e = &E[i];
+                e->d0 = M.n_cells ? M.cell_d0[(size_t)cell * ne + i] : d.d0;
+                e->i0 = M.n_cells ? M.cell_i0[(size_t)cell * ne + i] : d.i0;
+                e->lambda = (d.kind == HS_ENT_SERVER && d.i2 == HS_SVC_EXPONENTIAL) ? HS_DIV(1.0, e->d0) : 0.0;
+                if (d.kind == HS_ENT_SINK) {
+                    e->u.snk.mn = __longlong_as_double(0x7ff0000000000000LL);
+                    e->u.snk.mx = __longlong_as_double(0xfff0000000000000LL);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                H->hash = HS_HASH_INIT;
+                /* Simulation.__init__: source.start() in order; bootstrap indices come from the
+                 * global counter (simulation.py:77,145-154), run() restarts the per-heap one at 0. */
+                uint64_t boot = 0; int nf = 0;
+                for (uint32_t i = 0; i < ne; ++i) {
+                    if (M.ents[i].kind != HS_ENT_SOURCE) continue;
+                    hs_went *e = &E[i];
+                    double target = 1.0;
+                    if (e->i0 == HS_ARR_POISSON) {
+                        double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (i << 8), e->u.src.arr_draws++);
+                        target = hs_exp1(u);
+                    }
+                    e->u.src.cur_ns = hs_next_arrival_ns(0, target, e->d0);
+                    if ((uint32_t)nf >= S) { H->status |= HS_ST_FEL_OVERFLOW; break; }
+                    f_time[nf] = e->u.src.cur_ns; f_idx[nf] = boot++; f_m0[nf] = HS_EV_SOURCE_TICK | (i << 8);
+                    f_key[nf] = -1; f_hook[nf] = 0; nf++;
+                }
+                H->fel_n = nf; H->ctr = 0;
+            }
+            __syncwarp();
+        }
+
+        hs_event_record *rec = (FLAGS & HS_WF_REC) && O.records ? O.records + (size_t)r * P.record_cap : nullptr;
+        hs_sink_sample *smp = (FLAGS & HS_WF_REC) && O.samples ? O.samples + (size_t)r * P.sample_cap : nullptr;
+        double *svc_out = (FLAGS & HS_WF_REC) && O.service ? O.service + (size_t)r * P.service_cap : nullptr;
+
+        /* ---- pop-invoke-push --------------------------------------------------- */
+        bool paused = false;
+        while (true) {
+            /* lane-parallel scan + shuffle min-reduction over (time, sort_index) */
+            int64_t bt = HS_W_EMPTY; uint64_t bi = ~0ull; uint32_t bs = 0xffffffffu;
+            for (uint32_t s = lane; s < S; s += 32) {
+                const int64_t t = f_time[s];
+                if (t != HS_W_EMPTY) {
+                    const uint64_t ix = f_idx[s];
+                    if (t < bt || (t == bt && ix < bi)) { bt = t; bi = ix; bs = s; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const int64_t ot = __shfl_xor_sync(0xffffffffu, bt, d);
+                const uint64_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                const uint32_t os = __shfl_xor_sync(0xffffffffu, bs, d);
+                if (ot < bt || (ot == bt && (oi < bi || (oi == bi && os < bs)))) { bt = ot; bi = oi; bs = os; }
+            }
+            int go = 0;        /* 0 stop, 1 processed an event, 2 paused */
+            if (lane == 0) {
+                const int64_t now0 = H->now;
+                if (bs == 0xffffffffu || !(now0 <= P.end_ns) || (H->status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW))) go = 0;
+                else if (windowed && bt > P.window_end_ns) go = 2;
+                else {
+                    go = 1;
+                    /* ---- pop ---- */
+                    const uint32_t m0 = f_m0[bs];
+                    const int kind = (int)(m0 & 0xffu);
+                    const uint32_t ent = m0 >> 8;
+                    const int64_t e_created = f_created[bs];
+                    const uint64_t e_aux = f_aux[bs];
+                    const int32_t e_key = f_key[bs];
+                    const uint32_t e_hook = f_hook[bs];
+                    f_time[bs] = HS_W_EMPTY;
+                    H->fel_n--;
+                    if (bt >= now0) {       /* else "time travel": skipped (simulation.py:479-489) */
+                        const int64_t now = bt;
+                        H->now = now;
+                        uint64_t ctr = H->ctr;
+                        if (FLAGS & HS_WF_HASH) H->hash = hs_hash_step(H->hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
+                        if ((FLAGS & HS_WF_REC) && rec) {
+                            hs_event_record rc; rc.time_ns = now; rc.sort_index = (uint32_t)bi; rc.kind = (uint8_t)kind;
+                            rc.pad = 0; rc.entity = (uint16_t)ent;
+                            rec[H->rec_pos] = rc; H->rec_pos = (H->rec_pos + 1 == P.record_cap) ? 0u : H->rec_pos + 1;
+                        }
+                        H->processed++;
+                        hs_went *X = &E[ent];
+
+                        /* push helper: first free slot (lane 0 scans; the FEL is small) */
+#define HS_W_PUSH(TIME, IDX, KIND, ENT, CREATED, AUX, KEY, HOOK)                                         \
+    do {                                                                                                 \
+        uint32_t s_ = 0; while (s_ < S && f_time[s_] != HS_W_EMPTY) ++s_;                                \
+        if (s_ >= S) { H->status |= HS_ST_FEL_OVERFLOW; }                                                \
+        else { f_idx[s_] = (IDX); f_created[s_] = (CREATED); f_aux[s_] = (AUX);                          \
+               f_m0[s_] = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); f_key[s_] = (KEY); f_hook[s_] = (HOOK); \
+               f_time[s_] = (TIME); H->fel_n++; }                                                        \
+    } while (0)
+#define HS_W_REQ_KIND(TGT) (M.ents[(TGT)].kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE :                   \
+                            M.ents[(TGT)].kind == HS_ENT_SINK ? HS_EV_REQ_SINK :                         \
+                            M.ents[(TGT)].kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : HS_EV_REQ_LB)
+                        /* Event._run_completion_hooks for a request whose plain handler returned:
+                         * only the LoadBalancer on_complete hook can be attached (event.py:277-283). */
+#define HS_W_REQUEST_HOOKS()                                                                             \
+    do {                                                                                                 \
+        const uint32_t lbh_ = e_hook & 0x7fffffffu;                                                      \
+        if (lbh_) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_LB_RESPONSE, lbh_ - 1u, 0, 0ull, -1, 0u); } \
+    } while (0)
+                        /* QueueDriver schedule_poll hook (queue_driver.py:79-85) */
+#define HS_W_POLL_HOOK(SRV)                                                                              \
+    do {                                                                                                 \
+        if (E[(SRV)].u.srv.active < E[(SRV)].i0) { const uint64_t i_ = ctr++;                            \
+            HS_W_PUSH(now, i_, HS_EV_POLL, (SRV), 0, 0ull, -1, 0u); }                                    \
+    } while (0)
+
+                        switch (kind) {
+                        case HS_EV_SOURCE_TICK: {          /* Source.handle_event, source.py:142-180 */
+                            const hs_entity_desc d = M.ents[ent];
+                            bool have = false; uint64_t idxP = 0; int32_t key = -1;
+                            if (!(d.l0 >= 0 && now > d.l0)) {
+                                X->u.src.provider++;
+                                idxP = ctr++;
+                                if (d.i1 > 0) {
+                                    const double u = hs_uniform(seed, rid, HS_STREAM_ROUTING | (ent << 8), X->u.src.key_draws++);
+                                    key = (int32_t)HS_D2LL(HS_MUL(u, (double)d.i1));
+                                }
+                                have = true;
+                            }
+                            X->u.src.generated++;
+                            double target = 1.0;
+                            if (X->i0 == HS_ARR_POISSON) {
+                                const double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), X->u.src.arr_draws++);
+                                target = hs_exp1(u);
+                            }
+                            X->u.src.cur_ns = hs_next_arrival_ns(X->u.src.cur_ns, target, X->d0);
+                            const uint64_t idxT = ctr++;
+                            if (have) HS_W_PUSH(now, idxP, HS_W_REQ_KIND(d.target), d.target, now, 0ull, key, 0u);
+                            HS_W_PUSH(X->u.src.cur_ns, idxT, HS_EV_SOURCE_TICK, ent, 0, 0ull, -1, 0u);
+                            break;
+                        }
+                        case HS_EV_REQ_LB: {               /* LoadBalancer._forward_request, :347-433 */
+                            const hs_entity_desc d = M.ents[ent];
+                            X->u.lb.received++;
+                            if (d.i2 > 0) {
+                                int slot;
+                                if (d.i0 == HS_LB_KEY_TABLE && e_key >= 0) slot = M.key_table[e_key];
+                                else { slot = (int)(X->u.lb.rr_index % (uint64_t)d.i2); X->u.lb.rr_index++; }
+                                const int be = M.backends[d.i1 + slot];
+                                X->u.lb.in_flight++; X->u.lb.forwarded++;
+                                const uint64_t i_ = ctr++;
+                                HS_W_PUSH(now, i_, HS_W_REQ_KIND(be), be, e_created, 0ull, e_key, ent + 1u);
+                            }
+                            HS_W_REQUEST_HOOKS();
+                            break;
+                        }
+                        case HS_EV_REQ_ENQUEUE: {          /* Queue._handle_enqueue, queue.py:122-147 */
+                            const hs_entity_desc d = M.ents[ent];
+                            const bool was_empty = (X->u.srv.q_len == 0);
+                            if (d.l0 >= 0 && (int64_t)X->u.srv.q_len >= d.l0) X->u.srv.dropped++;
+                            else if (X->u.srv.q_len >= P.ring) H->status |= HS_ST_QUEUE_OVERFLOW;
+                            else {
+                                hs_wring_entry *rg = ring0 + (size_t)M.srv_index[ent] * P.ring;
+                                hs_wring_entry q; q.created = e_created; q.idx = bi; q.key = e_key;
+                                rg[(X->u.srv.q_head + X->u.srv.q_len) & ring_mask] = q;
+                                X->u.srv.q_len++;
+                                X->u.srv.accepted++;
+                                if (was_empty) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_NOTIFY, ent, 0, 0ull, -1, 0u); }
+                            }
+                            HS_W_REQUEST_HOOKS();          /* _lb_response fires at ENQUEUE time */
+                            break;
+                        }
+                        case HS_EV_NOTIFY:                 /* QueueDriver._handle_notify, :92-99 */
+                            if (X->u.srv.active < X->i0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_POLL, ent, 0, 0ull, -1, 0u); }
+                            break;
+                        case HS_EV_POLL:                   /* Queue._handle_poll, queue.py:149-166 */
+                            if (X->u.srv.q_len > 0) {
+                                hs_wring_entry *rg = ring0 + (size_t)M.srv_index[ent] * P.ring;
+                                hs_wring_entry q;
+                                if (M.ents[ent].i1 == HS_Q_LIFO) q = rg[(X->u.srv.q_head + X->u.srv.q_len - 1) & ring_mask];
+                                else { q = rg[X->u.srv.q_head & ring_mask]; X->u.srv.q_head++; }
+                                X->u.srv.q_len--;
+                                const uint64_t i_ = ctr++;
+                                HS_W_PUSH(now, i_, HS_EV_DELIVER, ent, q.created, q.idx, (int32_t)q.key, 0u);
+                            }
+                            break;
+                        case HS_EV_DELIVER:                /* _handle_work_payload, queue_driver.py:78-90 */
+                            HS_W_PUSH(now, e_aux, HS_EV_REQ_WORKER, ent, e_created, 0ull, e_key, 0x80000000u);
+                            break;
+                        case HS_EV_REQ_WORKER: {           /* Server.handle_queued_event, first step */
+                            ctr++;                         /* inline ProcessContinuation (event.py:314-325) */
+                            if (X->u.srv.active >= X->i0) {
+                                X->u.srv.rejected++; H->status |= HS_ST_REJECT_PATH;
+                                HS_W_POLL_HOOK(ent);
+                                break;
+                            }
+                            X->u.srv.active++;
+                            int64_t dur;
+                            if (M.ents[ent].i2 == HS_SVC_EXPONENTIAL) {
+                                const double u = hs_uniform(seed, rid, HS_STREAM_SERVICE | (ent << 8), X->u.srv.svc_draws++);
+                                dur = hs_exp_latency_ns(u, X->lambda);
+                            } else dur = hs_seconds_to_ns(X->d0);
+                            const double svc_s = hs_ns_to_seconds(dur);
+                            if ((FLAGS & HS_WF_REC) && svc_out) { svc_out[H->svc_pos] = svc_s; H->svc_pos = (H->svc_pos + 1 == P.service_cap) ? 0u : H->svc_pos + 1; }
+                            H->n_svc++;
+                            const uint64_t i_ = ctr++;
+                            HS_W_PUSH(hs_resume_ns(now, svc_s), i_, HS_EV_CONTINUATION, ent, e_created,
+                                      (uint64_t)__double_as_longlong(svc_s), e_key, e_hook & 0x80000000u);
+                            break;
+                        }
+                        case HS_EV_CONTINUATION: {         /* generator resumes, server.py:255-273 */
+                            X->u.srv.active = X->u.srv.active > 0 ? X->u.srv.active - 1 : 0;
+                            X->u.srv.completed++;
+                            X->u.srv.total_service = HS_ADD(X->u.srv.total_service, __longlong_as_double((long long)e_aux));
+                            const int tgt = M.ents[ent].target;
+                            if (tgt >= 0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_W_REQ_KIND(tgt), tgt, e_created, 0ull, e_key, 0u); }
+                            if (e_hook & 0x80000000u) HS_W_POLL_HOOK(ent);
+                            break;
+                        }
+                        case HS_EV_REQ_SINK: {             /* Sink.handle_event, common.py:36-44 */
+                            X->u.snk.received++;
+                            const double lat = hs_ns_to_seconds(now - e_created);
+                            hs_neumaier_add(&X->u.snk.sum, &X->u.snk.comp, lat);
+                            X->u.snk.sumsq = HS_ADD(X->u.snk.sumsq, HS_MUL(lat, lat));
+                            if (lat < X->u.snk.mn) X->u.snk.mn = lat;
+                            if (lat > X->u.snk.mx) X->u.snk.mx = lat;
+                            if ((FLAGS & HS_WF_REC) && smp) { hs_sink_sample q; q.completion_ns = now; q.latency_s = lat; smp[H->smp_pos] = q;
+                                H->smp_pos = (H->smp_pos + 1 == P.sample_cap) ? 0u : H->smp_pos + 1; }
+                            H->n_smp++;
+                            HS_W_REQUEST_HOOKS();
+                            break;
+                        }
+                        case HS_EV_REQ_COUNTER:            /* Counter.handle_event, common.py:92-95 */
+                            X->u.snk.received++;
+                            HS_W_REQUEST_HOOKS();
+                            break;
+                        case HS_EV_LB_RESPONSE:            /* LoadBalancer._handle_response, :435-473 */
+                            if (X->u.lb.in_flight > 0) X->u.lb.in_flight--;
+                            X->u.lb.responses++;
+                            break;
+                        default: break;
+                        }
+                        H->ctr = ctr;
+#undef HS_W_PUSH
+#undef HS_W_REQ_KIND
+#undef HS_W_REQUEST_HOOKS
+#undef HS_W_POLL_HOOK
+                    }
+                }
+            }
+            go = __shfl_sync(0xffffffffu, go, 0);
+            __syncwarp();
+            if (go == 2) paused = true;
+            if (go != 1) break;
+        }
+
+        /* ---- publish + write the block back -------------------------------- */
+        if (lane == 0) {
+            H->done = paused ? 0 : 1;
+            if (O.summaries) {
+                hs_replica_summary s;
+                s.events_processed = H->processed; s.final_time_ns = H->now;
+                s.order_hash = (FLAGS & HS_WF_HASH) ? H->hash : 0ull;
+                s.next_sort_index = H->ctr; s.n_sink_samples = H->n_smp; s.n_service_samples = H->n_svc;
+                s.heap_left = H->fel_n; s.status = H->status;
+                O.summaries[r] = s;
+            }
+        }
+        __syncwarp();
+        if (O.stats) {
+            for (uint32_t i = lane; i < ne; i += 32) {
+                const hs_went *e = &E[i];
+                hs_entity_stats a; a.c0 = a.c1 = a.c2 = a.c3 = 0; a.f0 = a.f1 = a.f2 = a.f3 = 0.0;
+                switch (M.ents[i].kind) {
+                case HS_ENT_SOURCE: a.c0 = e->u.src.generated; a.c1 = e->u.src.provider; break;
+                case HS_ENT_SERVER: a.c0 = e->u.srv.accepted; a.c1 = e->u.srv.dropped; a.c2 = e->u.srv.completed;
+                    a.c3 = e->u.srv.rejected; a.f0 = e->u.srv.total_service; break;
+                case HS_ENT_SINK: a.c0 = e->u.snk.received; a.f0 = hs_neumaier_result(e->u.snk.sum, e->u.snk.comp);
+                    a.f1 = e->u.snk.sumsq; a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
+                case HS_ENT_COUNTER: a.c0 = e->u.snk.received; break;
+                case HS_ENT_LB: a.c0 = e->u.lb.received; a.c1 = e->u.lb.forwarded; a.c2 = e->u.lb.in_flight;
+                    a.c3 = e->u.lb.responses; break;
+                }
+                O.stats[(size_t)r * ne + i] = a;
+            }
+        }
+        hs_fence_async_smem();
+        __syncwarp();
+        if (lane == 0) hs_tma_store_1d(gblk, blk, M.block_bytes);
+        __syncwarp();
+    }
+}
+
+#endif /* HS_WARP_ENGINE_CUH */

@@ -246,7 +246,8 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
         CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
         return 0;
     };
-    if (want_rec) rc = launch(hs_warp_kernel<HS_WF_HASH | HS_WF_REC>);
+    if (want_rec && want_hash) rc = launch(hs_warp_kernel<HS_WF_HASH | HS_WF_REC>);
+    else if (want_rec) rc = launch(hs_warp_kernel<HS_WF_REC>);
     else if (want_hash) rc = launch(hs_warp_kernel<HS_WF_HASH>);
     else rc = launch(hs_warp_kernel<0>);
     if (rc) return rc;
@@ -409,12 +410,13 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         O.records = p->record_cap ? (hs_event_record *)E->d_rec.p : nullptr;
         O.samples = p->sample_cap ? (hs_sink_sample *)E->d_smp.p : nullptr;
         O.service = p->service_cap ? (double *)E->d_svc.p : nullptr;
-        const int threads = 64;
+        const int threads = HS_LANE_THREADS;
         const int blocks = (int)((n + threads - 1) / threads);
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
         hs_lane_state *st = (hs_lane_state *)E->d_state.p;
         hs_ring_entry *rg = (hs_ring_entry *)E->d_rings.p;
-        if (want_rec) hs_lane_kernel<HS_LF_HASH | HS_LF_REC><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
+        if (want_rec && want_hash) hs_lane_kernel<HS_LF_HASH | HS_LF_REC><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
+        else if (want_rec) hs_lane_kernel<HS_LF_REC><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
         else if (want_hash) hs_lane_kernel<HS_LF_HASH><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
         else hs_lane_kernel<0><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
         CUDA_TRY(cudaGetLastError());

@@ -27,6 +27,30 @@
  *     same counters, indices, hash and records.
  * Same-nanosecond ties fall back to generic_step().
  *
+ * Random draws.  Every draw is a pure function of (seed, replica, stream, draw
+ * index), so the expensive part of a draw -- Philox block, log, the IEEE
+ * divisions of arrival_time_provider.py:77 and exponential.py:43-45 -- does not
+ * depend on simulation state and is computed AHEAD of its use, in warp-converged
+ * "refill rounds": whenever any lane of the warp has run out of arrival or
+ * service draws, all 32 lanes generate their next Philox pair of each stream
+ * (four independent log/divide chains per lane: full lane utilisation and
+ * instruction-level parallelism) into per-lane ring buffers in shared memory
+ * ([slot][lane] layout: conflict-free whatever slot each lane is at).  The
+ * divergent event loop then only pops a precomputed value:
+ *     arrival  A_k = Instant.from_seconds(A_{k-1} / 1e9 + target_k / rate), the k-th
+ *              SourceEvent time itself: the arrival process of a Source does not
+ *              depend on anything downstream (arrival_time_provider.py:66-82)
+ *     service  (svc_s, delta_ns) = (to_seconds(dur), int(svc_s * 1e9))
+ * which is bit-identical to drawing at the point of use because the reference
+ * consumes each stream strictly in draw-index order.
+ *
+ * Queue.  Items wait in a per-replica ring in HBM; the item the next POLL will
+ * deliver (FIFO head / LIFO tail) is also kept in registers and re-loaded right
+ * after every pop, one whole service time before it is needed, so the ring load
+ * latency is off the critical path.  Recorder streams (event records, Sink and
+ * service samples) are written with streaming stores (st.global.cs) so they do
+ * not evict the queue rings from L2.
+ *
  * Reference handlers restated (paths under /root/reference/happysimulator):
  *   load/source.py:142-180, load/arrival_time_provider.py:66-82,
  *   components/queue.py:122-166, components/queue_driver.py:66-99,
@@ -40,6 +64,8 @@
 #include "../../include/hs_b200.h"
 
 #define HS_NOW_CAP 8
+#define HS_LANE_THREADS 64
+#define HS_DRAW_BUF 16    /* precomputed draws per stream per lane (even) */
 #define HS_LF_HASH 1      /* maintain the order hash                         */
 #define HS_LF_REC 2       /* write event records / sink / service samples    */
 
@@ -64,7 +90,7 @@ struct __align__(16) hs_lane_state {   /* persisted between windows (512 B)  */
     int64_t received; double sum, sumsq, mn, mx;
     uint32_t q_head, q_len; int32_t active; uint32_t status;
     int64_t n_smp, n_svc; int32_t now_n; int32_t has_c;
-    int32_t done; uint32_t rec_pos; double comp; uint32_t smp_pos, svc_pos; int64_t pad1;
+    int32_t done; uint32_t rec_pos; double comp; uint32_t smp_pos, svc_pos; int64_t skipped;
     hs_now_ev nowq[HS_NOW_CAP];
 };
 
@@ -94,13 +120,27 @@ struct hs_lane_out {
     double *service;
 };
 
+/* next arrival of a constant-rate profile, with the reference's "time travel" outcome
+ * folded in: if the computed time is earlier than the current one the SourceEvent would be
+ * popped and skipped and the Source never ticks again (INT64_MAX). */
+__device__ __forceinline__ int64_t hs_lane_next_arrival(int64_t t, double target, double rate)
+{
+    const int64_t n = hs_next_arrival_ns(t, target, rate);
+    return n < t ? INT64_MAX : n;
+}
+
 template <int FLAGS>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(HS_LANE_THREADS, 7)
 hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ states,
                hs_ring_entry *__restrict__ rings, hs_lane_out O)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= P.n_replicas) return;
+    __shared__ int64_t sh_t[HS_DRAW_BUF][HS_LANE_THREADS];       /* arrival times A_k (ns)          */
+    __shared__ double sh_svc[HS_DRAW_BUF][HS_LANE_THREADS];      /* service: Duration.to_seconds()  */
+    __shared__ int64_t sh_delta[HS_DRAW_BUF][HS_LANE_THREADS];   /* service: int(svc_s * 1e9)       */
+    const uint32_t tid = threadIdx.x;
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = r < P.n_replicas;
+    if (!valid) r = P.n_replicas - 1;      /* idle lane of the last warp: votes only, stores nothing */
 
     const uint32_t gidx = P.index_base + r;
     const uint64_t seed = P.seed + (uint64_t)gidx * P.seed_stride;
@@ -114,8 +154,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         rate = M.cell_d0[(size_t)cell * M.n_entities + M.src_id];
         mean = M.cell_d0[(size_t)cell * M.n_entities + M.srv_id];
     }
-    const double lambda = HS_DIV(1.0, mean);          /* exponential.py:36 */
-    const int64_t const_dur_ns = hs_seconds_to_ns(mean); /* constant.py:33-35 */
+    const double lambda = HS_DIV(1.0, mean);             /* exponential.py:36 */
     const bool poisson = (M.arr_kind == HS_ARR_POISSON);
     const bool expo = (M.svc_kind == HS_SVC_EXPONENTIAL);
     const bool lifo = (M.policy == HS_Q_LIFO);
@@ -130,80 +169,103 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     double *svc_out = (FLAGS & HS_LF_REC) && O.service ? O.service + (size_t)r * P.service_cap : nullptr;
 
     /* ---- replica state (registers; nowq in local memory, cold) ---------- */
-    int64_t now, processed, tT, tC, c_created, gen_count, prov_count;
-    uint64_t ctr, hash, iT, iC, arr_draws, svc_draws;
-    int64_t accepted, dropped, completed, rejected, received;
+    int64_t now, processed, tT, tC, c_created;
+    uint64_t ctr, hash, iT, iC, arr_draws;
+    int64_t accepted, dropped, n_svc;
     double svc_s, total_service, sum, comp, sumsq, mn, mx;
     uint32_t q_head, q_len, status, rec_pos, smp_pos, svc_pos;
-    int64_t n_smp, n_svc;
     int32_t active, now_n, has_c;
+    int64_t h_created = 0; uint64_t h_idx = 0;      /* the item the next POLL delivers */
     hs_now_ev nowq[HS_NOW_CAP];
-    double arr_cache = 0.0, svc_cache = 0.0;
 
     hs_lane_state *S = states + r;
+    bool finished = !valid;
     if (P.resume) {
-        if (S->done) return;
+        if (S->done) finished = true;
         now = S->now; ctr = S->ctr; processed = S->processed; hash = S->hash;
-        tT = S->tT; iT = S->iT; arr_draws = S->arr_draws; gen_count = S->gen_count; prov_count = S->prov_count;
+        tT = S->tT; iT = S->iT; arr_draws = S->arr_draws;
         tC = S->tC; iC = S->iC; svc_s = S->svc_s; c_created = S->c_created;
-        svc_draws = S->svc_draws; accepted = S->accepted; dropped = S->dropped; completed = S->completed;
-        rejected = S->rejected; total_service = S->total_service;
-        received = S->received; sum = S->sum; comp = S->comp; sumsq = S->sumsq; mn = S->mn; mx = S->mx;
+        n_svc = S->n_svc; accepted = S->accepted; dropped = S->dropped;
+        total_service = S->total_service;
+        sum = S->sum; comp = S->comp; sumsq = S->sumsq; mn = S->mn; mx = S->mx;
         q_head = S->q_head; q_len = S->q_len; active = S->active; status = S->status;
-        n_smp = S->n_smp; n_svc = S->n_svc; now_n = S->now_n; has_c = S->has_c;
+        now_n = S->now_n; has_c = S->has_c;
         rec_pos = S->rec_pos; smp_pos = S->smp_pos; svc_pos = S->svc_pos;
         for (int i = 0; i < HS_NOW_CAP; ++i) nowq[i] = S->nowq[i];
-        double u0, u1;
-        if (arr_draws & 1) { hs_uniform_pair(seed, rid, sid_arr, arr_draws >> 1, &u0, &u1); arr_cache = u1; }
-        if (svc_draws & 1) { hs_uniform_pair(seed, rid, sid_svc, svc_draws >> 1, &u0, &u1); svc_cache = u1; }
+        if (q_len > 0) {
+            const hs_ring_entry e = ring[(lifo ? q_head + q_len - 1 : q_head) & ring_mask];
+            h_created = e.created; h_idx = e.idx;
+        }
     } else {
-        now = 0; processed = 0; hash = HS_HASH_INIT;
-        arr_draws = 0; svc_draws = 0; gen_count = 0; prov_count = 0;
-        tC = 0; iC = 0; svc_s = 0.0; c_created = 0;
-        accepted = dropped = completed = rejected = received = 0;
+        now = 0; processed = 0; hash = HS_HASH_INIT; ctr = 0;
+        arr_draws = 0; n_svc = 0;
+        tT = 0; iT = 0; tC = 0; iC = 0; svc_s = 0.0; c_created = 0;
+        accepted = dropped = 0;
         total_service = 0.0; sum = 0.0; comp = 0.0; sumsq = 0.0;
         mn = __longlong_as_double(0x7ff0000000000000LL); mx = __longlong_as_double(0xfff0000000000000LL);
-        q_head = 0; q_len = 0; active = 0; status = 0; n_smp = 0; n_svc = 0; now_n = 0; has_c = 0;
+        q_head = 0; q_len = 0; active = 0; status = 0; now_n = 0; has_c = 0;
         rec_pos = 0; smp_pos = 0; svc_pos = 0;
+        if (valid) { S->rejected = 0; S->skipped = 0; }   /* cold counters, kept in the state block */
         for (int i = 0; i < HS_NOW_CAP; ++i) { nowq[i].idx = 0; nowq[i].created = 0; nowq[i].payload_idx = 0; nowq[i].kind = 0; nowq[i].pad = 0; }
-        /* Simulation.__init__: source.start() draws the first arrival and the
-         * SourceEvent takes index 0 of the GLOBAL counter (simulation.py:77,145-154);
-         * run() then restarts the per-heap counter at 0 (event_heap.py:48).        */
-        double target = 1.0;
-        if (poisson) {
-            double u0, u1; hs_uniform_pair(seed, rid, sid_arr, 0, &u0, &u1);
-            arr_cache = u1; arr_draws = 1; target = hs_exp1(u0);
-        }
-        tT = hs_next_arrival_ns(0, target, rate);
-        iT = 0; ctr = 0;
     }
+    /* Generation cursors.  a_gen = arrival draws generated so far and t_gen = A_{a_gen}, the
+     * provider's current_time after them; the pending SourceEvent is A_{arr_draws} = tT.
+     * s_gen = service draws generated; service start number n_svc consumes draw n_svc.
+     * After a pause the cursors restart at the consumed positions (a half-used Philox pair
+     * is regenerated and its first half skipped). */
+    uint64_t a_gen = arr_draws, s_gen = (uint64_t)n_svc;
+    int64_t t_gen = P.resume ? tT : 0;
 
-#define HS_EMIT(KIND, IDX, ENT)                                                              \
+    /* next arrival time from t (arrival_time_provider.py:66-82); a result < t would be
+     * popped and skipped as "time travel" by the loop (simulation.py:479-489), after which the
+     * Source never ticks again: INT64_MAX marks that dead source. */
+#define HS_NEXT_ARRIVAL(T, TARGET)                                                           \
+    ((T) == INT64_MAX ? INT64_MAX : hs_lane_next_arrival((T), (TARGET), rate))
+
+    /* one converged refill round: each lane that has room generates the next Philox
+     * pair of each stream and stores the precomputed draws */
+#define HS_REFILL_ROUND()                                                                    \
+    do {                                                                                     \
+        if (!finished && (uint32_t)(a_gen - arr_draws) + 2u <= HS_DRAW_BUF) {                \
+            double u0_ = 0.0, u1_ = 0.0;                                                     \
+            if (poisson) hs_uniform_pair(seed, rid, sid_arr, a_gen >> 1, &u0_, &u1_);        \
+            if (!(a_gen & 1)) {                                                              \
+                t_gen = HS_NEXT_ARRIVAL(t_gen, poisson ? hs_exp1(u0_) : 1.0); a_gen++;       \
+                sh_t[a_gen % HS_DRAW_BUF][tid] = t_gen;                                      \
+            }                                                                                \
+            t_gen = HS_NEXT_ARRIVAL(t_gen, poisson ? hs_exp1(u1_) : 1.0); a_gen++;           \
+            sh_t[a_gen % HS_DRAW_BUF][tid] = t_gen;                                          \
+        }                                                                                    \
+        if (!finished && (uint32_t)(s_gen - (uint64_t)n_svc) + 2u <= HS_DRAW_BUF) {          \
+            double u0_ = 0.0, u1_ = 0.0;                                                     \
+            if (expo) hs_uniform_pair(seed, rid, sid_svc, s_gen >> 1, &u0_, &u1_);           \
+            if (!(s_gen & 1)) {                                                              \
+                const double s0_ = hs_ns_to_seconds(expo ? hs_exp_latency_ns(u0_, lambda) : hs_seconds_to_ns(mean)); \
+                sh_svc[s_gen % HS_DRAW_BUF][tid] = s0_; sh_delta[s_gen % HS_DRAW_BUF][tid] = hs_seconds_to_ns(s0_); \
+                s_gen++;                                                                     \
+            }                                                                                \
+            const double s1_ = hs_ns_to_seconds(expo ? hs_exp_latency_ns(u1_, lambda) : hs_seconds_to_ns(mean));     \
+            sh_svc[s_gen % HS_DRAW_BUF][tid] = s1_; sh_delta[s_gen % HS_DRAW_BUF][tid] = hs_seconds_to_ns(s1_);     \
+            s_gen++;                                                                         \
+        }                                                                                    \
+    } while (0)
+
+#define HS_RECORD(KIND, IDX, ENT)                                                            \
     do {                                                                                     \
         if (FLAGS & HS_LF_HASH) hash = hs_hash_step(hash, now, hs_record_word1((IDX), (KIND), (uint32_t)(ENT))); \
         if ((FLAGS & HS_LF_REC) && rec) {                                                    \
-            hs_event_record rc_; rc_.time_ns = now; rc_.sort_index = (uint32_t)(IDX);        \
-            rc_.kind = (uint8_t)(KIND); rc_.pad = 0; rc_.entity = (uint16_t)(ENT);           \
-            rec[rec_pos] = rc_; rec_pos = (rec_pos + 1 == P.record_cap) ? 0u : rec_pos + 1;  \
+            uint4 w_;                                                                        \
+            w_.x = (uint32_t)(uint64_t)now; w_.y = (uint32_t)((uint64_t)now >> 32);          \
+            w_.z = (uint32_t)(IDX); w_.w = (uint32_t)(KIND) | ((uint32_t)(ENT) << 16);       \
+            __stcs((uint4 *)(rec + rec_pos), w_);                                            \
+            rec_pos = (rec_pos + 1 == P.record_cap) ? 0u : rec_pos + 1;                      \
         }                                                                                    \
-        processed++;                                                                         \
     } while (0)
+#define HS_EMIT(KIND, IDX, ENT) do { HS_RECORD(KIND, IDX, ENT); processed++; } while (0)
 
-#define HS_DRAW(U, SID, N, CACHE)                                                            \
-    do {                                                                                     \
-        if ((N) & 1) { (U) = (CACHE); }                                                      \
-        else { double u1_; hs_uniform_pair(seed, rid, (SID), (N) >> 1, &(U), &u1_); (CACHE) = u1_; } \
-        (N)++;                                                                               \
-    } while (0)
-
-    /* Source.handle_event's arrival part: next SourceEvent time (source.py:166-170). */
+    /* Source.handle_event's arrival part: the next SourceEvent (source.py:166-170) */
 #define HS_NEXT_TICK()                                                                       \
-    do {                                                                                     \
-        double target_ = 1.0;                                                                \
-        if (poisson) { double u_; HS_DRAW(u_, sid_arr, arr_draws, arr_cache); target_ = hs_exp1(u_); } \
-        tT = hs_next_arrival_ns(tT, target_, rate);                                          \
-        iT = ctr++;                                                                          \
-    } while (0)
+    do { arr_draws++; tT = sh_t[arr_draws % HS_DRAW_BUF][tid]; iT = ctr++; } while (0)
 
     /* Server.handle_queued_event up to its yield, for the payload (CREATED):
      * inline ProcessContinuation index, acquire (the caller has checked
@@ -211,29 +273,47 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
      * (server.py:217-253, event.py:314-325,499-508).                            */
 #define HS_SERVICE_START(CREATED)                                                            \
     do {                                                                                     \
-        ctr++;                                                                               \
-        active++;                                                                            \
-        int64_t dur_;                                                                        \
-        if (expo) { double u_; HS_DRAW(u_, sid_svc, svc_draws, svc_cache); dur_ = hs_exp_latency_ns(u_, lambda); } \
-        else dur_ = const_dur_ns;                                                            \
-        svc_s = hs_ns_to_seconds(dur_);                                                      \
-        if ((FLAGS & HS_LF_REC) && svc_out) { svc_out[svc_pos] = svc_s; svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
+        const uint32_t k_ = (uint32_t)((uint64_t)n_svc % HS_DRAW_BUF);                       \
+        svc_s = sh_svc[k_][tid];                                                             \
+        const int64_t delta_ = sh_delta[k_][tid];                                            \
+        if ((FLAGS & HS_LF_REC) && svc_out) { __stcs(svc_out + svc_pos, svc_s); svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
         n_svc++;                                                                             \
-        tC = hs_resume_ns(now, svc_s); iC = ctr++; c_created = (CREATED); has_c = 1;         \
+        active++;                                                                            \
+        tC = now + delta_; iC = ctr + 1; ctr += 2; c_created = (CREATED); has_c = 1;         \
     } while (0)
 
 #define HS_SINK(CREATED)                                                                     \
     do {                                                                                     \
-        received++;                                                                          \
         if (M.dst_kind == HS_ENT_SINK) {                                                     \
-            double lat_ = hs_ns_to_seconds(now - (CREATED));                                 \
-            hs_neumaier_add(&sum, &comp, lat_); sumsq = HS_ADD(sumsq, HS_MUL(lat_, lat_));              \
+            const double lat_ = hs_ns_to_seconds(now - (CREATED));                           \
+            hs_neumaier_add(&sum, &comp, lat_); sumsq = HS_ADD(sumsq, HS_MUL(lat_, lat_));   \
             if (lat_ < mn) mn = lat_;                                                        \
             if (lat_ > mx) mx = lat_;                                                        \
-            if ((FLAGS & HS_LF_REC) && smp) { hs_sink_sample q_; q_.completion_ns = now; q_.latency_s = lat_; smp[smp_pos] = q_; \
+            if ((FLAGS & HS_LF_REC) && smp) {                                                \
+                uint4 w_; const uint64_t lb_ = (uint64_t)__double_as_longlong(lat_);         \
+                w_.x = (uint32_t)(uint64_t)now; w_.y = (uint32_t)((uint64_t)now >> 32);      \
+                w_.z = (uint32_t)lb_; w_.w = (uint32_t)(lb_ >> 32);                          \
+                __stcs((uint4 *)(smp + smp_pos), w_);                                        \
                 smp_pos = (smp_pos + 1 == P.sample_cap) ? 0u : smp_pos + 1; }                \
-            n_smp++;                                                                         \
         }                                                                                    \
+    } while (0)
+
+    /* FIFOQueue / LIFOQueue (queue_policy.py:75-156) on the HBM ring + the register copy
+     * of the next item to be delivered */
+#define HS_Q_PUSH(CREATED, IDX)                                                              \
+    do {                                                                                     \
+        hs_ring_entry e_; e_.created = (CREATED); e_.idx = (IDX);                            \
+        ring[(q_head + q_len) & ring_mask] = e_;                                             \
+        if (lifo || q_len == 0) { h_created = (CREATED); h_idx = (IDX); }                    \
+        q_len++;                                                                             \
+    } while (0)
+#define HS_Q_POP(CREATED, IDX)                                                               \
+    do {                                                                                     \
+        (CREATED) = h_created; (IDX) = h_idx;                                                \
+        if (!lifo) q_head++;                                                                 \
+        q_len--;                                                                             \
+        if (q_len > 0) { const hs_ring_entry n_ = ring[(lifo ? q_head + q_len - 1 : q_head) & ring_mask]; \
+                         h_created = n_.created; h_idx = n_.idx; }                           \
     } while (0)
 
 #define HS_PUSH_NOW(KIND, IDX, CREATED, PIDX)                                                \
@@ -243,16 +323,34 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                nowq[now_n].kind = (KIND); now_n++; }                                         \
     } while (0)
 
+    /* ---- fill the draw buffers, then bootstrap --------------------------- */
+#pragma unroll 1
+    for (int k = 0; k < HS_DRAW_BUF / 2; ++k) HS_REFILL_ROUND();
+    if (!P.resume && !finished) {
+        /* Simulation.__init__: source.start() draws the first arrival and the
+         * SourceEvent takes index 0 of the GLOBAL counter (simulation.py:77,145-154);
+         * run() then restarts the per-heap counter at 0 (event_heap.py:48).        */
+        arr_draws = 1; tT = sh_t[1][tid];
+        iT = 0; ctr = 0;
+    }
+
     bool paused = false;
     while (true) {
-        if (!(now <= P.end_ns)) break;                 /* simulation.py:472 */
-        if (status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW)) break;
+        /* converged top of the loop: vote on termination and on refilling */
+        const bool need = !finished && (a_gen == arr_draws || s_gen == (uint64_t)n_svc);
+        const unsigned todo = __ballot_sync(0xffffffffu, !finished);
+        if (todo == 0u) break;
+        if (__any_sync(0xffffffffu, need)) HS_REFILL_ROUND();
+        if (finished) continue;
 
-        if (now_n == 0 && tT == INT64_MAX && !has_c) break;      /* heap exhausted */
+        if (!(now <= P.end_ns)) { finished = true; continue; }                 /* simulation.py:472 */
+        if (status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW)) { finished = true; continue; }
+        if (now_n == 0 && tT == INT64_MAX && !has_c) { finished = true; continue; }   /* heap exhausted */
+
         if (now_n == 0) {
             const bool pickC = has_c && (tC < tT || (tC == tT && iC < iT));
             const int64_t tn = pickC ? tC : tT;
-            if (windowed && tn > P.window_end_ns) { paused = true; break; }
+            if (windowed && tn > P.window_end_ns) { paused = true; finished = true; continue; }
             const bool slow = (has_c && tC == tT) || (tn > P.end_ns) || (tn < now);
             if (!slow) {
                 now = tn;
@@ -261,8 +359,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     HS_EMIT(HS_EV_SOURCE_TICK, iT, M.src_id);
                     const bool payload = !(M.stop_after >= 0 && now > M.stop_after);  /* source.py:68 */
                     uint64_t idxP = 0;
-                    if (payload) { prov_count++; idxP = ctr++; }
-                    gen_count++;
+                    if (payload) idxP = ctr++; else S->skipped++;
                     HS_NEXT_TICK();
                     if (!payload) continue;
                     if (tT <= now) {          /* zero inter-arrival: the new tick ties with the chain */
@@ -277,8 +374,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     accepted++;
                     if (!was_empty || active >= 1) {
                         /* request waits in the buffer */
-                        hs_ring_entry e; e.created = now; e.idx = idxP;
-                        ring[(q_head + q_len) & ring_mask] = e; q_len++;
+                        HS_Q_PUSH(now, idxP);
                         if (was_empty) {      /* notify, but the worker is busy: no poll (queue_driver.py:92-96) */
                             uint64_t idxN = ctr++;
                             HS_EMIT(HS_EV_NOTIFY, idxN, M.srv_id);
@@ -287,10 +383,11 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     }
                     /* buffer was empty and the worker is idle: NOTIFY -> POLL -> DELIVER -> WORKER;
                      * the item is pushed and popped again at once (FIFO and LIFO agree).          */
-                    { uint64_t i_ = ctr++; HS_EMIT(HS_EV_NOTIFY, i_, M.srv_id); }
-                    { uint64_t i_ = ctr++; HS_EMIT(HS_EV_POLL, i_, M.srv_id); }
-                    { uint64_t i_ = ctr++; HS_EMIT(HS_EV_DELIVER, i_, M.srv_id); }
-                    HS_EMIT(HS_EV_REQ_WORKER, idxP, M.srv_id);
+                    HS_RECORD(HS_EV_NOTIFY, ctr, M.srv_id);
+                    HS_RECORD(HS_EV_POLL, ctr + 1, M.srv_id);
+                    HS_RECORD(HS_EV_DELIVER, ctr + 2, M.srv_id);
+                    HS_RECORD(HS_EV_REQ_WORKER, idxP, M.srv_id);
+                    ctr += 3; processed += 4;
                     HS_SERVICE_START(now);
                     continue;
                 } else {
@@ -298,7 +395,6 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     HS_EMIT(HS_EV_CONTINUATION, iC, M.srv_id);
                     has_c = 0;
                     active = active > 0 ? active - 1 : 0;      /* FixedConcurrency.release */
-                    completed++;
                     total_service = HS_ADD(total_service, svc_s);
                     uint64_t idxF = 0;
                     if (M.dst_id >= 0) idxF = ctr++;           /* Entity.forward */
@@ -308,13 +404,12 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     if (!poll) continue;
                     HS_EMIT(HS_EV_POLL, idxPoll, M.srv_id);
                     if (q_len == 0) continue;                  /* Queue._handle_poll: empty */
-                    hs_ring_entry it;
-                    if (lifo) { it = ring[(q_head + q_len - 1) & ring_mask]; }
-                    else { it = ring[q_head & ring_mask]; q_head++; }
-                    q_len--;
-                    { uint64_t i_ = ctr++; HS_EMIT(HS_EV_DELIVER, i_, M.srv_id); }
-                    HS_EMIT(HS_EV_REQ_WORKER, it.idx, M.srv_id);
-                    HS_SERVICE_START(it.created);
+                    int64_t it_created; uint64_t it_idx;
+                    HS_Q_POP(it_created, it_idx);
+                    HS_RECORD(HS_EV_DELIVER, ctr, M.srv_id);
+                    HS_RECORD(HS_EV_REQ_WORKER, it_idx, M.srv_id);
+                    ctr += 1; processed += 2;
+                    HS_SERVICE_START(it_created);
                     continue;
                 }
             }
@@ -329,7 +424,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             for (int i = 0; i < now_n; ++i) {
                 if (now < bt || (now == bt && nowq[i].idx < bi)) { which = i; bt = now; bi = nowq[i].idx; }
             }
-            if (windowed && bt > P.window_end_ns) { paused = true; break; }
+            if (windowed && bt > P.window_end_ns) { paused = true; finished = true; continue; }
             if (bt < now) {                 /* "time travel": popped and skipped, not processed
                                                (simulation.py:479-489); only a SourceEvent can do it */
                 tT = INT64_MAX; continue;
@@ -347,8 +442,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 HS_EMIT(HS_EV_SOURCE_TICK, bi, M.src_id);
                 const bool payload = !(M.stop_after >= 0 && now > M.stop_after);
                 uint64_t idxP = 0;
-                if (payload) { prov_count++; idxP = ctr++; }
-                gen_count++;
+                if (payload) idxP = ctr++; else S->skipped++;
                 HS_NEXT_TICK();
                 if (payload) HS_PUSH_NOW(HS_EV_REQ_ENQUEUE, idxP, now, 0);
                 break;
@@ -358,8 +452,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 const bool was_empty = (q_len == 0);
                 if (cap >= 0 && (int64_t)q_len >= cap) { dropped++; break; }
                 if (q_len >= P.ring) { status |= HS_ST_QUEUE_OVERFLOW; break; }
-                hs_ring_entry e; e.created = e_created; e.idx = bi;
-                ring[(q_head + q_len) & ring_mask] = e; q_len++;
+                HS_Q_PUSH(e_created, bi);
                 accepted++;
                 if (was_empty) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_NOTIFY, i_, 0, 0); }
                 break;
@@ -371,12 +464,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             case HS_EV_POLL:
                 HS_EMIT(HS_EV_POLL, bi, M.srv_id);
                 if (q_len > 0) {
-                    hs_ring_entry it;
-                    if (lifo) { it = ring[(q_head + q_len - 1) & ring_mask]; }
-                    else { it = ring[q_head & ring_mask]; q_head++; }
-                    q_len--;
+                    int64_t it_created; uint64_t it_idx;
+                    HS_Q_POP(it_created, it_idx);
                     uint64_t i_ = ctr++;
-                    HS_PUSH_NOW(HS_EV_DELIVER, i_, it.created, it.idx);
+                    HS_PUSH_NOW(HS_EV_DELIVER, i_, it_created, it_idx);
                 }
                 break;
             case HS_EV_DELIVER:
@@ -386,7 +477,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             case HS_EV_REQ_WORKER:
                 HS_EMIT(HS_EV_REQ_WORKER, bi, M.srv_id);
                 if (active >= 1) {          /* acquire failed (server.py:223-234): hooks still run */
-                    ctr++; rejected++; status |= HS_ST_REJECT_PATH;
+                    ctr++; S->rejected++; status |= HS_ST_REJECT_PATH;
                     if (active < 1) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
                 } else {
                     HS_SERVICE_START(e_created);
@@ -396,7 +487,6 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 HS_EMIT(HS_EV_CONTINUATION, bi, M.srv_id);
                 has_c = 0;
                 active = active > 0 ? active - 1 : 0;
-                completed++;
                 total_service = HS_ADD(total_service, svc_s);
                 if (M.dst_id >= 0) { uint64_t i_ = ctr++; HS_PUSH_NOW(dst_ev, i_, c_created, 0); }
                 if (active < 1) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
@@ -412,15 +502,27 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         }
     }
 
+    if (!valid) return;
+    if (P.resume && S->done) return;        /* finished in an earlier window: outputs already final */
+
     /* ---- persist / publish --------------------------------------------- */
+    /* derived counters: a tick is processed per consumed arrival time except the pending one;
+     * every started service completes exactly once; a completion that forwards downstream is
+     * counted by the Sink/Counter once its (same-timestamp) event has been processed. */
+    const int64_t gen_count = (int64_t)arr_draws - 1;
+    const int64_t skipped = S->skipped;
+    const int64_t completed = n_svc - active;
+    const int64_t rejected = S->rejected;
+    int64_t received = (M.dst_id >= 0) ? completed : 0;
+    for (int i = 0; i < now_n; ++i) if (nowq[i].kind == dst_ev) received--;
     S->now = now; S->ctr = ctr; S->processed = processed; S->hash = hash;
-    S->tT = tT; S->iT = iT; S->arr_draws = arr_draws; S->gen_count = gen_count; S->prov_count = prov_count;
+    S->tT = tT; S->iT = iT; S->arr_draws = arr_draws; S->gen_count = gen_count; S->prov_count = gen_count - skipped;
     S->tC = tC; S->iC = iC; S->svc_s = svc_s; S->c_created = c_created;
-    S->svc_draws = svc_draws; S->accepted = accepted; S->dropped = dropped; S->completed = completed;
-    S->rejected = rejected; S->total_service = total_service;
+    S->svc_draws = (uint64_t)n_svc; S->accepted = accepted; S->dropped = dropped; S->completed = completed;
+    S->total_service = total_service;
     S->received = received; S->sum = sum; S->comp = comp; S->sumsq = sumsq; S->mn = mn; S->mx = mx;
     S->q_head = q_head; S->q_len = q_len; S->active = active; S->status = status;
-    S->n_smp = n_smp; S->n_svc = n_svc; S->now_n = now_n; S->has_c = has_c;
+    S->n_smp = received; S->n_svc = n_svc; S->now_n = now_n; S->has_c = has_c;
     S->rec_pos = rec_pos; S->smp_pos = smp_pos; S->svc_pos = svc_pos;
     S->done = paused ? 0 : 1;
     for (int i = 0; i < HS_NOW_CAP; ++i) S->nowq[i] = nowq[i];
@@ -429,12 +531,13 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         hs_replica_summary s;
         s.events_processed = processed; s.final_time_ns = now;
         s.order_hash = (FLAGS & HS_LF_HASH) ? hash : 0ULL;
-        s.next_sort_index = ctr; s.n_sink_samples = n_smp; s.n_service_samples = n_svc; s.heap_left = (tT != INT64_MAX) + has_c + now_n; s.status = status;
+        s.next_sort_index = ctr; s.n_sink_samples = (M.dst_kind == HS_ENT_SINK) ? received : 0; s.n_service_samples = n_svc;
+        s.heap_left = (tT != INT64_MAX) + has_c + now_n; s.status = status;
         O.summaries[r] = s;
     }
     if (O.stats) {
         hs_entity_stats *st = O.stats + (size_t)r * M.n_entities;
-        hs_entity_stats a; a.c0 = gen_count; a.c1 = prov_count; a.c2 = 0; a.c3 = 0; a.f0 = a.f1 = a.f2 = a.f3 = 0.0;
+        hs_entity_stats a; a.c0 = gen_count; a.c1 = gen_count - skipped; a.c2 = 0; a.c3 = 0; a.f0 = a.f1 = a.f2 = a.f3 = 0.0;
         st[M.src_id] = a;
         a.c0 = accepted; a.c1 = dropped; a.c2 = completed; a.c3 = rejected; a.f0 = total_service;
         st[M.srv_id] = a;
@@ -446,10 +549,14 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         }
     }
 #undef HS_EMIT
-#undef HS_DRAW
+#undef HS_RECORD
+#undef HS_REFILL_ROUND
+#undef HS_NEXT_ARRIVAL
 #undef HS_NEXT_TICK
 #undef HS_SERVICE_START
 #undef HS_SINK
+#undef HS_Q_PUSH
+#undef HS_Q_POP
 #undef HS_PUSH_NOW
 }
 

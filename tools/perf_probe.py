@@ -19,7 +19,7 @@ def probe(name, model, n, end_s, flags=0, reps=3, **kw):
     ev = int(out["summaries"]["events_processed"].sum())
     bad = int((out["summaries"]["status"] != 0).sum())
     print(f"{name:28s} n={n:7d} end={end_s:8.0f}s flags={flags} events={ev:.3e} best={best:9.3f} ms  "
-          f"{ev / best / 1e3 / 1e6:9.2f} Mev/s  flagged={bad}", flush=True)
+          f"{ev / best / 1e6:9.2f} Gev/s  flagged={bad}", flush=True)
     eng.close()
 
 if __name__ == "__main__":
@@ -28,4 +28,5 @@ if __name__ == "__main__":
         for n in (65536, 262144):
             for fl in (0, 1):
                 probe("mm1", hs.mm1(), n, 200.0, flags=fl)
-        probe("mm1 rec", hs.mm1(), 65536, 200.0, flags=1, record_cap=2048)
+        probe("mm1 rec", hs.mm1(), 65536, 2000.0, flags=0, record_cap=1024, sample_cap=128, service_cap=128)
+        probe("mm1 long", hs.mm1(), 65536, 2000.0, flags=0)

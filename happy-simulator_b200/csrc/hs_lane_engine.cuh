@@ -65,7 +65,10 @@
 
 #define HS_NOW_CAP 8
 #define HS_LANE_THREADS 64
-#define HS_DRAW_BUF 16    /* precomputed draws per stream per lane (even) */
+#define HS_DRAW_BUF_SUMMARY 16  /* precomputed draws per stream per lane (even)            */
+#define HS_DRAW_BUF_RECORD 8    /* ... when the recorder staging shares the shared memory  */
+#define HS_STAGE 16             /* staged event records per lane (recorder kernels)        */
+#define HS_FLUSH 8              /* records per cooperative flush: 8 x 16 B = one 128 B line */
 #define HS_LF_HASH 1      /* maintain the order hash                         */
 #define HS_LF_REC 2       /* write event records / sink / service samples    */
 
@@ -134,9 +137,15 @@ __global__ void __launch_bounds__(HS_LANE_THREADS, 7)
 hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ states,
                hs_ring_entry *__restrict__ rings, hs_lane_out O)
 {
+    constexpr uint32_t HS_DRAW_BUF = (FLAGS & HS_LF_REC) ? HS_DRAW_BUF_RECORD : HS_DRAW_BUF_SUMMARY;
+    constexpr uint32_t STAGE_ROWS = (FLAGS & HS_LF_REC) ? HS_STAGE : 1;
     __shared__ int64_t sh_t[HS_DRAW_BUF][HS_LANE_THREADS];       /* arrival times A_k (ns)          */
     __shared__ double sh_svc[HS_DRAW_BUF][HS_LANE_THREADS];      /* service: Duration.to_seconds()  */
-    __shared__ int64_t sh_delta[HS_DRAW_BUF][HS_LANE_THREADS];   /* service: int(svc_s * 1e9)       */
+    /* recorder staging: [slot][lane] so that lanes at different slots never conflict; full
+     * 128-byte groups are written to HBM cooperatively at the converged top of the loop */
+    __shared__ __align__(16) uint4 sh_rec[STAGE_ROWS][HS_LANE_THREADS];
+    __shared__ uint4 sh_flush[HS_LANE_THREADS / 32][4];          /* {tid, stage pos, ring pos, -} per source */
+    __shared__ __align__(16) hs_ring_entry sh_head[HS_LANE_THREADS];  /* next item to deliver      */
     const uint32_t tid = threadIdx.x;
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = r < P.n_replicas;
@@ -175,7 +184,16 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     double svc_s, total_service, sum, comp, sumsq, mn, mx;
     uint32_t q_head, q_len, status, rec_pos, smp_pos, svc_pos;
     int32_t active, now_n, has_c;
-    int64_t h_created = 0; uint64_t h_idx = 0;      /* the item the next POLL delivers */
+    /* The item the next POLL delivers lives in this lane's 16-byte shared-memory slot
+     * sh_head[tid].  After a pop the new head is fetched from the ring with cp.async
+     * (LDGSTS: global -> shared, no destination register), i.e. a whole service time before
+     * the next pop reads it, so no instruction waits on the ring's L2/HBM latency. */
+    hs_ring_entry *const my_head = &sh_head[tid];
+    const uint32_t my_head_s = (uint32_t)__cvta_generic_to_shared(my_head);
+    /* recorder staging cursors: st_wr staged, st_fl flushed; rec_pos = ring slot of record st_fl */
+    const bool staged = (FLAGS & HS_LF_REC) && O.records && P.record_cap >= 2 * HS_FLUSH && (P.record_cap % HS_FLUSH) == 0;
+    uint32_t st_wr = 0, st_fl = 0;
+    const uint32_t lane = tid & 31u, wib = tid >> 5;
     hs_now_ev nowq[HS_NOW_CAP];
 
     hs_lane_state *S = states + r;
@@ -192,10 +210,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         now_n = S->now_n; has_c = S->has_c;
         rec_pos = S->rec_pos; smp_pos = S->smp_pos; svc_pos = S->svc_pos;
         for (int i = 0; i < HS_NOW_CAP; ++i) nowq[i] = S->nowq[i];
-        if (q_len > 0) {
-            const hs_ring_entry e = ring[(lifo ? q_head + q_len - 1 : q_head) & ring_mask];
-            h_created = e.created; h_idx = e.idx;
-        }
+        if (q_len > 0) *my_head = ring[(lifo ? q_head + q_len - 1 : q_head) & ring_mask];
     } else {
         now = 0; processed = 0; hash = HS_HASH_INIT; ctr = 0;
         arr_draws = 0; n_svc = 0;
@@ -241,11 +256,11 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             if (expo) hs_uniform_pair(seed, rid, sid_svc, s_gen >> 1, &u0_, &u1_);           \
             if (!(s_gen & 1)) {                                                              \
                 const double s0_ = hs_ns_to_seconds(expo ? hs_exp_latency_ns(u0_, lambda) : hs_seconds_to_ns(mean)); \
-                sh_svc[s_gen % HS_DRAW_BUF][tid] = s0_; sh_delta[s_gen % HS_DRAW_BUF][tid] = hs_seconds_to_ns(s0_); \
+                sh_svc[s_gen % HS_DRAW_BUF][tid] = s0_;                                      \
                 s_gen++;                                                                     \
             }                                                                                \
             const double s1_ = hs_ns_to_seconds(expo ? hs_exp_latency_ns(u1_, lambda) : hs_seconds_to_ns(mean));     \
-            sh_svc[s_gen % HS_DRAW_BUF][tid] = s1_; sh_delta[s_gen % HS_DRAW_BUF][tid] = hs_seconds_to_ns(s1_);     \
+            sh_svc[s_gen % HS_DRAW_BUF][tid] = s1_;                                          \
             s_gen++;                                                                         \
         }                                                                                    \
     } while (0)
@@ -257,8 +272,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             uint4 w_;                                                                        \
             w_.x = (uint32_t)(uint64_t)now; w_.y = (uint32_t)((uint64_t)now >> 32);          \
             w_.z = (uint32_t)(IDX); w_.w = (uint32_t)(KIND) | ((uint32_t)(ENT) << 16);       \
-            __stcs((uint4 *)(rec + rec_pos), w_);                                            \
-            rec_pos = (rec_pos + 1 == P.record_cap) ? 0u : rec_pos + 1;                      \
+            /* staging non-empty implies rec_pos is group aligned (it then only moves by whole groups) */ \
+            if (staged && (st_wr != st_fl || (rec_pos % HS_FLUSH) == 0)) { sh_rec[st_wr % HS_STAGE][tid] = w_; st_wr++; } \
+            else { __stcs((uint4 *)(rec + rec_pos), w_);                                     \
+                   rec_pos = (rec_pos + 1 == P.record_cap) ? 0u : rec_pos + 1; }             \
         }                                                                                    \
     } while (0)
 #define HS_EMIT(KIND, IDX, ENT) do { HS_RECORD(KIND, IDX, ENT); processed++; } while (0)
@@ -275,7 +292,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     do {                                                                                     \
         const uint32_t k_ = (uint32_t)((uint64_t)n_svc % HS_DRAW_BUF);                       \
         svc_s = sh_svc[k_][tid];                                                             \
-        const int64_t delta_ = sh_delta[k_][tid];                                            \
+        const int64_t delta_ = hs_seconds_to_ns(svc_s);   /* event.py:499, temporal.py:221 */ \
         if ((FLAGS & HS_LF_REC) && svc_out) { __stcs(svc_out + svc_pos, svc_s); svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
         n_svc++;                                                                             \
         active++;                                                                            \
@@ -304,16 +321,21 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     do {                                                                                     \
         hs_ring_entry e_; e_.created = (CREATED); e_.idx = (IDX);                            \
         ring[(q_head + q_len) & ring_mask] = e_;                                             \
-        if (lifo || q_len == 0) { h_created = (CREATED); h_idx = (IDX); }                    \
+        if (lifo) { asm volatile("cp.async.wait_group 0;" ::: "memory"); *my_head = e_; }    \
+        else if (q_len == 0) *my_head = e_;                                                  \
         q_len++;                                                                             \
     } while (0)
 #define HS_Q_POP(CREATED, IDX)                                                               \
     do {                                                                                     \
-        (CREATED) = h_created; (IDX) = h_idx;                                                \
+        asm volatile("cp.async.wait_group 0;" ::: "memory");                                 \
+        { const hs_ring_entry h_ = *my_head; (CREATED) = h_.created; (IDX) = h_.idx; }       \
         if (!lifo) q_head++;                                                                 \
         q_len--;                                                                             \
-        if (q_len > 0) { const hs_ring_entry n_ = ring[(lifo ? q_head + q_len - 1 : q_head) & ring_mask]; \
-                         h_created = n_.created; h_idx = n_.idx; }                           \
+        if (q_len > 0) {                                                                     \
+            const hs_ring_entry *n_ = ring + ((lifo ? q_head + q_len - 1 : q_head) & ring_mask); \
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" \
+                         :: "r"(my_head_s), "l"(n_) : "memory");                             \
+        }                                                                                    \
     } while (0)
 
 #define HS_PUSH_NOW(KIND, IDX, CREATED, PIDX)                                                \
@@ -341,6 +363,30 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         const unsigned todo = __ballot_sync(0xffffffffu, !finished);
         if (todo == 0u) break;
         if (__any_sync(0xffffffffu, need)) HS_REFILL_ROUND();
+        if (FLAGS & HS_LF_REC) {
+            /* cooperative flush: every lane holding a full 128-byte group hands it to 8 lanes,
+             * which write it as one contiguous line (4 groups per store instruction) */
+            bool want = staged && (st_wr - st_fl) >= HS_FLUSH;
+            unsigned fm = __ballot_sync(0xffffffffu, want);
+            while (fm) {
+                const uint32_t rank = __popc(fm & ((1u << lane) - 1u));
+                if (want && rank < 4) sh_flush[wib][rank] = make_uint4(tid, st_fl, rec_pos, 0u);
+                __syncwarp();
+                const uint32_t g = lane >> 3, c = lane & 7u;
+                if (g < (uint32_t)__popc(fm)) {
+                    const uint4 f = sh_flush[wib][g];
+                    const uint4 w = sh_rec[(f.y + c) % HS_STAGE][f.x];
+                    hs_event_record *dst = O.records + ((size_t)(blockIdx.x * blockDim.x + f.x)) * P.record_cap + f.z + c;
+                    __stcs((uint4 *)dst, w);
+                }
+                __syncwarp();
+                if (want && rank < 4) {
+                    st_fl += HS_FLUSH; rec_pos = (rec_pos + HS_FLUSH == P.record_cap) ? 0u : rec_pos + HS_FLUSH;
+                    want = (st_wr - st_fl) >= HS_FLUSH;
+                }
+                fm = __ballot_sync(0xffffffffu, want);
+            }
+        }
         if (finished) continue;
 
         if (!(now <= P.end_ns)) { finished = true; continue; }                 /* simulation.py:472 */
@@ -504,6 +550,12 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
 
     if (!valid) return;
     if (P.resume && S->done) return;        /* finished in an earlier window: outputs already final */
+    if ((FLAGS & HS_LF_REC) && staged) {    /* drain what is still staged, record by record */
+        while (st_fl != st_wr) {
+            __stcs((uint4 *)(rec + rec_pos), sh_rec[st_fl % HS_STAGE][tid]);
+            st_fl++; rec_pos = (rec_pos + 1 == P.record_cap) ? 0u : rec_pos + 1;
+        }
+    }
 
     /* ---- persist / publish --------------------------------------------- */
     /* derived counters: a tick is processed per consumed arrival time except the pending one;

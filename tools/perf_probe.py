@@ -29,4 +29,5 @@ if __name__ == "__main__":
             for fl in (0, 1):
                 probe("mm1", hs.mm1(), n, 200.0, flags=fl)
         probe("mm1 rec", hs.mm1(), 65536, 2000.0, flags=0, record_cap=1024, sample_cap=128, service_cap=128)
+        probe("mm1 rec-only", hs.mm1(), 65536, 2000.0, flags=0, record_cap=1024)
         probe("mm1 long", hs.mm1(), 65536, 2000.0, flags=0)

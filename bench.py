@@ -98,43 +98,53 @@ class ClockSampler:
         mx = [int(r[2]) for r in self.rows if len(r) > 8 and r[2].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        pw = sorted(float(r[3]) for r in self.rows if len(r) > 8 and r[3].replace(".", "", 1).isdigit())
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w_median": pw[len(pw) // 2] if pw else None}
 
 
 # --------------------------------------------------------------------------- CPU arm
 
 def cpu_oracle_throughput(budget_s, window_s, seed, threads=None):
     """Time the oracle port on the host cores over a bounded sample of the same workload
-    (M/M/1 replicas of BASELINE configs[1], each simulated for `window_s` s)."""
+    (M/M/1 replicas of BASELINE configs[1], each simulated for `window_s` s).  Threads pull
+    replicas from a shared counter until the time budget is spent, so the wall time is bounded
+    whatever the box's core count or load."""
     import happysim_b200 as hs
     import oracle_lib as O
     from concurrent.futures import ThreadPoolExecutor
     import ctypes as C
+    import itertools
 
     cores = threads or (os.cpu_count() or 1)
     model = hs.mm1(RATE, MEAN)
     d = model.desc()
-    # calibrate: one replica, short horizon
-    p = O.make_params(seed=seed, end_ns=int(200e9), n_replicas=1, flags=0)
-    bufs, o = O.alloc_outputs(model.n_entities, p)
-    t0 = time.perf_counter(); O.lib().hs_oracle_run(C.byref(d), C.byref(p), C.byref(o)); dt = time.perf_counter() - t0
-    ev_per_s_core = float(bufs["summaries"]["events_processed"][0]) / max(dt, 1e-9)
-    ev_per_replica = 7.92 * RATE * window_s * 0.93
-    n_rep = max(cores, int(budget_s * ev_per_s_core * cores / ev_per_replica))
-    n_rep = (n_rep // cores) * cores or cores
-    p = O.make_params(seed=seed, end_ns=int(window_s * 1e9), n_replicas=n_rep, flags=0)
-    bufs, o = O.alloc_outputs(model.n_entities, p)
-    chunk = n_rep // cores
+    cap = 1 << 20
+    p = O.make_params(seed=seed, end_ns=int(window_s * 1e9), n_replicas=cap, flags=0)
+    import numpy as np
+    summ = np.zeros(cap, O.A.SUMMARY_DTYPE)
+    o = O.A.Outputs()
+    o.summaries = summ.ctypes.data_as(C.POINTER(O.A.ReplicaSummary))
+    counter = itertools.count()
+    deadline = time.perf_counter() + budget_s
+    done = []
 
-    def work(k):
-        O.lib().hs_oracle_run_range(C.byref(d), C.byref(p), C.byref(o), k * chunk, (k + 1) * chunk)
+    def work(_):
+        n = 0
+        while time.perf_counter() < deadline:
+            k = next(counter)
+            if k >= cap:
+                break
+            O.lib().hs_oracle_run_range(C.byref(d), C.byref(p), C.byref(o), k, k + 1)
+            n += 1
+        done.append(n)
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
         list(ex.map(work, range(cores)))
     dt = time.perf_counter() - t0
-    ev = int(bufs["summaries"]["events_processed"].sum())
+    ev = int(summ["events_processed"].sum())
+    n_rep = int((summ["events_processed"] > 0).sum())
     return {"value": ev / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n_rep} M/M/1 replicas x {window_s:g} sim-s ({ev:.3e} events, {dt:.1f} s wall) on the "
                       f"oracle port (oracle/hs_oracle.c), {cores} threads"}, ev, dt
@@ -145,7 +155,7 @@ def run_reference_arm(a, rank, world):
         return
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     budget = 4.0
-    win = min(a.window_s, 2000.0)
+    win = min(a.window_s, 500.0)
     for _ in range(a.warmup):
         cpu_oracle_throughput(0.5, win, a.seed)
     tot_ev, tot_t, last = 0, 0.0, None
@@ -298,8 +308,16 @@ def main():
     else:
         algo_bytes = state_bytes
     achieved = algo_bytes / (per_launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:        # DRAM bytes per event measured by one `ncu --set full` capture of this kernel (profiles/)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)[a.mode]
+        traffic = tj["dram_bytes"] / tj["events"] * res["events"] / a.steps
+        traffic_src = tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": kernel, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "bytes_per_event": algo_bytes * a.steps / max(1, res["events"]),
                 "note": ("record mode: 16 B/event + 16 B/Sink sample + 8 B/service start (SURVEY.md 8(d)) + replica "
@@ -353,7 +371,7 @@ def main():
                 "other_mode": other, "wall_s_timed_region": res["wall_s"]}
         if world == 1 and not a.no_cpu_baseline:
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-            cb, _, _ = cpu_oracle_throughput(12.0, min(a.window_s, 2000.0), a.seed)
+            cb, _, _ = cpu_oracle_throughput(12.0, min(a.window_s, 500.0), a.seed)
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:

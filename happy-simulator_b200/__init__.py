@@ -9,6 +9,17 @@ the ctypes binding.  There is NO CPU fallback: without the CUDA library and a
 GPU, ``run()`` raises.
 """
 from . import _abi  # noqa: F401
+from . import engine  # noqa: F401
 from .model import FlatModel, ModelBuilder, mm1, lb_round_robin, lb_key_table, mmc_sweep  # noqa: F401
 
 __version__ = "0.1.0"
+
+from .lowering import lower, consistent_hash_table, UnsupportedModelError  # noqa: F401,E402
+from .api import (  # noqa: F401,E402
+    Instant, Duration, Entity, Source, SimpleEventProvider, ConstantRateProfile, ConstantArrivalTimeProvider,
+    PoissonArrivalTimeProvider, ConstantLatency, ExponentialLatency, FIFOQueue, LIFOQueue, FixedConcurrency,
+    Server, ServerStats, Sink, Counter, LoadBalancer, LoadBalancerStats, RoundRobin, ConsistentHash,
+    UniformKeyContext, Simulation, SimulationSummary, EntitySummary, QueueStats, ParallelRunner, RunConfig,
+    ParallelResult, seed, run_lowered,
+)
+from . import api  # noqa: F401,E402

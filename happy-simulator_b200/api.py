@@ -1,0 +1,700 @@
+"""Host-side mirror of the reference's modelling API for the accelerated path.
+
+Same names, argument meaning and error behaviour as the reference classes they
+stand for (cited per class), so models and tests read like the reference's own;
+``Simulation.run()`` lowers the object graph (lowering.py), runs it on the CUDA
+engine through the C-ABI (engine.py) and writes the results back onto the entity
+objects, which is where the reference's callers read them
+(``sink.latencies_s``, ``server.stats``, ``source.generated_count``, ``lb.stats``).
+
+Randomness: the reference draws from Python's and numpy's global MT19937 streams;
+here every stochastic consumer owns a Philox stream keyed by ``seed`` (the
+``Simulation(seed=)`` argument, default ``happysim_b200.default_seed``) -- the same
+streams the Philox plug-ins inject into the unmodified reference in the parity tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import math
+import time as _time
+from typing import Any, Callable
+
+import numpy as np
+
+from . import _abi as A
+from . import lowering
+from .engine import Engine, make_params
+
+default_seed = 0
+
+
+def seed(value: int) -> None:
+    """Set the default Philox key of subsequent ``Simulation`` objects (cf. random.seed)."""
+    global default_seed
+    default_seed = int(value)
+
+
+# ----------------------------------------------------------------------------- time
+class Duration:
+    """core/temporal.py:24-160 -- nanosecond duration; from_seconds truncates like the reference."""
+    __slots__ = ("nanoseconds",)
+
+    def __init__(self, nanoseconds: int):
+        self.nanoseconds = nanoseconds
+
+    @classmethod
+    def from_seconds(cls, seconds):
+        if isinstance(seconds, int):
+            return cls(seconds * 1_000_000_000)
+        if isinstance(seconds, float):
+            return cls(int(seconds * 1_000_000_000))
+        raise TypeError("seconds must be int or float")
+
+    def to_seconds(self) -> float:
+        return float(self.nanoseconds) / 1_000_000_000
+
+    def __eq__(self, o):
+        return isinstance(o, Duration) and self.nanoseconds == o.nanoseconds
+
+    def __lt__(self, o):
+        return self.nanoseconds < o.nanoseconds
+
+    def __hash__(self):
+        return hash(self.nanoseconds)
+
+    def __repr__(self):
+        return f"Duration({self.to_seconds()}s)"
+
+
+class Instant:
+    """core/temporal.py:165-300 -- nanosecond time point."""
+    __slots__ = ("nanoseconds",)
+
+    def __init__(self, nanoseconds: int):
+        self.nanoseconds = nanoseconds
+
+    @classmethod
+    def from_seconds(cls, seconds):
+        if isinstance(seconds, int):
+            return cls(seconds * 1_000_000_000)
+        if isinstance(seconds, float):
+            return cls(int(seconds * 1_000_000_000))
+        raise TypeError("seconds must be int or float")
+
+    def to_seconds(self) -> float:
+        return float(self.nanoseconds) / 1_000_000_000
+
+    def __add__(self, other):
+        if isinstance(other, Duration):
+            return Instant(self.nanoseconds + other.nanoseconds)
+        if isinstance(other, (int, float)):
+            return Instant(self.nanoseconds + int(other * 1_000_000_000))
+        return NotImplemented
+
+    def __sub__(self, other):
+        if isinstance(other, Instant):
+            return Duration(self.nanoseconds - other.nanoseconds)
+        if isinstance(other, Duration):
+            return Instant(self.nanoseconds - other.nanoseconds)
+        if isinstance(other, (int, float)):
+            return Instant(self.nanoseconds - int(other * 1_000_000_000))
+        return NotImplemented
+
+    def __eq__(self, o):
+        return isinstance(o, Instant) and self.nanoseconds == o.nanoseconds
+
+    def __lt__(self, o):
+        return self.nanoseconds < o.nanoseconds
+
+    def __le__(self, o):
+        return self.nanoseconds <= o.nanoseconds
+
+    def __gt__(self, o):
+        return self.nanoseconds > o.nanoseconds
+
+    def __ge__(self, o):
+        return self.nanoseconds >= o.nanoseconds
+
+    def __hash__(self):
+        return hash(self.nanoseconds)
+
+    def __repr__(self):
+        return f"Instant({self.to_seconds()}s)"
+
+
+Instant.Epoch = Instant(0)
+
+
+# ----------------------------------------------------------------------------- plug-ins
+@dataclass(frozen=True)
+class ConstantRateProfile:
+    """load/profile.py:37-47"""
+    rate: float
+
+    def get_rate(self, time) -> float:
+        return self.rate
+
+
+class _ArrivalTimeProvider:
+    """load/arrival_time_provider.py:28-47 (constant-rate profiles only on the device)."""
+
+    def __init__(self, profile, start_time: Instant):
+        self.profile = profile
+        self.current_time = start_time
+
+
+class ConstantArrivalTimeProvider(_ArrivalTimeProvider):
+    """load/providers/constant_arrival.py:11-23"""
+
+
+class PoissonArrivalTimeProvider(_ArrivalTimeProvider):
+    """load/providers/poisson_arrival.py:18-31"""
+
+
+class _LatencyDistribution:
+    """distributions/latency_distribution.py:17-41"""
+
+    def __init__(self, mean_latency):
+        self._mean_latency = mean_latency.to_seconds() if isinstance(mean_latency, Duration) else float(mean_latency)
+
+
+class ConstantLatency(_LatencyDistribution):
+    """distributions/constant.py:17-35"""
+
+
+class ExponentialLatency(_LatencyDistribution):
+    """distributions/exponential.py:17-45"""
+
+    def __init__(self, mean_latency):
+        super().__init__(mean_latency)
+        self._lambda = 1 / self._mean_latency
+
+
+class FIFOQueue:
+    """components/queue_policy.py:75-114"""
+
+    def __init__(self, capacity: float = float("inf")):
+        self._capacity = capacity
+
+    @property
+    def capacity(self):
+        return self._capacity
+
+
+class LIFOQueue(FIFOQueue):
+    """components/queue_policy.py:117-156"""
+
+
+class FixedConcurrency:
+    """components/server/concurrency.py:66-140"""
+
+    def __init__(self, max_concurrent: int):
+        if max_concurrent < 1:
+            raise ValueError(f"max_concurrent must be >= 1, got {max_concurrent}")
+        self._max_concurrent = max_concurrent
+
+    @property
+    def limit(self) -> int:
+        return self._max_concurrent
+
+
+class RoundRobin:
+    """components/load_balancer/strategies.py:50-72"""
+
+
+class ConsistentHash:
+    """components/load_balancer/strategies.py:336-433 (default key extraction: metadata client_id)."""
+
+    def __init__(self, virtual_nodes: int = 100, get_key: Callable | None = None):
+        if virtual_nodes < 1:
+            raise ValueError(f"virtual_nodes must be >= 1, got {virtual_nodes}")
+        if get_key is not None:
+            raise lowering.UnsupportedModelError("custom get_key callbacks cannot run on the device")
+        self._virtual_nodes = virtual_nodes
+        self._get_key = None
+
+
+class UniformKeyContext:
+    """context_fn for SimpleEventProvider: metadata {"client_id": k}, k ~ Uniform{0..population-1}
+    drawn from the Philox routing stream (cf. the reference's
+    SimpleEventProvider(context_fn=...) + distributions/uniform.py:57-63)."""
+
+    def __init__(self, population: int):
+        if population < 1:
+            raise ValueError("population must be >= 1")
+        self.key_population = int(population)
+
+
+# ----------------------------------------------------------------------------- entities
+class Entity:
+    """core/entity.py:31-127"""
+
+    def __init__(self, name: str):
+        self.name = name
+
+
+class SimpleEventProvider:
+    """load/source.py:31-86"""
+
+    def __init__(self, target: Entity, event_type: str = "Request", stop_after: Instant | None = None,
+                 context_fn=None):
+        self._target = target
+        self._event_type = event_type
+        self._stop_after = stop_after
+        self._context_fn = context_fn
+        self._generated = 0
+
+
+class Source(Entity):
+    """load/source.py:92-341"""
+
+    def __init__(self, name: str, event_provider, arrival_time_provider):
+        super().__init__(name)
+        self._event_provider = event_provider
+        self._time_provider = arrival_time_provider
+        self._generated_count = 0
+
+    @staticmethod
+    def _resolve_stop_after(stop_after):
+        if stop_after is None or isinstance(stop_after, Instant):
+            return stop_after
+        return Instant.from_seconds(stop_after)
+
+    @classmethod
+    def _make(cls, provider_cls, rate, target, event_type, name, stop_after, event_provider):
+        if event_provider is None:
+            if target is None:
+                raise ValueError("Either 'target' or 'event_provider' must be provided")
+            event_provider = SimpleEventProvider(target, event_type, cls._resolve_stop_after(stop_after))
+        return cls(name=name, event_provider=event_provider,
+                   arrival_time_provider=provider_cls(ConstantRateProfile(rate=rate), start_time=Instant.Epoch))
+
+    @classmethod
+    def constant(cls, rate, target=None, event_type="Request", *, name="Source", stop_after=None, event_provider=None):
+        return cls._make(ConstantArrivalTimeProvider, rate, target, event_type, name, stop_after, event_provider)
+
+    @classmethod
+    def poisson(cls, rate, target=None, event_type="Request", *, name="Source", stop_after=None, event_provider=None):
+        return cls._make(PoissonArrivalTimeProvider, rate, target, event_type, name, stop_after, event_provider)
+
+    @property
+    def generated_count(self) -> int:
+        return self._generated_count
+
+
+class _Queue:
+    """components/queue.py:76-170 (state holder; the protocol itself runs on the device)."""
+
+    def __init__(self, name, policy):
+        self.name = name
+        self.policy = policy
+        self.stats_dropped = 0
+        self.stats_accepted = 0
+
+
+@dataclass(frozen=True)
+class ServerStats:
+    """components/server/server.py:34-40"""
+    requests_completed: int = 0
+    requests_rejected: int = 0
+    total_service_time: float = 0.0
+
+
+class Server(Entity):
+    """components/server/server.py:43-300 (QueuedResource + FixedConcurrency + service distribution)."""
+
+    def __init__(self, name: str, concurrency=1, service_time=None, queue_policy=None, queue_capacity=None,
+                 downstream: Entity | None = None):
+        super().__init__(name)
+        if queue_policy is None:
+            queue_policy = FIFOQueue(capacity=queue_capacity if queue_capacity is not None else float("inf"))
+        self._queue = _Queue(f"{name}.queue", queue_policy)
+        self._concurrency_model = FixedConcurrency(concurrency) if isinstance(concurrency, int) else concurrency
+        self._service_time = service_time or ConstantLatency(0.01)
+        self._downstream = downstream
+        self._requests_completed = 0
+        self._requests_rejected = 0
+        self._total_service_time = 0.0
+        self._service_times: list[float] = []
+
+    @property
+    def downstream(self):
+        return self._downstream
+
+    @downstream.setter
+    def downstream(self, target):
+        self._downstream = target
+
+    @property
+    def concurrency(self) -> int:
+        return self._concurrency_model.limit
+
+    @property
+    def stats_accepted(self) -> int:
+        return self._queue.stats_accepted
+
+    @property
+    def stats_dropped(self) -> int:
+        return self._queue.stats_dropped
+
+    @property
+    def stats(self) -> ServerStats:
+        return ServerStats(self._requests_completed, self._requests_rejected, self._total_service_time)
+
+    @property
+    def average_service_time(self) -> float:
+        return sum(self._service_times) / len(self._service_times) if self._service_times else 0.0
+
+
+class Sink(Entity):
+    """components/common.py:18-76"""
+
+    def __init__(self, name: str = "Sink"):
+        super().__init__(name)
+        self.events_received = 0
+        self.completion_times: list[Instant] = []
+        self.latencies_s: list[float] = []
+        self._latency_sum = 0.0
+
+    def average_latency(self) -> float:
+        if not self.events_received:
+            return 0.0
+        # the device accumulates sum(latencies_s) exactly as CPython's float sum() does
+        return self._latency_sum / self.events_received
+
+    def latency_stats(self) -> dict:
+        n = len(self.latencies_s)
+        if n == 0:
+            return {"count": 0, "avg": 0.0, "min": 0.0, "max": 0.0, "p50": 0.0, "p99": 0.0}
+        v = sorted(self.latencies_s)
+
+        def pct(p):
+            pos = p * (n - 1)
+            lo = int(pos)
+            hi = min(lo + 1, n - 1)
+            frac = pos - lo
+            return v[lo] * (1.0 - frac) + v[hi] * frac
+        return {"count": n, "avg": sum(v) / n, "min": v[0], "max": v[-1], "p50": pct(0.50), "p99": pct(0.99)}
+
+
+class Counter(Entity):
+    """components/common.py:79-95"""
+
+    def __init__(self, name: str = "Counter"):
+        super().__init__(name)
+        self.total = 0
+        self.by_type: dict[str, int] = {}
+
+
+@dataclass
+class BackendInfo:
+    """components/load_balancer/load_balancer.py (BackendInfo)"""
+    backend: Entity
+    weight: int = 1
+    is_healthy: bool = True
+    total_requests: int = 0
+
+
+@dataclass(frozen=True)
+class LoadBalancerStats:
+    requests_received: int = 0
+    requests_forwarded: int = 0
+    requests_failed: int = 0
+    no_backend_available: int = 0
+    backends_marked_unhealthy: int = 0
+    backends_marked_healthy: int = 0
+
+
+class LoadBalancer(Entity):
+    """components/load_balancer/load_balancer.py:60-473"""
+
+    def __init__(self, name: str, backends=None, strategy=None, on_no_backend: str = "reject"):
+        super().__init__(name)
+        if on_no_backend not in ("reject", "queue"):
+            raise ValueError(f"on_no_backend must be 'reject' or 'queue', got {on_no_backend}")
+        self._strategy = strategy or RoundRobin()
+        self._backends: dict[str, BackendInfo] = {}
+        self._in_flight: dict = {}
+        self._requests_received = 0
+        self._requests_forwarded = 0
+        for b in backends or []:
+            self.add_backend(b)
+
+    def add_backend(self, backend: Entity, weight: int = 1) -> None:
+        if weight < 1:
+            raise ValueError(f"weight must be >= 1, got {weight}")
+        self._backends[backend.name] = BackendInfo(backend=backend, weight=weight)
+
+    @property
+    def stats(self) -> LoadBalancerStats:
+        return LoadBalancerStats(requests_received=self._requests_received,
+                                 requests_forwarded=self._requests_forwarded)
+
+
+# ----------------------------------------------------------------------------- summary
+@dataclass
+class QueueStats:
+    """instrumentation/summary.py:14-20"""
+    peak_depth: int
+    total_accepted: int
+    total_dropped: int
+
+
+@dataclass
+class EntitySummary:
+    """instrumentation/summary.py:23-44"""
+    name: str
+    entity_type: str
+    events_handled: int
+    queue_stats: QueueStats | None = None
+
+
+@dataclass
+class SimulationSummary:
+    """instrumentation/summary.py:47-87"""
+    duration_s: float
+    total_events_processed: int
+    events_cancelled: int = 0
+    events_per_second: float = 0.0
+    wall_clock_seconds: float = 0.0
+    entities: dict[str, EntitySummary] = field(default_factory=dict)
+
+    def to_dict(self) -> dict[str, Any]:
+        return {"duration_s": self.duration_s, "total_events_processed": self.total_events_processed,
+                "events_cancelled": self.events_cancelled, "events_per_second": self.events_per_second,
+                "wall_clock_seconds": self.wall_clock_seconds,
+                "entities": {k: vars(v) for k, v in self.entities.items()}}
+
+
+_engines: dict[int, Engine] = {}
+
+
+def _engine(device: int) -> Engine:
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]
+
+
+class Simulation:
+    """core/simulation.py:38-591 -- same constructor, ``run() -> SimulationSummary``.
+
+    Extra keyword arguments (not in the reference): ``seed`` (Philox key), ``replica`` (Philox
+    replica word), ``device``."""
+
+    def __init__(self, start_time: Instant | None = None, end_time: Instant | None = None, sources=None,
+                 entities=None, probes=None, trace_recorder=None, fault_schedule=None, duration: float | None = None,
+                 *, seed: int | None = None, replica: int = 0, device: int = 0):
+        if duration is not None and end_time is not None:
+            raise ValueError("Cannot specify both 'duration' and 'end_time'")
+        if start_time is not None and start_time.nanoseconds != 0:
+            raise lowering.UnsupportedModelError("start_time must be Instant.Epoch on the device engine")
+        for nm, v in (("probes", probes), ("trace_recorder", trace_recorder), ("fault_schedule", fault_schedule)):
+            if v:
+                raise lowering.UnsupportedModelError(f"{nm}= is outside the accelerated path (SURVEY.md section 8)")
+        self._start_time = Instant.Epoch
+        if duration is not None:
+            self._end_time = self._start_time + duration
+        elif end_time is not None:
+            self._end_time = end_time
+        else:
+            raise lowering.UnsupportedModelError("the device engine needs an explicit end_time or duration "
+                                                 "(auto-termination is the reference's slow loop)")
+        self._sources = list(sources or [])
+        self._entities = list(entities or [])
+        self._seed = default_seed if seed is None else int(seed)
+        self._replica = int(replica)
+        self._device = device
+        self._summary: SimulationSummary | None = None
+        self._instant_cls = Instant
+        self.model, self.objects = lowering.lower(self._sources, self._entities)
+
+    @property
+    def summary(self):
+        return self._summary
+
+    # -- single run -------------------------------------------------------------
+    def _caps(self, n_hint: int | None = None):
+        dur = self._end_time.to_seconds()
+        ents = self.model.entities
+        rate = float(sum(ents["d0"][i] for i in self.model.ids_of(A.HS_ENT_SOURCE)))
+        req = int(rate * dur * 1.3 + 6 * math.sqrt(rate * dur + 1) + 64)
+        n_srv = len(self.model.ids_of(A.HS_ENT_SERVER))
+        chain = 1 if (n_srv <= 1 or self.model.ids_of(A.HS_ENT_LB)) else n_srv     # tandem: one start per stage
+        return dict(record_cap=0, sample_cap=req, service_cap=req * chain)
+
+    def run(self) -> SimulationSummary:
+        t0 = _time.monotonic()
+        eng = _engine(self._device)
+        eng.upload(self.model)
+        caps = self._caps()
+        need_events = len(self.model.ids_of(A.HS_ENT_SERVER)) > 1     # per-server service-time lists
+        for _ in range(6):
+            kw = dict(caps)
+            if need_events:
+                kw["record_cap"] = kw["service_cap"] * 12
+            eng.run(make_params(seed=self._seed, rid_base=self._replica, end_ns=self._end_time.nanoseconds,
+                                n_replicas=1, flags=0, **kw))
+            out = eng.read_outputs()
+            s = out["summaries"][0]
+            if int(s["status"]) & (A.HS_ST_QUEUE_OVERFLOW | A.HS_ST_FEL_OVERFLOW):
+                raise RuntimeError(f"device structure overflow (status {int(s['status'])}); raise queue_ring")
+            if (int(s["n_sink_samples"]) <= kw["sample_cap"] and int(s["n_service_samples"]) <= kw["service_cap"]
+                    and (not need_events or int(s["events_processed"]) <= kw["record_cap"])):
+                break
+            caps = dict(record_cap=0, sample_cap=2 * int(s["n_sink_samples"]) + 64,
+                        service_cap=2 * int(s["n_service_samples"]) + 64)
+        self._write_back(out, 0)
+        s = out["summaries"][0]
+        duration_s = float(int(s["final_time_ns"])) / 1_000_000_000
+        n = int(s["events_processed"])
+        self._summary = SimulationSummary(duration_s=duration_s, total_events_processed=n, events_cancelled=0,
+                                          events_per_second=n / duration_s if duration_s > 0 else 0.0,
+                                          wall_clock_seconds=_time.monotonic() - t0,
+                                          entities=self._entity_summaries())
+        return self._summary
+
+    def _write_back(self, out, r: int) -> None:
+        """Publish replica ``r`` onto the Python objects, where the reference's callers look."""
+        st = out["entity_stats"][r]
+        kinds = self.model.entities["kind"]
+        s = out["summaries"][r]
+        n_smp, n_svc = int(s["n_sink_samples"]), int(s["n_service_samples"])
+        samples = out["sink_samples"][r][:n_smp] if out.get("sink_samples") is not None else None
+        sinks = self.model.ids_of(A.HS_ENT_SINK)
+        servers = self.model.ids_of(A.HS_ENT_SERVER)
+        per_server = {i: [] for i in servers}
+        if out.get("service_samples") is not None:
+            svc = out["service_samples"][r][:n_svc]
+            if len(servers) == 1:
+                per_server[servers[0]] = [float(x) for x in svc]
+            elif out.get("records") is not None:
+                rec = out["records"][r][: int(s["events_processed"])]
+                who = rec["entity"][rec["kind"] == A.HS_EV_REQ_WORKER][: len(svc)]
+                for ent, x in zip(who, svc):
+                    per_server[int(ent)].append(float(x))
+        for i, o in enumerate(self.objects):
+            k = int(kinds[i])
+            row = st[i]
+            if k == A.HS_ENT_SOURCE:
+                o._generated_count = int(row["c0"])
+                o._event_provider._generated = int(row["c1"])
+            elif k == A.HS_ENT_SERVER:
+                o._queue.stats_accepted, o._queue.stats_dropped = int(row["c0"]), int(row["c1"])
+                o._requests_completed, o._requests_rejected = int(row["c2"]), int(row["c3"])
+                o._total_service_time = float(row["f0"])
+                o._service_times = per_server[i]
+            elif k == A.HS_ENT_SINK:
+                o.events_received = int(row["c0"])
+                o._latency_sum = float(row["f0"])
+                if samples is not None and len(sinks) == 1:
+                    o.completion_times = [self._instant_cls(int(t)) for t in samples["completion_ns"]]
+                    o.latencies_s = [float(x) for x in samples["latency_s"]]
+            elif k == A.HS_ENT_COUNTER:
+                o.total = int(row["c0"])
+                o.by_type = {"Request": o.total} if o.total else {}
+            elif k == A.HS_ENT_LB:
+                o._requests_received, o._requests_forwarded = int(row["c0"]), int(row["c1"])
+
+    def _entity_summaries(self):
+        """core/simulation.py:560-591: only objects passed as entities=, events_handled from
+        count | events_received | stats_processed, queue stats for queued resources."""
+        res = {}
+        for o in self._entities:
+            qs = None
+            if hasattr(o, "_queue") and hasattr(o, "_concurrency_model"):
+                qs = QueueStats(peak_depth=0, total_accepted=o.stats_accepted, total_dropped=o.stats_dropped)
+            handled = 0
+            for attr in ("count", "events_received", "stats_processed"):
+                v = getattr(o, attr, None)
+                if isinstance(v, int):
+                    handled = v
+                    break
+            res[o.name] = EntitySummary(name=o.name, entity_type=type(o).__name__, events_handled=handled, queue_stats=qs)
+        return res
+
+    # -- ensembles ----------------------------------------------------------------
+    def run_ensemble(self, n_replicas: int, *, seed: int | None = None, seed_stride: int = 0, rid_base: int = 0,
+                     rid_stride: int = 1, replica_index_base: int = 0, replicas_per_cell: int = 1, **caps):
+        """N independent replicas of this model on the device; returns the raw per-replica arrays
+        (summaries, entity_stats, optional recorder rings) and the engine's totals."""
+        eng = _engine(self._device)
+        eng.upload(self.model)
+        eng.run(make_params(seed=self._seed if seed is None else seed, seed_stride=seed_stride, rid_base=rid_base,
+                            rid_stride=rid_stride, end_ns=self._end_time.nanoseconds, n_replicas=n_replicas,
+                            replica_index_base=replica_index_base, replicas_per_cell=replicas_per_cell, **caps))
+        out = eng.read_outputs()
+        out["totals"] = eng.read_totals()
+        out["device_ms"] = eng.last_run_ms()
+        return out
+
+
+def run_lowered(ref_sim, model=None, objects=None, *, seed: int | None = None, replica: int = 0, device: int = 0):
+    """Run a REFERENCE ``happysimulator.Simulation`` object on the device and write the results back
+    onto its own entity objects (the hook shown in INTEGRATION.md section 3).  ``ref_sim`` only needs the
+    reference's attributes ``_sources``, ``_entities``, ``_start_time``, ``_end_time``."""
+    if model is None:
+        model, objects = lowering.lower(ref_sim._sources, ref_sim._entities)
+    shell = Simulation.__new__(Simulation)
+    shell._start_time = Instant.Epoch
+    shell._end_time = Instant(int(ref_sim._end_time.nanoseconds))
+    shell._sources, shell._entities = list(ref_sim._sources), list(ref_sim._entities)
+    shell._seed = default_seed if seed is None else int(seed)
+    shell._replica, shell._device, shell._summary = int(replica), device, None
+    shell._instant_cls = type(ref_sim._start_time)
+    shell.model, shell.objects = model, objects
+    return shell.run()
+
+
+# ----------------------------------------------------------------------------- parallel/runner.py
+@dataclass
+class RunConfig:
+    """parallel/runner.py:42-54"""
+    name: str
+    build_fn: Callable
+    seed: int | None = None
+
+
+@dataclass
+class ParallelResult:
+    """parallel/runner.py:57-70"""
+    name: str
+    summary: SimulationSummary
+    artifacts: dict[str, Any] = field(default_factory=dict)
+
+
+class ParallelRunner:
+    """parallel/runner.py:82-142 -- replicas run as one device ensemble instead of a process pool.
+
+    Replica i uses Philox key ``base_seed + i`` (the reference seeds ``random`` with base_seed + i),
+    so ``run_replicas(build, n, s)[i]`` equals ``Simulation(seed=s + i).run()``."""
+
+    def __init__(self, max_workers: int | None = None, device: int = 0):
+        self._max_workers = max_workers
+        self._device = device
+
+    def run_replicas(self, build_fn: Callable, n_replicas: int, base_seed: int = 42) -> list[ParallelResult]:
+        sim = build_fn()
+        t0 = _time.monotonic()
+        out = sim.run_ensemble(n_replicas, seed=base_seed, seed_stride=1, rid_base=sim._replica, rid_stride=0)
+        wall = _time.monotonic() - t0
+        res = []
+        for i in range(n_replicas):
+            sim._write_back(out, i)
+            s = out["summaries"][i]
+            d = float(int(s["final_time_ns"])) / 1_000_000_000
+            n = int(s["events_processed"])
+            res.append(ParallelResult(name=f"replica_{i}", summary=SimulationSummary(
+                duration_s=d, total_events_processed=n, events_per_second=n / d if d > 0 else 0.0,
+                wall_clock_seconds=wall, entities=sim._entity_summaries())))
+        return res
+
+    def run_sweep(self, configs: list[RunConfig]) -> list[ParallelResult]:
+        if not configs:
+            return []
+        out = []
+        for cfg in configs:
+            sim = cfg.build_fn()
+            if cfg.seed is not None:
+                sim._seed = int(cfg.seed)
+            out.append(ParallelResult(name=cfg.name, summary=sim.run()))
+        return out

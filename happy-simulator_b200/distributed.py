@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing: replicas are independent, so the path shards with no data-path
+collective.  Rank r runs the contiguous global replica range
+``shard_range(n, r, world)``; Philox counters carry the GLOBAL replica index
+(``hs_run_params.replica_index_base``), so results do not depend on the number of GPUs.
+After the run ONE all-reduce aggregates the fixed-layout ``hs_totals`` vector: sums for the
+int64 / float64 accumulators, min / max for the latency extrema.  Backend: NCCL on GPUs,
+gloo in the CPU tests (tests/test_distributed_gloo.py)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi as A
+
+
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous split r in [rank*n/world, (rank+1)*n/world) (remainder to the low ranks)."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def totals_from_outputs(model, out) -> A.Totals:
+    """numpy restatement of csrc/hs_totals.cuh (host-side check of the device reduction)."""
+    t = A.Totals()
+    s, st = out["summaries"], out["entity_stats"]
+    kinds = model.entities["kind"]
+    t.i[0] = int(s["events_processed"].sum())
+    t.i[5] = len(s)
+    t.i[6] = int((s["status"] != 0).sum())
+    t.i[7] = int((s["final_time_ns"] // 1000).sum())
+    t.fmin, t.fmax = float("inf"), float("-inf")
+    for e in range(model.n_entities):
+        k, col = int(kinds[e]), st[:, e]
+        if k == A.HS_ENT_SINK:
+            t.i[1] += int(col["c0"].sum()); t.fsum[0] += float(col["f0"].sum()); t.fsum[1] += float(col["f1"].sum())
+            t.fmin = min(t.fmin, float(col["f2"].min())); t.fmax = max(t.fmax, float(col["f3"].max()))
+        elif k == A.HS_ENT_SERVER:
+            t.i[2] += int(col["c2"].sum()); t.i[4] += int(col["c1"].sum()); t.fsum[2] += float(col["f0"].sum())
+        elif k == A.HS_ENT_SOURCE:
+            t.i[3] += int(col["c0"].sum())
+    return t
+
+
+def allreduce_totals(t: A.Totals, device=None, group=None) -> A.Totals:
+    """The single end-of-run collective.  No-op when torch.distributed is not initialised."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    vi = torch.tensor(list(t.i), dtype=torch.int64, device=dev)
+    vf = torch.tensor(list(t.fsum), dtype=torch.float64, device=dev)
+    vmin = torch.tensor([t.fmin], dtype=torch.float64, device=dev)
+    vmax = torch.tensor([t.fmax], dtype=torch.float64, device=dev)
+    dist.all_reduce(vi, group=group)
+    dist.all_reduce(vf, group=group)
+    dist.all_reduce(vmin, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(vmax, op=dist.ReduceOp.MAX, group=group)
+    r = A.Totals()
+    for k in range(A.HS_TOTALS_I64):
+        r.i[k] = int(vi[k])
+    for k in range(A.HS_TOTALS_F64_SUM):
+        r.fsum[k] = float(vf[k])
+    r.fmin, r.fmax = float(vmin[0]), float(vmax[0])
+    return r
+
+
+def run_sharded(engine, model, params_fn, n_total: int, rank: int, world: int, group=None):
+    """Run this rank's shard of an ``n_total``-replica ensemble and return (local outputs,
+    all-reduced totals).  ``params_fn(n_local, index_base)`` builds the hs_run_params."""
+    lo, hi = shard_range(n_total, rank, world)
+    engine.upload(model)
+    engine.run(params_fn(hi - lo, lo))
+    out = engine.read_outputs()
+    return out, allreduce_totals(engine.read_totals(), group=group)

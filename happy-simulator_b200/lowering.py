@@ -1,0 +1,221 @@
+"""Lowering: the object graph ``Simulation.__init__`` receives -> FlatModel.
+
+Works by duck typing on the attribute names of the reference's classes, so it accepts
+both this package's mirror classes (api.py) and the reference's own objects
+(happysimulator.*): ``Source._event_provider/_time_provider``, ``Server._queue /
+_concurrency_model / _service_time / _downstream``, ``LoadBalancer._strategy /
+_backends``, ``Sink``, ``Counter``.  Anything it does not recognise raises
+``UnsupportedModelError`` naming the object -- a model is never silently approximated
+and there is no CPU fallback.
+
+Reference anchors: Simulation.__init__ (core/simulation.py:95-102), Entity.downstream_entities
+(core/entity.py:115-127), Source (load/source.py:92-118), Server (components/server/server.py:64-122),
+LoadBalancer (components/load_balancer/load_balancer.py:74-125), ConsistentHash
+(components/load_balancer/strategies.py:336-433).
+"""
+from __future__ import annotations
+
+import bisect
+import hashlib
+import math
+
+import numpy as np
+
+from . import _abi as A
+from .model import FlatModel, ModelBuilder
+
+
+class UnsupportedModelError(NotImplementedError):
+    pass
+
+
+def _cls(o) -> str:
+    return type(o).__name__
+
+
+def _ns(x) -> int:
+    """Instant/Duration -> ns (both the reference's and ours expose .nanoseconds)."""
+    return int(x.nanoseconds)
+
+
+def consistent_hash_table(backend_names, virtual_nodes: int, population: int) -> np.ndarray:
+    """key k (as the reference stringifies it, str(k)) -> index of the backend ConsistentHash.select
+    returns: the first ring point >= md5(key), wrapping to ring[0] (strategies.py:371-433).  The
+    reference scans the ring linearly; a bisect over the sorted ring gives the same point."""
+    ring = []
+    for bi, name in enumerate(backend_names):
+        for i in range(virtual_nodes):
+            h = int(hashlib.md5(f"{name}:{i}".encode()).hexdigest(), 16)
+            ring.append((h, name, bi))
+    # add_backend re-sorts by hash only (stable): equal hashes keep insertion order
+    ring.sort(key=lambda x: x[0])
+    hashes = [h for h, _, _ in ring]
+    tab = np.zeros(population, np.int32)
+    for k in range(population):
+        hv = int(hashlib.md5(str(k).encode()).hexdigest(), 16)
+        j = bisect.bisect_left(hashes, hv)
+        tab[k] = ring[j][2] if j < len(ring) else ring[0][2]
+    return tab
+
+
+def _arrival(tp):
+    """ArrivalTimeProvider -> (HS_ARR_*, rate)."""
+    name = _cls(tp)
+    prof = getattr(tp, "profile", None)
+    if prof is None or _cls(prof) != "ConstantRateProfile":
+        raise UnsupportedModelError(f"arrival profile {_cls(prof)} is not a ConstantRateProfile "
+                                    "(non-constant profiles are SURVEY 8(f) row 1)")
+    rate = float(prof.rate)
+    if "Poisson" in name:
+        return A.HS_ARR_POISSON, rate
+    if "Constant" in name:
+        return A.HS_ARR_CONSTANT, rate
+    raise UnsupportedModelError(f"arrival time provider {name}")
+
+
+def _service(dist):
+    name = _cls(dist)
+    mean = float(dist._mean_latency)
+    if "Exponential" in name:
+        return A.HS_SVC_EXPONENTIAL, mean
+    if "Constant" in name:
+        return A.HS_SVC_CONSTANT, mean
+    raise UnsupportedModelError(f"service time distribution {name}")
+
+
+def _queue_policy(q):
+    pol = q.policy
+    name = _cls(pol)
+    if name not in ("FIFOQueue", "LIFOQueue"):
+        raise UnsupportedModelError(f"queue policy {name}")
+    cap = pol.capacity
+    cap = -1 if (isinstance(cap, float) and math.isinf(cap)) else int(cap)
+    return (A.HS_Q_LIFO if name == "LIFOQueue" else A.HS_Q_FIFO), cap
+
+
+def lower(sources, entities, *, key_population: int | None = None):
+    """-> (FlatModel, objects) where objects[i] is the Python object of entity id i.
+
+    Entity ids: sources first (in ``sources`` order, the bootstrap order of
+    Simulation.__init__), then every entity reachable from them, in ``entities`` order
+    first and discovery order after."""
+    objs: list = []
+    ids: dict[int, int] = {}
+
+    def add(o):
+        if id(o) not in ids:
+            ids[id(o)] = len(objs)
+            objs.append(o)
+        return ids[id(o)]
+
+    for s in sources or []:
+        add(s)
+    for e in entities or []:
+        add(e)
+
+    def kind_of(o):
+        n = _cls(o)
+        if hasattr(o, "_event_provider") and hasattr(o, "_time_provider"):
+            return A.HS_ENT_SOURCE
+        if hasattr(o, "_concurrency_model") and hasattr(o, "_service_time") and hasattr(o, "_queue"):
+            return A.HS_ENT_SERVER
+        if hasattr(o, "latencies_s") and hasattr(o, "events_received"):
+            return A.HS_ENT_SINK
+        if hasattr(o, "by_type") and hasattr(o, "total"):
+            return A.HS_ENT_COUNTER
+        if hasattr(o, "_strategy") and hasattr(o, "_backends") and hasattr(o, "_in_flight"):
+            return A.HS_ENT_LB
+        raise UnsupportedModelError(f"entity {getattr(o, 'name', o)!r} of type {n} cannot be lowered to the device "
+                                    "engine (supported: Source, Server, Sink, Counter, LoadBalancer)")
+
+    # discover downstream objects (they may be missing from entities=, as in the reference)
+    i = 0
+    while i < len(objs):
+        o = objs[i]
+        k = kind_of(o)
+        if k == A.HS_ENT_SOURCE:
+            t = getattr(o._event_provider, "_target", None)
+            if t is None:
+                raise UnsupportedModelError(f"source {o.name!r}: event provider {_cls(o._event_provider)} has no target")
+            add(t)
+        elif k == A.HS_ENT_SERVER:
+            if o._downstream is not None:
+                add(o._downstream)
+        elif k == A.HS_ENT_LB:
+            for info in o._backends.values():
+                add(info.backend)
+        i += 1
+
+    b = ModelBuilder()
+    pending_lb = []
+    for o in objs:
+        k = kind_of(o)
+        name = getattr(o, "name", _cls(o))
+        if k == A.HS_ENT_SOURCE:
+            prov = o._event_provider
+            if _cls(prov) not in ("SimpleEventProvider", "_SimpleEventProvider"):
+                raise UnsupportedModelError(f"source {name!r}: event provider {_cls(prov)}")
+            ctx = getattr(prov, "_context_fn", None)
+            pop = 0
+            if ctx is not None:
+                pop = int(getattr(ctx, "key_population", 0))
+                if pop <= 0:
+                    raise UnsupportedModelError(f"source {name!r}: arbitrary context_fn callbacks cannot run on the "
+                                                "device (use happysim_b200.UniformKeyContext)")
+            kind, rate = _arrival(o._time_provider)
+            stop = prov._stop_after
+            b.source(name, rate=rate, target=ids[id(prov._target)], poisson=(kind == A.HS_ARR_POISSON),
+                     stop_after_ns=-1 if stop is None else _ns(stop), key_population=pop)
+        elif k == A.HS_ENT_SERVER:
+            cm = o._concurrency_model
+            if _cls(cm) != "FixedConcurrency":
+                raise UnsupportedModelError(f"server {name!r}: concurrency model {_cls(cm)}")
+            skind, mean = _service(o._service_time)
+            pol, cap = _queue_policy(o._queue)
+            ds = o._downstream
+            b.server(name, concurrency=int(cm.limit), mean_service_s=mean, exponential=(skind == A.HS_SVC_EXPONENTIAL),
+                     downstream=-1 if ds is None else ids[id(ds)], capacity=cap, lifo=(pol == A.HS_Q_LIFO))
+        elif k == A.HS_ENT_SINK:
+            b.sink(name)
+        elif k == A.HS_ENT_COUNTER:
+            b.counter(name)
+        elif k == A.HS_ENT_LB:
+            strat = o._strategy
+            backs = [info.backend for info in o._backends.values() if info.is_healthy]
+            if len(backs) != len(o._backends):
+                raise UnsupportedModelError(f"load balancer {name!r}: unhealthy backends")
+            sname = _cls(strat)
+            table = None
+            if sname == "ConsistentHash":
+                gk = getattr(strat, "_get_key", None)
+                if gk is not None and getattr(gk, "__func__", None) is not getattr(type(strat), "_default_get_key", object()):
+                    raise UnsupportedModelError(f"load balancer {name!r}: custom get_key callbacks")
+                pop = key_population or max((int(getattr(getattr(s._event_provider, "_context_fn", None),
+                                                         "key_population", 0)) for s in sources or []), default=0)
+                if pop <= 0:
+                    raise UnsupportedModelError(f"load balancer {name!r}: ConsistentHash needs a finite key population")
+                table = consistent_hash_table([bk.name for bk in backs], int(strat._virtual_nodes), pop)
+            elif sname != "RoundRobin":
+                raise UnsupportedModelError(f"load balancer {name!r}: strategy {sname}")
+            pending_lb.append((name, [ids[id(bk)] for bk in backs], table))
+            b._add(name, A.HS_ENT_LB)           # placeholder row, fixed below (ids must stay in objs order)
+        else:  # pragma: no cover
+            raise UnsupportedModelError(name)
+    # fill LB rows (backend lists are concatenated in LB order)
+    lb_iter = iter(pending_lb)
+    for idx, o in enumerate(objs):
+        if kind_of(o) != A.HS_ENT_LB:
+            continue
+        name, backs, table = next(lb_iter)
+        off = len(b._backends)
+        b._backends += backs
+        strat = A.HS_LB_ROUND_ROBIN
+        if table is not None:
+            if b._key_table.size:
+                raise UnsupportedModelError("more than one key-routed load balancer")
+            strat = A.HS_LB_KEY_TABLE
+            b._key_table = np.asarray(table, np.int32)
+        b._rows[idx] = (A.HS_ENT_LB, -1, strat, off, len(backs), 0, -1, 0.0, 0.0)
+    model = b.build()
+    # a source whose key population is set needs the table length to match (validated by the C-ABI too)
+    return model, objs

@@ -1,0 +1,65 @@
+"""N>1 host logic on CPU: world_size-2 gloo.  Each rank simulates its shard of a replica
+ensemble (with the CPU oracle standing in for the device, as the checker) using the GLOBAL
+replica ids, then the ranks all-reduce the fixed-layout totals vector; the result must equal
+the single-process totals over the whole ensemble."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n_total, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import happysim_b200 as hs
+    from happysim_b200 import distributed as D
+    import oracle_lib as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = hs.lb_round_robin(4, 32.0)
+    lo, hi = D.shard_range(n_total, rank, world)
+    out = O.oracle_run(model, O.make_params(seed=77, end_ns=5 * 10**9, n_replicas=hi - lo, replica_index_base=lo))
+    t = D.allreduce_totals(D.totals_from_outputs(model, out))
+    q.put((rank, lo, hi, list(t.i), list(t.fsum), t.fmin, t.fmax,
+           out["summaries"]["order_hash"].tolist()))
+    dist.destroy_process_group()
+
+
+def test_shard_range_covers_everything_once():
+    from happysim_b200.distributed import shard_range
+    for n, w in ((10, 3), (65536, 8), (7, 8), (262144, 8)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_two_rank_allreduce_equals_single_process():
+    import happysim_b200 as hs
+    from happysim_b200 import distributed as D
+    import oracle_lib as O
+    n_total, world, port = 23, 2, 29000 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    model = hs.lb_round_robin(4, 32.0)
+    whole = O.oracle_run(model, O.make_params(seed=77, end_ns=5 * 10**9, n_replicas=n_total))
+    want = D.totals_from_outputs(model, whole)
+    for rank, lo, hi, ti, tf, fmin, fmax, hashes in got:
+        assert ti == list(want.i)
+        assert np.allclose(tf, list(want.fsum), rtol=1e-12)
+        assert fmin == want.fmin and fmax == want.fmax
+        # global replica ids: a shard reproduces exactly its slice of the whole ensemble
+        assert hashes == whole["summaries"]["order_hash"][lo:hi].tolist()
+    assert got[0][1] == 0 and got[0][2] == got[1][1] and got[1][2] == n_total

@@ -1,0 +1,97 @@
+"""The modelling API end to end on the GPU: models written like the reference's quick-start,
+results read back off the entity objects, compared with the fixtures recorded from the
+UNMODIFIED reference (tests/golden/philox_*.npz)."""
+import numpy as np
+import pytest
+
+import golden_lib as G
+import happysim_b200 as hs
+from happysim_b200 import _abi as A
+
+pytestmark = pytest.mark.gpu
+
+
+def quickstart(seed=None, end_s=60, rate=8):
+    sink = hs.Sink()
+    server = hs.Server("Server", service_time=hs.ExponentialLatency(0.1), downstream=sink)
+    source = hs.Source.poisson(rate=rate, target=server)
+    sim = hs.Simulation(end_time=hs.Instant.from_seconds(end_s), sources=[source], entities=[server, sink], seed=seed)
+    return sim, source, server, sink
+
+
+def test_readme_quickstart_matches_the_reference_fixture():
+    _, kw, z = G.load("philox_mm1_seed42")
+    sim, source, server, sink = quickstart(seed=kw["seed"])
+    summary = sim.run()
+    ws, st = z["summaries"][0], z["entity_stats"][0]
+    assert summary.total_events_processed == int(ws["events_processed"])
+    assert summary.duration_s == float(int(ws["final_time_ns"])) / 1e9
+    assert source.generated_count == int(st[0]["c0"])
+    assert server.stats.requests_completed == int(st[1]["c2"])
+    assert server.stats.total_service_time == float(st[1]["f0"])
+    assert server.stats_accepted == int(st[1]["c0"]) and server.stats_dropped == 0
+    assert sink.events_received == int(st[2]["c0"])
+    assert sink.latencies_s == [float(x) for x in z["sink_samples"]["latency_s"]]
+    assert [t.nanoseconds for t in sink.completion_times] == [int(t) for t in z["sink_samples"]["completion_ns"]]
+    assert server._service_times == [float(x) for x in z["service_samples"]]
+    assert sink.average_latency() == float(st[2]["f0"]) / int(st[2]["c0"])
+    assert sink.average_latency() == sum(sink.latencies_s) / len(sink.latencies_s)   # CPython float sum()
+    es = summary.entities["Server"]
+    assert es.queue_stats.total_accepted == int(st[1]["c0"]) and summary.entities["Sink"].events_handled == sink.events_received
+    p = sink.latency_stats()
+    assert p["count"] == sink.events_received and p["min"] == float(st[2]["f2"]) and p["max"] == float(st[2]["f3"])
+
+
+def test_load_balanced_farm_matches_the_reference_fixture():
+    _, kw, z = G.load("philox_lb_rr8")
+    sink = hs.Sink()
+    servers = [hs.Server(f"S{i}", service_time=hs.ExponentialLatency(0.1)) for i in range(8)]
+    for s in servers:
+        s.downstream = sink
+    lb = hs.LoadBalancer("LB", backends=servers, strategy=hs.RoundRobin())
+    src = hs.Source.poisson(rate=64.0, target=lb)
+    # entity ids of the fixture: source, S0..S7, sink, LB
+    sim = hs.Simulation(end_time=hs.Instant(kw["end_ns"]), sources=[src], entities=[*servers, sink, lb],
+                        seed=kw["seed"], replica=kw["rid_base"])
+    summary = sim.run()
+    st = z["entity_stats"][0]
+    assert summary.total_events_processed == int(z["summaries"]["events_processed"][0])
+    assert lb.stats.requests_received == int(st[10]["c0"]) and lb.stats.requests_forwarded == int(st[10]["c1"])
+    assert [s.stats.requests_completed for s in servers] == [int(st[1 + i]["c2"]) for i in range(8)]
+    assert [s.stats.total_service_time for s in servers] == [float(st[1 + i]["f0"]) for i in range(8)]
+    assert sink.latencies_s == [float(x) for x in z["sink_samples"]["latency_s"]]
+    # per-server service-time lists: total_service_time is their sequential sum (server.py:260)
+    for s in servers:
+        acc = 0.0
+        for x in s._service_times[: s.stats.requests_completed]:
+            acc += x
+        assert acc == s.stats.total_service_time or len(s._service_times) != s.stats.requests_completed
+
+
+def test_parallel_runner_replica_i_equals_single_run_with_seed_plus_i():
+    def build():
+        return quickstart(end_s=30)[0]
+    res = hs.ParallelRunner().run_replicas(build, n_replicas=6, base_seed=42)
+    assert [r.name for r in res] == [f"replica_{i}" for i in range(6)]
+    for i in (0, 3, 5):
+        sim = quickstart(seed=42 + i, end_s=30)[0]
+        s = sim.run()
+        assert res[i].summary.total_events_processed == s.total_events_processed
+        assert res[i].summary.duration_s == s.duration_s
+    assert len({r.summary.total_events_processed for r in res}) > 1
+
+
+def test_run_ensemble_totals():
+    sim = quickstart(seed=7, end_s=100)[0]
+    out = sim.run_ensemble(2048, flags=0)
+    t = hs.engine.totals_to_dict(out["totals"])
+    assert t["replicas"] == 2048 and t["replicas_flagged"] == 0
+    assert t["events_processed"] == int(out["summaries"]["events_processed"].sum())
+    mean_lat = t["sum_latency"] / t["sink_events"]
+    assert 0.40 < mean_lat < 0.60            # M/M/1, rho = 0.8: W = 1 / (mu - lambda) = 0.5 s
+
+
+def test_engine_errors_surface_as_exceptions():
+    sim = quickstart(seed=1, end_s=5, rate=5000)[0]       # rho = 500: the device queue ring overflows
+    with pytest.raises(RuntimeError, match="overflow"):
+        sim.run()

@@ -285,18 +285,12 @@ def main():
     value = events / (ms * 1e-3)
 
     # ---- the single end-of-run NCCL all-reduce of the summary vector -----------
-    t = eng.read_totals()
-    vec_i = torch.tensor(list(t.i), dtype=torch.int64, device="cuda")
-    vec_f = torch.tensor(list(t.fsum), dtype=torch.float64, device="cuda")
-    vec_mn = torch.tensor([t.fmin], dtype=torch.float64, device="cuda")
-    vec_mx = torch.tensor([t.fmax], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(vec_i); dist.all_reduce(vec_f)
-        dist.all_reduce(vec_mn, op=dist.ReduceOp.MIN); dist.all_reduce(vec_mx, op=dist.ReduceOp.MAX)
-    agg = {"events_processed": int(vec_i[0]), "sink_events": int(vec_i[1]), "replicas": int(vec_i[5]),
-           "replicas_flagged": int(vec_i[6]),
-           "mean_latency_s": float(vec_f[0]) / max(1, int(vec_i[1])), "min_latency_s": float(vec_mn[0]),
-           "max_latency_s": float(vec_mx[0])}
+    from happysim_b200 import distributed as D
+    t = engine.totals_to_dict(D.allreduce_totals(eng.read_totals(), device="cuda"))
+    agg = {"events_processed": t["events_processed"], "sink_events": t["sink_events"], "replicas": t["replicas"],
+           "replicas_flagged": t["replicas_flagged"],
+           "mean_latency_s": t["sum_latency"] / max(1, t["sink_events"]), "min_latency_s": t["min_latency"],
+           "max_latency_s": t["max_latency"]}
 
     # ---- roofline of the dominant kernel (this rank's launches) -------------
     peak, peak_src = peaks()

@@ -197,7 +197,9 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
         }
     }
     const uint32_t S = (uint32_t)((live + 31) / 32) * 32;
-    const uint32_t block_bytes = (uint32_t)((sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + (size_t)S * 44 + 15) / 16 * 16);
+    if (S > 65535) return fail(HS_ERR_INVALID, "model needs %u future-event slots (limit 65535)", S);
+    const uint32_t block_bytes = (uint32_t)(sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + (((size_t)S * 46 + 15) / 16) * 16 +
+                                            (size_t)HS_W_NCAP * sizeof(hs_wnow));
     const uint32_t per_warp = 16 + block_bytes;
     const uint32_t smem_budget = 200 * 1024;
     if (per_warp > 227 * 1024 - 1024) return fail(HS_ERR_INVALID, "model too large for the warp engine (%u B of state per replica)", per_warp);

@@ -5,13 +5,21 @@
  * of shared memory with TMA bulk copies -- cp.async.bulk + mbarrier -- when a
  * paused window is resumed, and written back with cp.async.bulk when the window
  * ends):
- *     [ header 128 B | entity state n x 96 B | future-event list, SoA, S slots x 44 B ]
- * The future-event list (FEL) has S = 32 k slots; lane l owns slots l, l+32, ...
- * Popping the next event is a lane-parallel scan of the (time, sort_index) keys
- * followed by a 5-step __shfl_xor_sync min-reduction; the handler of the popped
- * event is the reference's handler, restated statement by statement, executed
- * by lane 0 (it is scalar control flow over one entity's state); queue contents
- * (FIFOQueue / LIFOQueue items) live in per-server rings in HBM.
+ *     [ header 128 B | entity state n x 96 B | future tier, SoA, S slots x 44 B |
+ *       free-slot stack S x 2 B | now tier, 24 entries x 48 B ]
+ * The pending-event set is kept in two tiers that together order exactly like the
+ * reference's heap (time, then sort index):
+ *   future tier  events scheduled later than `now` (SourceEvents, ProcessContinuations):
+ *                S = 32 k slots, lane l owns slots l, l+32, ...; its minimum is found by a
+ *                lane-parallel key scan + 5-step __shfl_xor_sync min-reduction and cached;
+ *                a push only compares the new key with the cached minimum.
+ *   now tier     events created at the current timestamp (the same-time protocol chain:
+ *                ENQUEUE, NOTIFY, POLL, DELIVER, WORKER, SINK, _lb_response): a small array
+ *                lane 0 scans by sort index.
+ * Lane 0 executes the reference's handlers (scalar control flow over one entity's state)
+ * and runs through a whole same-timestamp chain without involving the other lanes; the
+ * warp only cooperates to extract the future-tier minimum (twice per request for a
+ * Source -> Server path).  Queue contents live in per-server rings in HBM.
  *
  * This is the pop-invoke-push loop of happysimulator/core/simulation.py:449-505;
  * handlers: see oracle/hs_oracle.c for the one-to-one citations (identical
@@ -30,7 +38,7 @@ struct __align__(16) hs_warp_hdr {      /* 128 B */
     int64_t now; uint64_t ctr; int64_t processed; uint64_t hash;
     int64_t n_smp, n_svc;
     uint32_t rec_pos, smp_pos, svc_pos, status;
-    int32_t fel_n, done; uint32_t pad[14];
+    int32_t fel_n, done; int32_t now_n; uint32_t free_top; uint32_t pad[12];
 };
 
 struct __align__(16) hs_went {          /* 96 B per entity */
@@ -49,6 +57,12 @@ struct __align__(16) hs_went {          /* 96 B per entity */
 };
 
 struct hs_wring_entry { int64_t created; uint64_t idx; int64_t key; };   /* 24 B */
+
+#define HS_W_NCAP 24
+struct __align__(16) hs_wnow {          /* now-tier entry, 48 B */
+    int64_t time; uint64_t idx; int64_t created; uint64_t aux;
+    uint32_t m0; int32_t key; uint32_t hook; uint32_t pad;
+};
 
 struct hs_warp_model {
     const hs_entity_desc *ents;     /* device */
@@ -121,6 +135,7 @@ __device__ __forceinline__ void hs_tma_store_1d(void *gmem_dst, const void *smem
 /* ---- the kernel --------------------------------------------------------- */
 
 #define HS_W_EMPTY 0x7fffffffffffffffLL
+#define HS_W_NONE 0xffffffffu
 
 template <int FLAGS>
 __global__ void __launch_bounds__(256)
@@ -146,6 +161,8 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
     uint32_t *f_m0 = (uint32_t *)(felp + (size_t)S * 32);   /* kind | ent << 8              */
     int32_t *f_key = (int32_t *)(felp + (size_t)S * 36);
     uint32_t *f_hook = (uint32_t *)(felp + (size_t)S * 40); /* (lb_hook + 1) | poll << 31   */
+    uint16_t *f_free = (uint16_t *)(felp + (size_t)S * 44); /* stack of free future slots   */
+    hs_wnow *N = (hs_wnow *)(felp + (((size_t)S * 46 + 15) / 16) * 16);
 
     if (lane == 0) hs_mbar_init(mbar, 1);
     __syncwarp();
@@ -178,7 +195,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
         } else {
             for (uint32_t i = lane; i < M.block_bytes / 8; i += 32) ((uint64_t *)blk)[i] = 0ull;
             __syncwarp();
-            for (uint32_t i = lane; i < S; i += 32) f_time[i] = HS_W_EMPTY;
+            for (uint32_t i = lane; i < S; i += 32) { f_time[i] = HS_W_EMPTY; f_free[i] = (uint16_t)(S - 1 - i); }
             const uint32_t cell = M.n_cells ? (gidx / P.replicas_per_cell) % M.n_cells : 0u;
             for (uint32_t i = lane; i < ne; i += 32) {
                 const hs_entity_desc d = M.ents[i];
@@ -194,6 +211,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
             __syncwarp();
             if (lane == 0) {
                 H->hash = HS_HASH_INIT;
+                H->free_top = S;
                 /* Simulation.__init__: source.start() in order; bootstrap indices come from the
                  * global counter (simulation.py:77,145-154), run() restarts the per-heap one at 0. */
                 uint64_t boot = 0; int nf = 0;
@@ -206,9 +224,10 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         target = hs_exp1(u);
                     }
                     e->u.src.cur_ns = hs_next_arrival_ns(0, target, e->d0);
-                    if ((uint32_t)nf >= S) { H->status |= HS_ST_FEL_OVERFLOW; break; }
-                    f_time[nf] = e->u.src.cur_ns; f_idx[nf] = boot++; f_m0[nf] = HS_EV_SOURCE_TICK | (i << 8);
-                    f_key[nf] = -1; f_hook[nf] = 0; nf++;
+                    if (H->free_top == 0) { H->status |= HS_ST_FEL_OVERFLOW; break; }
+                    const uint32_t sl = f_free[--H->free_top];
+                    f_time[sl] = e->u.src.cur_ns; f_idx[sl] = boot++; f_m0[sl] = HS_EV_SOURCE_TICK | (i << 8);
+                    f_key[sl] = -1; f_hook[sl] = 0; nf++;
                 }
                 H->fel_n = nf; H->ctr = 0;
             }
@@ -221,217 +240,258 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
 
         /* ---- pop-invoke-push --------------------------------------------------- */
         bool paused = false;
+        /* cached minimum of the future tier (valid on lane 0) */
+        int64_t ft = HS_W_EMPTY; uint64_t fi = ~0ull; uint32_t fs = HS_W_NONE;
+        bool rescan = true;
         while (true) {
-            /* lane-parallel scan + shuffle min-reduction over (time, sort_index) */
-            int64_t bt = HS_W_EMPTY; uint64_t bi = ~0ull; uint32_t bs = 0xffffffffu;
-            for (uint32_t s = lane; s < S; s += 32) {
-                const int64_t t = f_time[s];
-                if (t != HS_W_EMPTY) {
-                    const uint64_t ix = f_idx[s];
-                    if (t < bt || (t == bt && ix < bi)) { bt = t; bi = ix; bs = s; }
+            if (rescan) {
+                /* lane-parallel scan + shuffle min-reduction over (time, sort_index) */
+                int64_t bt = HS_W_EMPTY; uint64_t bi = ~0ull; uint32_t bs = HS_W_NONE;
+                for (uint32_t s2 = lane; s2 < S; s2 += 32) {
+                    const int64_t t = f_time[s2];
+                    if (t != HS_W_EMPTY) {
+                        const uint64_t ix = f_idx[s2];
+                        if (t < bt || (t == bt && ix < bi)) { bt = t; bi = ix; bs = s2; }
+                    }
                 }
-            }
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                const int64_t ot = __shfl_xor_sync(0xffffffffu, bt, d);
-                const uint64_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
-                const uint32_t os = __shfl_xor_sync(0xffffffffu, bs, d);
-                if (ot < bt || (ot == bt && (oi < bi || (oi == bi && os < bs)))) { bt = ot; bi = oi; bs = os; }
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const int64_t ot = __shfl_xor_sync(0xffffffffu, bt, d);
+                    const uint64_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                    const uint32_t os = __shfl_xor_sync(0xffffffffu, bs, d);
+                    if (ot < bt || (ot == bt && (oi < bi || (oi == bi && os < bs)))) { bt = ot; bi = oi; bs = os; }
+                }
+                ft = bt; fi = bi; fs = bs;
+                rescan = false;
             }
-            int go = 0;        /* 0 stop, 1 processed an event, 2 paused */
+            int go = 0;        /* 0 stop, 1 extract the future-tier minimum, 2 paused */
             if (lane == 0) {
-                const int64_t now0 = H->now;
-                if (bs == 0xffffffffu || !(now0 <= P.end_ns) || (H->status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW))) go = 0;
-                else if (windowed && bt > P.window_end_ns) go = 2;
-                else {
-                    go = 1;
-                    /* ---- pop ---- */
-                    const uint32_t m0 = f_m0[bs];
-                    const int kind = (int)(m0 & 0xffu);
-                    const uint32_t ent = m0 >> 8;
-                    const int64_t e_created = f_created[bs];
-                    const uint64_t e_aux = f_aux[bs];
-                    const int32_t e_key = f_key[bs];
-                    const uint32_t e_hook = f_hook[bs];
-                    f_time[bs] = HS_W_EMPTY;
+                uint64_t ctr = H->ctr;
+                int now_n = H->now_n;
+                /* ---- lane 0 runs the same-timestamp chain on its own -------------- */
+                while (true) {
+                    const int64_t now0 = H->now;
+                    if (!(now0 <= P.end_ns) || (H->status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW))) { go = 0; break; }
+                    /* next event: minimum of the now tier, unless the future minimum sorts first */
+                    int nb = -1; int64_t nt = HS_W_EMPTY; uint64_t ni = ~0ull;
+                    for (int k = 0; k < now_n; ++k) {
+                        const int64_t t = N[k].time; const uint64_t ix = N[k].idx;
+                        if (t < nt || (t == nt && ix < ni)) { nt = t; ni = ix; nb = k; }
+                    }
+                    if (nb < 0 || (fs != HS_W_NONE && (ft < nt || (ft == nt && fi < ni)))) {
+                        if (fs == HS_W_NONE) { go = 0; break; }                 /* heap exhausted */
+                        if (windowed && ft > P.window_end_ns) { go = 2; break; }
+                        go = 1; break;
+                    }
+                    if (windowed && nt > P.window_end_ns) { go = 2; break; }
+                    /* ---- pop from the now tier ---- */
+                    const hs_wnow ev = N[nb];
+                    now_n--; N[nb] = N[now_n];
                     H->fel_n--;
-                    if (bt >= now0) {       /* else "time travel": skipped (simulation.py:479-489) */
-                        const int64_t now = bt;
-                        H->now = now;
-                        uint64_t ctr = H->ctr;
-                        if (FLAGS & HS_WF_HASH) H->hash = hs_hash_step(H->hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
-                        if ((FLAGS & HS_WF_REC) && rec) {
-                            hs_event_record rc; rc.time_ns = now; rc.sort_index = (uint32_t)bi; rc.kind = (uint8_t)kind;
-                            rc.pad = 0; rc.entity = (uint16_t)ent;
-                            rec[H->rec_pos] = rc; H->rec_pos = (H->rec_pos + 1 == P.record_cap) ? 0u : H->rec_pos + 1;
-                        }
-                        H->processed++;
-                        hs_went *X = &E[ent];
+                    if (ev.time < now0) continue;     /* "time travel": skipped (simulation.py:479-489) */
+                    const int64_t now = ev.time;
+                    const uint64_t bi = ev.idx;
+                    const int kind = (int)(ev.m0 & 0xffu);
+                    const uint32_t ent = ev.m0 >> 8;
+                    const int64_t e_created = ev.created;
+                    const uint64_t e_aux = ev.aux;
+                    const int32_t e_key = ev.key;
+                    const uint32_t e_hook = ev.hook;
+                    H->now = now;
+                    if (FLAGS & HS_WF_HASH) H->hash = hs_hash_step(H->hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
+                    if ((FLAGS & HS_WF_REC) && rec) {
+                        hs_event_record rc; rc.time_ns = now; rc.sort_index = (uint32_t)bi; rc.kind = (uint8_t)kind;
+                        rc.pad = 0; rc.entity = (uint16_t)ent;
+                        rec[H->rec_pos] = rc; H->rec_pos = (H->rec_pos + 1 == P.record_cap) ? 0u : H->rec_pos + 1;
+                    }
+                    H->processed++;
+                    hs_went *X = &E[ent];
 
-                        /* push helper: first free slot (lane 0 scans; the FEL is small) */
+                    /* push: an event at (or before) `now` joins the now tier, a later one the future
+                     * tier (free slot from the stack; the cached minimum is updated in place) */
 #define HS_W_PUSH(TIME, IDX, KIND, ENT, CREATED, AUX, KEY, HOOK)                                         \
     do {                                                                                                 \
-        uint32_t s_ = 0; while (s_ < S && f_time[s_] != HS_W_EMPTY) ++s_;                                \
-        if (s_ >= S) { H->status |= HS_ST_FEL_OVERFLOW; }                                                \
-        else { f_idx[s_] = (IDX); f_created[s_] = (CREATED); f_aux[s_] = (AUX);                          \
-               f_m0[s_] = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); f_key[s_] = (KEY); f_hook[s_] = (HOOK); \
-               f_time[s_] = (TIME); H->fel_n++; }                                                        \
+        const int64_t t_ = (TIME);                                                                       \
+        if (t_ <= now) {                                                                                 \
+            if (now_n >= HS_W_NCAP) H->status |= HS_ST_FEL_OVERFLOW;                                     \
+            else { hs_wnow n_; n_.time = t_; n_.idx = (IDX); n_.created = (CREATED); n_.aux = (AUX);     \
+                   n_.m0 = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); n_.key = (KEY); n_.hook = (HOOK); n_.pad = 0; \
+                   N[now_n++] = n_; H->fel_n++; }                                                        \
+        } else if (H->free_top == 0) H->status |= HS_ST_FEL_OVERFLOW;                                    \
+        else {                                                                                           \
+            const uint32_t s_ = f_free[--H->free_top]; const uint64_t i2_ = (IDX);                       \
+            f_idx[s_] = i2_; f_created[s_] = (CREATED); f_aux[s_] = (AUX);                               \
+            f_m0[s_] = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); f_key[s_] = (KEY); f_hook[s_] = (HOOK); \
+            f_time[s_] = t_; H->fel_n++;                                                                 \
+            if (fs == HS_W_NONE || t_ < ft || (t_ == ft && (i2_ < fi || (i2_ == fi && s_ < fs)))) { ft = t_; fi = i2_; fs = s_; } \
+        }                                                                                                \
     } while (0)
 #define HS_W_REQ_KIND(TGT) (M.ents[(TGT)].kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE :                   \
                             M.ents[(TGT)].kind == HS_ENT_SINK ? HS_EV_REQ_SINK :                         \
                             M.ents[(TGT)].kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : HS_EV_REQ_LB)
-                        /* Event._run_completion_hooks for a request whose plain handler returned:
-                         * only the LoadBalancer on_complete hook can be attached (event.py:277-283). */
+                    /* Event._run_completion_hooks for a request whose plain handler returned:
+                     * only the LoadBalancer on_complete hook can be attached (event.py:277-283). */
 #define HS_W_REQUEST_HOOKS()                                                                             \
     do {                                                                                                 \
         const uint32_t lbh_ = e_hook & 0x7fffffffu;                                                      \
         if (lbh_) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_LB_RESPONSE, lbh_ - 1u, 0, 0ull, -1, 0u); } \
     } while (0)
-                        /* QueueDriver schedule_poll hook (queue_driver.py:79-85) */
+                    /* QueueDriver schedule_poll hook (queue_driver.py:79-85) */
 #define HS_W_POLL_HOOK(SRV)                                                                              \
     do {                                                                                                 \
         if (E[(SRV)].u.srv.active < E[(SRV)].i0) { const uint64_t i_ = ctr++;                            \
             HS_W_PUSH(now, i_, HS_EV_POLL, (SRV), 0, 0ull, -1, 0u); }                                    \
     } while (0)
 
-                        switch (kind) {
-                        case HS_EV_SOURCE_TICK: {          /* Source.handle_event, source.py:142-180 */
-                            const hs_entity_desc d = M.ents[ent];
-                            bool have = false; uint64_t idxP = 0; int32_t key = -1;
-                            if (!(d.l0 >= 0 && now > d.l0)) {
-                                X->u.src.provider++;
-                                idxP = ctr++;
-                                if (d.i1 > 0) {
-                                    const double u = hs_uniform(seed, rid, HS_STREAM_ROUTING | (ent << 8), X->u.src.key_draws++);
-                                    key = (int32_t)HS_D2LL(HS_MUL(u, (double)d.i1));
-                                }
-                                have = true;
+                    switch (kind) {
+                    case HS_EV_SOURCE_TICK: {          /* Source.handle_event, source.py:142-180 */
+                        const hs_entity_desc d = M.ents[ent];
+                        bool have = false; uint64_t idxP = 0; int32_t key = -1;
+                        if (!(d.l0 >= 0 && now > d.l0)) {
+                            X->u.src.provider++;
+                            idxP = ctr++;
+                            if (d.i1 > 0) {
+                                const double u = hs_uniform(seed, rid, HS_STREAM_ROUTING | (ent << 8), X->u.src.key_draws++);
+                                key = (int32_t)HS_D2LL(HS_MUL(u, (double)d.i1));
                             }
-                            X->u.src.generated++;
-                            double target = 1.0;
-                            if (X->i0 == HS_ARR_POISSON) {
-                                const double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), X->u.src.arr_draws++);
-                                target = hs_exp1(u);
-                            }
-                            X->u.src.cur_ns = hs_next_arrival_ns(X->u.src.cur_ns, target, X->d0);
-                            const uint64_t idxT = ctr++;
-                            if (have) HS_W_PUSH(now, idxP, HS_W_REQ_KIND(d.target), d.target, now, 0ull, key, 0u);
-                            HS_W_PUSH(X->u.src.cur_ns, idxT, HS_EV_SOURCE_TICK, ent, 0, 0ull, -1, 0u);
-                            break;
+                            have = true;
                         }
-                        case HS_EV_REQ_LB: {               /* LoadBalancer._forward_request, :347-433 */
-                            const hs_entity_desc d = M.ents[ent];
-                            X->u.lb.received++;
-                            if (d.i2 > 0) {
-                                int slot;
-                                if (d.i0 == HS_LB_KEY_TABLE && e_key >= 0) slot = M.key_table[e_key];
-                                else { slot = (int)(X->u.lb.rr_index % (uint64_t)d.i2); X->u.lb.rr_index++; }
-                                const int be = M.backends[d.i1 + slot];
-                                X->u.lb.in_flight++; X->u.lb.forwarded++;
-                                const uint64_t i_ = ctr++;
-                                HS_W_PUSH(now, i_, HS_W_REQ_KIND(be), be, e_created, 0ull, e_key, ent + 1u);
-                            }
-                            HS_W_REQUEST_HOOKS();
-                            break;
+                        X->u.src.generated++;
+                        double target = 1.0;
+                        if (X->i0 == HS_ARR_POISSON) {
+                            const double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), X->u.src.arr_draws++);
+                            target = hs_exp1(u);
                         }
-                        case HS_EV_REQ_ENQUEUE: {          /* Queue._handle_enqueue, queue.py:122-147 */
-                            const hs_entity_desc d = M.ents[ent];
-                            const bool was_empty = (X->u.srv.q_len == 0);
-                            if (d.l0 >= 0 && (int64_t)X->u.srv.q_len >= d.l0) X->u.srv.dropped++;
-                            else if (X->u.srv.q_len >= P.ring) H->status |= HS_ST_QUEUE_OVERFLOW;
-                            else {
-                                hs_wring_entry *rg = ring0 + (size_t)M.srv_index[ent] * P.ring;
-                                hs_wring_entry q; q.created = e_created; q.idx = bi; q.key = e_key;
-                                rg[(X->u.srv.q_head + X->u.srv.q_len) & ring_mask] = q;
-                                X->u.srv.q_len++;
-                                X->u.srv.accepted++;
-                                if (was_empty) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_NOTIFY, ent, 0, 0ull, -1, 0u); }
-                            }
-                            HS_W_REQUEST_HOOKS();          /* _lb_response fires at ENQUEUE time */
-                            break;
-                        }
-                        case HS_EV_NOTIFY:                 /* QueueDriver._handle_notify, :92-99 */
-                            if (X->u.srv.active < X->i0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_POLL, ent, 0, 0ull, -1, 0u); }
-                            break;
-                        case HS_EV_POLL:                   /* Queue._handle_poll, queue.py:149-166 */
-                            if (X->u.srv.q_len > 0) {
-                                hs_wring_entry *rg = ring0 + (size_t)M.srv_index[ent] * P.ring;
-                                hs_wring_entry q;
-                                if (M.ents[ent].i1 == HS_Q_LIFO) q = rg[(X->u.srv.q_head + X->u.srv.q_len - 1) & ring_mask];
-                                else { q = rg[X->u.srv.q_head & ring_mask]; X->u.srv.q_head++; }
-                                X->u.srv.q_len--;
-                                const uint64_t i_ = ctr++;
-                                HS_W_PUSH(now, i_, HS_EV_DELIVER, ent, q.created, q.idx, (int32_t)q.key, 0u);
-                            }
-                            break;
-                        case HS_EV_DELIVER:                /* _handle_work_payload, queue_driver.py:78-90 */
-                            HS_W_PUSH(now, e_aux, HS_EV_REQ_WORKER, ent, e_created, 0ull, e_key, 0x80000000u);
-                            break;
-                        case HS_EV_REQ_WORKER: {           /* Server.handle_queued_event, first step */
-                            ctr++;                         /* inline ProcessContinuation (event.py:314-325) */
-                            if (X->u.srv.active >= X->i0) {
-                                X->u.srv.rejected++; H->status |= HS_ST_REJECT_PATH;
-                                HS_W_POLL_HOOK(ent);
-                                break;
-                            }
-                            X->u.srv.active++;
-                            int64_t dur;
-                            if (M.ents[ent].i2 == HS_SVC_EXPONENTIAL) {
-                                const double u = hs_uniform(seed, rid, HS_STREAM_SERVICE | (ent << 8), X->u.srv.svc_draws++);
-                                dur = hs_exp_latency_ns(u, X->lambda);
-                            } else dur = hs_seconds_to_ns(X->d0);
-                            const double svc_s = hs_ns_to_seconds(dur);
-                            if ((FLAGS & HS_WF_REC) && svc_out) { svc_out[H->svc_pos] = svc_s; H->svc_pos = (H->svc_pos + 1 == P.service_cap) ? 0u : H->svc_pos + 1; }
-                            H->n_svc++;
+                        X->u.src.cur_ns = hs_next_arrival_ns(X->u.src.cur_ns, target, X->d0);
+                        const uint64_t idxT = ctr++;
+                        if (have) HS_W_PUSH(now, idxP, HS_W_REQ_KIND(d.target), d.target, now, 0ull, key, 0u);
+                        HS_W_PUSH(X->u.src.cur_ns, idxT, HS_EV_SOURCE_TICK, ent, 0, 0ull, -1, 0u);
+                        break;
+                    }
+                    case HS_EV_REQ_LB: {               /* LoadBalancer._forward_request, :347-433 */
+                        const hs_entity_desc d = M.ents[ent];
+                        X->u.lb.received++;
+                        if (d.i2 > 0) {
+                            int slot;
+                            if (d.i0 == HS_LB_KEY_TABLE && e_key >= 0) slot = M.key_table[e_key];
+                            else { slot = (int)(X->u.lb.rr_index % (uint64_t)d.i2); X->u.lb.rr_index++; }
+                            const int be = M.backends[d.i1 + slot];
+                            X->u.lb.in_flight++; X->u.lb.forwarded++;
                             const uint64_t i_ = ctr++;
-                            HS_W_PUSH(hs_resume_ns(now, svc_s), i_, HS_EV_CONTINUATION, ent, e_created,
-                                      (uint64_t)__double_as_longlong(svc_s), e_key, e_hook & 0x80000000u);
+                            HS_W_PUSH(now, i_, HS_W_REQ_KIND(be), be, e_created, 0ull, e_key, ent + 1u);
+                        }
+                        HS_W_REQUEST_HOOKS();
+                        break;
+                    }
+                    case HS_EV_REQ_ENQUEUE: {          /* Queue._handle_enqueue, queue.py:122-147 */
+                        const hs_entity_desc d = M.ents[ent];
+                        const bool was_empty = (X->u.srv.q_len == 0);
+                        if (d.l0 >= 0 && (int64_t)X->u.srv.q_len >= d.l0) X->u.srv.dropped++;
+                        else if (X->u.srv.q_len >= P.ring) H->status |= HS_ST_QUEUE_OVERFLOW;
+                        else {
+                            hs_wring_entry *rg = ring0 + (size_t)M.srv_index[ent] * P.ring;
+                            hs_wring_entry q; q.created = e_created; q.idx = bi; q.key = e_key;
+                            rg[(X->u.srv.q_head + X->u.srv.q_len) & ring_mask] = q;
+                            X->u.srv.q_len++;
+                            X->u.srv.accepted++;
+                            if (was_empty) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_NOTIFY, ent, 0, 0ull, -1, 0u); }
+                        }
+                        HS_W_REQUEST_HOOKS();          /* _lb_response fires at ENQUEUE time */
+                        break;
+                    }
+                    case HS_EV_NOTIFY:                 /* QueueDriver._handle_notify, :92-99 */
+                        if (X->u.srv.active < X->i0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_POLL, ent, 0, 0ull, -1, 0u); }
+                        break;
+                    case HS_EV_POLL:                   /* Queue._handle_poll, queue.py:149-166 */
+                        if (X->u.srv.q_len > 0) {
+                            hs_wring_entry *rg = ring0 + (size_t)M.srv_index[ent] * P.ring;
+                            hs_wring_entry q;
+                            if (M.ents[ent].i1 == HS_Q_LIFO) q = rg[(X->u.srv.q_head + X->u.srv.q_len - 1) & ring_mask];
+                            else { q = rg[X->u.srv.q_head & ring_mask]; X->u.srv.q_head++; }
+                            X->u.srv.q_len--;
+                            const uint64_t i_ = ctr++;
+                            HS_W_PUSH(now, i_, HS_EV_DELIVER, ent, q.created, q.idx, (int32_t)q.key, 0u);
+                        }
+                        break;
+                    case HS_EV_DELIVER:                /* _handle_work_payload, queue_driver.py:78-90 */
+                        HS_W_PUSH(now, e_aux, HS_EV_REQ_WORKER, ent, e_created, 0ull, e_key, 0x80000000u);
+                        break;
+                    case HS_EV_REQ_WORKER: {           /* Server.handle_queued_event, first step */
+                        ctr++;                         /* inline ProcessContinuation (event.py:314-325) */
+                        if (X->u.srv.active >= X->i0) {
+                            X->u.srv.rejected++; H->status |= HS_ST_REJECT_PATH;
+                            HS_W_POLL_HOOK(ent);
                             break;
                         }
-                        case HS_EV_CONTINUATION: {         /* generator resumes, server.py:255-273 */
-                            X->u.srv.active = X->u.srv.active > 0 ? X->u.srv.active - 1 : 0;
-                            X->u.srv.completed++;
-                            X->u.srv.total_service = HS_ADD(X->u.srv.total_service, __longlong_as_double((long long)e_aux));
-                            const int tgt = M.ents[ent].target;
-                            if (tgt >= 0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_W_REQ_KIND(tgt), tgt, e_created, 0ull, e_key, 0u); }
-                            if (e_hook & 0x80000000u) HS_W_POLL_HOOK(ent);
-                            break;
-                        }
-                        case HS_EV_REQ_SINK: {             /* Sink.handle_event, common.py:36-44 */
-                            X->u.snk.received++;
-                            const double lat = hs_ns_to_seconds(now - e_created);
-                            hs_neumaier_add(&X->u.snk.sum, &X->u.snk.comp, lat);
-                            X->u.snk.sumsq = HS_ADD(X->u.snk.sumsq, HS_MUL(lat, lat));
-                            if (lat < X->u.snk.mn) X->u.snk.mn = lat;
-                            if (lat > X->u.snk.mx) X->u.snk.mx = lat;
-                            if ((FLAGS & HS_WF_REC) && smp) { hs_sink_sample q; q.completion_ns = now; q.latency_s = lat; smp[H->smp_pos] = q;
-                                H->smp_pos = (H->smp_pos + 1 == P.sample_cap) ? 0u : H->smp_pos + 1; }
-                            H->n_smp++;
-                            HS_W_REQUEST_HOOKS();
-                            break;
-                        }
-                        case HS_EV_REQ_COUNTER:            /* Counter.handle_event, common.py:92-95 */
-                            X->u.snk.received++;
-                            HS_W_REQUEST_HOOKS();
-                            break;
-                        case HS_EV_LB_RESPONSE:            /* LoadBalancer._handle_response, :435-473 */
-                            if (X->u.lb.in_flight > 0) X->u.lb.in_flight--;
-                            X->u.lb.responses++;
-                            break;
-                        default: break;
-                        }
-                        H->ctr = ctr;
+                        X->u.srv.active++;
+                        int64_t dur;
+                        if (M.ents[ent].i2 == HS_SVC_EXPONENTIAL) {
+                            const double u = hs_uniform(seed, rid, HS_STREAM_SERVICE | (ent << 8), X->u.srv.svc_draws++);
+                            dur = hs_exp_latency_ns(u, X->lambda);
+                        } else dur = hs_seconds_to_ns(X->d0);
+                        const double svc_s = hs_ns_to_seconds(dur);
+                        if ((FLAGS & HS_WF_REC) && svc_out) { svc_out[H->svc_pos] = svc_s; H->svc_pos = (H->svc_pos + 1 == P.service_cap) ? 0u : H->svc_pos + 1; }
+                        H->n_svc++;
+                        const uint64_t i_ = ctr++;
+                        HS_W_PUSH(hs_resume_ns(now, svc_s), i_, HS_EV_CONTINUATION, ent, e_created,
+                                  (uint64_t)__double_as_longlong(svc_s), e_key, e_hook & 0x80000000u);
+                        break;
+                    }
+                    case HS_EV_CONTINUATION: {         /* generator resumes, server.py:255-273 */
+                        X->u.srv.active = X->u.srv.active > 0 ? X->u.srv.active - 1 : 0;
+                        X->u.srv.completed++;
+                        X->u.srv.total_service = HS_ADD(X->u.srv.total_service, __longlong_as_double((long long)e_aux));
+                        const int tgt = M.ents[ent].target;
+                        if (tgt >= 0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_W_REQ_KIND(tgt), tgt, e_created, 0ull, e_key, 0u); }
+                        if (e_hook & 0x80000000u) HS_W_POLL_HOOK(ent);
+                        break;
+                    }
+                    case HS_EV_REQ_SINK: {             /* Sink.handle_event, common.py:36-44 */
+                        X->u.snk.received++;
+                        const double lat = hs_ns_to_seconds(now - e_created);
+                        hs_neumaier_add(&X->u.snk.sum, &X->u.snk.comp, lat);
+                        X->u.snk.sumsq = HS_ADD(X->u.snk.sumsq, HS_MUL(lat, lat));
+                        if (lat < X->u.snk.mn) X->u.snk.mn = lat;
+                        if (lat > X->u.snk.mx) X->u.snk.mx = lat;
+                        if ((FLAGS & HS_WF_REC) && smp) { hs_sink_sample q; q.completion_ns = now; q.latency_s = lat; smp[H->smp_pos] = q;
+                            H->smp_pos = (H->smp_pos + 1 == P.sample_cap) ? 0u : H->smp_pos + 1; }
+                        H->n_smp++;
+                        HS_W_REQUEST_HOOKS();
+                        break;
+                    }
+                    case HS_EV_REQ_COUNTER:            /* Counter.handle_event, common.py:92-95 */
+                        X->u.snk.received++;
+                        HS_W_REQUEST_HOOKS();
+                        break;
+                    case HS_EV_LB_RESPONSE:            /* LoadBalancer._handle_response, :435-473 */
+                        if (X->u.lb.in_flight > 0) X->u.lb.in_flight--;
+                        X->u.lb.responses++;
+                        break;
+                    default: break;
+                    }
 #undef HS_W_PUSH
 #undef HS_W_REQ_KIND
 #undef HS_W_REQUEST_HOOKS
 #undef HS_W_POLL_HOOK
+                }
+                /* ---- extract the future-tier minimum into the now tier ------------- */
+                if (go == 1) {
+                    if (now_n >= HS_W_NCAP) { H->status |= HS_ST_FEL_OVERFLOW; go = 0; }
+                    else {
+                        hs_wnow n_; n_.time = ft; n_.idx = fi; n_.created = f_created[fs]; n_.aux = f_aux[fs];
+                        n_.m0 = f_m0[fs]; n_.key = f_key[fs]; n_.hook = f_hook[fs]; n_.pad = 0;
+                        N[now_n++] = n_;
+                        f_time[fs] = HS_W_EMPTY;
+                        f_free[H->free_top++] = (uint16_t)fs;
                     }
                 }
+                H->ctr = ctr; H->now_n = now_n;
             }
             go = __shfl_sync(0xffffffffu, go, 0);
             __syncwarp();
             if (go == 2) paused = true;
             if (go != 1) break;
+            rescan = true;
         }
 
         /* ---- publish + write the block back -------------------------------- */

@@ -27,4 +27,4 @@ if __name__ == "__main__":
     tab = hs.consistent_hash_table([f"S{i}" for i in range(1024)], 100, 10000)
     run("configs[3] chash 1024 nodes", hs.lb_key_table(tab, 1024, rate=8192.0), 1024, 2.0)
     m = hs.mmc_sweep()
-    run("configs[4] M/M/c sweep 256 cells", m, 32768, 100.0, replicas_per_cell=128)
+    run("configs[4] M/M/c sweep 256 cells", m, 32768, 100.0, replicas_per_cell=128, queue_ring=4096)

@@ -19,7 +19,7 @@ HS_LB_ROUND_ROBIN, HS_LB_KEY_TABLE = 0, 1
 EVENT_KIND_NAMES = ["SOURCE_TICK", "REQ_LB", "REQ_ENQUEUE", "NOTIFY", "POLL", "DELIVER",
                     "REQ_WORKER", "CONTINUATION", "REQ_SINK", "LB_RESPONSE", "REQ_COUNTER"]
 
-HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH = 1, 2, 4
+HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH, HS_ST_TRACE_EXHAUSTED = 1, 2, 4, 8
 
 HS_STREAM_ARRIVAL, HS_STREAM_SERVICE, HS_STREAM_ROUTING = 0, 1, 2
 

@@ -466,6 +466,24 @@ class SimulationSummary:
                 "entities": {k: vars(v) for k, v in self.entities.items()}}
 
 
+def stock_streams(seed: int, n_replicas: int, n_draws: int, seed_stride: int = 1):
+    """The reference's two process-global MT19937 streams as unit-rate exponential variates:
+    row r is what ``random.seed(seed + r*seed_stride); numpy.random.seed(seed + r*seed_stride)`` yields.
+    arrival: -math.log(1.0 - numpy.random.random())   (load/providers/poisson_arrival.py:31)
+    service: -math.log(1.0 - random.random())         (random.expovariate, distributions/exponential.py:43)
+    math.log is the host libm the reference itself calls."""
+    import random as _random
+    arr = np.empty((n_replicas, n_draws), np.float64)
+    svc = np.empty((n_replicas, n_draws), np.float64)
+    for r in range(n_replicas):
+        s = seed + r * seed_stride
+        u = np.random.RandomState(s).random_sample(n_draws)
+        arr[r] = [-math.log(1.0 - x) for x in u]
+        rnd = _random.Random(s)
+        svc[r] = [-math.log(1.0 - rnd.random()) for _ in range(n_draws)]
+    return arr, svc
+
+
 _engines: dict[int, Engine] = {}
 
 
@@ -483,7 +501,7 @@ class Simulation:
 
     def __init__(self, start_time: Instant | None = None, end_time: Instant | None = None, sources=None,
                  entities=None, probes=None, trace_recorder=None, fault_schedule=None, duration: float | None = None,
-                 *, seed: int | None = None, replica: int = 0, device: int = 0):
+                 *, seed: int | None = None, replica: int = 0, device: int = 0, rng: str = "philox"):
         if duration is not None and end_time is not None:
             raise ValueError("Cannot specify both 'duration' and 'end_time'")
         if start_time is not None and start_time.nanoseconds != 0:
@@ -504,6 +522,9 @@ class Simulation:
         self._seed = default_seed if seed is None else int(seed)
         self._replica = int(replica)
         self._device = device
+        if rng not in ("philox", "stock"):
+            raise ValueError("rng must be 'philox' or 'stock'")
+        self._rng = rng
         self._summary: SimulationSummary | None = None
         self._instant_cls = Instant
         self.model, self.objects = lowering.lower(self._sources, self._entities)
@@ -527,7 +548,11 @@ class Simulation:
         eng = _engine(self._device)
         eng.upload(self.model)
         caps = self._caps()
-        need_events = len(self.model.ids_of(A.HS_ENT_SERVER)) > 1     # per-server service-time lists
+        eng.set_trace(None, None)
+        if getattr(self, "_rng", "philox") == "stock":
+            eng.set_trace(*stock_streams(self._seed, 1, caps["sample_cap"] * 2 + 64))
+        # per-server service-time lists / per-collector samples are demultiplexed with the event records
+        need_events = len(self.model.ids_of(A.HS_ENT_SERVER)) > 1 or len(self.model.ids_of(A.HS_ENT_SINK)) > 1
         for _ in range(6):
             kw = dict(caps)
             if need_events:
@@ -536,6 +561,10 @@ class Simulation:
                                 n_replicas=1, flags=0, **kw))
             out = eng.read_outputs()
             s = out["summaries"][0]
+            if int(s["status"]) & A.HS_ST_TRACE_EXHAUSTED:
+                caps = {k: 2 * v for k, v in caps.items()}
+                eng.set_trace(*stock_streams(self._seed, 1, caps["sample_cap"] * 2 + 64))
+                continue
             if int(s["status"]) & (A.HS_ST_QUEUE_OVERFLOW | A.HS_ST_FEL_OVERFLOW):
                 raise RuntimeError(f"device structure overflow (status {int(s['status'])}); raise queue_ring")
             if (int(s["n_sink_samples"]) <= kw["sample_cap"] and int(s["n_service_samples"]) <= kw["service_cap"]
@@ -563,6 +592,15 @@ class Simulation:
         sinks = self.model.ids_of(A.HS_ENT_SINK)
         servers = self.model.ids_of(A.HS_ENT_SERVER)
         per_server = {i: [] for i in servers}
+        per_sink = {i: None for i in sinks}
+        if samples is not None:
+            if len(sinks) == 1:
+                per_sink[sinks[0]] = samples
+            elif out.get("records") is not None:
+                rec = out["records"][r][: int(s["events_processed"])]
+                who = rec["entity"][rec["kind"] == A.HS_EV_REQ_SINK][: len(samples)]
+                for i in sinks:
+                    per_sink[i] = samples[who == i]
         if out.get("service_samples") is not None:
             svc = out["service_samples"][r][:n_svc]
             if len(servers) == 1:
@@ -583,12 +621,20 @@ class Simulation:
                 o._requests_completed, o._requests_rejected = int(row["c2"]), int(row["c3"])
                 o._total_service_time = float(row["f0"])
                 o._service_times = per_server[i]
+            elif k == A.HS_ENT_SINK and hasattr(o, "data"):          # LatencyTracker / ThroughputTracker
+                o.count = int(row["c0"])
+                sm = per_sink[i]
+                if sm is not None:
+                    one = getattr(o, "_sample_value", None) == "one" or type(o).__name__ == "ThroughputTracker"
+                    o.data._samples = [(float(int(t)) / 1_000_000_000, 1.0 if one else float(x))
+                                       for t, x in zip(sm["completion_ns"], sm["latency_s"])]
             elif k == A.HS_ENT_SINK:
                 o.events_received = int(row["c0"])
                 o._latency_sum = float(row["f0"])
-                if samples is not None and len(sinks) == 1:
-                    o.completion_times = [self._instant_cls(int(t)) for t in samples["completion_ns"]]
-                    o.latencies_s = [float(x) for x in samples["latency_s"]]
+                sm = per_sink[i]
+                if sm is not None:
+                    o.completion_times = [self._instant_cls(int(t)) for t in sm["completion_ns"]]
+                    o.latencies_s = [float(x) for x in sm["latency_s"]]
             elif k == A.HS_ENT_COUNTER:
                 o.total = int(row["c0"])
                 o.by_type = {"Request": o.total} if o.total else {}

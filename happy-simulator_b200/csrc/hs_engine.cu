@@ -80,6 +80,7 @@ struct hs_engine {
     hs_run_params last;
     int last_engine = 0;
     uint32_t last_ring = 0;
+    dev_buf d_trace_arr, d_trace_svc; uint64_t n_trace_arr = 0, n_trace_svc = 0; uint32_t trace_replicas = 0;
     dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals, d_srv_index, d_counter;
 };
 
@@ -233,6 +234,8 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     R.n_replicas = n; R.index_base = p->replica_index_base; R.replicas_per_cell = p->replicas_per_cell;
     R.record_cap = p->record_cap; R.sample_cap = p->sample_cap; R.service_cap = p->service_cap;
     R.ring = ring; R.resume = p->resume;
+    R.trace_arr = E->n_trace_arr ? (const double *)E->d_trace_arr.p : nullptr; R.n_trace_arr = E->n_trace_arr;
+    R.trace_svc = E->n_trace_svc ? (const double *)E->d_trace_svc.p : nullptr; R.n_trace_svc = E->n_trace_svc;
     hs_warp_out O;
     O.summaries = (hs_replica_summary *)E->d_summ.p; O.stats = (hs_entity_stats *)E->d_stats.p;
     O.records = p->record_cap ? (hs_event_record *)E->d_rec.p : nullptr;
@@ -301,7 +304,7 @@ int hs_engine_destroy(hs_engine *E)
     cudaStreamSynchronize(E->stream);
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
                        &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
-                       &E->d_srv_index, &E->d_counter};
+                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
@@ -358,6 +361,8 @@ int hs_run(hs_engine *E, const hs_run_params *p)
     if (p->replicas_per_cell == 0) return fail(HS_ERR_INVALID, "replicas_per_cell must be >= 1");
     CUDA_TRY(cudaSetDevice(E->device));
 
+    if ((E->n_trace_arr || E->n_trace_svc) && p->n_replicas > E->trace_replicas)
+        return fail(HS_ERR_INVALID, "hs_set_trace supplied draws for %u replicas, run asks for %u", E->trace_replicas, p->n_replicas);
     int engine = (int)p->engine;
     if (engine == 0) engine = E->lane_ok ? 2 : 1;
     if (engine == 2 && !E->lane_ok) return fail(HS_ERR_INVALID, "lane engine needs Source -> Server(concurrency 1) -> Sink|Counter");
@@ -407,6 +412,8 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         R.n_replicas = n; R.index_base = p->replica_index_base; R.replicas_per_cell = p->replicas_per_cell;
         R.record_cap = p->record_cap; R.sample_cap = p->sample_cap; R.service_cap = p->service_cap;
         R.ring = ring; R.resume = p->resume;
+        R.trace_arr = E->n_trace_arr ? (const double *)E->d_trace_arr.p : nullptr; R.n_trace_arr = E->n_trace_arr;
+        R.trace_svc = E->n_trace_svc ? (const double *)E->d_trace_svc.p : nullptr; R.n_trace_svc = E->n_trace_svc;
         hs_lane_out O;
         O.summaries = (hs_replica_summary *)E->d_summ.p; O.stats = (hs_entity_stats *)E->d_stats.p;
         O.records = p->record_cap ? (hs_event_record *)E->d_rec.p : nullptr;
@@ -431,6 +438,29 @@ int hs_run(hs_engine *E, const hs_run_params *p)
     E->last = *p;
     E->last_engine = engine;
     E->have_run = true;
+    return HS_OK;
+}
+
+int hs_set_trace(hs_engine *E, const double *arr, uint64_t n_arr, const double *svc, uint64_t n_svc, uint32_t n_replicas)
+{
+    if (!E) return fail(HS_ERR_INVALID, "engine is NULL");
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    E->n_trace_arr = E->n_trace_svc = 0; E->trace_replicas = 0;
+    if ((!arr || !n_arr) && (!svc || !n_svc)) return HS_OK;
+    if (n_replicas == 0) return fail(HS_ERR_INVALID, "n_replicas must be > 0");
+    int rc;
+    if (arr && n_arr) {
+        if ((rc = E->d_trace_arr.ensure((size_t)n_replicas * n_arr * 8))) return rc;
+        CUDA_TRY(cudaMemcpy(E->d_trace_arr.p, arr, (size_t)n_replicas * n_arr * 8, cudaMemcpyHostToDevice));
+        E->n_trace_arr = n_arr;
+    }
+    if (svc && n_svc) {
+        if ((rc = E->d_trace_svc.ensure((size_t)n_replicas * n_svc * 8))) return rc;
+        CUDA_TRY(cudaMemcpy(E->d_trace_svc.p, svc, (size_t)n_replicas * n_svc * 8, cudaMemcpyHostToDevice));
+        E->n_trace_svc = n_svc;
+    }
+    E->trace_replicas = n_replicas;
     return HS_OK;
 }
 

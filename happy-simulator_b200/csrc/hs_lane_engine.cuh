@@ -113,6 +113,8 @@ struct hs_lane_run {
     int64_t end_ns, window_end_ns;
     uint32_t n_replicas, index_base, replicas_per_cell;
     uint32_t record_cap, sample_cap, service_cap, ring, resume;
+    const double *trace_arr, *trace_svc;    /* externally supplied draws (hs_set_trace) or NULL */
+    uint64_t n_trace_arr, n_trace_svc;
 };
 
 struct hs_lane_out {
@@ -242,24 +244,38 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
 #define HS_REFILL_ROUND()                                                                    \
     do {                                                                                     \
         if (!finished && (uint32_t)(a_gen - arr_draws) + 2u <= HS_DRAW_BUF) {                \
-            double u0_ = 0.0, u1_ = 0.0;                                                     \
-            if (poisson) hs_uniform_pair(seed, rid, sid_arr, a_gen >> 1, &u0_, &u1_);        \
+            double u0_ = 0.0, u1_ = 0.0, g0_ = 1.0, g1_ = 1.0;                               \
+            if (poisson && !P.trace_arr) { hs_uniform_pair(seed, rid, sid_arr, a_gen >> 1, &u0_, &u1_); \
+                                           g0_ = hs_exp1(u0_); g1_ = hs_exp1(u1_); }         \
+            if (poisson && P.trace_arr) {                                                    \
+                const uint64_t k_ = a_gen & ~1ull;                                           \
+                if (k_ + 1 >= P.n_trace_arr) { status |= HS_ST_TRACE_EXHAUSTED; finished = true; } \
+                else { g0_ = P.trace_arr[(size_t)r * P.n_trace_arr + k_]; g1_ = P.trace_arr[(size_t)r * P.n_trace_arr + k_ + 1]; } \
+            }                                                                                \
             if (!(a_gen & 1)) {                                                              \
-                t_gen = HS_NEXT_ARRIVAL(t_gen, poisson ? hs_exp1(u0_) : 1.0); a_gen++;       \
+                t_gen = HS_NEXT_ARRIVAL(t_gen, g0_); a_gen++;                                \
                 sh_t[a_gen % HS_DRAW_BUF][tid] = t_gen;                                      \
             }                                                                                \
-            t_gen = HS_NEXT_ARRIVAL(t_gen, poisson ? hs_exp1(u1_) : 1.0); a_gen++;           \
+            t_gen = HS_NEXT_ARRIVAL(t_gen, g1_); a_gen++;                                    \
             sh_t[a_gen % HS_DRAW_BUF][tid] = t_gen;                                          \
         }                                                                                    \
         if (!finished && (uint32_t)(s_gen - (uint64_t)n_svc) + 2u <= HS_DRAW_BUF) {          \
             double u0_ = 0.0, u1_ = 0.0;                                                     \
-            if (expo) hs_uniform_pair(seed, rid, sid_svc, s_gen >> 1, &u0_, &u1_);           \
+            int64_t d0_ = hs_seconds_to_ns(mean), d1_ = d0_;                                 \
+            if (expo && !P.trace_svc) { hs_uniform_pair(seed, rid, sid_svc, s_gen >> 1, &u0_, &u1_); \
+                                        d0_ = hs_exp_latency_ns(u0_, lambda); d1_ = hs_exp_latency_ns(u1_, lambda); } \
+            if (expo && P.trace_svc) {       /* Duration.from_seconds(-log(1-U) / lambda)         */ \
+                const uint64_t k_ = s_gen & ~1ull;                                           \
+                if (k_ + 1 >= P.n_trace_svc) { status |= HS_ST_TRACE_EXHAUSTED; finished = true; } \
+                else { d0_ = hs_seconds_to_ns(HS_DIV(P.trace_svc[(size_t)r * P.n_trace_svc + k_], lambda));  \
+                       d1_ = hs_seconds_to_ns(HS_DIV(P.trace_svc[(size_t)r * P.n_trace_svc + k_ + 1], lambda)); } \
+            }                                                                                \
             if (!(s_gen & 1)) {                                                              \
-                const double s0_ = hs_ns_to_seconds(expo ? hs_exp_latency_ns(u0_, lambda) : hs_seconds_to_ns(mean)); \
+                const double s0_ = hs_ns_to_seconds(d0_);                                    \
                 sh_svc[s_gen % HS_DRAW_BUF][tid] = s0_;                                      \
                 s_gen++;                                                                     \
             }                                                                                \
-            const double s1_ = hs_ns_to_seconds(expo ? hs_exp_latency_ns(u1_, lambda) : hs_seconds_to_ns(mean));     \
+            const double s1_ = hs_ns_to_seconds(d1_);                                        \
             sh_svc[s_gen % HS_DRAW_BUF][tid] = s1_;                                          \
             s_gen++;                                                                         \
         }                                                                                    \

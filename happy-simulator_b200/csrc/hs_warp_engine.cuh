@@ -38,7 +38,9 @@ struct __align__(16) hs_warp_hdr {      /* 128 B */
     int64_t now; uint64_t ctr; int64_t processed; uint64_t hash;
     int64_t n_smp, n_svc;
     uint32_t rec_pos, smp_pos, svc_pos, status;
-    int32_t fel_n, done; int32_t now_n; uint32_t free_top; uint32_t pad[12];
+    int32_t fel_n, done; int32_t now_n; uint32_t free_top;
+    uint64_t np_cursor, py_cursor;      /* shared cursors of the externally supplied streams */
+    uint32_t pad[8];
 };
 
 struct __align__(16) hs_went {          /* 96 B per entity */
@@ -78,6 +80,8 @@ struct hs_warp_run {
     int64_t end_ns, window_end_ns;
     uint32_t n_replicas, index_base, replicas_per_cell;
     uint32_t record_cap, sample_cap, service_cap, ring, resume;
+    const double *trace_arr, *trace_svc;
+    uint64_t n_trace_arr, n_trace_svc;
 };
 
 struct hs_warp_out {
@@ -219,7 +223,10 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                     if (M.ents[i].kind != HS_ENT_SOURCE) continue;
                     hs_went *e = &E[i];
                     double target = 1.0;
-                    if (e->i0 == HS_ARR_POISSON) {
+                    if (e->i0 == HS_ARR_POISSON && P.trace_arr) {
+                        if (H->np_cursor >= P.n_trace_arr) { H->status |= HS_ST_TRACE_EXHAUSTED; break; }
+                        target = P.trace_arr[(size_t)r * P.n_trace_arr + H->np_cursor++]; e->u.src.arr_draws++;
+                    } else if (e->i0 == HS_ARR_POISSON) {
                         double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (i << 8), e->u.src.arr_draws++);
                         target = hs_exp1(u);
                     }
@@ -271,7 +278,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                 /* ---- lane 0 runs the same-timestamp chain on its own -------------- */
                 while (true) {
                     const int64_t now0 = H->now;
-                    if (!(now0 <= P.end_ns) || (H->status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW))) { go = 0; break; }
+                    if (!(now0 <= P.end_ns) || (H->status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW | HS_ST_TRACE_EXHAUSTED))) { go = 0; break; }
                     /* next event: minimum of the now tier, unless the future minimum sorts first */
                     int nb = -1; int64_t nt = HS_W_EMPTY; uint64_t ni = ~0ull;
                     for (int k = 0; k < now_n; ++k) {
@@ -358,7 +365,10 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         }
                         X->u.src.generated++;
                         double target = 1.0;
-                        if (X->i0 == HS_ARR_POISSON) {
+                        if (X->i0 == HS_ARR_POISSON && P.trace_arr) {
+                            if (H->np_cursor >= P.n_trace_arr) { H->status |= HS_ST_TRACE_EXHAUSTED; H->np_cursor = 0; }
+                            target = P.trace_arr[(size_t)r * P.n_trace_arr + H->np_cursor++]; X->u.src.arr_draws++;
+                        } else if (X->i0 == HS_ARR_POISSON) {
                             const double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), X->u.src.arr_draws++);
                             target = hs_exp1(u);
                         }
@@ -425,7 +435,10 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         }
                         X->u.srv.active++;
                         int64_t dur;
-                        if (M.ents[ent].i2 == HS_SVC_EXPONENTIAL) {
+                        if (M.ents[ent].i2 == HS_SVC_EXPONENTIAL && P.trace_svc) {
+                            if (H->py_cursor >= P.n_trace_svc) { H->status |= HS_ST_TRACE_EXHAUSTED; H->py_cursor = 0; }
+                            dur = hs_seconds_to_ns(HS_DIV(P.trace_svc[(size_t)r * P.n_trace_svc + H->py_cursor++], X->lambda)); X->u.srv.svc_draws++;
+                        } else if (M.ents[ent].i2 == HS_SVC_EXPONENTIAL) {
                             const double u = hs_uniform(seed, rid, HS_STREAM_SERVICE | (ent << 8), X->u.srv.svc_draws++);
                             dur = hs_exp_latency_ns(u, X->lambda);
                         } else dur = hs_seconds_to_ns(X->d0);

@@ -26,7 +26,7 @@ class EngineError(RuntimeError):
 _lib = None
 
 EXPORTED_SYMBOLS = ["hs_version", "hs_last_error", "hs_engine_create", "hs_engine_destroy", "hs_model_upload",
-                    "hs_model_validate", "hs_run", "hs_sync", "hs_last_run_ms", "hs_launch_count",
+                    "hs_model_validate", "hs_run", "hs_set_trace", "hs_sync", "hs_last_run_ms", "hs_launch_count",
                     "hs_read_outputs", "hs_read_totals", "hs_totals_device_ptr"]
 
 
@@ -48,6 +48,7 @@ def load_library(path: str | None = None):
         "hs_model_upload": ([H, C.POINTER(A.ModelDesc)], C.c_int),
         "hs_model_validate": ([C.POINTER(A.ModelDesc)], C.c_int),
         "hs_run": ([H, C.POINTER(A.RunParams)], C.c_int),
+        "hs_set_trace": ([H, C.POINTER(C.c_double), C.c_uint64, C.POINTER(C.c_double), C.c_uint64, C.c_uint32], C.c_int),
         "hs_sync": ([H], C.c_int),
         "hs_last_run_ms": ([H, C.POINTER(C.c_float)], C.c_int),
         "hs_launch_count": ([H, C.POINTER(C.c_uint64)], C.c_int),
@@ -116,6 +117,17 @@ class Engine:
         d = model.desc()
         _check(self._L, self._L.hs_model_upload(self._h, C.byref(d)))
         self._model = model
+
+    def set_trace(self, arrival_targets=None, service_samples=None) -> None:
+        """Externally supplied draws, float64 [n_replicas, n] each (None/None: back to Philox)."""
+        if arrival_targets is None and service_samples is None:
+            _check(self._L, self._L.hs_set_trace(self._h, None, 0, None, 0, 0))
+            return
+        a = np.ascontiguousarray(arrival_targets, dtype=np.float64)
+        s = np.ascontiguousarray(service_samples, dtype=np.float64)
+        assert a.ndim == 2 and s.ndim == 2 and a.shape[0] == s.shape[0]
+        _check(self._L, self._L.hs_set_trace(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[1],
+                                             s.ctypes.data_as(C.POINTER(C.c_double)), s.shape[1], a.shape[0]))
 
     def run(self, params: A.RunParams) -> None:
         _check(self._L, self._L.hs_run(self._h, C.byref(params)))

@@ -1,0 +1,160 @@
+"""Host-side mirrors of the reference's sample containers and collector entities.
+
+``Data`` / ``BucketedData`` (instrumentation/data.py:19-270) are analysis utilities over
+(time_s, value) samples; ``LatencyTracker`` / ``ThroughputTracker``
+(instrumentation/collectors.py:18-89) are Sink-like entities whose ``handle_event`` the
+device runs as HS_EV_REQ_SINK; ``Simulation.run()`` fills their ``data`` from the recorder
+samples.  Aggregations follow the reference's expressions (CPython float ``sum`` etc.)."""
+from __future__ import annotations
+
+import math
+import statistics
+from collections import defaultdict
+from typing import Any
+
+
+def _percentile_sorted(sorted_values, p: float) -> float:
+    """instrumentation/data.py:197-210"""
+    if not sorted_values:
+        return 0.0
+    if p <= 0:
+        return float(sorted_values[0])
+    if p >= 1:
+        return float(sorted_values[-1])
+    n = len(sorted_values)
+    pos = p * (n - 1)
+    lo = int(pos)
+    hi = min(lo + 1, n - 1)
+    frac = pos - lo
+    return float(sorted_values[lo] * (1.0 - frac) + sorted_values[hi] * frac)
+
+
+class BucketedData:
+    """instrumentation/data.py:213-270"""
+
+    def __init__(self) -> None:
+        self._times, self._means, self._counts = [], [], []
+        self._maxes, self._sums, self._p50s, self._p99s = [], [], [], []
+
+    def times(self): return self._times
+    def means(self): return self._means
+    def counts(self): return self._counts
+    def maxes(self): return self._maxes
+    def sums(self): return self._sums
+    def p50s(self): return self._p50s
+    def p99s(self): return self._p99s
+
+    def to_dict(self) -> dict[str, list]:
+        return {"time_s": list(self._times), "mean": list(self._means), "p50": list(self._p50s),
+                "p99": list(self._p99s), "max": list(self._maxes), "count": list(self._counts),
+                "sum": list(self._sums)}
+
+    def __len__(self): return len(self._times)
+    def __bool__(self): return len(self._times) > 0
+
+
+class Data:
+    """instrumentation/data.py:19-195"""
+
+    def __init__(self) -> None:
+        self._samples: list[tuple[float, Any]] = []
+
+    def add_stat(self, value: Any, time) -> None:
+        self._samples.append((time.to_seconds(), value))
+
+    def clear(self) -> None:
+        self._samples.clear()
+
+    @property
+    def values(self):
+        return self._samples
+
+    def between(self, start_s: float, end_s: float) -> "Data":
+        r = Data()
+        r._samples = [(t, v) for t, v in self._samples if start_s <= t < end_s]
+        return r
+
+    def mean(self) -> float:
+        vals = [v for _, v in self._samples]
+        return sum(vals) / len(vals) if vals else 0.0
+
+    def min(self) -> float:
+        vals = [v for _, v in self._samples]
+        return min(vals) if vals else 0.0
+
+    def max(self) -> float:
+        vals = [v for _, v in self._samples]
+        return max(vals) if vals else 0.0
+
+    def percentile(self, p: float) -> float:
+        return _percentile_sorted(sorted(v for _, v in self._samples), p)
+
+    def count(self) -> int:
+        return len(self._samples)
+
+    def sum(self) -> float:
+        return sum(v for _, v in self._samples)
+
+    def std(self) -> float:
+        vals = [v for _, v in self._samples]
+        return statistics.pstdev(vals) if len(vals) >= 2 else 0.0
+
+    def bucket(self, window_s: float = 1.0) -> BucketedData:
+        buckets: dict[int, list[float]] = defaultdict(list)
+        for t, v in self._samples:
+            buckets[math.floor(t / window_s)].append(float(v))
+        res = BucketedData()
+        for key in sorted(buckets):
+            vals = buckets[key]
+            vs = sorted(vals)
+            res._times.append(key * window_s)
+            res._means.append(sum(vals) / len(vals))
+            res._counts.append(len(vals))
+            res._maxes.append(max(vals))
+            res._sums.append(sum(vals))
+            res._p50s.append(_percentile_sorted(vs, 0.50))
+            res._p99s.append(_percentile_sorted(vs, 0.99))
+        return res
+
+    def times(self): return [t for t, _ in self._samples]
+    def raw_values(self): return [v for _, v in self._samples]
+
+    def rate(self, window_s: float = 1.0) -> "Data":
+        b = self.bucket(window_s)
+        r = Data()
+        for t, c in zip(b.times(), b.counts()):
+            r._samples.append((t, c / window_s))
+        return r
+
+    def __len__(self): return len(self._samples)
+    def __bool__(self): return len(self._samples) > 0
+
+
+class _Collector:
+    def __init__(self, name: str) -> None:
+        self.name = name
+        self.data = Data()
+        self.count: int = 0
+
+
+class LatencyTracker(_Collector):
+    """instrumentation/collectors.py:18-60: (completion_time_s, latency_s) per event."""
+    _sample_value = "latency"
+
+    def __init__(self, name: str = "LatencyTracker") -> None:
+        super().__init__(name)
+
+    def p50(self) -> float: return self.data.percentile(0.50)
+    def p99(self) -> float: return self.data.percentile(0.99)
+    def mean_latency(self) -> float: return self.data.mean()
+    def summary(self, window_s: float = 1.0) -> BucketedData: return self.data.bucket(window_s)
+
+
+class ThroughputTracker(_Collector):
+    """instrumentation/collectors.py:63-89: one (time_s, 1.0) sample per event."""
+    _sample_value = "one"
+
+    def __init__(self, name: str = "ThroughputTracker") -> None:
+        super().__init__(name)
+
+    def throughput(self, window_s: float = 1.0) -> BucketedData: return self.data.bucket(window_s)

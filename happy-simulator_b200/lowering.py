@@ -121,6 +121,9 @@ def lower(sources, entities, *, key_population: int | None = None):
             return A.HS_ENT_SERVER
         if hasattr(o, "latencies_s") and hasattr(o, "events_received"):
             return A.HS_ENT_SINK
+        if hasattr(o, "data") and hasattr(o, "count") and hasattr(getattr(o, "data"), "_samples") and \
+                _cls(o) in ("LatencyTracker", "ThroughputTracker"):
+            return A.HS_ENT_SINK        # collectors.py:38-44,76-79: a Sink that appends to a Data
         if hasattr(o, "by_type") and hasattr(o, "total"):
             return A.HS_ENT_COUNTER
         if hasattr(o, "_strategy") and hasattr(o, "_backends") and hasattr(o, "_in_flight"):

@@ -135,6 +135,7 @@ typedef struct hs_run_params {
 #define HS_ST_QUEUE_OVERFLOW 1u   /* a server's device queue ring filled up  */
 #define HS_ST_FEL_OVERFLOW 2u     /* future-event list slots exhausted       */
 #define HS_ST_REJECT_PATH 4u      /* Server acquire failed (server.py:223)   */
+#define HS_ST_TRACE_EXHAUSTED 8u  /* ran out of externally supplied draws    */
 
 typedef struct hs_replica_summary {
     int64_t events_processed;  /* SimulationSummary.total_events_processed (simulation.py:553) */
@@ -218,6 +219,22 @@ int hs_model_upload(hs_engine *e, const hs_model_desc *model);
 
 /* Validate a model without a device (used by host-side tests). */
 int hs_model_validate(const hs_model_desc *model);
+
+/* Externally supplied draws ("stock generator" mode).  The reference draws arrival target
+ * areas as -log(1 - numpy.random.random()) (load/providers/poisson_arrival.py:31) and service
+ * samples as random.expovariate(lambda) (distributions/exponential.py:43) from two process-global
+ * MT19937 streams that every consumer shares in call order.  The host can generate those two
+ * streams with the very generators the reference uses and hand them over: replica r reads
+ * arrival_targets[r * n_arrival + k] for the k-th Poisson draw made by ANY source and
+ * service_samples[r * n_service + k] for the k-th exponential draw made by ANY server, in
+ * simulation order.  Both arrays hold unit-rate exponential variates -log(1 - U) evaluated on the
+ * host with the reference's libm; the consumer's own rate / lambda is applied on the device
+ * (target / rate, and expovariate's  -log(1 - U) / lambd).  Everything downstream of the draw
+ * (divisions, ns truncation) is the device's usual arithmetic, so a run reproduces the unmodified, stock-seeded reference bit for bit.
+ * Buffers are copied to the device; pass NULL/0 to return to the Philox streams.  A replica that
+ * runs out of draws stops with HS_ST_TRACE_EXHAUSTED. */
+int hs_set_trace(hs_engine *e, const double *arrival_targets, uint64_t n_arrival,
+                 const double *service_samples, uint64_t n_service, uint32_t n_replicas);
 
 /* Simulation.run() for params->n_replicas replicas (core/simulation.py:230,
  * 449-505).  Asynchronous on the engine's stream; results stay on the device

@@ -151,7 +151,8 @@ typedef struct orun {
     /* optional externally supplied draws (hs_oracle_run_trace): the reference's own
      * RNG outputs, so the restatement can be checked against a STOCK-seed run */
     const double *trace_targets; uint64_t n_trace_targets;   /* -log(1-U) per arrival  */
-    const double *trace_service; uint64_t n_trace_service;   /* expovariate() samples   */
+    const double *trace_service; uint64_t n_trace_service;   /* -log(1-U) of random.random() */
+    uint64_t np_cursor, py_cursor;   /* the process-global streams are shared by all consumers */
     /* outputs of this replica */
     hs_event_record *rec;
     hs_sink_sample *smp; int64_t n_smp;
@@ -209,8 +210,8 @@ static int64_t next_arrival(orun *R, int sid, oent *s)
 {
     double target;
     if (s->d.i0 == HS_ARR_POISSON && R->trace_targets) {
-        target = s->arr_draws < R->n_trace_targets ? R->trace_targets[s->arr_draws] : 1e300;
-        s->arr_draws++;
+        target = R->np_cursor < R->n_trace_targets ? R->trace_targets[R->np_cursor] : 1e300;
+        R->np_cursor++; s->arr_draws++;
     } else if (s->d.i0 == HS_ARR_POISSON) {
         double u = hs_uniform(R->seed, R->rid, HS_STREAM_ARRIVAL | ((uint32_t)sid << 8), s->arr_draws++);
         target = hs_exp1(u);              /* poisson_arrival.py:31                */
@@ -338,8 +339,9 @@ static void handle(orun *R, oev *e)
         E->active++;
         int64_t dur_ns;
         if (E->d.i2 == HS_SVC_EXPONENTIAL && R->trace_service) {
-            double sample = E->svc_draws < R->n_trace_service ? R->trace_service[E->svc_draws] : 1e300;
-            E->svc_draws++;
+            /* random.expovariate(lambd) = -log(1.0 - random()) / lambd; the trace holds -log(1 - U) */
+            double sample = (R->py_cursor < R->n_trace_service ? R->trace_service[R->py_cursor] : 1e300) / E->lambda;
+            R->py_cursor++; E->svc_draws++;
             dur_ns = hs_seconds_to_ns(sample);            /* Duration.from_seconds(sample) */
         } else if (E->d.i2 == HS_SVC_EXPONENTIAL) {
             double u = hs_uniform(R->seed, R->rid, HS_STREAM_SERVICE | ((uint32_t)e->ent << 8), E->svc_draws++);

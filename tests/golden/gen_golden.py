@@ -118,18 +118,22 @@ def main():
         print(f"philox_{name}: {len(ref['records'])} events, hash {int(ref['summaries']['order_hash'][0]):#x}")
 
     # ---- stock generators: the README quick-start known answers ----
-    for seed, end_s in ((42, 60), (7, 200)):
-        model = hs.mm1()
+    stock = [("mm1_seed42", hs.mm1(), 42, 60), ("mm1_seed7", hs.mm1(), 7, 200),
+             # several servers share Python's global stream in simulation order
+             ("lb_rr8_seed5", hs.lb_round_robin(n_servers=8, rate=64.0), 5, 8),
+             ("mmc4_seed9", hs.mm1(rate=32, concurrency=4), 9, 20)]
+    for sname, model, seed, end_s in stock:
         ref = RH.run_reference(model, seed=seed, end_ns=int(end_s * 1e9), stock_rng=True)
         n_draw = len(ref["records"])
         u = np.random.RandomState(seed).random_sample(n_draw)          # numpy legacy global stream
         targets = np.array([-math.log(1.0 - x) for x in u])            # poisson_arrival.py:31
         rnd = random.Random(seed)
-        service = np.array([rnd.expovariate(1 / 0.1) for _ in range(n_draw)])   # exponential.py:36,43
+        # random.expovariate(l) = -log(1.0 - random()) / l (exponential.py:36,43): store -log(1 - U)
+        service = np.array([-math.log(1.0 - rnd.random()) for _ in range(n_draw)])
         meta = dict(seed=seed, rid=0, end_s=end_s, trace_targets=targets, trace_service=service)
-        save_case(os.path.join(HERE, f"stock_mm1_seed{seed}.npz"), model, ref, meta)
-        sink = ref["objects"][2]
-        print(f"stock_mm1_seed{seed}: events={ref['summary'].total_events_processed} "
+        save_case(os.path.join(HERE, f"stock_{sname}.npz"), model, ref, meta)
+        sink = [o for o in ref["objects"] if type(o).__name__ == "Sink"][0]
+        print(f"stock_{sname}: events={ref['summary'].total_events_processed} "
               f"sink={sink.events_received} avg_latency={sink.average_latency()!r} "
               f"final_ns={int(ref['summaries']['final_time_ns'][0])} heap_left={int(ref['summaries']['heap_left'][0])}")
 

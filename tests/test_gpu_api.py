@@ -95,3 +95,70 @@ def test_engine_errors_surface_as_exceptions():
     sim = quickstart(seed=1, end_s=5, rate=5000)[0]       # rho = 500: the device queue ring overflows
     with pytest.raises(RuntimeError, match="overflow"):
         sim.run()
+
+
+def test_latency_tracker_and_throughput_tracker_collect_like_the_reference_sink():
+    """instrumentation/collectors.py: LatencyTracker stores (completion_time_s, latency_s); the values
+    must be the ones the reference's Sink recorded for the same run (fixture)."""
+    _, kw, z = G.load("philox_mm1_seed42")
+    lt = hs.LatencyTracker()
+    server = hs.Server("Server", service_time=hs.ExponentialLatency(0.1), downstream=lt)
+    sim = hs.Simulation(end_time=hs.Instant(kw["end_ns"]), sources=[hs.Source.poisson(rate=8, target=server)],
+                        entities=[server, lt], seed=kw["seed"])
+    summary = sim.run()
+    assert summary.total_events_processed == int(z["summaries"]["events_processed"][0])
+    assert lt.count == int(z["entity_stats"][0][2]["c0"])
+    assert lt.data.raw_values() == [float(x) for x in z["sink_samples"]["latency_s"]]
+    assert lt.data.times() == [float(int(t)) / 1e9 for t in z["sink_samples"]["completion_ns"]]
+    assert lt.mean_latency() == sum(lt.data.raw_values()) / lt.count
+    assert summary.entities["LatencyTracker"].events_handled == lt.count          # simulation.py:579 ("count")
+    b = lt.summary(window_s=10.0)
+    assert sum(b.counts()) == lt.count and len(b) == 7                              # 60 s + the overshoot event
+    tt = hs.ThroughputTracker()
+    server2 = hs.Server("Server", service_time=hs.ExponentialLatency(0.1), downstream=tt)
+    hs.Simulation(end_time=hs.Instant(kw["end_ns"]), sources=[hs.Source.poisson(rate=8, target=server2)],
+                  entities=[server2, tt], seed=kw["seed"]).run()
+    assert tt.count == lt.count and tt.data.times() == lt.data.times() and set(tt.data.raw_values()) == {1.0}
+
+
+def test_parallel_simulation_independent_partitions():
+    """parallel/simulation.py:170-195: without links each partition is its own Simulation."""
+    def part(name, rate):
+        sink = hs.Sink(f"{name}.sink")
+        srv = hs.Server(f"{name}.srv", service_time=hs.ExponentialLatency(0.05), downstream=sink)
+        return hs.SimulationPartition(name, entities=[srv, sink], sources=[hs.Source.poisson(rate=rate, target=srv)]), sink
+    (pa, sa), (pb, sb) = part("a", 10.0), part("b", 15.0)
+    ps = hs.ParallelSimulation([pa, pb], duration=40.0, seed=5)
+    summ = ps.run()
+    assert set(summ.partitions) == {"a", "b"} and summ.total_windows == 0
+    assert summ.total_events_processed == sum(s.total_events_processed for s in summ.partitions.values())
+    assert summ.duration_s == max(s.duration_s for s in summ.partitions.values())
+    assert set(summ.entities) == {"a.srv", "a.sink", "b.srv", "b.sink"}
+    # partition k == a plain Simulation with the same seed and replica word k
+    (pa2, sa2), _ = part("a", 10.0), None
+    alone = hs.Simulation(duration=40.0, sources=pa2.sources, entities=pa2.entities, seed=5, replica=0).run()
+    assert alone.total_events_processed == summ.partitions["a"].total_events_processed
+    assert sa2.latencies_s == sa.latencies_s and sb.events_received > sa.events_received
+    with pytest.raises(hs.UnsupportedModelError, match="windowed coordinator"):
+        hs.ParallelSimulation([pa, pb], duration=1.0, links=[hs.PartitionLink("a", "b", min_latency=0.1)])
+    with pytest.raises(ValueError, match="min_latency must be > 0"):
+        hs.PartitionLink("a", "b", min_latency=0.0)
+
+
+@pytest.mark.parametrize("name", G.case_names("stock_"))
+def test_stock_seeded_reference_run_is_reproduced_bit_for_bit(name):
+    """random.seed(s); numpy.random.seed(s) on the UNMODIFIED reference (no plug-ins at all) vs the
+    device fed with those two MT19937 streams (rng="stock"): the README quick-start known answers."""
+    _, kw, z = G.load(name)
+    sim, source, server, sink = quickstart(seed=kw["seed"], end_s=kw["end_ns"] / 1e9)
+    sim2 = hs.Simulation(end_time=hs.Instant(kw["end_ns"]), sources=sim._sources, entities=sim._entities,
+                         seed=kw["seed"], rng="stock")
+    summary = sim2.run()
+    ws, st = z["summaries"][0], z["entity_stats"][0]
+    assert summary.total_events_processed == int(ws["events_processed"])
+    assert summary.duration_s == float(int(ws["final_time_ns"])) / 1e9
+    assert sink.events_received == int(st[2]["c0"]) and source.generated_count == int(st[0]["c0"])
+    assert sink.latencies_s == [float(x) for x in z["sink_samples"]["latency_s"]]
+    assert server.stats.total_service_time == float(st[1]["f0"])
+    if name == "stock_mm1_seed42":
+        assert summary.total_events_processed == 3621 and sink.average_latency() == 0.5696996189709543

@@ -45,3 +45,20 @@ def test_flight_recorder_rings_keep_the_tail(eng):
     assert np.array_equal(A.unroll_ring(ring["sink_samples"][0], ns, 300), whole["sink_samples"][0][ns - 300:ns])
     assert np.array_equal(A.unroll_ring(ring["service_samples"][0], nv, 77), whole["service_samples"][0][nv - 77:nv])
     assert int(s["order_hash"]) == int(z["summaries"]["order_hash"][0])
+
+
+@pytest.mark.parametrize("name", G.case_names("stock_"))
+def test_engine_reproduces_stock_seeded_reference_from_its_generator_streams(eng, name):
+    """The UNMODIFIED, stock-seeded reference (no plug-ins) vs the engine fed with the two MT19937
+    streams as unit-rate exponentials (hs_set_trace): lane engine for M/M/1, warp engine with the
+    shared-stream cursors for several servers."""
+    model, kw, z = G.load(name)
+    kw = dict(kw); kw.pop("seed"); kw.pop("rid_base")
+    eng.upload(model)
+    eng.set_trace(z["trace_targets"][None, :], z["trace_service"][None, :])
+    try:
+        eng.run(engine.make_params(n_replicas=1, **G.caps(z), **kw))
+        got = eng.read_outputs()
+    finally:
+        eng.set_trace(None, None)
+    G.check_against(z, got)

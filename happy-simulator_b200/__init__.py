@@ -20,7 +20,7 @@ from .api import (  # noqa: F401,E402
     PoissonArrivalTimeProvider, ConstantLatency, ExponentialLatency, FIFOQueue, LIFOQueue, FixedConcurrency,
     Server, ServerStats, Sink, Counter, LoadBalancer, LoadBalancerStats, RoundRobin, ConsistentHash,
     UniformKeyContext, Simulation, SimulationSummary, EntitySummary, QueueStats, ParallelRunner, RunConfig,
-    ParallelResult, seed, run_lowered,
+    ParallelResult, seed, run_lowered, LinearRampProfile, SpikeProfile,
 )
 from . import api  # noqa: F401,E402
 from .instrumentation import Data, BucketedData, LatencyTracker, ThroughputTracker  # noqa: F401,E402

@@ -12,6 +12,7 @@ HS_ARR_CONSTANT, HS_ARR_POISSON = 0, 1
 HS_SVC_CONSTANT, HS_SVC_EXPONENTIAL = 0, 1
 HS_Q_FIFO, HS_Q_LIFO = 0, 1
 HS_LB_ROUND_ROBIN, HS_LB_KEY_TABLE = 0, 1
+HS_PROF_CONSTANT, HS_PROF_LINEAR_RAMP, HS_PROF_SPIKE = 0, 1, 2
 
 (HS_EV_SOURCE_TICK, HS_EV_REQ_LB, HS_EV_REQ_ENQUEUE, HS_EV_NOTIFY, HS_EV_POLL, HS_EV_DELIVER,
  HS_EV_REQ_WORKER, HS_EV_CONTINUATION, HS_EV_REQ_SINK, HS_EV_LB_RESPONSE, HS_EV_REQ_COUNTER) = range(11)
@@ -38,7 +39,8 @@ class ModelDesc(C.Structure):
                 ("n_backends", C.c_uint32), ("key_population", C.c_uint32),
                 ("backends", C.POINTER(C.c_int32)), ("key_table", C.POINTER(C.c_int32)),
                 ("n_cells", C.c_uint32), ("reserved", C.c_uint32),
-                ("cell_d0", C.POINTER(C.c_double)), ("cell_i0", C.POINTER(C.c_int32))]
+                ("cell_d0", C.POINTER(C.c_double)), ("cell_i0", C.POINTER(C.c_int32)),
+                ("n_profiles", C.c_uint32), ("reserved2", C.c_uint32), ("profiles", C.c_void_p)]
 
 
 class RunParams(C.Structure):
@@ -107,6 +109,8 @@ ENTITY_DTYPE = _np.dtype([("kind", "<i4"), ("target", "<i4"), ("i0", "<i4"), ("i
                           ("i3", "<i4"), ("l0", "<i8"), ("d0", "<f8"), ("d1", "<f8")])
 assert SUMMARY_DTYPE.itemsize == 56 and STATS_DTYPE.itemsize == 64 and RECORD_DTYPE.itemsize == 16
 assert ENTITY_DTYPE.itemsize == 48
+PROFILE_DTYPE = _np.dtype([("kind", "<i4"), ("pad", "<i4"), ("p", "<f8", (4,))])
+assert PROFILE_DTYPE.itemsize == 40
 
 
 def unroll_ring(buf, count: int, cap: int):

@@ -135,6 +135,39 @@ class ConstantRateProfile:
         return self.rate
 
 
+@dataclass(frozen=True)
+class LinearRampProfile:
+    """load/profile.py:51-74"""
+    duration_s: float
+    start_rate: float
+    end_rate: float
+
+    def get_rate(self, time) -> float:
+        t = time.to_seconds()
+        if t <= 0:
+            return self.start_rate
+        if t >= self.duration_s:
+            return self.end_rate
+        return self.start_rate + (t / self.duration_s) * (self.end_rate - self.start_rate)
+
+
+@dataclass(frozen=True)
+class SpikeProfile:
+    """load/profile.py:77-110"""
+    baseline_rate: float = 10.0
+    spike_rate: float = 150.0
+    warmup_s: float = 10.0
+    spike_duration_s: float = 15.0
+
+    def get_rate(self, time) -> float:
+        t = time.to_seconds()
+        if t < self.warmup_s:
+            return self.baseline_rate
+        if t < self.warmup_s + self.spike_duration_s:
+            return self.spike_rate
+        return self.baseline_rate
+
+
 class _ArrivalTimeProvider:
     """load/arrival_time_provider.py:28-47 (constant-rate profiles only on the device)."""
 
@@ -276,6 +309,18 @@ class Source(Entity):
     @classmethod
     def poisson(cls, rate, target=None, event_type="Request", *, name="Source", stop_after=None, event_provider=None):
         return cls._make(PoissonArrivalTimeProvider, rate, target, event_type, name, stop_after, event_provider)
+
+    @classmethod
+    def with_profile(cls, profile, target=None, event_type="Request", *, poisson=True, name="Source",
+                     stop_after=None, event_provider=None):
+        """load/source.py:271-318"""
+        if event_provider is None:
+            if target is None:
+                raise ValueError("Either 'target' or 'event_provider' must be provided")
+            event_provider = SimpleEventProvider(target, event_type, cls._resolve_stop_after(stop_after))
+        provider_cls = PoissonArrivalTimeProvider if poisson else ConstantArrivalTimeProvider
+        return cls(name=name, event_provider=event_provider,
+                   arrival_time_provider=provider_cls(profile, start_time=Instant.Epoch))
 
     @property
     def generated_count(self) -> int:
@@ -537,7 +582,14 @@ class Simulation:
     def _caps(self, n_hint: int | None = None):
         dur = self._end_time.to_seconds()
         ents = self.model.entities
-        rate = float(sum(ents["d0"][i] for i in self.model.ids_of(A.HS_ENT_SOURCE)))
+        rate = 0.0
+        for i in self.model.ids_of(A.HS_ENT_SOURCE):
+            pi = int(ents["i3"][i])
+            if pi == 0:
+                rate += float(ents["d0"][i])
+            else:        # non-constant profile: bound by its largest parameter that can be a rate
+                pr = self.model.profiles[pi - 1]
+                rate += float(max(pr["p"][1:3]) if int(pr["kind"]) == A.HS_PROF_LINEAR_RAMP else max(pr["p"][0:2]))
         req = int(rate * dur * 1.3 + 6 * math.sqrt(rate * dur + 1) + 64)
         n_srv = len(self.model.ids_of(A.HS_ENT_SERVER))
         chain = 1 if (n_srv <= 1 or self.model.ids_of(A.HS_ENT_LB)) else n_srv     # tandem: one start per stage

@@ -70,8 +70,9 @@ struct hs_engine {
     std::vector<hs_entity_desc> ents;
     std::vector<int32_t> backends, key_table;
     std::vector<double> cell_d0; std::vector<int32_t> cell_i0;
+    std::vector<hs_profile_desc> profiles;
     uint32_t n_cells = 0;
-    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0;
+    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0, d_profiles;
     bool lane_ok = false;
     hs_lane_model lane_model;
 
@@ -100,7 +101,20 @@ static int validate_model(const hs_model_desc *m)
             n_src++;
             if (e.target < 0 || (uint32_t)e.target >= n) return fail(HS_ERR_INVALID, "entity %u: source target %d out of range", i, e.target);
             if (m->entities[e.target].kind == HS_ENT_SOURCE) return fail(HS_ERR_INVALID, "entity %u: source targets a source", i);
-            if (!(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: source rate must be > 0 (arrival_time_provider.py:75)", i);
+            if (e.i3 < 0 || (uint32_t)e.i3 > m->n_profiles) return fail(HS_ERR_INVALID, "entity %u: profile index %d out of range", i, e.i3);
+            if (e.i3 > 0 && !m->profiles) return fail(HS_ERR_INVALID, "profiles is NULL");
+            if (e.i3 > 0 && (m->profiles[e.i3 - 1].kind < HS_PROF_CONSTANT || m->profiles[e.i3 - 1].kind > HS_PROF_SPIKE))
+                return fail(HS_ERR_INVALID, "entity %u: unknown profile kind", i);
+            if (e.i3 > 0 && m->profiles[e.i3 - 1].kind == HS_PROF_LINEAR_RAMP && !(m->profiles[e.i3 - 1].p[0] > 0.0))
+                return fail(HS_ERR_INVALID, "entity %u: LinearRampProfile duration must be > 0", i);
+            if (e.i3 > 0) {     /* a rate that reaches zero sends the reference's bracket search to times beyond int64 ns */
+                const hs_profile_desc &pr = m->profiles[e.i3 - 1];
+                const bool ok = pr.kind == HS_PROF_LINEAR_RAMP ? (pr.p[1] > 0.0 && pr.p[2] > 0.0)
+                              : pr.kind == HS_PROF_SPIKE ? (pr.p[0] > 0.0 && pr.p[1] > 0.0 && pr.p[2] >= 0.0 && pr.p[3] >= 0.0)
+                              : (pr.p[0] > 0.0);
+                if (!ok) return fail(HS_ERR_INVALID, "entity %u: profile rates must stay > 0", i);
+            }
+            if (e.i3 == 0 && !(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: source rate must be > 0 (arrival_time_provider.py:75)", i);
             if (e.i0 != HS_ARR_CONSTANT && e.i0 != HS_ARR_POISSON) return fail(HS_ERR_INVALID, "entity %u: bad arrival kind", i);
             if (e.i1 < 0 || (e.i1 > 0 && (uint32_t)e.i1 != m->key_population)) return fail(HS_ERR_INVALID, "entity %u: key population %d != key_table length %u", i, e.i1, m->key_population);
             break;
@@ -138,7 +152,7 @@ static int validate_model(const hs_model_desc *m)
         for (uint32_t i = 0; i < n; ++i) {
             const hs_entity_desc &e = m->entities[i];
             double d = m->cell_d0[(size_t)c * n + i]; int32_t v = m->cell_i0[(size_t)c * n + i];
-            if (e.kind == HS_ENT_SOURCE && !(d > 0.0)) return fail(HS_ERR_INVALID, "cell %u: source rate must be > 0", c);
+            if (e.kind == HS_ENT_SOURCE && e.i3 == 0 && !(d > 0.0)) return fail(HS_ERR_INVALID, "cell %u: source rate must be > 0", c);
             if (e.kind == HS_ENT_SERVER && (v < 1 || d < 0.0)) return fail(HS_ERR_INVALID, "cell %u: bad server override", c);
             if (e.kind != HS_ENT_SERVER && v != e.i0) return fail(HS_ERR_INVALID, "cell %u: i0 override only applies to servers", c);
         }
@@ -170,6 +184,8 @@ static bool classify_lane(hs_engine *E)
     L.arr_kind = en[src].i0; L.svc_kind = en[srv].i2; L.policy = en[srv].i1; L.n_entities = (int32_t)n;
     L.capacity = en[srv].l0; L.stop_after = en[src].l0;
     L.rate = en[src].d0; L.mean = en[srv].d0;
+    L.has_profile = en[src].i3 > 0;
+    if (L.has_profile) L.prof = E->profiles[en[src].i3 - 1];
     L.n_cells = E->n_cells;
     L.cell_d0 = (const double *)E->d_cell_d0.p;
     return true;
@@ -227,6 +243,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     M.backends = (const int32_t *)E->d_backends.p; M.key_table = (const int32_t *)E->d_key_table.p;
     M.srv_index = (const int32_t *)E->d_srv_index.p;
     M.cell_d0 = (const double *)E->d_cell_d0.p; M.cell_i0 = (const int32_t *)E->d_cell_i0.p;
+    M.profiles = (const hs_profile_desc *)E->d_profiles.p;
     M.n_entities = ne; M.n_cells = E->n_cells; M.n_servers = n_servers; M.fel_slots = S; M.block_bytes = block_bytes;
     hs_warp_run R;
     R.seed = p->seed; R.seed_stride = p->seed_stride; R.rid_base = p->rid_base; R.rid_stride = p->rid_stride;
@@ -304,7 +321,7 @@ int hs_engine_destroy(hs_engine *E)
     cudaStreamSynchronize(E->stream);
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
                        &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
-                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc};
+                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
@@ -324,6 +341,7 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
     E->backends.assign(m->backends, m->backends + (m->backends ? m->n_backends : 0));
     E->key_table.assign(m->key_table, m->key_table + (m->key_table ? m->key_population : 0));
     E->n_cells = m->n_cells;
+    E->profiles.assign(m->profiles, m->profiles + (m->profiles ? m->n_profiles : 0));
     E->cell_d0.clear(); E->cell_i0.clear();
     if (m->n_cells) {
         E->cell_d0.assign(m->cell_d0, m->cell_d0 + (size_t)m->n_cells * n);
@@ -343,6 +361,7 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
     if ((rc = up(E->d_key_table, E->key_table.data(), E->key_table.size() * 4))) return rc;
     if ((rc = up(E->d_cell_d0, E->cell_d0.data(), E->cell_d0.size() * 8))) return rc;
     if ((rc = up(E->d_cell_i0, E->cell_i0.data(), E->cell_i0.size() * 4))) return rc;
+    if ((rc = up(E->d_profiles, E->profiles.data(), E->profiles.size() * sizeof(hs_profile_desc)))) return rc;
     CUDA_TRY(cudaStreamSynchronize(E->stream));   /* host vectors may be reused by the caller's next upload */
     E->lane_ok = classify_lane(E);
     E->have_model = true;
@@ -424,10 +443,17 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
         hs_lane_state *st = (hs_lane_state *)E->d_state.p;
         hs_ring_entry *rg = (hs_ring_entry *)E->d_rings.p;
-        if (want_rec && want_hash) hs_lane_kernel<HS_LF_HASH | HS_LF_REC><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
-        else if (want_rec) hs_lane_kernel<HS_LF_REC><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
-        else if (want_hash) hs_lane_kernel<HS_LF_HASH><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
-        else hs_lane_kernel<0><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O);
+        const int fl = (want_hash ? HS_LF_HASH : 0) | (want_rec ? HS_LF_REC : 0) | (M.has_profile ? HS_LF_PROFILE : 0);
+        switch (fl) {
+        case 0: hs_lane_kernel<0><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        case 1: hs_lane_kernel<1><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        case 2: hs_lane_kernel<2><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        case 3: hs_lane_kernel<3><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        case 4: hs_lane_kernel<4><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        case 5: hs_lane_kernel<5><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        case 6: hs_lane_kernel<6><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        default: hs_lane_kernel<7><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
         E->launches += 1;

@@ -61,6 +61,7 @@
 #define HS_LANE_ENGINE_CUH
 
 #include "hs_sampler.h"
+#include "hs_profile.h"
 #include "../../include/hs_b200.h"
 
 #define HS_NOW_CAP 8
@@ -71,6 +72,7 @@
 #define HS_FLUSH 8              /* records per cooperative flush: 8 x 16 B = one 128 B line */
 #define HS_LF_HASH 1      /* maintain the order hash                         */
 #define HS_LF_REC 2       /* write event records / sink / service samples    */
+#define HS_LF_PROFILE 4   /* non-constant rate profile (Simpson + Brent path) */
 
 struct hs_now_ev {        /* an event created at the current timestamp       */
     uint64_t idx;         /* Event._sort_index                               */
@@ -105,6 +107,8 @@ struct hs_lane_model {
     double rate, mean;
     uint32_t n_cells, pad;
     const double *cell_d0;            /* device pointers or NULL                */
+    hs_profile_desc prof;             /* the Source's rate profile                */
+    int32_t has_profile, pad2;        /* 0: ConstantRateProfile fast path         */
 };
 
 struct hs_lane_run {
@@ -128,9 +132,15 @@ struct hs_lane_out {
 /* next arrival of a constant-rate profile, with the reference's "time travel" outcome
  * folded in: if the computed time is earlier than the current one the SourceEvent would be
  * popped and skipped and the Source never ticks again (INT64_MAX). */
-__device__ __forceinline__ int64_t hs_lane_next_arrival(int64_t t, double target, double rate)
+template <bool PROFILE>
+__device__ __forceinline__ int64_t hs_lane_next_arrival(int64_t t, double target, double rate,
+                                                        const hs_profile_desc *prof)
 {
-    const int64_t n = hs_next_arrival_ns(t, target, rate);
+    if (t >= HS_T_EXHAUSTED) return t;              /* dead / exhausted source stays so */
+    int64_t n;
+    if (PROFILE) n = hs_next_arrival_profile_ns(prof, t, target);
+    else n = hs_next_arrival_ns(t, target, rate);
+    if (n == HS_T_EXHAUSTED) return n;              /* RuntimeError: no further SourceEvent object */
     return n < t ? INT64_MAX : n;
 }
 
@@ -166,6 +176,9 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         mean = M.cell_d0[(size_t)cell * M.n_entities + M.srv_id];
     }
     const double lambda = HS_DIV(1.0, mean);             /* exponential.py:36 */
+    hs_profile_desc prof_local;
+    if (FLAGS & HS_LF_PROFILE) prof_local = M.prof;
+    const hs_profile_desc *profp = (FLAGS & HS_LF_PROFILE) ? &prof_local : nullptr;
     const bool poisson = (M.arr_kind == HS_ARR_POISSON);
     const bool expo = (M.svc_kind == HS_SVC_EXPONENTIAL);
     const bool lifo = (M.policy == HS_Q_LIFO);
@@ -236,8 +249,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     /* next arrival time from t (arrival_time_provider.py:66-82); a result < t would be
      * popped and skipped as "time travel" by the loop (simulation.py:479-489), after which the
      * Source never ticks again: INT64_MAX marks that dead source. */
-#define HS_NEXT_ARRIVAL(T, TARGET)                                                           \
-    ((T) == INT64_MAX ? INT64_MAX : hs_lane_next_arrival((T), (TARGET), rate))
+#define HS_NEXT_ARRIVAL(T, TARGET) hs_lane_next_arrival<(FLAGS & HS_LF_PROFILE) != 0>((T), (TARGET), rate, profp)
 
     /* one converged refill round: each lane that has room generates the next Philox
      * pair of each stream and stores the precomputed draws */
@@ -298,7 +310,8 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
 
     /* Source.handle_event's arrival part: the next SourceEvent (source.py:166-170) */
 #define HS_NEXT_TICK()                                                                       \
-    do { arr_draws++; tT = sh_t[arr_draws % HS_DRAW_BUF][tid]; iT = ctr++; } while (0)
+    do { arr_draws++; tT = sh_t[arr_draws % HS_DRAW_BUF][tid];                               \
+         if (tT == HS_T_EXHAUSTED) tT = INT64_MAX; else iT = ctr++; } while (0)
 
     /* Server.handle_queued_event up to its yield, for the payload (CREATED):
      * inline ProcessContinuation index, acquire (the caller has checked
@@ -369,6 +382,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
          * SourceEvent takes index 0 of the GLOBAL counter (simulation.py:77,145-154);
          * run() then restarts the per-heap counter at 0 (event_heap.py:48).        */
         arr_draws = 1; tT = sh_t[1][tid];
+        if (tT == HS_T_EXHAUSTED) tT = INT64_MAX;      /* source.start(): RuntimeError, no first tick */
         iT = 0; ctr = 0;
     }
 

@@ -29,6 +29,7 @@
 #define HS_WARP_ENGINE_CUH
 
 #include "hs_sampler.h"
+#include "hs_profile.h"
 #include "../../include/hs_b200.h"
 
 #define HS_WF_HASH 1
@@ -70,6 +71,7 @@ struct hs_warp_model {
     const hs_entity_desc *ents;     /* device */
     const int32_t *backends, *key_table, *srv_index;
     const double *cell_d0; const int32_t *cell_i0;
+    const hs_profile_desc *profiles;
     uint32_t n_entities, n_cells, n_servers, fel_slots;   /* fel_slots = S, multiple of 32 */
     uint32_t block_bytes;           /* bytes of one replica block (multiple of 16)          */
 };
@@ -230,7 +232,11 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (i << 8), e->u.src.arr_draws++);
                         target = hs_exp1(u);
                     }
-                    e->u.src.cur_ns = hs_next_arrival_ns(0, target, e->d0);
+                    const int32_t pi = M.ents[i].i3;
+                    const int64_t first = pi > 0 ? hs_next_arrival_profile_ns(&M.profiles[pi - 1], 0, target)
+                                                 : hs_next_arrival_ns(0, target, e->d0);
+                    if (first == HS_T_EXHAUSTED) continue;      /* source.start(): RuntimeError, no tick */
+                    e->u.src.cur_ns = first;
                     if (H->free_top == 0) { H->status |= HS_ST_FEL_OVERFLOW; break; }
                     const uint32_t sl = f_free[--H->free_top];
                     f_time[sl] = e->u.src.cur_ns; f_idx[sl] = boot++; f_m0[sl] = HS_EV_SOURCE_TICK | (i << 8);
@@ -372,10 +378,14 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                             const double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), X->u.src.arr_draws++);
                             target = hs_exp1(u);
                         }
-                        X->u.src.cur_ns = hs_next_arrival_ns(X->u.src.cur_ns, target, X->d0);
-                        const uint64_t idxT = ctr++;
+                        const int64_t nt = d.i3 > 0 ? hs_next_arrival_profile_ns(&M.profiles[d.i3 - 1], X->u.src.cur_ns, target)
+                                                    : hs_next_arrival_ns(X->u.src.cur_ns, target, X->d0);
                         if (have) HS_W_PUSH(now, idxP, HS_W_REQ_KIND(d.target), d.target, now, 0ull, key, 0u);
-                        HS_W_PUSH(X->u.src.cur_ns, idxT, HS_EV_SOURCE_TICK, ent, 0, 0ull, -1, 0u);
+                        if (nt != HS_T_EXHAUSTED) {          /* else "Source exhausted", source.py:176-180 */
+                            X->u.src.cur_ns = nt;
+                            const uint64_t idxT = ctr++;
+                            HS_W_PUSH(nt, idxT, HS_EV_SOURCE_TICK, ent, 0, 0ull, -1, 0u);
+                        }
                         break;
                     }
                     case HS_EV_REQ_LB: {               /* LoadBalancer._forward_request, :347-433 */

@@ -59,17 +59,27 @@ def consistent_hash_table(backend_names, virtual_nodes: int, population: int) ->
 
 
 def _arrival(tp):
-    """ArrivalTimeProvider -> (HS_ARR_*, rate)."""
+    """ArrivalTimeProvider -> (HS_ARR_*, rate, profile tuple or None).  The reference's built-in
+    profile classes (load/profile.py) are lowered; a user-defined Profile.get_rate is a Python
+    callback and cannot run on the device."""
     name = _cls(tp)
     prof = getattr(tp, "profile", None)
-    if prof is None or _cls(prof) != "ConstantRateProfile":
-        raise UnsupportedModelError(f"arrival profile {_cls(prof)} is not a ConstantRateProfile "
-                                    "(non-constant profiles are SURVEY 8(f) row 1)")
-    rate = float(prof.rate)
+    pname = _cls(prof)
+    rate, ptuple = 0.0, None
+    if pname == "ConstantRateProfile":
+        rate = float(prof.rate)
+    elif pname == "LinearRampProfile":
+        ptuple = ("linear_ramp", float(prof.duration_s), float(prof.start_rate), float(prof.end_rate))
+    elif pname == "SpikeProfile":
+        ptuple = ("spike", float(prof.baseline_rate), float(prof.spike_rate), float(prof.warmup_s),
+                  float(prof.spike_duration_s))
+    else:
+        raise UnsupportedModelError(f"arrival profile {pname}: only ConstantRateProfile, LinearRampProfile and "
+                                    "SpikeProfile are lowered (a custom get_rate is a Python callback)")
     if "Poisson" in name:
-        return A.HS_ARR_POISSON, rate
+        return A.HS_ARR_POISSON, rate, ptuple
     if "Constant" in name:
-        return A.HS_ARR_CONSTANT, rate
+        return A.HS_ARR_CONSTANT, rate, ptuple
     raise UnsupportedModelError(f"arrival time provider {name}")
 
 
@@ -165,10 +175,10 @@ def lower(sources, entities, *, key_population: int | None = None):
                 if pop <= 0:
                     raise UnsupportedModelError(f"source {name!r}: arbitrary context_fn callbacks cannot run on the "
                                                 "device (use happysim_b200.UniformKeyContext)")
-            kind, rate = _arrival(o._time_provider)
+            kind, rate, ptuple = _arrival(o._time_provider)
             stop = prov._stop_after
             b.source(name, rate=rate, target=ids[id(prov._target)], poisson=(kind == A.HS_ARR_POISSON),
-                     stop_after_ns=-1 if stop is None else _ns(stop), key_population=pop)
+                     stop_after_ns=-1 if stop is None else _ns(stop), key_population=pop, profile=ptuple)
         elif k == A.HS_ENT_SERVER:
             cm = o._concurrency_model
             if _cls(cm) != "FixedConcurrency":

@@ -25,6 +25,7 @@ class FlatModel:
     key_table: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     cell_d0: np.ndarray | None = None         # float64[n_cells, n]
     cell_i0: np.ndarray | None = None         # int32[n_cells, n]
+    profiles: np.ndarray = field(default_factory=lambda: np.zeros(0, A.PROFILE_DTYPE))
 
     @property
     def n_entities(self) -> int:
@@ -59,6 +60,11 @@ class FlatModel:
             d.cell_d0 = cd.ctypes.data_as(C.POINTER(C.c_double))
             d.cell_i0 = ci.ctypes.data_as(C.POINTER(C.c_int32))
             keep += [cd, ci]
+        if len(self.profiles):
+            pr = np.ascontiguousarray(self.profiles, dtype=A.PROFILE_DTYPE)
+            d.n_profiles = pr.shape[0]
+            d.profiles = pr.ctypes.data
+            keep.append(pr)
         d._keep = keep
         return d
 
@@ -71,15 +77,25 @@ class ModelBuilder:
         self._names: list[str] = []
         self._backends: list[int] = []
         self._key_table = np.zeros(0, np.int32)
+        self._profiles: list[tuple] = []
 
-    def _add(self, name, kind, target=-1, i0=0, i1=0, i2=0, l0=-1, d0=0.0):
-        self._rows.append((kind, target, i0, i1, i2, 0, l0, d0, 0.0))
+    def _add(self, name, kind, target=-1, i0=0, i1=0, i2=0, l0=-1, d0=0.0, i3=0):
+        self._rows.append((kind, target, i0, i1, i2, i3, l0, d0, 0.0))
         self._names.append(name)
         return len(self._rows) - 1
 
-    def source(self, name="Source", *, rate, target=-1, poisson=True, stop_after_ns=-1, key_population=0):
+    def source(self, name="Source", *, rate=0.0, target=-1, poisson=True, stop_after_ns=-1, key_population=0,
+               profile=None):
+        """profile: None (ConstantRateProfile(rate)) or ("linear_ramp", duration_s, start_rate, end_rate)
+        or ("spike", baseline_rate, spike_rate, warmup_s, spike_duration_s)."""
+        i3 = 0
+        if profile is not None:
+            kind = {"constant": A.HS_PROF_CONSTANT, "linear_ramp": A.HS_PROF_LINEAR_RAMP, "spike": A.HS_PROF_SPIKE}[profile[0]]
+            ps = [float(x) for x in profile[1:]] + [0.0] * (5 - len(profile))
+            self._profiles.append((kind, 0, ps))
+            i3 = len(self._profiles)
         return self._add(name, A.HS_ENT_SOURCE, target, A.HS_ARR_POISSON if poisson else A.HS_ARR_CONSTANT,
-                         key_population, 0, stop_after_ns, float(rate))
+                         key_population, 0, stop_after_ns, float(rate), i3=i3)
 
     def server(self, name="Server", *, concurrency=1, mean_service_s=0.01, exponential=True,
                downstream=-1, capacity=-1, lifo=False):
@@ -108,9 +124,12 @@ class ModelBuilder:
 
     def build(self) -> FlatModel:
         ents = np.array(self._rows, dtype=A.ENTITY_DTYPE)
-        return FlatModel(entities=ents, names=list(self._names),
-                         backends=np.asarray(self._backends, dtype=np.int32),
-                         key_table=self._key_table)
+        m = FlatModel(entities=ents, names=list(self._names),
+                      backends=np.asarray(self._backends, dtype=np.int32),
+                      key_table=self._key_table)
+        if self._profiles:
+            m.profiles = np.array(self._profiles, dtype=A.PROFILE_DTYPE)
+        return m
 
 
 # ---- the BASELINE.json configurations ------------------------------------

@@ -77,7 +77,8 @@ typedef struct hs_entity_desc {
     int32_t i1;        /* SOURCE: key population (0 = no routing key); SERVER: HS_Q_*;
                           LB: offset of its backend list in hs_model_desc.backends              */
     int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends                              */
-    int32_t i3;        /* reserved, 0                                                           */
+    int32_t i3;        /* SOURCE: 0 = ConstantRateProfile(d0); k > 0 = profiles[k - 1] (non-constant
+                          rate profile, general arrival path); others: reserved, 0              */
     int64_t l0;        /* SOURCE: stop_after in ns or -1; SERVER: queue capacity or -1 (= inf)  */
     double d0;         /* SOURCE: rate (events/s); SERVER: mean / constant service time (s)     */
     double d1;         /* reserved, 0                                                           */
@@ -97,7 +98,20 @@ typedef struct hs_model_desc {
     uint32_t reserved;
     const double *cell_d0;         /* [n_cells][n_entities] or NULL */
     const int32_t *cell_i0;        /* [n_cells][n_entities] or NULL */
+    /* Non-constant rate profiles (load/profile.py LinearRampProfile, SpikeProfile): arrival times
+     * come from the reference's adaptive-Simpson + Brent path (arrival_time_provider.py:84-144). */
+    uint32_t n_profiles;
+    uint32_t reserved2;
+    const struct hs_profile_desc *profiles;   /* 40 bytes each, see below */
 } hs_model_desc;
+
+enum { HS_PROF_CONSTANT = 0, HS_PROF_LINEAR_RAMP = 1, HS_PROF_SPIKE = 2 };
+typedef struct hs_profile_desc {
+    int32_t kind;      /* HS_PROF_*                                                          */
+    int32_t pad;
+    double p[4];       /* CONSTANT: rate | LINEAR_RAMP: duration_s, start_rate, end_rate
+                          | SPIKE: baseline_rate, spike_rate, warmup_s, spike_duration_s    */
+} hs_profile_desc;     /* 40 bytes */
 
 /* ---- run --------------------------------------------------------------- */
 

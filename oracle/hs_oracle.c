@@ -42,6 +42,7 @@
 
 #include "../include/hs_b200.h"
 #include "../happy-simulator_b200/csrc/hs_sampler.h"
+#include "../happy-simulator_b200/csrc/hs_profile.h"
 
 /* ---- one pending Event object ------------------------------------------ */
 typedef struct oev {
@@ -218,6 +219,11 @@ static int64_t next_arrival(orun *R, int sid, oent *s)
     } else {
         target = 1.0;                     /* constant_arrival.py:21-23            */
     }
+    if (s->d.i3 > 0) {                    /* non-constant profile: Simpson + Brent path */
+        int64_t t = hs_next_arrival_profile_ns(&R->m->profiles[s->d.i3 - 1], s->cur_ns, target);
+        if (t != HS_T_EXHAUSTED) s->cur_ns = t;
+        return t;
+    }
     s->cur_ns = hs_next_arrival_ns(s->cur_ns, target, s->d.d0);
     return s->cur_ns;
 }
@@ -263,9 +269,11 @@ static void handle(orun *R, oev *e)
         }
         E->generated_count++;
         int64_t nt = next_arrival(R, e->ent, E);
-        oev tick = new_event(R, nt, HS_EV_SOURCE_TICK, e->ent);
         if (have_payload) heap_push(&R->heap, &pay);
-        heap_push(&R->heap, &tick);
+        if (nt != HS_T_EXHAUSTED) {       /* RuntimeError: "Source exhausted", source.py:176-180 */
+            oev tick = new_event(R, nt, HS_EV_SOURCE_TICK, e->ent);
+            heap_push(&R->heap, &tick);
+        }
         break;
     }
     case HS_EV_REQ_LB: {                  /* LoadBalancer._forward_request, :347-433 */
@@ -434,6 +442,7 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
         if (E->d.kind != HS_ENT_SOURCE) continue;
         E->cur_ns = 0;                    /* provider.current_time = start_time   */
         int64_t first = next_arrival(&R, (int)i, E);
+        if (first == HS_T_EXHAUSTED) continue;   /* source.start(): RuntimeError -> no tick, source.py:138-140 */
         oev tick = new_event(&R, first, HS_EV_SOURCE_TICK, (int)i);
         heap_push(&R.heap, &tick);
     }
@@ -534,5 +543,11 @@ int64_t hs_cpu_next_arrival_ns(int64_t cur, double target, double rate) { return
 int64_t hs_cpu_exp_latency_ns(double u, double lambda) { return hs_exp_latency_ns(u, lambda); }
 uint64_t hs_cpu_hash_step(uint64_t h, int64_t t, uint64_t idx, uint32_t kind, uint32_t ent)
 { return hs_hash_step(h, t, hs_record_word1(idx, kind, ent)); }
+int64_t hs_cpu_next_arrival_profile_ns(int32_t kind, double p0, double p1, double p2, double p3, int64_t cur, double target)
+{ hs_profile_desc P; P.kind = kind; P.pad = 0; P.p[0] = p0; P.p[1] = p1; P.p[2] = p2; P.p[3] = p3;
+  return hs_next_arrival_profile_ns(&P, cur, target); }
+double hs_cpu_integrate_rate(int32_t kind, double p0, double p1, double p2, double p3, double a, double b)
+{ hs_profile_desc P; P.kind = kind; P.pad = 0; P.p[0] = p0; P.p[1] = p1; P.p[2] = p2; P.p[3] = p3;
+  return hs_integrate_rate(&P, a, b); }
 void hs_cpu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4)
 { hs_u32x4 r = hs_philox4x32_10(c0, c1, c2, c3, k0, k1); out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w; }

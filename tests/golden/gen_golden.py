@@ -75,6 +75,24 @@ def two_sources():
     return b.build()
 
 
+def profiled(profile, poisson, lb=0):
+    b = hs.ModelBuilder()
+    src = b.source(profile=profile, poisson=poisson)
+    snk = None
+    if lb:
+        servers = [b.server(f"S{i}", mean_service_s=0.05) for i in range(lb)]
+        snk = b.sink()
+        l = b.load_balancer(backends=servers)
+        b.set_target(src, l)
+        for sv in servers:
+            b.set_target(sv, snk)
+    else:
+        srv = b.server(mean_service_s=0.05)
+        snk = b.sink()
+        b.set_target(src, srv); b.set_target(srv, snk)
+    return b.build()
+
+
 def philox_cases():
     c = {}
     c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
@@ -93,6 +111,11 @@ def philox_cases():
     c["tandem"] = (tandem(), dict(seed=13, rid=0, end_s=60))
     c["source_to_counter"] = (source_to_counter(), dict(seed=0, rid=0, end_s=60))
     c["two_sources"] = (two_sources(), dict(seed=21, rid=6, end_s=40))
+    # non-constant rate profiles (adaptive Simpson + Brent arrival path)
+    c["ramp_poisson_mm1"] = (profiled(("linear_ramp", 20.0, 2.0, 12.0), True), dict(seed=31, rid=2, end_s=30))
+    c["spike_poisson_mm1"] = (profiled(("spike", 5.0, 40.0, 4.0, 3.0), True), dict(seed=32, rid=0, end_s=12))
+    c["ramp_down_constant"] = (profiled(("linear_ramp", 5.0, 20.0, 1.0), False), dict(seed=0, rid=0, end_s=20))
+    c["spike_constant_lb4"] = (profiled(("spike", 10.0, 100.0, 2.0, 1.0), False, lb=4), dict(seed=3, rid=1, end_s=6))
     return c
 
 
@@ -100,7 +123,7 @@ def save_case(path, model, ref, meta):
     rec = ref["records"]
     np.savez_compressed(
         path,
-        entities=model.entities, backends=model.backends, key_table=model.key_table,
+        entities=model.entities, backends=model.backends, key_table=model.key_table, profiles=model.profiles,
         names=np.array(model.names), meta=np.array([meta["seed"], meta["rid"], int(meta["end_s"] * 1e9)], dtype=np.int64),
         summaries=ref["summaries"], entity_stats=ref["entity_stats"],
         n_records=np.int64(len(rec)), records=rec[:MAX_REC],

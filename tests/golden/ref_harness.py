@@ -54,7 +54,7 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     from happysimulator.distributions.exponential import ExponentialLatency
     from happysimulator.distributions.latency_distribution import LatencyDistribution
     from happysimulator.load.arrival_time_provider import ArrivalTimeProvider
-    from happysimulator.load.profile import ConstantRateProfile
+    from happysimulator.load.profile import ConstantRateProfile, LinearRampProfile, SpikeProfile
     from happysimulator.load.providers.constant_arrival import ConstantArrivalTimeProvider
     from happysimulator.load.providers.poisson_arrival import PoissonArrivalTimeProvider
     from happysimulator.load.source import SimpleEventProvider, Source
@@ -135,6 +135,11 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
                 return {"created_at": time, "request_id": count, "metadata": {"client_id": int(u * _pop)}}
         prov = SimpleEventProvider(target, "Request", stop, ctx_fn)
         profile = ConstantRateProfile(rate=float(e["d0"]))
+        if int(e["i3"]) > 0:
+            pr = model.profiles[int(e["i3"]) - 1]
+            pp = [float(x) for x in pr["p"]]
+            profile = (LinearRampProfile(pp[0], pp[1], pp[2]) if int(pr["kind"]) == A.HS_PROF_LINEAR_RAMP
+                       else SpikeProfile(pp[0], pp[1], pp[2], pp[3]))
         if int(e["i0"]) == A.HS_ARR_POISSON:
             atp = (PoissonArrivalTimeProvider(profile, Instant.Epoch) if stock_rng
                    else PhiloxPoissonArrival(profile, Instant.Epoch, i))

@@ -17,6 +17,8 @@ def load(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     model = hs.FlatModel(entities=z["entities"], names=[str(s) for s in z["names"]], backends=z["backends"],
                          key_table=z["key_table"])
+    if "profiles" in z.files and len(z["profiles"]):
+        model.profiles = z["profiles"]
     seed, rid, end_ns = (int(v) for v in z["meta"])
     return model, dict(seed=seed, rid_base=rid, end_ns=end_ns), z
 

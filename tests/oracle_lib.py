@@ -40,6 +40,10 @@ def lib():
         L.hs_cpu_exp_latency_ns.argtypes = [C.c_double, C.c_double]; L.hs_cpu_exp_latency_ns.restype = C.c_int64
         L.hs_cpu_hash_step.argtypes = [C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.hs_cpu_hash_step.restype = C.c_uint64
+        L.hs_cpu_next_arrival_profile_ns.argtypes = [C.c_int32] + [C.c_double] * 4 + [C.c_int64, C.c_double]
+        L.hs_cpu_next_arrival_profile_ns.restype = C.c_int64
+        L.hs_cpu_integrate_rate.argtypes = [C.c_int32] + [C.c_double] * 6
+        L.hs_cpu_integrate_rate.restype = C.c_double
         L.hs_cpu_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
         L.hs_cpu_philox.restype = None
         _lib = L

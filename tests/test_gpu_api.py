@@ -163,3 +163,17 @@ def test_stock_seeded_reference_run_is_reproduced_bit_for_bit(name):
     assert server.stats.total_service_time == float(st[1]["f0"])
     if name == "stock_mm1_seed42":
         assert summary.total_events_processed == 3621 and sink.average_latency() == 0.5696996189709543
+
+
+def test_source_with_profile_matches_the_reference_fixture():
+    """Source.with_profile(LinearRampProfile) -- arrival times from the adaptive
+    Simpson + Brent path on the device -- against the fixture recorded from the reference."""
+    _, kw, z = G.load("philox_ramp_poisson_mm1")
+    sink = hs.Sink()
+    server = hs.Server("Server", service_time=hs.ExponentialLatency(0.05), downstream=sink)
+    src = hs.Source.with_profile(hs.LinearRampProfile(20.0, 2.0, 12.0), target=server)
+    summary = hs.Simulation(end_time=hs.Instant(kw["end_ns"]), sources=[src], entities=[server, sink],
+                            seed=kw["seed"], replica=kw["rid_base"]).run()
+    assert summary.total_events_processed == int(z["summaries"]["events_processed"][0])
+    want = [float(x) for x in z["sink_samples"]["latency_s"]]
+    assert sink.latencies_s[: len(want)] == want

@@ -55,6 +55,10 @@ CASES = {
     "mm1_capacity0": (dict(rate=5, mean_service_s=0.1, capacity=0), 20),
     "mm1_lifo": (dict(rate=9, mean_service_s=0.1, lifo=True), 60),
     "overload": (dict(rate=20, mean_service_s=0.1), 10),
+    # inter-arrival of 0.5 ns: ticks tie with their own chain (generic path) and, once
+    # float(t)/1e9*1e9 rounds below t, the next tick is "time travel" and the Source dies
+    "time_travel_source": (dict(poisson=False, rate=2e9, mean_service_s=1e-7, exponential=False), 1),
+    "zero_gap_poisson": (dict(rate=3e8, mean_service_s=2e-9), 2e-5),
 }
 
 

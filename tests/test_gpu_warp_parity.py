@@ -63,6 +63,7 @@ CASES = {
     "tandem": (tandem, 60, 40),
     "two_sources": (two_sources, 40, 40),
     "source_to_sink_only": (lambda: _src_sink(), 30, 8),
+    "time_travel_source": (lambda: hs.mm1(poisson=False, rate=2e9, mean_service_s=1e-7, exponential=False, concurrency=2), 1, 8),
 }
 
 

@@ -80,3 +80,27 @@ def test_constant_rate_tick_drift_golden_vector():
         t = L.hs_cpu_next_arrival_ns(t, 1.0, 100.0)
         got.append(t)
     assert got[-1] == 99999999
+
+
+def test_nonconstant_profile_golden_vectors_of_the_reference():
+    """tests/regression/test_arrival_time_regression.py:46-103 of the reference: the first arrivals of
+    ConstantArrivalTimeProvider over LinearRampProfile / SpikeProfile (adaptive Simpson + Brent)."""
+    L = O.lib()
+
+    def series(kind, p, n):
+        t, out = 0, []
+        for _ in range(n):
+            t = L.hs_cpu_next_arrival_profile_ns(kind, *p, t, 1.0)
+            out.append(t / 1e9)
+        return out
+    up = [0.095864499, 0.184655976, 0.267741515, 0.346097448, 0.420449859, 0.49135612, 0.55925515, 0.624499924,
+          0.687379335, 0.748133387]
+    down = [0.010004504, 0.020018032, 0.030040609, 0.040072259, 0.050113007, 0.060162878, 0.070221897, 0.080290089,
+            0.090367479, 0.100454092]
+    spike = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.799999999, 0.899999998, 0.999999998, 1.099999998, 1.199999998,
+             1.299999998, 1.399999998, 1.499999998, 1.599999998, 1.699999998, 1.799999998, 1.899999998, 1.999999997,
+             2.009999997, 2.019999996, 2.029999996, 2.039999995, 2.049999994, 2.059999994, 2.069999993, 2.079999993,
+             2.089999992, 2.099999991]
+    assert all(abs(a - b) < 1e-8 for a, b in zip(series(1, (10.0, 10.0, 100.0, 0.0), 10), up))
+    assert all(abs(a - b) < 1e-8 for a, b in zip(series(1, (10.0, 100.0, 10.0, 0.0), 10), down))
+    assert all(abs(a - b) < 1e-8 for a, b in zip(series(2, (10.0, 100.0, 2.0, 1.0), 30), spike))

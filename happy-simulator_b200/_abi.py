@@ -20,7 +20,7 @@ HS_PROF_CONSTANT, HS_PROF_LINEAR_RAMP, HS_PROF_SPIKE = 0, 1, 2
 EVENT_KIND_NAMES = ["SOURCE_TICK", "REQ_LB", "REQ_ENQUEUE", "NOTIFY", "POLL", "DELIVER",
                     "REQ_WORKER", "CONTINUATION", "REQ_SINK", "LB_RESPONSE", "REQ_COUNTER"]
 
-HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH, HS_ST_TRACE_EXHAUSTED = 1, 2, 4, 8
+HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH, HS_ST_TRACE_EXHAUSTED, HS_ST_EVENT_LIMIT = 1, 2, 4, 8, 16
 
 HS_STREAM_ARRIVAL, HS_STREAM_SERVICE, HS_STREAM_ROUTING = 0, 1, 2
 
@@ -51,7 +51,8 @@ class RunParams(C.Structure):
                 ("replicas_per_cell", C.c_uint32), ("record_cap", C.c_uint32),
                 ("sample_cap", C.c_uint32), ("service_cap", C.c_uint32),
                 ("queue_ring", C.c_uint32), ("engine", C.c_uint32),
-                ("window_end_ns", C.c_int64), ("resume", C.c_uint32), ("flags", C.c_uint32)]
+                ("window_end_ns", C.c_int64), ("resume", C.c_uint32), ("flags", C.c_uint32),
+                ("max_events", C.c_int64)]
 
 
 class ReplicaSummary(C.Structure):
@@ -91,7 +92,7 @@ assert C.sizeof(ReplicaSummary) == 56
 assert C.sizeof(EntityStats) == 64
 assert C.sizeof(EventRecord) == 16
 assert C.sizeof(SinkSample) == 16
-assert C.sizeof(RunParams) == 80
+assert C.sizeof(RunParams) == 88
 HS_RUN_ORDER_HASH = 1
 
 # numpy views of the same layouts (host buffers are numpy structured arrays)

@@ -610,13 +610,16 @@ class Simulation:
             if need_events:
                 kw["record_cap"] = kw["service_cap"] * 12
             eng.run(make_params(seed=self._seed, rid_base=self._replica, end_ns=self._end_time.nanoseconds,
-                                n_replicas=1, flags=0, **kw))
+                                n_replicas=1, flags=0, max_events=60 * kw["sample_cap"] + 1_000_000, **kw))
             out = eng.read_outputs()
             s = out["summaries"][0]
             if int(s["status"]) & A.HS_ST_TRACE_EXHAUSTED:
                 caps = {k: 2 * v for k, v in caps.items()}
                 eng.set_trace(*stock_streams(self._seed, 1, caps["sample_cap"] * 2 + 64))
                 continue
+            if int(s["status"]) & A.HS_ST_EVENT_LIMIT:
+                raise RuntimeError("event limit reached: the model's clock does not advance (a source faster than "
+                                   "one event per nanosecond never terminates in the reference either)")
             if int(s["status"]) & (A.HS_ST_QUEUE_OVERFLOW | A.HS_ST_FEL_OVERFLOW):
                 raise RuntimeError(f"device structure overflow (status {int(s['status'])}); raise queue_ring")
             if (int(s["n_sink_samples"]) <= kw["sample_cap"] and int(s["n_service_samples"]) <= kw["service_cap"]

@@ -117,6 +117,7 @@ struct hs_lane_run {
     int64_t end_ns, window_end_ns;
     uint32_t n_replicas, index_base, replicas_per_cell;
     uint32_t record_cap, sample_cap, service_cap, ring, resume;
+    int64_t max_events;                     /* INT64_MAX = unlimited */
     const double *trace_arr, *trace_svc;    /* externally supplied draws (hs_set_trace) or NULL */
     uint64_t n_trace_arr, n_trace_svc;
 };
@@ -427,7 +428,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             const bool pickC = has_c && (tC < tT || (tC == tT && iC < iT));
             const int64_t tn = pickC ? tC : tT;
             if (windowed && tn > P.window_end_ns) { paused = true; finished = true; continue; }
-            const bool slow = (has_c && tC == tT) || (tn > P.end_ns) || (tn < now);
+            const bool slow = (has_c && tC == tT) || (tn > P.end_ns) || (tn < now) || (processed + 8 > P.max_events);   /* a chain is <= 6 events: single-step near the limit */
             if (!slow) {
                 now = tn;
                 if (!pickC) {
@@ -492,6 +493,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         }
 
         /* ===== generic single-event step (ties, run end, leftovers) ========= */
+        if (processed >= P.max_events) { status |= HS_ST_EVENT_LIMIT; finished = true; continue; }
         {
             /* pop the (time, sort_index) minimum of T, C and nowq (event.py:337-344) */
             int which = -1;                 /* -1 T, -2 C, >=0 nowq slot */

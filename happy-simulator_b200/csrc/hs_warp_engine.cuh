@@ -82,6 +82,7 @@ struct hs_warp_run {
     int64_t end_ns, window_end_ns;
     uint32_t n_replicas, index_base, replicas_per_cell;
     uint32_t record_cap, sample_cap, service_cap, ring, resume;
+    int64_t max_events;
     const double *trace_arr, *trace_svc;
     uint64_t n_trace_arr, n_trace_svc;
 };
@@ -285,6 +286,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                 while (true) {
                     const int64_t now0 = H->now;
                     if (!(now0 <= P.end_ns) || (H->status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW | HS_ST_TRACE_EXHAUSTED))) { go = 0; break; }
+                    if (H->processed >= P.max_events) { H->status |= HS_ST_EVENT_LIMIT; go = 0; break; }
                     /* next event: minimum of the now tier, unless the future minimum sorts first */
                     int nb = -1; int64_t nt = HS_W_EMPTY; uint64_t ni = ~0ull;
                     for (int k = 0; k < now_n; ++k) {

@@ -141,6 +141,10 @@ typedef struct hs_run_params {
     int64_t window_end_ns;
     uint32_t resume;           /* 1 = continue the replicas of the previous call          */
     uint32_t flags;            /* HS_RUN_* bits                                           */
+    int64_t max_events;        /* safety valve: a replica stops (HS_ST_EVENT_LIMIT) once it has
+                                  processed this many events in total; 0 = unlimited.  A model
+                                  whose clock cannot advance (e.g. a constant source faster than
+                                  1 event/ns) never terminates in the reference either.        */
 } hs_run_params;
 
 #define HS_RUN_ORDER_HASH 1u   /* maintain hs_replica_summary.order_hash (off: hash = 0)  */
@@ -150,6 +154,7 @@ typedef struct hs_run_params {
 #define HS_ST_FEL_OVERFLOW 2u     /* future-event list slots exhausted       */
 #define HS_ST_REJECT_PATH 4u      /* Server acquire failed (server.py:223)   */
 #define HS_ST_TRACE_EXHAUSTED 8u  /* ran out of externally supplied draws    */
+#define HS_ST_EVENT_LIMIT 16u     /* hs_run_params.max_events reached        */
 
 typedef struct hs_replica_summary {
     int64_t events_processed;  /* SimulationSummary.total_events_processed (simulation.py:553) */

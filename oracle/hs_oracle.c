@@ -459,6 +459,7 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
          * before the first event later than the window end; resume is not modelled
          * here -- a paused prefix is compared against the device's paused prefix. */
         if (windowed && R.heap.a[0].time > p->window_end_ns) break;
+        if (p->max_events > 0 && processed >= p->max_events) { R.status |= HS_ST_EVENT_LIMIT; break; }
         oev e = heap_pop(&R.heap);
         if (e.time < R.now) continue;     /* "time travel": skipped, not counted (simulation.py:479-489) */
         R.now = e.time;

@@ -55,9 +55,7 @@ CASES = {
     "mm1_capacity0": (dict(rate=5, mean_service_s=0.1, capacity=0), 20),
     "mm1_lifo": (dict(rate=9, mean_service_s=0.1, lifo=True), 60),
     "overload": (dict(rate=20, mean_service_s=0.1), 10),
-    # inter-arrival of 0.5 ns: ticks tie with their own chain (generic path) and, once
-    # float(t)/1e9*1e9 rounds below t, the next tick is "time travel" and the Source dies
-    "time_travel_source": (dict(poisson=False, rate=2e9, mean_service_s=1e-7, exponential=False), 1),
+    # inter-arrivals of a few ns: many SourceEvents tie with their own chain (generic path)
     "zero_gap_poisson": (dict(rate=3e8, mean_service_s=2e-9), 2e-5),
 }
 
@@ -140,3 +138,17 @@ def test_totals_match_per_replica_sums(eng):
     assert t["min_latency"] == float(sink["f2"].min()) and t["max_latency"] == float(sink["f3"].max())
     assert abs(t["sum_latency"] - float(sink["f0"].sum())) <= 1e-9 * abs(t["sum_latency"])
     assert t["server_completions"] == int(got["entity_stats"][:, 1]["c2"].sum())
+
+
+@pytest.mark.parametrize("engine_id", [1, 2])
+def test_event_limit_stops_a_model_whose_clock_cannot_advance(eng, engine_id):
+    """A constant source faster than one event per ns computes every next tick at the same
+    nanosecond (int((t/1e9 + 5e-10) * 1e9) == t): the reference would spin forever.  max_events is
+    the safety valve; until it trips, every SourceEvent ties with its own chain, so this also
+    drives the generic (tie) path hard -- on both engines, against the oracle."""
+    model = hs.mm1(poisson=False, rate=2e9, mean_service_s=1e-7, exponential=False)
+    kw = dict(seed=1, end_ns=10**9, n_replicas=40, record_cap=6000, max_events=5003, engine=engine_id)
+    got, want = run_both(eng, model, **kw)
+    assert (want["summaries"]["events_processed"] == 5003).all()
+    assert (want["summaries"]["status"] & hs._abi.HS_ST_EVENT_LIMIT).all()
+    assert_same(got, want)

@@ -63,7 +63,7 @@ CASES = {
     "tandem": (tandem, 60, 40),
     "two_sources": (two_sources, 40, 40),
     "source_to_sink_only": (lambda: _src_sink(), 30, 8),
-    "time_travel_source": (lambda: hs.mm1(poisson=False, rate=2e9, mean_service_s=1e-7, exponential=False, concurrency=2), 1, 8),
+    "zero_gap_poisson_c2": (lambda: hs.mm1(rate=3e8, mean_service_s=4e-9, concurrency=2), 2e-5, 8),
 }
 
 

@@ -146,7 +146,7 @@ def test_event_limit_stops_a_model_whose_clock_cannot_advance(eng, engine_id):
     nanosecond (int((t/1e9 + 5e-10) * 1e9) == t): the reference would spin forever.  max_events is
     the safety valve; until it trips, every SourceEvent ties with its own chain, so this also
     drives the generic (tie) path hard -- on both engines, against the oracle."""
-    model = hs.mm1(poisson=False, rate=2e9, mean_service_s=1e-7, exponential=False)
+    model = hs.mm1(poisson=False, rate=2e9, mean_service_s=1e-7, exponential=False, capacity=5)   # bounded queue
     kw = dict(seed=1, end_ns=10**9, n_replicas=40, record_cap=6000, max_events=5003, engine=engine_id)
     got, want = run_both(eng, model, **kw)
     assert (want["summaries"]["events_processed"] == 5003).all()

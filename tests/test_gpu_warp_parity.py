@@ -80,7 +80,8 @@ def test_warp_matches_oracle(eng, name):
     mk, end_s, n = CASES[name]
     model = mk()
     got, want = both(eng, model, seed=99, end_ns=int(end_s * 1e9), n_replicas=n, record_cap=30000,
-                     sample_cap=3000, service_cap=3000, engine=1)
+                     sample_cap=3000, service_cap=3000, engine=1,
+                     queue_ring=(1 << 16) if name.startswith("zero_gap") else 0)
     assert int(want["summaries"]["events_processed"].min()) > 100
     assert_same(got, want)
 

@@ -23,5 +23,5 @@ from .api import (  # noqa: F401,E402
     ParallelResult, seed, run_lowered, LinearRampProfile, SpikeProfile,
 )
 from . import api  # noqa: F401,E402
-from .instrumentation import Data, BucketedData, LatencyTracker, ThroughputTracker  # noqa: F401,E402
+from .instrumentation import Data, BucketedData, LatencyTracker, ThroughputTracker, Probe  # noqa: F401,E402
 from .parallel import SimulationPartition, PartitionLink, ParallelSimulation, ParallelSimulationSummary  # noqa: F401,E402

@@ -7,7 +7,9 @@ HS_ABI_VERSION = 1
 
 HS_OK, HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_NO_DEVICE, HS_ERR_STATE, HS_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
 
-HS_ENT_SOURCE, HS_ENT_SERVER, HS_ENT_SINK, HS_ENT_COUNTER, HS_ENT_LB = 1, 2, 3, 4, 5
+HS_ENT_SOURCE, HS_ENT_SERVER, HS_ENT_SINK, HS_ENT_COUNTER, HS_ENT_LB, HS_ENT_PROBE = 1, 2, 3, 4, 5, 6
+METRICS = {"depth": 0, "active_requests": 1, "utilization": 2, "available_capacity": 3, "stats_accepted": 4,
+           "stats_dropped": 5, "events_received": 6, "total": 7, "generated_count": 8}
 HS_ARR_CONSTANT, HS_ARR_POISSON = 0, 1
 HS_SVC_CONSTANT, HS_SVC_EXPONENTIAL = 0, 1
 HS_Q_FIFO, HS_Q_LIFO = 0, 1
@@ -15,10 +17,11 @@ HS_LB_ROUND_ROBIN, HS_LB_KEY_TABLE = 0, 1
 HS_PROF_CONSTANT, HS_PROF_LINEAR_RAMP, HS_PROF_SPIKE = 0, 1, 2
 
 (HS_EV_SOURCE_TICK, HS_EV_REQ_LB, HS_EV_REQ_ENQUEUE, HS_EV_NOTIFY, HS_EV_POLL, HS_EV_DELIVER,
- HS_EV_REQ_WORKER, HS_EV_CONTINUATION, HS_EV_REQ_SINK, HS_EV_LB_RESPONSE, HS_EV_REQ_COUNTER) = range(11)
+ HS_EV_REQ_WORKER, HS_EV_CONTINUATION, HS_EV_REQ_SINK, HS_EV_LB_RESPONSE, HS_EV_REQ_COUNTER,
+ HS_EV_PROBE) = range(12)
 
 EVENT_KIND_NAMES = ["SOURCE_TICK", "REQ_LB", "REQ_ENQUEUE", "NOTIFY", "POLL", "DELIVER",
-                    "REQ_WORKER", "CONTINUATION", "REQ_SINK", "LB_RESPONSE", "REQ_COUNTER"]
+                    "REQ_WORKER", "CONTINUATION", "REQ_SINK", "LB_RESPONSE", "REQ_COUNTER", "PROBE"]
 
 HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH, HS_ST_TRACE_EXHAUSTED, HS_ST_EVENT_LIMIT = 1, 2, 4, 8, 16
 

@@ -551,7 +551,7 @@ class Simulation:
             raise ValueError("Cannot specify both 'duration' and 'end_time'")
         if start_time is not None and start_time.nanoseconds != 0:
             raise lowering.UnsupportedModelError("start_time must be Instant.Epoch on the device engine")
-        for nm, v in (("probes", probes), ("trace_recorder", trace_recorder), ("fault_schedule", fault_schedule)):
+        for nm, v in (("trace_recorder", trace_recorder), ("fault_schedule", fault_schedule)):
             if v:
                 raise lowering.UnsupportedModelError(f"{nm}= is outside the accelerated path (SURVEY.md section 8)")
         self._start_time = Instant.Epoch
@@ -564,6 +564,7 @@ class Simulation:
                                                  "(auto-termination is the reference's slow loop)")
         self._sources = list(sources or [])
         self._entities = list(entities or [])
+        self._probes = list(probes or [])
         self._seed = default_seed if seed is None else int(seed)
         self._replica = int(replica)
         self._device = device
@@ -572,7 +573,7 @@ class Simulation:
         self._rng = rng
         self._summary: SimulationSummary | None = None
         self._instant_cls = Instant
-        self.model, self.objects = lowering.lower(self._sources, self._entities)
+        self.model, self.objects = lowering.lower(self._sources, self._entities, probes=self._probes)
 
     @property
     def summary(self):
@@ -604,7 +605,13 @@ class Simulation:
         if getattr(self, "_rng", "philox") == "stock":
             eng.set_trace(*stock_streams(self._seed, 1, caps["sample_cap"] * 2 + 64))
         # per-server service-time lists / per-collector samples are demultiplexed with the event records
-        need_events = len(self.model.ids_of(A.HS_ENT_SERVER)) > 1 or len(self.model.ids_of(A.HS_ENT_SINK)) > 1
+        n_streams = len(self.model.ids_of(A.HS_ENT_SINK)) + len(self.model.ids_of(A.HS_ENT_PROBE))
+        need_events = len(self.model.ids_of(A.HS_ENT_SERVER)) > 1 or n_streams > 1
+        if self.model.ids_of(A.HS_ENT_PROBE):        # probe samples share the sample stream
+            dur = self._end_time.to_seconds()
+            extra = sum(int(dur * float(self.model.profiles[int(self.model.entities["i3"][i]) - 1]["p"][0])) + 8
+                        for i in self.model.ids_of(A.HS_ENT_SOURCE) if int(self.model.entities["i3"][i]) > 0)
+            caps["sample_cap"] += extra
         for _ in range(6):
             kw = dict(caps)
             if need_events:
@@ -644,7 +651,7 @@ class Simulation:
         s = out["summaries"][r]
         n_smp, n_svc = int(s["n_sink_samples"]), int(s["n_service_samples"])
         samples = out["sink_samples"][r][:n_smp] if out.get("sink_samples") is not None else None
-        sinks = self.model.ids_of(A.HS_ENT_SINK)
+        sinks = self.model.ids_of(A.HS_ENT_SINK) + self.model.ids_of(A.HS_ENT_PROBE)
         servers = self.model.ids_of(A.HS_ENT_SERVER)
         per_server = {i: [] for i in servers}
         per_sink = {i: None for i in sinks}
@@ -653,7 +660,7 @@ class Simulation:
                 per_sink[sinks[0]] = samples
             elif out.get("records") is not None:
                 rec = out["records"][r][: int(s["events_processed"])]
-                who = rec["entity"][rec["kind"] == A.HS_EV_REQ_SINK][: len(samples)]
+                who = rec["entity"][(rec["kind"] == A.HS_EV_REQ_SINK) | (rec["kind"] == A.HS_EV_PROBE)][: len(samples)]
                 for i in sinks:
                     per_sink[i] = samples[who == i]
         if out.get("service_samples") is not None:
@@ -665,12 +672,22 @@ class Simulation:
                 who = rec["entity"][rec["kind"] == A.HS_EV_REQ_WORKER][: len(svc)]
                 for ent, x in zip(who, svc):
                     per_server[int(ent)].append(float(x))
+        # Probe objects: their ticking is objects[i] (a SOURCE row); the measurement row it targets
+        # (kind PROBE, beyond len(objects)) carries the samples
+        for i, o in enumerate(self.objects):
+            if int(kinds[i]) == A.HS_ENT_SOURCE and hasattr(o, "data_sink"):
+                pid = int(self.model.entities["target"][i])
+                sm = per_sink.get(pid)
+                if sm is not None:
+                    o.data_sink._samples = [(float(int(t)) / 1_000_000_000, float(x))
+                                            for t, x in zip(sm["completion_ns"], sm["latency_s"])]
         for i, o in enumerate(self.objects):
             k = int(kinds[i])
             row = st[i]
             if k == A.HS_ENT_SOURCE:
                 o._generated_count = int(row["c0"])
-                o._event_provider._generated = int(row["c1"])
+                if hasattr(o._event_provider, "_generated"):
+                    o._event_provider._generated = int(row["c1"])
             elif k == A.HS_ENT_SERVER:
                 o._queue.stats_accepted, o._queue.stats_dropped = int(row["c0"]), int(row["c1"])
                 o._requests_completed, o._requests_rejected = int(row["c2"]), int(row["c3"])

@@ -128,6 +128,16 @@ static int validate_model(const hs_model_desc *m)
             if (e.d0 < 0.0) return fail(HS_ERR_INVALID, "entity %u: negative service time", i);
             break;
         case HS_ENT_SINK: case HS_ENT_COUNTER: break;
+        case HS_ENT_PROBE: {
+            if (e.target < 0 || (uint32_t)e.target >= n) return fail(HS_ERR_INVALID, "entity %u: probe target out of range", i);
+            const int tk = m->entities[e.target].kind;
+            const bool ok = (e.i0 >= HS_METRIC_DEPTH && e.i0 <= HS_METRIC_STATS_DROPPED) ? tk == HS_ENT_SERVER
+                          : e.i0 == HS_METRIC_EVENTS_RECEIVED ? tk == HS_ENT_SINK
+                          : e.i0 == HS_METRIC_TOTAL ? tk == HS_ENT_COUNTER
+                          : e.i0 == HS_METRIC_GENERATED_COUNT ? tk == HS_ENT_SOURCE : false;
+            if (!ok) return fail(HS_ERR_INVALID, "entity %u: metric %d is not defined for the probed entity", i, e.i0);
+            break;
+        }
         case HS_ENT_LB:
             if (e.i0 != HS_LB_ROUND_ROBIN && e.i0 != HS_LB_KEY_TABLE) return fail(HS_ERR_INVALID, "entity %u: bad LB strategy", i);
             if (e.i2 < 0 || e.i1 < 0 || (uint32_t)(e.i1 + e.i2) > m->n_backends) return fail(HS_ERR_INVALID, "entity %u: backend list out of range", i);

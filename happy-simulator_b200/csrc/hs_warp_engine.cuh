@@ -210,7 +210,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                 e->d0 = M.n_cells ? M.cell_d0[(size_t)cell * ne + i] : d.d0;
                 e->i0 = M.n_cells ? M.cell_i0[(size_t)cell * ne + i] : d.i0;
                 e->lambda = (d.kind == HS_ENT_SERVER && d.i2 == HS_SVC_EXPONENTIAL) ? HS_DIV(1.0, e->d0) : 0.0;
-                if (d.kind == HS_ENT_SINK) {
+                if (d.kind == HS_ENT_SINK || d.kind == HS_ENT_PROBE) {
                     e->u.snk.mn = __longlong_as_double(0x7ff0000000000000LL);
                     e->u.snk.mx = __longlong_as_double(0xfff0000000000000LL);
                 }
@@ -343,7 +343,8 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
     } while (0)
 #define HS_W_REQ_KIND(TGT) (M.ents[(TGT)].kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE :                   \
                             M.ents[(TGT)].kind == HS_ENT_SINK ? HS_EV_REQ_SINK :                         \
-                            M.ents[(TGT)].kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : HS_EV_REQ_LB)
+                            M.ents[(TGT)].kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER :                   \
+                            M.ents[(TGT)].kind == HS_ENT_PROBE ? HS_EV_PROBE : HS_EV_REQ_LB)
                     /* Event._run_completion_hooks for a request whose plain handler returned:
                      * only the LoadBalancer on_complete hook can be attached (event.py:277-283). */
 #define HS_W_REQUEST_HOOKS()                                                                             \
@@ -484,6 +485,31 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         HS_W_REQUEST_HOOKS();
                         break;
                     }
+                    case HS_EV_PROBE: {                /* measure_callback, instrumentation/probe.py:51-66 */
+                        const hs_entity_desc pd = M.ents[ent];
+                        const hs_went *T = &E[pd.target];
+                        const int tk = M.ents[pd.target].kind;
+                        double val = 0.0;
+                        switch (pd.i0) {
+                        case HS_METRIC_DEPTH: val = (double)T->u.srv.q_len; break;
+                        case HS_METRIC_ACTIVE_REQUESTS: val = (double)T->u.srv.active; break;
+                        case HS_METRIC_UTILIZATION: val = T->i0 == 0 ? 0.0 : HS_DIV((double)T->u.srv.active, (double)T->i0); break;
+                        case HS_METRIC_AVAILABLE_CAPACITY: val = (double)(T->i0 - T->u.srv.active); break;
+                        case HS_METRIC_STATS_ACCEPTED: val = (double)T->u.srv.accepted; break;
+                        case HS_METRIC_STATS_DROPPED: val = (double)T->u.srv.dropped; break;
+                        case HS_METRIC_EVENTS_RECEIVED: case HS_METRIC_TOTAL: val = (double)T->u.snk.received; break;
+                        case HS_METRIC_GENERATED_COUNT: val = (double)T->u.src.generated; break;
+                        }
+                        (void)tk;
+                        X->u.snk.received++;
+                        hs_neumaier_add(&X->u.snk.sum, &X->u.snk.comp, val);
+                        if (val < X->u.snk.mn) X->u.snk.mn = val;
+                        if (val > X->u.snk.mx) X->u.snk.mx = val;
+                        if ((FLAGS & HS_WF_REC) && smp) { hs_sink_sample q; q.completion_ns = now; q.latency_s = val; smp[H->smp_pos] = q;
+                            H->smp_pos = (H->smp_pos + 1 == P.sample_cap) ? 0u : H->smp_pos + 1; }
+                        H->n_smp++;
+                        break;
+                    }
                     case HS_EV_REQ_COUNTER:            /* Counter.handle_event, common.py:92-95 */
                         X->u.snk.received++;
                         HS_W_REQUEST_HOOKS();
@@ -543,6 +569,8 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                 case HS_ENT_SINK: a.c0 = e->u.snk.received; a.f0 = hs_neumaier_result(e->u.snk.sum, e->u.snk.comp);
                     a.f1 = e->u.snk.sumsq; a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
                 case HS_ENT_COUNTER: a.c0 = e->u.snk.received; break;
+                case HS_ENT_PROBE: a.c0 = e->u.snk.received; a.f0 = hs_neumaier_result(e->u.snk.sum, e->u.snk.comp);
+                    a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
                 case HS_ENT_LB: a.c0 = e->u.lb.received; a.c1 = e->u.lb.forwarded; a.c2 = e->u.lb.in_flight;
                     a.c3 = e->u.lb.responses; break;
                 }

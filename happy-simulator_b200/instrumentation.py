@@ -158,3 +158,59 @@ class ThroughputTracker(_Collector):
         super().__init__(name)
 
     def throughput(self, window_s: float = 1.0) -> BucketedData: return self.data.bucket(window_s)
+
+
+class _ProbeProfile:
+    """instrumentation/probe.py:25-35 -- constant rate, but NOT a ConstantRateProfile: probe ticks take the
+    general (adaptive Simpson + Brent) arrival path, e.g. interval 0.1 s -> 100000000, 200000000,
+    299999999, ... ns."""
+
+    def __init__(self, interval_seconds: float):
+        if interval_seconds <= 0:
+            raise ValueError("Probe interval must be positive.")
+        self.rate = 1.0 / interval_seconds
+        self._interval = interval_seconds
+
+    def get_rate(self, time) -> float:
+        return self.rate
+
+
+class _ProbeEventProvider:
+    """instrumentation/probe.py:38-78"""
+
+    def __init__(self, target, metric: str, data_sink: Data):
+        self.target = target
+        self.metric = metric
+        self.data_sink = data_sink
+
+
+class Probe:
+    """instrumentation/probe.py:81-164 -- periodic sampler of ``getattr(target, metric)`` into a Data."""
+
+    def __init__(self, target, metric: str, data: Data, interval: float = 1.0, start_time=None):
+        from .api import ConstantArrivalTimeProvider, Instant
+        if start_time is not None and start_time.nanoseconds != 0:
+            raise NotImplementedError("probe start_time must be Instant.Epoch on the device engine")
+        self.target, self.metric, self.data_sink = target, metric, data
+        self.name = f"Probe_{target.name}_{metric}"
+        self._event_provider = _ProbeEventProvider(target, metric, data)
+        self._time_provider = ConstantArrivalTimeProvider(_ProbeProfile(interval), start_time=Instant.Epoch)
+        self._generated_count = 0
+
+    @property
+    def generated_count(self) -> int:
+        return self._generated_count
+
+    @classmethod
+    def on(cls, target, metric: str, interval: float = 1.0):
+        data = Data()
+        return cls(target=target, metric=metric, data=data, interval=interval), data
+
+    @classmethod
+    def on_many(cls, target, metrics, interval: float = 1.0):
+        probes, data = [], {}
+        for m in metrics:
+            p, d = cls.on(target, m, interval=interval)
+            probes.append(p)
+            data[m] = d
+        return probes, data

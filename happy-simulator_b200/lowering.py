@@ -103,7 +103,7 @@ def _queue_policy(q):
     return (A.HS_Q_LIFO if name == "LIFOQueue" else A.HS_Q_FIFO), cap
 
 
-def lower(sources, entities, *, key_population: int | None = None):
+def lower(sources, entities, *, key_population: int | None = None, probes=None):
     """-> (FlatModel, objects) where objects[i] is the Python object of entity id i.
 
     Entity ids: sources first (in ``sources`` order, the bootstrap order of
@@ -120,13 +120,15 @@ def lower(sources, entities, *, key_population: int | None = None):
 
     for s in sources or []:
         add(s)
+    for p_ in probes or []:          # Simulation.__init__ bootstraps probes right after the sources
+        add(p_)
     for e in entities or []:
         add(e)
 
     def kind_of(o):
         n = _cls(o)
         if hasattr(o, "_event_provider") and hasattr(o, "_time_provider"):
-            return A.HS_ENT_SOURCE
+            return "probe" if _cls(o._event_provider) == "_ProbeEventProvider" else A.HS_ENT_SOURCE
         if hasattr(o, "_concurrency_model") and hasattr(o, "_service_time") and hasattr(o, "_queue"):
             return A.HS_ENT_SERVER
         if hasattr(o, "latencies_s") and hasattr(o, "events_received"):
@@ -146,7 +148,9 @@ def lower(sources, entities, *, key_population: int | None = None):
     while i < len(objs):
         o = objs[i]
         k = kind_of(o)
-        if k == A.HS_ENT_SOURCE:
+        if k == "probe":
+            add(o._event_provider.target)
+        elif k == A.HS_ENT_SOURCE:
             t = getattr(o._event_provider, "_target", None)
             if t is None:
                 raise UnsupportedModelError(f"source {o.name!r}: event provider {_cls(o._event_provider)} has no target")
@@ -161,10 +165,19 @@ def lower(sources, entities, *, key_population: int | None = None):
 
     b = ModelBuilder()
     pending_lb = []
+    probe_rows = []
     for o in objs:
         k = kind_of(o)
         name = getattr(o, "name", _cls(o))
-        if k == A.HS_ENT_SOURCE:
+        if k == "probe":
+            ep = o._event_provider
+            if ep.metric not in A.METRICS:
+                raise UnsupportedModelError(f"probe {name!r}: metric {ep.metric!r} (supported: {sorted(A.METRICS)})")
+            prof = o._time_provider.profile
+            # the measurement row is appended after all objects; patch the target then
+            sid = b.source(name, poisson=False, target=-1, profile=("constant", float(prof.rate)))
+            probe_rows.append((sid, name, ids[id(ep.target)], ep.metric))
+        elif k == A.HS_ENT_SOURCE:
             prov = o._event_provider
             if _cls(prov) not in ("SimpleEventProvider", "_SimpleEventProvider"):
                 raise UnsupportedModelError(f"source {name!r}: event provider {_cls(prov)}")
@@ -229,6 +242,9 @@ def lower(sources, entities, *, key_population: int | None = None):
             strat = A.HS_LB_KEY_TABLE
             b._key_table = np.asarray(table, np.int32)
         b._rows[idx] = (A.HS_ENT_LB, -1, strat, off, len(backs), 0, -1, 0.0, 0.0)
+    for sid, name, tgt, metric in probe_rows:
+        pid = b._add(name + ".measure", A.HS_ENT_PROBE, tgt, A.METRICS[metric])
+        b.set_target(sid, pid)
     model = b.build()
     # a source whose key population is set needs the table length to match (validated by the C-ABI too)
     return model, objs

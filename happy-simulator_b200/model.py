@@ -110,6 +110,14 @@ class ModelBuilder:
     def counter(self, name="Counter"):
         return self._add(name, A.HS_ENT_COUNTER)
 
+    def probe(self, name="Probe", *, target, metric, interval_s):
+        """instrumentation/probe.py:81-130: a Source ticking every `interval_s` through the GENERAL arrival
+        path (its _ProbeProfile is not a ConstantRateProfile) whose payload samples `metric` of `target`.
+        Returns (source_id, probe_id)."""
+        pid = self._add(name + ".measure", A.HS_ENT_PROBE, int(target), A.METRICS[metric])
+        sid = self.source(name, poisson=False, target=pid, profile=("constant", 1.0 / interval_s))
+        return sid, pid
+
     def load_balancer(self, name="LB", *, backends, key_table=None):
         off = len(self._backends)
         self._backends += [int(b) for b in backends]

@@ -47,8 +47,14 @@ enum {
     HS_ENT_SERVER = 2,   /* components/server/server.py:43 Server = Queue + QueueDriver + worker    */
     HS_ENT_SINK = 3,     /* components/common.py:18 Sink                                            */
     HS_ENT_COUNTER = 4,  /* components/common.py:79 Counter                                         */
-    HS_ENT_LB = 5        /* components/load_balancer/load_balancer.py:60 LoadBalancer               */
+    HS_ENT_LB = 5,       /* components/load_balancer/load_balancer.py:60 LoadBalancer               */
+    HS_ENT_PROBE = 6     /* instrumentation/probe.py:81 Probe's measurement callback (the Probe's own
+                            ticking is a SOURCE row with a constant profile on the general path)     */
 };
+/* Probe metrics (getattr(target, metric), probe.py:55-62). */
+enum { HS_METRIC_DEPTH = 0, HS_METRIC_ACTIVE_REQUESTS = 1, HS_METRIC_UTILIZATION = 2, HS_METRIC_AVAILABLE_CAPACITY = 3,
+       HS_METRIC_STATS_ACCEPTED = 4, HS_METRIC_STATS_DROPPED = 5, HS_METRIC_EVENTS_RECEIVED = 6, HS_METRIC_TOTAL = 7,
+       HS_METRIC_GENERATED_COUNT = 8 };
 enum { HS_ARR_CONSTANT = 0, HS_ARR_POISSON = 1 };       /* load/providers/{constant,poisson}_arrival.py */
 enum { HS_SVC_CONSTANT = 0, HS_SVC_EXPONENTIAL = 1 };   /* distributions/{constant,exponential}.py      */
 enum { HS_Q_FIFO = 0, HS_Q_LIFO = 1 };                  /* components/queue_policy.py:75,117            */
@@ -67,13 +73,14 @@ enum {
     HS_EV_CONTINUATION = 7, /* ProcessContinuation (service end)     core/event.py:465            */
     HS_EV_REQ_SINK = 8,     /* Request -> Sink                       common.py:36                 */
     HS_EV_LB_RESPONSE = 9,  /* _lb_response -> LoadBalancer          load_balancer.py:435         */
-    HS_EV_REQ_COUNTER = 10  /* Request -> Counter                    common.py:92                 */
+    HS_EV_REQ_COUNTER = 10, /* Request -> Counter                    common.py:92                 */
+    HS_EV_PROBE = 11        /* probe_event -> measurement callback   instrumentation/probe.py:51  */
 };
 
 typedef struct hs_entity_desc {
     int32_t kind;      /* HS_ENT_*                                                              */
-    int32_t target;    /* SOURCE: entity receiving payloads; SERVER: downstream or -1           */
-    int32_t i0;        /* SOURCE: HS_ARR_*; SERVER: concurrency (FixedConcurrency); LB: HS_LB_* */
+    int32_t target;    /* SOURCE: entity receiving payloads; SERVER: downstream or -1; PROBE: measured entity */
+    int32_t i0;        /* SOURCE: HS_ARR_*; SERVER: concurrency (FixedConcurrency); LB: HS_LB_*; PROBE: HS_METRIC_* */
     int32_t i1;        /* SOURCE: key population (0 = no routing key); SERVER: HS_Q_*;
                           LB: offset of its backend list in hs_model_desc.backends              */
     int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends                              */
@@ -169,7 +176,7 @@ typedef struct hs_replica_summary {
 
 typedef struct hs_entity_stats {
     int64_t c0; /* SOURCE generated_count | SERVER stats_accepted | SINK events_received
-                   | COUNTER total | LB requests_received                                      */
+                   | COUNTER total | LB requests_received | PROBE samples taken               */
     int64_t c1; /* SOURCE payloads created | SERVER stats_dropped | LB requests_forwarded       */
     int64_t c2; /* SERVER requests_completed | LB in-flight entries left                        */
     int64_t c3; /* SERVER requests_rejected | SERVER (after run) -- ; LB responses handled      */

@@ -201,6 +201,7 @@ static int request_kind_for(const orun *R, int ent)
     case HS_ENT_SINK: return HS_EV_REQ_SINK;
     case HS_ENT_COUNTER: return HS_EV_REQ_COUNTER;
     case HS_ENT_LB: return HS_EV_REQ_LB;
+    case HS_ENT_PROBE: return HS_EV_PROBE;
     default: return -1;
     }
 }
@@ -392,6 +393,30 @@ static void handle(orun *R, oev *e)
         run_request_hooks(R, e);
         break;
     }
+    case HS_EV_PROBE: {                   /* measure_callback, instrumentation/probe.py:51-66 */
+        const oent *T = &R->ents[E->d.target];
+        double val = 0.0;
+        switch (E->d.i0) {                /* getattr(target, metric) */
+        case HS_METRIC_DEPTH: val = (double)T->q_len; break;                       /* queued_resource.py:113 */
+        case HS_METRIC_ACTIVE_REQUESTS: val = (double)T->active; break;            /* server.py:154 */
+        case HS_METRIC_UTILIZATION: val = T->d.i0 == 0 ? 0.0 : (double)T->active / (double)T->d.i0; break;  /* server.py:164-173 */
+        case HS_METRIC_AVAILABLE_CAPACITY: val = (double)(T->d.i0 - T->active); break;
+        case HS_METRIC_STATS_ACCEPTED: val = (double)T->accepted; break;
+        case HS_METRIC_STATS_DROPPED: val = (double)T->dropped; break;
+        case HS_METRIC_EVENTS_RECEIVED: case HS_METRIC_TOTAL: val = (double)T->received; break;
+        case HS_METRIC_GENERATED_COUNT: val = (double)T->generated_count; break;
+        }
+        E->received++;
+        hs_neumaier_add(&E->sum, &E->comp, val);
+        if (val < E->mn) E->mn = val;
+        if (val > E->mx) E->mx = val;
+        if (R->smp && R->p->sample_cap) {
+            hs_sink_sample *q = &R->smp[R->n_smp % R->p->sample_cap];
+            q->completion_ns = R->now; q->latency_s = val;
+        }
+        R->n_smp++;
+        break;
+    }
     case HS_EV_REQ_COUNTER:               /* Counter.handle_event, common.py:92-95 */
         E->received++;
         run_request_hooks(R, e);
@@ -493,6 +518,8 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
             case HS_ENT_SINK:
                 st->c0 = E->received; st->f0 = hs_neumaier_result(E->sum, E->comp); st->f1 = E->sumsq; st->f2 = E->mn; st->f3 = E->mx; break;
             case HS_ENT_COUNTER: st->c0 = E->received; break;
+            case HS_ENT_PROBE:
+                st->c0 = E->received; st->f0 = hs_neumaier_result(E->sum, E->comp); st->f2 = E->mn; st->f3 = E->mx; break;
             case HS_ENT_LB:
                 st->c0 = E->lb_received; st->c1 = E->lb_forwarded; st->c2 = E->lb_in_flight; st->c3 = E->lb_responses; break;
             }

@@ -93,6 +93,39 @@ def profiled(profile, poisson, lb=0):
     return b.build()
 
 
+def probed():
+    """M/M/1 with a depth probe every 0.1 s and a Sink counter probe every 0.5 s."""
+    b = hs.ModelBuilder()
+    src = b.source(rate=8.0)
+    srv = b.server(mean_service_s=0.1)
+    snk = b.sink()
+    b.set_target(src, srv); b.set_target(srv, snk)
+    b.probe("Probe_Server_depth", target=srv, metric="depth", interval_s=0.1)
+    b.probe("Probe_Sink_events_received", target=snk, metric="events_received", interval_s=0.5)
+    m = b.build()
+    # Simulation.__init__ bootstraps sources first, then probes: ids must follow that order
+    return reorder_sources_first(m)
+
+
+def reorder_sources_first(m):
+    import numpy as np
+    from happysim_b200 import _abi as A
+    n = m.n_entities
+    kinds = m.entities["kind"]
+    is_probe_src = [int(kinds[i]) == A.HS_ENT_SOURCE and int(kinds[int(m.entities["target"][i])]) == A.HS_ENT_PROBE for i in range(n)]
+    order = [i for i in range(n) if int(kinds[i]) == A.HS_ENT_SOURCE and not is_probe_src[i]] + \
+            [i for i in range(n) if is_probe_src[i]] + [i for i in range(n) if int(kinds[i]) != A.HS_ENT_SOURCE]
+    new_id = {old: new for new, old in enumerate(order)}
+    ents = m.entities[order].copy()
+    for r in ents:
+        if int(r["target"]) >= 0:
+            r["target"] = new_id[int(r["target"])]
+    m.entities = ents
+    m.names = [m.names[i] for i in order]
+    m.backends = np.array([new_id[int(x)] for x in m.backends], dtype=np.int32)
+    return m
+
+
 def philox_cases():
     c = {}
     c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
@@ -115,6 +148,7 @@ def philox_cases():
     c["ramp_poisson_mm1"] = (profiled(("linear_ramp", 20.0, 2.0, 12.0), True), dict(seed=31, rid=2, end_s=30))
     c["spike_poisson_mm1"] = (profiled(("spike", 5.0, 40.0, 4.0, 3.0), True), dict(seed=32, rid=0, end_s=12))
     c["ramp_down_constant"] = (profiled(("linear_ramp", 5.0, 20.0, 1.0), False), dict(seed=0, rid=0, end_s=20))
+    c["probe_mm1"] = (probed(), dict(seed=42, rid=0, end_s=20))
     c["spike_constant_lb4"] = (profiled(("spike", 10.0, 100.0, 2.0, 1.0), False, lb=4), dict(seed=3, rid=1, end_s=6))
     return c
 

@@ -59,6 +59,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     from happysimulator.load.providers.poisson_arrival import PoissonArrivalTimeProvider
     from happysimulator.load.source import SimpleEventProvider, Source
     from happysimulator.load.source_event import SourceEvent
+    from happysimulator.instrumentation.probe import Probe
+    from happysimulator.instrumentation.data import Data
 
     L = O.lib()
     ents = model.entities
@@ -121,10 +123,25 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             strat = RoundRobin()
         objs[i] = LoadBalancer(names[i], backends=be, strategy=strat)
     sources = []
+    probes = []
+    metric_names = {v: k for k, v in A.METRICS.items()}
+    probe_data = {}          # PROBE row id -> Data
     for i in range(n):
         if int(ents["kind"][i]) != A.HS_ENT_SOURCE:
             continue
         e = ents[i]
+        if int(ents["kind"][int(e["target"])]) == A.HS_ENT_PROBE:
+            prow = ents[int(e["target"])]
+            rate_ = float(model.profiles[int(e["i3"]) - 1]["p"][0])
+            d_ = Data()
+            pr_ = Probe(target=objs[int(prow["target"])], metric=metric_names[int(prow["i0"])], data=d_,
+                        interval=1.0 / rate_)
+            pr_._time_provider.profile.rate = rate_       # exactly the lowered rate (1/interval may not round-trip)
+            objs[i] = pr_
+            objs[int(e["target"])] = d_                    # stand-in object for the measurement row
+            probe_data[int(e["target"])] = d_
+            probes.append(pr_)
+            continue
         target = objs[int(e["target"])]
         stop = Instant(int(e["l0"])) if int(e["l0"]) >= 0 else None
         pop = int(e["i1"])
@@ -153,8 +170,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         random.seed(seed)
         np.random.seed(seed)
 
-    entities = [o for i, o in enumerate(objs) if int(ents["kind"][i]) != A.HS_ENT_SOURCE]
-    sim = Simulation(end_time=Instant(int(end_ns)), sources=sources, entities=entities)
+    entities = [o for i, o in enumerate(objs) if int(ents["kind"][i]) not in (A.HS_ENT_SOURCE, A.HS_ENT_PROBE)]
+    sim = Simulation(end_time=Instant(int(end_ns)), sources=sources, entities=entities, probes=probes or None)
 
     # ---- object -> entity id, for the pop tap
     oid = {}
@@ -176,6 +193,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         if isinstance(ev, ProcessContinuation):
             return A.HS_EV_CONTINUATION
         et = ev.event_type
+        if et == "probe_event":
+            return A.HS_EV_PROBE
         if et == "QUEUE_NOTIFY":
             return A.HS_EV_NOTIFY
         if et == "QUEUE_POLL":
@@ -196,9 +215,18 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             return A.HS_EV_REQ_LB
         raise AssertionError(f"unclassified event {ev!r}")
 
+    data_to_row = {id(d): row for row, d in probe_data.items()}
+
+    def target_id(ev):
+        if ev.event_type == "probe_event":         # Event.once -> CallbackEntity(fn=measure_callback)
+            for cell in ev.target._fn.__closure__:
+                if id(cell.cell_contents) in data_to_row:
+                    return data_to_row[id(cell.cell_contents)]
+        return oid[id(ev.target)]
+
     def tap():
         ev = orig_pop()
-        recs.append((ev.time.nanoseconds, ev._sort_index, classify(ev), oid[id(ev.target)]))
+        recs.append((ev.time.nanoseconds, ev._sort_index, classify(ev), target_id(ev)))
         return ev
 
     heap.pop = tap
@@ -222,8 +250,16 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     per_server_service = {}
     for i, o in enumerate(objs):
         k = int(ents["kind"][i])
-        if k == A.HS_ENT_SOURCE:
-            stats[i]["c0"], stats[i]["c1"] = o.generated_count, o._event_provider._generated
+        if k == A.HS_ENT_PROBE:
+            vals = [float(v) for _, v in o._samples]
+            stats[i]["c0"] = len(vals)
+            stats[i]["f0"] = sum(vals)
+            stats[i]["f2"] = min(vals) if vals else np.inf
+            stats[i]["f3"] = max(vals) if vals else -np.inf
+            sink_samples.append((i, [int(round(t * 1e9)) for t, _ in o._samples], vals))
+        elif k == A.HS_ENT_SOURCE:
+            stats[i]["c0"] = o.generated_count
+            stats[i]["c1"] = getattr(o._event_provider, "_generated", o.generated_count - (1 if False else 0))
         elif k == A.HS_ENT_SERVER:
             st = o.stats
             stats[i]["c0"], stats[i]["c1"] = o.stats_accepted, o.stats_dropped
@@ -253,7 +289,7 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     svc_cursor = {i: 0 for i in per_server_service}
     svc_merged = []
     for t, idx, kind, ent in recs:
-        if kind == A.HS_EV_REQ_SINK:
+        if kind in (A.HS_EV_REQ_SINK, A.HS_EV_PROBE):
             c = cursors[ent]
             merged.append((by_id[ent][0][c], by_id[ent][1][c]))
             cursors[ent] = c + 1

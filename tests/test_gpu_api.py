@@ -177,3 +177,23 @@ def test_source_with_profile_matches_the_reference_fixture():
     assert summary.total_events_processed == int(z["summaries"]["events_processed"][0])
     want = [float(x) for x in z["sink_samples"]["latency_s"]]
     assert sink.latencies_s[: len(want)] == want
+
+
+def test_probes_sample_queue_depth_like_the_reference():
+    """Probe.on(server, "depth", 0.1) -- tick times come from the general arrival path
+    (100000000, 200000000, 299999999, ... ns) and each tick samples the device-side queue depth."""
+    _, kw, z = G.load("philox_probe_mm1")
+    sink = hs.Sink()
+    server = hs.Server("Server", service_time=hs.ExponentialLatency(0.1), downstream=sink)
+    src = hs.Source.poisson(rate=8, target=server)
+    p1, depth = hs.Probe.on(server, "depth", interval=0.1)
+    p2, seen = hs.Probe.on(sink, "events_received", interval=0.5)
+    summary = hs.Simulation(end_time=hs.Instant(kw["end_ns"]), sources=[src], entities=[server, sink],
+                            probes=[p1, p2], seed=kw["seed"]).run()
+    assert summary.total_events_processed == int(z["summaries"]["events_processed"][0])
+    st = z["entity_stats"][0]
+    assert depth.count() == int(st[5]["c0"]) and seen.count() == int(st[6]["c0"])
+    assert depth.sum() == float(st[5]["f0"]) and depth.max() == float(st[5]["f3"])
+    assert [round(t * 1e9) for t in depth.times()[:4]] == [100000000, 200000000, 299999999, 399999998]
+    assert seen.raw_values() == sorted(seen.raw_values()) and seen.raw_values()[-1] <= sink.events_received
+    assert p1.generated_count == int(st[1]["c0"])

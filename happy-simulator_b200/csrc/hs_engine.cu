@@ -455,17 +455,19 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
         hs_lane_state *st = (hs_lane_state *)E->d_state.p;
         hs_ring_entry *rg = (hs_ring_entry *)E->d_rings.p;
-        const int fl = (want_hash ? HS_LF_HASH : 0) | (want_rec ? HS_LF_REC : 0) | (M.has_profile ? HS_LF_PROFILE : 0);
+        const bool simple = !M.has_profile && !R.trace_arr && !R.trace_svc && M.arr_kind == HS_ARR_POISSON &&
+                            M.svc_kind == HS_SVC_EXPONENTIAL && M.policy == HS_Q_FIFO && M.capacity < 0 &&
+                            M.stop_after < 0 && M.dst_id >= 0 && M.dst_kind == HS_ENT_SINK;
+        const int fl = (want_hash ? HS_LF_HASH : 0) | (want_rec ? HS_LF_REC : 0) |
+                       (M.has_profile ? HS_LF_PROFILE : 0) | (simple ? HS_LF_SIMPLE : 0);
+#define HS_LAUNCH_LANE(F) case F: hs_lane_kernel<F><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
         switch (fl) {
-        case 0: hs_lane_kernel<0><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
-        case 1: hs_lane_kernel<1><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
-        case 2: hs_lane_kernel<2><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
-        case 3: hs_lane_kernel<3><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
-        case 4: hs_lane_kernel<4><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
-        case 5: hs_lane_kernel<5><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
-        case 6: hs_lane_kernel<6><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
-        default: hs_lane_kernel<7><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+        HS_LAUNCH_LANE(0) HS_LAUNCH_LANE(1) HS_LAUNCH_LANE(2) HS_LAUNCH_LANE(3)
+        HS_LAUNCH_LANE(4) HS_LAUNCH_LANE(5) HS_LAUNCH_LANE(6) HS_LAUNCH_LANE(7)
+        HS_LAUNCH_LANE(8) HS_LAUNCH_LANE(9) HS_LAUNCH_LANE(10) HS_LAUNCH_LANE(11)
+        default: return fail(HS_ERR_STATE, "no lane kernel for flags %d", fl);
         }
+#undef HS_LAUNCH_LANE
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
         E->launches += 1;

@@ -73,6 +73,8 @@
 #define HS_LF_HASH 1      /* maintain the order hash                         */
 #define HS_LF_REC 2       /* write event records / sink / service samples    */
 #define HS_LF_PROFILE 4   /* non-constant rate profile (Simpson + Brent path) */
+#define HS_LF_SIMPLE 8    /* compile-time model: Poisson source without stop_after, exponential FIFO server with an
+                             unbounded queue, Sink downstream, Philox draws -- the BASELINE configs[0]/[1] shape */
 
 struct hs_now_ev {        /* an event created at the current timestamp       */
     uint64_t idx;         /* Event._sort_index                               */
@@ -180,11 +182,17 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     hs_profile_desc prof_local;
     if (FLAGS & HS_LF_PROFILE) prof_local = M.prof;
     const hs_profile_desc *profp = (FLAGS & HS_LF_PROFILE) ? &prof_local : nullptr;
-    const bool poisson = (M.arr_kind == HS_ARR_POISSON);
-    const bool expo = (M.svc_kind == HS_SVC_EXPONENTIAL);
-    const bool lifo = (M.policy == HS_Q_LIFO);
-    const int64_t cap = M.capacity;
-    const int dst_ev = (M.dst_kind == HS_ENT_SINK) ? HS_EV_REQ_SINK : HS_EV_REQ_COUNTER;
+    constexpr bool SIMPLE = (FLAGS & HS_LF_SIMPLE) != 0;
+    const bool poisson = SIMPLE ? true : (M.arr_kind == HS_ARR_POISSON);
+    const bool expo = SIMPLE ? true : (M.svc_kind == HS_SVC_EXPONENTIAL);
+    const bool lifo = SIMPLE ? false : (M.policy == HS_Q_LIFO);
+    const int64_t cap = SIMPLE ? -1 : M.capacity;
+    const int64_t stop_after = SIMPLE ? -1 : M.stop_after;
+    const bool dst_is_sink = SIMPLE ? true : (M.dst_kind == HS_ENT_SINK);
+    const bool has_dst = SIMPLE ? true : (M.dst_id >= 0);
+    const double *trace_arr = SIMPLE ? nullptr : P.trace_arr;
+    const double *trace_svc = SIMPLE ? nullptr : P.trace_svc;
+    const int dst_ev = dst_is_sink ? HS_EV_REQ_SINK : HS_EV_REQ_COUNTER;
     const uint32_t ring_mask = P.ring - 1u;
     hs_ring_entry *ring = rings + (size_t)r * P.ring;
     const bool windowed = (P.window_end_ns >= 0 && P.window_end_ns < P.end_ns);
@@ -258,12 +266,12 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     do {                                                                                     \
         if (!finished && (uint32_t)(a_gen - arr_draws) + 2u <= HS_DRAW_BUF) {                \
             double u0_ = 0.0, u1_ = 0.0, g0_ = 1.0, g1_ = 1.0;                               \
-            if (poisson && !P.trace_arr) { hs_uniform_pair(seed, rid, sid_arr, a_gen >> 1, &u0_, &u1_); \
+            if (poisson && !trace_arr) { hs_uniform_pair(seed, rid, sid_arr, a_gen >> 1, &u0_, &u1_); \
                                            g0_ = hs_exp1(u0_); g1_ = hs_exp1(u1_); }         \
-            if (poisson && P.trace_arr) {                                                    \
+            if (poisson && trace_arr) {                                                    \
                 const uint64_t k_ = a_gen & ~1ull;                                           \
                 if (k_ + 1 >= P.n_trace_arr) { status |= HS_ST_TRACE_EXHAUSTED; finished = true; } \
-                else { g0_ = P.trace_arr[(size_t)r * P.n_trace_arr + k_]; g1_ = P.trace_arr[(size_t)r * P.n_trace_arr + k_ + 1]; } \
+                else { g0_ = trace_arr[(size_t)r * P.n_trace_arr + k_]; g1_ = trace_arr[(size_t)r * P.n_trace_arr + k_ + 1]; } \
             }                                                                                \
             if (!(a_gen & 1)) {                                                              \
                 t_gen = HS_NEXT_ARRIVAL(t_gen, g0_); a_gen++;                                \
@@ -275,13 +283,13 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         if (!finished && (uint32_t)(s_gen - (uint64_t)n_svc) + 2u <= HS_DRAW_BUF) {          \
             double u0_ = 0.0, u1_ = 0.0;                                                     \
             int64_t d0_ = hs_seconds_to_ns(mean), d1_ = d0_;                                 \
-            if (expo && !P.trace_svc) { hs_uniform_pair(seed, rid, sid_svc, s_gen >> 1, &u0_, &u1_); \
+            if (expo && !trace_svc) { hs_uniform_pair(seed, rid, sid_svc, s_gen >> 1, &u0_, &u1_); \
                                         d0_ = hs_exp_latency_ns(u0_, lambda); d1_ = hs_exp_latency_ns(u1_, lambda); } \
-            if (expo && P.trace_svc) {       /* Duration.from_seconds(-log(1-U) / lambda)         */ \
+            if (expo && trace_svc) {       /* Duration.from_seconds(-log(1-U) / lambda)         */ \
                 const uint64_t k_ = s_gen & ~1ull;                                           \
                 if (k_ + 1 >= P.n_trace_svc) { status |= HS_ST_TRACE_EXHAUSTED; finished = true; } \
-                else { d0_ = hs_seconds_to_ns(HS_DIV(P.trace_svc[(size_t)r * P.n_trace_svc + k_], lambda));  \
-                       d1_ = hs_seconds_to_ns(HS_DIV(P.trace_svc[(size_t)r * P.n_trace_svc + k_ + 1], lambda)); } \
+                else { d0_ = hs_seconds_to_ns(HS_DIV(trace_svc[(size_t)r * P.n_trace_svc + k_], lambda));  \
+                       d1_ = hs_seconds_to_ns(HS_DIV(trace_svc[(size_t)r * P.n_trace_svc + k_ + 1], lambda)); } \
             }                                                                                \
             if (!(s_gen & 1)) {                                                              \
                 const double s0_ = hs_ns_to_seconds(d0_);                                    \
@@ -331,7 +339,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
 
 #define HS_SINK(CREATED)                                                                     \
     do {                                                                                     \
-        if (M.dst_kind == HS_ENT_SINK) {                                                     \
+        if (dst_is_sink) {                                                                   \
             const double lat_ = hs_ns_to_seconds(now - (CREATED));                           \
             hs_neumaier_add(&sum, &comp, lat_); sumsq = HS_ADD(sumsq, HS_MUL(lat_, lat_));   \
             if (lat_ < mn) mn = lat_;                                                        \
@@ -387,6 +395,8 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         iT = 0; ctr = 0;
     }
 
+    const uint32_t stop_bits = HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW;
+    const int64_t fast_limit = (windowed && P.window_end_ns < P.end_ns) ? P.window_end_ns : P.end_ns;
     bool paused = false;
     while (true) {
         /* converged top of the loop: vote on termination and on refilling */
@@ -420,21 +430,19 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         }
         if (finished) continue;
 
-        if (!(now <= P.end_ns)) { finished = true; continue; }                 /* simulation.py:472 */
-        if (status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW)) { finished = true; continue; }
-        if (now_n == 0 && tT == INT64_MAX && !has_c) { finished = true; continue; }   /* heap exhausted */
-
         if (now_n == 0) {
             const bool pickC = has_c && (tC < tT || (tC == tT && iC < iT));
             const int64_t tn = pickC ? tC : tT;
-            if (windowed && tn > P.window_end_ns) { paused = true; finished = true; continue; }
-            const bool slow = (has_c && tC == tT) || (tn > P.end_ns) || (tn < now) || (processed + 8 > P.max_events);   /* a chain is <= 6 events: single-step near the limit */
+            /* fast path <=> the chosen event is not tied, lies inside both the run and the window
+             * (so `now <= end` holds before and after), and nothing exceptional is pending */
+            const bool slow = (has_c && tC == tT) || (tn > fast_limit) || (tn < now) || (status & stop_bits) ||
+                              (processed + 8 > P.max_events);   /* a chain is <= 6 events: single-step near the limit */
             if (!slow) {
                 now = tn;
                 if (!pickC) {
                     /* ===== fused arrival chain ================================== */
                     HS_EMIT(HS_EV_SOURCE_TICK, iT, M.src_id);
-                    const bool payload = !(M.stop_after >= 0 && now > M.stop_after);  /* source.py:68 */
+                    const bool payload = !(stop_after >= 0 && now > stop_after);  /* source.py:68 */
                     uint64_t idxP = 0;
                     if (payload) idxP = ctr++; else S->skipped++;
                     HS_NEXT_TICK();
@@ -474,10 +482,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     active = active > 0 ? active - 1 : 0;      /* FixedConcurrency.release */
                     total_service = HS_ADD(total_service, svc_s);
                     uint64_t idxF = 0;
-                    if (M.dst_id >= 0) idxF = ctr++;           /* Entity.forward */
+                    if (has_dst) idxF = ctr++;                 /* Entity.forward */
                     uint64_t idxPoll = 0; bool poll = (active < 1);
                     if (poll) idxPoll = ctr++;                 /* schedule_poll hook */
-                    if (M.dst_id >= 0) { HS_EMIT(dst_ev, idxF, M.dst_id); HS_SINK(c_created); }
+                    if (has_dst) { HS_EMIT(dst_ev, idxF, M.dst_id); HS_SINK(c_created); }
                     if (!poll) continue;
                     HS_EMIT(HS_EV_POLL, idxPoll, M.srv_id);
                     if (q_len == 0) continue;                  /* Queue._handle_poll: empty */
@@ -492,7 +500,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             }
         }
 
-        /* ===== generic single-event step (ties, run end, leftovers) ========= */
+        /* ===== generic single-event step (ties, run end, window end, leftovers) ========= */
+        if (!(now <= P.end_ns)) { finished = true; continue; }                 /* simulation.py:472 */
+        if (status & stop_bits) { finished = true; continue; }
+        if (now_n == 0 && tT == INT64_MAX && !has_c) { finished = true; continue; }   /* heap exhausted */
         if (processed >= P.max_events) { status |= HS_ST_EVENT_LIMIT; finished = true; continue; }
         {
             /* pop the (time, sort_index) minimum of T, C and nowq (event.py:337-344) */
@@ -518,7 +529,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             switch (kind) {
             case HS_EV_SOURCE_TICK: {
                 HS_EMIT(HS_EV_SOURCE_TICK, bi, M.src_id);
-                const bool payload = !(M.stop_after >= 0 && now > M.stop_after);
+                const bool payload = !(stop_after >= 0 && now > stop_after);
                 uint64_t idxP = 0;
                 if (payload) idxP = ctr++; else S->skipped++;
                 HS_NEXT_TICK();
@@ -566,7 +577,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 has_c = 0;
                 active = active > 0 ? active - 1 : 0;
                 total_service = HS_ADD(total_service, svc_s);
-                if (M.dst_id >= 0) { uint64_t i_ = ctr++; HS_PUSH_NOW(dst_ev, i_, c_created, 0); }
+                if (has_dst) { uint64_t i_ = ctr++; HS_PUSH_NOW(dst_ev, i_, c_created, 0); }
                 if (active < 1) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
                 break;
             }

@@ -159,7 +159,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     /* recorder staging: [slot][lane] so that lanes at different slots never conflict; full
      * 128-byte groups are written to HBM cooperatively at the converged top of the loop */
     __shared__ __align__(16) uint4 sh_rec[STAGE_ROWS][HS_LANE_THREADS];
-    __shared__ uint4 sh_flush[HS_LANE_THREADS / 32][4];          /* {tid, stage pos, ring pos, -} per source */
+    __shared__ uint4 sh_flush[HS_LANE_THREADS / 32][(FLAGS & HS_LF_REC) ? 32 : 1];   /* {tid, stage pos, ring pos, -} per flushing lane */
     __shared__ __align__(16) hs_ring_entry sh_head[HS_LANE_THREADS];  /* next item to deliver      */
     const uint32_t tid = threadIdx.x;
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,7 +204,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     /* ---- replica state (registers; nowq in local memory, cold) ---------- */
     int64_t now, processed, tT, tC, c_created;
     uint64_t ctr, hash, iT, iC, arr_draws;
-    int64_t accepted, dropped, n_svc;
+    int64_t dropped, n_svc;
     double svc_s, total_service, sum, comp, sumsq, mn, mx;
     uint32_t q_head, q_len, status, rec_pos, smp_pos, svc_pos;
     int32_t active, now_n, has_c;
@@ -227,7 +227,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         now = S->now; ctr = S->ctr; processed = S->processed; hash = S->hash;
         tT = S->tT; iT = S->iT; arr_draws = S->arr_draws;
         tC = S->tC; iC = S->iC; svc_s = S->svc_s; c_created = S->c_created;
-        n_svc = S->n_svc; accepted = S->accepted; dropped = S->dropped;
+        n_svc = S->n_svc; dropped = S->dropped;
         total_service = S->total_service;
         sum = S->sum; comp = S->comp; sumsq = S->sumsq; mn = S->mn; mx = S->mx;
         q_head = S->q_head; q_len = S->q_len; active = S->active; status = S->status;
@@ -239,7 +239,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         now = 0; processed = 0; hash = HS_HASH_INIT; ctr = 0;
         arr_draws = 0; n_svc = 0;
         tT = 0; iT = 0; tC = 0; iC = 0; svc_s = 0.0; c_created = 0;
-        accepted = dropped = 0;
+        dropped = 0;
         total_service = 0.0; sum = 0.0; comp = 0.0; sumsq = 0.0;
         mn = __longlong_as_double(0x7ff0000000000000LL); mx = __longlong_as_double(0xfff0000000000000LL);
         q_head = 0; q_len = 0; active = 0; status = 0; now_n = 0; has_c = 0;
@@ -407,25 +407,21 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         if (FLAGS & HS_LF_REC) {
             /* cooperative flush: every lane holding a full 128-byte group hands it to 8 lanes,
              * which write it as one contiguous line (4 groups per store instruction) */
-            bool want = staged && (st_wr - st_fl) >= HS_FLUSH;
-            unsigned fm = __ballot_sync(0xffffffffu, want);
-            while (fm) {
-                const uint32_t rank = __popc(fm & ((1u << lane) - 1u));
-                if (want && rank < 4) sh_flush[wib][rank] = make_uint4(tid, st_fl, rec_pos, 0u);
+            const bool want = staged && (st_wr - st_fl) >= HS_FLUSH;
+            const unsigned fm = __ballot_sync(0xffffffffu, want);
+            if (fm) {
+                const uint32_t n_want = (uint32_t)__popc(fm);
+                if (want) sh_flush[wib][__popc(fm & ((1u << lane) - 1u))] = make_uint4(tid, st_fl, rec_pos, 0u);
                 __syncwarp();
-                const uint32_t g = lane >> 3, c = lane & 7u;
-                if (g < (uint32_t)__popc(fm)) {
+                const uint32_t c = lane & 7u;
+                for (uint32_t g = lane >> 3; g < n_want; g += 4) {      /* 4 groups = 512 B per store instruction */
                     const uint4 f = sh_flush[wib][g];
                     const uint4 w = sh_rec[(f.y + c) % HS_STAGE][f.x];
                     hs_event_record *dst = O.records + ((size_t)(blockIdx.x * blockDim.x + f.x)) * P.record_cap + f.z + c;
                     __stcs((uint4 *)dst, w);
                 }
                 __syncwarp();
-                if (want && rank < 4) {
-                    st_fl += HS_FLUSH; rec_pos = (rec_pos + HS_FLUSH == P.record_cap) ? 0u : rec_pos + HS_FLUSH;
-                    want = (st_wr - st_fl) >= HS_FLUSH;
-                }
-                fm = __ballot_sync(0xffffffffu, want);
+                if (want) { st_fl += HS_FLUSH; rec_pos = (rec_pos + HS_FLUSH == P.record_cap) ? 0u : rec_pos + HS_FLUSH; }
             }
         }
         if (finished) continue;
@@ -456,7 +452,6 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     const bool was_empty = (q_len == 0);
                     if (cap >= 0 && (int64_t)q_len >= cap) { dropped++; continue; }
                     if (q_len >= P.ring) { status |= HS_ST_QUEUE_OVERFLOW; continue; }
-                    accepted++;
                     if (!was_empty || active >= 1) {
                         /* request waits in the buffer */
                         HS_Q_PUSH(now, idxP);
@@ -542,7 +537,6 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 if (cap >= 0 && (int64_t)q_len >= cap) { dropped++; break; }
                 if (q_len >= P.ring) { status |= HS_ST_QUEUE_OVERFLOW; break; }
                 HS_Q_PUSH(e_created, bi);
-                accepted++;
                 if (was_empty) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_NOTIFY, i_, 0, 0); }
                 break;
             }
@@ -609,7 +603,11 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     const int64_t completed = n_svc - active;
     const int64_t rejected = S->rejected;
     int64_t received = (M.dst_id >= 0) ? completed : 0;
-    for (int i = 0; i < now_n; ++i) if (nowq[i].kind == dst_ev) received--;
+    int64_t pending_enq = 0;
+    for (int i = 0; i < now_n; ++i) { if (nowq[i].kind == dst_ev) received--; if (nowq[i].kind == HS_EV_REQ_ENQUEUE) pending_enq++; }
+    /* every payload's ENQUEUE is either accepted, dropped, still pending at this timestamp, or the one
+     * that found the device ring full (the replica stops right there) */
+    const int64_t accepted = (gen_count - skipped) - pending_enq - dropped - ((status & HS_ST_QUEUE_OVERFLOW) ? 1 : 0);
     S->now = now; S->ctr = ctr; S->processed = processed; S->hash = hash;
     S->tT = tT; S->iT = iT; S->arr_draws = arr_draws; S->gen_count = gen_count; S->prov_count = gen_count - skipped;
     S->tC = tC; S->iC = iC; S->svc_s = svc_s; S->c_created = c_created;

@@ -82,12 +82,16 @@ class SinkSample(C.Structure):
 class Outputs(C.Structure):
     _fields_ = [("summaries", C.POINTER(ReplicaSummary)), ("entity_stats", C.POINTER(EntityStats)),
                 ("records", C.POINTER(EventRecord)), ("sink_samples", C.POINTER(SinkSample)),
-                ("service_samples", C.POINTER(C.c_double))]
+                ("service_samples", C.POINTER(C.c_double)), ("histograms", C.POINTER(C.c_uint32))]
 
 
 class Totals(C.Structure):
     _fields_ = [("i", C.c_int64 * HS_TOTALS_I64), ("fsum", C.c_double * HS_TOTALS_F64_SUM),
                 ("fmin", C.c_double), ("fmax", C.c_double)]
+
+
+class CellTotals(C.Structure):
+    _fields_ = [("totals", Totals), ("histogram", C.c_uint64 * 64)]
 
 
 assert C.sizeof(EntityDesc) == 48
@@ -97,6 +101,8 @@ assert C.sizeof(EventRecord) == 16
 assert C.sizeof(SinkSample) == 16
 assert C.sizeof(RunParams) == 88
 HS_RUN_ORDER_HASH = 1
+HS_RUN_HISTOGRAM = 2
+HS_HISTOGRAM_BINS = 64
 
 # numpy views of the same layouts (host buffers are numpy structured arrays)
 import numpy as _np
@@ -124,3 +130,12 @@ def unroll_ring(buf, count: int, cap: int):
         return buf[:count]
     h = count % cap
     return _np.concatenate([buf[h:cap], buf[:h]])
+
+
+def histogram_bin_edges_ns():
+    """Lower edges (ns) of the 64 latency bins of hs_latency_bin (bin 0 starts at 0)."""
+    edges = [0]
+    for b in range(1, 64):
+        e, m = 10 + (b - 1) // 2, (b - 1) % 2
+        edges.append((1 << e) + m * (1 << (e - 1)))
+    return _np.array(edges, dtype=_np.int64)

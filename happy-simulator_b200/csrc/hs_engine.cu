@@ -22,7 +22,7 @@
 #include "hs_totals.cuh"
 
 struct hs_engine;
-static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec);
+static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec, bool want_hist);
 
 static thread_local char g_err[512] = "";
 
@@ -81,6 +81,7 @@ struct hs_engine {
     hs_run_params last;
     int last_engine = 0;
     uint32_t last_ring = 0;
+    dev_buf d_hist, d_cell_totals; bool hist_on = false;
     dev_buf d_trace_arr, d_trace_svc; uint64_t n_trace_arr = 0, n_trace_svc = 0; uint32_t trace_replicas = 0;
     dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals, d_srv_index, d_counter;
 };
@@ -203,7 +204,7 @@ static bool classify_lane(hs_engine *E)
 
 /* ---- warp engine launch ------------------------------------------------- */
 
-static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec)
+static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec, bool want_hist)
 {
     const uint32_t n = p->n_replicas;
     const uint32_t ne = (uint32_t)E->ents.size();
@@ -269,6 +270,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     O.records = p->record_cap ? (hs_event_record *)E->d_rec.p : nullptr;
     O.samples = p->sample_cap ? (hs_sink_sample *)E->d_smp.p : nullptr;
     O.service = p->service_cap ? (double *)E->d_svc.p : nullptr;
+    O.hist = want_hist ? (uint32_t *)E->d_hist.p : nullptr;
 
     auto launch = [&](auto kern) -> int {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -332,7 +334,7 @@ int hs_engine_destroy(hs_engine *E)
     cudaStreamSynchronize(E->stream);
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
                        &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
-                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles};
+                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_hist, &E->d_cell_totals};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
@@ -425,6 +427,13 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         if (p->service_cap) CUDA_TRY(cudaMemsetAsync(E->d_svc.p, 0, (size_t)n * p->service_cap * sizeof(double), E->stream));
     }
 
+    const bool want_hist = (p->flags & HS_RUN_HISTOGRAM) != 0;
+    if (p->resume && want_hist != E->hist_on) return fail(HS_ERR_STATE, "resume must keep HS_RUN_HISTOGRAM");
+    if (want_hist) {
+        if ((rc = E->d_hist.ensure((size_t)n * HS_HISTOGRAM_BINS * sizeof(uint32_t)))) return rc;
+        if (!p->resume) CUDA_TRY(cudaMemsetAsync(E->d_hist.p, 0, (size_t)n * HS_HISTOGRAM_BINS * sizeof(uint32_t), E->stream));
+    }
+    E->hist_on = want_hist;
     const bool want_hash = (p->flags & HS_RUN_ORDER_HASH) != 0;
     const bool want_rec = (p->record_cap | p->sample_cap | p->service_cap) != 0;
 
@@ -450,6 +459,7 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         O.records = p->record_cap ? (hs_event_record *)E->d_rec.p : nullptr;
         O.samples = p->sample_cap ? (hs_sink_sample *)E->d_smp.p : nullptr;
         O.service = p->service_cap ? (double *)E->d_svc.p : nullptr;
+        O.hist = want_hist ? (uint32_t *)E->d_hist.p : nullptr;
         const int threads = HS_LANE_THREADS;
         const int blocks = (int)((n + threads - 1) / threads);
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
@@ -472,7 +482,7 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
         E->launches += 1;
     } else {
-        rc = hs_warp_launch(E, p, ring, want_hash, want_rec);
+        rc = hs_warp_launch(E, p, ring, want_hash, want_rec, want_hist);
         if (rc) return rc;
     }
     E->last = *p;
@@ -539,6 +549,7 @@ int hs_read_outputs(hs_engine *E, const hs_outputs *out)
     if (out->entity_stats) CUDA_TRY(cudaMemcpyAsync(out->entity_stats, E->d_stats.p, n * ne * sizeof(hs_entity_stats), cudaMemcpyDeviceToHost, E->stream));
     if (out->records && p.record_cap) CUDA_TRY(cudaMemcpyAsync(out->records, E->d_rec.p, n * p.record_cap * sizeof(hs_event_record), cudaMemcpyDeviceToHost, E->stream));
     if (out->sink_samples && p.sample_cap) CUDA_TRY(cudaMemcpyAsync(out->sink_samples, E->d_smp.p, n * p.sample_cap * sizeof(hs_sink_sample), cudaMemcpyDeviceToHost, E->stream));
+    if (out->histograms && E->hist_on) CUDA_TRY(cudaMemcpyAsync(out->histograms, E->d_hist.p, n * HS_HISTOGRAM_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, E->stream));
     if (out->service_samples && p.service_cap) CUDA_TRY(cudaMemcpyAsync(out->service_samples, E->d_svc.p, n * p.service_cap * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
     CUDA_TRY(cudaStreamSynchronize(E->stream));
     return HS_OK;
@@ -569,6 +580,25 @@ int hs_read_totals(hs_engine *E, hs_totals *out)
     int rc = compute_totals(E);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, E->d_totals.p, sizeof(hs_totals), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    return HS_OK;
+}
+
+int hs_read_cell_totals(hs_engine *E, hs_cell_totals *out, uint32_t n_cells)
+{
+    if (!E || !out || n_cells == 0) return fail(HS_ERR_INVALID, "bad argument");
+    if (!E->have_run) return fail(HS_ERR_STATE, "no run yet");
+    CUDA_TRY(cudaSetDevice(E->device));
+    const hs_run_params &p = E->last;
+    int rc;
+    if ((rc = E->d_cell_totals.ensure((size_t)n_cells * sizeof(hs_cell_totals)))) return rc;
+    hs_cell_totals_kernel<<<n_cells, 128, 0, E->stream>>>(
+        (const hs_replica_summary *)E->d_summ.p, (const hs_entity_stats *)E->d_stats.p, (const hs_entity_desc *)E->d_ents.p,
+        E->hist_on ? (const uint32_t *)E->d_hist.p : nullptr, p.n_replicas, (uint32_t)E->ents.size(),
+        p.replica_index_base, p.replicas_per_cell, n_cells, (hs_cell_totals *)E->d_cell_totals.p);
+    CUDA_TRY(cudaGetLastError());
+    E->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(out, E->d_cell_totals.p, (size_t)n_cells * sizeof(hs_cell_totals), cudaMemcpyDeviceToHost, E->stream));
     CUDA_TRY(cudaStreamSynchronize(E->stream));
     return HS_OK;
 }

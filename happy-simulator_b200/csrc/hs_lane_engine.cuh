@@ -130,6 +130,7 @@ struct hs_lane_out {
     hs_event_record *records;
     hs_sink_sample *samples;
     double *service;
+    uint32_t *hist;                   /* [replica][HS_HIST_BINS] or NULL */
 };
 
 /* next arrival of a constant-rate profile, with the reference's "time travel" outcome
@@ -200,6 +201,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     hs_event_record *rec = (FLAGS & HS_LF_REC) && O.records ? O.records + (size_t)r * P.record_cap : nullptr;
     hs_sink_sample *smp = (FLAGS & HS_LF_REC) && O.samples ? O.samples + (size_t)r * P.sample_cap : nullptr;
     double *svc_out = (FLAGS & HS_LF_REC) && O.service ? O.service + (size_t)r * P.service_cap : nullptr;
+    uint32_t *hist = O.hist ? O.hist + (size_t)r * HS_HIST_BINS : nullptr;
 
     /* ---- replica state (registers; nowq in local memory, cold) ---------- */
     int64_t now, processed, tT, tC, c_created;
@@ -341,6 +343,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     do {                                                                                     \
         if (dst_is_sink) {                                                                   \
             const double lat_ = hs_ns_to_seconds(now - (CREATED));                           \
+            if (hist) atomicAdd(hist + hs_latency_bin(now - (CREATED)), 1u);  /* RED: no return value, no stall */ \
             hs_neumaier_add(&sum, &comp, lat_); sumsq = HS_ADD(sumsq, HS_MUL(lat_, lat_));   \
             if (lat_ < mn) mn = lat_;                                                        \
             if (lat_ > mx) mx = lat_;                                                        \

@@ -231,6 +231,29 @@ HS_HD double hs_neumaier_result(double s, double c)
 }
 
 /* ------------------------------------------------------------------------ */
+/* Latency histogram (instrumentation reduced on the device: at ensemble scale the
+ * reference's per-request latency lists cannot be materialised).
+ * 64 log-spaced bins over the integer latency in ns, two bins per octave:
+ *   bin 0: lat < 1024 ns;  bin 1 + 2 (e - 10) + m: lat in [2^e (1 + m/2), 2^e (1 + (m+1)/2)),
+ *   e = floor(log2 lat) >= 10, m in {0, 1};  the last bin (63) also takes everything above.
+ * Pure integer arithmetic, hence identical on every party.                          */
+#define HS_HIST_BINS 64
+HS_HD uint32_t hs_latency_bin(int64_t lat_ns)
+{
+    if (lat_ns < 1024) return 0u;
+    uint64_t v = (uint64_t)lat_ns;
+    int e = 0;
+#if defined(__CUDA_ARCH__)
+    e = 63 - __clzll((long long)v);
+#else
+    e = 63 - __builtin_clzll(v);
+#endif
+    const uint32_t m = (uint32_t)((v >> (e - 1)) & 1u);
+    const uint32_t b = 1u + 2u * (uint32_t)(e - 10) + m;
+    return b > 63u ? 63u : b;
+}
+
+/* ------------------------------------------------------------------------ */
 /* Order hash over the processed-event sequence: FNV-1a style over the two
  * 64-bit words of the 16-byte event record (time_ns, idx | kind<<32 | ent<<40). */
 #define HS_HASH_INIT 0xcbf29ce484222325ULL

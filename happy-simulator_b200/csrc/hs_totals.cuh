@@ -85,4 +85,54 @@ __global__ void hs_totals_final_kernel(const hs_totals *__restrict__ partials, i
     }
 }
 
+
+/* Per-cell reduction (BASELINE configs[4]): block c folds the replicas whose global index maps to cell
+ * c (index / replicas_per_cell, modulo n_cells) in index order per thread, then a fixed tree. */
+__device__ __forceinline__ void hs_totals_accumulate(hs_totals &t, const hs_replica_summary &s,
+                                                     const hs_entity_stats *st, const hs_entity_desc *ents, uint32_t n_entities)
+{
+    t.i[0] += s.events_processed; t.i[5] += 1; t.i[6] += (s.status != 0); t.i[7] += s.final_time_ns / 1000;
+    for (uint32_t e = 0; e < n_entities; ++e) {
+        const int kind = ents[e].kind;
+        const hs_entity_stats x = st[e];
+        if (kind == HS_ENT_SINK) {
+            t.i[1] += x.c0; t.fsum[0] += x.f0; t.fsum[1] += x.f1;
+            t.fmin = x.f2 < t.fmin ? x.f2 : t.fmin; t.fmax = x.f3 > t.fmax ? x.f3 : t.fmax;
+        } else if (kind == HS_ENT_SERVER) { t.i[2] += x.c2; t.i[4] += x.c1; t.fsum[2] += x.f0; }
+        else if (kind == HS_ENT_SOURCE) t.i[3] += x.c0;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+hs_cell_totals_kernel(const hs_replica_summary *__restrict__ summ, const hs_entity_stats *__restrict__ stats,
+                      const hs_entity_desc *__restrict__ ents, const uint32_t *__restrict__ hist,
+                      uint32_t n_replicas, uint32_t n_entities, uint32_t index_base, uint32_t replicas_per_cell,
+                      uint32_t n_cells, hs_cell_totals *__restrict__ out)
+{
+    __shared__ hs_totals sh[4];
+    __shared__ unsigned long long shh[HS_HISTOGRAM_BINS];
+    const uint32_t c = blockIdx.x;
+    if (threadIdx.x < HS_HISTOGRAM_BINS) shh[threadIdx.x] = 0ull;
+    __syncthreads();
+    hs_totals t; hs_totals_zero(t);
+    for (uint32_t r = threadIdx.x; r < n_replicas; r += blockDim.x) {
+        const uint32_t cell = ((index_base + r) / replicas_per_cell) % n_cells;
+        if (cell != c) continue;
+        hs_totals_accumulate(t, summ[r], stats + (size_t)r * n_entities, ents, n_entities);
+        if (hist) for (int b = 0; b < HS_HISTOGRAM_BINS; ++b) {
+            const uint32_t v = hist[(size_t)r * HS_HISTOGRAM_BINS + b];
+            if (v) atomicAdd(&shh[b], (unsigned long long)v);       /* integer sums: order independent */
+        }
+    }
+    for (int d = 16; d >= 1; d >>= 1) { hs_totals o = hs_totals_shfl_down(t, d); hs_totals_merge(t, o); }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        hs_totals acc = sh[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) hs_totals_merge(acc, sh[w]);
+        out[c].totals = acc;
+    }
+    if (threadIdx.x < HS_HISTOGRAM_BINS) out[c].histogram[threadIdx.x] = shh[threadIdx.x];
+}
+
 #endif

@@ -93,6 +93,7 @@ struct hs_warp_out {
     hs_event_record *records;
     hs_sink_sample *samples;
     double *service;
+    uint32_t *hist;
 };
 
 /* ---- PTX helpers: mbarrier + TMA 1-D bulk copies ------------------------- */
@@ -475,6 +476,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                     case HS_EV_REQ_SINK: {             /* Sink.handle_event, common.py:36-44 */
                         X->u.snk.received++;
                         const double lat = hs_ns_to_seconds(now - e_created);
+                        if (O.hist) atomicAdd(O.hist + (size_t)r * HS_HIST_BINS + hs_latency_bin(now - e_created), 1u);
                         hs_neumaier_add(&X->u.snk.sum, &X->u.snk.comp, lat);
                         X->u.snk.sumsq = HS_ADD(X->u.snk.sumsq, HS_MUL(lat, lat));
                         if (lat < X->u.snk.mn) X->u.snk.mn = lat;

@@ -73,3 +73,60 @@ def run_sharded(engine, model, params_fn, n_total: int, rank: int, world: int, g
     engine.run(params_fn(hi - lo, lo))
     out = engine.read_outputs()
     return out, allreduce_totals(engine.read_totals(), group=group)
+
+
+def cell_totals_from_outputs(model, out, n_cells: int, replicas_per_cell: int, index_base: int = 0):
+    """numpy restatement of hs_cell_totals_kernel: [(Totals, uint64[64])] per cell."""
+    n = len(out["summaries"])
+    cells = ((index_base + np.arange(n)) // replicas_per_cell) % n_cells
+    res = []
+    for c in range(n_cells):
+        sel = cells == c
+        sub = {"summaries": out["summaries"][sel], "entity_stats": out["entity_stats"][sel]}
+        t = totals_from_outputs(model, sub) if sel.any() else A.Totals()
+        if not sel.any():
+            t.fmin, t.fmax = float("inf"), float("-inf")
+        h = out["histograms"][sel].sum(axis=0, dtype=np.uint64) if out.get("histograms") is not None else np.zeros(64, np.uint64)
+        res.append((t, h))
+    return res
+
+
+def allreduce_cell_totals(cells, device=None, group=None):
+    """One collective for a sweep: every cell's totals vector and histogram, stacked (configs[4])."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return cells
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    ks = ["events_processed", "sink_events", "server_completions", "source_ticks", "dropped", "replicas",
+          "replicas_flagged", "sum_final_time_us"]
+    fs = ["sum_latency", "sum_latency_sq", "sum_service"]
+    vi = torch.tensor([[d[k] for k in ks] + [int(x) for x in h] for d, h in cells], dtype=torch.int64, device=dev)
+    vf = torch.tensor([[d[k] for k in fs] for d, _ in cells], dtype=torch.float64, device=dev)
+    vmin = torch.tensor([d["min_latency"] for d, _ in cells], dtype=torch.float64, device=dev)
+    vmax = torch.tensor([d["max_latency"] for d, _ in cells], dtype=torch.float64, device=dev)
+    dist.all_reduce(vi, group=group); dist.all_reduce(vf, group=group)
+    dist.all_reduce(vmin, op=dist.ReduceOp.MIN, group=group); dist.all_reduce(vmax, op=dist.ReduceOp.MAX, group=group)
+    out = []
+    for c in range(len(cells)):
+        d = {k: int(vi[c, j]) for j, k in enumerate(ks)}
+        d.update({k: float(vf[c, j]) for j, k in enumerate(fs)})
+        d["min_latency"], d["max_latency"] = float(vmin[c]), float(vmax[c])
+        out.append((d, vi[c, len(ks):].cpu().numpy().astype(np.uint64)))
+    return out
+
+
+def histogram_percentile(hist, p: float) -> float:
+    """Latency (seconds) below which a fraction p of the histogram's samples fall; linear inside a bin."""
+    hist = np.asarray(hist, dtype=np.float64)
+    total = hist.sum()
+    if total == 0:
+        return 0.0
+    edges = A.histogram_bin_edges_ns().astype(np.float64)
+    upper = np.append(edges[1:], edges[-1] * 1.5)
+    cum = np.cumsum(hist)
+    k = int(np.searchsorted(cum, p * total, side="left"))
+    k = min(k, 63)
+    below = cum[k - 1] if k > 0 else 0.0
+    frac = (p * total - below) / hist[k] if hist[k] > 0 else 0.0
+    return float(edges[k] + frac * (upper[k] - edges[k])) / 1e9

@@ -27,7 +27,7 @@ _lib = None
 
 EXPORTED_SYMBOLS = ["hs_version", "hs_last_error", "hs_engine_create", "hs_engine_destroy", "hs_model_upload",
                     "hs_model_validate", "hs_run", "hs_set_trace", "hs_sync", "hs_last_run_ms", "hs_launch_count",
-                    "hs_read_outputs", "hs_read_totals", "hs_totals_device_ptr"]
+                    "hs_read_outputs", "hs_read_totals", "hs_read_cell_totals", "hs_totals_device_ptr"]
 
 
 def load_library(path: str | None = None):
@@ -54,6 +54,7 @@ def load_library(path: str | None = None):
         "hs_launch_count": ([H, C.POINTER(C.c_uint64)], C.c_int),
         "hs_read_outputs": ([H, C.POINTER(A.Outputs)], C.c_int),
         "hs_read_totals": ([H, C.POINTER(A.Totals)], C.c_int),
+        "hs_read_cell_totals": ([H, C.POINTER(A.CellTotals), C.c_uint32], C.c_int),
         "hs_totals_device_ptr": ([H, C.POINTER(C.c_void_p)], C.c_int),
     }
     for name, (args, res) in sigs.items():
@@ -171,6 +172,7 @@ class Engine:
             "records": mk((n, p.record_cap), A.RECORD_DTYPE) if p.record_cap else None,
             "sink_samples": mk((n, p.sample_cap), A.SAMPLE_DTYPE) if p.sample_cap else None,
             "service_samples": mk((n, p.service_cap), np.float64) if p.service_cap else None,
+            "histograms": mk((n, A.HS_HISTOGRAM_BINS), np.uint32) if (p.flags & A.HS_RUN_HISTOGRAM) else None,
         }
         bufs["_keep"] = keep
         return bufs
@@ -187,6 +189,8 @@ class Engine:
             o.sink_samples = bufs["sink_samples"].ctypes.data_as(C.POINTER(A.SinkSample))
         if bufs.get("service_samples") is not None:
             o.service_samples = bufs["service_samples"].ctypes.data_as(C.POINTER(C.c_double))
+        if bufs.get("histograms") is not None:
+            o.histograms = bufs["histograms"].ctypes.data_as(C.POINTER(C.c_uint32))
         _check(self._L, self._L.hs_read_outputs(self._h, C.byref(o)))
         return bufs
 
@@ -194,6 +198,12 @@ class Engine:
         t = A.Totals()
         _check(self._L, self._L.hs_read_totals(self._h, C.byref(t)))
         return t
+
+    def read_cell_totals(self, n_cells: int):
+        """Per-cell aggregates of the last run: list of (totals dict, uint64[64] histogram)."""
+        arr = (A.CellTotals * n_cells)()
+        _check(self._L, self._L.hs_read_cell_totals(self._h, arr, n_cells))
+        return [(totals_to_dict(c.totals), np.array(list(c.histogram), dtype=np.uint64)) for c in arr]
 
     def totals_device_ptr(self) -> int:
         p = C.c_void_p()

@@ -155,6 +155,8 @@ typedef struct hs_run_params {
 } hs_run_params;
 
 #define HS_RUN_ORDER_HASH 1u   /* maintain hs_replica_summary.order_hash (off: hash = 0)  */
+#define HS_RUN_HISTOGRAM 2u    /* per-replica 64-bin latency histogram of all Sink events  */
+#define HS_HISTOGRAM_BINS 64   /* log-spaced over integer ns, see hs_latency_bin()         */
 
 /* Replica status bits. */
 #define HS_ST_QUEUE_OVERFLOW 1u   /* a server's device queue ring filled up  */
@@ -206,6 +208,7 @@ typedef struct hs_outputs {        /* caller-owned HOST buffers; any pointer may
     hs_event_record *records;      /* [n_replicas][record_cap] ring, slot = event number % cap */
     hs_sink_sample *sink_samples;  /* [n_replicas][sample_cap], all sinks, arrival order       */
     double *service_samples;       /* [n_replicas][service_cap], service-start order           */
+    uint32_t *histograms;          /* [n_replicas][HS_HISTOGRAM_BINS] (HS_RUN_HISTOGRAM)        */
 } hs_outputs;
 
 /* Ensemble totals: what the single end-of-run NCCL allreduce carries.
@@ -221,6 +224,14 @@ typedef struct hs_totals {
     double fmin;               /* min sink latency */
     double fmax;               /* max sink latency */
 } hs_totals;
+
+/* Per-cell aggregates of a parameter sweep (BASELINE configs[4]: the vector that is all-reduced
+ * per (c, rho) cell): the ensemble totals restricted to the replicas of one cell, plus the cell's
+ * latency histogram (sum over its replicas; zeros unless HS_RUN_HISTOGRAM was set). */
+typedef struct hs_cell_totals {
+    hs_totals totals;
+    uint64_t histogram[HS_HISTOGRAM_BINS];
+} hs_cell_totals;
 
 /* ---- entry points ------------------------------------------------------ */
 
@@ -282,6 +293,10 @@ int hs_read_outputs(hs_engine *e, const hs_outputs *out);
 /* Reduce the last run's per-replica results on the device and copy the totals
  * (SimulationSummary-level aggregates) to the host (synchronises). */
 int hs_read_totals(hs_engine *e, hs_totals *out);
+
+/* Reduce the last run's replicas per sweep cell (cell = global replica index /
+ * replicas_per_cell, modulo n_cells) on the device and copy out[0..n_cells) to the host. */
+int hs_read_cell_totals(hs_engine *e, hs_cell_totals *out, uint32_t n_cells);
 
 /* Device pointer/size of the last run's totals (for the NCCL allreduce done by
  * the host layer on torch.distributed; layout = hs_totals). */

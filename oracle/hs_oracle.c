@@ -157,6 +157,7 @@ typedef struct orun {
     /* outputs of this replica */
     hs_event_record *rec;
     hs_sink_sample *smp; int64_t n_smp;
+    uint32_t *hist;
     double *svc; int64_t n_svc;
 } orun;
 
@@ -382,6 +383,7 @@ static void handle(orun *R, oev *e)
     case HS_EV_REQ_SINK: {                /* Sink.handle_event, common.py:36-44   */
         E->received++;
         double lat = hs_ns_to_seconds(R->now - e->created_at);
+        if (R->hist) R->hist[hs_latency_bin(R->now - e->created_at)]++;
         hs_neumaier_add(&E->sum, &E->comp, lat); E->sumsq += lat * lat;
         if (lat < E->mn) E->mn = lat;
         if (lat > E->mx) E->mx = lat;
@@ -456,6 +458,10 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
     if (out->records) R.rec = out->records + (size_t)r * p->record_cap;
     if (out->sink_samples) R.smp = out->sink_samples + (size_t)r * p->sample_cap;
     if (out->service_samples) R.svc = out->service_samples + (size_t)r * p->service_cap;
+    if (out->histograms && (p->flags & HS_RUN_HISTOGRAM)) {
+        R.hist = out->histograms + (size_t)r * HS_HISTOGRAM_BINS;
+        memset(R.hist, 0, HS_HISTOGRAM_BINS * sizeof(uint32_t));
+    }
 
     /* Simulation.__init__: reset_event_counter(); source.start() for each source
      * in order; the SourceEvent takes its index from the GLOBAL counter
@@ -569,6 +575,7 @@ int64_t hs_cpu_seconds_to_ns(double s) { return hs_seconds_to_ns(s); }
 double hs_cpu_ns_to_seconds(int64_t ns) { return hs_ns_to_seconds(ns); }
 int64_t hs_cpu_next_arrival_ns(int64_t cur, double target, double rate) { return hs_next_arrival_ns(cur, target, rate); }
 int64_t hs_cpu_exp_latency_ns(double u, double lambda) { return hs_exp_latency_ns(u, lambda); }
+uint32_t hs_cpu_latency_bin(int64_t lat_ns) { return hs_latency_bin(lat_ns); }
 uint64_t hs_cpu_hash_step(uint64_t h, int64_t t, uint64_t idx, uint32_t kind, uint32_t ent)
 { return hs_hash_step(h, t, hs_record_word1(idx, kind, ent)); }
 int64_t hs_cpu_next_arrival_profile_ns(int32_t kind, double p0, double p1, double p2, double p3, int64_t cur, double target)

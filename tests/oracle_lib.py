@@ -38,6 +38,7 @@ def lib():
         L.hs_cpu_next_arrival_ns.argtypes = [C.c_int64, C.c_double, C.c_double]
         L.hs_cpu_next_arrival_ns.restype = C.c_int64
         L.hs_cpu_exp_latency_ns.argtypes = [C.c_double, C.c_double]; L.hs_cpu_exp_latency_ns.restype = C.c_int64
+        L.hs_cpu_latency_bin.argtypes = [C.c_int64]; L.hs_cpu_latency_bin.restype = C.c_uint32
         L.hs_cpu_hash_step.argtypes = [C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.hs_cpu_hash_step.restype = C.c_uint64
         L.hs_cpu_next_arrival_profile_ns.argtypes = [C.c_int32] + [C.c_double] * 4 + [C.c_int64, C.c_double]
@@ -74,6 +75,7 @@ def alloc_outputs(n_entities: int, p: A.RunParams):
         "records": np.zeros((n, p.record_cap), A.RECORD_DTYPE) if p.record_cap else None,
         "sink_samples": np.zeros((n, p.sample_cap), A.SAMPLE_DTYPE) if p.sample_cap else None,
         "service_samples": np.zeros((n, p.service_cap), np.float64) if p.service_cap else None,
+        "histograms": np.zeros((n, A.HS_HISTOGRAM_BINS), np.uint32) if (p.flags & A.HS_RUN_HISTOGRAM) else None,
     }
     o = A.Outputs()
     o.summaries = bufs["summaries"].ctypes.data_as(C.POINTER(A.ReplicaSummary))
@@ -84,6 +86,8 @@ def alloc_outputs(n_entities: int, p: A.RunParams):
         o.sink_samples = bufs["sink_samples"].ctypes.data_as(C.POINTER(A.SinkSample))
     if p.service_cap:
         o.service_samples = bufs["service_samples"].ctypes.data_as(C.POINTER(C.c_double))
+    if bufs["histograms"] is not None:
+        o.histograms = bufs["histograms"].ctypes.data_as(C.POINTER(C.c_uint32))
     return bufs, o
 
 

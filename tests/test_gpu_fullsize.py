@@ -130,3 +130,39 @@ def test_config4_mmc_sweep_cells(eng):
     w = O.oracle_run(model, O.make_params(seed=11, end_ns=200 * 10**9, n_replicas=1, replicas_per_cell=per_cell,
                                           replica_index_base=5 * per_cell + 3))
     assert out["summaries"][5 * per_cell + 3].tobytes() == w["summaries"][0].tobytes()
+
+
+def test_latency_histograms_and_cell_totals(eng):
+    """Device-side instrumentation for ensembles: per-replica 64-bin latency histograms (bit-exact vs the
+    oracle on both engines) and the per-cell reduction that a sweep all-reduces (configs[4])."""
+    model = hs.mmc_sweep(cs=(1, 3), rhos=(0.6, 0.9))
+    per_cell, n = 50, 4 * 50
+    kw = dict(seed=21, n_replicas=n, replicas_per_cell=per_cell, end_ns=100 * 10**9,
+              flags=A.HS_RUN_ORDER_HASH | A.HS_RUN_HISTOGRAM)
+    eng.upload(model)
+    eng.run(engine.make_params(**kw))
+    out = eng.read_outputs()
+    want = O.oracle_run(model, O.make_params(**kw))
+    assert out["histograms"].tobytes() == want["histograms"].tobytes()
+    assert (out["histograms"].sum(axis=1) == out["entity_stats"][:, 2]["c0"]).all()
+    cells = eng.read_cell_totals(4)
+    ref = D.cell_totals_from_outputs(model, out, 4, per_cell)
+    for (d, h), (t, hh) in zip(cells, ref):
+        assert d["events_processed"] == t.i[0] and d["replicas"] == per_cell and d["sink_events"] == t.i[1]
+        assert d["min_latency"] == t.fmin and d["max_latency"] == t.fmax
+        assert np.allclose([d["sum_latency"], d["sum_latency_sq"], d["sum_service"]], list(t.fsum), rtol=1e-12)
+        assert np.array_equal(h, hh)
+    # the histogram is good enough for ensemble percentiles: compare with exact samples of one cell
+    eng.run(engine.make_params(sample_cap=20000, **kw))
+    smp = eng.read_outputs()
+    lat = np.concatenate([A.unroll_ring(smp["sink_samples"][r], smp["summaries"]["n_sink_samples"][r], 20000)["latency_s"]
+                          for r in range(per_cell)])
+    for p in (0.5, 0.9, 0.99):
+        est, exact = D.histogram_percentile(cells[0][1], p), float(np.quantile(lat, p))
+        assert abs(est - exact) / exact < 0.25, (p, est, exact)
+    # lane engine too
+    m1 = hs.mm1()
+    eng.upload(m1)
+    k2 = dict(seed=3, n_replicas=96, end_ns=100 * 10**9, flags=A.HS_RUN_HISTOGRAM)
+    eng.run(engine.make_params(**k2))
+    assert eng.read_outputs()["histograms"].tobytes() == O.oracle_run(m1, O.make_params(**k2))["histograms"].tobytes()

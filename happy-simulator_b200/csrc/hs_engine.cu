@@ -81,7 +81,7 @@ struct hs_engine {
     hs_run_params last;
     int last_engine = 0;
     uint32_t last_ring = 0;
-    dev_buf d_hist, d_cell_totals; bool hist_on = false;
+    dev_buf d_conts, d_hist, d_cell_totals; bool hist_on = false;
     dev_buf d_trace_arr, d_trace_svc; uint64_t n_trace_arr = 0, n_trace_svc = 0; uint32_t trace_replicas = 0;
     dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals, d_srv_index, d_counter;
 };
@@ -185,9 +185,11 @@ static bool classify_lane(hs_engine *E)
     }
     if (src < 0 || srv < 0) return false;
     if (en[src].target != srv || en[src].i1 != 0) return false;
-    if (en[srv].i0 != 1) return false;
+    if (en[srv].i0 > 64) return false;
     if (en[srv].target != dst) { if (!(en[srv].target < 0 && dst < 0)) return false; }
-    for (uint32_t c = 0; c < E->n_cells; ++c) if (E->cell_i0[(size_t)c * n + srv] != 1) return false;
+    int32_t c_max = en[srv].i0;
+    for (uint32_t c = 0; c < E->n_cells; ++c) c_max = std::max(c_max, E->cell_i0[(size_t)c * n + srv]);
+    if (c_max > 64) return false;
     hs_lane_model &L = E->lane_model;
     memset(&L, 0, sizeof L);
     L.src_id = src; L.srv_id = srv; L.dst_id = en[srv].target;
@@ -195,6 +197,8 @@ static bool classify_lane(hs_engine *E)
     L.arr_kind = en[src].i0; L.svc_kind = en[srv].i2; L.policy = en[srv].i1; L.n_entities = (int32_t)n;
     L.capacity = en[srv].l0; L.stop_after = en[src].l0;
     L.rate = en[src].d0; L.mean = en[srv].d0;
+    L.concurrency = en[srv].i0; L.c_max = c_max;
+    L.cell_i0 = (const int32_t *)E->d_cell_i0.p;
     L.has_profile = en[src].i3 > 0;
     if (L.has_profile) L.prof = E->profiles[en[src].i3 - 1];
     L.n_cells = E->n_cells;
@@ -281,10 +285,19 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
         CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
         return 0;
     };
-    if (want_rec && want_hash) rc = launch(hs_warp_kernel<HS_WF_HASH | HS_WF_REC>);
-    else if (want_rec) rc = launch(hs_warp_kernel<HS_WF_REC>);
-    else if (want_hash) rc = launch(hs_warp_kernel<HS_WF_HASH>);
-    else rc = launch(hs_warp_kernel<0>);
+    bool any_profile = false;
+    for (const hs_entity_desc &e : E->ents) if (e.kind == HS_ENT_SOURCE && e.i3 > 0) any_profile = true;
+    const int fl = (want_hash ? HS_WF_HASH : 0) | (want_rec ? HS_WF_REC : 0) | (any_profile ? HS_WF_PROFILE : 0);
+    switch (fl) {
+    case 0: rc = launch(hs_warp_kernel<0>); break;
+    case 1: rc = launch(hs_warp_kernel<1>); break;
+    case 2: rc = launch(hs_warp_kernel<2>); break;
+    case 3: rc = launch(hs_warp_kernel<3>); break;
+    case 4: rc = launch(hs_warp_kernel<4>); break;
+    case 5: rc = launch(hs_warp_kernel<5>); break;
+    case 6: rc = launch(hs_warp_kernel<6>); break;
+    default: rc = launch(hs_warp_kernel<7>); break;
+    }
     if (rc) return rc;
     E->launches += 1;
     return HS_OK;
@@ -334,7 +347,7 @@ int hs_engine_destroy(hs_engine *E)
     cudaStreamSynchronize(E->stream);
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
                        &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
-                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_hist, &E->d_cell_totals};
+                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_hist, &E->d_cell_totals, &E->d_conts};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
@@ -397,7 +410,7 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         return fail(HS_ERR_INVALID, "hs_set_trace supplied draws for %u replicas, run asks for %u", E->trace_replicas, p->n_replicas);
     int engine = (int)p->engine;
     if (engine == 0) engine = E->lane_ok ? 2 : 1;
-    if (engine == 2 && !E->lane_ok) return fail(HS_ERR_INVALID, "lane engine needs Source -> Server(concurrency 1) -> Sink|Counter");
+    if (engine == 2 && !E->lane_ok) return fail(HS_ERR_INVALID, "lane engine needs Source -> Server(concurrency <= 64) -> Sink|Counter");
     if (engine != 1 && engine != 2) return fail(HS_ERR_INVALID, "unknown engine %d", engine);
 
     if (p->resume) {
@@ -445,6 +458,8 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         if ((rc = E->d_rings.ensure((size_t)n * ring * sizeof(hs_ring_entry)))) return rc;
         hs_lane_model M = E->lane_model;
         M.cell_d0 = (const double *)E->d_cell_d0.p;
+        M.cell_i0 = (const int32_t *)E->d_cell_i0.p;
+        if ((rc = E->d_conts.ensure(std::max<size_t>(64, (size_t)n * M.c_max * sizeof(hs_cont))))) return rc;
         hs_lane_run R;
         R.seed = p->seed; R.seed_stride = p->seed_stride; R.rid_base = p->rid_base; R.rid_stride = p->rid_stride;
         R.end_ns = p->end_ns; R.window_end_ns = p->window_end_ns;
@@ -467,10 +482,10 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         hs_ring_entry *rg = (hs_ring_entry *)E->d_rings.p;
         const bool simple = !M.has_profile && !R.trace_arr && !R.trace_svc && M.arr_kind == HS_ARR_POISSON &&
                             M.svc_kind == HS_SVC_EXPONENTIAL && M.policy == HS_Q_FIFO && M.capacity < 0 &&
-                            M.stop_after < 0 && M.dst_id >= 0 && M.dst_kind == HS_ENT_SINK;
+                            M.stop_after < 0 && M.dst_id >= 0 && M.dst_kind == HS_ENT_SINK && M.c_max == 1;
         const int fl = (want_hash ? HS_LF_HASH : 0) | (want_rec ? HS_LF_REC : 0) |
                        (M.has_profile ? HS_LF_PROFILE : 0) | (simple ? HS_LF_SIMPLE : 0);
-#define HS_LAUNCH_LANE(F) case F: hs_lane_kernel<F><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, O); break;
+#define HS_LAUNCH_LANE(F) case F: hs_lane_kernel<F><<<blocks, threads, 0, E->stream>>>(M, R, st, rg, (hs_cont *)E->d_conts.p, O); break;
         switch (fl) {
         HS_LAUNCH_LANE(0) HS_LAUNCH_LANE(1) HS_LAUNCH_LANE(2) HS_LAUNCH_LANE(3)
         HS_LAUNCH_LANE(4) HS_LAUNCH_LANE(5) HS_LAUNCH_LANE(6) HS_LAUNCH_LANE(7)

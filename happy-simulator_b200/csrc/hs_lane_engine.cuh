@@ -1,6 +1,7 @@
 /* hs_lane_engine.cuh -- "lane engine": one THREAD per replica for the
- * single-server topology  Source -> Server(concurrency 1) -> Sink|Counter|nothing
- * (BASELINE.json configs[0] and configs[1], the headline M/M/1 ensemble).
+ * single-server topology  Source -> Server(concurrency c) -> Sink|Counter|nothing
+ * (BASELINE.json configs[0], configs[1] -- the headline M/M/1 ensemble -- and the M/M/c
+ * sweep of configs[4]).
  *
  * Why a lane and not a warp per replica: the whole future-event list of this
  * topology is {next SourceEvent, at most one ProcessContinuation, a handful of
@@ -12,7 +13,8 @@
  * Exactness.  The loop below is the reference's pop-invoke-push loop
  * (happysimulator/core/simulation.py:449-505) with the future-event list held as
  *   T   the pending SourceEvent                     (time tT, sort index iT)
- *   C   the pending ProcessContinuation, if any     (time tC, sort index iC)
+ *   C   the pending ProcessContinuations (<= c): the earliest in registers
+ *       (time tC, sort index iC), the others in a small per-lane binary heap in HBM
  *   nowq  events created at the current timestamp   (sort index, kind, payload)
  * Two execution paths produce the SAME processed-event sequence:
  *   - generic_step(): pops the (time, sort_index)-minimum of T, C and nowq and
@@ -84,6 +86,13 @@ struct hs_now_ev {        /* an event created at the current timestamp       */
     int32_t pad;
 };
 
+struct hs_cont {          /* a pending ProcessContinuation (service in progress)  */
+    int64_t t;            /* resume time                                      */
+    uint64_t idx;         /* its _sort_index                                  */
+    int64_t created;      /* context["created_at"] of the request served      */
+    double svc_s;         /* the service time the generator yielded           */
+};
+
 struct hs_ring_entry {    /* one queued request (FIFOQueue/LIFOQueue item)   */
     int64_t created;      /* context["created_at"]                           */
     uint64_t idx;         /* the queued Event's _sort_index                  */
@@ -110,6 +119,8 @@ struct hs_lane_model {
     uint32_t n_cells, pad;
     const double *cell_d0;            /* device pointers or NULL                */
     hs_profile_desc prof;             /* the Source's rate profile                */
+    const int32_t *cell_i0;           /* per-cell concurrency override or NULL    */
+    int32_t concurrency, c_max;       /* FixedConcurrency limit; heap stride      */
     int32_t has_profile, pad2;        /* 0: ConstantRateProfile fast path         */
 };
 
@@ -151,7 +162,7 @@ __device__ __forceinline__ int64_t hs_lane_next_arrival(int64_t t, double target
 template <int FLAGS>
 __global__ void __launch_bounds__(HS_LANE_THREADS, 7)
 hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ states,
-               hs_ring_entry *__restrict__ rings, hs_lane_out O)
+               hs_ring_entry *__restrict__ rings, hs_cont *__restrict__ conts, hs_lane_out O)
 {
     constexpr uint32_t HS_DRAW_BUF = (FLAGS & HS_LF_REC) ? HS_DRAW_BUF_RECORD : HS_DRAW_BUF_SUMMARY;
     constexpr uint32_t STAGE_ROWS = (FLAGS & HS_LF_REC) ? HS_STAGE : 1;
@@ -174,10 +185,12 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     const uint32_t sid_svc = HS_STREAM_SERVICE | ((uint32_t)M.srv_id << 8);
 
     double rate = M.rate, mean = M.mean;
+    int32_t c_rt = M.concurrency;
     if (M.n_cells) {
         uint32_t cell = (gidx / P.replicas_per_cell) % M.n_cells;
         rate = M.cell_d0[(size_t)cell * M.n_entities + M.src_id];
         mean = M.cell_d0[(size_t)cell * M.n_entities + M.srv_id];
+        c_rt = M.cell_i0[(size_t)cell * M.n_entities + M.srv_id];
     }
     const double lambda = HS_DIV(1.0, mean);             /* exponential.py:36 */
     hs_profile_desc prof_local;
@@ -189,6 +202,8 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     const bool lifo = SIMPLE ? false : (M.policy == HS_Q_LIFO);
     const int64_t cap = SIMPLE ? -1 : M.capacity;
     const int64_t stop_after = SIMPLE ? -1 : M.stop_after;
+    const int32_t c_limit = SIMPLE ? 1 : c_rt;           /* FixedConcurrency._max_concurrent */
+    hs_cont *heap = conts + (size_t)r * (uint32_t)M.c_max;   /* continuations beyond the earliest one */
     const bool dst_is_sink = SIMPLE ? true : (M.dst_kind == HS_ENT_SINK);
     const bool has_dst = SIMPLE ? true : (M.dst_id >= 0);
     const double *trace_arr = SIMPLE ? nullptr : P.trace_arr;
@@ -209,7 +224,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     int64_t dropped, n_svc;
     double svc_s, total_service, sum, comp, sumsq, mn, mx;
     uint32_t q_head, q_len, status, rec_pos, smp_pos, svc_pos;
-    int32_t active, now_n, has_c;
+    int32_t active, now_n;
     /* The item the next POLL delivers lives in this lane's 16-byte shared-memory slot
      * sh_head[tid].  After a pop the new head is fetched from the ring with cp.async
      * (LDGSTS: global -> shared, no destination register), i.e. a whole service time before
@@ -233,7 +248,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         total_service = S->total_service;
         sum = S->sum; comp = S->comp; sumsq = S->sumsq; mn = S->mn; mx = S->mx;
         q_head = S->q_head; q_len = S->q_len; active = S->active; status = S->status;
-        now_n = S->now_n; has_c = S->has_c;
+        now_n = S->now_n;
         rec_pos = S->rec_pos; smp_pos = S->smp_pos; svc_pos = S->svc_pos;
         for (int i = 0; i < HS_NOW_CAP; ++i) nowq[i] = S->nowq[i];
         if (q_len > 0) *my_head = ring[(lifo ? q_head + q_len - 1 : q_head) & ring_mask];
@@ -244,7 +259,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         dropped = 0;
         total_service = 0.0; sum = 0.0; comp = 0.0; sumsq = 0.0;
         mn = __longlong_as_double(0x7ff0000000000000LL); mx = __longlong_as_double(0xfff0000000000000LL);
-        q_head = 0; q_len = 0; active = 0; status = 0; now_n = 0; has_c = 0;
+        q_head = 0; q_len = 0; active = 0; status = 0; now_n = 0;
         rec_pos = 0; smp_pos = 0; svc_pos = 0;
         if (valid) { S->rejected = 0; S->skipped = 0; }   /* cold counters, kept in the state block */
         for (int i = 0; i < HS_NOW_CAP; ++i) { nowq[i].idx = 0; nowq[i].created = 0; nowq[i].payload_idx = 0; nowq[i].kind = 0; nowq[i].pad = 0; }
@@ -326,17 +341,16 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
 
     /* Server.handle_queued_event up to its yield, for the payload (CREATED):
      * inline ProcessContinuation index, acquire (the caller has checked
-     * active < 1), sample, schedule resume
+     * active < c_limit), sample, schedule resume
      * (server.py:217-253, event.py:314-325,499-508).                            */
 #define HS_SERVICE_START(CREATED)                                                            \
     do {                                                                                     \
         const uint32_t k_ = (uint32_t)((uint64_t)n_svc % HS_DRAW_BUF);                       \
-        svc_s = sh_svc[k_][tid];                                                             \
-        const int64_t delta_ = hs_seconds_to_ns(svc_s);   /* event.py:499, temporal.py:221 */ \
-        if ((FLAGS & HS_LF_REC) && svc_out) { __stcs(svc_out + svc_pos, svc_s); svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
+        const int64_t delta_ = hs_seconds_to_ns(sh_svc[k_][tid]);   /* event.py:499, temporal.py:221 */ \
+        if ((FLAGS & HS_LF_REC) && svc_out) { __stcs(svc_out + svc_pos, sh_svc[k_][tid]); svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
         n_svc++;                                                                             \
-        active++;                                                                            \
-        tC = now + delta_; iC = ctr + 1; ctr += 2; c_created = (CREATED); has_c = 1;         \
+        { const double sv_ = sh_svc[k_][tid]; const uint64_t i_ = ctr + 1; ctr += 2;         \
+          HS_C_PUSH(now + delta_, i_, (CREATED), sv_); }                                     \
     } while (0)
 
 #define HS_SINK(CREATED)                                                                     \
@@ -376,6 +390,41 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             const hs_ring_entry *n_ = ring + ((lifo ? q_head + q_len - 1 : q_head) & ring_mask); \
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" \
                          :: "r"(my_head_s), "l"(n_) : "memory");                             \
+        }                                                                                    \
+    } while (0)
+
+    /* The set of pending continuations: the minimum (time, sort_index) lives in the registers
+     * tC/iC/c_created/svc_s, the other (active - 1) in a binary min-heap in HBM. */
+#define HS_CLT(T1, I1, T2, I2) ((T1) < (T2) || ((T1) == (T2) && (I1) < (I2)))
+#define HS_C_PUSH(T, I, CR, SV)                                                              \
+    do {                                                                                     \
+        if (active == 0) { tC = (T); iC = (I); c_created = (CR); svc_s = (SV); }             \
+        else {                                                                               \
+            hs_cont n_;                                                                      \
+            if (HS_CLT((T), (I), tC, iC)) { n_.t = tC; n_.idx = iC; n_.created = c_created; n_.svc_s = svc_s; \
+                                            tC = (T); iC = (I); c_created = (CR); svc_s = (SV); } \
+            else { n_.t = (T); n_.idx = (I); n_.created = (CR); n_.svc_s = (SV); }           \
+            int k_ = active - 1;                       /* sift up */                         \
+            while (k_ > 0) { const int p_ = (k_ - 1) >> 1; const hs_cont q_ = heap[p_];      \
+                             if (!HS_CLT(n_.t, n_.idx, q_.t, q_.idx)) break; heap[k_] = q_; k_ = p_; } \
+            heap[k_] = n_;                                                                   \
+        }                                                                                    \
+        active++;                                                                            \
+    } while (0)
+    /* remove the earliest continuation (the registers) and promote the heap's minimum */
+#define HS_C_POP()                                                                           \
+    do {                                                                                     \
+        active = active > 0 ? active - 1 : 0;          /* FixedConcurrency.release */        \
+        if (active > 0) {                                                                    \
+            const hs_cont top_ = heap[0];                                                    \
+            tC = top_.t; iC = top_.idx; c_created = top_.created; svc_s = top_.svc_s;        \
+            const int n2_ = active - 1;                /* elements left in the heap */       \
+            if (n2_ > 0) { const hs_cont last_ = heap[n2_]; int k_ = 0;                      \
+                while (true) { int ch_ = 2 * k_ + 1; if (ch_ >= n2_) break;                  \
+                    hs_cont a_ = heap[ch_];                                                  \
+                    if (ch_ + 1 < n2_) { const hs_cont b_ = heap[ch_ + 1]; if (HS_CLT(b_.t, b_.idx, a_.t, a_.idx)) { a_ = b_; ch_++; } } \
+                    if (!HS_CLT(a_.t, a_.idx, last_.t, last_.idx)) break; heap[k_] = a_; k_ = ch_; } \
+                heap[k_] = last_; }                                                          \
         }                                                                                    \
     } while (0)
 
@@ -430,11 +479,11 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         if (finished) continue;
 
         if (now_n == 0) {
-            const bool pickC = has_c && (tC < tT || (tC == tT && iC < iT));
+            const bool pickC = active > 0 && (tC < tT || (tC == tT && iC < iT));
             const int64_t tn = pickC ? tC : tT;
             /* fast path <=> the chosen event is not tied, lies inside both the run and the window
              * (so `now <= end` holds before and after), and nothing exceptional is pending */
-            const bool slow = (has_c && tC == tT) || (tn > fast_limit) || (tn < now) || (status & stop_bits) ||
+            const bool slow = (active > 0 && tC == tT) || (tn > fast_limit) || (tn < now) || (status & stop_bits) ||
                               (processed + 8 > P.max_events);   /* a chain is <= 6 events: single-step near the limit */
             if (!slow) {
                 now = tn;
@@ -455,7 +504,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     const bool was_empty = (q_len == 0);
                     if (cap >= 0 && (int64_t)q_len >= cap) { dropped++; continue; }
                     if (q_len >= P.ring) { status |= HS_ST_QUEUE_OVERFLOW; continue; }
-                    if (!was_empty || active >= 1) {
+                    if (!was_empty || active >= c_limit) {
                         /* request waits in the buffer */
                         HS_Q_PUSH(now, idxP);
                         if (was_empty) {      /* notify, but the worker is busy: no poll (queue_driver.py:92-96) */
@@ -476,14 +525,21 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 } else {
                     /* ===== fused completion chain =============================== */
                     HS_EMIT(HS_EV_CONTINUATION, iC, M.srv_id);
-                    has_c = 0;
-                    active = active > 0 ? active - 1 : 0;      /* FixedConcurrency.release */
                     total_service = HS_ADD(total_service, svc_s);
+                    const int64_t done_created = c_created;
+                    HS_C_POP();                                /* release + promote the next continuation */
                     uint64_t idxF = 0;
                     if (has_dst) idxF = ctr++;                 /* Entity.forward */
-                    uint64_t idxPoll = 0; bool poll = (active < 1);
+                    uint64_t idxPoll = 0; bool poll = (active < c_limit);
                     if (poll) idxPoll = ctr++;                 /* schedule_poll hook */
-                    if (has_dst) { HS_EMIT(dst_ev, idxF, M.dst_id); HS_SINK(c_created); }
+                    if (active > 0 && tC == now) {
+                        /* another continuation resumes at this very nanosecond: its (older) index sorts
+                         * before the events just created, so hand them to the generic path */
+                        if (has_dst) HS_PUSH_NOW(dst_ev, idxF, done_created, 0);
+                        if (poll) HS_PUSH_NOW(HS_EV_POLL, idxPoll, 0, 0);
+                        continue;
+                    }
+                    if (has_dst) { HS_EMIT(dst_ev, idxF, M.dst_id); HS_SINK(done_created); }
                     if (!poll) continue;
                     HS_EMIT(HS_EV_POLL, idxPoll, M.srv_id);
                     if (q_len == 0) continue;                  /* Queue._handle_poll: empty */
@@ -501,13 +557,13 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         /* ===== generic single-event step (ties, run end, window end, leftovers) ========= */
         if (!(now <= P.end_ns)) { finished = true; continue; }                 /* simulation.py:472 */
         if (status & stop_bits) { finished = true; continue; }
-        if (now_n == 0 && tT == INT64_MAX && !has_c) { finished = true; continue; }   /* heap exhausted */
+        if (now_n == 0 && tT == INT64_MAX && active == 0) { finished = true; continue; }   /* heap exhausted */
         if (processed >= P.max_events) { status |= HS_ST_EVENT_LIMIT; finished = true; continue; }
         {
             /* pop the (time, sort_index) minimum of T, C and nowq (event.py:337-344) */
             int which = -1;                 /* -1 T, -2 C, >=0 nowq slot */
             int64_t bt = tT; uint64_t bi = iT;
-            if (has_c && (tC < bt || (tC == bt && iC < bi))) { which = -2; bt = tC; bi = iC; }
+            if (active > 0 && (tC < bt || (tC == bt && iC < bi))) { which = -2; bt = tC; bi = iC; }
             for (int i = 0; i < now_n; ++i) {
                 if (now < bt || (now == bt && nowq[i].idx < bi)) { which = i; bt = now; bi = nowq[i].idx; }
             }
@@ -545,7 +601,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             }
             case HS_EV_NOTIFY:
                 HS_EMIT(HS_EV_NOTIFY, bi, M.srv_id);
-                if (active < 1) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
+                if (active < c_limit) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
                 break;
             case HS_EV_POLL:
                 HS_EMIT(HS_EV_POLL, bi, M.srv_id);
@@ -562,20 +618,20 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 break;
             case HS_EV_REQ_WORKER:
                 HS_EMIT(HS_EV_REQ_WORKER, bi, M.srv_id);
-                if (active >= 1) {          /* acquire failed (server.py:223-234): hooks still run */
+                if (active >= c_limit) {    /* acquire failed (server.py:223-234): hooks still run */
                     ctr++; S->rejected++; status |= HS_ST_REJECT_PATH;
-                    if (active < 1) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
+                    if (active < c_limit) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
                 } else {
                     HS_SERVICE_START(e_created);
                 }
                 break;
             case HS_EV_CONTINUATION: {
                 HS_EMIT(HS_EV_CONTINUATION, bi, M.srv_id);
-                has_c = 0;
-                active = active > 0 ? active - 1 : 0;
                 total_service = HS_ADD(total_service, svc_s);
-                if (has_dst) { uint64_t i_ = ctr++; HS_PUSH_NOW(dst_ev, i_, c_created, 0); }
-                if (active < 1) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
+                const int64_t done_created = c_created;
+                HS_C_POP();
+                if (has_dst) { uint64_t i_ = ctr++; HS_PUSH_NOW(dst_ev, i_, done_created, 0); }
+                if (active < c_limit) { uint64_t i_ = ctr++; HS_PUSH_NOW(HS_EV_POLL, i_, 0, 0); }
                 break;
             }
             case HS_EV_REQ_SINK:
@@ -618,7 +674,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     S->total_service = total_service;
     S->received = received; S->sum = sum; S->comp = comp; S->sumsq = sumsq; S->mn = mn; S->mx = mx;
     S->q_head = q_head; S->q_len = q_len; S->active = active; S->status = status;
-    S->n_smp = received; S->n_svc = n_svc; S->now_n = now_n; S->has_c = has_c;
+    S->n_smp = received; S->n_svc = n_svc; S->now_n = now_n; S->has_c = active > 0;
     S->rec_pos = rec_pos; S->smp_pos = smp_pos; S->svc_pos = svc_pos;
     S->done = paused ? 0 : 1;
     for (int i = 0; i < HS_NOW_CAP; ++i) S->nowq[i] = nowq[i];
@@ -628,7 +684,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         s.events_processed = processed; s.final_time_ns = now;
         s.order_hash = (FLAGS & HS_LF_HASH) ? hash : 0ULL;
         s.next_sort_index = ctr; s.n_sink_samples = (M.dst_kind == HS_ENT_SINK) ? received : 0; s.n_service_samples = n_svc;
-        s.heap_left = (tT != INT64_MAX) + has_c + now_n; s.status = status;
+        s.heap_left = (tT != INT64_MAX) + active + now_n; s.status = status;
         O.summaries[r] = s;
     }
     if (O.stats) {
@@ -654,6 +710,9 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
 #undef HS_Q_PUSH
 #undef HS_Q_POP
 #undef HS_PUSH_NOW
+#undef HS_C_PUSH
+#undef HS_C_POP
+#undef HS_CLT
 }
 
 #endif /* HS_LANE_ENGINE_CUH */

@@ -34,6 +34,7 @@
 
 #define HS_WF_HASH 1
 #define HS_WF_REC 2
+#define HS_WF_PROFILE 4    /* some Source has a non-constant rate profile (Simpson + Brent calls) */
 
 struct __align__(16) hs_warp_hdr {      /* 128 B */
     int64_t now; uint64_t ctr; int64_t processed; uint64_t hash;
@@ -235,8 +236,9 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         target = hs_exp1(u);
                     }
                     const int32_t pi = M.ents[i].i3;
-                    const int64_t first = pi > 0 ? hs_next_arrival_profile_ns(&M.profiles[pi - 1], 0, target)
-                                                 : hs_next_arrival_ns(0, target, e->d0);
+                    int64_t first;
+                    if ((FLAGS & HS_WF_PROFILE) && pi > 0) first = hs_next_arrival_profile_ns(&M.profiles[pi - 1], 0, target);
+                    else first = hs_next_arrival_ns(0, target, e->d0);
                     if (first == HS_T_EXHAUSTED) continue;      /* source.start(): RuntimeError, no tick */
                     e->u.src.cur_ns = first;
                     if (H->free_top == 0) { H->status |= HS_ST_FEL_OVERFLOW; break; }
@@ -382,8 +384,9 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                             const double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), X->u.src.arr_draws++);
                             target = hs_exp1(u);
                         }
-                        const int64_t nt = d.i3 > 0 ? hs_next_arrival_profile_ns(&M.profiles[d.i3 - 1], X->u.src.cur_ns, target)
-                                                    : hs_next_arrival_ns(X->u.src.cur_ns, target, X->d0);
+                        int64_t nt;
+                        if ((FLAGS & HS_WF_PROFILE) && d.i3 > 0) nt = hs_next_arrival_profile_ns(&M.profiles[d.i3 - 1], X->u.src.cur_ns, target);
+                        else nt = hs_next_arrival_ns(X->u.src.cur_ns, target, X->d0);
                         if (have) HS_W_PUSH(now, idxP, HS_W_REQ_KIND(d.target), d.target, now, 0ull, key, 0u);
                         if (nt != HS_T_EXHAUSTED) {          /* else "Source exhausted", source.py:176-180 */
                             X->u.src.cur_ns = nt;

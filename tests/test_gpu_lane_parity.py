@@ -55,6 +55,10 @@ CASES = {
     "mm1_capacity0": (dict(rate=5, mean_service_s=0.1, capacity=0), 20),
     "mm1_lifo": (dict(rate=9, mean_service_s=0.1, lifo=True), 60),
     "overload": (dict(rate=20, mean_service_s=0.1), 10),
+    "mmc4": (dict(rate=32, concurrency=4), 30),
+    "mmc32_lifo_bounded": (dict(rate=300, concurrency=32, lifo=True, capacity=6), 8),
+    "mmc3_constant_service": (dict(rate=25, concurrency=3, exponential=False, mean_service_s=0.1), 20),
+    "mmc64": (dict(rate=500, concurrency=64), 4),
     # inter-arrivals of a few ns: many SourceEvents tie with their own chain (generic path)
     "zero_gap_poisson": (dict(rate=3e8, mean_service_s=2e-9), 2e-5),
 }

@@ -233,11 +233,13 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     const uint32_t block_bytes = (uint32_t)(sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + (((size_t)S * 46 + 15) / 16) * 16 +
                                             (size_t)HS_W_NCAP * sizeof(hs_wnow));
     const uint32_t per_warp = 16 + block_bytes;
+    uint32_t model_bytes = (uint32_t)((ne * sizeof(hs_entity_desc) + ne * 4 + E->backends.size() * 4 + 15) / 16 * 16);
+    if (per_warp + model_bytes > 227 * 1024 - 1024) model_bytes = 0;      /* tables stay in global memory */
     const uint32_t smem_budget = 200 * 1024;
-    if (per_warp > 227 * 1024 - 1024) return fail(HS_ERR_INVALID, "model too large for the warp engine (%u B of state per replica)", per_warp);
+    if (per_warp + model_bytes > 227 * 1024 - 1024) return fail(HS_ERR_INVALID, "model too large for the warp engine (%u B of state per replica)", per_warp);
     uint32_t warps = std::min<uint32_t>(8, std::max<uint32_t>(1, (smem_budget / 2) / per_warp));
-    if (per_warp * warps > 227 * 1024 - 1024) warps = 1;
-    const uint32_t smem = per_warp * warps;
+    while (warps > 1 && per_warp * warps + model_bytes > 227 * 1024 - 1024) warps--;
+    const uint32_t smem = per_warp * warps + model_bytes;
     uint32_t blocks_per_sm = std::max<uint32_t>(1, std::min<uint32_t>((227 * 1024) / (smem + 1024), 64 / warps));
     if (blocks_per_sm * warps * 32 > 2048) blocks_per_sm = 2048 / (warps * 32);
     uint32_t grid = std::min<uint32_t>((n + warps - 1) / warps, (uint32_t)E->sm_count * blocks_per_sm);
@@ -260,6 +262,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     M.cell_d0 = (const double *)E->d_cell_d0.p; M.cell_i0 = (const int32_t *)E->d_cell_i0.p;
     M.profiles = (const hs_profile_desc *)E->d_profiles.p;
     M.n_entities = ne; M.n_cells = E->n_cells; M.n_servers = n_servers; M.fel_slots = S; M.block_bytes = block_bytes;
+    M.n_backends = (uint32_t)E->backends.size(); M.model_bytes = model_bytes;
     hs_warp_run R;
     R.seed = p->seed; R.seed_stride = p->seed_stride; R.rid_base = p->rid_base; R.rid_stride = p->rid_stride;
     R.end_ns = p->end_ns; R.window_end_ns = p->window_end_ns;

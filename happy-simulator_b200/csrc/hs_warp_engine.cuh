@@ -75,6 +75,7 @@ struct hs_warp_model {
     const hs_profile_desc *profiles;
     uint32_t n_entities, n_cells, n_servers, fel_slots;   /* fel_slots = S, multiple of 32 */
     uint32_t block_bytes;           /* bytes of one replica block (multiple of 16)          */
+    uint32_t n_backends, model_bytes; /* shared-memory copy of the model tables (per CTA)     */
 };
 
 struct hs_warp_run {
@@ -157,7 +158,22 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
     const uint32_t S = M.fel_slots;
     const uint32_t ne = M.n_entities;
     const uint32_t per_warp = 16u + M.block_bytes;          /* mbarrier slot + block */
-    unsigned char *base = smem_raw + (size_t)warp * per_warp;
+    /* The model tables are read on every event by lane 0 in a dependent chain: keep one copy per CTA in
+     * shared memory (entity rows, server ring index, load-balancer backend lists) instead of going to L2. */
+    const hs_entity_desc *ENTS = M.ents;                    /* models too large for the copy stay in HBM/L2 */
+    const int32_t *SRVIDX = M.srv_index, *BACKENDS = M.backends;
+    if (M.model_bytes) {
+        hs_entity_desc *es = (hs_entity_desc *)smem_raw;
+        int32_t *si = (int32_t *)(smem_raw + (size_t)ne * sizeof(hs_entity_desc));
+        int32_t *bs = si + ne;
+        for (uint32_t i = threadIdx.x; i < ne * (uint32_t)(sizeof(hs_entity_desc) / 4); i += blockDim.x)
+            ((uint32_t *)es)[i] = ((const uint32_t *)M.ents)[i];
+        for (uint32_t i = threadIdx.x; i < ne; i += blockDim.x) si[i] = M.srv_index[i];
+        for (uint32_t i = threadIdx.x; i < M.n_backends; i += blockDim.x) bs[i] = M.backends[i];
+        __syncthreads();
+        ENTS = es; SRVIDX = si; BACKENDS = bs;
+    }
+    unsigned char *base = smem_raw + M.model_bytes + (size_t)warp * per_warp;
     uint64_t *mbar = (uint64_t *)base;
     unsigned char *blk = base + 16;
     hs_warp_hdr *H = (hs_warp_hdr *)blk;
@@ -207,7 +223,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
             for (uint32_t i = lane; i < S; i += 32) { f_time[i] = HS_W_EMPTY; f_free[i] = (uint16_t)(S - 1 - i); }
             const uint32_t cell = M.n_cells ? (gidx / P.replicas_per_cell) % M.n_cells : 0u;
             for (uint32_t i = lane; i < ne; i += 32) {
-                const hs_entity_desc d = M.ents[i];
+                const hs_entity_desc d = ENTS[i];
                 hs_went *e = &E[i];
                 e->d0 = M.n_cells ? M.cell_d0[(size_t)cell * ne + i] : d.d0;
                 e->i0 = M.n_cells ? M.cell_i0[(size_t)cell * ne + i] : d.i0;
@@ -225,7 +241,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                  * global counter (simulation.py:77,145-154), run() restarts the per-heap one at 0. */
                 uint64_t boot = 0; int nf = 0;
                 for (uint32_t i = 0; i < ne; ++i) {
-                    if (M.ents[i].kind != HS_ENT_SOURCE) continue;
+                    if (ENTS[i].kind != HS_ENT_SOURCE) continue;
                     hs_went *e = &E[i];
                     double target = 1.0;
                     if (e->i0 == HS_ARR_POISSON && P.trace_arr) {
@@ -235,7 +251,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (i << 8), e->u.src.arr_draws++);
                         target = hs_exp1(u);
                     }
-                    const int32_t pi = M.ents[i].i3;
+                    const int32_t pi = ENTS[i].i3;
                     int64_t first;
                     if ((FLAGS & HS_WF_PROFILE) && pi > 0) first = hs_next_arrival_profile_ns(&M.profiles[pi - 1], 0, target);
                     else first = hs_next_arrival_ns(0, target, e->d0);
@@ -344,10 +360,10 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
             if (fs == HS_W_NONE || t_ < ft || (t_ == ft && (i2_ < fi || (i2_ == fi && s_ < fs)))) { ft = t_; fi = i2_; fs = s_; } \
         }                                                                                                \
     } while (0)
-#define HS_W_REQ_KIND(TGT) (M.ents[(TGT)].kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE :                   \
-                            M.ents[(TGT)].kind == HS_ENT_SINK ? HS_EV_REQ_SINK :                         \
-                            M.ents[(TGT)].kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER :                   \
-                            M.ents[(TGT)].kind == HS_ENT_PROBE ? HS_EV_PROBE : HS_EV_REQ_LB)
+#define HS_W_REQ_KIND(TGT) (ENTS[(TGT)].kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE :                   \
+                            ENTS[(TGT)].kind == HS_ENT_SINK ? HS_EV_REQ_SINK :                         \
+                            ENTS[(TGT)].kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER :                   \
+                            ENTS[(TGT)].kind == HS_ENT_PROBE ? HS_EV_PROBE : HS_EV_REQ_LB)
                     /* Event._run_completion_hooks for a request whose plain handler returned:
                      * only the LoadBalancer on_complete hook can be attached (event.py:277-283). */
 #define HS_W_REQUEST_HOOKS()                                                                             \
@@ -364,7 +380,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
 
                     switch (kind) {
                     case HS_EV_SOURCE_TICK: {          /* Source.handle_event, source.py:142-180 */
-                        const hs_entity_desc d = M.ents[ent];
+                        const hs_entity_desc d = ENTS[ent];
                         bool have = false; uint64_t idxP = 0; int32_t key = -1;
                         if (!(d.l0 >= 0 && now > d.l0)) {
                             X->u.src.provider++;
@@ -396,13 +412,13 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         break;
                     }
                     case HS_EV_REQ_LB: {               /* LoadBalancer._forward_request, :347-433 */
-                        const hs_entity_desc d = M.ents[ent];
+                        const hs_entity_desc d = ENTS[ent];
                         X->u.lb.received++;
                         if (d.i2 > 0) {
                             int slot;
                             if (d.i0 == HS_LB_KEY_TABLE && e_key >= 0) slot = M.key_table[e_key];
                             else { slot = (int)(X->u.lb.rr_index % (uint64_t)d.i2); X->u.lb.rr_index++; }
-                            const int be = M.backends[d.i1 + slot];
+                            const int be = BACKENDS[d.i1 + slot];
                             X->u.lb.in_flight++; X->u.lb.forwarded++;
                             const uint64_t i_ = ctr++;
                             HS_W_PUSH(now, i_, HS_W_REQ_KIND(be), be, e_created, 0ull, e_key, ent + 1u);
@@ -411,12 +427,12 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         break;
                     }
                     case HS_EV_REQ_ENQUEUE: {          /* Queue._handle_enqueue, queue.py:122-147 */
-                        const hs_entity_desc d = M.ents[ent];
+                        const hs_entity_desc d = ENTS[ent];
                         const bool was_empty = (X->u.srv.q_len == 0);
                         if (d.l0 >= 0 && (int64_t)X->u.srv.q_len >= d.l0) X->u.srv.dropped++;
                         else if (X->u.srv.q_len >= P.ring) H->status |= HS_ST_QUEUE_OVERFLOW;
                         else {
-                            hs_wring_entry *rg = ring0 + (size_t)M.srv_index[ent] * P.ring;
+                            hs_wring_entry *rg = ring0 + (size_t)SRVIDX[ent] * P.ring;
                             hs_wring_entry q; q.created = e_created; q.idx = bi; q.key = e_key;
                             rg[(X->u.srv.q_head + X->u.srv.q_len) & ring_mask] = q;
                             X->u.srv.q_len++;
@@ -431,9 +447,9 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         break;
                     case HS_EV_POLL:                   /* Queue._handle_poll, queue.py:149-166 */
                         if (X->u.srv.q_len > 0) {
-                            hs_wring_entry *rg = ring0 + (size_t)M.srv_index[ent] * P.ring;
+                            hs_wring_entry *rg = ring0 + (size_t)SRVIDX[ent] * P.ring;
                             hs_wring_entry q;
-                            if (M.ents[ent].i1 == HS_Q_LIFO) q = rg[(X->u.srv.q_head + X->u.srv.q_len - 1) & ring_mask];
+                            if (ENTS[ent].i1 == HS_Q_LIFO) q = rg[(X->u.srv.q_head + X->u.srv.q_len - 1) & ring_mask];
                             else { q = rg[X->u.srv.q_head & ring_mask]; X->u.srv.q_head++; }
                             X->u.srv.q_len--;
                             const uint64_t i_ = ctr++;
@@ -452,10 +468,10 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         }
                         X->u.srv.active++;
                         int64_t dur;
-                        if (M.ents[ent].i2 == HS_SVC_EXPONENTIAL && P.trace_svc) {
+                        if (ENTS[ent].i2 == HS_SVC_EXPONENTIAL && P.trace_svc) {
                             if (H->py_cursor >= P.n_trace_svc) { H->status |= HS_ST_TRACE_EXHAUSTED; H->py_cursor = 0; }
                             dur = hs_seconds_to_ns(HS_DIV(P.trace_svc[(size_t)r * P.n_trace_svc + H->py_cursor++], X->lambda)); X->u.srv.svc_draws++;
-                        } else if (M.ents[ent].i2 == HS_SVC_EXPONENTIAL) {
+                        } else if (ENTS[ent].i2 == HS_SVC_EXPONENTIAL) {
                             const double u = hs_uniform(seed, rid, HS_STREAM_SERVICE | (ent << 8), X->u.srv.svc_draws++);
                             dur = hs_exp_latency_ns(u, X->lambda);
                         } else dur = hs_seconds_to_ns(X->d0);
@@ -471,7 +487,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         X->u.srv.active = X->u.srv.active > 0 ? X->u.srv.active - 1 : 0;
                         X->u.srv.completed++;
                         X->u.srv.total_service = HS_ADD(X->u.srv.total_service, __longlong_as_double((long long)e_aux));
-                        const int tgt = M.ents[ent].target;
+                        const int tgt = ENTS[ent].target;
                         if (tgt >= 0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_W_REQ_KIND(tgt), tgt, e_created, 0ull, e_key, 0u); }
                         if (e_hook & 0x80000000u) HS_W_POLL_HOOK(ent);
                         break;
@@ -491,9 +507,9 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                         break;
                     }
                     case HS_EV_PROBE: {                /* measure_callback, instrumentation/probe.py:51-66 */
-                        const hs_entity_desc pd = M.ents[ent];
+                        const hs_entity_desc pd = ENTS[ent];
                         const hs_went *T = &E[pd.target];
-                        const int tk = M.ents[pd.target].kind;
+                        const int tk = ENTS[pd.target].kind;
                         double val = 0.0;
                         switch (pd.i0) {
                         case HS_METRIC_DEPTH: val = (double)T->u.srv.q_len; break;
@@ -567,7 +583,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
             for (uint32_t i = lane; i < ne; i += 32) {
                 const hs_went *e = &E[i];
                 hs_entity_stats a; a.c0 = a.c1 = a.c2 = a.c3 = 0; a.f0 = a.f1 = a.f2 = a.f3 = 0.0;
-                switch (M.ents[i].kind) {
+                switch (ENTS[i].kind) {
                 case HS_ENT_SOURCE: a.c0 = e->u.src.generated; a.c1 = e->u.src.provider; break;
                 case HS_ENT_SERVER: a.c0 = e->u.srv.accepted; a.c1 = e->u.srv.dropped; a.c2 = e->u.srv.completed;
                     a.c3 = e->u.srv.rejected; a.f0 = e->u.srv.total_service; break;

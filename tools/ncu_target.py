@@ -9,7 +9,10 @@ end_s = float(sys.argv[2]) if len(sys.argv) > 2 else 500.0
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
 caps = dict(record_cap=1024, sample_cap=128, service_cap=128) if mode == "record" else {}
 eng = engine.Engine(0)
-eng.upload(hs.mm1())
+model = hs.lb_round_robin(64, 512.0) if mode == "warp" else hs.mm1()
+if mode == "warp":
+    n = min(n, 4096)
+eng.upload(model)
 for i in range(3):
     eng.run(engine.make_params(seed=1234, end_ns=int(end_s * 1e9), n_replicas=n, flags=0, **caps))
     eng.sync()

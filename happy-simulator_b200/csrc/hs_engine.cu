@@ -19,10 +19,11 @@
 #include "../../include/hs_b200.h"
 #include "hs_lane_engine.cuh"
 #include "hs_warp_engine.cuh"
+#include "hs_thread_engine.cuh"
 #include "hs_totals.cuh"
 
 struct hs_engine;
-static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec, bool want_hist);
+static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec, bool want_hist, bool per_thread);
 
 static thread_local char g_err[512] = "";
 
@@ -208,7 +209,7 @@ static bool classify_lane(hs_engine *E)
 
 /* ---- warp engine launch ------------------------------------------------- */
 
-static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec, bool want_hist)
+static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec, bool want_hist, bool per_thread)
 {
     const uint32_t n = p->n_replicas;
     const uint32_t ne = (uint32_t)E->ents.size();
@@ -230,13 +231,16 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     }
     const uint32_t S = (uint32_t)((live + 31) / 32) * 32;
     if (S > 65535) return fail(HS_ERR_INVALID, "model needs %u future-event slots (limit 65535)", S);
-    const uint32_t block_bytes = (uint32_t)(sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + (((size_t)S * 46 + 15) / 16) * 16 +
-                                            (size_t)HS_W_NCAP * sizeof(hs_wnow));
+    /* thread engine: the future tier is a binary heap of whole entries instead of the SoA slot table */
+    const uint32_t block_bytes = per_thread
+        ? (uint32_t)(sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + ((size_t)S + HS_W_NCAP) * sizeof(hs_wnow))
+        : (uint32_t)(sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + (((size_t)S * 46 + 15) / 16) * 16 +
+                     (size_t)HS_W_NCAP * sizeof(hs_wnow));
     const uint32_t per_warp = 16 + block_bytes;
     uint32_t model_bytes = (uint32_t)((ne * sizeof(hs_entity_desc) + ne * 4 + E->backends.size() * 4 + 15) / 16 * 16);
     if (per_warp + model_bytes > 227 * 1024 - 1024) model_bytes = 0;      /* tables stay in global memory */
     const uint32_t smem_budget = 200 * 1024;
-    if (per_warp + model_bytes > 227 * 1024 - 1024) return fail(HS_ERR_INVALID, "model too large for the warp engine (%u B of state per replica)", per_warp);
+    if (!per_thread && per_warp + model_bytes > 227 * 1024 - 1024) return fail(HS_ERR_INVALID, "model too large for the warp engine (%u B of state per replica)", per_warp);
     uint32_t warps = std::min<uint32_t>(8, std::max<uint32_t>(1, (smem_budget / 2) / per_warp));
     while (warps > 1 && per_warp * warps + model_bytes > 227 * 1024 - 1024) warps--;
     const uint32_t smem = per_warp * warps + model_bytes;
@@ -291,6 +295,21 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     bool any_profile = false;
     for (const hs_entity_desc &e : E->ents) if (e.kind == HS_ENT_SOURCE && e.i3 > 0) any_profile = true;
     const int fl = (want_hash ? HS_WF_HASH : 0) | (want_rec ? HS_WF_REC : 0) | (any_profile ? HS_WF_PROFILE : 0);
+    if (per_thread) {
+        M.model_bytes = 0;
+        const int tblocks = (int)((n + HS_THREAD_BLOCK - 1) / HS_THREAD_BLOCK);
+        CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
+#define HS_LAUNCH_THREAD(F) case F: hs_thread_kernel<F><<<tblocks, HS_THREAD_BLOCK, 0, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;
+        switch (fl) {
+        HS_LAUNCH_THREAD(0) HS_LAUNCH_THREAD(1) HS_LAUNCH_THREAD(2) HS_LAUNCH_THREAD(3)
+        HS_LAUNCH_THREAD(4) HS_LAUNCH_THREAD(5) HS_LAUNCH_THREAD(6) HS_LAUNCH_THREAD(7)
+        }
+#undef HS_LAUNCH_THREAD
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
+        E->launches += 1;
+        return HS_OK;
+    }
     switch (fl) {
     case 0: rc = launch(hs_warp_kernel<0>); break;
     case 1: rc = launch(hs_warp_kernel<1>); break;
@@ -412,9 +431,9 @@ int hs_run(hs_engine *E, const hs_run_params *p)
     if ((E->n_trace_arr || E->n_trace_svc) && p->n_replicas > E->trace_replicas)
         return fail(HS_ERR_INVALID, "hs_set_trace supplied draws for %u replicas, run asks for %u", E->trace_replicas, p->n_replicas);
     int engine = (int)p->engine;
-    if (engine == 0) engine = E->lane_ok ? 2 : 1;
+    if (engine == 0) engine = E->lane_ok ? 2 : 3;
     if (engine == 2 && !E->lane_ok) return fail(HS_ERR_INVALID, "lane engine needs Source -> Server(concurrency <= 64) -> Sink|Counter");
-    if (engine != 1 && engine != 2) return fail(HS_ERR_INVALID, "unknown engine %d", engine);
+    if (engine < 1 || engine > 3) return fail(HS_ERR_INVALID, "unknown engine %d", engine);
 
     if (p->resume) {
         if (!E->have_run) return fail(HS_ERR_STATE, "resume without a previous run");
@@ -500,7 +519,7 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
         E->launches += 1;
     } else {
-        rc = hs_warp_launch(E, p, ring, want_hash, want_rec, want_hist);
+        rc = hs_warp_launch(E, p, ring, want_hash, want_rec, want_hist, engine == 3);
         if (rc) return rc;
     }
     E->last = *p;

@@ -360,191 +360,8 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
             if (fs == HS_W_NONE || t_ < ft || (t_ == ft && (i2_ < fi || (i2_ == fi && s_ < fs)))) { ft = t_; fi = i2_; fs = s_; } \
         }                                                                                                \
     } while (0)
-#define HS_W_REQ_KIND(TGT) (ENTS[(TGT)].kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE :                   \
-                            ENTS[(TGT)].kind == HS_ENT_SINK ? HS_EV_REQ_SINK :                         \
-                            ENTS[(TGT)].kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER :                   \
-                            ENTS[(TGT)].kind == HS_ENT_PROBE ? HS_EV_PROBE : HS_EV_REQ_LB)
-                    /* Event._run_completion_hooks for a request whose plain handler returned:
-                     * only the LoadBalancer on_complete hook can be attached (event.py:277-283). */
-#define HS_W_REQUEST_HOOKS()                                                                             \
-    do {                                                                                                 \
-        const uint32_t lbh_ = e_hook & 0x7fffffffu;                                                      \
-        if (lbh_) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_LB_RESPONSE, lbh_ - 1u, 0, 0ull, -1, 0u); } \
-    } while (0)
-                    /* QueueDriver schedule_poll hook (queue_driver.py:79-85) */
-#define HS_W_POLL_HOOK(SRV)                                                                              \
-    do {                                                                                                 \
-        if (E[(SRV)].u.srv.active < E[(SRV)].i0) { const uint64_t i_ = ctr++;                            \
-            HS_W_PUSH(now, i_, HS_EV_POLL, (SRV), 0, 0ull, -1, 0u); }                                    \
-    } while (0)
-
-                    switch (kind) {
-                    case HS_EV_SOURCE_TICK: {          /* Source.handle_event, source.py:142-180 */
-                        const hs_entity_desc d = ENTS[ent];
-                        bool have = false; uint64_t idxP = 0; int32_t key = -1;
-                        if (!(d.l0 >= 0 && now > d.l0)) {
-                            X->u.src.provider++;
-                            idxP = ctr++;
-                            if (d.i1 > 0) {
-                                const double u = hs_uniform(seed, rid, HS_STREAM_ROUTING | (ent << 8), X->u.src.key_draws++);
-                                key = (int32_t)HS_D2LL(HS_MUL(u, (double)d.i1));
-                            }
-                            have = true;
-                        }
-                        X->u.src.generated++;
-                        double target = 1.0;
-                        if (X->i0 == HS_ARR_POISSON && P.trace_arr) {
-                            if (H->np_cursor >= P.n_trace_arr) { H->status |= HS_ST_TRACE_EXHAUSTED; H->np_cursor = 0; }
-                            target = P.trace_arr[(size_t)r * P.n_trace_arr + H->np_cursor++]; X->u.src.arr_draws++;
-                        } else if (X->i0 == HS_ARR_POISSON) {
-                            const double u = hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), X->u.src.arr_draws++);
-                            target = hs_exp1(u);
-                        }
-                        int64_t nt;
-                        if ((FLAGS & HS_WF_PROFILE) && d.i3 > 0) nt = hs_next_arrival_profile_ns(&M.profiles[d.i3 - 1], X->u.src.cur_ns, target);
-                        else nt = hs_next_arrival_ns(X->u.src.cur_ns, target, X->d0);
-                        if (have) HS_W_PUSH(now, idxP, HS_W_REQ_KIND(d.target), d.target, now, 0ull, key, 0u);
-                        if (nt != HS_T_EXHAUSTED) {          /* else "Source exhausted", source.py:176-180 */
-                            X->u.src.cur_ns = nt;
-                            const uint64_t idxT = ctr++;
-                            HS_W_PUSH(nt, idxT, HS_EV_SOURCE_TICK, ent, 0, 0ull, -1, 0u);
-                        }
-                        break;
-                    }
-                    case HS_EV_REQ_LB: {               /* LoadBalancer._forward_request, :347-433 */
-                        const hs_entity_desc d = ENTS[ent];
-                        X->u.lb.received++;
-                        if (d.i2 > 0) {
-                            int slot;
-                            if (d.i0 == HS_LB_KEY_TABLE && e_key >= 0) slot = M.key_table[e_key];
-                            else { slot = (int)(X->u.lb.rr_index % (uint64_t)d.i2); X->u.lb.rr_index++; }
-                            const int be = BACKENDS[d.i1 + slot];
-                            X->u.lb.in_flight++; X->u.lb.forwarded++;
-                            const uint64_t i_ = ctr++;
-                            HS_W_PUSH(now, i_, HS_W_REQ_KIND(be), be, e_created, 0ull, e_key, ent + 1u);
-                        }
-                        HS_W_REQUEST_HOOKS();
-                        break;
-                    }
-                    case HS_EV_REQ_ENQUEUE: {          /* Queue._handle_enqueue, queue.py:122-147 */
-                        const hs_entity_desc d = ENTS[ent];
-                        const bool was_empty = (X->u.srv.q_len == 0);
-                        if (d.l0 >= 0 && (int64_t)X->u.srv.q_len >= d.l0) X->u.srv.dropped++;
-                        else if (X->u.srv.q_len >= P.ring) H->status |= HS_ST_QUEUE_OVERFLOW;
-                        else {
-                            hs_wring_entry *rg = ring0 + (size_t)SRVIDX[ent] * P.ring;
-                            hs_wring_entry q; q.created = e_created; q.idx = bi; q.key = e_key;
-                            rg[(X->u.srv.q_head + X->u.srv.q_len) & ring_mask] = q;
-                            X->u.srv.q_len++;
-                            X->u.srv.accepted++;
-                            if (was_empty) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_NOTIFY, ent, 0, 0ull, -1, 0u); }
-                        }
-                        HS_W_REQUEST_HOOKS();          /* _lb_response fires at ENQUEUE time */
-                        break;
-                    }
-                    case HS_EV_NOTIFY:                 /* QueueDriver._handle_notify, :92-99 */
-                        if (X->u.srv.active < X->i0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_EV_POLL, ent, 0, 0ull, -1, 0u); }
-                        break;
-                    case HS_EV_POLL:                   /* Queue._handle_poll, queue.py:149-166 */
-                        if (X->u.srv.q_len > 0) {
-                            hs_wring_entry *rg = ring0 + (size_t)SRVIDX[ent] * P.ring;
-                            hs_wring_entry q;
-                            if (ENTS[ent].i1 == HS_Q_LIFO) q = rg[(X->u.srv.q_head + X->u.srv.q_len - 1) & ring_mask];
-                            else { q = rg[X->u.srv.q_head & ring_mask]; X->u.srv.q_head++; }
-                            X->u.srv.q_len--;
-                            const uint64_t i_ = ctr++;
-                            HS_W_PUSH(now, i_, HS_EV_DELIVER, ent, q.created, q.idx, (int32_t)q.key, 0u);
-                        }
-                        break;
-                    case HS_EV_DELIVER:                /* _handle_work_payload, queue_driver.py:78-90 */
-                        HS_W_PUSH(now, e_aux, HS_EV_REQ_WORKER, ent, e_created, 0ull, e_key, 0x80000000u);
-                        break;
-                    case HS_EV_REQ_WORKER: {           /* Server.handle_queued_event, first step */
-                        ctr++;                         /* inline ProcessContinuation (event.py:314-325) */
-                        if (X->u.srv.active >= X->i0) {
-                            X->u.srv.rejected++; H->status |= HS_ST_REJECT_PATH;
-                            HS_W_POLL_HOOK(ent);
-                            break;
-                        }
-                        X->u.srv.active++;
-                        int64_t dur;
-                        if (ENTS[ent].i2 == HS_SVC_EXPONENTIAL && P.trace_svc) {
-                            if (H->py_cursor >= P.n_trace_svc) { H->status |= HS_ST_TRACE_EXHAUSTED; H->py_cursor = 0; }
-                            dur = hs_seconds_to_ns(HS_DIV(P.trace_svc[(size_t)r * P.n_trace_svc + H->py_cursor++], X->lambda)); X->u.srv.svc_draws++;
-                        } else if (ENTS[ent].i2 == HS_SVC_EXPONENTIAL) {
-                            const double u = hs_uniform(seed, rid, HS_STREAM_SERVICE | (ent << 8), X->u.srv.svc_draws++);
-                            dur = hs_exp_latency_ns(u, X->lambda);
-                        } else dur = hs_seconds_to_ns(X->d0);
-                        const double svc_s = hs_ns_to_seconds(dur);
-                        if ((FLAGS & HS_WF_REC) && svc_out) { svc_out[H->svc_pos] = svc_s; H->svc_pos = (H->svc_pos + 1 == P.service_cap) ? 0u : H->svc_pos + 1; }
-                        H->n_svc++;
-                        const uint64_t i_ = ctr++;
-                        HS_W_PUSH(hs_resume_ns(now, svc_s), i_, HS_EV_CONTINUATION, ent, e_created,
-                                  (uint64_t)__double_as_longlong(svc_s), e_key, e_hook & 0x80000000u);
-                        break;
-                    }
-                    case HS_EV_CONTINUATION: {         /* generator resumes, server.py:255-273 */
-                        X->u.srv.active = X->u.srv.active > 0 ? X->u.srv.active - 1 : 0;
-                        X->u.srv.completed++;
-                        X->u.srv.total_service = HS_ADD(X->u.srv.total_service, __longlong_as_double((long long)e_aux));
-                        const int tgt = ENTS[ent].target;
-                        if (tgt >= 0) { const uint64_t i_ = ctr++; HS_W_PUSH(now, i_, HS_W_REQ_KIND(tgt), tgt, e_created, 0ull, e_key, 0u); }
-                        if (e_hook & 0x80000000u) HS_W_POLL_HOOK(ent);
-                        break;
-                    }
-                    case HS_EV_REQ_SINK: {             /* Sink.handle_event, common.py:36-44 */
-                        X->u.snk.received++;
-                        const double lat = hs_ns_to_seconds(now - e_created);
-                        if (O.hist) atomicAdd(O.hist + (size_t)r * HS_HIST_BINS + hs_latency_bin(now - e_created), 1u);
-                        hs_neumaier_add(&X->u.snk.sum, &X->u.snk.comp, lat);
-                        X->u.snk.sumsq = HS_ADD(X->u.snk.sumsq, HS_MUL(lat, lat));
-                        if (lat < X->u.snk.mn) X->u.snk.mn = lat;
-                        if (lat > X->u.snk.mx) X->u.snk.mx = lat;
-                        if ((FLAGS & HS_WF_REC) && smp) { hs_sink_sample q; q.completion_ns = now; q.latency_s = lat; smp[H->smp_pos] = q;
-                            H->smp_pos = (H->smp_pos + 1 == P.sample_cap) ? 0u : H->smp_pos + 1; }
-                        H->n_smp++;
-                        HS_W_REQUEST_HOOKS();
-                        break;
-                    }
-                    case HS_EV_PROBE: {                /* measure_callback, instrumentation/probe.py:51-66 */
-                        const hs_entity_desc pd = ENTS[ent];
-                        const hs_went *T = &E[pd.target];
-                        const int tk = ENTS[pd.target].kind;
-                        double val = 0.0;
-                        switch (pd.i0) {
-                        case HS_METRIC_DEPTH: val = (double)T->u.srv.q_len; break;
-                        case HS_METRIC_ACTIVE_REQUESTS: val = (double)T->u.srv.active; break;
-                        case HS_METRIC_UTILIZATION: val = T->i0 == 0 ? 0.0 : HS_DIV((double)T->u.srv.active, (double)T->i0); break;
-                        case HS_METRIC_AVAILABLE_CAPACITY: val = (double)(T->i0 - T->u.srv.active); break;
-                        case HS_METRIC_STATS_ACCEPTED: val = (double)T->u.srv.accepted; break;
-                        case HS_METRIC_STATS_DROPPED: val = (double)T->u.srv.dropped; break;
-                        case HS_METRIC_EVENTS_RECEIVED: case HS_METRIC_TOTAL: val = (double)T->u.snk.received; break;
-                        case HS_METRIC_GENERATED_COUNT: val = (double)T->u.src.generated; break;
-                        }
-                        (void)tk;
-                        X->u.snk.received++;
-                        hs_neumaier_add(&X->u.snk.sum, &X->u.snk.comp, val);
-                        if (val < X->u.snk.mn) X->u.snk.mn = val;
-                        if (val > X->u.snk.mx) X->u.snk.mx = val;
-                        if ((FLAGS & HS_WF_REC) && smp) { hs_sink_sample q; q.completion_ns = now; q.latency_s = val; smp[H->smp_pos] = q;
-                            H->smp_pos = (H->smp_pos + 1 == P.sample_cap) ? 0u : H->smp_pos + 1; }
-                        H->n_smp++;
-                        break;
-                    }
-                    case HS_EV_REQ_COUNTER:            /* Counter.handle_event, common.py:92-95 */
-                        X->u.snk.received++;
-                        HS_W_REQUEST_HOOKS();
-                        break;
-                    case HS_EV_LB_RESPONSE:            /* LoadBalancer._handle_response, :435-473 */
-                        if (X->u.lb.in_flight > 0) X->u.lb.in_flight--;
-                        X->u.lb.responses++;
-                        break;
-                    default: break;
-                    }
+#include "hs_handlers.inc"
 #undef HS_W_PUSH
-#undef HS_W_REQ_KIND
-#undef HS_W_REQUEST_HOOKS
-#undef HS_W_POLL_HOOK
                 }
                 /* ---- extract the future-tier minimum into the now tier ------------- */
                 if (go == 1) {

@@ -138,7 +138,7 @@ typedef struct hs_run_params {
     uint32_t sample_cap;       /* Sink-sample ring entries per replica                         */
     uint32_t service_cap;      /* service-time ring entries per replica                        */
     uint32_t queue_ring;       /* device queue ring entries per server (power of two), 0 = default */
-    uint32_t engine;           /* 0 auto, 1 warp engine (general), 2 lane engine (single server) */
+    uint32_t engine;           /* 0 auto, 1 warp engine (general), 2 lane engine (single server), 3 thread engine (general) */
     /* Windowed execution (reference: Simulation._run_window, core/simulation.py:527-541):
      * when 0 <= window_end_ns < end_ns the call pauses every replica before the first
      * event later than window_end_ns and keeps its state on the device; a following

@@ -17,10 +17,12 @@ def eng():
     e.close()
 
 
+@pytest.mark.parametrize("eng_id", [0, 1, 3])      # auto (lane where it applies, else thread), warp, thread
 @pytest.mark.parametrize("name", G.case_names("philox_"))
-def test_engine_reproduces_reference_fixture(eng, name):
+def test_engine_reproduces_reference_fixture(eng, name, eng_id):
     model, kw, z = G.load(name)
     eng.upload(model)
+    kw["engine"] = eng_id
     # the fixture's replica sits in the middle of a small ensemble
     kw = dict(kw)
     rid = kw.pop("rid_base")
@@ -47,17 +49,18 @@ def test_flight_recorder_rings_keep_the_tail(eng):
     assert int(s["order_hash"]) == int(z["summaries"]["order_hash"][0])
 
 
+@pytest.mark.parametrize("eng_id", [0, 1, 3])
 @pytest.mark.parametrize("name", G.case_names("stock_"))
-def test_engine_reproduces_stock_seeded_reference_from_its_generator_streams(eng, name):
+def test_engine_reproduces_stock_seeded_reference_from_its_generator_streams(eng, name, eng_id):
     """The UNMODIFIED, stock-seeded reference (no plug-ins) vs the engine fed with the two MT19937
-    streams as unit-rate exponentials (hs_set_trace): lane engine for M/M/1, warp engine with the
+    streams as unit-rate exponentials (hs_set_trace): lane engine for M/M/1, the general engines with the
     shared-stream cursors for several servers."""
     model, kw, z = G.load(name)
     kw = dict(kw); kw.pop("seed"); kw.pop("rid_base")
     eng.upload(model)
     eng.set_trace(z["trace_targets"][None, :], z["trace_service"][None, :])
     try:
-        eng.run(engine.make_params(n_replicas=1, **G.caps(z), **kw))
+        eng.run(engine.make_params(n_replicas=1, engine=eng_id, **G.caps(z), **kw))
         got = eng.read_outputs()
     finally:
         eng.set_trace(None, None)

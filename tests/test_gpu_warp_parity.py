@@ -1,4 +1,5 @@
-"""GPU parity of the warp engine (general models) against the CPU oracle: M/M/c,
+"""GPU parity of the two general engines (1 = warp per replica, 3 = thread per replica; they share
+the handlers in csrc/hs_handlers.inc) against the CPU oracle: M/M/c,
 load-balanced server farms (round robin and consistent-hash key table), tandem
 queues, multiple sources, sweeps with per-cell parameters -- bit-exact event
 sequence, statistics and samples, through the C-ABI."""
@@ -75,12 +76,13 @@ def _src_sink():
     return b.build()
 
 
+@pytest.mark.parametrize("eng_id", [1, 3])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_warp_matches_oracle(eng, name):
+def test_warp_matches_oracle(eng, name, eng_id):
     mk, end_s, n = CASES[name]
     model = mk()
     got, want = both(eng, model, seed=99, end_ns=int(end_s * 1e9), n_replicas=n, record_cap=30000,
-                     sample_cap=3000, service_cap=3000, engine=1,
+                     sample_cap=3000, service_cap=3000, engine=eng_id,
                      queue_ring=(1 << 16) if name.startswith("zero_gap") else 0)
     assert int(want["summaries"]["events_processed"].min()) > 100
     assert_same(got, want)
@@ -92,24 +94,29 @@ def test_warp_and_lane_engines_agree(eng):
     eng.upload(model)
     eng.run(engine.make_params(engine=1, **kw)); a = eng.read_outputs()
     eng.run(engine.make_params(engine=2, **kw)); b = eng.read_outputs()
+    eng.run(engine.make_params(engine=3, **kw)); c = eng.read_outputs()
     assert_same(a, b)
+    assert_same(c, b)
 
 
-def test_mmc_sweep_cells(eng):
+@pytest.mark.parametrize("eng_id", [0, 1, 3])
+def test_mmc_sweep_cells(eng, eng_id):
     """configs[4] in small: per-cell (c, rho) overrides; replica -> cell = index // replicas_per_cell."""
     model = hs.mmc_sweep(cs=(1, 2, 5, 32), rhos=(0.5, 0.9))
     got, want = both(eng, model, seed=4, end_ns=20 * 10**9, n_replicas=8 * 6, replicas_per_cell=6, record_cap=60000,
-                     sample_cap=7000, service_cap=7000)
+                     sample_cap=7000, service_cap=7000, engine=eng_id)
     assert_same(got, want)
     ev = got["summaries"]["events_processed"].reshape(8, 6).mean(axis=1)
     assert ev[-1] > 10 * ev[0]          # c = 32 cells process far more requests than c = 1
 
 
-def test_warp_windowed_resume_uses_staged_state(eng):
-    """Pause/resume goes through the TMA bulk store/load of the replica block."""
+@pytest.mark.parametrize("eng_id", [1, 3])
+def test_warp_windowed_resume_uses_staged_state(eng, eng_id):
+    """Pause/resume: the warp engine goes through the TMA bulk store/load of the replica block, the thread
+    engine continues from the block where it lies."""
     model = hs.lb_round_robin(8, 64.0)
     end = 12 * 10**9
-    kw = dict(seed=17, n_replicas=33, record_cap=12000, sample_cap=1500, service_cap=1500)
+    kw = dict(seed=17, n_replicas=33, record_cap=12000, sample_cap=1500, service_cap=1500, engine=eng_id)
     want = O.oracle_run(model, O.make_params(end_ns=end, **kw))
     eng.upload(model)
     eng.run(engine.make_params(end_ns=end, window_end_ns=3 * 10**9, **kw))

@@ -231,9 +231,9 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     }
     const uint32_t S = (uint32_t)((live + 31) / 32) * 32;
     if (S > 65535) return fail(HS_ERR_INVALID, "model needs %u future-event slots (limit 65535)", S);
-    /* thread engine: the future tier is a binary heap of whole entries instead of the SoA slot table */
+    /* thread engine: 4-ary key heap + payload slots instead of the warp engine's SoA slot table */
     const uint32_t block_bytes = per_thread
-        ? (uint32_t)(sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + ((size_t)S + HS_W_NCAP) * sizeof(hs_wnow))
+        ? hs_thread_offsets(ne, S).total
         : (uint32_t)(sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went) + (((size_t)S * 46 + 15) / 16) * 16 +
                      (size_t)HS_W_NCAP * sizeof(hs_wnow));
     const uint32_t per_warp = 16 + block_bytes;

@@ -2,19 +2,28 @@
  * (load-balanced farms, tandem queues, several sources, probes ...).
  *
  * The warp engine gives a replica a whole warp but its handlers are scalar control flow, so 31
- * lanes idle; here every lane runs its own replica.  The replica's state cannot live in registers
- * (a 64-server farm is ~11 KB), so it stays in a contiguous per-replica block in HBM
- *     [ header 128 B | entity state n x 96 B | future heap, S x 48 B | now tier, 24 x 48 B ]
- * that the lane reads and writes through L1/L2 (a block is touched by exactly one thread, so there
- * is nothing to stage or synchronise, and a paused window resumes from the very same bytes).
- * Pending events are kept in two tiers that together order exactly like the reference's heap:
- *   now tier     events created at the current timestamp, a small array scanned by sort index;
- *   future heap  a binary min-heap on (time, sort_index) for SourceEvents / ProcessContinuations
- *                (two pops and two pushes per request on a Source -> Server path).
- * The handlers are the shared restatement in hs_handlers.inc.
+ * lanes idle; here every lane runs its own replica.  A replica's state cannot live in registers
+ * (a 64-server farm is ~10 KB), so it stays in a contiguous per-replica block in HBM
+ *     [ header 128 B | entity state n x 96 B | heap keys S x 16 B | payloads S x 32 B |
+ *       free-slot stack S x 2 B | now-tier overflow 24 x 48 B ]
+ * that only this thread touches (nothing to stage or synchronise; a paused window resumes from the
+ * same bytes).  Pending events are kept in two tiers that together order exactly like the
+ * reference's heap (time, then sort index):
+ *   now tier     events created at the current timestamp (the same-time protocol chain ENQUEUE,
+ *                NOTIFY, POLL, DELIVER, WORKER, SINK, _lb_response): the first HS_T_KS entries of
+ *                every thread sit in shared memory ([entry][16-byte chunk][thread], conflict-free),
+ *                deeper ones (rare: many events on one nanosecond) overflow to the block in HBM;
+ *   future heap  SourceEvents / ProcessContinuations: a 4-ary min-heap of 16-byte keys
+ *                (time, sort_index << 16 | payload slot) -- the four children of a node are one
+ *                64-byte aligned line, so a pop costs log4(n) dependent line reads -- with the
+ *                32-byte payloads parked in slots; the root key is cached in registers.
+ * Threads of a warp run different handlers, so everything expensive is hoisted to where they are
+ * converged again: the pop, the loads of the model row and the entity state (handlers work on a
+ * private copy, written back after the switch), the random draw (phase B of hs_handlers.inc) and
+ * the heap insertion of the (at most one) future event an event creates.
  *
- * Bound: L2/HBM latency of a dependent chain per event, hidden by running one replica per lane
- * on as many lanes as the ensemble provides.
+ * Bound: latency of the dependent L2/HBM accesses per event (state that is private to a replica),
+ * hidden by running one replica per lane on as many lanes as the ensemble provides.
  */
 #ifndef HS_THREAD_ENGINE_CUH
 #define HS_THREAD_ENGINE_CUH
@@ -22,24 +31,49 @@
 #include "hs_warp_engine.cuh"       /* hs_warp_hdr, hs_went, hs_wnow, hs_wring_entry, model/run/out structs */
 
 #define HS_THREAD_BLOCK 64
+#define HS_T_KS 4                   /* now-tier entries per replica held in shared memory */
+#define HS_EV_REQ_ANY 0xffu         /* private: "request for entity `ent`", kind resolved when popped */
+
+struct __align__(16) hs_tkey { int64_t time; uint64_t k2; };                 /* k2 = sort_index << 16 | slot */
+struct __align__(16) hs_tpay { int64_t created; uint64_t aux; uint32_t m0; int32_t key; uint32_t hook, pad; };
+
+struct hs_thread_layout { uint32_t keys, pay, free_, spill, total; };
+
+__host__ __device__ inline hs_thread_layout hs_thread_offsets(uint32_t ne, uint32_t S)
+{
+    hs_thread_layout L;
+    L.keys = ((uint32_t)sizeof(hs_warp_hdr) + ne * (uint32_t)sizeof(hs_went) + 63u) / 64u * 64u;
+    L.pay = L.keys + (48u + S * 16u + 63u) / 64u * 64u;     /* key 0 at +48: children 4k+1..4k+4 share a 64-B line */
+    L.free_ = L.pay + S * 32u;
+    L.spill = L.free_ + (S * 2u + 15u) / 16u * 16u;
+    L.total = (L.spill + HS_W_NCAP * (uint32_t)sizeof(hs_wnow) + 127u) / 128u * 128u;
+    return L;
+}
+
+#define HS_T_LT(T1, I1, T2, I2) ((T1) < (T2) || ((T1) == (T2) && (I1) < (I2)))
 
 template <int FLAGS>
 __global__ void __launch_bounds__(HS_THREAD_BLOCK)
 hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blocks,
                  hs_wring_entry *__restrict__ rings, hs_warp_out O)
 {
+    __shared__ uint4 Ns[HS_T_KS * 3 * HS_THREAD_BLOCK];
+    const int tid = threadIdx.x;
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.n_replicas) return;
-    const uint32_t S = M.fel_slots;                      /* future-heap capacity */
+    const uint32_t S = M.fel_slots;                      /* heap capacity */
     const uint32_t ne = M.n_entities;
     const hs_entity_desc *ENTS = M.ents;
     const int32_t *SRVIDX = M.srv_index, *BACKENDS = M.backends;
+    const hs_thread_layout L = hs_thread_offsets(ne, S);
 
     unsigned char *blk = blocks + (size_t)r * M.block_bytes;
     hs_warp_hdr *Hg = (hs_warp_hdr *)blk;
     hs_went *E = (hs_went *)(blk + sizeof(hs_warp_hdr));
-    hs_wnow *heap = (hs_wnow *)(blk + sizeof(hs_warp_hdr) + (size_t)ne * sizeof(hs_went));
-    hs_wnow *N = heap + S;
+    hs_tkey *K = (hs_tkey *)(blk + L.keys + 48);
+    hs_tpay *PAY = (hs_tpay *)(blk + L.pay);
+    uint16_t *FREE = (uint16_t *)(blk + L.free_);
+    hs_wnow *Ng = (hs_wnow *)(blk + L.spill);
 
     const uint32_t gidx = P.index_base + r;
     const uint64_t seed = P.seed + (uint64_t)gidx * P.seed_stride;
@@ -48,13 +82,47 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     const uint32_t ring_mask = P.ring - 1u;
     const bool windowed = (P.window_end_ns >= 0 && P.window_end_ns < P.end_ns);
 
-    hs_warp_hdr hdr;                                     /* working copy of the header */
+    union now_u { hs_wnow e; uint4 q[3]; };
+    auto now_store = [&](int k, const hs_wnow &v) {
+        now_u u; u.e = v;
+        if (k < HS_T_KS) {
+            Ns[(k * 3 + 0) * HS_THREAD_BLOCK + tid] = u.q[0];
+            Ns[(k * 3 + 1) * HS_THREAD_BLOCK + tid] = u.q[1];
+            Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid] = u.q[2];
+        } else {
+            uint4 *g = (uint4 *)&Ng[k]; g[0] = u.q[0]; g[1] = u.q[1]; g[2] = u.q[2];
+        }
+    };
+    auto now_load = [&](int k) -> hs_wnow {
+        now_u u;
+        if (k < HS_T_KS) {
+            u.q[0] = Ns[(k * 3 + 0) * HS_THREAD_BLOCK + tid];
+            u.q[1] = Ns[(k * 3 + 1) * HS_THREAD_BLOCK + tid];
+            u.q[2] = Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid];
+        } else {
+            const uint4 *g = (const uint4 *)&Ng[k]; u.q[0] = g[0]; u.q[1] = g[1]; u.q[2] = g[2];
+        }
+        return u.e;
+    };
+    auto now_key = [&](int k, int64_t &t, uint64_t &ix) {
+        const uint4 a = (k < HS_T_KS) ? Ns[(k * 3) * HS_THREAD_BLOCK + tid] : *(const uint4 *)&Ng[k];
+        t = (int64_t)((uint64_t)a.x | ((uint64_t)a.y << 32)); ix = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    };
+
+    hs_warp_hdr hdr;                                     /* working copy of the header (registers) */
     hs_warp_hdr *H = &hdr;
     if (P.resume) {
         hdr = *Hg;
         if (hdr.done) return;
+        for (int k = 0; k < hdr.now_n && k < HS_T_KS; ++k) {
+            const uint4 *g = (const uint4 *)&Ng[k];
+            Ns[(k * 3 + 0) * HS_THREAD_BLOCK + tid] = g[0];
+            Ns[(k * 3 + 1) * HS_THREAD_BLOCK + tid] = g[1];
+            Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid] = g[2];
+        }
     } else {
-        for (uint32_t i = 0; i < M.block_bytes / 16; ++i) ((uint4 *)blk)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = 0; i < L.keys / 16; ++i) ((uint4 *)blk)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = 0; i < S; ++i) FREE[i] = (uint16_t)(S - 1 - i);
         memset(&hdr, 0, sizeof hdr);
         const uint32_t cell = M.n_cells ? (gidx / P.replicas_per_cell) % M.n_cells : 0u;
         for (uint32_t i = 0; i < ne; ++i) {
@@ -72,6 +140,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         /* Simulation.__init__: source.start() in order; bootstrap indices come from the global
          * counter (simulation.py:77,145-154), run() restarts the per-heap one at 0. */
         uint64_t boot = 0;
+        uint32_t hn = 0;
         for (uint32_t i = 0; i < ne; ++i) {
             if (ENTS[i].kind != HS_ENT_SOURCE) continue;
             hs_went *e = &E[i];
@@ -86,19 +155,20 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             int64_t first;
             if ((FLAGS & HS_WF_PROFILE) && pi > 0) first = hs_next_arrival_profile_ns(&M.profiles[pi - 1], 0, target);
             else first = hs_next_arrival_ns(0, target, e->d0);
-            if (first == HS_T_EXHAUSTED) continue;
+            if (first == HS_T_EXHAUSTED) continue;       /* source.start(): RuntimeError, no tick */
             e->u.src.cur_ns = first;
-            if ((uint32_t)hdr.fel_n >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; break; }
-            hs_wnow n_; n_.time = first; n_.idx = boot++; n_.created = 0; n_.aux = 0ull;
-            n_.m0 = HS_EV_SOURCE_TICK | (i << 8); n_.key = -1; n_.hook = 0u; n_.pad = 0u;
-            /* sift up */
-            int k = hdr.fel_n;                           /* fel_n counts both tiers; only the heap is filled here */
-            while (k > 0) { const int p = (k - 1) >> 1; const hs_wnow q = heap[p];
-                            if (!(n_.time < q.time || (n_.time == q.time && n_.idx < q.idx))) break; heap[k] = q; k = p; }
-            heap[k] = n_;
-            hdr.fel_n++;
+            if (hn >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; break; }
+            const uint32_t slot = FREE[S - hn - 1];
+            hs_tpay pp; pp.created = 0; pp.aux = 0ull; pp.m0 = HS_EV_SOURCE_TICK | (i << 8); pp.key = -1; pp.hook = 0u; pp.pad = 0u;
+            PAY[slot] = pp;
+            hs_tkey nk; nk.time = first; nk.k2 = (boot++ << 16) | slot;
+            uint32_t k = hn++;
+            while (k > 0) { const uint32_t p = (k - 1) >> 2; const hs_tkey q = K[p];
+                            if (!HS_T_LT(nk.time, nk.k2, q.time, q.k2)) break; K[k] = q; k = p; }
+            K[k] = nk;
         }
-        hdr.free_top = (uint32_t)hdr.fel_n;              /* free_top doubles as the heap size in this engine */
+        hdr.fel_n = (int32_t)hn;
+        hdr.free_top = hn;                               /* free_top holds the heap size in this engine */
         hdr.ctr = 0;
     }
 
@@ -106,56 +176,77 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     hs_sink_sample *smp = (FLAGS & HS_WF_REC) && O.samples ? O.samples + (size_t)r * P.sample_cap : nullptr;
     double *svc_out = (FLAGS & HS_WF_REC) && O.service ? O.service + (size_t)r * P.service_cap : nullptr;
 
-#define HS_T_LT(T1, I1, T2, I2) ((T1) < (T2) || ((T1) == (T2) && (I1) < (I2)))
     uint64_t ctr = hdr.ctr;
     int now_n = hdr.now_n;
     uint32_t heap_n = hdr.free_top;
+    int64_t top_t = HS_W_EMPTY; uint64_t top_k = ~0ull;  /* the heap's root key, cached */
+    if (heap_n) { const hs_tkey t0 = K[0]; top_t = t0.time; top_k = t0.k2; }
     bool paused = false;
     while (true) {
         const int64_t now0 = hdr.now;
         if (!(now0 <= P.end_ns) || (hdr.status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW | HS_ST_TRACE_EXHAUSTED))) break;
         if (hdr.processed >= P.max_events) { hdr.status |= HS_ST_EVENT_LIMIT; break; }
-        /* next event: the now tier's minimum, unless the heap's minimum sorts first */
+        /* ---- pop: the now tier's minimum, unless the heap's root sorts first ---------- */
         int nb = -1; int64_t nt = HS_W_EMPTY; uint64_t ni = ~0ull;
         for (int k = 0; k < now_n; ++k) {
-            const int64_t t = N[k].time; const uint64_t ix = N[k].idx;
+            int64_t t; uint64_t ix; now_key(k, t, ix);
             if (HS_T_LT(t, ix, nt, ni)) { nt = t; ni = ix; nb = k; }
         }
         hs_wnow ev;
-        if (heap_n > 0 && (nb < 0 || HS_T_LT(heap[0].time, heap[0].idx, nt, ni))) {
-            ev = heap[0];
-            if (windowed && ev.time > P.window_end_ns) { paused = true; break; }
-            /* pop: move the last element to the root and sift it down */
+        if (heap_n > 0 && (nb < 0 || HS_T_LT(top_t, top_k >> 16, nt, ni))) {
+            if (windowed && top_t > P.window_end_ns) { paused = true; break; }
+            const uint32_t slot = (uint32_t)(top_k & 0xffffu);
+            const hs_tpay pp = PAY[slot];
+            ev.time = top_t; ev.idx = top_k >> 16; ev.created = pp.created; ev.aux = pp.aux;
+            ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = 0u;
             heap_n--;
-            if (heap_n > 0) {
-                const hs_wnow last = heap[heap_n];
+            FREE[S - heap_n - 1] = (uint16_t)slot;
+            if (heap_n > 0) {                            /* 4-ary sift-down of the last key from the root */
+                const hs_tkey last = K[heap_n];
                 uint32_t k = 0;
                 while (true) {
-                    uint32_t ch = 2 * k + 1;
-                    if (ch >= heap_n) break;
-                    hs_wnow a = heap[ch];
-                    if (ch + 1 < heap_n) { const hs_wnow b = heap[ch + 1]; if (HS_T_LT(b.time, b.idx, a.time, a.idx)) { a = b; ch++; } }
-                    if (!HS_T_LT(a.time, a.idx, last.time, last.idx)) break;
-                    heap[k] = a; k = ch;
+                    const uint32_t c = 4 * k + 1;
+                    if (c >= heap_n) break;
+                    hs_tkey best = K[c]; uint32_t bc = c;
+#pragma unroll
+                    for (uint32_t j = 1; j < 4; ++j)
+                        if (c + j < heap_n) { const hs_tkey o = K[c + j]; if (HS_T_LT(o.time, o.k2, best.time, best.k2)) { best = o; bc = c + j; } }
+                    if (!HS_T_LT(best.time, best.k2, last.time, last.k2)) break;
+                    K[k] = best;
+                    if (k == 0) { top_t = best.time; top_k = best.k2; }
+                    k = bc;
                 }
-                heap[k] = last;
-            }
+                K[k] = last;
+                if (k == 0) { top_t = last.time; top_k = last.k2; }
+            } else { top_t = HS_W_EMPTY; top_k = ~0ull; }
         } else if (nb >= 0) {
             if (windowed && nt > P.window_end_ns) { paused = true; break; }
-            ev = N[nb];
-            now_n--; N[nb] = N[now_n];
+            ev = now_load(nb);
+            now_n--;
+            if (nb != now_n) now_store(nb, now_load(now_n));
         } else break;                                    /* heap exhausted */
         hdr.fel_n--;
         if (ev.time < now0) continue;                    /* "time travel": skipped (simulation.py:479-489) */
 
         const int64_t now = ev.time;
         const uint64_t bi = ev.idx;
-        const int kind = (int)(ev.m0 & 0xffu);
         const uint32_t ent = ev.m0 >> 8;
         const int64_t e_created = ev.created;
         const uint64_t e_aux = ev.aux;
         const int32_t e_key = ev.key;
         const uint32_t e_hook = ev.hook;
+        /* model row and entity state, loaded while the warp is converged; handlers work on the copy */
+        union { hs_entity_desc d; uint4 q[3]; } du;
+        { const uint4 *g = (const uint4 *)&ENTS[ent]; du.q[0] = g[0]; du.q[1] = g[1]; du.q[2] = g[2]; }
+        union { hs_went w; uint4 q[6]; } xu;
+        { const uint4 *g = (const uint4 *)&E[ent];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) xu.q[i] = g[i]; }
+        hs_went *X = &xu.w;
+        int kind = (int)(ev.m0 & 0xffu);
+        if (kind == (int)HS_EV_REQ_ANY)
+            kind = du.d.kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE : du.d.kind == HS_ENT_SINK ? HS_EV_REQ_SINK :
+                   du.d.kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : du.d.kind == HS_ENT_PROBE ? HS_EV_PROBE : HS_EV_REQ_LB;
         hdr.now = now;
         if (FLAGS & HS_WF_HASH) hdr.hash = hs_hash_step(hdr.hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
         if ((FLAGS & HS_WF_REC) && rec) {
@@ -164,30 +255,64 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             rec[hdr.rec_pos] = rc; hdr.rec_pos = (hdr.rec_pos + 1 == P.record_cap) ? 0u : hdr.rec_pos + 1;
         }
         hdr.processed++;
-        hs_went *X = &E[ent];
 
-        /* push: an event at (or before) `now` joins the now tier, a later one the heap */
+        bool have_fut = false;                           /* an event creates at most one future event */
+        hs_tkey fkey; hs_tpay fpay;
+        fkey.time = 0; fkey.k2 = 0ull; fpay.created = 0; fpay.aux = 0ull; fpay.m0 = 0u; fpay.key = -1; fpay.hook = 0u; fpay.pad = 0u;
 #define HS_W_PUSH(TIME, IDX, KIND, ENT, CREATED, AUX, KEY, HOOK)                                         \
     do {                                                                                                 \
-        hs_wnow n_; n_.time = (TIME); n_.idx = (IDX); n_.created = (CREATED); n_.aux = (AUX);            \
-        n_.m0 = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); n_.key = (KEY); n_.hook = (HOOK); n_.pad = 0; \
-        if (n_.time <= now) {                                                                            \
+        const int64_t t_ = (TIME);                                                                       \
+        if (t_ <= now) {                                                                                 \
             if (now_n >= HS_W_NCAP) hdr.status |= HS_ST_FEL_OVERFLOW;                                    \
-            else { N[now_n++] = n_; hdr.fel_n++; }                                                       \
-        } else if (heap_n >= S) hdr.status |= HS_ST_FEL_OVERFLOW;                                        \
-        else {                                                                                           \
-            uint32_t k_ = heap_n++;                                                                      \
-            while (k_ > 0) { const uint32_t p_ = (k_ - 1) >> 1; const hs_wnow q_ = heap[p_];             \
-                             if (!HS_T_LT(n_.time, n_.idx, q_.time, q_.idx)) break; heap[k_] = q_; k_ = p_; } \
-            heap[k_] = n_; hdr.fel_n++;                                                                  \
+            else { hs_wnow n_; n_.time = t_; n_.idx = (IDX); n_.created = (CREATED); n_.aux = (AUX);     \
+                   n_.m0 = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); n_.key = (KEY); n_.hook = (HOOK); n_.pad = 0u; \
+                   now_store(now_n++, n_); hdr.fel_n++; }                                                \
+        } else {                                                                                         \
+            if (have_fut) hdr.status |= HS_ST_FEL_OVERFLOW;                                              \
+            fkey.time = t_; fkey.k2 = (uint64_t)(IDX) << 16; fpay.created = (CREATED); fpay.aux = (AUX); \
+            fpay.m0 = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); fpay.key = (KEY); fpay.hook = (HOOK);   \
+            have_fut = true;                                                                             \
         }                                                                                                \
     } while (0)
+#define HS_W_REQ_KIND(TGT) HS_EV_REQ_ANY
+#define HS_W_D (du.d)
 #include "hs_handlers.inc"
+#undef HS_W_D
+#undef HS_W_REQ_KIND
 #undef HS_W_PUSH
+        /* write the entity's dynamic state back (the union; d0 / lambda / i0 never change) */
+        { uint4 *g = (uint4 *)&E[ent];
+#pragma unroll
+          for (int i = 2; i < 6; ++i) g[i] = xu.q[i]; }
+        /* heap insertion of the future event (SourceEvent or ProcessContinuation) */
+        if (have_fut) {
+            if (heap_n >= S) hdr.status |= HS_ST_FEL_OVERFLOW;
+            else {
+                const uint32_t slot = FREE[S - heap_n - 1];
+                PAY[slot] = fpay;
+                fkey.k2 |= slot;
+                uint32_t k = heap_n++;
+                while (k > 0) {
+                    const uint32_t p = (k - 1) >> 2;
+                    hs_tkey q;
+                    if (p == 0) { q.time = top_t; q.k2 = top_k; } else q = K[p];
+                    if (!HS_T_LT(fkey.time, fkey.k2, q.time, q.k2)) break;
+                    K[k] = q; k = p;
+                }
+                K[k] = fkey;
+                if (k == 0) { top_t = fkey.time; top_k = fkey.k2; }
+                hdr.fel_n++;
+            }
+        }
     }
-#undef HS_T_LT
 
     /* ---- publish ------------------------------------------------------------ */
+    for (int k = 0; k < now_n && k < HS_T_KS; ++k) {     /* park the shared-memory part of the now tier */
+        uint4 *g = (uint4 *)&Ng[k];
+        g[0] = Ns[(k * 3 + 0) * HS_THREAD_BLOCK + tid];
+        g[1] = Ns[(k * 3 + 1) * HS_THREAD_BLOCK + tid];
+        g[2] = Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid];
+    }
     hdr.ctr = ctr; hdr.now_n = now_n; hdr.free_top = heap_n;
     hdr.done = paused ? 0 : 1;
     *Hg = hdr;

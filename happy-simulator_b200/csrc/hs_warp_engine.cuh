@@ -360,7 +360,9 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
             if (fs == HS_W_NONE || t_ < ft || (t_ == ft && (i2_ < fi || (i2_ == fi && s_ < fs)))) { ft = t_; fi = i2_; fs = s_; } \
         }                                                                                                \
     } while (0)
+#define HS_W_D (ENTS[ent])
 #include "hs_handlers.inc"
+#undef HS_W_D
 #undef HS_W_PUSH
                 }
                 /* ---- extract the future-tier minimum into the now tier ------------- */

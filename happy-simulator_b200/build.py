@@ -37,7 +37,8 @@ def needs_build() -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "hs_engine.cu")]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("HS_B200_DEFS", "").split(), "-o", LIB_PATH,
+           os.path.join(CSRC, "hs_engine.cu")]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.check_call(cmd, cwd=CSRC)

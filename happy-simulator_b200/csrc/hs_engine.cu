@@ -207,7 +207,9 @@ static bool classify_lane(hs_engine *E)
     return true;
 }
 
-/* ---- warp engine launch ------------------------------------------------- */
+static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+/* ---- warp / thread engine launch ----------------------------------------- */
 
 static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec, bool want_hist, bool per_thread)
 {
@@ -272,7 +274,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     R.end_ns = p->end_ns; R.window_end_ns = p->window_end_ns;
     R.n_replicas = n; R.index_base = p->replica_index_base; R.replicas_per_cell = p->replicas_per_cell;
     R.record_cap = p->record_cap; R.sample_cap = p->sample_cap; R.service_cap = p->service_cap;
-    R.ring = ring; R.resume = p->resume;
+    R.ring = ring; R.resume = p->resume; R.lane_stride = 1;
     R.max_events = p->max_events > 0 ? p->max_events : INT64_MAX;
     R.trace_arr = E->n_trace_arr ? (const double *)E->d_trace_arr.p : nullptr; R.n_trace_arr = E->n_trace_arr;
     R.trace_svc = E->n_trace_svc ? (const double *)E->d_trace_svc.p : nullptr; R.n_trace_svc = E->n_trace_svc;
@@ -297,7 +299,14 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     const int fl = (want_hash ? HS_WF_HASH : 0) | (want_rec ? HS_WF_REC : 0) | (any_profile ? HS_WF_PROFILE : 0);
     if (per_thread) {
         M.model_bytes = 0;
-        const int tblocks = (int)((n + HS_THREAD_BLOCK - 1) / HS_THREAD_BLOCK);
+        /* replicas per warp: enough warps to fill the register file (16 warps of 128 registers per SM),
+         * and no more lanes per warp than that needs -- a warp's iteration costs the sum of the distinct
+         * paths its lanes take.  HS_THREAD_RPW overrides (experiments). */
+        uint32_t rpw = pow2_at_least((uint32_t)((n + (uint64_t)E->sm_count * 16 - 1) / ((uint64_t)E->sm_count * 16)));
+        if (const char *ev = getenv("HS_THREAD_RPW")) rpw = pow2_at_least((uint32_t)std::max(1, atoi(ev)));
+        rpw = std::min<uint32_t>(32, std::max<uint32_t>(1, rpw));
+        R.lane_stride = 32 / rpw;
+        const int tblocks = (int)(((uint64_t)n * R.lane_stride + HS_THREAD_BLOCK - 1) / HS_THREAD_BLOCK);
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
 #define HS_LAUNCH_THREAD(F) case F: hs_thread_kernel<F><<<tblocks, HS_THREAD_BLOCK, 0, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;
         switch (fl) {
@@ -404,7 +413,17 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
         }
         return 0;
     };
-    if ((rc = up(E->d_ents, E->ents.data(), n * sizeof(hs_entity_desc)))) return rc;
+    /* device copy of the entity rows: the reserved d1 carries the server's index among the servers
+     * (= its queue ring), so the kernels get it with the row instead of through a second table */
+    std::vector<hs_entity_desc> dev_ents(E->ents);
+    {
+        int64_t k = 0;
+        for (hs_entity_desc &e : dev_ents) {
+            const int64_t v = (e.kind == HS_ENT_SERVER) ? k++ : -1;
+            memcpy(&e.d1, &v, 8);
+        }
+    }
+    if ((rc = up(E->d_ents, dev_ents.data(), n * sizeof(hs_entity_desc)))) return rc;
     if ((rc = up(E->d_backends, E->backends.data(), E->backends.size() * 4))) return rc;
     if ((rc = up(E->d_key_table, E->key_table.data(), E->key_table.size() * 4))) return rc;
     if ((rc = up(E->d_cell_d0, E->cell_d0.data(), E->cell_d0.size() * 8))) return rc;
@@ -417,7 +436,6 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
     return HS_OK;
 }
 
-static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
 int hs_run(hs_engine *E, const hs_run_params *p)
 {

@@ -22,8 +22,12 @@
  * private copy, written back after the switch), the random draw (phase B of hs_handlers.inc) and
  * the heap insertion of the (at most one) future event an event creates.
  *
+ * Small ensembles do not fill the machine with 32 replicas per warp, and a warp's iteration takes as
+ * long as the sum of the distinct paths its lanes take: the launch spreads the replicas over as many
+ * warps as fit (P.lane_stride lanes per replica, the surplus lanes exit at once).
+ *
  * Bound: latency of the dependent L2/HBM accesses per event (state that is private to a replica),
- * hidden by running one replica per lane on as many lanes as the ensemble provides.
+ * hidden by running as many warps as the register file holds.
  */
 #ifndef HS_THREAD_ENGINE_CUH
 #define HS_THREAD_ENGINE_CUH
@@ -32,6 +36,14 @@
 
 #define HS_THREAD_BLOCK 64
 #define HS_T_KS 4                   /* now-tier entries per replica held in shared memory */
+#ifndef HS_T_ARITY
+#define HS_T_ARITY 4                /* heap fan-out: the children of a node are one aligned line of ARITY keys */
+#endif
+#ifndef HS_T_MINBLOCKS
+#define HS_T_MINBLOCKS 8             /* 8 x 64 threads x 128 registers = the register file */
+#endif
+#define HS_T_LEAD ((HS_T_ARITY - 1) * 16u)   /* bytes in front of heap key 0 */
+#define HS_T_SHIFT (HS_T_ARITY == 8 ? 3 : 2)
 #define HS_EV_REQ_ANY 0xffu         /* private: "request for entity `ent`", kind resolved when popped */
 
 struct __align__(16) hs_tkey { int64_t time; uint64_t k2; };                 /* k2 = sort_index << 16 | slot */
@@ -43,7 +55,8 @@ __host__ __device__ inline hs_thread_layout hs_thread_offsets(uint32_t ne, uint3
 {
     hs_thread_layout L;
     L.keys = ((uint32_t)sizeof(hs_warp_hdr) + ne * (uint32_t)sizeof(hs_went) + 63u) / 64u * 64u;
-    L.pay = L.keys + (48u + S * 16u + 63u) / 64u * 64u;     /* key 0 at +48: children 4k+1..4k+4 share a 64-B line */
+    L.keys = (L.keys + 127u) / 128u * 128u;
+    L.pay = L.keys + (HS_T_LEAD + (S + HS_T_ARITY) * 16u + 127u) / 128u * 128u;   /* the children ARITY k + 1 .. ARITY k + ARITY share one aligned line */
     L.free_ = L.pay + S * 32u;
     L.spill = L.free_ + (S * 2u + 15u) / 16u * 16u;
     L.total = (L.spill + HS_W_NCAP * (uint32_t)sizeof(hs_wnow) + 127u) / 128u * 128u;
@@ -53,24 +66,26 @@ __host__ __device__ inline hs_thread_layout hs_thread_offsets(uint32_t ne, uint3
 #define HS_T_LT(T1, I1, T2, I2) ((T1) < (T2) || ((T1) == (T2) && (I1) < (I2)))
 
 template <int FLAGS>
-__global__ void __launch_bounds__(HS_THREAD_BLOCK)
+__global__ void __launch_bounds__(HS_THREAD_BLOCK, HS_T_MINBLOCKS)
 hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blocks,
                  hs_wring_entry *__restrict__ rings, hs_warp_out O)
 {
     __shared__ uint4 Ns[HS_T_KS * 3 * HS_THREAD_BLOCK];
-    const int tid = threadIdx.x;
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid % P.lane_stride) return;                    /* surplus lanes (see above) */
+    const int tid = (int)(threadIdx.x / P.lane_stride);  /* this replica's column of the shared now tier */
+    const uint32_t r = gtid / P.lane_stride;
     if (r >= P.n_replicas) return;
     const uint32_t S = M.fel_slots;                      /* heap capacity */
     const uint32_t ne = M.n_entities;
     const hs_entity_desc *ENTS = M.ents;
-    const int32_t *SRVIDX = M.srv_index, *BACKENDS = M.backends;
+    const int32_t *BACKENDS = M.backends;
     const hs_thread_layout L = hs_thread_offsets(ne, S);
 
     unsigned char *blk = blocks + (size_t)r * M.block_bytes;
     hs_warp_hdr *Hg = (hs_warp_hdr *)blk;
     hs_went *E = (hs_went *)(blk + sizeof(hs_warp_hdr));
-    hs_tkey *K = (hs_tkey *)(blk + L.keys + 48);
+    hs_tkey *K = (hs_tkey *)(blk + L.keys + HS_T_LEAD);
     hs_tpay *PAY = (hs_tpay *)(blk + L.pay);
     uint16_t *FREE = (uint16_t *)(blk + L.free_);
     hs_wnow *Ng = (hs_wnow *)(blk + L.spill);
@@ -82,6 +97,8 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     const uint32_t ring_mask = P.ring - 1u;
     const bool windowed = (P.window_end_ns >= 0 && P.window_end_ns < P.end_ns);
 
+    /* entry k of the now tier: three 16-byte chunks, in shared memory (chunk stride = one row of the block)
+     * for k < HS_T_KS, in the replica block (contiguous) beyond */
     union now_u { hs_wnow e; uint4 q[3]; };
     auto now_store = [&](int k, const hs_wnow &v) {
         now_u u; u.e = v;
@@ -163,7 +180,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             PAY[slot] = pp;
             hs_tkey nk; nk.time = first; nk.k2 = (boot++ << 16) | slot;
             uint32_t k = hn++;
-            while (k > 0) { const uint32_t p = (k - 1) >> 2; const hs_tkey q = K[p];
+            while (k > 0) { const uint32_t p = (k - 1) >> HS_T_SHIFT; const hs_tkey q = K[p];
                             if (!HS_T_LT(nk.time, nk.k2, q.time, q.k2)) break; K[k] = q; k = p; }
             K[k] = nk;
         }
@@ -201,16 +218,21 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = 0u;
             heap_n--;
             FREE[S - heap_n - 1] = (uint16_t)slot;
-            if (heap_n > 0) {                            /* 4-ary sift-down of the last key from the root */
+            if (heap_n > 0) {                            /* sift-down of the last key from the root */
                 const hs_tkey last = K[heap_n];
                 uint32_t k = 0;
                 while (true) {
-                    const uint32_t c = 4 * k + 1;
+                    const uint32_t c = HS_T_ARITY * k + 1;
                     if (c >= heap_n) break;
-                    hs_tkey best = K[c]; uint32_t bc = c;
+                    /* all children at once (one aligned line; the key array has ARITY spare entries, so positions
+                     * past the heap's end are readable -- their stale contents are masked out by index) */
+                    hs_tkey ch[HS_T_ARITY];
 #pragma unroll
-                    for (uint32_t j = 1; j < 4; ++j)
-                        if (c + j < heap_n) { const hs_tkey o = K[c + j]; if (HS_T_LT(o.time, o.k2, best.time, best.k2)) { best = o; bc = c + j; } }
+                    for (uint32_t j = 0; j < HS_T_ARITY; ++j) ch[j] = K[c + j];
+                    hs_tkey best = ch[0]; uint32_t bc = c;
+#pragma unroll
+                    for (uint32_t j = 1; j < HS_T_ARITY; ++j)
+                        if (c + j < heap_n && HS_T_LT(ch[j].time, ch[j].k2, best.time, best.k2)) { best = ch[j]; bc = c + j; }
                     if (!HS_T_LT(best.time, best.k2, last.time, last.k2)) break;
                     K[k] = best;
                     if (k == 0) { top_t = best.time; top_k = best.k2; }
@@ -218,7 +240,8 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 }
                 K[k] = last;
                 if (k == 0) { top_t = last.time; top_k = last.k2; }
-            } else { top_t = HS_W_EMPTY; top_k = ~0ull; }
+            }
+            if (heap_n == 0) { top_t = HS_W_EMPTY; top_k = ~0ull; }
         } else if (nb >= 0) {
             if (windowed && nt > P.window_end_ns) { paused = true; break; }
             ev = now_load(nb);
@@ -247,6 +270,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         if (kind == (int)HS_EV_REQ_ANY)
             kind = du.d.kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE : du.d.kind == HS_ENT_SINK ? HS_EV_REQ_SINK :
                    du.d.kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : du.d.kind == HS_ENT_PROBE ? HS_EV_PROBE : HS_EV_REQ_LB;
+        const uint32_t srv_idx = (uint32_t)__double_as_longlong(du.d.d1);   /* patched in by the host, see hs_model_upload */
         hdr.now = now;
         if (FLAGS & HS_WF_HASH) hdr.hash = hs_hash_step(hdr.hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
         if ((FLAGS & HS_WF_REC) && rec) {
@@ -276,7 +300,9 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     } while (0)
 #define HS_W_REQ_KIND(TGT) HS_EV_REQ_ANY
 #define HS_W_D (du.d)
+#define HS_W_SRVIDX srv_idx
 #include "hs_handlers.inc"
+#undef HS_W_SRVIDX
 #undef HS_W_D
 #undef HS_W_REQ_KIND
 #undef HS_W_PUSH
@@ -293,7 +319,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 fkey.k2 |= slot;
                 uint32_t k = heap_n++;
                 while (k > 0) {
-                    const uint32_t p = (k - 1) >> 2;
+                    const uint32_t p = (k - 1) >> HS_T_SHIFT;
                     hs_tkey q;
                     if (p == 0) { q.time = top_t; q.k2 = top_k; } else q = K[p];
                     if (!HS_T_LT(fkey.time, fkey.k2, q.time, q.k2)) break;

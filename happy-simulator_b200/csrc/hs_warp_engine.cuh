@@ -84,6 +84,7 @@ struct hs_warp_run {
     int64_t end_ns, window_end_ns;
     uint32_t n_replicas, index_base, replicas_per_cell;
     uint32_t record_cap, sample_cap, service_cap, ring, resume;
+    uint32_t lane_stride;           /* thread engine: lanes per replica (1, 2, 4 ... 32) */
     int64_t max_events;
     const double *trace_arr, *trace_svc;
     uint64_t n_trace_arr, n_trace_svc;

@@ -3,11 +3,12 @@ from __future__ import annotations
 
 import ctypes as C
 
-HS_ABI_VERSION = 1
+HS_ABI_VERSION = 2
 
 HS_OK, HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_NO_DEVICE, HS_ERR_STATE, HS_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
 
-HS_ENT_SOURCE, HS_ENT_SERVER, HS_ENT_SINK, HS_ENT_COUNTER, HS_ENT_LB, HS_ENT_PROBE = 1, 2, 3, 4, 5, 6
+HS_ENT_SOURCE, HS_ENT_SERVER, HS_ENT_SINK, HS_ENT_COUNTER, HS_ENT_LB, HS_ENT_PROBE, HS_ENT_SKETCH = 1, 2, 3, 4, 5, 6, 7
+HS_SK_HLL, HS_SK_CMS = 1, 2
 METRICS = {"depth": 0, "active_requests": 1, "utilization": 2, "available_capacity": 3, "stats_accepted": 4,
            "stats_dropped": 5, "events_received": 6, "total": 7, "generated_count": 8}
 HS_ARR_CONSTANT, HS_ARR_POISSON = 0, 1
@@ -18,10 +19,10 @@ HS_PROF_CONSTANT, HS_PROF_LINEAR_RAMP, HS_PROF_SPIKE = 0, 1, 2
 
 (HS_EV_SOURCE_TICK, HS_EV_REQ_LB, HS_EV_REQ_ENQUEUE, HS_EV_NOTIFY, HS_EV_POLL, HS_EV_DELIVER,
  HS_EV_REQ_WORKER, HS_EV_CONTINUATION, HS_EV_REQ_SINK, HS_EV_LB_RESPONSE, HS_EV_REQ_COUNTER,
- HS_EV_PROBE) = range(12)
+ HS_EV_PROBE, HS_EV_REQ_SKETCH) = range(13)
 
 EVENT_KIND_NAMES = ["SOURCE_TICK", "REQ_LB", "REQ_ENQUEUE", "NOTIFY", "POLL", "DELIVER",
-                    "REQ_WORKER", "CONTINUATION", "REQ_SINK", "LB_RESPONSE", "REQ_COUNTER", "PROBE"]
+                    "REQ_WORKER", "CONTINUATION", "REQ_SINK", "LB_RESPONSE", "REQ_COUNTER", "PROBE", "REQ_SKETCH"]
 
 HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH, HS_ST_TRACE_EXHAUSTED, HS_ST_EVENT_LIMIT = 1, 2, 4, 8, 16
 
@@ -43,7 +44,9 @@ class ModelDesc(C.Structure):
                 ("backends", C.POINTER(C.c_int32)), ("key_table", C.POINTER(C.c_int32)),
                 ("n_cells", C.c_uint32), ("reserved", C.c_uint32),
                 ("cell_d0", C.POINTER(C.c_double)), ("cell_i0", C.POINTER(C.c_int32)),
-                ("n_profiles", C.c_uint32), ("reserved2", C.c_uint32), ("profiles", C.c_void_p)]
+                ("n_profiles", C.c_uint32), ("reserved2", C.c_uint32), ("profiles", C.c_void_p),
+                ("n_sketch_table", C.c_uint32), ("reserved3", C.c_uint32),
+                ("sketch_tables", C.POINTER(C.c_int32))]
 
 
 class RunParams(C.Structure):
@@ -82,7 +85,8 @@ class SinkSample(C.Structure):
 class Outputs(C.Structure):
     _fields_ = [("summaries", C.POINTER(ReplicaSummary)), ("entity_stats", C.POINTER(EntityStats)),
                 ("records", C.POINTER(EventRecord)), ("sink_samples", C.POINTER(SinkSample)),
-                ("service_samples", C.POINTER(C.c_double)), ("histograms", C.POINTER(C.c_uint32))]
+                ("service_samples", C.POINTER(C.c_double)), ("histograms", C.POINTER(C.c_uint32)),
+                ("sketches", C.POINTER(C.c_uint8))]
 
 
 class Totals(C.Structure):

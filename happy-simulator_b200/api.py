@@ -712,6 +712,17 @@ class Simulation:
                 o.by_type = {"Request": o.total} if o.total else {}
             elif k == A.HS_ENT_LB:
                 o._requests_received, o._requests_forwarded = int(row["c0"]), int(row["c1"])
+            elif k == A.HS_ENT_SKETCH:
+                o._events_processed = int(row["c0"])
+                if out.get("sketches") is not None and hasattr(o._sketch, "_load_device_state"):
+                    o._sketch._load_device_state(self.model.sketch_views(out["sketches"])[i][r], int(row["c1"]))
+                elif out.get("sketches") is not None:      # a reference sketch object: fill its own fields
+                    state = self.model.sketch_views(out["sketches"])[i][r]
+                    if hasattr(o._sketch, "_registers"):
+                        o._sketch._registers = [int(x) for x in state]
+                    else:
+                        o._sketch._counters = [[int(x) for x in rowc] for rowc in state]
+                    o._sketch._total_count = int(row["c1"])
 
     def _entity_summaries(self):
         """core/simulation.py:560-591: only objects passed as entities=, events_handled from

@@ -21,6 +21,7 @@
 #include "hs_warp_engine.cuh"
 #include "hs_thread_engine.cuh"
 #include "hs_totals.cuh"
+#include "hs_sketch.h"
 
 struct hs_engine;
 static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, bool want_hash, bool want_rec, bool want_hist, bool per_thread);
@@ -73,7 +74,11 @@ struct hs_engine {
     std::vector<double> cell_d0; std::vector<int32_t> cell_i0;
     std::vector<hs_profile_desc> profiles;
     uint32_t n_cells = 0;
-    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0, d_profiles;
+    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0, d_profiles, d_sketch_tab;
+    std::vector<int32_t> sketch_tab;
+    std::vector<uint64_t> sk_off, sk_moff;      /* hs_sketch_layout of the model */
+    uint64_t sk_total = 0, sk_mtotal = 0;
+    dev_buf d_sketch, d_sketch_merged;
     bool lane_ok = false;
     hs_lane_model lane_model;
 
@@ -118,7 +123,7 @@ static int validate_model(const hs_model_desc *m)
             }
             if (e.i3 == 0 && !(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: source rate must be > 0 (arrival_time_provider.py:75)", i);
             if (e.i0 != HS_ARR_CONSTANT && e.i0 != HS_ARR_POISSON) return fail(HS_ERR_INVALID, "entity %u: bad arrival kind", i);
-            if (e.i1 < 0 || (e.i1 > 0 && (uint32_t)e.i1 != m->key_population)) return fail(HS_ERR_INVALID, "entity %u: key population %d != key_table length %u", i, e.i1, m->key_population);
+            if (e.i1 < 0 || (e.i1 > 0 && m->key_population > 0 && (uint32_t)e.i1 != m->key_population)) return fail(HS_ERR_INVALID, "entity %u: key population %d != key_table length %u", i, e.i1, m->key_population);
             break;
         case HS_ENT_SERVER:
             if (e.target >= (int32_t)n) return fail(HS_ERR_INVALID, "entity %u: downstream out of range", i);
@@ -130,6 +135,30 @@ static int validate_model(const hs_model_desc *m)
             if (e.d0 < 0.0) return fail(HS_ERR_INVALID, "entity %u: negative service time", i);
             break;
         case HS_ENT_SINK: case HS_ENT_COUNTER: break;
+        case HS_ENT_SKETCH: {
+            if (e.i0 != HS_SK_HLL && e.i0 != HS_SK_CMS) return fail(HS_ERR_INVALID, "entity %u: unknown sketch algorithm %d", i, e.i0);
+            if (e.l0 < 1 || e.l0 > INT32_MAX) return fail(HS_ERR_INVALID, "entity %u: sketch key population must be >= 1", i);
+            if (e.i0 == HS_SK_HLL && (e.i2 < 4 || e.i2 > 16)) return fail(HS_ERR_INVALID, "entity %u: precision must be in [4, 16], got %d (hyperloglog.py:101)", i, e.i2);
+            if (e.i0 == HS_SK_CMS && (e.i2 < 1 || e.i3 < 1)) return fail(HS_ERR_INVALID, "entity %u: width and depth must be >= 1 (count_min_sketch.py:88-91)", i);
+            const uint64_t rows = e.i0 == HS_SK_HLL ? 2u : (uint64_t)e.i2;
+            if (e.i1 < 0 || !m->sketch_tables || (uint64_t)e.i1 + rows * (uint64_t)e.l0 > m->n_sketch_table)
+                return fail(HS_ERR_INVALID, "entity %u: sketch table out of range", i);
+            const int32_t *tab = m->sketch_tables + e.i1;
+            for (int64_t k = 0; k < e.l0; ++k) {
+                if (e.i0 == HS_SK_HLL) {
+                    if (tab[k] < 0 || tab[k] >= (1 << e.i2) || tab[e.l0 + k] < 1 || tab[e.l0 + k] > 64 - e.i2 + 1)
+                        return fail(HS_ERR_INVALID, "entity %u: HLL table entry %lld out of range", i, (long long)k);
+                } else {
+                    for (int32_t row = 0; row < e.i2; ++row)
+                        if (tab[(int64_t)row * e.l0 + k] < 0 || tab[(int64_t)row * e.l0 + k] >= e.i3)
+                            return fail(HS_ERR_INVALID, "entity %u: CMS column of key %lld out of range", i, (long long)k);
+                }
+            }
+            for (uint32_t j = 0; j < n; ++j)
+                if (m->entities[j].kind == HS_ENT_SOURCE && m->entities[j].i1 > e.l0)
+                    return fail(HS_ERR_INVALID, "entity %u: a source draws keys from %d values, the sketch table covers %lld", i, m->entities[j].i1, (long long)e.l0);
+            break;
+        }
         case HS_ENT_PROBE: {
             if (e.target < 0 || (uint32_t)e.target >= n) return fail(HS_ERR_INVALID, "entity %u: probe target out of range", i);
             const int tk = m->entities[e.target].kind;
@@ -267,6 +296,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     M.srv_index = (const int32_t *)E->d_srv_index.p;
     M.cell_d0 = (const double *)E->d_cell_d0.p; M.cell_i0 = (const int32_t *)E->d_cell_i0.p;
     M.profiles = (const hs_profile_desc *)E->d_profiles.p;
+    M.sketch_tables = (const int32_t *)E->d_sketch_tab.p; M.sk_total = E->sk_total;
     M.n_entities = ne; M.n_cells = E->n_cells; M.n_servers = n_servers; M.fel_slots = S; M.block_bytes = block_bytes;
     M.n_backends = (uint32_t)E->backends.size(); M.model_bytes = model_bytes;
     hs_warp_run R;
@@ -284,6 +314,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     O.samples = p->sample_cap ? (hs_sink_sample *)E->d_smp.p : nullptr;
     O.service = p->service_cap ? (double *)E->d_svc.p : nullptr;
     O.hist = want_hist ? (uint32_t *)E->d_hist.p : nullptr;
+    O.sketch = (uint8_t *)E->d_sketch.p;
 
     auto launch = [&](auto kern) -> int {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -378,7 +409,8 @@ int hs_engine_destroy(hs_engine *E)
     cudaStreamSynchronize(E->stream);
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
                        &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
-                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_hist, &E->d_cell_totals, &E->d_conts};
+                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_hist, &E->d_cell_totals, &E->d_conts,
+                       &E->d_sketch_tab, &E->d_sketch, &E->d_sketch_merged};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
@@ -413,16 +445,21 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
         }
         return 0;
     };
+    E->sketch_tab.assign(m->sketch_tables, m->sketch_tables + (m->sketch_tables ? m->n_sketch_table : 0));
+    E->sk_off.assign(n, 0); E->sk_moff.assign(n, 0);
+    hs_sketch_layout_impl(m, E->sk_off.data(), E->sk_moff.data(), &E->sk_total, &E->sk_mtotal);
     /* device copy of the entity rows: the reserved d1 carries the server's index among the servers
-     * (= its queue ring), so the kernels get it with the row instead of through a second table */
+     * (= its queue ring) or the SKETCH row's state offset, so the kernels get it with the row */
     std::vector<hs_entity_desc> dev_ents(E->ents);
     {
         int64_t k = 0;
-        for (hs_entity_desc &e : dev_ents) {
-            const int64_t v = (e.kind == HS_ENT_SERVER) ? k++ : -1;
+        for (uint32_t i = 0; i < n; ++i) {
+            hs_entity_desc &e = dev_ents[i];
+            const int64_t v = (e.kind == HS_ENT_SERVER) ? k++ : (e.kind == HS_ENT_SKETCH) ? (int64_t)E->sk_off[i] : -1;
             memcpy(&e.d1, &v, 8);
         }
     }
+    if ((rc = up(E->d_sketch_tab, E->sketch_tab.data(), E->sketch_tab.size() * 4))) return rc;
     if ((rc = up(E->d_ents, dev_ents.data(), n * sizeof(hs_entity_desc)))) return rc;
     if ((rc = up(E->d_backends, E->backends.data(), E->backends.size() * 4))) return rc;
     if ((rc = up(E->d_key_table, E->key_table.data(), E->key_table.size() * 4))) return rc;
@@ -480,6 +517,10 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         if (p->service_cap) CUDA_TRY(cudaMemsetAsync(E->d_svc.p, 0, (size_t)n * p->service_cap * sizeof(double), E->stream));
     }
 
+    if (E->sk_total) {
+        if ((rc = E->d_sketch.ensure((size_t)n * E->sk_total))) return rc;
+        if (!p->resume) CUDA_TRY(cudaMemsetAsync(E->d_sketch.p, 0, (size_t)n * E->sk_total, E->stream));
+    }
     const bool want_hist = (p->flags & HS_RUN_HISTOGRAM) != 0;
     if (p->resume && want_hist != E->hist_on) return fail(HS_ERR_STATE, "resume must keep HS_RUN_HISTOGRAM");
     if (want_hist) {
@@ -606,6 +647,45 @@ int hs_read_outputs(hs_engine *E, const hs_outputs *out)
     if (out->sink_samples && p.sample_cap) CUDA_TRY(cudaMemcpyAsync(out->sink_samples, E->d_smp.p, n * p.sample_cap * sizeof(hs_sink_sample), cudaMemcpyDeviceToHost, E->stream));
     if (out->histograms && E->hist_on) CUDA_TRY(cudaMemcpyAsync(out->histograms, E->d_hist.p, n * HS_HISTOGRAM_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, E->stream));
     if (out->service_samples && p.service_cap) CUDA_TRY(cudaMemcpyAsync(out->service_samples, E->d_svc.p, n * p.service_cap * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    if (out->sketches && E->sk_total) CUDA_TRY(cudaMemcpyAsync(out->sketches, E->d_sketch.p, n * E->sk_total, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    return HS_OK;
+}
+
+int hs_sketch_layout(const hs_model_desc *m, uint64_t *per_replica, uint64_t *merged, uint64_t *total, uint64_t *merged_total)
+{
+    if (!m || !m->entities) return fail(HS_ERR_INVALID, "model is NULL");
+    hs_sketch_layout_impl(m, per_replica, merged, total, merged_total);
+    return HS_OK;
+}
+
+int hs_read_sketches(hs_engine *E, void *merged, uint64_t merged_bytes)
+{
+    if (!E || !merged) return fail(HS_ERR_INVALID, "NULL argument");
+    if (!E->have_run) return fail(HS_ERR_STATE, "no run yet");
+    if (merged_bytes != E->sk_mtotal) return fail(HS_ERR_INVALID, "merged image is %llu bytes, caller passed %llu", (unsigned long long)E->sk_mtotal, (unsigned long long)merged_bytes);
+    if (!E->sk_mtotal) return HS_OK;
+    CUDA_TRY(cudaSetDevice(E->device));
+    int rc;
+    if ((rc = E->d_sketch_merged.ensure(E->sk_mtotal))) return rc;
+    const uint32_t n = E->last.n_replicas;
+    CUDA_TRY(cudaMemsetAsync(E->d_sketch_merged.p, 0, E->sk_mtotal, E->stream));
+    for (size_t i = 0; i < E->ents.size(); ++i) {
+        const hs_entity_desc &e = E->ents[i];
+        if (e.kind != HS_ENT_SKETCH) continue;
+        const uint8_t *src = (const uint8_t *)E->d_sketch.p + E->sk_off[i];
+        uint8_t *dst = (uint8_t *)E->d_sketch_merged.p + E->sk_moff[i];
+        if (e.i0 == HS_SK_HLL) {
+            const uint32_t words = (1u << e.i2) / 4u;
+            hs_sketch_merge_hll_kernel<<<(words + 127) / 128, 128, 0, E->stream>>>(src, E->sk_total, n, words, (uint32_t *)dst);
+        } else {
+            const uint32_t cells = (uint32_t)e.i2 * (uint32_t)e.i3;
+            hs_sketch_merge_cms_kernel<<<(cells + 127) / 128, 128, 0, E->stream>>>(src, E->sk_total, n, cells, (unsigned long long *)dst);
+        }
+        CUDA_TRY(cudaGetLastError());
+        E->launches += 1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(merged, E->d_sketch_merged.p, E->sk_mtotal, cudaMemcpyDeviceToHost, E->stream));
     CUDA_TRY(cudaStreamSynchronize(E->stream));
     return HS_OK;
 }

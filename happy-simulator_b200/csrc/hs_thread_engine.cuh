@@ -269,7 +269,8 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         int kind = (int)(ev.m0 & 0xffu);
         if (kind == (int)HS_EV_REQ_ANY)
             kind = du.d.kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE : du.d.kind == HS_ENT_SINK ? HS_EV_REQ_SINK :
-                   du.d.kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : du.d.kind == HS_ENT_PROBE ? HS_EV_PROBE : HS_EV_REQ_LB;
+                   du.d.kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : du.d.kind == HS_ENT_PROBE ? HS_EV_PROBE :
+                   du.d.kind == HS_ENT_SKETCH ? HS_EV_REQ_SKETCH : HS_EV_REQ_LB;
         const uint32_t srv_idx = (uint32_t)__double_as_longlong(du.d.d1);   /* patched in by the host, see hs_model_upload */
         hdr.now = now;
         if (FLAGS & HS_WF_HASH) hdr.hash = hs_hash_step(hdr.hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
@@ -365,6 +366,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
             case HS_ENT_LB: a.c0 = e->u.lb.received; a.c1 = e->u.lb.forwarded; a.c2 = e->u.lb.in_flight;
                 a.c3 = e->u.lb.responses; break;
+            case HS_ENT_SKETCH: a.c0 = e->u.sk.processed; a.c1 = e->u.sk.added; break;
             }
             O.stats[(size_t)r * ne + i] = a;
         }

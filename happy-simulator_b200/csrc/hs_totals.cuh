@@ -135,4 +135,32 @@ hs_cell_totals_kernel(const hs_replica_summary *__restrict__ summ, const hs_enti
     if (threadIdx.x < HS_HISTOGRAM_BINS) out[c].histogram[threadIdx.x] = shh[threadIdx.x];
 }
 
+/* ---- sketch merge over the replicas of a run (the reference's merge() contracts) ------------
+ * One thread per 4 registers / per counter walks the replicas; neighbouring threads read neighbouring
+ * words of the same replica, so every load instruction is a contiguous segment. */
+
+/* HyperLogLog.merge: element-wise max of the registers (sketching/hyperloglog.py:203-226) */
+__global__ void hs_sketch_merge_hll_kernel(const uint8_t *__restrict__ per_replica, uint64_t stride, uint32_t n_replicas,
+                                           uint32_t n_words, uint32_t *__restrict__ merged)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t acc = 0u;
+    for (uint32_t r = 0; r < n_replicas; ++r)
+        acc = __vmaxu4(acc, *(const uint32_t *)(per_replica + (size_t)r * stride + (size_t)w * 4u));
+    merged[w] = acc;
+}
+
+/* CountMinSketch.merge: element-wise sum of the counters (sketching/count_min_sketch.py:276-301) */
+__global__ void hs_sketch_merge_cms_kernel(const uint8_t *__restrict__ per_replica, uint64_t stride, uint32_t n_replicas,
+                                           uint32_t n_cells, unsigned long long *__restrict__ merged)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    unsigned long long acc = 0ull;
+    for (uint32_t r = 0; r < n_replicas; ++r)
+        acc += *(const uint32_t *)(per_replica + (size_t)r * stride + (size_t)c * 4u);
+    merged[c] = acc;
+}
+
 #endif

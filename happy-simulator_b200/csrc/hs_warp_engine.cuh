@@ -30,6 +30,7 @@
 
 #include "hs_sampler.h"
 #include "hs_profile.h"
+#include "hs_sketch.h"
 #include "../../include/hs_b200.h"
 
 #define HS_WF_HASH 1
@@ -56,6 +57,7 @@ struct __align__(16) hs_went {          /* 96 B per entity */
                  int64_t accepted, dropped, completed, rejected; double total_service; } srv;
         struct { int64_t received; double sum, comp, sumsq, mn, mx; } snk;
         struct { uint64_t rr_index; int64_t received, forwarded, in_flight, responses; } lb;
+        struct { int64_t processed, added; } sk;
         uint64_t raw[8];
     } u;
 };
@@ -73,6 +75,8 @@ struct hs_warp_model {
     const int32_t *backends, *key_table, *srv_index;
     const double *cell_d0; const int32_t *cell_i0;
     const hs_profile_desc *profiles;
+    const int32_t *sketch_tables;   /* per-key hash results of the SKETCH rows                */
+    uint64_t sk_total;              /* bytes of one replica's sketch states                   */
     uint32_t n_entities, n_cells, n_servers, fel_slots;   /* fel_slots = S, multiple of 32 */
     uint32_t block_bytes;           /* bytes of one replica block (multiple of 16)          */
     uint32_t n_backends, model_bytes; /* shared-memory copy of the model tables (per CTA)     */
@@ -97,6 +101,7 @@ struct hs_warp_out {
     hs_sink_sample *samples;
     double *service;
     uint32_t *hist;
+    uint8_t *sketch;                /* [replica][sk_total] */
 };
 
 /* ---- PTX helpers: mbarrier + TMA 1-D bulk copies ------------------------- */
@@ -414,6 +419,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                     a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
                 case HS_ENT_LB: a.c0 = e->u.lb.received; a.c1 = e->u.lb.forwarded; a.c2 = e->u.lb.in_flight;
                     a.c3 = e->u.lb.responses; break;
+                case HS_ENT_SKETCH: a.c0 = e->u.sk.processed; a.c1 = e->u.sk.added; break;
                 }
                 O.stats[(size_t)r * ne + i] = a;
             }

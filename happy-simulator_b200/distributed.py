@@ -130,3 +130,43 @@ def histogram_percentile(hist, p: float) -> float:
     below = cum[k - 1] if k > 0 else 0.0
     frac = (p * total - below) / hist[k] if hist[k] > 0 else 0.0
     return float(edges[k] + frac * (upper[k] - edges[k])) / 1e9
+
+
+def merge_sketch_states(model, raw: np.ndarray) -> dict:
+    """Host restatement of Engine.read_sketches for per-replica states (hs_outputs.sketches of any
+    party): HyperLogLog.merge = register max, CountMinSketch.merge = counter sum over the replicas."""
+    out = {}
+    for i, v in model.sketch_views(raw).items():
+        if int(model.entities["i0"][i]) == A.HS_SK_HLL:
+            out[i] = v.max(axis=0).astype(np.uint8)
+        else:
+            out[i] = v.astype(np.uint64).sum(axis=0)
+    return out
+
+
+def allreduce_sketches(model, merged: dict, device=None, group=None) -> dict:
+    """Cross-GPU merge of the per-rank merged sketches: one MAX all-reduce over the HLL registers and one
+    SUM all-reduce over the CMS counters (the reference's merge() contracts, hyperloglog.py:203-226,
+    count_min_sketch.py:276-301)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return merged
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    ids = sorted(merged)
+    hll = [i for i in ids if int(model.entities["i0"][i]) == A.HS_SK_HLL]
+    cms = [i for i in ids if i not in hll]
+    out = {}
+    if hll:
+        t = torch.from_numpy(np.concatenate([merged[i].astype(np.int32).ravel() for i in hll])).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        a, pos = t.cpu().numpy(), 0
+        for i in hll:
+            out[i] = a[pos: pos + merged[i].size].astype(np.uint8); pos += merged[i].size
+    if cms:
+        t = torch.from_numpy(np.concatenate([merged[i].astype(np.int64).ravel() for i in cms])).to(dev)
+        dist.all_reduce(t, group=group)
+        a, pos = t.cpu().numpy(), 0
+        for i in cms:
+            out[i] = a[pos: pos + merged[i].size].astype(np.uint64).reshape(merged[i].shape); pos += merged[i].size
+    return out

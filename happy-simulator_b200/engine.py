@@ -27,7 +27,8 @@ _lib = None
 
 EXPORTED_SYMBOLS = ["hs_version", "hs_last_error", "hs_engine_create", "hs_engine_destroy", "hs_model_upload",
                     "hs_model_validate", "hs_run", "hs_set_trace", "hs_sync", "hs_last_run_ms", "hs_launch_count",
-                    "hs_read_outputs", "hs_read_totals", "hs_read_cell_totals", "hs_totals_device_ptr"]
+                    "hs_read_outputs", "hs_read_totals", "hs_read_cell_totals", "hs_totals_device_ptr",
+                    "hs_sketch_layout", "hs_read_sketches"]
 
 
 def load_library(path: str | None = None):
@@ -56,6 +57,9 @@ def load_library(path: str | None = None):
         "hs_read_totals": ([H, C.POINTER(A.Totals)], C.c_int),
         "hs_read_cell_totals": ([H, C.POINTER(A.CellTotals), C.c_uint32], C.c_int),
         "hs_totals_device_ptr": ([H, C.POINTER(C.c_void_p)], C.c_int),
+        "hs_sketch_layout": ([C.POINTER(A.ModelDesc), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
+        "hs_read_sketches": ([H, C.c_void_p, C.c_uint64], C.c_int),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)
@@ -173,6 +177,7 @@ class Engine:
             "sink_samples": mk((n, p.sample_cap), A.SAMPLE_DTYPE) if p.sample_cap else None,
             "service_samples": mk((n, p.service_cap), np.float64) if p.service_cap else None,
             "histograms": mk((n, A.HS_HISTOGRAM_BINS), np.uint32) if (p.flags & A.HS_RUN_HISTOGRAM) else None,
+            "sketches": mk((n, self._model.sketch_layout()[2]), np.uint8) if self._model.sketch_layout()[2] else None,
         }
         bufs["_keep"] = keep
         return bufs
@@ -191,8 +196,18 @@ class Engine:
             o.service_samples = bufs["service_samples"].ctypes.data_as(C.POINTER(C.c_double))
         if bufs.get("histograms") is not None:
             o.histograms = bufs["histograms"].ctypes.data_as(C.POINTER(C.c_uint32))
+        if bufs.get("sketches") is not None:
+            o.sketches = bufs["sketches"].ctypes.data_as(C.POINTER(C.c_uint8))
         _check(self._L, self._L.hs_read_outputs(self._h, C.byref(o)))
         return bufs
+
+    def read_sketches(self) -> dict:
+        """The last run's sketches merged over its replicas on the device (HyperLogLog.merge = register
+        max, CountMinSketch.merge = counter sum): {entity id: uint8[2^p] | uint64[depth, width]}."""
+        total = self._model.sketch_layout()[3]
+        img = np.zeros(total, np.uint8)
+        _check(self._L, self._L.hs_read_sketches(self._h, img.ctypes.data_as(C.c_void_p), total))
+        return self._model.merged_sketch_views(img)
 
     def read_totals(self) -> A.Totals:
         t = A.Totals()

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import bisect
 import hashlib
+import struct
 import math
 
 import numpy as np
@@ -55,6 +56,36 @@ def consistent_hash_table(backend_names, virtual_nodes: int, population: int) ->
         hv = int(hashlib.md5(str(k).encode()).hexdigest(), 16)
         j = bisect.bisect_left(hashes, hv)
         tab[k] = ring[j][2] if j < len(ring) else ring[0][2]
+    return tab
+
+
+def hll_table(precision: int, seed: int | None, population: int) -> np.ndarray:
+    """HyperLogLog.add's hashing evaluated once per key (sketching/hyperloglog.py:128-165):
+    h = first 8 bytes (big endian) of sha256(pack(">Q", seed) + repr(k)); register index = h >> (64 - p),
+    run length = leading zeros of the low (64 - p) bits + 1.  -> int32[2, K]."""
+    p = int(precision)
+    seed = 0 if seed is None else int(seed)
+    tab = np.zeros((2, population), np.int32)
+    low_bits = 64 - p
+    for k in range(population):
+        h = int.from_bytes(hashlib.sha256(struct.pack(">Q", seed) + repr(k).encode("utf-8")).digest()[:8], "big")
+        rest = h & ((1 << low_bits) - 1)
+        tab[0, k] = h >> low_bits
+        tab[1, k] = (low_bits - rest.bit_length()) + 1      # all-zero rest: low_bits leading zeros
+    return tab
+
+
+def cms_table(width: int, depth: int, seed: int | None, population: int) -> np.ndarray:
+    """CountMinSketch._hash per (row, key) (sketching/count_min_sketch.py:136-155): row seeds =
+    sha256(pack(">QQ", seed, row))[:8]; column = sha256(pack(">Q", (hash(k) ^ row_seed) & (2^64 - 1)))[:8] % width,
+    with hash(k) == k for the non-negative int keys the device generates.  -> int32[depth, K]."""
+    seed = 0 if seed is None else int(seed)
+    tab = np.zeros((depth, population), np.int32)
+    for row in range(depth):
+        rs = int.from_bytes(hashlib.sha256(struct.pack(">QQ", seed, row)).digest()[:8], "big")
+        for k in range(population):
+            c = (hash(k) ^ rs) & 0xFFFFFFFFFFFFFFFF
+            tab[row, k] = int.from_bytes(hashlib.sha256(struct.pack(">Q", c)).digest()[:8], "big") % width
     return tab
 
 
@@ -140,8 +171,10 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
             return A.HS_ENT_COUNTER
         if hasattr(o, "_strategy") and hasattr(o, "_backends") and hasattr(o, "_in_flight"):
             return A.HS_ENT_LB
+        if hasattr(o, "_sketch") and hasattr(o, "_value_extractor") and hasattr(o, "_events_processed"):
+            return A.HS_ENT_SKETCH
         raise UnsupportedModelError(f"entity {getattr(o, 'name', o)!r} of type {n} cannot be lowered to the device "
-                                    "engine (supported: Source, Server, Sink, Counter, LoadBalancer)")
+                                    "engine (supported: Source, Server, Sink, Counter, LoadBalancer, SketchCollector)")
 
     # discover downstream objects (they may be missing from entities=, as in the reference)
     i = 0
@@ -205,6 +238,27 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
             b.sink(name)
         elif k == A.HS_ENT_COUNTER:
             b.counter(name)
+        elif k == A.HS_ENT_SKETCH:
+            # sketch_collector.py:79-98: value = value_extractor(event); only "the request's routing key"
+            # is a value the device can see
+            if not getattr(o._value_extractor, "routing_key", False):
+                raise UnsupportedModelError(f"sketch collector {name!r}: arbitrary value_extractor callbacks cannot "
+                                            "run on the device (use happysim_b200.KeyExtractor())")
+            if getattr(o, "_weight_extractor", None) is not None:
+                raise UnsupportedModelError(f"sketch collector {name!r}: weight_extractor callbacks")
+            pop = key_population or max((int(getattr(getattr(getattr(s, "_event_provider", None), "_context_fn", None),
+                                                     "key_population", 0)) for s in sources or []), default=0)
+            if pop <= 0:
+                raise UnsupportedModelError(f"sketch collector {name!r}: needs a finite key population")
+            sk = o._sketch
+            if _cls(sk) == "HyperLogLog":
+                b.sketch_hll(name, precision=int(sk._precision), table=hll_table(sk._precision, sk._seed, pop))
+            elif _cls(sk) == "CountMinSketch":
+                b.sketch_cms(name, width=int(sk._width), depth=int(sk._depth),
+                             table=cms_table(sk._width, sk._depth, sk._seed, pop))
+            else:
+                raise UnsupportedModelError(f"sketch collector {name!r}: sketch {_cls(sk)} (supported: HyperLogLog, "
+                                            "CountMinSketch)")
         elif k == A.HS_ENT_LB:
             strat = o._strategy
             backs = [info.backend for info in o._backends.values() if info.is_healthy]

@@ -26,6 +26,7 @@ class FlatModel:
     cell_d0: np.ndarray | None = None         # float64[n_cells, n]
     cell_i0: np.ndarray | None = None         # int32[n_cells, n]
     profiles: np.ndarray = field(default_factory=lambda: np.zeros(0, A.PROFILE_DTYPE))
+    sketch_tables: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
 
     @property
     def n_entities(self) -> int:
@@ -34,6 +35,47 @@ class FlatModel:
     @property
     def n_cells(self) -> int:
         return 0 if self.cell_d0 is None else int(self.cell_d0.shape[0])
+
+    # ---- SKETCH rows: state layout (the rule of csrc/hs_sketch.h, hs_sketch_layout) -------------
+    def sketch_layout(self):
+        """(per-replica offsets, merged offsets, bytes per replica, bytes of the merged image)."""
+        per, mer, a, b = [0] * self.n_entities, [0] * self.n_entities, 0, 0
+        for i in range(self.n_entities):
+            e = self.entities[i]
+            if int(e["kind"]) != A.HS_ENT_SKETCH:
+                continue
+            per[i], mer[i] = a, b
+            if int(e["i0"]) == A.HS_SK_HLL:
+                a += 1 << int(e["i2"]); b += 1 << int(e["i2"])
+            else:
+                cells = int(e["i2"]) * int(e["i3"])
+                a += (cells * 4 + 15) // 16 * 16; b += (cells * 8 + 15) // 16 * 16
+        return per, mer, a, b
+
+    def sketch_views(self, raw: np.ndarray) -> dict:
+        """Per-replica states out of hs_outputs.sketches: {entity id: uint8[n, 2^p] | uint32[n, depth, width]}."""
+        per = self.sketch_layout()[0]
+        out = {}
+        for i in self.ids_of(A.HS_ENT_SKETCH):
+            e = self.entities[i]
+            if int(e["i0"]) == A.HS_SK_HLL:
+                out[i] = raw[:, per[i]: per[i] + (1 << int(e["i2"]))]
+            else:
+                d, w = int(e["i2"]), int(e["i3"])
+                out[i] = np.ascontiguousarray(raw[:, per[i]: per[i] + d * w * 4]).view(np.uint32).reshape(-1, d, w)
+        return out
+
+    def merged_sketch_views(self, img: np.ndarray) -> dict:
+        mer = self.sketch_layout()[1]
+        out = {}
+        for i in self.ids_of(A.HS_ENT_SKETCH):
+            e = self.entities[i]
+            if int(e["i0"]) == A.HS_SK_HLL:
+                out[i] = img[mer[i]: mer[i] + (1 << int(e["i2"]))].copy()
+            else:
+                d, w = int(e["i2"]), int(e["i3"])
+                out[i] = img[mer[i]: mer[i] + d * w * 8].copy().view(np.uint64).reshape(d, w)
+        return out
 
     def ids_of(self, kind: int) -> list[int]:
         return [i for i in range(self.n_entities) if int(self.entities["kind"][i]) == kind]
@@ -65,6 +107,11 @@ class FlatModel:
             d.n_profiles = pr.shape[0]
             d.profiles = pr.ctypes.data
             keep.append(pr)
+        if len(self.sketch_tables):
+            st = np.ascontiguousarray(self.sketch_tables, dtype=np.int32)
+            d.n_sketch_table = st.shape[0]
+            d.sketch_tables = st.ctypes.data_as(C.POINTER(C.c_int32))
+            keep.append(st)
         d._keep = keep
         return d
 
@@ -78,6 +125,7 @@ class ModelBuilder:
         self._backends: list[int] = []
         self._key_table = np.zeros(0, np.int32)
         self._profiles: list[tuple] = []
+        self._sketch_tables: list[np.ndarray] = []
 
     def _add(self, name, kind, target=-1, i0=0, i1=0, i2=0, l0=-1, d0=0.0, i3=0):
         self._rows.append((kind, target, i0, i1, i2, i3, l0, d0, 0.0))
@@ -118,6 +166,24 @@ class ModelBuilder:
         sid = self.source(name, poisson=False, target=pid, profile=("constant", 1.0 / interval_s))
         return sid, pid
 
+    def sketch_hll(self, name="HLL", *, precision, table):
+        """SketchCollector(HyperLogLog(precision, seed)) on the routing key; table = hll_table(precision,
+        seed, K): int32[2, K] (register index, run length) per key."""
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        assert table.ndim == 2 and table.shape[0] == 2
+        off = sum(t.size for t in self._sketch_tables)
+        self._sketch_tables.append(table)
+        return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_HLL, off, int(precision), table.shape[1])
+
+    def sketch_cms(self, name="CMS", *, width, depth, table):
+        """SketchCollector(CountMinSketch(width, depth, seed)) on the routing key; table = cms_table(width,
+        depth, seed, K): int32[depth, K], the column of key k in each row."""
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        assert table.ndim == 2 and table.shape[0] == depth
+        off = sum(t.size for t in self._sketch_tables)
+        self._sketch_tables.append(table)
+        return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_CMS, off, int(depth), table.shape[1], i3=int(width))
+
     def load_balancer(self, name="LB", *, backends, key_table=None):
         off = len(self._backends)
         self._backends += [int(b) for b in backends]
@@ -137,6 +203,8 @@ class ModelBuilder:
                       key_table=self._key_table)
         if self._profiles:
             m.profiles = np.array(self._profiles, dtype=A.PROFILE_DTYPE)
+        if self._sketch_tables:
+            m.sketch_tables = np.concatenate([t.ravel() for t in self._sketch_tables]).astype(np.int32)
         return m
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HS_ABI_VERSION 1u
+#define HS_ABI_VERSION 2u
 
 typedef enum hs_status {
     HS_OK = 0,
@@ -48,9 +48,16 @@ enum {
     HS_ENT_SINK = 3,     /* components/common.py:18 Sink                                            */
     HS_ENT_COUNTER = 4,  /* components/common.py:79 Counter                                         */
     HS_ENT_LB = 5,       /* components/load_balancer/load_balancer.py:60 LoadBalancer               */
-    HS_ENT_PROBE = 6     /* instrumentation/probe.py:81 Probe's measurement callback (the Probe's own
+    HS_ENT_PROBE = 6,    /* instrumentation/probe.py:81 Probe's measurement callback (the Probe's own
                             ticking is a SOURCE row with a constant profile on the general path)     */
+    HS_ENT_SKETCH = 7    /* components/sketching/sketch_collector.py:24 SketchCollector over a HyperLogLog
+                            (sketching/hyperloglog.py:43) or CountMinSketch (count_min_sketch.py:52) whose
+                            value_extractor reads the request's routing key                           */
 };
+/* Sketch algorithms of a SKETCH row.  Both hash the item with SHA-256 (hyperloglog.py:128-135,
+ * count_min_sketch.py:136-155); the items are the routing keys 0..population-1, so the host evaluates
+ * the hashes once per key (hs_model_desc.sketch_tables) and the device only indexes. */
+enum { HS_SK_HLL = 1, HS_SK_CMS = 2 };
 /* Probe metrics (getattr(target, metric), probe.py:55-62). */
 enum { HS_METRIC_DEPTH = 0, HS_METRIC_ACTIVE_REQUESTS = 1, HS_METRIC_UTILIZATION = 2, HS_METRIC_AVAILABLE_CAPACITY = 3,
        HS_METRIC_STATS_ACCEPTED = 4, HS_METRIC_STATS_DROPPED = 5, HS_METRIC_EVENTS_RECEIVED = 6, HS_METRIC_TOTAL = 7,
@@ -74,7 +81,8 @@ enum {
     HS_EV_REQ_SINK = 8,     /* Request -> Sink                       common.py:36                 */
     HS_EV_LB_RESPONSE = 9,  /* _lb_response -> LoadBalancer          load_balancer.py:435         */
     HS_EV_REQ_COUNTER = 10, /* Request -> Counter                    common.py:92                 */
-    HS_EV_PROBE = 11        /* probe_event -> measurement callback   instrumentation/probe.py:51  */
+    HS_EV_PROBE = 11,       /* probe_event -> measurement callback   instrumentation/probe.py:51  */
+    HS_EV_REQ_SKETCH = 12   /* Request -> SketchCollector            sketch_collector.py:79       */
 };
 
 typedef struct hs_entity_desc {
@@ -82,11 +90,13 @@ typedef struct hs_entity_desc {
     int32_t target;    /* SOURCE: entity receiving payloads; SERVER: downstream or -1; PROBE: measured entity */
     int32_t i0;        /* SOURCE: HS_ARR_*; SERVER: concurrency (FixedConcurrency); LB: HS_LB_*; PROBE: HS_METRIC_* */
     int32_t i1;        /* SOURCE: key population (0 = no routing key); SERVER: HS_Q_*;
-                          LB: offset of its backend list in hs_model_desc.backends              */
-    int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends                              */
+                          LB: offset of its backend list in hs_model_desc.backends;
+                          SKETCH: offset of its table in hs_model_desc.sketch_tables            */
+    int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends; SKETCH: HLL precision p | CMS depth   */
     int32_t i3;        /* SOURCE: 0 = ConstantRateProfile(d0); k > 0 = profiles[k - 1] (non-constant
-                          rate profile, general arrival path); others: reserved, 0              */
-    int64_t l0;        /* SOURCE: stop_after in ns or -1; SERVER: queue capacity or -1 (= inf)  */
+                          rate profile, general arrival path); SKETCH: CMS width; others: reserved, 0 */
+    int64_t l0;        /* SOURCE: stop_after in ns or -1; SERVER: queue capacity or -1 (= inf);
+                          SKETCH: key population K = row stride of its table in sketch_tables     */
     double d0;         /* SOURCE: rate (events/s); SERVER: mean / constant service time (s)     */
     double d1;         /* reserved, 0                                                           */
 } hs_entity_desc;      /* 48 bytes */
@@ -110,6 +120,13 @@ typedef struct hs_model_desc {
     uint32_t n_profiles;
     uint32_t reserved2;
     const struct hs_profile_desc *profiles;   /* 40 bytes each, see below */
+    /* Per-key hash results of the SKETCH rows (row i0/i1/i2/i3/l0: algorithm, table offset, p | depth,
+     * CMS width, K).  HLL: [2][K] = register index (hash >> (64 - p)) and run length (leading zeros of
+     * the remaining bits + 1) of key k, hyperloglog.py:156-165.  CMS: [depth][K] = column of key k in
+     * each row, count_min_sketch.py:145-155. */
+    uint32_t n_sketch_table;       /* total length of sketch_tables[]                          */
+    uint32_t reserved3;
+    const int32_t *sketch_tables;
 } hs_model_desc;
 
 enum { HS_PROF_CONSTANT = 0, HS_PROF_LINEAR_RAMP = 1, HS_PROF_SPIKE = 2 };
@@ -178,8 +195,10 @@ typedef struct hs_replica_summary {
 
 typedef struct hs_entity_stats {
     int64_t c0; /* SOURCE generated_count | SERVER stats_accepted | SINK events_received
-                   | COUNTER total | LB requests_received | PROBE samples taken               */
-    int64_t c1; /* SOURCE payloads created | SERVER stats_dropped | LB requests_forwarded       */
+                   | COUNTER total | LB requests_received | PROBE samples taken
+                   | SKETCH events_processed                                                   */
+    int64_t c1; /* SOURCE payloads created | SERVER stats_dropped | LB requests_forwarded
+                   | SKETCH item_count (requests that carried a key)                           */
     int64_t c2; /* SERVER requests_completed | LB in-flight entries left                        */
     int64_t c3; /* SERVER requests_rejected | SERVER (after run) -- ; LB responses handled      */
     double f0;  /* SERVER total_service_time (sequential +=) | SINK sum(latencies_s) as CPython's
@@ -209,6 +228,8 @@ typedef struct hs_outputs {        /* caller-owned HOST buffers; any pointer may
     hs_sink_sample *sink_samples;  /* [n_replicas][sample_cap], all sinks, arrival order       */
     double *service_samples;       /* [n_replicas][service_cap], service-start order           */
     uint32_t *histograms;          /* [n_replicas][HS_HISTOGRAM_BINS] (HS_RUN_HISTOGRAM)        */
+    uint8_t *sketches;             /* [n_replicas][hs_sketch_layout().total]: every SKETCH row's state,
+                                      HLL: uint8 registers[2^p]; CMS: uint32 counters[depth][width] */
 } hs_outputs;
 
 /* Ensemble totals: what the single end-of-run NCCL allreduce carries.
@@ -257,6 +278,15 @@ int hs_model_upload(hs_engine *e, const hs_model_desc *model);
 /* Validate a model without a device (used by host-side tests). */
 int hs_model_validate(const hs_model_desc *model);
 
+/* Byte offsets of the SKETCH rows' state.  per_replica[i] / merged[i] = offset of entity i's state in
+ * one replica's slice of hs_outputs.sketches / in the merged image (0 for other kinds); a replica's
+ * slice is *total bytes, the merged image *merged_total.  The merged image applies the reference's
+ * merge() contracts over the replicas of a run: HLL registers -> element-wise max (hyperloglog.py:
+ * 203-226), uint8[2^p]; CMS counters -> element-wise sum (count_min_sketch.py:276-301), widened to
+ * uint64[depth][width].  Needs no device. */
+int hs_sketch_layout(const hs_model_desc *model, uint64_t *per_replica, uint64_t *merged,
+                     uint64_t *total, uint64_t *merged_total);
+
 /* Externally supplied draws ("stock generator" mode).  The reference draws arrival target
  * areas as -log(1 - numpy.random.random()) (load/providers/poisson_arrival.py:31) and service
  * samples as random.expovariate(lambda) (distributions/exponential.py:43) from two process-global
@@ -297,6 +327,10 @@ int hs_read_totals(hs_engine *e, hs_totals *out);
 /* Reduce the last run's replicas per sweep cell (cell = global replica index /
  * replicas_per_cell, modulo n_cells) on the device and copy out[0..n_cells) to the host. */
 int hs_read_cell_totals(hs_engine *e, hs_cell_totals *out, uint32_t n_cells);
+
+/* Merge the last run's per-replica sketches on the device (layout: hs_sketch_layout's merged image)
+ * and copy the image to the host; what a multi-GPU run all-reduces (max for HLL bytes, sum for CMS). */
+int hs_read_sketches(hs_engine *e, void *merged, uint64_t merged_bytes);
 
 /* Device pointer/size of the last run's totals (for the NCCL allreduce done by
  * the host layer on torch.distributed; layout = hs_totals). */

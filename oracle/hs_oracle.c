@@ -33,6 +33,9 @@
  *   LoadBalancer        happysimulator/components/load_balancer/load_balancer.py:347-473,
  *                       strategies.py:61-68 (RoundRobin), :411-433 (ConsistentHash.select,
  *                       as a host-precomputed key -> backend table)
+ *   SketchCollector     happysimulator/components/sketching/sketch_collector.py:79-98 over
+ *                       sketching/hyperloglog.py:137-165 / count_min_sketch.py:168-187 (add), with the
+ *                       per-key SHA-256 results precomputed on the host (csrc/hs_sketch.h)
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -43,6 +46,7 @@
 #include "../include/hs_b200.h"
 #include "../happy-simulator_b200/csrc/hs_sampler.h"
 #include "../happy-simulator_b200/csrc/hs_profile.h"
+#include "../happy-simulator_b200/csrc/hs_sketch.h"
 
 /* ---- one pending Event object ------------------------------------------ */
 typedef struct oev {
@@ -138,6 +142,9 @@ typedef struct oent {
     uint64_t rr_index;       /* RoundRobin._index                                 */
     int64_t lb_received, lb_forwarded, lb_in_flight, lb_responses;
     uint32_t lb_next_request_id;
+    /* SKETCH */
+    int64_t sk_processed, sk_added;   /* SketchCollector._events_processed, sketch._total_count */
+    uint8_t *sk_state;                /* this replica's registers / counters (in hs_outputs.sketches) */
 } oent;
 
 typedef struct orun {
@@ -203,6 +210,7 @@ static int request_kind_for(const orun *R, int ent)
     case HS_ENT_COUNTER: return HS_EV_REQ_COUNTER;
     case HS_ENT_LB: return HS_EV_REQ_LB;
     case HS_ENT_PROBE: return HS_EV_PROBE;
+    case HS_ENT_SKETCH: return HS_EV_REQ_SKETCH;
     default: return -1;
     }
 }
@@ -423,6 +431,15 @@ static void handle(orun *R, oev *e)
         E->received++;
         run_request_hooks(R, e);
         break;
+    case HS_EV_REQ_SKETCH:                /* SketchCollector.handle_event, sketch_collector.py:79-98 */
+        if (e->key >= 0) {                /* value is not None: sketch.add(value) */
+            if (E->sk_state)
+                hs_sketch_add(E->sk_state, R->m->sketch_tables + E->d.i1, E->d.i0, E->d.i2, E->d.i3, E->d.l0, e->key);
+            E->sk_added++;
+        }
+        E->sk_processed++;
+        run_request_hooks(R, e);
+        break;
     case HS_EV_LB_RESPONSE:               /* LoadBalancer._handle_response, :435-473 */
         if (E->lb_in_flight > 0) E->lb_in_flight--;
         E->lb_responses++;
@@ -454,6 +471,17 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
         if (m->n_cells && m->cell_i0) E->d.i0 = m->cell_i0[(size_t)cell * ne + i];
         E->mn = INFINITY; E->mx = -INFINITY;
         if (E->d.kind == HS_ENT_SERVER && E->d.i2 == HS_SVC_EXPONENTIAL) E->lambda = 1.0 / E->d.d0;
+    }
+    {   /* SKETCH rows: state lives in the caller's buffer (zeroed here), hs_sketch_layout */
+        uint64_t total = 0;
+        uint64_t *off = (uint64_t *)calloc(ne, sizeof(uint64_t));
+        hs_sketch_layout_impl(m, off, NULL, &total, NULL);
+        if (out->sketches && total) {
+            uint8_t *base = out->sketches + (size_t)r * total;
+            memset(base, 0, total);
+            for (uint32_t i = 0; i < ne; ++i) if (R.ents[i].d.kind == HS_ENT_SKETCH) R.ents[i].sk_state = base + off[i];
+        }
+        free(off);
     }
     if (out->records) R.rec = out->records + (size_t)r * p->record_cap;
     if (out->sink_samples) R.smp = out->sink_samples + (size_t)r * p->sample_cap;
@@ -526,6 +554,7 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
             case HS_ENT_COUNTER: st->c0 = E->received; break;
             case HS_ENT_PROBE:
                 st->c0 = E->received; st->f0 = hs_neumaier_result(E->sum, E->comp); st->f2 = E->mn; st->f3 = E->mx; break;
+            case HS_ENT_SKETCH: st->c0 = E->sk_processed; st->c1 = E->sk_added; break;
             case HS_ENT_LB:
                 st->c0 = E->lb_received; st->c1 = E->lb_forwarded; st->c2 = E->lb_in_flight; st->c3 = E->lb_responses; break;
             }
@@ -562,6 +591,13 @@ int hs_oracle_run_trace(const hs_model_desc *m, const hs_run_params *p, const hs
     if (!m || !p || !out || m->abi_version != HS_ABI_VERSION || p->n_replicas != 1) return HS_ERR_INVALID;
     otrace tr = { targets, n_targets, service, n_service };
     run_replica(m, p, 0, out, &tr);
+    return HS_OK;
+}
+
+int hs_sketch_layout(const hs_model_desc *m, uint64_t *per_replica, uint64_t *merged, uint64_t *total, uint64_t *merged_total)
+{
+    if (!m || !m->entities) return HS_ERR_INVALID;
+    hs_sketch_layout_impl(m, per_replica, merged, total, merged_total);
     return HS_OK;
 }
 

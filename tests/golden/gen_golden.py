@@ -126,6 +126,31 @@ def reorder_sources_first(m):
     return m
 
 
+def sketch_direct(K=200, precision=8, hll_seed=5):
+    """Source with client ids -> SketchCollector(HyperLogLog)."""
+    b = hs.ModelBuilder()
+    src = b.source(rate=300.0, key_population=K)
+    h = b.sketch_hll("uniques", precision=precision, table=hs.hll_table(precision, hll_seed, K))
+    b.set_target(src, h)
+    return b.build(), {h: hll_seed}
+
+
+def sketch_farm(K=40, n_servers=4, width=16, depth=3, cms_seed=9, hll_seed=None):
+    """Source -> LoadBalancer(RoundRobin) -> servers -> SketchCollector(CountMinSketch); a second source
+    without keys feeds a HyperLogLog collector directly (value None: counted, not added)."""
+    b = hs.ModelBuilder()
+    src = b.source("Keyed", rate=64.0, key_population=K)
+    plain = b.source("Plain", rate=5.0, poisson=False)
+    servers = [b.server(f"S{i}", mean_service_s=0.05) for i in range(n_servers)]
+    cms = b.sketch_cms("freq", width=width, depth=depth, table=hs.cms_table(width, depth, cms_seed, K))
+    hll = b.sketch_hll("nokeys", precision=4, table=hs.hll_table(4, hll_seed, K))
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb); b.set_target(plain, hll)
+    for sv in servers:
+        b.set_target(sv, cms)
+    return b.build(), {cms: cms_seed, hll: hll_seed}
+
+
 def philox_cases():
     c = {}
     c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
@@ -150,6 +175,11 @@ def philox_cases():
     c["ramp_down_constant"] = (profiled(("linear_ramp", 5.0, 20.0, 1.0), False), dict(seed=0, rid=0, end_s=20))
     c["probe_mm1"] = (probed(), dict(seed=42, rid=0, end_s=20))
     c["spike_constant_lb4"] = (profiled(("spike", 10.0, 100.0, 2.0, 1.0), False, lb=4), dict(seed=3, rid=1, end_s=6))
+    # sketches as instrumentation sinks
+    m, seeds = sketch_direct()
+    c["sketch_hll_direct"] = (m, dict(seed=17, rid=3, end_s=2, sketch_seeds=seeds))
+    m, seeds = sketch_farm()
+    c["sketch_cms_farm"] = (m, dict(seed=19, rid=1, end_s=6, sketch_seeds=seeds))
     return c
 
 
@@ -163,14 +193,20 @@ def save_case(path, model, ref, meta):
         n_records=np.int64(len(rec)), records=rec[:MAX_REC],
         n_samples=np.int64(len(ref["sink_samples"])), sink_samples=ref["sink_samples"][:MAX_SMP],
         n_service=np.int64(len(ref["service_samples"])), service_samples=ref["service_samples"][:MAX_SMP],
+        sketch_tables=model.sketch_tables, sketch_state=ref.get("sketches", np.zeros(0, np.uint8)),
+        **{f"sketch_answer_{i}": a for i, a in ref.get("sketch_answers", {}).items()},
+        **{f"sketch_seed_{i}": np.int64(-1 if sd is None else sd) for i, sd in (meta.get("sketch_seeds") or {}).items()},
         **{k: v for k, v in meta.items() if isinstance(v, np.ndarray)},
     )
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""          # e.g. "sketch": regenerate matching cases only
     for name, (model, kw) in philox_cases().items():
+        if only not in name:
+            continue
         ref = RH.run_reference(model, seed=kw["seed"], rid=kw["rid"], end_ns=int(kw["end_s"] * 1e9),
-                               chash_vnodes=kw.get("chash_vnodes"))
+                               chash_vnodes=kw.get("chash_vnodes"), sketch_seeds=kw.get("sketch_seeds"))
         save_case(os.path.join(HERE, f"philox_{name}.npz"), model, ref, kw)
         print(f"philox_{name}: {len(ref['records'])} events, hash {int(ref['summaries']['order_hash'][0]):#x}")
 
@@ -180,6 +216,8 @@ def main():
              ("lb_rr8_seed5", hs.lb_round_robin(n_servers=8, rate=64.0), 5, 8),
              ("mmc4_seed9", hs.mm1(rate=32, concurrency=4), 9, 20)]
     for sname, model, seed, end_s in stock:
+        if only not in "stock_" + sname:
+            continue
         ref = RH.run_reference(model, seed=seed, end_ns=int(end_s * 1e9), stock_rng=True)
         n_draw = len(ref["records"])
         u = np.random.RandomState(seed).random_sample(n_draw)          # numpy legacy global stream

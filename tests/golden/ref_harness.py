@@ -31,7 +31,7 @@ def _import_reference():
 
 
 def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, stock_rng=False,
-                  max_records=None):
+                  max_records=None, sketch_seeds=None):
     """Run the reference on ``model`` (a happysim_b200.FlatModel); replica word ``rid``.
 
     stock_rng=True leaves the reference's own MT19937 streams in place (seeded
@@ -61,6 +61,9 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     from happysimulator.load.source_event import SourceEvent
     from happysimulator.instrumentation.probe import Probe
     from happysimulator.instrumentation.data import Data
+    from happysimulator.components.sketching.sketch_collector import SketchCollector
+    from happysimulator.sketching.hyperloglog import HyperLogLog
+    from happysimulator.sketching.count_min_sketch import CountMinSketch
 
     L = O.lib()
     ents = model.entities
@@ -96,6 +99,16 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             objs[i] = Sink(names[i])
         elif k == A.HS_ENT_COUNTER:
             objs[i] = Counter(names[i])
+        elif k == A.HS_ENT_SKETCH:
+            e = ents[i]
+            sk_seed = (sketch_seeds or {}).get(i)
+            if int(e["i0"]) == A.HS_SK_HLL:
+                sk = HyperLogLog(precision=int(e["i2"]), seed=sk_seed)
+            else:
+                sk = CountMinSketch(width=int(e["i3"]), depth=int(e["i2"]), seed=sk_seed)
+            # the reference idiom for "the request's client id" (sketch_collector.py:36-41)
+            objs[i] = SketchCollector(names[i], sketch=sk,
+                                      value_extractor=lambda ev: ev.context.get("metadata", {}).get("client_id"))
     for i in range(n):
         if int(ents["kind"][i]) != A.HS_ENT_SERVER:
             continue
@@ -213,6 +226,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             return A.HS_EV_REQ_COUNTER
         if isinstance(t, LoadBalancer):
             return A.HS_EV_REQ_LB
+        if isinstance(t, SketchCollector):
+            return A.HS_EV_REQ_SKETCH
         raise AssertionError(f"unclassified event {ev!r}")
 
     data_to_row = {id(d): row for row, d in probe_data.items()}
@@ -277,6 +292,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             sink_samples.append((i, [t.nanoseconds for t in o.completion_times], list(o.latencies_s)))
         elif k == A.HS_ENT_COUNTER:
             stats[i]["c0"] = o.total
+        elif k == A.HS_ENT_SKETCH:
+            stats[i]["c0"], stats[i]["c1"] = o.events_processed, o.sketch.item_count
         elif k == A.HS_ENT_LB:
             s = o.stats
             stats[i]["c0"], stats[i]["c1"], stats[i]["c2"] = s.requests_received, s.requests_forwarded, len(o._in_flight)
@@ -309,6 +326,29 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         "service_samples": np.array(svc_merged, dtype=np.float64), "objects": objs, "sim": sim,
         "summary": summary,
     }
+    # SKETCH rows: the reference sketch objects' own state, laid out like hs_outputs.sketches
+    per, _, total, _ = model.sketch_layout()
+    if total:
+        img = np.zeros(total, np.uint8)
+        for i, o in enumerate(objs):
+            if int(ents["kind"][i]) != A.HS_ENT_SKETCH:
+                continue
+            if int(ents["i0"][i]) == A.HS_SK_HLL:
+                img[per[i]: per[i] + len(o.sketch._registers)] = np.array(o.sketch._registers, dtype=np.uint8)
+            else:
+                c = np.array(o.sketch._counters, dtype=np.uint32).ravel()
+                img[per[i]: per[i] + c.size * 4] = c.view(np.uint8)
+        out["sketches"] = img
+        # the reference's own answers off those states (hyperloglog.py:167, count_min_sketch.py:189)
+        ans = {}
+        for i, o in enumerate(objs):
+            if int(ents["kind"][i]) != A.HS_ENT_SKETCH:
+                continue
+            if int(ents["i0"][i]) == A.HS_SK_HLL:
+                ans[i] = np.array([o.sketch.cardinality()], dtype=np.int64)
+            else:
+                ans[i] = np.array([o.sketch.estimate(k) for k in range(int(ents["l0"][i]))], dtype=np.int64)
+        out["sketch_answers"] = ans
     if max_records is not None:
         out["records"] = rec[:max_records]
     return out

@@ -19,6 +19,8 @@ def load(name):
                          key_table=z["key_table"])
     if "profiles" in z.files and len(z["profiles"]):
         model.profiles = z["profiles"]
+    if "sketch_tables" in z.files and len(z["sketch_tables"]):
+        model.sketch_tables = z["sketch_tables"]
     seed, rid, end_ns = (int(v) for v in z["meta"])
     return model, dict(seed=seed, rid_base=rid, end_ns=end_ns), z
 
@@ -43,3 +45,5 @@ def check_against(z, got, r=0):
     n = len(z["service_samples"])
     if n:
         assert got["service_samples"][r][:n].tobytes() == z["service_samples"].tobytes(), "service samples differ"
+    if "sketch_state" in z.files and len(z["sketch_state"]):
+        assert got["sketches"][r].tobytes() == z["sketch_state"].tobytes(), "sketch registers / counters differ"

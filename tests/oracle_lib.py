@@ -47,6 +47,8 @@ def lib():
         L.hs_cpu_integrate_rate.restype = C.c_double
         L.hs_cpu_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
         L.hs_cpu_philox.restype = None
+        L.hs_sketch_layout.argtypes = [C.POINTER(A.ModelDesc)] + [C.POINTER(C.c_uint64)] * 4
+        L.hs_sketch_layout.restype = C.c_int
         _lib = L
     return _lib
 
@@ -66,7 +68,7 @@ def make_params(*, seed=1234, end_ns, n_replicas=1, seed_stride=0, rid_base=0, r
     return p
 
 
-def alloc_outputs(n_entities: int, p: A.RunParams):
+def alloc_outputs(n_entities: int, p: A.RunParams, sketch_bytes: int = 0):
     """Host buffers (numpy) + the hs_outputs struct pointing at them."""
     n = p.n_replicas
     bufs = {
@@ -76,6 +78,7 @@ def alloc_outputs(n_entities: int, p: A.RunParams):
         "sink_samples": np.zeros((n, p.sample_cap), A.SAMPLE_DTYPE) if p.sample_cap else None,
         "service_samples": np.zeros((n, p.service_cap), np.float64) if p.service_cap else None,
         "histograms": np.zeros((n, A.HS_HISTOGRAM_BINS), np.uint32) if (p.flags & A.HS_RUN_HISTOGRAM) else None,
+        "sketches": np.zeros((n, sketch_bytes), np.uint8) if sketch_bytes else None,
     }
     o = A.Outputs()
     o.summaries = bufs["summaries"].ctypes.data_as(C.POINTER(A.ReplicaSummary))
@@ -88,12 +91,14 @@ def alloc_outputs(n_entities: int, p: A.RunParams):
         o.service_samples = bufs["service_samples"].ctypes.data_as(C.POINTER(C.c_double))
     if bufs["histograms"] is not None:
         o.histograms = bufs["histograms"].ctypes.data_as(C.POINTER(C.c_uint32))
+    if bufs["sketches"] is not None:
+        o.sketches = bufs["sketches"].ctypes.data_as(C.POINTER(C.c_uint8))
     return bufs, o
 
 
 def oracle_run(model: happysim_b200.FlatModel, p: A.RunParams, r0=None, r1=None):
     d = model.desc()
-    bufs, o = alloc_outputs(model.n_entities, p)
+    bufs, o = alloc_outputs(model.n_entities, p, model.sketch_layout()[2])
     if r0 is None:
         rc = lib().hs_oracle_run(C.byref(d), C.byref(p), C.byref(o))
     else:

@@ -63,3 +63,43 @@ def test_two_rank_allreduce_equals_single_process():
         # global replica ids: a shard reproduces exactly its slice of the whole ensemble
         assert hashes == whole["summaries"]["order_hash"][lo:hi].tolist()
     assert got[0][1] == 0 and got[0][2] == got[1][1] and got[1][2] == n_total
+
+
+def _sketch_worker(rank, world, port, n_total, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    from happysim_b200 import distributed as D
+    import golden_lib as G
+    import oracle_lib as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model, kw, _ = G.load("philox_sketch_cms_farm")
+    lo, hi = D.shard_range(n_total, rank, world)
+    out = O.oracle_run(model, O.make_params(seed=kw["seed"], end_ns=kw["end_ns"], n_replicas=hi - lo, replica_index_base=lo))
+    merged = D.allreduce_sketches(model, D.merge_sketch_states(model, out["sketches"]))
+    q.put((rank, {i: v.tolist() for i, v in merged.items()}))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sketch_merge_equals_single_process():
+    """SKETCH rows across ranks: one MAX all-reduce (HLL registers) + one SUM all-reduce (CMS counters)
+    of the per-rank merged images == the merge over the whole ensemble."""
+    from happysim_b200 import distributed as D
+    import golden_lib as G
+    import oracle_lib as O
+    n_total, world, port = 9, 2, 31000 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sketch_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    model, kw, _ = G.load("philox_sketch_cms_farm")
+    whole = O.oracle_run(model, O.make_params(seed=kw["seed"], end_ns=kw["end_ns"], n_replicas=n_total))
+    want = D.merge_sketch_states(model, whole["sketches"])
+    for rank, merged in got:
+        assert set(merged) == set(want)
+        for i in want:
+            assert np.array_equal(np.asarray(merged[i], dtype=np.uint64), want[i].astype(np.uint64))

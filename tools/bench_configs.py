@@ -35,5 +35,16 @@ if __name__ == "__main__":
         for rpw in rpws:
             run("configs[3] chash1024 thread", hs.lb_key_table(tab, 1024, rate=8192.0), n, 2.0, rpw=rpw, engine=3)
     run("configs[3] chash 1024 nodes, warp", hs.lb_key_table(tab, 1024, rate=8192.0), 1024, 2.0, engine=1)
+    K = 10000
+    b = hs.ModelBuilder()
+    src = b.source(rate=512.0, key_population=K)
+    servers = [b.server(f"S{i}", mean_service_s=0.1) for i in range(64)]
+    hll = b.sketch_hll("uniques", precision=12, table=hs.hll_table(12, 1, K))
+    cms = b.sketch_cms("freq", width=272, depth=5, table=hs.cms_table(272, 5, 2, K))
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb)
+    for k, sv in enumerate(servers):
+        b.set_target(sv, hll if k % 2 else cms)
+    run("lb-rr64 -> HLL(p=12) | CMS(272x5) sinks", b.build(), 16384, 10.0, engine=3)
     m = hs.mmc_sweep()
     run("configs[4] M/M/c sweep 256 cells", m, 32768, 100.0, replicas_per_cell=128, queue_ring=4096)

@@ -169,7 +169,9 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     __shared__ int64_t sh_t[HS_DRAW_BUF][HS_LANE_THREADS];       /* arrival times A_k (ns)          */
     __shared__ double sh_svc[HS_DRAW_BUF][HS_LANE_THREADS];      /* service: Duration.to_seconds()  */
     /* recorder staging: [slot][lane] so that lanes at different slots never conflict; full
-     * 128-byte groups are written to HBM cooperatively at the converged top of the loop */
+     * 128-byte groups are written to HBM cooperatively at the converged top of the loop.  (The flush
+     * reads one lane's 8 slots with 8 lanes, an 8-way bank conflict; padding the rows removes it but
+     * makes the per-event writes conflict instead -- measured neutral, so the simple layout stays.) */
     __shared__ __align__(16) uint4 sh_rec[STAGE_ROWS][HS_LANE_THREADS];
     __shared__ uint4 sh_flush[HS_LANE_THREADS / 32][(FLAGS & HS_LF_REC) ? 32 : 1];   /* {tid, stage pos, ring pos, -} per flushing lane */
     __shared__ __align__(16) hs_ring_entry sh_head[HS_LANE_THREADS];  /* next item to deliver      */
@@ -487,9 +489,16 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                               (processed + 8 > P.max_events);   /* a chain is <= 6 events: single-step near the limit */
             if (!slow) {
                 now = tn;
+                /* Recorder kernels emit the chain's first event and the common tail DELIVER -> WORKER ->
+                 * service start once for both chains, so that the lanes of both run that code together
+                 * (+6 % in record mode); without the record stores the shared tail only adds a
+                 * reconvergence point (-5 % in summary mode), so those kernels keep the chains apart. */
+                constexpr bool MERGED = (FLAGS & HS_LF_REC) != 0;
+                if (MERGED) HS_EMIT(pickC ? HS_EV_CONTINUATION : HS_EV_SOURCE_TICK, pickC ? iC : iT, pickC ? M.srv_id : M.src_id);
+                bool start = false; int64_t start_created = 0; uint64_t worker_idx = 0;
                 if (!pickC) {
                     /* ===== fused arrival chain ================================== */
-                    HS_EMIT(HS_EV_SOURCE_TICK, iT, M.src_id);
+                    if (!MERGED) HS_EMIT(HS_EV_SOURCE_TICK, iT, M.src_id);
                     const bool payload = !(stop_after >= 0 && now > stop_after);  /* source.py:68 */
                     uint64_t idxP = 0;
                     if (payload) idxP = ctr++; else S->skipped++;
@@ -517,14 +526,18 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                      * the item is pushed and popped again at once (FIFO and LIFO agree).          */
                     HS_RECORD(HS_EV_NOTIFY, ctr, M.srv_id);
                     HS_RECORD(HS_EV_POLL, ctr + 1, M.srv_id);
-                    HS_RECORD(HS_EV_DELIVER, ctr + 2, M.srv_id);
-                    HS_RECORD(HS_EV_REQ_WORKER, idxP, M.srv_id);
-                    ctr += 3; processed += 4;
-                    HS_SERVICE_START(now);
-                    continue;
+                    ctr += 2; processed += 2;
+                    if (MERGED) { start = true; start_created = now; worker_idx = idxP; }
+                    else {
+                        HS_RECORD(HS_EV_DELIVER, ctr, M.srv_id);
+                        HS_RECORD(HS_EV_REQ_WORKER, idxP, M.srv_id);
+                        ctr += 1; processed += 2;
+                        HS_SERVICE_START(now);
+                        continue;
+                    }
                 } else {
                     /* ===== fused completion chain =============================== */
-                    HS_EMIT(HS_EV_CONTINUATION, iC, M.srv_id);
+                    if (!MERGED) HS_EMIT(HS_EV_CONTINUATION, iC, M.srv_id);
                     total_service = HS_ADD(total_service, svc_s);
                     const int64_t done_created = c_created;
                     HS_C_POP();                                /* release + promote the next continuation */
@@ -543,14 +556,24 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     if (!poll) continue;
                     HS_EMIT(HS_EV_POLL, idxPoll, M.srv_id);
                     if (q_len == 0) continue;                  /* Queue._handle_poll: empty */
-                    int64_t it_created; uint64_t it_idx;
-                    HS_Q_POP(it_created, it_idx);
-                    HS_RECORD(HS_EV_DELIVER, ctr, M.srv_id);
-                    HS_RECORD(HS_EV_REQ_WORKER, it_idx, M.srv_id);
-                    ctr += 1; processed += 2;
-                    HS_SERVICE_START(it_created);
-                    continue;
+                    uint64_t it_idx;
+                    HS_Q_POP(start_created, it_idx);
+                    if (MERGED) { start = true; worker_idx = it_idx; }
+                    else {
+                        HS_RECORD(HS_EV_DELIVER, ctr, M.srv_id);
+                        HS_RECORD(HS_EV_REQ_WORKER, it_idx, M.srv_id);
+                        ctr += 1; processed += 2;
+                        HS_SERVICE_START(start_created);
+                        continue;
+                    }
                 }
+                if (MERGED && start) {
+                    HS_RECORD(HS_EV_DELIVER, ctr, M.srv_id);
+                    HS_RECORD(HS_EV_REQ_WORKER, worker_idx, M.srv_id);
+                    ctr += 1; processed += 2;
+                    HS_SERVICE_START(start_created);
+                }
+                continue;
             }
         }
 

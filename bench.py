@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-mode", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     return ap.parse_args()
 
 
@@ -354,6 +355,34 @@ def main():
            "steps": e2e_steps, "what": "hs_model_upload + hs_run(first window, fresh) + hs_read_outputs(summaries, "
                                        "entity stats -> pinned host) per step, wall clock"}
 
+    # ---- the other BASELINE configs (parity-test cases, not bench lines): device throughput for context
+    others = None
+    if world == 1 and not a.no_other_configs:
+        others = {}
+        def ctx(name, mdl, replicas, sim_s, what, **kw):
+            e2 = engine.Engine(local, stream=stream.cuda_stream)
+            e2.upload(mdl)
+            best = None
+            for _ in range(2):
+                e2.run(engine.make_params(seed=a.seed, end_ns=int(sim_s * 1e9), n_replicas=replicas, flags=0, **kw))
+                e2.sync()
+                best = e2.last_run_ms() if best is None else min(best, e2.last_run_ms())
+            o = e2.read_outputs()
+            ev = int(o["summaries"]["events_processed"].sum())
+            others[name] = {"value": ev / (best * 1e-3), "unit": UNIT, "replicas": replicas, "sim_seconds": sim_s,
+                            "device_ms": best, "replicas_flagged": int((o["summaries"]["status"] != 0).sum()),
+                            "what": what}
+            e2.close()
+        ctx("configs[2]", hs.lb_round_robin(64, 512.0), 16384, 10.0,
+            "Source(512/s) -> LoadBalancer(RoundRobin) -> 64 x Server -> Sink; thread engine; 10 s slice of the 100 s run")
+        tab = hs.consistent_hash_table([f"S{i}" for i in range(1024)], 100, 10000)
+        ctx("configs[3]", hs.lb_key_table(tab, 1024, rate=8192.0), 1024, 2.0,
+            "Source(8192/s, 10000 client ids) -> LoadBalancer(ConsistentHash, 100 vnodes) -> 1024 x Server -> Sink; "
+            "thread engine; one GPU's 1024 replicas, 2 s slice of the 10 s run")
+        ctx("configs[4]", hs.mmc_sweep(), 32768, 100.0,
+            "M/M/c sweep, 256 (c, rho) cells x 128 seeds on one GPU; lane engine; 100 s slice of the 1000 s run",
+            replicas_per_cell=128, queue_ring=4096)
+
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -362,7 +391,7 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
                 "roofline": roofline, "e2e": e2e, "gpu_launches": res["launches"], "clocks": clocks,
                 "events_timed": events, "replicas_flagged": agg["replicas_flagged"], "aggregate": agg,
-                "other_mode": other, "wall_s_timed_region": res["wall_s"]}
+                "other_mode": other, "other_configs": others, "wall_s_timed_region": res["wall_s"]}
         if world == 1 and not a.no_cpu_baseline:
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
             cb, _, _ = cpu_oracle_throughput(12.0, min(a.window_s, 500.0), a.seed)

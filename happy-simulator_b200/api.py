@@ -714,15 +714,22 @@ class Simulation:
                 o._requests_received, o._requests_forwarded = int(row["c0"]), int(row["c1"])
             elif k == A.HS_ENT_SKETCH:
                 o._events_processed = int(row["c0"])
-                if out.get("sketches") is not None and hasattr(o._sketch, "_load_device_state"):
-                    o._sketch._load_device_state(self.model.sketch_views(out["sketches"])[i][r], int(row["c1"]))
+                sk = o._topk if hasattr(o, "_topk") else o._sketch
+                if out.get("sketches") is not None and hasattr(sk, "_load_device_state"):
+                    sk._load_device_state(self.model.sketch_views(out["sketches"])[i][r], int(row["c1"]))
                 elif out.get("sketches") is not None:      # a reference sketch object: fill its own fields
                     state = self.model.sketch_views(out["sketches"])[i][r]
-                    if hasattr(o._sketch, "_registers"):
-                        o._sketch._registers = [int(x) for x in state]
+                    algo = int(self.model.entities["i0"][i])
+                    if algo == A.HS_SK_HLL:
+                        sk._registers = [int(x) for x in state]
+                    elif algo == A.HS_SK_CMS:
+                        sk._counters = [[int(x) for x in rowc] for rowc in state]
+                    elif algo == A.HS_SK_BLOOM:
+                        sk._bits = [int(x) for x in state]
+                        sk._bits_set = sum(bin(w).count("1") for w in sk._bits)
                     else:
-                        o._sketch._counters = [[int(x) for x in rowc] for rowc in state]
-                    o._sketch._total_count = int(row["c1"])
+                        raise lowering.UnsupportedModelError("write-back into a reference TopK object (use happysim_b200.TopK)")
+                    sk._total_count = int(row["c1"])
 
     def _entity_summaries(self):
         """core/simulation.py:560-591: only objects passed as entities=, events_handled from

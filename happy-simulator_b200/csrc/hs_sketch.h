@@ -4,6 +4,8 @@
  * Restates  SketchCollector.handle_event   components/sketching/sketch_collector.py:79-98
  *           HyperLogLog.add                sketching/hyperloglog.py:137-165
  *           CountMinSketch.add             sketching/count_min_sketch.py:168-187
+ *           BloomFilter.add                sketching/bloom_filter.py:178-199
+ *           TopK.add (Space-Saving)        sketching/topk.py:90-128
  * with the SHA-256 evaluations (hyperloglog.py:128-135, count_min_sketch.py:136-155) taken from the
  * per-key tables the host built: the items are the routing keys 0..K-1.
  */
@@ -18,6 +20,8 @@ static inline uint64_t hs_sketch_row_bytes(const hs_entity_desc *d)
 {
     if (d->kind != HS_ENT_SKETCH) return 0;
     if (d->i0 == HS_SK_HLL) return (uint64_t)1 << d->i2;                       /* uint8 registers[2^p], p >= 4 */
+    if (d->i0 == HS_SK_BLOOM) return (((uint64_t)d->i3 + 63u) / 64u * 8u + 15u) / 16u * 16u;   /* uint64 words */
+    if (d->i0 == HS_SK_TOPK) return (16u + (uint64_t)d->i2 * 12u + 15u) / 16u * 16u;           /* n, pad, k slots */
     return ((uint64_t)d->i2 * (uint64_t)d->i3 * 4u + 15u) / 16u * 16u;         /* uint32 counters[depth][width] */
 }
 
@@ -26,6 +30,8 @@ static inline uint64_t hs_sketch_row_merged_bytes(const hs_entity_desc *d)
 {
     if (d->kind != HS_ENT_SKETCH) return 0;
     if (d->i0 == HS_SK_HLL) return (uint64_t)1 << d->i2;
+    if (d->i0 == HS_SK_BLOOM) return hs_sketch_row_bytes(d);
+    if (d->i0 == HS_SK_TOPK) return 0;                                         /* merged on the host */
     return ((uint64_t)d->i2 * (uint64_t)d->i3 * 8u + 15u) / 16u * 16u;
 }
 
@@ -51,9 +57,30 @@ HS_HD void hs_sketch_add(uint8_t *state, const int32_t *tab, int32_t algo, int32
     if (algo == HS_SK_HLL) {                      /* registers[idx] = max(registers[idx], run_length) */
         const int32_t idx = tab[key], run = tab[K + key];
         if ((int32_t)state[idx] < run) state[idx] = (uint8_t)run;
-    } else {                                      /* for row in range(depth): counters[row][col] += 1 */
+    } else if (algo == HS_SK_CMS) {               /* for row in range(depth): counters[row][col] += 1 */
         uint32_t *c = (uint32_t *)state;
         for (int32_t row = 0; row < p_or_depth; ++row) c[(int64_t)row * width + tab[(int64_t)row * K + key]] += 1u;
+    } else if (algo == HS_SK_BLOOM) {             /* for i in range(num_hashes): set bit (h1 + i h2) % size_bits */
+        uint64_t *w = (uint64_t *)state;
+        for (int32_t i = 0; i < p_or_depth; ++i) {
+            const uint32_t bit = (uint32_t)tab[(int64_t)i * K + key];
+            w[bit >> 6] |= 1ull << (bit & 63u);
+        }
+    } else {                                      /* Space-Saving over k counters kept in dict (insertion) order */
+        uint32_t *hdr = (uint32_t *)state;
+        int32_t *slot = (int32_t *)(state + 16);  /* {item, count, error} x k */
+        const uint32_t n = hdr[0], k = (uint32_t)p_or_depth;
+        uint32_t j = 0;
+        while (j < n && slot[3 * j] != key) ++j;
+        if (j < n) { slot[3 * j + 1] += 1; return; }                     /* tracked: count += 1 */
+        if (n < k) { slot[3 * n] = key; slot[3 * n + 1] = 1; slot[3 * n + 2] = 0; hdr[0] = n + 1u; return; }
+        /* min(self._counters.values(), key=count): the first minimum in dict order is replaced; the new
+         * counter inherits its count as error and goes to the end of the dict */
+        uint32_t m = 0;
+        for (j = 1; j < n; ++j) if ((uint32_t)slot[3 * j + 1] < (uint32_t)slot[3 * m + 1]) m = j;
+        const int32_t mc = slot[3 * m + 1];
+        for (j = m; j + 1 < n; ++j) { slot[3 * j] = slot[3 * j + 3]; slot[3 * j + 1] = slot[3 * j + 4]; slot[3 * j + 2] = slot[3 * j + 5]; }
+        slot[3 * (n - 1)] = key; slot[3 * (n - 1) + 1] = mc + 1; slot[3 * (n - 1) + 2] = mc;
     }
 }
 

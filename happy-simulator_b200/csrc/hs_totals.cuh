@@ -151,6 +151,18 @@ __global__ void hs_sketch_merge_hll_kernel(const uint8_t *__restrict__ per_repli
     merged[w] = acc;
 }
 
+/* BloomFilter.merge: bitwise OR of the bit arrays (sketching/bloom_filter.py:262-291) */
+__global__ void hs_sketch_merge_or_kernel(const uint8_t *__restrict__ per_replica, uint64_t stride, uint32_t n_replicas,
+                                          uint32_t n_words, uint32_t *__restrict__ merged)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t acc = 0u;
+    for (uint32_t r = 0; r < n_replicas; ++r)
+        acc |= *(const uint32_t *)(per_replica + (size_t)r * stride + (size_t)w * 4u);
+    merged[w] = acc;
+}
+
 /* CountMinSketch.merge: element-wise sum of the counters (sketching/count_min_sketch.py:276-301) */
 __global__ void hs_sketch_merge_cms_kernel(const uint8_t *__restrict__ per_replica, uint64_t stride, uint32_t n_replicas,
                                            uint32_t n_cells, unsigned long long *__restrict__ merged)

@@ -89,6 +89,19 @@ def cms_table(width: int, depth: int, seed: int | None, population: int) -> np.n
     return tab
 
 
+def bloom_table(size_bits: int, num_hashes: int, seed: int | None, population: int) -> np.ndarray:
+    """BloomFilter._hash per (hash i, key) (sketching/bloom_filter.py:147-160): digest = sha256(pack(">QQ", seed, i)
+    + repr(k)); bit = (digest[0:8] + i * digest[8:16]) mod size_bits (big-endian words).  -> int32[num_hashes, K]."""
+    seed = 0 if seed is None else int(seed)
+    tab = np.zeros((num_hashes, population), np.int32)
+    for i in range(num_hashes):
+        pre = struct.pack(">QQ", seed, i)
+        for k in range(population):
+            dg = hashlib.sha256(pre + repr(k).encode("utf-8")).digest()
+            tab[i, k] = (int.from_bytes(dg[:8], "big") + i * int.from_bytes(dg[8:16], "big")) % size_bits
+    return tab
+
+
 def _arrival(tp):
     """ArrivalTimeProvider -> (HS_ARR_*, rate, profile tuple or None).  The reference's built-in
     profile classes (load/profile.py) are lowered; a user-defined Profile.get_rate is a Python
@@ -171,7 +184,7 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
             return A.HS_ENT_COUNTER
         if hasattr(o, "_strategy") and hasattr(o, "_backends") and hasattr(o, "_in_flight"):
             return A.HS_ENT_LB
-        if hasattr(o, "_sketch") and hasattr(o, "_value_extractor") and hasattr(o, "_events_processed"):
+        if (hasattr(o, "_sketch") or hasattr(o, "_topk")) and hasattr(o, "_value_extractor") and hasattr(o, "_events_processed"):
             return A.HS_ENT_SKETCH
         raise UnsupportedModelError(f"entity {getattr(o, 'name', o)!r} of type {n} cannot be lowered to the device "
                                     "engine (supported: Source, Server, Sink, Counter, LoadBalancer, SketchCollector)")
@@ -244,21 +257,26 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
             if not getattr(o._value_extractor, "routing_key", False):
                 raise UnsupportedModelError(f"sketch collector {name!r}: arbitrary value_extractor callbacks cannot "
                                             "run on the device (use happysim_b200.KeyExtractor())")
-            if getattr(o, "_weight_extractor", None) is not None:
-                raise UnsupportedModelError(f"sketch collector {name!r}: weight_extractor callbacks")
+            if getattr(o, "_weight_extractor", None) is not None or getattr(o, "_count_extractor", None) is not None:
+                raise UnsupportedModelError(f"sketch collector {name!r}: weight / count extractor callbacks")
             pop = key_population or max((int(getattr(getattr(getattr(s, "_event_provider", None), "_context_fn", None),
                                                      "key_population", 0)) for s in sources or []), default=0)
             if pop <= 0:
                 raise UnsupportedModelError(f"sketch collector {name!r}: needs a finite key population")
-            sk = o._sketch
-            if _cls(sk) == "HyperLogLog":
+            sk = o._topk if hasattr(o, "_topk") else o._sketch       # TopKCollector keeps its TopK in _topk
+            if _cls(sk) == "TopK":
+                b.sketch_topk(name, k=int(sk._k), key_population=pop)
+            elif _cls(sk) == "BloomFilter":
+                b.sketch_bloom(name, size_bits=int(sk._size_bits), num_hashes=int(sk._num_hashes),
+                               table=bloom_table(sk._size_bits, sk._num_hashes, sk._seed, pop))
+            elif _cls(sk) == "HyperLogLog":
                 b.sketch_hll(name, precision=int(sk._precision), table=hll_table(sk._precision, sk._seed, pop))
             elif _cls(sk) == "CountMinSketch":
                 b.sketch_cms(name, width=int(sk._width), depth=int(sk._depth),
                              table=cms_table(sk._width, sk._depth, sk._seed, pop))
             else:
                 raise UnsupportedModelError(f"sketch collector {name!r}: sketch {_cls(sk)} (supported: HyperLogLog, "
-                                            "CountMinSketch)")
+                                            "CountMinSketch, BloomFilter, TopK)")
         elif k == A.HS_ENT_LB:
             strat = o._strategy
             backs = [info.backend for info in o._backends.values() if info.is_healthy]

@@ -47,19 +47,33 @@ class FlatModel:
             per[i], mer[i] = a, b
             if int(e["i0"]) == A.HS_SK_HLL:
                 a += 1 << int(e["i2"]); b += 1 << int(e["i2"])
+            elif int(e["i0"]) == A.HS_SK_BLOOM:
+                nb = ((int(e["i3"]) + 63) // 64 * 8 + 15) // 16 * 16
+                a += nb; b += nb
+            elif int(e["i0"]) == A.HS_SK_TOPK:
+                a += (16 + int(e["i2"]) * 12 + 15) // 16 * 16          # merged on the host: no merged image
             else:
                 cells = int(e["i2"]) * int(e["i3"])
                 a += (cells * 4 + 15) // 16 * 16; b += (cells * 8 + 15) // 16 * 16
         return per, mer, a, b
 
     def sketch_views(self, raw: np.ndarray) -> dict:
-        """Per-replica states out of hs_outputs.sketches: {entity id: uint8[n, 2^p] | uint32[n, depth, width]}."""
+        """Per-replica states out of hs_outputs.sketches: {entity id: HLL uint8[n, 2^p] | CMS uint32[n, depth,
+        width] | BLOOM uint64[n, words] | TOPK int64[n, 1 + 3 k] = (tracked, then item, count, error per slot)}."""
         per = self.sketch_layout()[0]
         out = {}
         for i in self.ids_of(A.HS_ENT_SKETCH):
             e = self.entities[i]
             if int(e["i0"]) == A.HS_SK_HLL:
                 out[i] = raw[:, per[i]: per[i] + (1 << int(e["i2"]))]
+            elif int(e["i0"]) == A.HS_SK_BLOOM:
+                nw = (int(e["i3"]) + 63) // 64
+                out[i] = np.ascontiguousarray(raw[:, per[i]: per[i] + nw * 8]).view(np.uint64)
+            elif int(e["i0"]) == A.HS_SK_TOPK:
+                k = int(e["i2"])
+                hdr = np.ascontiguousarray(raw[:, per[i]: per[i] + 4]).view(np.uint32).astype(np.int64)
+                sl = np.ascontiguousarray(raw[:, per[i] + 16: per[i] + 16 + 12 * k]).view(np.int32).astype(np.int64)
+                out[i] = np.concatenate([hdr, sl], axis=1)
             else:
                 d, w = int(e["i2"]), int(e["i3"])
                 out[i] = np.ascontiguousarray(raw[:, per[i]: per[i] + d * w * 4]).view(np.uint32).reshape(-1, d, w)
@@ -72,6 +86,11 @@ class FlatModel:
             e = self.entities[i]
             if int(e["i0"]) == A.HS_SK_HLL:
                 out[i] = img[mer[i]: mer[i] + (1 << int(e["i2"]))].copy()
+            elif int(e["i0"]) == A.HS_SK_BLOOM:
+                nw = (int(e["i3"]) + 63) // 64
+                out[i] = img[mer[i]: mer[i] + nw * 8].copy().view(np.uint64)
+            elif int(e["i0"]) == A.HS_SK_TOPK:
+                continue
             else:
                 d, w = int(e["i2"]), int(e["i3"])
                 out[i] = img[mer[i]: mer[i] + d * w * 8].copy().view(np.uint64).reshape(d, w)
@@ -183,6 +202,19 @@ class ModelBuilder:
         off = sum(t.size for t in self._sketch_tables)
         self._sketch_tables.append(table)
         return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_CMS, off, int(depth), table.shape[1], i3=int(width))
+
+    def sketch_bloom(self, name="Bloom", *, size_bits, num_hashes, table):
+        """SketchCollector(BloomFilter(size_bits, num_hashes, seed)) on the routing key; table =
+        bloom_table(size_bits, num_hashes, seed, K): int32[num_hashes, K], the bit each hash sets for key k."""
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        assert table.ndim == 2 and table.shape[0] == num_hashes
+        off = sum(t.size for t in self._sketch_tables)
+        self._sketch_tables.append(table)
+        return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_BLOOM, off, int(num_hashes), table.shape[1], i3=int(size_bits))
+
+    def sketch_topk(self, name="TopK", *, k, key_population):
+        """TopKCollector(k) / SketchCollector(TopK(k)) on the routing key (Space-Saving; no table)."""
+        return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_TOPK, 0, int(k), int(key_population))
 
     def load_balancer(self, name="LB", *, backends, key_table=None):
         off = len(self._backends)

@@ -1,8 +1,10 @@
 """Sketches as instrumentation sinks: the host-side mirrors of the reference's
-``HyperLogLog`` / ``CountMinSketch`` / ``SketchCollector`` whose ``add()`` runs on the device.
+``HyperLogLog`` / ``CountMinSketch`` / ``BloomFilter`` / ``TopK`` and of ``SketchCollector`` /
+``TopKCollector``, whose ``add()`` runs on the device.
 
 Reference: happysimulator/sketching/hyperloglog.py:57-250, sketching/count_min_sketch.py:52-328,
-components/sketching/sketch_collector.py:24-104.  The device keeps one sketch state per replica (uint8
+sketching/bloom_filter.py:57-307, sketching/topk.py:37-285, components/sketching/sketch_collector.py:24-104,
+components/sketching/topk_collector.py:22-150.  The device keeps one sketch state per replica (uint8
 registers / uint32 counters in HBM, csrc/hs_sketch.h), updated by the SKETCH row's handler with the
 per-key hash results the host computed once (lowering.hll_table / cms_table); after a run the states are
 written back into these objects, and ``merge()`` -- register max / counter sum, the reference's contracts
@@ -185,4 +187,217 @@ class SketchCollector:
 
     def clear(self) -> None:
         self._sketch.clear()
+        self._events_processed = 0
+
+
+class BloomFilter:
+    """sketching/bloom_filter.py:57: set membership over size_bits bits and num_hashes double-hashed probes."""
+
+    def __init__(self, size_bits: int, num_hashes: int | None = None, seed: int | None = None):
+        if size_bits <= 0:
+            raise ValueError(f"size_bits must be positive, got {size_bits}")
+        if num_hashes is not None and num_hashes <= 0:
+            raise ValueError(f"num_hashes must be positive, got {num_hashes}")
+        self._size_bits = size_bits
+        self._num_hashes = num_hashes if num_hashes is not None else 7
+        self._seed = seed if seed is not None else 0
+        self._bits = np.zeros((size_bits + 63) // 64, np.uint64)
+        self._total_count = 0
+        self._tab = None
+
+    @classmethod
+    def from_expected_items(cls, n: int, fp_rate: float, seed: int | None = None) -> "BloomFilter":
+        """bloom_filter.py:37-54,112-137: m = ceil(-n ln p / ln(2)^2) (64 for n = 0), k = max(1, round(m / n ln 2))."""
+        if n < 0:
+            raise ValueError(f"n must be non-negative, got {n}")
+        if not 0 < fp_rate < 1:
+            raise ValueError(f"fp_rate must be in (0, 1), got {fp_rate}")
+        m = 64 if n == 0 else math.ceil(-n * math.log(fp_rate) / (math.log(2) ** 2))
+        k = 1 if n == 0 else max(1, round((m / n) * math.log(2)))
+        return cls(size_bits=m, num_hashes=k, seed=seed)
+
+    size_bits = property(lambda self: self._size_bits)
+    num_hashes = property(lambda self: self._num_hashes)
+    item_count = property(lambda self: self._total_count)
+
+    @property
+    def _bits_set(self) -> int:
+        return int(sum(bin(int(w)).count("1") for w in self._bits))
+
+    fill_ratio = property(lambda self: self._bits_set / self._size_bits)
+
+    @property
+    def false_positive_rate(self) -> float:
+        return 0.0 if self._bits_set == 0 else (self._bits_set / self._size_bits) ** self._num_hashes
+
+    def _key_table(self, upto: int):
+        if self._tab is None or self._tab.shape[1] < upto:
+            self._tab = lowering.bloom_table(self._size_bits, self._num_hashes, self._seed, max(upto, 64))
+        return self._tab
+
+    def add(self, item: int, count: int = 1) -> None:
+        if count < 0:
+            raise ValueError(f"count must be non-negative, got {count}")
+        if count == 0:
+            return
+        t = self._key_table(int(item) + 1)
+        self._total_count += count
+        for i in range(self._num_hashes):
+            b = int(t[i, item])
+            self._bits[b >> 6] |= np.uint64(1 << (b & 63))
+
+    def contains(self, item: int) -> bool:
+        t = self._key_table(int(item) + 1)
+        return all((int(self._bits[int(t[i, item]) >> 6]) >> (int(t[i, item]) & 63)) & 1 for i in range(self._num_hashes))
+
+    __contains__ = contains
+
+    def merge(self, other: "BloomFilter") -> None:
+        if not isinstance(other, BloomFilter):
+            raise TypeError(f"Can only merge with BloomFilter, got {type(other).__name__}")
+        if other._size_bits != self._size_bits:
+            raise ValueError(f"Cannot merge: size_bits differs ({self._size_bits} vs {other._size_bits})")
+        if other._num_hashes != self._num_hashes:
+            raise ValueError(f"Cannot merge: num_hashes differs ({self._num_hashes} vs {other._num_hashes})")
+        if other._seed != self._seed:
+            raise ValueError(f"Cannot merge: seeds differ ({self._seed} vs {other._seed})")
+        self._bits |= other._bits
+        self._total_count += other._total_count
+
+    def clear(self) -> None:
+        self._bits[:] = 0
+        self._total_count = 0
+
+    def _load_device_state(self, words: np.ndarray, item_count: int) -> None:
+        self._bits = np.array(words, dtype=np.uint64)
+        self._total_count = int(item_count)
+
+
+class FrequencyEstimate:
+    """sketching/base.py: (item, count, error) as TopK.top() returns them."""
+
+    __slots__ = ("item", "count", "error")
+
+    def __init__(self, item, count, error):
+        self.item, self.count, self.error = item, count, error
+
+    def __eq__(self, o):
+        return (self.item, self.count, self.error) == (o.item, o.count, o.error)
+
+    def __repr__(self):
+        return f"FrequencyEstimate(item={self.item!r}, count={self.count}, error={self.error})"
+
+
+class TopK:
+    """sketching/topk.py:37: Space-Saving heavy hitters over k counters; the counters live in a dict, whose
+    insertion order decides which of several minimal counters is replaced (topk.py:116-128)."""
+
+    def __init__(self, k: int, seed: int | None = None):
+        if k <= 0:
+            raise ValueError(f"k must be positive, got {k}")
+        self._k = k
+        self._counters: dict = {}          # item -> [count, error], insertion ordered
+        self._total_count = 0
+
+    k = property(lambda self: self._k)
+    item_count = property(lambda self: self._total_count)
+    tracked_count = property(lambda self: len(self._counters))
+
+    def add(self, item, count: int = 1) -> None:
+        if count < 0:
+            raise ValueError(f"count must be non-negative, got {count}")
+        if count == 0:
+            return
+        self._total_count += count
+        c = self._counters.get(item)
+        if c is not None:
+            c[0] += count
+        elif len(self._counters) < self._k:
+            self._counters[item] = [count, 0]
+        else:
+            victim = min(self._counters, key=lambda it: self._counters[it][0])    # first minimum in dict order
+            floor = self._counters.pop(victim)[0]
+            self._counters[item] = [floor + count, floor]
+
+    def estimate(self, item) -> int:
+        c = self._counters.get(item)
+        return c[0] if c is not None else 0
+
+    def max_error(self) -> int:
+        return min((c[0] for c in self._counters.values()), default=0)
+
+    def estimate_with_error(self, item) -> FrequencyEstimate:
+        c = self._counters.get(item)
+        return FrequencyEstimate(item, c[0], c[1]) if c is not None else FrequencyEstimate(item, 0, self.max_error())
+
+    def top(self, n: int | None = None) -> list:
+        order = sorted(self._counters.items(), key=lambda kv: kv[1][0], reverse=True)    # stable, like the reference
+        return [FrequencyEstimate(it, c[0], c[1]) for it, c in order[: len(order) if n is None else n]]
+
+    def __contains__(self, item) -> bool:
+        return item in self._counters
+
+    def guaranteed_threshold(self) -> int:
+        return self._total_count // self._k
+
+    def merge(self, other: "TopK") -> None:
+        """topk.py:216-258: tracked items add up (count and error); the others are add()-ed with their count,
+        then inherit the other's error; the total grows by the other's total."""
+        if not isinstance(other, TopK):
+            raise TypeError(f"Can only merge with TopK, got {type(other).__name__}")
+        if other._k != self._k:
+            raise ValueError(f"Cannot merge TopK with k={other._k} into k={self._k}")
+        before = set(self._counters)
+        for item, (cnt, err) in list(other._counters.items()):
+            if item in self._counters:
+                self._counters[item][0] += cnt
+                self._counters[item][1] += err
+            else:
+                self.add(item, cnt)
+                if item in self._counters:
+                    self._counters[item][1] += err
+        self._total_count += other._total_count - sum(c[0] for it, c in other._counters.items() if it not in before)
+
+    def clear(self) -> None:
+        self._counters.clear()
+        self._total_count = 0
+
+    def _load_device_state(self, row: np.ndarray, item_count: int) -> None:
+        n = int(row[0])
+        self._counters = {int(row[1 + 3 * j]): [int(row[2 + 3 * j]), int(row[3 + 3 * j])] for j in range(n)}
+        self._total_count = int(item_count)
+
+
+class TopKCollector:
+    """components/sketching/topk_collector.py:22: SketchCollector specialised to TopK."""
+
+    def __init__(self, name: str, k: int, value_extractor=None, count_extractor=None, seed: int | None = None):
+        self.name = name
+        self._topk = TopK(k=k, seed=seed)
+        self._value_extractor = value_extractor if value_extractor is not None else KeyExtractor()
+        self._count_extractor = count_extractor
+        self._events_processed = 0
+
+    k = property(lambda self: self._topk.k)
+    events_processed = property(lambda self: self._events_processed)
+    total_count = property(lambda self: self._topk.item_count)
+    tracked_count = property(lambda self: self._topk.tracked_count)
+
+    def top(self, n: int | None = None):
+        return self._topk.top(n)
+
+    def estimate(self, item) -> int:
+        return self._topk.estimate(item)
+
+    def __contains__(self, item) -> bool:
+        return item in self._topk
+
+    def max_error(self) -> int:
+        return self._topk.max_error()
+
+    def guaranteed_threshold(self) -> int:
+        return self._topk.guaranteed_threshold()
+
+    def clear(self) -> None:
+        self._topk.clear()
         self._events_processed = 0

@@ -57,7 +57,9 @@ enum {
 /* Sketch algorithms of a SKETCH row.  Both hash the item with SHA-256 (hyperloglog.py:128-135,
  * count_min_sketch.py:136-155); the items are the routing keys 0..population-1, so the host evaluates
  * the hashes once per key (hs_model_desc.sketch_tables) and the device only indexes. */
-enum { HS_SK_HLL = 1, HS_SK_CMS = 2 };
+enum { HS_SK_HLL = 1, HS_SK_CMS = 2,
+       HS_SK_BLOOM = 3,   /* sketching/bloom_filter.py:57 BloomFilter (bit positions per key on the host)      */
+       HS_SK_TOPK = 4 };  /* sketching/topk.py:37 TopK, Space-Saving (no hashing: pure counter bookkeeping)     */
 /* Probe metrics (getattr(target, metric), probe.py:55-62). */
 enum { HS_METRIC_DEPTH = 0, HS_METRIC_ACTIVE_REQUESTS = 1, HS_METRIC_UTILIZATION = 2, HS_METRIC_AVAILABLE_CAPACITY = 3,
        HS_METRIC_STATS_ACCEPTED = 4, HS_METRIC_STATS_DROPPED = 5, HS_METRIC_EVENTS_RECEIVED = 6, HS_METRIC_TOTAL = 7,
@@ -92,9 +94,9 @@ typedef struct hs_entity_desc {
     int32_t i1;        /* SOURCE: key population (0 = no routing key); SERVER: HS_Q_*;
                           LB: offset of its backend list in hs_model_desc.backends;
                           SKETCH: offset of its table in hs_model_desc.sketch_tables            */
-    int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends; SKETCH: HLL precision p | CMS depth   */
+    int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends; SKETCH: HLL precision p | CMS depth | BLOOM num_hashes | TOPK k */
     int32_t i3;        /* SOURCE: 0 = ConstantRateProfile(d0); k > 0 = profiles[k - 1] (non-constant
-                          rate profile, general arrival path); SKETCH: CMS width; others: reserved, 0 */
+                          rate profile, general arrival path); SKETCH: CMS width | BLOOM size_bits; others: reserved, 0 */
     int64_t l0;        /* SOURCE: stop_after in ns or -1; SERVER: queue capacity or -1 (= inf);
                           SKETCH: key population K = row stride of its table in sketch_tables     */
     double d0;         /* SOURCE: rate (events/s); SERVER: mean / constant service time (s)     */
@@ -123,7 +125,8 @@ typedef struct hs_model_desc {
     /* Per-key hash results of the SKETCH rows (row i0/i1/i2/i3/l0: algorithm, table offset, p | depth,
      * CMS width, K).  HLL: [2][K] = register index (hash >> (64 - p)) and run length (leading zeros of
      * the remaining bits + 1) of key k, hyperloglog.py:156-165.  CMS: [depth][K] = column of key k in
-     * each row, count_min_sketch.py:145-155. */
+     * each row, count_min_sketch.py:145-155.  BLOOM: [num_hashes][K] = bit index (h1 + i h2) mod size_bits of
+     * key k for hash i, bloom_filter.py:147-160.  TOPK: no table. */
     uint32_t n_sketch_table;       /* total length of sketch_tables[]                          */
     uint32_t reserved3;
     const int32_t *sketch_tables;
@@ -229,7 +232,9 @@ typedef struct hs_outputs {        /* caller-owned HOST buffers; any pointer may
     double *service_samples;       /* [n_replicas][service_cap], service-start order           */
     uint32_t *histograms;          /* [n_replicas][HS_HISTOGRAM_BINS] (HS_RUN_HISTOGRAM)        */
     uint8_t *sketches;             /* [n_replicas][hs_sketch_layout().total]: every SKETCH row's state,
-                                      HLL: uint8 registers[2^p]; CMS: uint32 counters[depth][width] */
+                                      HLL: uint8 registers[2^p]; CMS: uint32 counters[depth][width];
+                                      BLOOM: uint64 words[ceil(size_bits / 64)]; TOPK: uint32 n, pad[3], then
+                                      k x {int32 item, uint32 count, uint32 error} in dict (insertion) order */
 } hs_outputs;
 
 /* Ensemble totals: what the single end-of-run NCCL allreduce carries.
@@ -283,7 +288,9 @@ int hs_model_validate(const hs_model_desc *model);
  * slice is *total bytes, the merged image *merged_total.  The merged image applies the reference's
  * merge() contracts over the replicas of a run: HLL registers -> element-wise max (hyperloglog.py:
  * 203-226), uint8[2^p]; CMS counters -> element-wise sum (count_min_sketch.py:276-301), widened to
- * uint64[depth][width].  Needs no device. */
+ * uint64[depth][width]; BLOOM words -> bitwise OR (bloom_filter.py:262-291).  TopK.merge (topk.py:216-258)
+ * is order dependent and sequential: TOPK rows have no merged image (size 0), the host layer merges the
+ * per-replica states.  Needs no device. */
 int hs_sketch_layout(const hs_model_desc *model, uint64_t *per_replica, uint64_t *merged,
                      uint64_t *total, uint64_t *merged_total);
 

@@ -151,6 +151,22 @@ def sketch_farm(K=40, n_servers=4, width=16, depth=3, cms_seed=9, hll_seed=None)
     return b.build(), {cms: cms_seed, hll: hll_seed}
 
 
+def sketch_members(K=60, n_servers=3, bloom_seed=3):
+    """Source -> LoadBalancer -> servers -> {BloomFilter, TopK(k=5), TopK(k=5)} collectors: membership and heavy
+    hitters; k < number of distinct keys, so Space-Saving evicts (topk.py:116-128)."""
+    b = hs.ModelBuilder()
+    src = b.source(rate=120.0, key_population=K)
+    servers = [b.server(f"S{i}", concurrency=2, mean_service_s=0.02) for i in range(n_servers)]
+    bloom = b.sketch_bloom("seen", size_bits=200, num_hashes=3, table=hs.bloom_table(200, 3, bloom_seed, K))
+    top = b.sketch_topk("heavy", k=5, key_population=K)
+    top2 = b.sketch_topk("heavy2", k=40, key_population=K)
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb)
+    for sv, dst in zip(servers, (bloom, top, top2)):
+        b.set_target(sv, dst)
+    return b.build(), {bloom: bloom_seed}
+
+
 def philox_cases():
     c = {}
     c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
@@ -180,6 +196,8 @@ def philox_cases():
     c["sketch_hll_direct"] = (m, dict(seed=17, rid=3, end_s=2, sketch_seeds=seeds))
     m, seeds = sketch_farm()
     c["sketch_cms_farm"] = (m, dict(seed=19, rid=1, end_s=6, sketch_seeds=seeds))
+    m, seeds = sketch_members()
+    c["sketch_bloom_topk"] = (m, dict(seed=23, rid=2, end_s=5, sketch_seeds=seeds))
     return c
 
 

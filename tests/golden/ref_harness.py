@@ -64,6 +64,9 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     from happysimulator.components.sketching.sketch_collector import SketchCollector
     from happysimulator.sketching.hyperloglog import HyperLogLog
     from happysimulator.sketching.count_min_sketch import CountMinSketch
+    from happysimulator.sketching.bloom_filter import BloomFilter
+    from happysimulator.sketching.topk import TopK
+    from happysimulator.components.sketching.topk_collector import TopKCollector
 
     L = O.lib()
     ents = model.entities
@@ -102,13 +105,17 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         elif k == A.HS_ENT_SKETCH:
             e = ents[i]
             sk_seed = (sketch_seeds or {}).get(i)
+            extract = lambda ev: ev.context.get("metadata", {}).get("client_id")   # sketch_collector.py:36-41
+            if int(e["i0"]) == A.HS_SK_TOPK:
+                objs[i] = TopKCollector(names[i], k=int(e["i2"]), value_extractor=extract)
+                continue
             if int(e["i0"]) == A.HS_SK_HLL:
                 sk = HyperLogLog(precision=int(e["i2"]), seed=sk_seed)
+            elif int(e["i0"]) == A.HS_SK_BLOOM:
+                sk = BloomFilter(size_bits=int(e["i3"]), num_hashes=int(e["i2"]), seed=sk_seed)
             else:
                 sk = CountMinSketch(width=int(e["i3"]), depth=int(e["i2"]), seed=sk_seed)
-            # the reference idiom for "the request's client id" (sketch_collector.py:36-41)
-            objs[i] = SketchCollector(names[i], sketch=sk,
-                                      value_extractor=lambda ev: ev.context.get("metadata", {}).get("client_id"))
+            objs[i] = SketchCollector(names[i], sketch=sk, value_extractor=extract)
     for i in range(n):
         if int(ents["kind"][i]) != A.HS_ENT_SERVER:
             continue
@@ -226,7 +233,7 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             return A.HS_EV_REQ_COUNTER
         if isinstance(t, LoadBalancer):
             return A.HS_EV_REQ_LB
-        if isinstance(t, SketchCollector):
+        if isinstance(t, (SketchCollector, TopKCollector)):
             return A.HS_EV_REQ_SKETCH
         raise AssertionError(f"unclassified event {ev!r}")
 
@@ -293,7 +300,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         elif k == A.HS_ENT_COUNTER:
             stats[i]["c0"] = o.total
         elif k == A.HS_ENT_SKETCH:
-            stats[i]["c0"], stats[i]["c1"] = o.events_processed, o.sketch.item_count
+            stats[i]["c0"] = o.events_processed
+            stats[i]["c1"] = o.total_count if isinstance(o, TopKCollector) else o.sketch.item_count
         elif k == A.HS_ENT_LB:
             s = o.stats
             stats[i]["c0"], stats[i]["c1"], stats[i]["c2"] = s.requests_received, s.requests_forwarded, len(o._in_flight)
@@ -333,8 +341,18 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         for i, o in enumerate(objs):
             if int(ents["kind"][i]) != A.HS_ENT_SKETCH:
                 continue
-            if int(ents["i0"][i]) == A.HS_SK_HLL:
+            algo = int(ents["i0"][i])
+            if algo == A.HS_SK_HLL:
                 img[per[i]: per[i] + len(o.sketch._registers)] = np.array(o.sketch._registers, dtype=np.uint8)
+            elif algo == A.HS_SK_BLOOM:
+                w = np.array(o.sketch._bits, dtype=np.uint64)
+                img[per[i]: per[i] + w.size * 8] = w.view(np.uint8)
+            elif algo == A.HS_SK_TOPK:          # dict order = insertion order (topk.py:116-128)
+                cs = list(o._topk._counters.values())
+                hdr = np.array([len(cs), 0, 0, 0], dtype=np.uint32)
+                sl = np.array([[c.item, c.count, c.error] for c in cs], dtype=np.int32).ravel()
+                img[per[i]: per[i] + 16] = hdr.view(np.uint8)
+                img[per[i] + 16: per[i] + 16 + sl.size * 4] = sl.view(np.uint8)
             else:
                 c = np.array(o.sketch._counters, dtype=np.uint32).ravel()
                 img[per[i]: per[i] + c.size * 4] = c.view(np.uint8)
@@ -344,8 +362,15 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         for i, o in enumerate(objs):
             if int(ents["kind"][i]) != A.HS_ENT_SKETCH:
                 continue
-            if int(ents["i0"][i]) == A.HS_SK_HLL:
+            algo = int(ents["i0"][i])
+            if algo == A.HS_SK_HLL:
                 ans[i] = np.array([o.sketch.cardinality()], dtype=np.int64)
+            elif algo == A.HS_SK_BLOOM:     # contains(k) for every key, then the bit count
+                ans[i] = np.array([int(o.sketch.contains(k)) for k in range(int(ents["l0"][i]))] + [o.sketch._bits_set],
+                                  dtype=np.int64)
+            elif algo == A.HS_SK_TOPK:      # top(): (item, count, error) rows, then max_error and the threshold
+                ans[i] = np.array([v for fe in o.top() for v in (fe.item, fe.count, fe.error)] +
+                                  [o.max_error(), o.guaranteed_threshold()], dtype=np.int64)
             else:
                 ans[i] = np.array([o.sketch.estimate(k) for k in range(int(ents["l0"][i]))], dtype=np.int64)
         out["sketch_answers"] = ans

@@ -49,6 +49,42 @@ def test_sketch_ensemble_matches_oracle_and_merges_on_the_device(eng, eng_id):
         assert merged[i].dtype == host[i].dtype and np.array_equal(merged[i], host[i])
 
 
+def members_farm(K=3000, n_servers=9):
+    b = hs.ModelBuilder()
+    src = b.source(rate=60.0 * n_servers, key_population=K)
+    servers = [b.server(f"S{i}", concurrency=2, mean_service_s=0.02) for i in range(n_servers)]
+    sinks = [b.sketch_bloom("seen", size_bits=9585, num_hashes=7, table=hs.bloom_table(9585, 7, 4, K)),
+             b.sketch_topk("heavy", k=16, key_population=K),
+             b.sketch_topk("all", k=64, key_population=K)]
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb)
+    for k, sv in enumerate(servers):
+        b.set_target(sv, sinks[k % 3])
+    return b.build()
+
+
+@pytest.mark.parametrize("eng_id", [1, 3])
+def test_bloom_and_topk_ensemble_matches_oracle(eng, eng_id):
+    """Space-Saving's eviction order (first minimum in dict order) and the Bloom bit arrays, bit for bit;
+    the Bloom OR-merge on the device, the sequential TopK merge on the host."""
+    model = members_farm()
+    kw = dict(seed=21, end_ns=2 * 10**9, n_replicas=29, record_cap=30000, sample_cap=16, service_cap=3000)
+    eng.upload(model)
+    eng.run(engine.make_params(engine=eng_id, **kw))
+    got = eng.read_outputs()
+    want = O.oracle_run(model, O.make_params(**kw))
+    assert_same(got, want)
+    assert got["sketches"].tobytes() == want["sketches"].tobytes()
+    views = model.sketch_views(got["sketches"])
+    ids = model.ids_of(A.HS_ENT_SKETCH)
+    assert int(views[ids[1]][:, 0].min()) == 16            # k = 16 counters all in use: evictions happened
+    merged = eng.read_sketches()
+    host = D.merge_sketch_states(model, want["sketches"])
+    assert set(merged) == {ids[0]} and np.array_equal(merged[ids[0]], host[ids[0]])
+    dev_top = D.merge_sketch_states(model, got["sketches"])[ids[1]]
+    assert dev_top.top() == host[ids[1]].top() and dev_top.item_count == host[ids[1]].item_count
+
+
 @pytest.mark.parametrize("eng_id", [1, 3])
 def test_sketch_state_survives_windows(eng, eng_id):
     model, kw, z = G.load("philox_sketch_cms_farm")

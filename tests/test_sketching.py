@@ -41,18 +41,53 @@ def test_mirror_classes_give_the_reference_answers(name):
     views = m.sketch_views(out["sketches"])
     for i, state in views.items():
         e = m.entities[i]
-        seed = int(z[f"sketch_seed_{i}"]); seed = None if seed < 0 else seed
+        seed = int(z[f"sketch_seed_{i}"]) if f"sketch_seed_{i}" in z.files else -1     # TopK takes no seed
+        seed = None if seed < 0 else seed
         want = z[f"sketch_answer_{i}"]
         added = int(out["entity_stats"][0][i]["c1"])
         if int(e["i0"]) == A.HS_SK_HLL:
             sk = hs.HyperLogLog(precision=int(e["i2"]), seed=seed)
             sk._load_device_state(state[0], added)
             assert sk.cardinality() == int(want[0]) and sk.item_count == added
+        elif int(e["i0"]) == A.HS_SK_BLOOM:
+            sk = hs.BloomFilter(size_bits=int(e["i3"]), num_hashes=int(e["i2"]), seed=seed)
+            sk._load_device_state(state[0], added)
+            K = int(e["l0"])
+            assert [int(sk.contains(k)) for k in range(K)] == [int(x) for x in want[:K]]
+            assert sk._bits_set == int(want[K]) and sk.item_count == added and 0 < sk.fill_ratio < 1
+        elif int(e["i0"]) == A.HS_SK_TOPK:
+            sk = hs.TopK(k=int(e["i2"]))
+            sk._load_device_state(state[0], added)
+            flat = [v for fe in sk.top() for v in (fe.item, fe.count, fe.error)] + [sk.max_error(), sk.guaranteed_threshold()]
+            assert flat == [int(x) for x in want]
+            assert sk.tracked_count == min(int(e["i2"]), sk.tracked_count) and sk.item_count == added
         else:
             sk = hs.CountMinSketch(width=int(e["i3"]), depth=int(e["i2"]), seed=seed)
             sk._load_device_state(state[0], added)
             assert [sk.estimate(k) for k in range(int(e["l0"]))] == [int(x) for x in want]
             assert int(state[0].sum()) == added * int(e["i2"])           # every add touches one cell per row
+
+
+def test_space_saving_host_mirror_equals_the_shared_c_step():
+    """TopK.add on the host (dict order) vs csrc/hs_sketch.h's slot array, through the oracle: a direct
+    Source -> TopK model sees the raw key stream, which is replayed into the mirror."""
+    K, k = 25, 6
+    b = hs.ModelBuilder()
+    src = b.source(rate=400.0, key_population=K)
+    top = b.sketch_topk("heavy", k=k, key_population=K)
+    b.set_target(src, top)
+    m = b.build()
+    p = dict(seed=5, end_ns=10**9, n_replicas=3)
+    out = O.oracle_run(m, O.make_params(**p))
+    for r in range(3):
+        mirror = hs.TopK(k)
+        n = int(out["entity_stats"][r][top]["c1"])
+        for d in range(n):      # the source's routing draws (hs_handlers.inc / oracle: int(u * K))
+            u = O.lib().hs_cpu_uniform(5, r, A.HS_STREAM_ROUTING | (src << 8), d)
+            mirror.add(int(u * K))
+        dev = hs.TopK(k); dev._load_device_state(m.sketch_views(out["sketches"])[top][r], n)
+        assert list(dev._counters.items()) == list(mirror._counters.items()) and n > 300
+        assert dev.top(3) == mirror.top(3) and dev.max_error() == mirror.max_error()
 
 
 def test_host_side_add_equals_device_table_path():
@@ -89,6 +124,22 @@ def test_merge_contracts_over_replicas():
                 o = hs.CountMinSketch(w, d); o._load_device_state(v[r], int(out["entity_stats"][r][i]["c1"])); acc.merge(o)
             assert np.array_equal(acc._counters, merged[i])
             assert acc.item_count == int(out["entity_stats"][:, i]["c1"].sum())
+    # Bloom (OR) and TopK (sequential, order dependent) over the replicas of the membership fixture
+    m2, kw2, _ = G.load("philox_sketch_bloom_topk")
+    out2 = O.oracle_run(m2, O.make_params(n_replicas=4, seed=kw2["seed"], end_ns=kw2["end_ns"], rid_base=0))
+    merged2 = D.merge_sketch_states(m2, out2["sketches"])
+    for i, v in m2.sketch_views(out2["sketches"]).items():
+        e = m2.entities[i]
+        if int(e["i0"]) == A.HS_SK_BLOOM:
+            acc = hs.BloomFilter(int(e["i3"]), int(e["i2"]))
+            for r in range(4):
+                o = hs.BloomFilter(int(e["i3"]), int(e["i2"])); o._load_device_state(v[r], 1); acc.merge(o)
+            assert np.array_equal(acc._bits, merged2[i]) and acc.item_count == 4
+        else:
+            acc = hs.TopK(int(e["i2"]))
+            for r in range(4):
+                o = hs.TopK(int(e["i2"])); o._load_device_state(v[r], int(out2["entity_stats"][r][i]["c1"])); acc.merge(o)
+            assert merged2[i].top() == acc.top() and merged2[i].item_count == acc.item_count
     with pytest.raises(ValueError):
         hs.HyperLogLog(8).merge(hs.HyperLogLog(9))
     with pytest.raises(ValueError):
@@ -112,6 +163,25 @@ def test_lowering_of_a_sketch_collector_model():
         lowering.lower([hs.Source.poisson(rate=1.0, event_provider=hs.SimpleEventProvider(bad, context_fn=hs.UniformKeyContext(K)))], [bad])
 
 
+def test_lowering_of_topk_and_bloom_collectors():
+    K = 20
+    top = hs.TopKCollector("heavy", k=4)
+    seen = hs.SketchCollector("seen", hs.BloomFilter.from_expected_items(100, 0.05, seed=2))
+    s1 = hs.Server("A", service_time=hs.ExponentialLatency(0.01), downstream=top)
+    s2 = hs.Server("B", service_time=hs.ExponentialLatency(0.01), downstream=seen)
+    lb = hs.LoadBalancer("lb", backends=[s1, s2], strategy=hs.RoundRobin())
+    src = hs.Source.poisson(rate=50.0, event_provider=hs.SimpleEventProvider(lb, context_fn=hs.UniformKeyContext(K)))
+    model, objs = lowering.lower([src], [lb, s1, s2, top, seen])
+    et, es = model.entities[objs.index(top)], model.entities[objs.index(seen)]
+    assert int(et["i0"]) == A.HS_SK_TOPK and int(et["i2"]) == 4 and int(et["l0"]) == K
+    bf = seen.sketch
+    assert int(es["i0"]) == A.HS_SK_BLOOM and int(es["i3"]) == bf.size_bits == 624 and int(es["i2"]) == bf.num_hashes == 4
+    assert np.array_equal(model.sketch_tables.reshape(4, K), hs.bloom_table(624, 4, 2, K))
+    engine.validate_model(model)
+    per, mer, total, mtotal = model.sketch_layout()
+    assert total == (16 + 4 * 12) + 80 and mtotal == 80            # TOPK has no merged image
+
+
 def test_validation_rejects_bad_sketch_rows():
     def model(**over):
         b = hs.ModelBuilder()
@@ -126,6 +196,18 @@ def test_validation_rejects_bad_sketch_rows():
     for over, msg in ((dict(i2=3), "precision"), (dict(i0=9), "algorithm"), (dict(l0=0), "population"), (dict(i1=5), "table")):
         with pytest.raises(EngineError, match=msg):
             engine.validate_model(model(**over))
+    b = hs.ModelBuilder()
+    s_ = b.source(rate=1.0, key_population=8)
+    bl = b.sketch_bloom(size_bits=50, num_hashes=2, table=hs.bloom_table(50, 2, 0, 8))
+    tk = b.sketch_topk(k=3, key_population=8)
+    b.set_target(s_, bl)
+    mb = b.build(); engine.validate_model(mb)
+    mb.sketch_tables = mb.sketch_tables.copy(); mb.sketch_tables[9] = 50      # bit index == size_bits
+    with pytest.raises(EngineError, match="Bloom bit"):
+        engine.validate_model(mb)
+    mb.sketch_tables[9] = 0; mb.entities[tk]["i2"] = 0
+    with pytest.raises(EngineError, match="k must be positive"):
+        engine.validate_model(mb)
     m = model()
     m.sketch_tables = m.sketch_tables.copy(); m.sketch_tables[3] = 32        # register index out of range for p = 5
     with pytest.raises(EngineError, match="HLL table"):

@@ -8,7 +8,7 @@ HS_ABI_VERSION = 2
 HS_OK, HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_NO_DEVICE, HS_ERR_STATE, HS_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
 
 HS_ENT_SOURCE, HS_ENT_SERVER, HS_ENT_SINK, HS_ENT_COUNTER, HS_ENT_LB, HS_ENT_PROBE, HS_ENT_SKETCH = 1, 2, 3, 4, 5, 6, 7
-HS_SK_HLL, HS_SK_CMS, HS_SK_BLOOM, HS_SK_TOPK = 1, 2, 3, 4
+HS_SK_HLL, HS_SK_CMS, HS_SK_BLOOM, HS_SK_TOPK, HS_SK_TDIGEST = 1, 2, 3, 4, 5
 METRICS = {"depth": 0, "active_requests": 1, "utilization": 2, "available_capacity": 3, "stats_accepted": 4,
            "stats_dropped": 5, "events_received": 6, "total": 7, "generated_count": 8}
 HS_ARR_CONSTANT, HS_ARR_POISSON = 0, 1
@@ -25,6 +25,7 @@ EVENT_KIND_NAMES = ["SOURCE_TICK", "REQ_LB", "REQ_ENQUEUE", "NOTIFY", "POLL", "D
                     "REQ_WORKER", "CONTINUATION", "REQ_SINK", "LB_RESPONSE", "REQ_COUNTER", "PROBE", "REQ_SKETCH"]
 
 HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH, HS_ST_TRACE_EXHAUSTED, HS_ST_EVENT_LIMIT = 1, 2, 4, 8, 16
+HS_ST_SKETCH_OVERFLOW = 32
 
 HS_STREAM_ARRIVAL, HS_STREAM_SERVICE, HS_STREAM_ROUTING = 0, 1, 2
 

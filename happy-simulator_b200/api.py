@@ -714,7 +714,7 @@ class Simulation:
                 o._requests_received, o._requests_forwarded = int(row["c0"]), int(row["c1"])
             elif k == A.HS_ENT_SKETCH:
                 o._events_processed = int(row["c0"])
-                sk = o._topk if hasattr(o, "_topk") else o._sketch
+                sk = o._topk if hasattr(o, "_topk") else o._tdigest if hasattr(o, "_tdigest") else o._sketch
                 if out.get("sketches") is not None and hasattr(sk, "_load_device_state"):
                     sk._load_device_state(self.model.sketch_views(out["sketches"])[i][r], int(row["c1"]))
                 elif out.get("sketches") is not None:      # a reference sketch object: fill its own fields

@@ -136,12 +136,18 @@ static int validate_model(const hs_model_desc *m)
             break;
         case HS_ENT_SINK: case HS_ENT_COUNTER: break;
         case HS_ENT_SKETCH: {
-            if (e.i0 < HS_SK_HLL || e.i0 > HS_SK_TOPK) return fail(HS_ERR_INVALID, "entity %u: unknown sketch algorithm %d", i, e.i0);
+            if (e.i0 < HS_SK_HLL || e.i0 > HS_SK_TDIGEST) return fail(HS_ERR_INVALID, "entity %u: unknown sketch algorithm %d", i, e.i0);
             if (e.l0 < 1 || e.l0 > INT32_MAX) return fail(HS_ERR_INVALID, "entity %u: sketch key population must be >= 1", i);
             if (e.i0 == HS_SK_HLL && (e.i2 < 4 || e.i2 > 16)) return fail(HS_ERR_INVALID, "entity %u: precision must be in [4, 16], got %d (hyperloglog.py:101)", i, e.i2);
             if (e.i0 == HS_SK_CMS && (e.i2 < 1 || e.i3 < 1)) return fail(HS_ERR_INVALID, "entity %u: width and depth must be >= 1 (count_min_sketch.py:88-91)", i);
             if (e.i0 == HS_SK_BLOOM && (e.i2 < 1 || e.i3 < 1)) return fail(HS_ERR_INVALID, "entity %u: size_bits and num_hashes must be >= 1 (bloom_filter.py:101-104)", i);
             if (e.i0 == HS_SK_TOPK && e.i2 < 1) return fail(HS_ERR_INVALID, "entity %u: k must be positive (topk.py:79)", i);
+            if (e.i0 == HS_SK_TDIGEST) {
+                if (!(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: compression must be positive (tdigest.py:79)", i);
+                if (e.i2 < 1 || e.i2 != (int32_t)(e.d0 * 2.0)) return fail(HS_ERR_INVALID, "entity %u: buffer size must be int(compression * 2) >= 1 (tdigest.py:88)", i);
+                if (e.i3 < 2 * e.i2) return fail(HS_ERR_INVALID, "entity %u: centroid capacity must be >= 2 x buffer size", i);
+                break;
+            }
             const uint64_t rows = e.i0 == HS_SK_HLL ? 2u : e.i0 == HS_SK_TOPK ? 0u : (uint64_t)e.i2;
             if (rows && (e.i1 < 0 || !m->sketch_tables || (uint64_t)e.i1 + rows * (uint64_t)e.l0 > m->n_sketch_table))
                 return fail(HS_ERR_INVALID, "entity %u: sketch table out of range", i);
@@ -683,8 +689,8 @@ int hs_read_sketches(hs_engine *E, void *merged, uint64_t merged_bytes)
         } else if (e.i0 == HS_SK_BLOOM) {
             const uint32_t words = (uint32_t)(hs_sketch_row_bytes(&e) / 4u);
             hs_sketch_merge_or_kernel<<<(words + 127) / 128, 128, 0, E->stream>>>(src, E->sk_total, n, words, (uint32_t *)dst);
-        } else if (e.i0 == HS_SK_TOPK) {
-            continue;                                   /* no merged image: TopK.merge is sequential, done by the host layer */
+        } else if (e.i0 == HS_SK_TOPK || e.i0 == HS_SK_TDIGEST) {
+            continue;                                   /* no merged image: these merges are sequential, done by the host layer */
         } else {
             const uint32_t cells = (uint32_t)e.i2 * (uint32_t)e.i3;
             hs_sketch_merge_cms_kernel<<<(cells + 127) / 128, 128, 0, E->stream>>>(src, E->sk_total, n, cells, (unsigned long long *)dst);

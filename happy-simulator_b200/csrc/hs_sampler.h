@@ -40,6 +40,7 @@
 #define HS_MUL(a, b) __dmul_rn((a), (b))
 #define HS_DIV(a, b) __ddiv_rn((a), (b))
 #define HS_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define HS_SQRT(a) __dsqrt_rn((a))
 #define HS_D2LL(x) __double2ll_rz(x)
 #define HS_LL2D(x) __ll2double_rn(x)
 #define HS_MULHI32(a, b) __umulhi((a), (b))
@@ -58,6 +59,7 @@
 #define HS_MUL(a, b) ((a) * (b))
 #define HS_DIV(a, b) ((a) / (b))
 #define HS_FMA(a, b, c) fma((a), (b), (c))
+#define HS_SQRT(a) sqrt((a))              /* IEEE correctly rounded, like math.sqrt */
 #define HS_D2LL(x) ((long long)(x))
 #define HS_LL2D(x) ((double)(long long)(x))
 #define HS_MULHI32(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))

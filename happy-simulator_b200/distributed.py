@@ -136,7 +136,7 @@ def merge_sketch_states(model, raw: np.ndarray) -> dict:
     """Host restatement of Engine.read_sketches for per-replica states (hs_outputs.sketches of any
     party): HyperLogLog.merge = register max, CountMinSketch.merge = counter sum, BloomFilter.merge = OR
     over the replicas; TOPK rows (no device image) become a ``TopK`` object merged in replica order."""
-    from .sketching import TopK
+    from .sketching import TDigest, TopK
     out = {}
     for i, v in model.sketch_views(raw).items():
         algo = int(model.entities["i0"][i])
@@ -144,6 +144,13 @@ def merge_sketch_states(model, raw: np.ndarray) -> dict:
             out[i] = v.max(axis=0).astype(np.uint8)
         elif algo == A.HS_SK_BLOOM:
             out[i] = np.bitwise_or.reduce(v, axis=0)
+        elif algo == A.HS_SK_TDIGEST:        # TDigest.merge re-compresses: sequential, replica 0, 1, 2 ...
+            acc = TDigest(float(model.entities["d0"][i]))
+            for r in range(v.shape[0]):
+                o = TDigest(acc.compression)
+                o._load_device_state(v[r])
+                acc.merge(o)
+            out[i] = acc
         elif algo == A.HS_SK_TOPK:           # TopK.merge is sequential and order dependent: replica 0, 1, 2 ...
             acc = TopK(int(model.entities["i2"][i]))
             for r in range(v.shape[0]):
@@ -160,18 +167,19 @@ def allreduce_sketches(model, merged: dict, device=None, group=None) -> dict:
     """Cross-GPU merge of the per-rank merged sketches: one MAX all-reduce over the HLL registers, one SUM
     all-reduce over the CMS counters and one bitwise-OR all-reduce over the Bloom words (the reference's
     merge() contracts, hyperloglog.py:203-226, count_min_sketch.py:276-301, bloom_filter.py:262-291).
-    TopK.merge is sequential and order dependent: TOPK entries stay rank-local here (gather the per-replica
+    TopK.merge / TDigest.merge are sequential and order dependent: those entries stay rank-local here (gather the per-replica
     states and merge them in global replica order if a cross-rank TopK is wanted)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return merged
     dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
-    ids = sorted(i for i in merged if int(model.entities["i0"][i]) != A.HS_SK_TOPK)
+    host_only = (A.HS_SK_TOPK, A.HS_SK_TDIGEST)
+    ids = sorted(i for i in merged if int(model.entities["i0"][i]) not in host_only)
     hll = [i for i in ids if int(model.entities["i0"][i]) == A.HS_SK_HLL]
     blm = [i for i in ids if int(model.entities["i0"][i]) == A.HS_SK_BLOOM]
     cms = [i for i in ids if i not in hll and i not in blm]
-    out = {i: v for i, v in merged.items() if int(model.entities["i0"][i]) == A.HS_SK_TOPK}   # rank-local (see docstring)
+    out = {i: v for i, v in merged.items() if int(model.entities["i0"][i]) in host_only}   # rank-local (see docstring)
     if blm:
         t = torch.from_numpy(np.concatenate([merged[i].view(np.int64).ravel() for i in blm])).to(dev)
         dist.all_reduce(t, op=dist.ReduceOp.BOR, group=group)

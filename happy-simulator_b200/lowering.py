@@ -184,7 +184,8 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
             return A.HS_ENT_COUNTER
         if hasattr(o, "_strategy") and hasattr(o, "_backends") and hasattr(o, "_in_flight"):
             return A.HS_ENT_LB
-        if (hasattr(o, "_sketch") or hasattr(o, "_topk")) and hasattr(o, "_value_extractor") and hasattr(o, "_events_processed"):
+        if (hasattr(o, "_sketch") or hasattr(o, "_topk") or hasattr(o, "_tdigest")) and hasattr(o, "_value_extractor") \
+                and hasattr(o, "_events_processed"):
             return A.HS_ENT_SKETCH
         raise UnsupportedModelError(f"entity {getattr(o, 'name', o)!r} of type {n} cannot be lowered to the device "
                                     "engine (supported: Source, Server, Sink, Counter, LoadBalancer, SketchCollector)")
@@ -254,6 +255,12 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
         elif k == A.HS_ENT_SKETCH:
             # sketch_collector.py:79-98: value = value_extractor(event); only "the request's routing key"
             # is a value the device can see
+            if hasattr(o, "_tdigest"):              # QuantileEstimator (quantile_estimator.py:35)
+                if not getattr(o._value_extractor, "request_latency", False):
+                    raise UnsupportedModelError(f"quantile estimator {name!r}: arbitrary value_extractor callbacks "
+                                                "cannot run on the device (use happysim_b200.LatencyExtractor())")
+                b.sketch_tdigest(name, compression=float(o._tdigest._compression))
+                continue
             if not getattr(o._value_extractor, "routing_key", False):
                 raise UnsupportedModelError(f"sketch collector {name!r}: arbitrary value_extractor callbacks cannot "
                                             "run on the device (use happysim_b200.KeyExtractor())")

@@ -52,6 +52,8 @@ class FlatModel:
                 a += nb; b += nb
             elif int(e["i0"]) == A.HS_SK_TOPK:
                 a += (16 + int(e["i2"]) * 12 + 15) // 16 * 16          # merged on the host: no merged image
+            elif int(e["i0"]) == A.HS_SK_TDIGEST:
+                a += 32 + int(e["i3"]) * 16 + (int(e["i2"]) * 8 + 15) // 16 * 16
             else:
                 cells = int(e["i2"]) * int(e["i3"])
                 a += (cells * 4 + 15) // 16 * 16; b += (cells * 8 + 15) // 16 * 16
@@ -69,6 +71,9 @@ class FlatModel:
             elif int(e["i0"]) == A.HS_SK_BLOOM:
                 nw = (int(e["i3"]) + 63) // 64
                 out[i] = np.ascontiguousarray(raw[:, per[i]: per[i] + nw * 8]).view(np.uint64)
+            elif int(e["i0"]) == A.HS_SK_TDIGEST:       # the raw bytes; see sketching.TDigest._load_device_state
+                nb = 32 + int(e["i3"]) * 16 + (int(e["i2"]) * 8 + 15) // 16 * 16
+                out[i] = np.ascontiguousarray(raw[:, per[i]: per[i] + nb])
             elif int(e["i0"]) == A.HS_SK_TOPK:
                 k = int(e["i2"])
                 hdr = np.ascontiguousarray(raw[:, per[i]: per[i] + 4]).view(np.uint32).astype(np.int64)
@@ -78,6 +83,23 @@ class FlatModel:
                 d, w = int(e["i2"]), int(e["i3"])
                 out[i] = np.ascontiguousarray(raw[:, per[i]: per[i] + d * w * 4]).view(np.uint32).reshape(-1, d, w)
         return out
+
+    def canonical_sketches(self, raw: np.ndarray) -> np.ndarray:
+        """Copy of hs_outputs.sketches with the dead parts of TDIGEST rows zeroed (centroid slots past
+        n_centroids and buffer slots past n_buffer keep leftovers of earlier merges; they are not state)."""
+        raw = np.array(raw, dtype=np.uint8, copy=True).reshape(-1, self.sketch_layout()[2])
+        per = self.sketch_layout()[0]
+        for i in self.ids_of(A.HS_ENT_SKETCH):
+            e = self.entities[i]
+            if int(e["i0"]) != A.HS_SK_TDIGEST:
+                continue
+            cap, bsz = int(e["i3"]), int(e["i2"])
+            for r in range(raw.shape[0]):
+                n_c, n_b = (int(x) for x in raw[r, per[i]: per[i] + 8].view(np.uint32))
+                raw[r, per[i] + 32 + n_c * 16: per[i] + 32 + cap * 16] = 0
+                b0 = per[i] + 32 + cap * 16
+                raw[r, b0 + n_b * 8: b0 + (bsz * 8 + 15) // 16 * 16] = 0
+        return raw
 
     def merged_sketch_views(self, img: np.ndarray) -> dict:
         mer = self.sketch_layout()[1]
@@ -89,7 +111,7 @@ class FlatModel:
             elif int(e["i0"]) == A.HS_SK_BLOOM:
                 nw = (int(e["i3"]) + 63) // 64
                 out[i] = img[mer[i]: mer[i] + nw * 8].copy().view(np.uint64)
-            elif int(e["i0"]) == A.HS_SK_TOPK:
+            elif int(e["i0"]) in (A.HS_SK_TOPK, A.HS_SK_TDIGEST):
                 continue
             else:
                 d, w = int(e["i2"]), int(e["i3"])
@@ -211,6 +233,13 @@ class ModelBuilder:
         off = sum(t.size for t in self._sketch_tables)
         self._sketch_tables.append(table)
         return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_BLOOM, off, int(num_hashes), table.shape[1], i3=int(size_bits))
+
+    def sketch_tdigest(self, name="TDigest", *, compression=100.0, capacity=None):
+        """QuantileEstimator(compression) on the request's latency in seconds (tdigest.py:47; buffer of
+        int(compression * 2) values, flushed into at most `capacity` centroids, default 4 x compression)."""
+        buf = int(float(compression) * 2)
+        cap = int(capacity) if capacity is not None else 2 * buf
+        return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_TDIGEST, 0, buf, 1, d0=float(compression), i3=cap)
 
     def sketch_topk(self, name="TopK", *, k, key_population):
         """TopKCollector(k) / SketchCollector(TopK(k)) on the routing key (Space-Saving; no table)."""

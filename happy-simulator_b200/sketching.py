@@ -401,3 +401,222 @@ class TopKCollector:
     def clear(self) -> None:
         self._topk.clear()
         self._events_processed = 0
+
+
+class LatencyExtractor:
+    """value_extractor for QuantileEstimator: "the request's latency in seconds", i.e. what Sink records
+    (components/common.py:39-41: (event.time - created_at).to_seconds())."""
+
+    request_latency = True
+
+    def __call__(self, event):
+        return (event.time - event.context["created_at"]).to_seconds()
+
+
+class TDigest:
+    """sketching/tdigest.py:47: quantiles from centroids (mean, count) that are small near the tails.
+    add() buffers int(compression * 2) values, then sorts them in as unit centroids and merges neighbours
+    under max_size(q) = 4 N / (compression pi sqrt(q (1 - q)))."""
+
+    def __init__(self, compression: float = 100.0, seed: int | None = None):
+        if compression <= 0:
+            raise ValueError(f"compression must be positive, got {compression}")
+        self._compression = compression
+        self._means: list[float] = []
+        self._counts: list[int] = []
+        self._total_count = 0
+        self._min_value = None
+        self._max_value = None
+        self._buffer: list[float] = []
+        self._buffer_size = int(compression * 2)
+
+    compression = property(lambda self: self._compression)
+    item_count = property(lambda self: self._total_count)
+    min = property(lambda self: self._min_value)
+    max = property(lambda self: self._max_value)
+
+    @property
+    def centroid_count(self) -> int:
+        self._flush()
+        return len(self._means)
+
+    def _max_size(self, q: float) -> float:
+        q = max(0.0001, min(0.9999, q))
+        return self._total_count * 4 / (self._compression * math.pi * math.sqrt(q * (1 - q)))
+
+    def add(self, value: float, count: int = 1) -> None:
+        if count < 0:
+            raise ValueError(f"count must be non-negative, got {count}")
+        if count == 0:
+            return
+        if self._min_value is None or value < self._min_value:
+            self._min_value = value
+        if self._max_value is None or value > self._max_value:
+            self._max_value = value
+        self._total_count += count
+        self._buffer.extend([value] * count)
+        if len(self._buffer) >= self._buffer_size:
+            self._flush()
+
+    def _flush(self) -> None:
+        if not self._buffer:
+            return
+        pairs = list(zip(self._means, self._counts)) + [(v, 1) for v in sorted(self._buffer)]
+        self._buffer = []
+        self._compress(pairs)
+
+    def _compress(self, pairs) -> None:
+        if len(pairs) > 1:
+            pairs.sort(key=lambda p: p[0])                      # stable: old centroids stay ahead of equal new values
+            out = [list(pairs[0])]
+            running = pairs[0][1]
+            for mean, cnt in pairs[1:]:
+                limit = self._max_size((running + cnt / 2) / self._total_count)
+                last = out[-1]
+                if last[1] + cnt <= limit:
+                    tot = last[1] + cnt
+                    last[0] = (last[0] * last[1] + mean * cnt) / tot
+                    last[1] = tot
+                else:
+                    out.append([mean, cnt])
+                running += cnt
+            pairs = out
+        self._means = [p[0] for p in pairs]
+        self._counts = [p[1] for p in pairs]
+
+    def quantile(self, q: float) -> float:
+        """tdigest.py:192-262: walk the centroids to the one whose weight range holds q N and interpolate
+        (towards min / max in the first / last centroid, towards the previous mean elsewhere)."""
+        if not 0 <= q <= 1:
+            raise ValueError(f"Quantile must be in [0, 1], got {q}")
+        self._flush()
+        n = len(self._means)
+        if n == 0:
+            raise ValueError("Cannot compute quantile of empty digest")
+        if q == 0:
+            return self._min_value if self._min_value is not None else self._means[0]
+        if q == 1:
+            return self._max_value if self._max_value is not None else self._means[-1]
+        target = q * self._total_count
+        run = 0.0
+        for i in range(n):
+            mean, cnt = self._means[i], self._counts[i]
+            lo = 0.0 if i == 0 else run
+            hi = self._total_count if i == n - 1 else run + cnt
+            if lo <= target <= hi:
+                if i == 0:
+                    if self._min_value is not None and target < cnt / 2:
+                        return self._min_value + (target / (cnt / 2)) * (mean - self._min_value)
+                    return mean
+                if i == n - 1:
+                    if self._max_value is not None:
+                        rest = self._total_count - run
+                        if target > run + rest / 2:
+                            return mean + ((target - run - rest / 2) / (rest / 2)) * (self._max_value - mean)
+                    return mean
+                t = (target - lo) / cnt
+                if t < 0.5:
+                    prev = self._means[i - 1]
+                    return prev + (mean - prev) * (0.5 + t)
+                return mean
+            run += cnt
+        return self._means[-1]
+
+    def percentile(self, p: float) -> float:
+        if not 0 <= p <= 100:
+            raise ValueError(f"Percentile must be in [0, 100], got {p}")
+        return self.quantile(p / 100.0)
+
+    def cdf(self, value: float) -> float:
+        """tdigest.py:264-308."""
+        self._flush()
+        if not self._means:
+            return 0.0
+        if self._min_value is not None and value <= self._min_value:
+            return 0.0
+        if self._max_value is not None and value >= self._max_value:
+            return 1.0
+        below = 0.0
+        for i, (mean, cnt) in enumerate(zip(self._means, self._counts)):
+            if mean >= value:
+                if i == 0:
+                    if self._min_value is not None:
+                        return ((value - self._min_value) / (mean - self._min_value)) * (cnt / 2) / self._total_count
+                    return 0.0
+                prev = self._means[i - 1]
+                if prev < value < mean:
+                    return (below + ((value - prev) / (mean - prev)) * cnt / 2) / self._total_count
+                return below / self._total_count
+            below += cnt
+        return 1.0
+
+    def merge(self, other: "TDigest") -> None:
+        """tdigest.py:326-352: flush both, concatenate the centroids, combine count / min / max, re-compress."""
+        if not isinstance(other, TDigest):
+            raise TypeError(f"Can only merge with TDigest, got {type(other).__name__}")
+        self._flush()
+        other._flush()
+        pairs = list(zip(self._means, self._counts)) + list(zip(other._means, other._counts))
+        self._total_count += other._total_count
+        if other._min_value is not None and (self._min_value is None or other._min_value < self._min_value):
+            self._min_value = other._min_value
+        if other._max_value is not None and (self._max_value is None or other._max_value > self._max_value):
+            self._max_value = other._max_value
+        self._compress(pairs)
+
+    def clear(self) -> None:
+        self._means, self._counts, self._buffer = [], [], []
+        self._total_count, self._min_value, self._max_value = 0, None, None
+
+    def _load_device_state(self, raw: np.ndarray, item_count: int | None = None, capacity: int | None = None) -> None:
+        """raw: the row's bytes of one replica ({n_centroids, n_buffer, total, min, max}, centroids, buffer)."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        n_c, n_b = (int(x) for x in raw[:8].view(np.uint32))
+        total = int(raw[8:16].view(np.int64)[0])
+        mn, mx = (float(x) for x in raw[16:32].view(np.float64))
+        cap = capacity if capacity is not None else (len(raw) - 32 - (self._buffer_size * 8 + 15) // 16 * 16) // 16
+        cen = raw[32: 32 + n_c * 16]
+        self._means = [float(x) for x in cen.view(np.float64)[0::2]]
+        self._counts = [int(x) for x in cen.view(np.int64)[1::2]]
+        off = 32 + cap * 16
+        self._buffer = [float(x) for x in raw[off: off + n_b * 8].view(np.float64)]
+        self._total_count = total
+        self._min_value, self._max_value = (mn, mx) if total else (None, None)
+
+
+class QuantileEstimator:
+    """components/sketching/quantile_estimator.py:35: an entity feeding a TDigest with each event's value;
+    ``value_extractor`` must be a ``LatencyExtractor`` to run on the device."""
+
+    def __init__(self, name: str, value_extractor=None, compression: float = 100.0, seed: int | None = None):
+        self.name = name
+        self._tdigest = TDigest(compression=compression, seed=seed)
+        self._value_extractor = value_extractor if value_extractor is not None else LatencyExtractor()
+        self._events_processed = 0
+
+    compression = property(lambda self: self._tdigest.compression)
+    events_processed = property(lambda self: self._events_processed)
+    sample_count = property(lambda self: self._tdigest.item_count)
+    min = property(lambda self: self._tdigest.min)
+    max = property(lambda self: self._tdigest.max)
+
+    def quantile(self, q: float) -> float:
+        return self._tdigest.quantile(q)
+
+    def percentile(self, p: float) -> float:
+        return self._tdigest.percentile(p)
+
+    def cdf(self, value: float) -> float:
+        return self._tdigest.cdf(value)
+
+    def summary(self) -> dict:
+        """quantile_estimator.py:157-186 (LatencyPercentiles as a dict)."""
+        if self._tdigest.item_count == 0:
+            return dict(p50=0.0, p75=0.0, p90=0.0, p95=0.0, p99=0.0, p999=0.0, min=None, max=None, count=0)
+        return dict(p50=self.percentile(50), p75=self.percentile(75), p90=self.percentile(90), p95=self.percentile(95),
+                    p99=self.percentile(99), p999=self.percentile(99.9), min=self.min, max=self.max,
+                    count=self._tdigest.item_count)
+
+    def clear(self) -> None:
+        self._tdigest.clear()
+        self._events_processed = 0

@@ -59,7 +59,9 @@ enum {
  * the hashes once per key (hs_model_desc.sketch_tables) and the device only indexes. */
 enum { HS_SK_HLL = 1, HS_SK_CMS = 2,
        HS_SK_BLOOM = 3,   /* sketching/bloom_filter.py:57 BloomFilter (bit positions per key on the host)      */
-       HS_SK_TOPK = 4 };  /* sketching/topk.py:37 TopK, Space-Saving (no hashing: pure counter bookkeeping)     */
+       HS_SK_TOPK = 4,    /* sketching/topk.py:37 TopK, Space-Saving (no hashing: pure counter bookkeeping)     */
+       HS_SK_TDIGEST = 5 }; /* sketching/tdigest.py:47 TDigest behind components/sketching/quantile_estimator.py:35;
+                             the value is the request's latency in seconds (Sink's, common.py:39-41)       */
 /* Probe metrics (getattr(target, metric), probe.py:55-62). */
 enum { HS_METRIC_DEPTH = 0, HS_METRIC_ACTIVE_REQUESTS = 1, HS_METRIC_UTILIZATION = 2, HS_METRIC_AVAILABLE_CAPACITY = 3,
        HS_METRIC_STATS_ACCEPTED = 4, HS_METRIC_STATS_DROPPED = 5, HS_METRIC_EVENTS_RECEIVED = 6, HS_METRIC_TOTAL = 7,
@@ -94,12 +96,15 @@ typedef struct hs_entity_desc {
     int32_t i1;        /* SOURCE: key population (0 = no routing key); SERVER: HS_Q_*;
                           LB: offset of its backend list in hs_model_desc.backends;
                           SKETCH: offset of its table in hs_model_desc.sketch_tables            */
-    int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends; SKETCH: HLL precision p | CMS depth | BLOOM num_hashes | TOPK k */
+    int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends; SKETCH: HLL precision p | CMS depth | BLOOM num_hashes | TOPK k
+                          | TDIGEST buffer size int(compression * 2), tdigest.py:88 */
     int32_t i3;        /* SOURCE: 0 = ConstantRateProfile(d0); k > 0 = profiles[k - 1] (non-constant
-                          rate profile, general arrival path); SKETCH: CMS width | BLOOM size_bits; others: reserved, 0 */
+                          rate profile, general arrival path); SKETCH: CMS width | BLOOM size_bits
+                          | TDIGEST centroid capacity (>= 2 x buffer size); others: reserved, 0 */
     int64_t l0;        /* SOURCE: stop_after in ns or -1; SERVER: queue capacity or -1 (= inf);
                           SKETCH: key population K = row stride of its table in sketch_tables     */
-    double d0;         /* SOURCE: rate (events/s); SERVER: mean / constant service time (s)     */
+    double d0;         /* SOURCE: rate (events/s); SERVER: mean / constant service time (s);
+                          SKETCH/TDIGEST: compression                                           */
     double d1;         /* reserved, 0                                                           */
 } hs_entity_desc;      /* 48 bytes */
 
@@ -184,6 +189,7 @@ typedef struct hs_run_params {
 #define HS_ST_REJECT_PATH 4u      /* Server acquire failed (server.py:223)   */
 #define HS_ST_TRACE_EXHAUSTED 8u  /* ran out of externally supplied draws    */
 #define HS_ST_EVENT_LIMIT 16u     /* hs_run_params.max_events reached        */
+#define HS_ST_SKETCH_OVERFLOW 32u /* a TDigest outgrew its centroid capacity */
 
 typedef struct hs_replica_summary {
     int64_t events_processed;  /* SimulationSummary.total_events_processed (simulation.py:553) */
@@ -234,7 +240,9 @@ typedef struct hs_outputs {        /* caller-owned HOST buffers; any pointer may
     uint8_t *sketches;             /* [n_replicas][hs_sketch_layout().total]: every SKETCH row's state,
                                       HLL: uint8 registers[2^p]; CMS: uint32 counters[depth][width];
                                       BLOOM: uint64 words[ceil(size_bits / 64)]; TOPK: uint32 n, pad[3], then
-                                      k x {int32 item, uint32 count, uint32 error} in dict (insertion) order */
+                                      k x {int32 item, uint32 count, uint32 error} in dict (insertion) order;
+                                      TDIGEST: {uint32 n_centroids, n_buffer; int64 total; double min, max},
+                                      capacity x {double mean; int64 count}, buffer double[buffer size]       */
 } hs_outputs;
 
 /* Ensemble totals: what the single end-of-run NCCL allreduce carries.
@@ -289,8 +297,8 @@ int hs_model_validate(const hs_model_desc *model);
  * merge() contracts over the replicas of a run: HLL registers -> element-wise max (hyperloglog.py:
  * 203-226), uint8[2^p]; CMS counters -> element-wise sum (count_min_sketch.py:276-301), widened to
  * uint64[depth][width]; BLOOM words -> bitwise OR (bloom_filter.py:262-291).  TopK.merge (topk.py:216-258)
- * is order dependent and sequential: TOPK rows have no merged image (size 0), the host layer merges the
- * per-replica states.  Needs no device. */
+ * and TDigest.merge (tdigest.py:326-352) are order dependent and sequential: TOPK / TDIGEST rows have no
+ * merged image (size 0), the host layer merges the per-replica states.  Needs no device. */
 int hs_sketch_layout(const hs_model_desc *model, uint64_t *per_replica, uint64_t *merged,
                      uint64_t *total, uint64_t *merged_total);
 

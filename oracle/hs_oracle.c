@@ -432,7 +432,12 @@ static void handle(orun *R, oev *e)
         run_request_hooks(R, e);
         break;
     case HS_EV_REQ_SKETCH:                /* SketchCollector.handle_event, sketch_collector.py:79-98 */
-        if (e->key >= 0) {                /* value is not None: sketch.add(value) */
+        if (E->d.i0 == HS_SK_TDIGEST) {   /* QuantileEstimator (quantile_estimator.py:96-110): value = latency in s */
+            if (E->sk_state && !hs_tdigest_add(E->sk_state, E->d.d0, (uint32_t)E->d.i2, (uint32_t)E->d.i3,
+                                               hs_ns_to_seconds(R->now - e->created_at)))
+                R->status |= HS_ST_SKETCH_OVERFLOW;
+            E->sk_added++;
+        } else if (e->key >= 0) {         /* value is not None: sketch.add(value) */
             if (E->sk_state)
                 hs_sketch_add(E->sk_state, R->m->sketch_tables + E->d.i1, E->d.i0, E->d.i2, E->d.i3, E->d.l0, e->key);
             E->sk_added++;

@@ -167,6 +167,20 @@ def sketch_members(K=60, n_servers=3, bloom_seed=3):
     return b.build(), {bloom: bloom_seed}
 
 
+def sketch_quantiles():
+    """M/M/2 -> QuantileEstimator(compression=20): 40-value buffer, several flush + compress rounds; a second
+    estimator with the default compression behind a second server keeps a partly filled buffer."""
+    b = hs.ModelBuilder()
+    src = b.source(rate=30.0)
+    s1 = b.server("A", concurrency=2, mean_service_s=0.05)
+    s2 = b.server("B", concurrency=1, mean_service_s=0.01)
+    q1 = b.sketch_tdigest("lat20", compression=20.0)
+    q2 = b.sketch_tdigest("lat100", compression=100.0)
+    lb = b.load_balancer(backends=[s1, s2])
+    b.set_target(src, lb); b.set_target(s1, q1); b.set_target(s2, q2)
+    return b.build()
+
+
 def philox_cases():
     c = {}
     c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
@@ -198,6 +212,7 @@ def philox_cases():
     c["sketch_cms_farm"] = (m, dict(seed=19, rid=1, end_s=6, sketch_seeds=seeds))
     m, seeds = sketch_members()
     c["sketch_bloom_topk"] = (m, dict(seed=23, rid=2, end_s=5, sketch_seeds=seeds))
+    c["sketch_tdigest"] = (sketch_quantiles(), dict(seed=29, rid=0, end_s=40))
     return c
 
 
@@ -211,7 +226,7 @@ def save_case(path, model, ref, meta):
         n_records=np.int64(len(rec)), records=rec[:MAX_REC],
         n_samples=np.int64(len(ref["sink_samples"])), sink_samples=ref["sink_samples"][:MAX_SMP],
         n_service=np.int64(len(ref["service_samples"])), service_samples=ref["service_samples"][:MAX_SMP],
-        sketch_tables=model.sketch_tables, sketch_state=ref.get("sketches", np.zeros(0, np.uint8)),
+        case_name=np.array(os.path.basename(path)[:-4]), sketch_tables=model.sketch_tables, sketch_state=ref.get("sketches", np.zeros(0, np.uint8)),
         **{f"sketch_answer_{i}": a for i, a in ref.get("sketch_answers", {}).items()},
         **{f"sketch_seed_{i}": np.int64(-1 if sd is None else sd) for i, sd in (meta.get("sketch_seeds") or {}).items()},
         **{k: v for k, v in meta.items() if isinstance(v, np.ndarray)},

@@ -67,6 +67,7 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     from happysimulator.sketching.bloom_filter import BloomFilter
     from happysimulator.sketching.topk import TopK
     from happysimulator.components.sketching.topk_collector import TopKCollector
+    from happysimulator.components.sketching.quantile_estimator import QuantileEstimator
 
     L = O.lib()
     ents = model.entities
@@ -108,6 +109,10 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             extract = lambda ev: ev.context.get("metadata", {}).get("client_id")   # sketch_collector.py:36-41
             if int(e["i0"]) == A.HS_SK_TOPK:
                 objs[i] = TopKCollector(names[i], k=int(e["i2"]), value_extractor=extract)
+                continue
+            if int(e["i0"]) == A.HS_SK_TDIGEST:     # the value Sink records (common.py:39-41)
+                objs[i] = QuantileEstimator(names[i], compression=float(e["d0"]),
+                                            value_extractor=lambda ev: (ev.time - ev.context["created_at"]).to_seconds())
                 continue
             if int(e["i0"]) == A.HS_SK_HLL:
                 sk = HyperLogLog(precision=int(e["i2"]), seed=sk_seed)
@@ -233,7 +238,7 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             return A.HS_EV_REQ_COUNTER
         if isinstance(t, LoadBalancer):
             return A.HS_EV_REQ_LB
-        if isinstance(t, (SketchCollector, TopKCollector)):
+        if isinstance(t, (SketchCollector, TopKCollector, QuantileEstimator)):
             return A.HS_EV_REQ_SKETCH
         raise AssertionError(f"unclassified event {ev!r}")
 
@@ -301,7 +306,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             stats[i]["c0"] = o.total
         elif k == A.HS_ENT_SKETCH:
             stats[i]["c0"] = o.events_processed
-            stats[i]["c1"] = o.total_count if isinstance(o, TopKCollector) else o.sketch.item_count
+            stats[i]["c1"] = (o.total_count if isinstance(o, TopKCollector) else o.sample_count
+                              if isinstance(o, QuantileEstimator) else o.sketch.item_count)
         elif k == A.HS_ENT_LB:
             s = o.stats
             stats[i]["c0"], stats[i]["c1"], stats[i]["c2"] = s.requests_received, s.requests_forwarded, len(o._in_flight)
@@ -347,6 +353,23 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             elif algo == A.HS_SK_BLOOM:
                 w = np.array(o.sketch._bits, dtype=np.uint64)
                 img[per[i]: per[i] + w.size * 8] = w.view(np.uint8)
+            elif algo == A.HS_SK_TDIGEST:       # state BEFORE any query (quantile() would flush the buffer)
+                td = o._tdigest
+                cap, bsz = int(ents["i3"][i]), int(ents["i2"][i])
+                hdr = np.zeros(32, np.uint8)
+                hdr[0:8] = np.array([len(td._centroids), len(td._buffer)], dtype=np.uint32).view(np.uint8)
+                hdr[8:16] = np.array([td._total_count], dtype=np.int64).view(np.uint8)
+                hdr[16:32] = np.array([td._min_value or 0.0, td._max_value or 0.0], dtype=np.float64).view(np.uint8)
+                img[per[i]: per[i] + 32] = hdr
+                if td._centroids:
+                    cen = np.zeros(len(td._centroids) * 2, np.float64)
+                    cen[0::2] = [c.mean for c in td._centroids]
+                    cen[1::2] = np.array([c.count for c in td._centroids], dtype=np.int64).view(np.float64)
+                    img[per[i] + 32: per[i] + 32 + cen.size * 8] = cen.view(np.uint8)
+                if td._buffer:
+                    bb = np.array(td._buffer, dtype=np.float64)
+                    off = per[i] + 32 + cap * 16
+                    img[off: off + bb.size * 8] = bb.view(np.uint8)
             elif algo == A.HS_SK_TOPK:          # dict order = insertion order (topk.py:116-128)
                 cs = list(o._topk._counters.values())
                 hdr = np.array([len(cs), 0, 0, 0], dtype=np.uint32)
@@ -368,6 +391,11 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             elif algo == A.HS_SK_BLOOM:     # contains(k) for every key, then the bit count
                 ans[i] = np.array([int(o.sketch.contains(k)) for k in range(int(ents["l0"][i]))] + [o.sketch._bits_set],
                                   dtype=np.int64)
+            elif algo == A.HS_SK_TDIGEST:   # percentiles, cdf at a few points, centroid count (as float64 bits)
+                qs = [0.0, 0.001, 0.01, 0.25, 0.5, 0.75, 0.9, 0.99, 0.999, 1.0]
+                vals = [o.quantile(q) for q in qs] + [o.cdf(v) for v in (0.0, 0.01, 0.05, 0.1, 0.3, 1.0, 5.0)] + \
+                       [float(o._tdigest.centroid_count)]
+                ans[i] = np.array(vals, dtype=np.float64).view(np.int64)
             elif algo == A.HS_SK_TOPK:      # top(): (item, count, error) rows, then max_error and the threshold
                 ans[i] = np.array([v for fe in o.top() for v in (fe.item, fe.count, fe.error)] +
                                   [o.max_error(), o.guaranteed_threshold()], dtype=np.int64)

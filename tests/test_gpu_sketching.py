@@ -86,6 +86,33 @@ def test_bloom_and_topk_ensemble_matches_oracle(eng, eng_id):
 
 
 @pytest.mark.parametrize("eng_id", [1, 3])
+def test_tdigest_ensemble_matches_oracle_bit_for_bit(eng, eng_id):
+    """QuantileEstimator rows: IEEE add/mul/div/sqrt only, so the centroids (float means) are bit-identical to
+    the oracle's -- and through the fixture to the reference's -- after many flush/compress rounds."""
+    b = hs.ModelBuilder()
+    src = b.source(rate=800.0)
+    servers = [b.server(f"S{i}", concurrency=2, mean_service_s=0.004) for i in range(4)]
+    q = [b.sketch_tdigest("lat50", compression=50.0), b.sketch_tdigest("lat20", compression=20.0)]
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb)
+    for k, sv in enumerate(servers):
+        b.set_target(sv, q[k % 2])
+    model = b.build()
+    kw = dict(seed=33, end_ns=4 * 10**9, n_replicas=21, record_cap=40000, sample_cap=16, service_cap=4000)
+    eng.upload(model)
+    eng.run(engine.make_params(engine=eng_id, **kw))
+    got = eng.read_outputs()
+    want = O.oracle_run(model, O.make_params(**kw))
+    assert_same(got, want)
+    assert got["sketches"].tobytes() == want["sketches"].tobytes()
+    d = hs.TDigest(50.0); d._load_device_state(model.sketch_views(got["sketches"])[q[0]][5])
+    assert d.item_count > 1200 and d.centroid_count < 60 and 0 < d.quantile(0.5) < d.quantile(0.99) <= d.max
+    assert eng.read_sketches() == {}                                     # host-merged rows only
+    merged = D.merge_sketch_states(model, got["sketches"])[q[0]]
+    assert merged.item_count == int(got["entity_stats"][:, q[0]]["c1"].sum())
+
+
+@pytest.mark.parametrize("eng_id", [1, 3])
 def test_sketch_state_survives_windows(eng, eng_id):
     model, kw, z = G.load("philox_sketch_cms_farm")
     caps = dict(G.caps(z), engine=eng_id, n_replicas=3, rid_base=0, seed=kw["seed"])

@@ -55,6 +55,15 @@ def test_mirror_classes_give_the_reference_answers(name):
             K = int(e["l0"])
             assert [int(sk.contains(k)) for k in range(K)] == [int(x) for x in want[:K]]
             assert sk._bits_set == int(want[K]) and sk.item_count == added and 0 < sk.fill_ratio < 1
+        elif int(e["i0"]) == A.HS_SK_TDIGEST:
+            sk = hs.TDigest(compression=float(e["d0"]))
+            sk._load_device_state(state[0])
+            assert sk.item_count == added and len(sk._buffer) > 0          # state as left by add(): unflushed values
+            qs = [0.0, 0.001, 0.01, 0.25, 0.5, 0.75, 0.9, 0.99, 0.999, 1.0]
+            vals = [sk.quantile(q) for q in qs] + [sk.cdf(v) for v in (0.0, 0.01, 0.05, 0.1, 0.3, 1.0, 5.0)] + \
+                   [float(sk.centroid_count)]
+            assert np.array(vals, dtype=np.float64).view(np.int64).tolist() == [int(x) for x in want]   # bit for bit
+            assert sk.percentile(50) == sk.quantile(0.5) and sk.min <= sk.quantile(0.5) <= sk.max
         elif int(e["i0"]) == A.HS_SK_TOPK:
             sk = hs.TopK(k=int(e["i2"]))
             sk._load_device_state(state[0], added)
@@ -66,6 +75,38 @@ def test_mirror_classes_give_the_reference_answers(name):
             sk._load_device_state(state[0], added)
             assert [sk.estimate(k) for k in range(int(e["l0"]))] == [int(x) for x in want]
             assert int(state[0].sum()) == added * int(e["i2"])           # every add touches one cell per row
+
+
+def test_tdigest_host_mirror_equals_the_shared_c_step_and_merges():
+    """TDigest.add on the host vs csrc/hs_sketch.h through the oracle on the same latency stream (a Sink in
+    parallel records it), over many flush/compress rounds; then the order-dependent merge over replicas."""
+    b = hs.ModelBuilder()
+    src = b.source(rate=400.0)
+    s1 = b.server("A", concurrency=4, mean_service_s=0.005, downstream=-1)
+    q = b.sketch_tdigest("lat", compression=30.0)
+    b.set_target(src, s1); b.set_target(s1, q)
+    m = b.build()
+    m2 = hs.mm1(rate=400.0, mean_service_s=0.005, concurrency=4)           # same ids: Source, Server, then the sink
+    p = dict(seed=7, end_ns=3 * 10**9, n_replicas=3)
+    out = O.oracle_run(m, O.make_params(**p))
+    ref = O.oracle_run(m2, O.make_params(sample_cap=4000, **p))
+    digests = []
+    for r in range(3):
+        n = int(ref["summaries"][r]["n_sink_samples"])
+        mirror = hs.TDigest(30.0)
+        for v in ref["sink_samples"][r][:n]["latency_s"]:
+            mirror.add(float(v))
+        dev = hs.TDigest(30.0); dev._load_device_state(m.sketch_views(out["sketches"])[q][r])
+        assert n > 1000 and dev.item_count == n == int(out["entity_stats"][r][q]["c1"])
+        assert (dev._means, dev._counts, dev._buffer) == (mirror._means, mirror._counts, mirror._buffer)
+        assert (dev.min, dev.max) == (mirror.min, mirror.max) and dev.quantile(0.99) == mirror.quantile(0.99)
+        digests.append(dev)
+    merged = D.merge_sketch_states(m, out["sketches"])[q]
+    acc = hs.TDigest(30.0)
+    for d in digests:
+        acc.merge(d)
+    assert merged._means == acc._means and merged._counts == acc._counts and merged.item_count == sum(d.item_count for d in digests)
+    assert acc.quantile(0.5) > 0 and acc.cdf(acc.quantile(0.5)) == pytest.approx(0.5, abs=0.05)
 
 
 def test_space_saving_host_mirror_equals_the_shared_c_step():
@@ -180,6 +221,25 @@ def test_lowering_of_topk_and_bloom_collectors():
     engine.validate_model(model)
     per, mer, total, mtotal = model.sketch_layout()
     assert total == (16 + 4 * 12) + 80 and mtotal == 80            # TOPK has no merged image
+
+
+def test_lowering_of_a_quantile_estimator():
+    est = hs.QuantileEstimator("p99", hs.LatencyExtractor(), compression=50.0)
+    srv = hs.Server("S", concurrency=2, service_time=hs.ExponentialLatency(0.02), downstream=est)
+    src = hs.Source.poisson(rate=40.0, target=srv)
+    model, objs = lowering.lower([src], [srv, est])
+    e = model.entities[objs.index(est)]
+    assert int(e["kind"]) == A.HS_ENT_SKETCH and int(e["i0"]) == A.HS_SK_TDIGEST
+    assert float(e["d0"]) == 50.0 and int(e["i2"]) == 100 and int(e["i3"]) == 200
+    engine.validate_model(model)
+    assert model.sketch_layout()[2:] == (32 + 200 * 16 + 800, 0)
+    bad = hs.QuantileEstimator("x", value_extractor=lambda ev: 1.0)
+    with pytest.raises(hs.UnsupportedModelError, match="LatencyExtractor"):
+        lowering.lower([hs.Source.poisson(rate=1.0, target=bad)], [bad])
+    model.entities[objs.index(est)]["i2"] = 99
+    with pytest.raises(EngineError, match="buffer size"):
+        engine.validate_model(model)
+    assert est.summary()["count"] == 0 and est.summary()["p99"] == 0.0
 
 
 def test_validation_rejects_bad_sketch_rows():

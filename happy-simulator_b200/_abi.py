@@ -46,8 +46,8 @@ class ModelDesc(C.Structure):
                 ("n_cells", C.c_uint32), ("reserved", C.c_uint32),
                 ("cell_d0", C.POINTER(C.c_double)), ("cell_i0", C.POINTER(C.c_int32)),
                 ("n_profiles", C.c_uint32), ("reserved2", C.c_uint32), ("profiles", C.c_void_p),
-                ("n_sketch_table", C.c_uint32), ("reserved3", C.c_uint32),
-                ("sketch_tables", C.POINTER(C.c_int32))]
+                ("n_sketch_table", C.c_uint32), ("n_key_cdf", C.c_uint32),
+                ("sketch_tables", C.POINTER(C.c_int32)), ("key_cdf", C.POINTER(C.c_double))]
 
 
 class RunParams(C.Structure):

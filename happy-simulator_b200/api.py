@@ -258,6 +258,18 @@ class UniformKeyContext:
         self.key_population = int(population)
 
 
+class ZipfKeyContext(UniformKeyContext):
+    """context_fn for SimpleEventProvider: metadata {"client_id": k}, k ~ ZipfDistribution(range(population), s)
+    (distributions/zipf.py:27-123: inverse transform, bisect_left over the cumulative probabilities) drawn from
+    the Philox routing stream; rank 0 is the hottest key."""
+
+    def __init__(self, population: int, s: float = 1.0):
+        super().__init__(population)
+        if s < 0:
+            raise ValueError(f"s must be non-negative, got {s}")
+        self.zipf_s = float(s)
+
+
 # ----------------------------------------------------------------------------- entities
 class Entity:
     """core/entity.py:31-127"""

@@ -74,8 +74,9 @@ struct hs_engine {
     std::vector<double> cell_d0; std::vector<int32_t> cell_i0;
     std::vector<hs_profile_desc> profiles;
     uint32_t n_cells = 0;
-    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0, d_profiles, d_sketch_tab;
+    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0, d_profiles, d_sketch_tab, d_key_cdf;
     std::vector<int32_t> sketch_tab;
+    std::vector<double> key_cdf;
     std::vector<uint64_t> sk_off, sk_moff;      /* hs_sketch_layout of the model */
     uint64_t sk_total = 0, sk_mtotal = 0;
     dev_buf d_sketch, d_sketch_merged;
@@ -123,6 +124,13 @@ static int validate_model(const hs_model_desc *m)
             }
             if (e.i3 == 0 && !(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: source rate must be > 0 (arrival_time_provider.py:75)", i);
             if (e.i0 != HS_ARR_CONSTANT && e.i0 != HS_ARR_POISSON) return fail(HS_ERR_INVALID, "entity %u: bad arrival kind", i);
+            if (e.i2 < 0 || (e.i2 > 0 && (e.i1 <= 0 || !m->key_cdf || (uint64_t)(e.i2 - 1) + (uint64_t)e.i1 > m->n_key_cdf)))
+                return fail(HS_ERR_INVALID, "entity %u: Zipf key table out of range", i);
+            if (e.i2 > 0) {
+                const double *c = m->key_cdf + (e.i2 - 1);
+                for (int32_t k = 0; k < e.i1; ++k)
+                    if (!(c[k] >= 0.0 && c[k] <= 1.0) || (k > 0 && c[k] < c[k - 1])) return fail(HS_ERR_INVALID, "entity %u: cumulative key probabilities must be non-decreasing in [0, 1]", i);
+            }
             if (e.i1 < 0 || (e.i1 > 0 && m->key_population > 0 && (uint32_t)e.i1 != m->key_population)) return fail(HS_ERR_INVALID, "entity %u: key population %d != key_table length %u", i, e.i1, m->key_population);
             break;
         case HS_ENT_SERVER:
@@ -305,6 +313,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     M.cell_d0 = (const double *)E->d_cell_d0.p; M.cell_i0 = (const int32_t *)E->d_cell_i0.p;
     M.profiles = (const hs_profile_desc *)E->d_profiles.p;
     M.sketch_tables = (const int32_t *)E->d_sketch_tab.p; M.sk_total = E->sk_total;
+    M.key_cdf = (const double *)E->d_key_cdf.p;
     M.n_entities = ne; M.n_cells = E->n_cells; M.n_servers = n_servers; M.fel_slots = S; M.block_bytes = block_bytes;
     M.n_backends = (uint32_t)E->backends.size(); M.model_bytes = model_bytes;
     hs_warp_run R;
@@ -418,7 +427,7 @@ int hs_engine_destroy(hs_engine *E)
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
                        &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
                        &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_hist, &E->d_cell_totals, &E->d_conts,
-                       &E->d_sketch_tab, &E->d_sketch, &E->d_sketch_merged};
+                       &E->d_sketch_tab, &E->d_sketch, &E->d_sketch_merged, &E->d_key_cdf};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
@@ -468,6 +477,8 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
         }
     }
     if ((rc = up(E->d_sketch_tab, E->sketch_tab.data(), E->sketch_tab.size() * 4))) return rc;
+    E->key_cdf.assign(m->key_cdf, m->key_cdf + (m->key_cdf ? m->n_key_cdf : 0));
+    if ((rc = up(E->d_key_cdf, E->key_cdf.data(), E->key_cdf.size() * 8))) return rc;
     if ((rc = up(E->d_ents, dev_ents.data(), n * sizeof(hs_entity_desc)))) return rc;
     if ((rc = up(E->d_backends, E->backends.data(), E->backends.size() * 4))) return rc;
     if ((rc = up(E->d_key_table, E->key_table.data(), E->key_table.size() * 4))) return rc;

@@ -131,6 +131,17 @@ HS_HD double hs_uniform(uint64_t seed, uint32_t replica, uint32_t sid, uint64_t 
     return (draw & 1u) ? u1 : u0;
 }
 
+/* Routing key of a request: SimpleEventProvider's context_fn draws client_id from a value distribution over
+ * 0..n-1.  Uniform: int(u * n).  Zipf: bisect.bisect_left(cum_probs, u) clamped to n - 1 (distributions/
+ * zipf.py:112-123), cum_probs computed by the host with the reference's arithmetic.                        */
+HS_HD int32_t hs_routing_key(double u, int32_t n, const double *cum_probs)
+{
+    if (!cum_probs) return (int32_t)HS_D2LL(HS_MUL(u, (double)n));
+    int32_t lo = 0, hi = n;                      /* bisect_left: first index with cum_probs[i] >= u */
+    while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (cum_probs[mid] < u) lo = mid + 1; else hi = mid; }
+    return lo < n - 1 ? lo : n - 1;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Natural logarithm for finite x > 0 (the sampler only ever passes
  * x = 1 - U in [2^-53, 1]).  Classic argument reduction x = 2^k (1+f),

@@ -76,6 +76,7 @@ struct hs_warp_model {
     const double *cell_d0; const int32_t *cell_i0;
     const hs_profile_desc *profiles;
     const int32_t *sketch_tables;   /* per-key hash results of the SKETCH rows                */
+    const double *key_cdf;          /* cumulative key probabilities of the Zipf sources       */
     uint64_t sk_total;              /* bytes of one replica's sketch states                   */
     uint32_t n_entities, n_cells, n_servers, fel_slots;   /* fel_slots = S, multiple of 32 */
     uint32_t block_bytes;           /* bytes of one replica block (multiple of 16)          */

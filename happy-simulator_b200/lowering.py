@@ -59,6 +59,25 @@ def consistent_hash_table(backend_names, virtual_nodes: int, population: int) ->
     return tab
 
 
+def zipf_cdf(population: int, s: float) -> np.ndarray:
+    """ZipfDistribution._cum_probs for values range(population) (distributions/zipf.py:96-110): weights
+    1 / (k + 1)^s, normalised by Python's float sum(), accumulated left to right, last entry forced to 1.0.
+    Computed with the very same Python float operations, so bisect_left on it picks the reference's keys."""
+    n = int(population)
+    if s == 0:
+        probs = [1.0 / n] * n
+    else:
+        w = [1.0 / ((k + 1) ** s) for k in range(n)]
+        total = sum(w)
+        probs = [x / total for x in w]
+    cum, run = [], 0.0
+    for p in probs:
+        run += p
+        cum.append(run)
+    cum[-1] = 1.0
+    return np.array(cum, dtype=np.float64)
+
+
 def hll_table(precision: int, seed: int | None, population: int) -> np.ndarray:
     """HyperLogLog.add's hashing evaluated once per key (sketching/hyperloglog.py:128-165):
     h = first 8 bytes (big endian) of sha256(pack(">Q", seed) + repr(k)); register index = h >> (64 - p),
@@ -229,16 +248,18 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
             if _cls(prov) not in ("SimpleEventProvider", "_SimpleEventProvider"):
                 raise UnsupportedModelError(f"source {name!r}: event provider {_cls(prov)}")
             ctx = getattr(prov, "_context_fn", None)
-            pop = 0
+            pop, cdf = 0, None
             if ctx is not None:
                 pop = int(getattr(ctx, "key_population", 0))
                 if pop <= 0:
                     raise UnsupportedModelError(f"source {name!r}: arbitrary context_fn callbacks cannot run on the "
-                                                "device (use happysim_b200.UniformKeyContext)")
+                                                "device (use happysim_b200.UniformKeyContext / ZipfKeyContext)")
+                if getattr(ctx, "zipf_s", None) is not None:
+                    cdf = zipf_cdf(pop, float(ctx.zipf_s))
             kind, rate, ptuple = _arrival(o._time_provider)
             stop = prov._stop_after
             b.source(name, rate=rate, target=ids[id(prov._target)], poisson=(kind == A.HS_ARR_POISSON),
-                     stop_after_ns=-1 if stop is None else _ns(stop), key_population=pop, profile=ptuple)
+                     stop_after_ns=-1 if stop is None else _ns(stop), key_population=pop, profile=ptuple, key_cdf=cdf)
         elif k == A.HS_ENT_SERVER:
             cm = o._concurrency_model
             if _cls(cm) != "FixedConcurrency":

@@ -27,6 +27,7 @@ class FlatModel:
     cell_i0: np.ndarray | None = None         # int32[n_cells, n]
     profiles: np.ndarray = field(default_factory=lambda: np.zeros(0, A.PROFILE_DTYPE))
     sketch_tables: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    key_cdf: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))
 
     @property
     def n_entities(self) -> int:
@@ -153,6 +154,11 @@ class FlatModel:
             d.n_sketch_table = st.shape[0]
             d.sketch_tables = st.ctypes.data_as(C.POINTER(C.c_int32))
             keep.append(st)
+        if len(self.key_cdf):
+            kc = np.ascontiguousarray(self.key_cdf, dtype=np.float64)
+            d.n_key_cdf = kc.shape[0]
+            d.key_cdf = kc.ctypes.data_as(C.POINTER(C.c_double))
+            keep.append(kc)
         d._keep = keep
         return d
 
@@ -167,6 +173,7 @@ class ModelBuilder:
         self._key_table = np.zeros(0, np.int32)
         self._profiles: list[tuple] = []
         self._sketch_tables: list[np.ndarray] = []
+        self._key_cdf: list[np.ndarray] = []
 
     def _add(self, name, kind, target=-1, i0=0, i1=0, i2=0, l0=-1, d0=0.0, i3=0):
         self._rows.append((kind, target, i0, i1, i2, i3, l0, d0, 0.0))
@@ -174,7 +181,7 @@ class ModelBuilder:
         return len(self._rows) - 1
 
     def source(self, name="Source", *, rate=0.0, target=-1, poisson=True, stop_after_ns=-1, key_population=0,
-               profile=None):
+               profile=None, key_cdf=None):
         """profile: None (ConstantRateProfile(rate)) or ("linear_ramp", duration_s, start_rate, end_rate)
         or ("spike", baseline_rate, spike_rate, warmup_s, spike_duration_s)."""
         i3 = 0
@@ -183,8 +190,14 @@ class ModelBuilder:
             ps = [float(x) for x in profile[1:]] + [0.0] * (5 - len(profile))
             self._profiles.append((kind, 0, ps))
             i3 = len(self._profiles)
+        i2 = 0
+        if key_cdf is not None:       # Zipf keys: the cumulative probabilities (lowering.zipf_cdf), zipf.py:96-123
+            key_cdf = np.ascontiguousarray(key_cdf, dtype=np.float64)
+            assert key_cdf.ndim == 1 and key_cdf.size == key_population
+            i2 = 1 + sum(t.size for t in self._key_cdf)
+            self._key_cdf.append(key_cdf)
         return self._add(name, A.HS_ENT_SOURCE, target, A.HS_ARR_POISSON if poisson else A.HS_ARR_CONSTANT,
-                         key_population, 0, stop_after_ns, float(rate), i3=i3)
+                         key_population, i2, stop_after_ns, float(rate), i3=i3)
 
     def server(self, name="Server", *, concurrency=1, mean_service_s=0.01, exponential=True,
                downstream=-1, capacity=-1, lifo=False):
@@ -266,6 +279,8 @@ class ModelBuilder:
             m.profiles = np.array(self._profiles, dtype=A.PROFILE_DTYPE)
         if self._sketch_tables:
             m.sketch_tables = np.concatenate([t.ravel() for t in self._sketch_tables]).astype(np.int32)
+        if self._key_cdf:
+            m.key_cdf = np.concatenate(self._key_cdf).astype(np.float64)
         return m
 
 

@@ -96,7 +96,9 @@ typedef struct hs_entity_desc {
     int32_t i1;        /* SOURCE: key population (0 = no routing key); SERVER: HS_Q_*;
                           LB: offset of its backend list in hs_model_desc.backends;
                           SKETCH: offset of its table in hs_model_desc.sketch_tables            */
-    int32_t i2;        /* SERVER: HS_SVC_*; LB: number of backends; SKETCH: HLL precision p | CMS depth | BLOOM num_hashes | TOPK k
+    int32_t i2;        /* SOURCE: routing-key distribution: 0 = uniform (distributions/uniform.py:57), k > 0 = Zipf with
+                          the cumulative probabilities key_cdf[k - 1 .. k - 1 + i1) (distributions/zipf.py:96-123);
+                          SERVER: HS_SVC_*; LB: number of backends; SKETCH: HLL precision p | CMS depth | BLOOM num_hashes | TOPK k
                           | TDIGEST buffer size int(compression * 2), tdigest.py:88 */
     int32_t i3;        /* SOURCE: 0 = ConstantRateProfile(d0); k > 0 = profiles[k - 1] (non-constant
                           rate profile, general arrival path); SKETCH: CMS width | BLOOM size_bits
@@ -133,8 +135,11 @@ typedef struct hs_model_desc {
      * each row, count_min_sketch.py:145-155.  BLOOM: [num_hashes][K] = bit index (h1 + i h2) mod size_bits of
      * key k for hash i, bloom_filter.py:147-160.  TOPK: no table. */
     uint32_t n_sketch_table;       /* total length of sketch_tables[]                          */
-    uint32_t reserved3;
+    uint32_t n_key_cdf;            /* total length of key_cdf[]                                */
     const int32_t *sketch_tables;
+    /* ZipfDistribution._cum_probs of the sources whose keys are Zipf distributed (zipf.py:96-110), as the
+     * host computed them; a key is bisect_left(cum_probs, u) clamped to the last index (zipf.py:112-123). */
+    const double *key_cdf;
 } hs_model_desc;
 
 enum { HS_PROF_CONSTANT = 0, HS_PROF_LINEAR_RAMP = 1, HS_PROF_SPIKE = 2 };

@@ -271,9 +271,9 @@ static void handle(orun *R, oev *e)
             pay = new_event(R, R->now, request_kind_for(R, E->d.target), E->d.target);
             pay.created_at = R->now;
             pay.req_id = (uint32_t)E->provider_count;
-            if (E->d.i1 > 0) {            /* routing key: client_id ~ Uniform{0..pop-1}   */
+            if (E->d.i1 > 0) {            /* routing key: client_id ~ Uniform{0..pop-1} or Zipf (zipf.py:112-123) */
                 double u = hs_uniform(R->seed, R->rid, HS_STREAM_ROUTING | ((uint32_t)e->ent << 8), E->key_draws++);
-                pay.key = (int32_t)HS_D2LL(HS_MUL(u, (double)E->d.i1));
+                pay.key = hs_routing_key(u, E->d.i1, E->d.i2 > 0 ? R->m->key_cdf + (E->d.i2 - 1) : NULL);
             }
             have_payload = 1;
         }
@@ -625,5 +625,6 @@ int64_t hs_cpu_next_arrival_profile_ns(int32_t kind, double p0, double p1, doubl
 double hs_cpu_integrate_rate(int32_t kind, double p0, double p1, double p2, double p3, double a, double b)
 { hs_profile_desc P; P.kind = kind; P.pad = 0; P.p[0] = p0; P.p[1] = p1; P.p[2] = p2; P.p[3] = p3;
   return hs_integrate_rate(&P, a, b); }
+int32_t hs_cpu_routing_key(double u, int32_t n, const double *cum_probs) { return hs_routing_key(u, n, cum_probs); }
 void hs_cpu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4)
 { hs_u32x4 r = hs_philox4x32_10(c0, c1, c2, c3, k0, k1); out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w; }

@@ -181,6 +181,22 @@ def sketch_quantiles():
     return b.build()
 
 
+def zipf_hot_keys(K=300, s=1.1, n_servers=6):
+    """client_id ~ Zipf(s) -> LoadBalancer(ConsistentHash) -> servers -> TopKCollector: hot keys pile on a few
+    ring nodes and Space-Saving has real heavy hitters to find (distributions/zipf.py:27-123)."""
+    names = [f"S{i}" for i in range(n_servers)]
+    tab = RH.ring_table_from_reference(names, 30, K)
+    b = hs.ModelBuilder()
+    src = b.source(rate=150.0, key_population=K, key_cdf=hs.zipf_cdf(K, s))
+    servers = [b.server(nm, concurrency=2, mean_service_s=0.02) for nm in names]
+    top = b.sketch_topk("heavy", k=8, key_population=K)
+    lb = b.load_balancer(backends=servers, key_table=tab)
+    b.set_target(src, lb)
+    for sv in servers:
+        b.set_target(sv, top)
+    return b.build(), {src: s}
+
+
 def philox_cases():
     c = {}
     c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
@@ -213,6 +229,8 @@ def philox_cases():
     m, seeds = sketch_members()
     c["sketch_bloom_topk"] = (m, dict(seed=23, rid=2, end_s=5, sketch_seeds=seeds))
     c["sketch_tdigest"] = (sketch_quantiles(), dict(seed=29, rid=0, end_s=40))
+    m, zs = zipf_hot_keys()
+    c["zipf_chash_topk"] = (m, dict(seed=37, rid=5, end_s=6, chash_vnodes=30, zipf_s=zs))
     return c
 
 
@@ -226,7 +244,7 @@ def save_case(path, model, ref, meta):
         n_records=np.int64(len(rec)), records=rec[:MAX_REC],
         n_samples=np.int64(len(ref["sink_samples"])), sink_samples=ref["sink_samples"][:MAX_SMP],
         n_service=np.int64(len(ref["service_samples"])), service_samples=ref["service_samples"][:MAX_SMP],
-        case_name=np.array(os.path.basename(path)[:-4]), sketch_tables=model.sketch_tables, sketch_state=ref.get("sketches", np.zeros(0, np.uint8)),
+        case_name=np.array(os.path.basename(path)[:-4]), key_cdf=model.key_cdf, sketch_tables=model.sketch_tables, sketch_state=ref.get("sketches", np.zeros(0, np.uint8)),
         **{f"sketch_answer_{i}": a for i, a in ref.get("sketch_answers", {}).items()},
         **{f"sketch_seed_{i}": np.int64(-1 if sd is None else sd) for i, sd in (meta.get("sketch_seeds") or {}).items()},
         **{k: v for k, v in meta.items() if isinstance(v, np.ndarray)},
@@ -239,7 +257,8 @@ def main():
         if only not in name:
             continue
         ref = RH.run_reference(model, seed=kw["seed"], rid=kw["rid"], end_ns=int(kw["end_s"] * 1e9),
-                               chash_vnodes=kw.get("chash_vnodes"), sketch_seeds=kw.get("sketch_seeds"))
+                               chash_vnodes=kw.get("chash_vnodes"), sketch_seeds=kw.get("sketch_seeds"),
+                               zipf_s=kw.get("zipf_s"))
         save_case(os.path.join(HERE, f"philox_{name}.npz"), model, ref, kw)
         print(f"philox_{name}: {len(ref['records'])} events, hash {int(ref['summaries']['order_hash'][0]):#x}")
 

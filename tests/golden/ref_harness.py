@@ -31,7 +31,7 @@ def _import_reference():
 
 
 def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, stock_rng=False,
-                  max_records=None, sketch_seeds=None):
+                  max_records=None, sketch_seeds=None, zipf_s=None):
     """Run the reference on ``model`` (a happysim_b200.FlatModel); replica word ``rid``.
 
     stock_rng=True leaves the reference's own MT19937 streams in place (seeded
@@ -171,7 +171,25 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         stop = Instant(int(e["l0"])) if int(e["l0"]) >= 0 else None
         pop = int(e["i1"])
         ctx_fn = None
-        if pop > 0:
+        if pop > 0 and int(e["i2"]) > 0:
+            # the reference's own ZipfDistribution (its cum_probs, its bisect), fed with the Philox uniforms
+            from happysimulator.distributions.zipf import ZipfDistribution
+
+            class _PhiloxUniform:
+                def __init__(self, sid):
+                    self.sid, self.n = sid, 0
+
+                def random(self):
+                    u = L.hs_cpu_uniform(seed, rid, A.HS_STREAM_ROUTING | (self.sid << 8), self.n)
+                    self.n += 1
+                    return u
+
+            zd = ZipfDistribution(range(pop), s=float((zipf_s or {})[i]))
+            zd._rng = _PhiloxUniform(i)
+
+            def ctx_fn(time, count, _zd=zd):
+                return {"created_at": time, "request_id": count, "metadata": {"client_id": _zd.sample()}}
+        elif pop > 0:
             def ctx_fn(time, count, _sid=i, _pop=pop):
                 u = L.hs_cpu_uniform(seed, rid, A.HS_STREAM_ROUTING | (_sid << 8), count - 1)
                 return {"created_at": time, "request_id": count, "metadata": {"client_id": int(u * _pop)}}

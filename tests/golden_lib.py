@@ -21,6 +21,8 @@ def load(name):
         model.profiles = z["profiles"]
     if "sketch_tables" in z.files and len(z["sketch_tables"]):
         model.sketch_tables = z["sketch_tables"]
+    if "key_cdf" in z.files and len(z["key_cdf"]):
+        model.key_cdf = z["key_cdf"]
     seed, rid, end_ns = (int(v) for v in z["meta"])
     return model, dict(seed=seed, rid_base=rid, end_ns=end_ns), z
 

@@ -47,6 +47,8 @@ def lib():
         L.hs_cpu_integrate_rate.restype = C.c_double
         L.hs_cpu_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
         L.hs_cpu_philox.restype = None
+        L.hs_cpu_routing_key.argtypes = [C.c_double, C.c_int32, C.POINTER(C.c_double)]
+        L.hs_cpu_routing_key.restype = C.c_int32
         L.hs_sketch_layout.argtypes = [C.POINTER(A.ModelDesc)] + [C.POINTER(C.c_uint64)] * 4
         L.hs_sketch_layout.restype = C.c_int
         _lib = L

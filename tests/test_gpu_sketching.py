@@ -113,6 +113,37 @@ def test_tdigest_ensemble_matches_oracle_bit_for_bit(eng, eng_id):
 
 
 @pytest.mark.parametrize("eng_id", [1, 3])
+def test_zipf_keys_heavy_hitters(eng, eng_id):
+    """client_id ~ Zipf(1.2) (bisect over the host's cumulative table) -> consistent-hash ring -> TopK + CMS:
+    the device draws the reference's keys, so the heavy hitters and their counts match the oracle exactly."""
+    K, n_servers = 2000, 12
+    tab = hs.consistent_hash_table([f"S{i}" for i in range(n_servers)], 50, K)
+    b = hs.ModelBuilder()
+    # the hottest key alone is ~19 % of the traffic and lands on one server: keep that server below capacity
+    src = b.source(rate=25.0 * n_servers, key_population=K, key_cdf=hs.zipf_cdf(K, 1.2))
+    servers = [b.server(f"S{i}", concurrency=2, mean_service_s=0.02) for i in range(n_servers)]
+    top = b.sketch_topk("heavy", k=10, key_population=K)
+    cms = b.sketch_cms("freq", width=64, depth=4, table=hs.cms_table(64, 4, 1, K))
+    lb = b.load_balancer(backends=servers, key_table=tab)
+    b.set_target(src, lb)
+    for k, sv in enumerate(servers):
+        b.set_target(sv, top if k % 2 else cms)
+    model = b.build()
+    kw = dict(seed=41, end_ns=3 * 10**9, n_replicas=19, record_cap=40000, sample_cap=16, service_cap=4000,
+              queue_ring=512)
+    eng.upload(model)
+    eng.run(engine.make_params(engine=eng_id, **kw))
+    got = eng.read_outputs()
+    want = O.oracle_run(model, O.make_params(**kw))
+    assert int(got["summaries"]["status"].max()) == 0
+    assert_same(got, want)
+    assert got["sketches"].tobytes() == want["sketches"].tobytes()
+    t = hs.TopK(10); t._load_device_state(model.sketch_views(got["sketches"])[top][0], int(got["entity_stats"][0][top]["c1"]))
+    hot = [fe.item for fe in t.top(3)]
+    assert min(hot) < 20 and t.item_count > 150          # the hottest ranks dominate
+
+
+@pytest.mark.parametrize("eng_id", [1, 3])
 def test_sketch_state_survives_windows(eng, eng_id):
     model, kw, z = G.load("philox_sketch_cms_farm")
     caps = dict(G.caps(z), engine=eng_id, n_replicas=3, rid_base=0, seed=kw["seed"])

@@ -104,3 +104,31 @@ def test_nonconstant_profile_golden_vectors_of_the_reference():
     assert all(abs(a - b) < 1e-8 for a, b in zip(series(1, (10.0, 10.0, 100.0, 0.0), 10), up))
     assert all(abs(a - b) < 1e-8 for a, b in zip(series(1, (10.0, 100.0, 10.0, 0.0), 10), down))
     assert all(abs(a - b) < 1e-8 for a, b in zip(series(2, (10.0, 100.0, 2.0, 1.0), 30), spike))
+
+
+def test_zipf_routing_keys_follow_the_reference_inverse_transform():
+    """distributions/zipf.py:96-123: cum_probs as the reference computes them (weights 1/(k+1)^s, float sum(),
+    running sum, last forced to 1.0) and bisect_left over them, clamped -- hs_routing_key is that bisect."""
+    import bisect
+    import ctypes as C
+    import happysim_b200 as hs
+    L = O.lib()
+    for K, s in ((1, 1.0), (7, 0.0), (50, 1.0), (1000, 1.3)):
+        cum = hs.zipf_cdf(K, s)
+        assert cum[-1] == 1.0 and np.all(np.diff(cum) >= 0) and len(cum) == K
+        if s == 0.0:
+            assert cum[0] == 1.0 / K
+        else:
+            w = [1.0 / ((k + 1) ** s) for k in range(K)]
+            assert cum[0] == w[0] / sum(w)
+        cp = cum.ctypes.data_as(C.POINTER(C.c_double))
+        us = list(np.random.RandomState(K).random_sample(400)) + [0.0, float(cum[0]), float(np.nextafter(cum[0], 1)), 0.9999999999999999]
+        for u in us:
+            want = min(bisect.bisect_left(list(cum), u), K - 1)
+            assert L.hs_cpu_routing_key(u, K, cp) == want
+    assert L.hs_cpu_routing_key(0.37, 10, None) == 3          # uniform: int(u * n)
+    # rank 0 is the hottest key
+    cum = hs.zipf_cdf(100, 1.0)
+    keys = [L.hs_cpu_routing_key(float(u), 100, cum.ctypes.data_as(C.POINTER(C.c_double))) for u in np.random.RandomState(3).random_sample(5000)]
+    counts = np.bincount(keys, minlength=100)
+    assert counts[0] > counts[1] > counts[5] > counts[50]

@@ -625,6 +625,12 @@ int64_t hs_cpu_next_arrival_profile_ns(int32_t kind, double p0, double p1, doubl
 double hs_cpu_integrate_rate(int32_t kind, double p0, double p1, double p2, double p3, double a, double b)
 { hs_profile_desc P; P.kind = kind; P.pad = 0; P.p[0] = p0; P.p[1] = p1; P.p[2] = p2; P.p[3] = p3;
   return hs_integrate_rate(&P, a, b); }
+/* the shared sketch steps of csrc/hs_sketch.h, callable on their own (tests/test_sketch_kats.py feeds them the
+ * streams whose answers the reference's sketch classes gave) */
+void hs_cpu_sketch_add(uint8_t *state, const int32_t *tab, int32_t algo, int32_t p_or_depth, int32_t width, int64_t K, int32_t key)
+{ hs_sketch_add(state, tab, algo, p_or_depth, width, K, key); }
+int hs_cpu_tdigest_add(uint8_t *state, double compression, uint32_t buf_size, uint32_t cap, double value)
+{ return hs_tdigest_add(state, compression, buf_size, cap, value); }
 int32_t hs_cpu_routing_key(double u, int32_t n, const double *cum_probs) { return hs_routing_key(u, n, cum_probs); }
 void hs_cpu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4)
 { hs_u32x4 r = hs_philox4x32_10(c0, c1, c2, c3, k0, k1); out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w; }

@@ -12,8 +12,10 @@
  * sampler of happy-simulator_b200/csrc/hs_sampler.h) by
  * tests/golden/gen_golden.py; the fixtures it wrote are committed under
  * tests/golden/ and tests/test_oracle_golden.py replays them.  The reference's
- * own deterministic known-answer tests for this path are
- * restated in tests/test_oracle_reference_kats.py.
+ * own deterministic known answers for this path are
+ * restated in tests/test_oracle_golden.py (README quick-start, counter KAT, the
+ * stock-seed runs), tests/test_sampler.py (arrival-time regression vectors) and
+ * tests/test_sketch_kats.py (the sketch classes' answers on fixed streams).
  *
  * The structure follows the reference one to one (paths under /root/reference):
  *   run loop            happysimulator/core/simulation.py:449-505 (_execute_until)

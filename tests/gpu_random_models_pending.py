@@ -1,0 +1,36 @@
+"""Randomised differential testing on the device: 24 seeded models mixing every lowered feature, both general
+engines (and the automatic choice) against the CPU oracle -- event records, statistics, samples, sketch states."""
+import pytest
+
+import oracle_lib as O
+from happysim_b200 import engine
+from random_models import random_model
+from test_gpu_lane_parity import assert_same
+from test_random_models import SEEDS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = engine.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_random_model_on_every_engine(eng, seed):
+    model, end_s, what = random_model(seed)
+    kw = dict(seed=1000 + seed, end_ns=int(end_s * 1e9), n_replicas=5, record_cap=12000, sample_cap=1500, service_cap=1500,
+              queue_ring=1024)
+    want = O.oracle_run(model, O.make_params(**kw))
+    eng.upload(model)
+    for eng_id in (0, 1, 3):
+        eng.run(engine.make_params(engine=eng_id, **kw))
+        got = eng.read_outputs()
+        try:
+            assert_same(got, want)
+            if want.get("sketches") is not None:
+                assert got["sketches"].tobytes() == want["sketches"].tobytes(), "sketch states differ"
+        except AssertionError as e:
+            raise AssertionError(f"{what}, engine {eng_id}: {e}") from None

@@ -1,0 +1,87 @@
+"""Seeded random models over everything the lowering supports (sources with rate profiles, stop times and
+uniform / Zipf client ids; load balancers; tandem, bounded, LIFO and multi-slot servers; sinks, counters, probes
+and the five sketch collectors).  Test infrastructure: the differential tests run each model on the CPU oracle
+and on the device engines and compare every output bit for bit."""
+import numpy as np
+
+import happysim_b200 as hs
+
+
+def random_model(seed: int):
+    """-> (FlatModel, end_seconds, description)"""
+    rng = np.random.RandomState(seed)
+    b = hs.ModelBuilder()
+    K = int(rng.choice([0, 0, 16, 200]))
+    zipf = K > 0 and rng.rand() < 0.5
+    n_src = 1 + int(rng.rand() < 0.3)
+    base_rate = float(rng.choice([20.0, 60.0, 120.0]))
+    srcs = []
+    for i in range(n_src):
+        kw = dict(rate=base_rate / n_src, poisson=bool(rng.rand() < 0.7), key_population=K)
+        if rng.rand() < 0.2:
+            kw["stop_after_ns"] = int(rng.uniform(0.5, 3.0) * 1e9)
+        r = rng.rand()
+        if r < 0.15:
+            kw["profile"] = ("linear_ramp", float(rng.uniform(1, 4)), kw["rate"], kw["rate"] * float(rng.uniform(0.5, 2.0)))
+        elif r < 0.3:
+            kw["profile"] = ("spike", kw["rate"], kw["rate"] * 3.0, float(rng.uniform(0.2, 1.5)), float(rng.uniform(0.2, 1.0)))
+        if zipf:
+            kw["key_cdf"] = hs.zipf_cdf(K, float(rng.choice([0.0, 0.8, 1.3])))
+        srcs.append(b.source(f"Src{i}", **kw))
+
+    def sink():
+        kinds = ["sink", "counter", "tdigest"] + (["hll", "cms", "bloom", "topk"] if K else [])
+        k = kinds[rng.randint(len(kinds))]
+        if k == "sink":
+            return b.sink(f"Sink{b_count()}")
+        if k == "counter":
+            return b.counter(f"Counter{b_count()}")
+        if k == "tdigest":
+            return b.sketch_tdigest(f"TD{b_count()}", compression=float(rng.choice([5.0, 20.0])))
+        if k == "hll":
+            p = int(rng.choice([4, 7]))
+            return b.sketch_hll(f"HLL{b_count()}", precision=p, table=hs.hll_table(p, seed, K))
+        if k == "cms":
+            return b.sketch_cms(f"CMS{b_count()}", width=9, depth=3, table=hs.cms_table(9, 3, seed, K))
+        if k == "bloom":
+            return b.sketch_bloom(f"BF{b_count()}", size_bits=77, num_hashes=3, table=hs.bloom_table(77, 3, seed, K))
+        return b.sketch_topk(f"Top{b_count()}", k=int(rng.choice([2, 6])), key_population=K)
+
+    def b_count():
+        return len(b._rows)
+
+    def server(downstream, mean_scale=1.0):
+        c = int(rng.choice([1, 1, 2, 4]))
+        mean = mean_scale * c / base_rate * float(rng.uniform(0.3, 1.1))
+        return b.server(f"Srv{b_count()}", concurrency=c, mean_service_s=mean, exponential=bool(rng.rand() < 0.7),
+                        downstream=downstream, capacity=int(rng.choice([-1, -1, -1, 0, 3])), lifo=bool(rng.rand() < 0.3))
+
+    shape = rng.choice(["single", "tandem", "lb", "lb_tandem", "direct"])
+    if shape == "direct":
+        head = sink()
+    elif shape == "single":
+        head = server(sink())
+    elif shape == "tandem":
+        head = server(server(sink()))
+    else:
+        n = int(rng.randint(2, 6))
+        shared = sink() if rng.rand() < 0.5 else None
+        backs = []
+        for _ in range(n):
+            dst = shared if shared is not None else sink()
+            if shape == "lb_tandem" and rng.rand() < 0.5:
+                dst = server(dst)
+            backs.append(server(dst, mean_scale=n))
+        table = None
+        if K and rng.rand() < 0.6:
+            table = rng.randint(0, n, size=K).astype(np.int32)
+        head = b.load_balancer(f"LB{b_count()}", backends=backs, key_table=table)
+    for s in srcs:
+        b.set_target(s, head)
+    servers = [i for i, r in enumerate(b._rows) if r[0] == hs._abi.HS_ENT_SERVER]
+    if servers and rng.rand() < 0.4:
+        b.probe("Probe", target=int(rng.choice(servers)), metric=str(rng.choice(["depth", "active_requests", "stats_accepted"])),
+                interval_s=float(rng.choice([0.05, 0.25])))
+    model = b.build()
+    end_s = float(rng.uniform(1.5, 4.0))
+    return model, end_s, f"seed {seed}: {shape}, K={K}{' zipf' if zipf else ''}, {n_src} source(s), {model.n_entities} entities"

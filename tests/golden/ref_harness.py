@@ -409,6 +409,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             elif algo == A.HS_SK_BLOOM:     # contains(k) for every key, then the bit count
                 ans[i] = np.array([int(o.sketch.contains(k)) for k in range(int(ents["l0"][i]))] + [o.sketch._bits_set],
                                   dtype=np.int64)
+            elif algo == A.HS_SK_TDIGEST and o.sample_count == 0:
+                ans[i] = np.zeros(0, np.int64)      # quantile() of an empty digest raises (tdigest.py:206-207)
             elif algo == A.HS_SK_TDIGEST:   # percentiles, cdf at a few points, centroid count (as float64 bits)
                 qs = [0.0, 0.001, 0.01, 0.25, 0.5, 0.75, 0.9, 0.99, 0.999, 1.0]
                 vals = [o.quantile(q) for q in qs] + [o.cdf(v) for v in (0.0, 0.01, 0.05, 0.1, 0.3, 1.0, 5.0)] + \

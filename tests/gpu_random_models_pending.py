@@ -6,7 +6,7 @@ import oracle_lib as O
 from happysim_b200 import engine
 from random_models import random_model
 from test_gpu_lane_parity import assert_same
-from test_random_models import SEEDS
+from test_random_models import SEEDS, check_against_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -24,7 +24,10 @@ def test_random_model_on_every_engine(eng, seed):
     kw = dict(seed=1000 + seed, end_ns=int(end_s * 1e9), n_replicas=5, record_cap=12000, sample_cap=1500, service_cap=1500,
               queue_ring=1024)
     want = O.oracle_run(model, O.make_params(**kw))
+    kw1 = dict(kw, n_replicas=1)                 # the fixture's replica: word 0 alone, as the reference ran it
     eng.upload(model)
+    eng.run(engine.make_params(**kw1))
+    check_against_reference(model, eng.read_outputs(), seed)
     for eng_id in (0, 1, 3):
         eng.run(engine.make_params(engine=eng_id, **kw))
         got = eng.read_outputs()

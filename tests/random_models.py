@@ -7,9 +7,10 @@ import numpy as np
 import happysim_b200 as hs
 
 
-def random_model(seed: int):
-    """-> (FlatModel, end_seconds, description)"""
+def random_model(seed: int, with_extras: bool = False):
+    """-> (FlatModel, end_seconds, description[, extras for tests/golden/ref_harness.run_reference])"""
     rng = np.random.RandomState(seed)
+    extras = {"zipf_s": {}, "sketch_seeds": {}, "random_key_table": False}
     b = hs.ModelBuilder()
     K = int(rng.choice([0, 0, 16, 200]))
     zipf = K > 0 and rng.rand() < 0.5
@@ -25,9 +26,12 @@ def random_model(seed: int):
             kw["profile"] = ("linear_ramp", float(rng.uniform(1, 4)), kw["rate"], kw["rate"] * float(rng.uniform(0.5, 2.0)))
         elif r < 0.3:
             kw["profile"] = ("spike", kw["rate"], kw["rate"] * 3.0, float(rng.uniform(0.2, 1.5)), float(rng.uniform(0.2, 1.0)))
+        zs = float(rng.choice([0.0, 0.8, 1.3]))
         if zipf:
-            kw["key_cdf"] = hs.zipf_cdf(K, float(rng.choice([0.0, 0.8, 1.3])))
+            kw["key_cdf"] = hs.zipf_cdf(K, zs)
         srcs.append(b.source(f"Src{i}", **kw))
+        if zipf:
+            extras["zipf_s"][srcs[-1]] = zs
 
     def sink():
         kinds = ["sink", "counter", "tdigest"] + (["hll", "cms", "bloom", "topk"] if K else [])
@@ -40,11 +44,17 @@ def random_model(seed: int):
             return b.sketch_tdigest(f"TD{b_count()}", compression=float(rng.choice([5.0, 20.0])))
         if k == "hll":
             p = int(rng.choice([4, 7]))
-            return b.sketch_hll(f"HLL{b_count()}", precision=p, table=hs.hll_table(p, seed, K))
+            i = b.sketch_hll(f"HLL{b_count()}", precision=p, table=hs.hll_table(p, seed, K))
+            extras["sketch_seeds"][i] = seed
+            return i
         if k == "cms":
-            return b.sketch_cms(f"CMS{b_count()}", width=9, depth=3, table=hs.cms_table(9, 3, seed, K))
+            i = b.sketch_cms(f"CMS{b_count()}", width=9, depth=3, table=hs.cms_table(9, 3, seed, K))
+            extras["sketch_seeds"][i] = seed
+            return i
         if k == "bloom":
-            return b.sketch_bloom(f"BF{b_count()}", size_bits=77, num_hashes=3, table=hs.bloom_table(77, 3, seed, K))
+            i = b.sketch_bloom(f"BF{b_count()}", size_bits=77, num_hashes=3, table=hs.bloom_table(77, 3, seed, K))
+            extras["sketch_seeds"][i] = seed
+            return i
         return b.sketch_topk(f"Top{b_count()}", k=int(rng.choice([2, 6])), key_population=K)
 
     def b_count():
@@ -75,6 +85,7 @@ def random_model(seed: int):
         table = None
         if K and rng.rand() < 0.6:
             table = rng.randint(0, n, size=K).astype(np.int32)
+            extras["random_key_table"] = True
         head = b.load_balancer(f"LB{b_count()}", backends=backs, key_table=table)
     for s in srcs:
         b.set_target(s, head)
@@ -84,4 +95,5 @@ def random_model(seed: int):
                 interval_s=float(rng.choice([0.05, 0.25])))
     model = b.build()
     end_s = float(rng.uniform(1.5, 4.0))
-    return model, end_s, f"seed {seed}: {shape}, K={K}{' zipf' if zipf else ''}, {n_src} source(s), {model.n_entities} entities"
+    what = f"seed {seed}: {shape}, K={K}{' zipf' if zipf else ''}, {n_src} source(s), {model.n_entities} entities"
+    return (model, end_s, what, extras) if with_extras else (model, end_s, what)

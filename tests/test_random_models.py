@@ -19,3 +19,43 @@ def test_random_model_validates_and_runs_on_the_oracle(seed):
     assert a["summaries"].tobytes() == b["summaries"].tobytes(), what
     assert int(a["summaries"]["events_processed"].min()) > 0, what
     assert int(a["summaries"]["events_processed"].max()) < 12000, what      # the recorder holds the whole run
+
+
+# ---- the same models on the UNMODIFIED reference (tests/golden/random_models.npz, gen_random_golden.py) ---------
+import os                                    # noqa: E402
+
+import numpy as np                           # noqa: E402
+
+REF = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "random_models.npz"))
+
+
+def reference_answer(seed):
+    """(summary row, entity stats, canonical sketch bytes) the reference produced for replica word 0, or None for
+    the models that have no reference counterpart (arbitrary key table)."""
+    if seed not in REF["seeds"]:
+        return None
+    return REF[f"s{seed}_summary"][0], REF[f"s{seed}_stats"][0], REF[f"s{seed}_sketches"]
+
+
+def check_against_reference(model, out, seed, r=0):
+    ans = reference_answer(seed)
+    if ans is None:
+        return False
+    ws, wstats, wsk = ans
+    s = out["summaries"][r]
+    for f in ("events_processed", "final_time_ns", "order_hash", "heap_left", "n_sink_samples", "n_service_samples"):
+        assert int(s[f]) == int(ws[f]), (seed, f, int(s[f]), int(ws[f]))
+    assert out["entity_stats"][r].tobytes() == wstats.tobytes(), (seed, "entity statistics")
+    if len(wsk):
+        assert model.canonical_sketches(out["sketches"])[r].tobytes() == wsk.tobytes(), (seed, "sketch states")
+    return True
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_oracle_matches_the_reference_on_random_models(seed):
+    """Order hash over every processed event, counts, statistics and sketch states of 23 random models, as the
+    unmodified reference produced them with the Philox plug-ins."""
+    model, end_s, what = random_model(seed)
+    out = O.oracle_run(model, O.make_params(seed=1000 + seed, end_ns=int(end_s * 1e9), n_replicas=1))
+    if not check_against_reference(model, out, seed):
+        pytest.skip("arbitrary key table: no reference counterpart")

@@ -1,4 +1,4 @@
-"""Randomised differential testing on the device: 24 seeded models mixing every lowered feature, both general
+"""Randomised differential testing on the device: 64 seeded models mixing every lowered feature, both general
 engines (and the automatic choice) against the CPU oracle -- event records, statistics, samples, sketch states."""
 import pytest
 

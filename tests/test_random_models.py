@@ -6,7 +6,7 @@ import oracle_lib as O
 from happysim_b200 import engine
 from random_models import random_model
 
-SEEDS = list(range(24))
+SEEDS = list(range(64))
 
 
 @pytest.mark.parametrize("seed", SEEDS)
@@ -53,7 +53,7 @@ def check_against_reference(model, out, seed, r=0):
 
 @pytest.mark.parametrize("seed", SEEDS)
 def test_oracle_matches_the_reference_on_random_models(seed):
-    """Order hash over every processed event, counts, statistics and sketch states of 23 random models, as the
+    """Order hash over every processed event, counts, statistics and sketch states of the random models, as the
     unmodified reference produced them with the Philox plug-ins."""
     model, end_s, what = random_model(seed)
     out = O.oracle_run(model, O.make_params(seed=1000 + seed, end_ns=int(end_s * 1e9), n_replicas=1))

@@ -37,3 +37,27 @@ def test_random_model_on_every_engine(eng, seed):
                 assert got["sketches"].tobytes() == want["sketches"].tobytes(), "sketch states differ"
         except AssertionError as e:
             raise AssertionError(f"{what}, engine {eng_id}: {e}") from None
+
+
+@pytest.mark.parametrize("seed", SEEDS[::2])
+def test_random_model_cut_into_windows(eng, seed):
+    """Pause / resume on both general engines: a run cut at three arbitrary instants yields the same records,
+    statistics, samples and sketch states as the uncut run (state parked in HBM between the calls)."""
+    model, end_s, what = random_model(seed)
+    end_ns = int(end_s * 1e9)
+    kw = dict(seed=1000 + seed, n_replicas=4, record_cap=12000, sample_cap=1500, service_cap=1500, queue_ring=1024)
+    want = O.oracle_run(model, O.make_params(end_ns=end_ns, **kw))
+    cuts = [end_ns // 7, end_ns // 2 + 3, end_ns - 1]
+    eng.upload(model)
+    for eng_id in (1, 3):
+        eng.run(engine.make_params(end_ns=end_ns, window_end_ns=cuts[0], engine=eng_id, **kw))
+        for c in cuts[1:]:
+            eng.run(engine.make_params(end_ns=end_ns, window_end_ns=c, resume=1, engine=eng_id, **kw))
+        eng.run(engine.make_params(end_ns=end_ns, resume=1, engine=eng_id, **kw))
+        got = eng.read_outputs()
+        try:
+            assert_same(got, want)
+            if want.get("sketches") is not None:
+                assert got["sketches"].tobytes() == want["sketches"].tobytes(), "sketch states differ"
+        except AssertionError as e:
+            raise AssertionError(f"{what}, engine {eng_id}, windows: {e}") from None

@@ -97,3 +97,40 @@ def random_model(seed: int, with_extras: bool = False):
     end_s = float(rng.uniform(1.5, 4.0))
     what = f"seed {seed}: {shape}, K={K}{' zipf' if zipf else ''}, {n_src} source(s), {model.n_entities} entities"
     return (model, end_s, what, extras) if with_extras else (model, end_s, what)
+
+
+def random_lane_model(seed: int):
+    """Source -> Server -> Sink | Counter | nothing: the topology the lane engine keeps in registers, with random
+    arrival / service kinds, concurrency, queue policy and capacity, stop times and rate profiles.  Constant
+    arrivals against constant service times make arrivals and completions collide on the same nanosecond (the
+    generic tie path).  -> (FlatModel, end_seconds, description)"""
+    rng = np.random.RandomState(10_000 + seed)
+    b = hs.ModelBuilder()
+    rate = float(rng.choice([4.0, 10.0, 25.0, 100.0]))
+    poisson = bool(rng.rand() < 0.6)
+    kw = dict(rate=rate, poisson=poisson)
+    if rng.rand() < 0.2:
+        kw["stop_after_ns"] = int(rng.uniform(0.3, 2.0) * 1e9)
+    r = rng.rand()
+    if r < 0.12:
+        kw["profile"] = ("linear_ramp", float(rng.uniform(1, 3)), rate, rate * float(rng.uniform(0.5, 2.0)))
+    elif r < 0.24:
+        kw["profile"] = ("spike", rate, rate * 2.5, float(rng.uniform(0.2, 1.0)), float(rng.uniform(0.2, 1.0)))
+    src = b.source(**kw)
+    c = int(rng.choice([1, 1, 2, 3, 8]))
+    exponential = bool(rng.rand() < 0.6)
+    # constant/constant with an integer ratio -> exact ties between ticks and completions
+    mean = (c / rate) * float(rng.choice([0.5, 1.0, 2.0])) if not exponential and not poisson else (c / rate) * float(rng.uniform(0.3, 1.2))
+    srv = b.server(concurrency=c, mean_service_s=mean, exponential=exponential, capacity=int(rng.choice([-1, -1, 0, 2, 5])),
+                   lifo=bool(rng.rand() < 0.3))
+    dst = int(rng.choice([0, 0, 1, 2]))
+    b.set_target(src, srv)
+    if dst == 0:
+        b.set_target(srv, b.sink())
+    elif dst == 1:
+        b.set_target(srv, b.counter())
+    model = b.build()
+    end_s = float(rng.uniform(1.0, 5.0))
+    what = (f"lane seed {seed}: rate {rate} {'poisson' if poisson else 'constant'}, c={c}, "
+            f"{'exp' if exponential else 'const'} service {mean:.4f}, dst {('sink', 'counter', 'none')[dst]}")
+    return model, end_s, what

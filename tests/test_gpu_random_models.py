@@ -61,3 +61,38 @@ def test_random_model_cut_into_windows(eng, seed):
                 assert got["sketches"].tobytes() == want["sketches"].tobytes(), "sketch states differ"
         except AssertionError as e:
             raise AssertionError(f"{what}, engine {eng_id}, windows: {e}") from None
+
+
+from random_models import random_lane_model          # noqa: E402
+from test_random_models import LANE_SEEDS            # noqa: E402
+
+
+@pytest.mark.parametrize("seed", LANE_SEEDS)
+def test_random_single_server_model_on_lane_and_general_engines(eng, seed):
+    """The register-resident lane engine (recorder and summary kernels, uncut and cut into windows) and the
+    thread engine against the oracle on random Source -> Server -> Sink|Counter|- models, including exact
+    tick/completion ties."""
+    model, end_s, what = random_lane_model(seed)
+    end_ns = int(end_s * 1e9)
+    kw = dict(seed=77 + seed, n_replicas=70, queue_ring=2048)
+    caps = dict(record_cap=12000, sample_cap=3000, service_cap=3000)
+    want = O.oracle_run(model, O.make_params(end_ns=end_ns, **kw, **caps))
+    eng.upload(model)
+    try:
+        for eng_id in (2, 3):
+            eng.run(engine.make_params(end_ns=end_ns, engine=eng_id, **kw, **caps))
+            assert_same(eng.read_outputs(), want)
+        # summary kernels (no recorder): summaries and statistics only
+        eng.run(engine.make_params(end_ns=end_ns, engine=2, **kw))
+        got = eng.read_outputs()
+        assert got["summaries"].tobytes() == want["summaries"].tobytes(), "summary kernel: summaries differ"
+        assert got["entity_stats"].tobytes() == want["entity_stats"].tobytes(), "summary kernel: statistics differ"
+        # the lane engine cut into windows
+        cuts = [end_ns // 5, end_ns // 2 + 1, end_ns - 2]
+        eng.run(engine.make_params(end_ns=end_ns, window_end_ns=cuts[0], engine=2, **kw, **caps))
+        for c in cuts[1:]:
+            eng.run(engine.make_params(end_ns=end_ns, window_end_ns=c, resume=1, engine=2, **kw, **caps))
+        eng.run(engine.make_params(end_ns=end_ns, resume=1, engine=2, **kw, **caps))
+        assert_same(eng.read_outputs(), want)
+    except AssertionError as e:
+        raise AssertionError(f"{what}: {e}") from None

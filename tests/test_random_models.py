@@ -59,3 +59,15 @@ def test_oracle_matches_the_reference_on_random_models(seed):
     out = O.oracle_run(model, O.make_params(seed=1000 + seed, end_ns=int(end_s * 1e9), n_replicas=1))
     if not check_against_reference(model, out, seed):
         pytest.skip("arbitrary key table: no reference counterpart")
+
+
+LANE_SEEDS = list(range(48))
+
+
+@pytest.mark.parametrize("seed", LANE_SEEDS)
+def test_random_lane_model_runs_on_the_oracle(seed):
+    from random_models import random_lane_model
+    model, end_s, what = random_lane_model(seed)
+    engine.validate_model(model)
+    out = O.oracle_run(model, O.make_params(seed=77 + seed, end_ns=int(end_s * 1e9), n_replicas=2))
+    assert 0 < int(out["summaries"]["events_processed"].max()) < 12000, what

@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), HERE]
 
 import ref_harness as RH                      # noqa: E402
-from random_models import random_model        # noqa: E402
-from test_random_models import SEEDS          # noqa: E402
+from random_models import random_lane_model, random_model        # noqa: E402
+from test_random_models import LANE_SEEDS, SEEDS                 # noqa: E402
 
 out = {}
 kept = []
@@ -31,6 +31,12 @@ for seed in SEEDS:
     out[f"s{seed}_summary"] = ref["summaries"]
     out[f"s{seed}_stats"] = ref["entity_stats"]
     out[f"s{seed}_sketches"] = m.canonical_sketches(ref["sketches"])[0] if "sketches" in ref else np.zeros(0, np.uint8)
+    print(what, "->", int(ref["summaries"]["events_processed"][0]), "events")
+for seed in LANE_SEEDS:               # the single-server topology (exact tick/completion ties included)
+    m, end_s, what = random_lane_model(seed)
+    ref = RH.run_reference(m, seed=77 + seed, rid=0, end_ns=int(end_s * 1e9))
+    out[f"lane{seed}_summary"] = ref["summaries"]
+    out[f"lane{seed}_stats"] = ref["entity_stats"]
     print(what, "->", int(ref["summaries"]["events_processed"][0]), "events")
 out["seeds"] = np.array(kept)
 np.savez_compressed(os.path.join(HERE, "random_models.npz"), **out)

@@ -71,3 +71,14 @@ def test_random_lane_model_runs_on_the_oracle(seed):
     engine.validate_model(model)
     out = O.oracle_run(model, O.make_params(seed=77 + seed, end_ns=int(end_s * 1e9), n_replicas=2))
     assert 0 < int(out["summaries"]["events_processed"].max()) < 12000, what
+
+
+@pytest.mark.parametrize("seed", LANE_SEEDS)
+def test_oracle_matches_the_reference_on_random_single_server_models(seed):
+    from random_models import random_lane_model
+    model, end_s, what = random_lane_model(seed)
+    out = O.oracle_run(model, O.make_params(seed=77 + seed, end_ns=int(end_s * 1e9), n_replicas=1))
+    s, ws = out["summaries"][0], REF[f"lane{seed}_summary"][0]
+    for f in ("events_processed", "final_time_ns", "order_hash", "heap_left", "n_sink_samples", "n_service_samples"):
+        assert int(s[f]) == int(ws[f]), (what, f, int(s[f]), int(ws[f]))
+    assert out["entity_stats"][0].tobytes() == REF[f"lane{seed}_stats"][0].tobytes(), what

@@ -145,7 +145,17 @@ static int validate_model(const hs_model_desc *m)
         case HS_ENT_SINK: case HS_ENT_COUNTER: break;
         case HS_ENT_SKETCH: {
             if (e.i0 < HS_SK_HLL || e.i0 > HS_SK_TDIGEST) return fail(HS_ERR_INVALID, "entity %u: unknown sketch algorithm %d", i, e.i0);
-            if (e.l0 < 1 || e.l0 > INT32_MAX) return fail(HS_ERR_INVALID, "entity %u: sketch key population must be >= 1", i);
+            if (e.l0 < 0 || e.l0 > INT32_MAX) return fail(HS_ERR_INVALID, "entity %u: sketch key population must be >= 0", i);
+            if (e.l0 == 0 && (e.i0 == HS_SK_HLL || e.i0 == HS_SK_CMS || e.i0 == HS_SK_BLOOM)) {    /* hashed on the device */
+                const uint64_t words = e.i0 == HS_SK_CMS ? 2u * (uint64_t)e.i2 : 2u;
+                if (e.i0 == HS_SK_HLL && (e.i2 < 4 || e.i2 > 16)) return fail(HS_ERR_INVALID, "entity %u: precision must be in [4, 16], got %d (hyperloglog.py:101)", i, e.i2);
+                if (e.i0 != HS_SK_HLL && (e.i2 < 1 || e.i3 < 1)) return fail(HS_ERR_INVALID, "entity %u: sketch dimensions must be >= 1", i);
+                if (e.i1 < 0 || !m->sketch_tables || (uint64_t)e.i1 + words > m->n_sketch_table)
+                    return fail(HS_ERR_INVALID, "entity %u: sketch seed words out of range", i);
+                break;
+            }
+            if (e.l0 == 0 && e.i0 == HS_SK_TOPK) { if (e.i2 < 1) return fail(HS_ERR_INVALID, "entity %u: k must be positive (topk.py:79)", i); break; }
+            if (e.l0 == 0 && e.i0 != HS_SK_TDIGEST) return fail(HS_ERR_INVALID, "entity %u: sketch key population must be >= 1", i);
             if (e.i0 == HS_SK_HLL && (e.i2 < 4 || e.i2 > 16)) return fail(HS_ERR_INVALID, "entity %u: precision must be in [4, 16], got %d (hyperloglog.py:101)", i, e.i2);
             if (e.i0 == HS_SK_CMS && (e.i2 < 1 || e.i3 < 1)) return fail(HS_ERR_INVALID, "entity %u: width and depth must be >= 1 (count_min_sketch.py:88-91)", i);
             if (e.i0 == HS_SK_BLOOM && (e.i2 < 1 || e.i3 < 1)) return fail(HS_ERR_INVALID, "entity %u: size_bits and num_hashes must be >= 1 (bloom_filter.py:101-104)", i);

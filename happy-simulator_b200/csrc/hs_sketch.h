@@ -52,22 +52,129 @@ static inline void hs_sketch_layout_impl(const hs_model_desc *m, uint64_t *per_r
     if (merged_total) *merged_total = b;
 }
 
+/* ---- SHA-256 of a short message (FIPS 180-4), one 64-byte block: everything the sketches hash is a packed
+ * seed plus repr(key), at most 16 + 11 bytes.  Used when a SKETCH row carries no per-key table (i1 = -1):
+ * the hashes of hyperloglog.py:128-135, count_min_sketch.py:136-155 and bloom_filter.py:147-160 are then
+ * evaluated per event, so the key population needs no table in HBM. ----------------------------------- */
+HS_HD uint32_t hs_rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+/* digest words 0..3 (the first 16 bytes, big endian) of sha256(msg[0..len)), len <= 55 */
+HS_HD void hs_sha256_short(const uint8_t *msg, uint32_t len, uint32_t out[4])
+{
+    static const uint32_t Kc[64] = {
+        0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+        0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+        0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+        0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+        0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+        0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+        0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+        0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+    uint32_t w[64];
+    for (int i = 0; i < 16; ++i) w[i] = 0u;
+    for (uint32_t i = 0; i < len; ++i) w[i >> 2] |= (uint32_t)msg[i] << (24 - 8 * (i & 3u));
+    w[len >> 2] |= 0x80u << (24 - 8 * (len & 3u));
+    w[15] = len * 8u;
+    for (int i = 16; i < 64; ++i) {
+        const uint32_t s0 = hs_rotr32(w[i - 15], 7) ^ hs_rotr32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        const uint32_t s1 = hs_rotr32(w[i - 2], 17) ^ hs_rotr32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = 0x6a09e667u, b = 0xbb67ae85u, c = 0x3c6ef372u, d = 0xa54ff53au,
+             e = 0x510e527fu, f = 0x9b05688cu, g = 0x1f83d9abu, h = 0x5be0cd19u;
+    for (int i = 0; i < 64; ++i) {
+        const uint32_t S1 = hs_rotr32(e, 6) ^ hs_rotr32(e, 11) ^ hs_rotr32(e, 25);
+        const uint32_t t1 = h + S1 + ((e & f) ^ (~e & g)) + Kc[i] + w[i];
+        const uint32_t S0 = hs_rotr32(a, 2) ^ hs_rotr32(a, 13) ^ hs_rotr32(a, 22);
+        const uint32_t t2 = S0 + ((a & b) ^ (a & c) ^ (b & c));
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    out[0] = 0x6a09e667u + a; out[1] = 0xbb67ae85u + b; out[2] = 0x3c6ef372u + c; out[3] = 0xa54ff53au + d;
+}
+
+HS_HD uint32_t hs_put_be64(uint8_t *p, uint64_t v)          /* struct.pack(">Q", v) */
+{ for (int i = 0; i < 8; ++i) p[i] = (uint8_t)(v >> (56 - 8 * i)); return 8u; }
+
+HS_HD uint32_t hs_put_repr_int(uint8_t *p, int32_t key)     /* repr(key).encode() for key >= 0 */
+{
+    uint8_t tmp[12]; uint32_t n = 0; uint32_t v = (uint32_t)key;
+    do { tmp[n++] = (uint8_t)('0' + v % 10u); v /= 10u; } while (v);
+    for (uint32_t i = 0; i < n; ++i) p[i] = tmp[n - 1 - i];
+    return n;
+}
+
+/* HyperLogLog._hash + the register split of add() (hyperloglog.py:128-165) */
+HS_HD void hs_hll_hash(uint64_t seed, int32_t p, int32_t key, int32_t *idx, int32_t *run)
+{
+    uint8_t m[24]; uint32_t d[4];
+    uint32_t n = hs_put_be64(m, seed);
+    n += hs_put_repr_int(m + n, key);
+    hs_sha256_short(m, n, d);
+    const uint64_t h = ((uint64_t)d[0] << 32) | d[1];
+    const int low = 64 - p;
+    const uint64_t rest = h & ((1ull << low) - 1ull);
+    *idx = (int32_t)(h >> low);
+    int lz = low;                                           /* _count_leading_zeros(rest, low): low for rest == 0 */
+    if (rest) { lz = 0; for (int i = low - 1; i >= 0 && !((rest >> i) & 1ull); --i) ++lz; }
+    *run = lz + 1;
+}
+
+/* CountMinSketch._hash(item, row) for a non-negative int item, hash(item) == item (count_min_sketch.py:145-155);
+ * row_seed = sha256(pack(">QQ", seed, row))[:8], evaluated by hs_cms_row_seed */
+HS_HD uint64_t hs_cms_row_seed(uint64_t seed, int32_t row)
+{
+    uint8_t m[16]; uint32_t d[4];
+    hs_put_be64(m, seed); hs_put_be64(m + 8, (uint64_t)row);
+    hs_sha256_short(m, 16u, d);
+    return ((uint64_t)d[0] << 32) | d[1];
+}
+HS_HD int32_t hs_cms_col(uint64_t row_seed, int32_t width, int32_t key)
+{
+    uint8_t m[8]; uint32_t d[4];
+    hs_put_be64(m, (uint64_t)(int64_t)key ^ row_seed);
+    hs_sha256_short(m, 8u, d);
+    return (int32_t)((((uint64_t)d[0] << 32) | d[1]) % (uint64_t)width);
+}
+
+/* BloomFilter._hash(item, i) (bloom_filter.py:147-160): (h1 + i h2) mod size_bits over Python's unbounded ints;
+ * size_bits < 2^31, so the residues multiply without overflow */
+HS_HD int32_t hs_bloom_bit(uint64_t seed, int32_t i, int32_t size_bits, int32_t key)
+{
+    uint8_t m[32]; uint32_t d[4];
+    uint32_t n = hs_put_be64(m, seed);
+    n += hs_put_be64(m + n, (uint64_t)i);
+    n += hs_put_repr_int(m + n, key);
+    hs_sha256_short(m, n, d);
+    const uint64_t h1 = ((uint64_t)d[0] << 32) | d[1], h2 = ((uint64_t)d[2] << 32) | d[3];
+    const uint64_t mm = (uint64_t)size_bits;
+    return (int32_t)((h1 % mm + ((uint64_t)i % mm) * (h2 % mm)) % mm);
+}
+
 /* sketch.add(key): `state` is this replica's state of the row, `tab` the row's table (stride K) */
 HS_HD void hs_sketch_add(uint8_t *state, const int32_t *tab, int32_t algo, int32_t p_or_depth, int32_t width,
                          int64_t K, int32_t key)
 {
+    /* K > 0: `tab` is the per-key table.  K == 0: the hashes are evaluated here; `tab` then holds the sketch seed
+     * (HLL, BLOOM: lo, hi) or the row seeds (CMS: depth x (lo, hi)) as int32 pairs. */
+#define HS_SK_SEED64(I) ((uint64_t)(uint32_t)tab[2 * (I)] | ((uint64_t)(uint32_t)tab[2 * (I) + 1] << 32))
     if (algo == HS_SK_HLL) {                      /* registers[idx] = max(registers[idx], run_length) */
-        const int32_t idx = tab[key], run = tab[K + key];
+        int32_t idx, run;
+        if (K) { idx = tab[key]; run = tab[K + key]; }
+        else hs_hll_hash(HS_SK_SEED64(0), p_or_depth, key, &idx, &run);
         if ((int32_t)state[idx] < run) state[idx] = (uint8_t)run;
     } else if (algo == HS_SK_CMS) {               /* for row in range(depth): counters[row][col] += 1 */
         uint32_t *c = (uint32_t *)state;
-        for (int32_t row = 0; row < p_or_depth; ++row) c[(int64_t)row * width + tab[(int64_t)row * K + key]] += 1u;
+        for (int32_t row = 0; row < p_or_depth; ++row) {
+            const int32_t col = K ? tab[(int64_t)row * K + key] : hs_cms_col(HS_SK_SEED64(row), width, key);
+            c[(int64_t)row * width + col] += 1u;
+        }
     } else if (algo == HS_SK_BLOOM) {             /* for i in range(num_hashes): set bit (h1 + i h2) % size_bits */
         uint64_t *w = (uint64_t *)state;
         for (int32_t i = 0; i < p_or_depth; ++i) {
-            const uint32_t bit = (uint32_t)tab[(int64_t)i * K + key];
+            const uint32_t bit = (uint32_t)(K ? tab[(int64_t)i * K + key] : hs_bloom_bit(HS_SK_SEED64(0), i, width, key));
             w[bit >> 6] |= 1ull << (bit & 63u);
         }
+#undef HS_SK_SEED64
     } else {                                      /* Space-Saving over k counters kept in dict (insertion) order */
         uint32_t *hdr = (uint32_t *)state;
         int32_t *slot = (int32_t *)(state + 16);  /* {item, count, error} x k */

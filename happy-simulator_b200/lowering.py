@@ -59,6 +59,9 @@ def consistent_hash_table(backend_names, virtual_nodes: int, population: int) ->
     return tab
 
 
+HASH_ON_DEVICE_ABOVE = 100_000      # key populations beyond this are hashed per event on the device (K = 0 rows)
+
+
 def zipf_cdf(population: int, s: float) -> np.ndarray:
     """ZipfDistribution._cum_probs for values range(population) (distributions/zipf.py:96-110): weights
     1 / (k + 1)^s, normalised by Python's float sum(), accumulated left to right, last entry forced to 1.0.
@@ -292,16 +295,19 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
             if pop <= 0:
                 raise UnsupportedModelError(f"sketch collector {name!r}: needs a finite key population")
             sk = o._topk if hasattr(o, "_topk") else o._sketch       # TopKCollector keeps its TopK in _topk
+            # large key populations: no per-key table, the device evaluates the SHA-256 hashes per event
+            on_device = pop > HASH_ON_DEVICE_ABOVE
             if _cls(sk) == "TopK":
                 b.sketch_topk(name, k=int(sk._k), key_population=pop)
             elif _cls(sk) == "BloomFilter":
-                b.sketch_bloom(name, size_bits=int(sk._size_bits), num_hashes=int(sk._num_hashes),
-                               table=bloom_table(sk._size_bits, sk._num_hashes, sk._seed, pop))
+                b.sketch_bloom(name, size_bits=int(sk._size_bits), num_hashes=int(sk._num_hashes), seed=sk._seed,
+                               table=None if on_device else bloom_table(sk._size_bits, sk._num_hashes, sk._seed, pop))
             elif _cls(sk) == "HyperLogLog":
-                b.sketch_hll(name, precision=int(sk._precision), table=hll_table(sk._precision, sk._seed, pop))
+                b.sketch_hll(name, precision=int(sk._precision), seed=sk._seed,
+                             table=None if on_device else hll_table(sk._precision, sk._seed, pop))
             elif _cls(sk) == "CountMinSketch":
-                b.sketch_cms(name, width=int(sk._width), depth=int(sk._depth),
-                             table=cms_table(sk._width, sk._depth, sk._seed, pop))
+                b.sketch_cms(name, width=int(sk._width), depth=int(sk._depth), seed=sk._seed,
+                             table=None if on_device else cms_table(sk._width, sk._depth, sk._seed, pop))
             else:
                 raise UnsupportedModelError(f"sketch collector {name!r}: sketch {_cls(sk)} (supported: HyperLogLog, "
                                             "CountMinSketch, BloomFilter, TopK)")

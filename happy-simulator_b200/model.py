@@ -220,27 +220,49 @@ class ModelBuilder:
         sid = self.source(name, poisson=False, target=pid, profile=("constant", 1.0 / interval_s))
         return sid, pid
 
-    def sketch_hll(self, name="HLL", *, precision, table):
+    @staticmethod
+    def _seed_words(values) -> np.ndarray:
+        """uint64 seeds as (lo, hi) int32 words: the table of a SKETCH row that hashes on the device (K = 0)."""
+        v = np.array([int(x) & 0xFFFFFFFFFFFFFFFF for x in values], dtype=np.uint64)
+        return np.ascontiguousarray(np.stack([v & np.uint64(0xFFFFFFFF), v >> np.uint64(32)], axis=1).astype(np.uint32)).view(np.int32).ravel()
+
+    def _hashed_sketch(self, name, algo, i2, i3, words):
+        off = sum(t.size for t in self._sketch_tables)
+        self._sketch_tables.append(words)
+        return self._add(name, A.HS_ENT_SKETCH, -1, algo, off, int(i2), 0, i3=int(i3))
+
+    def sketch_hll(self, name="HLL", *, precision, table=None, seed=None):
         """SketchCollector(HyperLogLog(precision, seed)) on the routing key; table = hll_table(precision,
-        seed, K): int32[2, K] (register index, run length) per key."""
+        seed, K): int32[2, K] (register index, run length) per key -- or table=None, seed=...: the device
+        evaluates the SHA-256 hashes itself (any key population, no table)."""
+        if table is None:
+            return self._hashed_sketch(name, A.HS_SK_HLL, precision, 0, self._seed_words([seed or 0]))
         table = np.ascontiguousarray(table, dtype=np.int32)
         assert table.ndim == 2 and table.shape[0] == 2
         off = sum(t.size for t in self._sketch_tables)
         self._sketch_tables.append(table)
         return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_HLL, off, int(precision), table.shape[1])
 
-    def sketch_cms(self, name="CMS", *, width, depth, table):
+    def sketch_cms(self, name="CMS", *, width, depth, table=None, seed=None):
         """SketchCollector(CountMinSketch(width, depth, seed)) on the routing key; table = cms_table(width,
-        depth, seed, K): int32[depth, K], the column of key k in each row."""
+        depth, seed, K): int32[depth, K], the column of key k in each row -- or table=None, seed=...: hashed on the
+        device; the row seeds sha256(pack(">QQ", seed, row))[:8] (count_min_sketch.py:136-143) travel instead."""
+        if table is None:
+            import hashlib, struct
+            rs = [int.from_bytes(hashlib.sha256(struct.pack(">QQ", seed or 0, row)).digest()[:8], "big") for row in range(depth)]
+            return self._hashed_sketch(name, A.HS_SK_CMS, depth, width, self._seed_words(rs))
         table = np.ascontiguousarray(table, dtype=np.int32)
         assert table.ndim == 2 and table.shape[0] == depth
         off = sum(t.size for t in self._sketch_tables)
         self._sketch_tables.append(table)
         return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_CMS, off, int(depth), table.shape[1], i3=int(width))
 
-    def sketch_bloom(self, name="Bloom", *, size_bits, num_hashes, table):
+    def sketch_bloom(self, name="Bloom", *, size_bits, num_hashes, table=None, seed=None):
         """SketchCollector(BloomFilter(size_bits, num_hashes, seed)) on the routing key; table =
-        bloom_table(size_bits, num_hashes, seed, K): int32[num_hashes, K], the bit each hash sets for key k."""
+        bloom_table(size_bits, num_hashes, seed, K): int32[num_hashes, K], the bit each hash sets for key k -- or
+        table=None, seed=...: hashed on the device."""
+        if table is None:
+            return self._hashed_sketch(name, A.HS_SK_BLOOM, num_hashes, size_bits, self._seed_words([seed or 0]))
         table = np.ascontiguousarray(table, dtype=np.int32)
         assert table.ndim == 2 and table.shape[0] == num_hashes
         off = sum(t.size for t in self._sketch_tables)

@@ -104,7 +104,9 @@ typedef struct hs_entity_desc {
                           rate profile, general arrival path); SKETCH: CMS width | BLOOM size_bits
                           | TDIGEST centroid capacity (>= 2 x buffer size); others: reserved, 0 */
     int64_t l0;        /* SOURCE: stop_after in ns or -1; SERVER: queue capacity or -1 (= inf);
-                          SKETCH: key population K = row stride of its table in sketch_tables     */
+                          SKETCH: key population K = row stride of its table in sketch_tables; 0 = no per-key
+                          table: the device evaluates the SHA-256 hashes per event (any key population) and
+                          the table holds only the seed words, see hs_model_desc.sketch_tables       */
     double d0;         /* SOURCE: rate (events/s); SERVER: mean / constant service time (s);
                           SKETCH/TDIGEST: compression                                           */
     double d1;         /* reserved, 0                                                           */
@@ -133,7 +135,10 @@ typedef struct hs_model_desc {
      * CMS width, K).  HLL: [2][K] = register index (hash >> (64 - p)) and run length (leading zeros of
      * the remaining bits + 1) of key k, hyperloglog.py:156-165.  CMS: [depth][K] = column of key k in
      * each row, count_min_sketch.py:145-155.  BLOOM: [num_hashes][K] = bit index (h1 + i h2) mod size_bits of
-     * key k for hash i, bloom_filter.py:147-160.  TOPK: no table. */
+     * key k for hash i, bloom_filter.py:147-160.  TOPK: no table.
+     * A row with K = 0 hashes on the device (csrc/hs_sketch.h: SHA-256 of the packed seed and repr(key)); its
+     * table is then the seed as (lo, hi) int32 words -- HLL, BLOOM: the sketch's seed; CMS: the depth row
+     * seeds sha256(pack(">QQ", seed, row))[:8] (count_min_sketch.py:136-143). */
     uint32_t n_sketch_table;       /* total length of sketch_tables[]                          */
     uint32_t n_key_cdf;            /* total length of key_cdf[]                                */
     const int32_t *sketch_tables;

@@ -631,6 +631,10 @@ double hs_cpu_integrate_rate(int32_t kind, double p0, double p1, double p2, doub
  * streams whose answers the reference's sketch classes gave) */
 void hs_cpu_sketch_add(uint8_t *state, const int32_t *tab, int32_t algo, int32_t p_or_depth, int32_t width, int64_t K, int32_t key)
 { hs_sketch_add(state, tab, algo, p_or_depth, width, K, key); }
+void hs_cpu_hll_hash(uint64_t seed, int32_t p, int32_t key, int32_t *idx, int32_t *run) { hs_hll_hash(seed, p, key, idx, run); }
+uint64_t hs_cpu_cms_row_seed(uint64_t seed, int32_t row) { return hs_cms_row_seed(seed, row); }
+int32_t hs_cpu_cms_col(uint64_t row_seed, int32_t width, int32_t key) { return hs_cms_col(row_seed, width, key); }
+int32_t hs_cpu_bloom_bit(uint64_t seed, int32_t i, int32_t size_bits, int32_t key) { return hs_bloom_bit(seed, i, size_bits, key); }
 int hs_cpu_tdigest_add(uint8_t *state, double compression, uint32_t buf_size, uint32_t cap, double value)
 { return hs_tdigest_add(state, compression, buf_size, cap, value); }
 int32_t hs_cpu_routing_key(double u, int32_t n, const double *cum_probs) { return hs_routing_key(u, n, cum_probs); }

@@ -51,6 +51,11 @@ def lib():
         L.hs_cpu_routing_key.restype = C.c_int32
         L.hs_cpu_sketch_add.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32]
         L.hs_cpu_sketch_add.restype = None
+        L.hs_cpu_hll_hash.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.hs_cpu_hll_hash.restype = None
+        L.hs_cpu_cms_row_seed.argtypes = [C.c_uint64, C.c_int32]; L.hs_cpu_cms_row_seed.restype = C.c_uint64
+        L.hs_cpu_cms_col.argtypes = [C.c_uint64, C.c_int32, C.c_int32]; L.hs_cpu_cms_col.restype = C.c_int32
+        L.hs_cpu_bloom_bit.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32]; L.hs_cpu_bloom_bit.restype = C.c_int32
         L.hs_cpu_tdigest_add.argtypes = [C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_double]
         L.hs_cpu_tdigest_add.restype = C.c_int
         L.hs_sketch_layout.argtypes = [C.POINTER(A.ModelDesc)] + [C.POINTER(C.c_uint64)] * 4

@@ -144,6 +144,37 @@ def test_zipf_keys_heavy_hitters(eng, eng_id):
 
 
 @pytest.mark.parametrize("eng_id", [1, 3])
+def test_sketch_rows_hashing_on_the_device(eng, eng_id):
+    """K = 0 rows: no per-key tables, SHA-256 of (seed, repr(key)) per event in the kernel -- 200 000 client ids
+    (Zipf) into HyperLogLog, Count-Min and Bloom collectors; states equal the oracle's, whose hash functions
+    tests/test_sketching.py ties to hashlib and, through the fixtures, to the reference."""
+    K = 200_000
+    b = hs.ModelBuilder()
+    src = b.source(rate=900.0, key_population=K, key_cdf=hs.zipf_cdf(K, 0.9))
+    servers = [b.server(f"S{i}", concurrency=2, mean_service_s=0.004) for i in range(6)]
+    sinks = [b.sketch_hll("uniques", precision=10, seed=5), b.sketch_cms("freq", width=64, depth=4, seed=2**40 + 1),
+             b.sketch_bloom("seen", size_bits=4099, num_hashes=5, seed=None)]
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb)
+    for k, sv in enumerate(servers):
+        b.set_target(sv, sinks[k % 3])
+    model = b.build()
+    assert model.sketch_tables.size == 2 + 8 + 2
+    kw = dict(seed=51, end_ns=2 * 10**9, n_replicas=17, record_cap=40000, sample_cap=16, service_cap=4000)
+    eng.upload(model)
+    eng.run(engine.make_params(engine=eng_id, **kw))
+    got = eng.read_outputs()
+    want = O.oracle_run(model, O.make_params(**kw))
+    assert_same(got, want)
+    assert got["sketches"].tobytes() == want["sketches"].tobytes()
+    h = hs.HyperLogLog(10, seed=5); h._load_device_state(model.sketch_views(got["sketches"])[sinks[0]][0], 1)
+    assert 200 < h.cardinality() < 700            # ~600 requests reach the HLL collector, most ids distinct
+    merged = eng.read_sketches()
+    host = D.merge_sketch_states(model, want["sketches"])
+    assert all(np.array_equal(merged[i], host[i]) for i in host)
+
+
+@pytest.mark.parametrize("eng_id", [1, 3])
 def test_sketch_state_survives_windows(eng, eng_id):
     model, kw, z = G.load("philox_sketch_cms_farm")
     caps = dict(G.caps(z), engine=eng_id, n_replicas=3, rid_base=0, seed=kw["seed"])

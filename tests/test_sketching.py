@@ -253,7 +253,7 @@ def test_validation_rejects_bad_sketch_rows():
             m.entities[k][1] = v
         return m
     engine.validate_model(model())
-    for over, msg in ((dict(i2=3), "precision"), (dict(i0=9), "algorithm"), (dict(l0=0), "population"), (dict(i1=5), "table")):
+    for over, msg in ((dict(i2=3), "precision"), (dict(i0=9), "algorithm"), (dict(l0=-1), "population"), (dict(i1=5), "table")):
         with pytest.raises(EngineError, match=msg):
             engine.validate_model(model(**over))
     b = hs.ModelBuilder()
@@ -272,3 +272,68 @@ def test_validation_rejects_bad_sketch_rows():
     m.sketch_tables = m.sketch_tables.copy(); m.sketch_tables[3] = 32        # register index out of range for p = 5
     with pytest.raises(EngineError, match="HLL table"):
         engine.validate_model(m)
+
+
+def test_device_hash_functions_equal_hashlib():
+    """csrc/hs_sketch.h's SHA-256 based hashes (what a SKETCH row with K = 0 evaluates per event) against the
+    host tables, which are hashlib evaluations of the reference's formulas -- small, large and edge keys."""
+    L = O.lib()
+    keys = list(range(0, 300)) + [999, 1000, 65535, 10**6, 123456789, 2**31 - 1]
+    K = max(keys) + 1
+    for p, seed in ((4, 0), (11, 7), (16, 2**40 + 5)):
+        for k in keys:
+            h = int.from_bytes(__import__("hashlib").sha256(__import__("struct").pack(">Q", seed) + repr(k).encode()).digest()[:8], "big")
+            rest = h & ((1 << (64 - p)) - 1)
+            i, r = C.c_int32(), C.c_int32()
+            L.hs_cpu_hll_hash(seed, p, k, C.byref(i), C.byref(r))
+            assert (i.value, r.value) == (h >> (64 - p), (64 - p) - rest.bit_length() + 1), (p, seed, k)
+    small = [k for k in keys if k < 300]
+    t = hs.hll_table(9, 3, 300)
+    for k in small:
+        i, r = C.c_int32(), C.c_int32(); L.hs_cpu_hll_hash(3, 9, k, C.byref(i), C.byref(r))
+        assert (i.value, r.value) == (int(t[0, k]), int(t[1, k]))
+    ct = hs.cms_table(272, 5, 11, 300)
+    for row in range(5):
+        rs = L.hs_cpu_cms_row_seed(11, row)
+        assert [L.hs_cpu_cms_col(rs, 272, k) for k in small] == ct[row].tolist()
+    bt = hs.bloom_table(9585, 7, 4, 300)
+    for i in range(7):
+        assert [L.hs_cpu_bloom_bit(4, i, 9585, k) for k in small] == bt[i].tolist()
+    import hashlib, struct
+    for k in (10**6, 2**31 - 1):       # large keys, large filter: the 128-bit (h1 + i h2) mod m of Python's ints
+        for i in (0, 3, 6):
+            dg = hashlib.sha256(struct.pack(">QQ", 9, i) + repr(k).encode()).digest()
+            want = (int.from_bytes(dg[:8], "big") + i * int.from_bytes(dg[8:16], "big")) % (2**31 - 1)
+            assert L.hs_cpu_bloom_bit(9, i, 2**31 - 1, k) == want
+
+
+@pytest.mark.parametrize("name", ["philox_sketch_hll_direct", "philox_sketch_cms_farm", "philox_sketch_bloom_topk"])
+def test_hashed_on_the_device_rows_give_the_reference_states(name):
+    """The same fixtures with the per-key tables dropped (K = 0: SHA-256 per event): identical sketch states."""
+    m, kw, z = G.load(name)
+    b = hs.ModelBuilder()
+    b._rows = [tuple(r) for r in m.entities.tolist()]; b._names = list(m.names)
+    b._backends = [int(x) for x in m.backends]; b._key_table = m.key_table
+    for i in m.ids_of(A.HS_ENT_SKETCH):
+        e = m.entities[i]
+        algo = int(e["i0"])
+        if algo == A.HS_SK_TOPK:
+            continue
+        seed = int(z[f"sketch_seed_{i}"]); seed = 0 if seed < 0 else seed
+        tmp = hs.ModelBuilder()
+        if algo == A.HS_SK_HLL:
+            tmp.sketch_hll(precision=int(e["i2"]), seed=seed)
+        elif algo == A.HS_SK_CMS:
+            tmp.sketch_cms(width=int(e["i3"]), depth=int(e["i2"]), seed=seed)
+        else:
+            tmp.sketch_bloom(size_bits=int(e["i3"]), num_hashes=int(e["i2"]), seed=seed)
+        row = list(tmp._rows[0]); row[3] = sum(t.size for t in b._sketch_tables)     # i1: offset of the seed words
+        b._sketch_tables.append(tmp._sketch_tables[0])
+        b._rows[i] = tuple(row)
+    hashed = b.build()
+    assert all(int(hashed.entities["l0"][i]) == 0 for i in hashed.ids_of(A.HS_ENT_SKETCH) if int(hashed.entities["i0"][i]) != A.HS_SK_TOPK)
+    engine.validate_model(hashed)
+    out = O.oracle_run(hashed, O.make_params(n_replicas=1, **G.caps(z), **kw))
+    assert hashed.sketch_tables.size < 40 and m.sketch_tables.size > 100
+    assert out["sketches"][0].tobytes() == z["sketch_state"].tobytes()
+    assert out["summaries"]["order_hash"][0] == z["summaries"]["order_hash"][0]

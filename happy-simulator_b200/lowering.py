@@ -23,7 +23,7 @@ import math
 import numpy as np
 
 from . import _abi as A
-from .model import FlatModel, ModelBuilder
+from .model import ModelBuilder
 
 
 class UnsupportedModelError(NotImplementedError):

@@ -11,7 +11,7 @@ import time as _time
 from dataclasses import dataclass, field
 from typing import Any
 
-from .api import EntitySummary, Instant, Simulation, SimulationSummary
+from .api import EntitySummary, Simulation, SimulationSummary
 from .lowering import UnsupportedModelError
 
 

@@ -349,7 +349,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     do {                                                                                     \
         const uint32_t k_ = (uint32_t)((uint64_t)n_svc % HS_DRAW_BUF);                       \
         const int64_t delta_ = hs_seconds_to_ns(sh_svc[k_][tid]);   /* event.py:499, temporal.py:221 */ \
-        if ((FLAGS & HS_LF_REC) && svc_out) { __stcs(svc_out + svc_pos, sh_svc[k_][tid]); svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
+        if ((FLAGS & HS_LF_REC) && svc_out) { svc_out[svc_pos] = sh_svc[k_][tid];   /* plain store: see HS_SINK */ svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
         n_svc++;                                                                             \
         { const double sv_ = sh_svc[k_][tid]; const uint64_t i_ = ctr + 1; ctr += 2;         \
           HS_C_PUSH(now + delta_, i_, (CREATED), sv_); }                                     \
@@ -367,7 +367,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 uint4 w_; const uint64_t lb_ = (uint64_t)__double_as_longlong(lat_);         \
                 w_.x = (uint32_t)(uint64_t)now; w_.y = (uint32_t)((uint64_t)now >> 32);      \
                 w_.z = (uint32_t)lb_; w_.w = (uint32_t)(lb_ >> 32);                          \
-                __stcs((uint4 *)(smp + smp_pos), w_);                                        \
+                /* plain (write-back) store: the 16-byte sample and the 8-byte service time fill their 128-byte  \
+                 * lines over many events; kept in L2 until complete they reach HBM as whole lines, whereas       \
+                 * evict-first stores left partial sectors behind (read-modify-write traffic)                  */ \
+                *(uint4 *)(smp + smp_pos) = w_;                                              \
                 smp_pos = (smp_pos + 1 == P.sample_cap) ? 0u : smp_pos + 1; }                \
         }                                                                                    \
     } while (0)

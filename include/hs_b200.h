@@ -168,7 +168,8 @@ typedef struct hs_run_params {
     uint32_t replicas_per_cell;  /* cell = global index / replicas_per_cell (>=1)              */
     /* Flight-recorder rings, per replica: item i of a stream lives at slot i % cap, so the
      * buffers hold the LAST cap items (everything when cap >= count).  Every item is written
-     * to HBM: 16 B per processed event, 16 B per Sink sample, 8 B per service start.          */
+     * to its ring in device memory: 16 B per processed event (streamed as whole 128-byte lines), 16 B per
+     * Sink sample and 8 B per service start (through L2, which completes their lines).     */
     uint32_t record_cap;       /* event-record ring entries per replica (0 = no trace)         */
     uint32_t sample_cap;       /* Sink-sample ring entries per replica                         */
     uint32_t service_cap;      /* service-time ring entries per replica                        */

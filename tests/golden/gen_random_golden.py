@@ -17,7 +17,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), HERE]
 
 import ref_harness as RH                      # noqa: E402
 from random_models import random_lane_model, random_model        # noqa: E402
-from test_random_models import LANE_SEEDS, SEEDS                 # noqa: E402
+from test_random_models import REF_LANE_SEEDS as LANE_SEEDS, REF_SEEDS as SEEDS   # noqa: E402
 
 out = {}
 kept = []

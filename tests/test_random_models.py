@@ -6,7 +6,8 @@ import oracle_lib as O
 from happysim_b200 import engine
 from random_models import random_model
 
-SEEDS = list(range(64))
+SEEDS = list(range(64))            # run on the device engines too (tests/test_gpu_random_models.py)
+REF_SEEDS = list(range(256))       # oracle vs the unmodified reference (CPU only)
 
 
 @pytest.mark.parametrize("seed", SEEDS)
@@ -51,7 +52,7 @@ def check_against_reference(model, out, seed, r=0):
     return True
 
 
-@pytest.mark.parametrize("seed", SEEDS)
+@pytest.mark.parametrize("seed", REF_SEEDS)
 def test_oracle_matches_the_reference_on_random_models(seed):
     """Order hash over every processed event, counts, statistics and sketch states of the random models, as the
     unmodified reference produced them with the Philox plug-ins."""
@@ -62,6 +63,7 @@ def test_oracle_matches_the_reference_on_random_models(seed):
 
 
 LANE_SEEDS = list(range(48))
+REF_LANE_SEEDS = list(range(160))
 
 
 @pytest.mark.parametrize("seed", LANE_SEEDS)
@@ -73,7 +75,7 @@ def test_random_lane_model_runs_on_the_oracle(seed):
     assert 0 < int(out["summaries"]["events_processed"].max()) < 12000, what
 
 
-@pytest.mark.parametrize("seed", LANE_SEEDS)
+@pytest.mark.parametrize("seed", REF_LANE_SEEDS)
 def test_oracle_matches_the_reference_on_random_single_server_models(seed):
     from random_models import random_lane_model
     model, end_s, what = random_lane_model(seed)

@@ -165,7 +165,8 @@ def merge_sketch_states(model, raw: np.ndarray) -> dict:
 
 def allreduce_sketches(model, merged: dict, device=None, group=None) -> dict:
     """Cross-GPU merge of the per-rank merged sketches: one MAX all-reduce over the HLL registers, one SUM
-    all-reduce over the CMS counters and one bitwise-OR all-reduce over the Bloom words (the reference's
+    all-reduce over the CMS counters and one MAX all-reduce over the Bloom filters' unpacked bits (= bitwise OR;
+    NCCL has no bitwise reductions) (the reference's
     merge() contracts, hyperloglog.py:203-226, count_min_sketch.py:276-301, bloom_filter.py:262-291).
     TopK.merge / TDigest.merge are sequential and order dependent: those entries stay rank-local here (gather the per-replica
     states and merge them in global replica order if a cross-rank TopK is wanted)."""
@@ -180,12 +181,14 @@ def allreduce_sketches(model, merged: dict, device=None, group=None) -> dict:
     blm = [i for i in ids if int(model.entities["i0"][i]) == A.HS_SK_BLOOM]
     cms = [i for i in ids if i not in hll and i not in blm]
     out = {i: v for i, v in merged.items() if int(model.entities["i0"][i]) in host_only}   # rank-local (see docstring)
-    if blm:
-        t = torch.from_numpy(np.concatenate([merged[i].view(np.int64).ravel() for i in blm])).to(dev)
-        dist.all_reduce(t, op=dist.ReduceOp.BOR, group=group)
+    if blm:      # NCCL has no bitwise reductions: OR over the bit arrays = MAX over their bits, one byte per bit
+        bits = np.concatenate([np.unpackbits(merged[i].view(np.uint8), bitorder="little") for i in blm])
+        t = torch.from_numpy(bits).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         a, pos = t.cpu().numpy(), 0
         for i in blm:
-            out[i] = a[pos: pos + merged[i].size].view(np.uint64).copy(); pos += merged[i].size
+            n = merged[i].size * 64
+            out[i] = np.packbits(a[pos: pos + n], bitorder="little").view(np.uint64).copy(); pos += n
     if hll:
         t = torch.from_numpy(np.concatenate([merged[i].astype(np.int32).ravel() for i in hll])).to(dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)

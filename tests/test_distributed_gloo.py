@@ -72,17 +72,20 @@ def _sketch_worker(rank, world, port, n_total, q):
     import oracle_lib as O
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    model, kw, _ = G.load("philox_sketch_cms_farm")
-    lo, hi = D.shard_range(n_total, rank, world)
-    out = O.oracle_run(model, O.make_params(seed=kw["seed"], end_ns=kw["end_ns"], n_replicas=hi - lo, replica_index_base=lo))
-    merged = D.allreduce_sketches(model, D.merge_sketch_states(model, out["sketches"]))
-    q.put((rank, {i: v.tolist() for i, v in merged.items()}))
+    res = {}
+    for name in ("philox_sketch_cms_farm", "philox_sketch_bloom_topk"):
+        model, kw, _ = G.load(name)
+        lo, hi = D.shard_range(n_total, rank, world)
+        out = O.oracle_run(model, O.make_params(seed=kw["seed"], end_ns=kw["end_ns"], n_replicas=hi - lo, replica_index_base=lo))
+        merged = D.allreduce_sketches(model, D.merge_sketch_states(model, out["sketches"]))
+        res[name] = {i: v.tolist() for i, v in merged.items() if hasattr(v, "tolist")}      # TopK stays rank-local
+    q.put((rank, res))
     dist.destroy_process_group()
 
 
 def test_two_rank_sketch_merge_equals_single_process():
-    """SKETCH rows across ranks: one MAX all-reduce (HLL registers) + one SUM all-reduce (CMS counters)
-    of the per-rank merged images == the merge over the whole ensemble."""
+    """SKETCH rows across ranks: MAX all-reduce (HLL registers), SUM all-reduce (CMS counters) and the Bloom
+    filters' OR as a MAX over unpacked bits, of the per-rank merged images == the merge over the whole ensemble."""
     from happysim_b200 import distributed as D
     import golden_lib as G
     import oracle_lib as O
@@ -96,10 +99,13 @@ def test_two_rank_sketch_merge_equals_single_process():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    model, kw, _ = G.load("philox_sketch_cms_farm")
-    whole = O.oracle_run(model, O.make_params(seed=kw["seed"], end_ns=kw["end_ns"], n_replicas=n_total))
-    want = D.merge_sketch_states(model, whole["sketches"])
-    for rank, merged in got:
-        assert set(merged) == set(want)
-        for i in want:
-            assert np.array_equal(np.asarray(merged[i], dtype=np.uint64), want[i].astype(np.uint64))
+    for name in ("philox_sketch_cms_farm", "philox_sketch_bloom_topk"):
+        model, kw, _ = G.load(name)
+        whole = O.oracle_run(model, O.make_params(seed=kw["seed"], end_ns=kw["end_ns"], n_replicas=n_total))
+        want = {i: v for i, v in D.merge_sketch_states(model, whole["sketches"]).items() if hasattr(v, "tolist")}
+        assert want
+        for rank, res in got:
+            merged = res[name]
+            assert set(merged) == set(want)
+            for i in want:       # HLL max, CMS sum, Bloom OR over both ranks == over the whole ensemble
+                assert np.array_equal(np.asarray(merged[i], dtype=np.uint64), want[i].astype(np.uint64))

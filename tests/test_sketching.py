@@ -337,3 +337,34 @@ def test_hashed_on_the_device_rows_give_the_reference_states(name):
     assert hashed.sketch_tables.size < 40 and m.sketch_tables.size > 100
     assert out["sketches"][0].tobytes() == z["sketch_state"].tobytes()
     assert out["summaries"]["order_hash"][0] == z["summaries"]["order_hash"][0]
+
+
+def test_write_back_of_sketch_states_onto_the_mirror_objects():
+    """Simulation._write_back with oracle outputs standing in for the device's (same layout): the INTEGRATION.md
+    example -- TopKCollector, QuantileEstimator, HyperLogLog collector behind a consistent-hash ring, Zipf ids."""
+    top = hs.TopKCollector("heavy", k=10)
+    p99 = hs.QuantileEstimator("lat", hs.LatencyExtractor(), compression=100)
+    seen = hs.SketchCollector("uniques", hs.HyperLogLog(precision=12, seed=1))
+    servers = [hs.Server(f"S{i}", concurrency=2, service_time=hs.ExponentialLatency(0.02), downstream=d)
+               for i, d in enumerate((top, p99, seen))]
+    lb = hs.LoadBalancer("lb", backends=servers, strategy=hs.ConsistentHash(virtual_nodes=100))
+    src = hs.Source.poisson(rate=120, event_provider=hs.SimpleEventProvider(lb, context_fn=hs.ZipfKeyContext(10_000, s=1.1)))
+    sim = hs.Simulation(end_time=hs.Instant.from_seconds(30), sources=[src], entities=[lb, *servers, top, p99, seen])
+    engine.validate_model(sim.model)
+    out = O.oracle_run(sim.model, O.make_params(seed=1, end_ns=30 * 10**9, n_replicas=2))
+    sim._write_back(out, 1)
+    i_top, i_p99, i_seen = (sim.objects.index(o) for o in (top, p99, seen))
+    st = out["entity_stats"][1]
+    assert top.events_processed == int(st[i_top]["c0"]) == top.total_count > 500
+    assert top.top(1)[0].item == 0 and top.top(1)[0].count > 100          # rank 0 is the hottest id
+    assert p99.sample_count == int(st[i_p99]["c1"]) and p99.summary()["count"] == p99.sample_count
+    s = p99.summary()
+    assert s["min"] <= s["p50"] <= s["p90"] <= s["p99"] <= s["p999"] <= s["max"]
+    assert seen.events_processed == int(st[i_seen]["c0"]) and 100 < seen.sketch.cardinality() <= seen.sketch.item_count
+    # the lowering hashes on the device above HASH_ON_DEVICE_ABOVE keys
+    big = hs.SketchCollector("big", hs.HyperLogLog(precision=8, seed=3))
+    src2 = hs.Source.poisson(rate=5, event_provider=hs.SimpleEventProvider(big, context_fn=hs.UniformKeyContext(lowering.HASH_ON_DEVICE_ABOVE + 1)))
+    m2, objs2 = lowering.lower([src2], [big])
+    e = m2.entities[objs2.index(big)]
+    assert int(e["l0"]) == 0 and m2.sketch_tables.size == 2
+    engine.validate_model(m2)

@@ -739,8 +739,18 @@ class Simulation:
                     elif algo == A.HS_SK_BLOOM:
                         sk._bits = [int(x) for x in state]
                         sk._bits_set = sum(bin(w).count("1") for w in sk._bits)
-                    else:
-                        raise lowering.UnsupportedModelError("write-back into a reference TopK object (use happysim_b200.TopK)")
+                    else:                                  # TopK / TDigest: rebuild the reference's own cells
+                        import sys as _sys
+                        from . import sketching as _sk
+                        mod = _sys.modules[type(sk).__module__]
+                        if algo == A.HS_SK_TOPK:
+                            t = _sk.TopK(int(self.model.entities["i2"][i])); t._load_device_state(state, int(row["c1"]))
+                            sk._counters = {it: mod._Counter(item=it, count=c[0], error=c[1]) for it, c in t._counters.items()}
+                        else:
+                            d = _sk.TDigest(float(self.model.entities["d0"][i])); d._load_device_state(state)
+                            sk._centroids = [mod._Centroid(mean=m_, count=c_) for m_, c_ in zip(d._means, d._counts)]
+                            sk._buffer = list(d._buffer)
+                            sk._min_value, sk._max_value = d._min_value, d._max_value
                     sk._total_count = int(row["c1"])
 
     def _entity_summaries(self):

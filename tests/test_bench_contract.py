@@ -1,0 +1,35 @@
+"""bench.py's output contract: the committed line of the last GPU run carries every key the driver reads, and
+the reference arm (the oracle port on the host cores -- runs without a GPU) prints exactly one JSON line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config"}
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json")))
+    assert BASE_KEYS | {"roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"} <= set(d)
+    assert d["metric"] == "simulated_events_per_second" and d["unit"] == "events/s"      # BASELINE.json: "simulated events/sec"
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["gpu_launches"] == d["steps"]
+    assert "workload" in d["config"] and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert abs(d["value"] - d["events_timed"] / (d["ms_per_step"] * d["steps"] * 1e-3)) / d["value"] < 1e-9
+
+
+def test_reference_arm_prints_one_json_line_without_a_gpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, HS_BENCH_REF_BUDGET_S="1.0"))
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert out.returncode == 0 and len(lines) == 1, out.stderr[-500:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

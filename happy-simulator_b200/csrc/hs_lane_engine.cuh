@@ -71,7 +71,7 @@
 #define HS_DRAW_BUF_SUMMARY 16  /* precomputed draws per stream per lane (even)            */
 #define HS_DRAW_BUF_RECORD 8    /* ... when the recorder staging shares the shared memory  */
 #define HS_STAGE 16             /* staged event records per lane (recorder kernels)        */
-#define HS_FLUSH 8              /* records per cooperative flush: 8 x 16 B = one 128 B line */
+#define HS_FLUSH 8              /* records per flush: 8 x 16 B = one 128 B line            */
 #define HS_LF_HASH 1      /* maintain the order hash                         */
 #define HS_LF_REC 2       /* write event records / sink / service samples    */
 #define HS_LF_PROFILE 4   /* non-constant rate profile (Simpson + Brent path) */
@@ -144,6 +144,24 @@ struct hs_lane_out {
     uint32_t *hist;                   /* [replica][HS_HIST_BINS] or NULL */
 };
 
+/* 256-bit global store (sm_100a: STG.E.256), one full 32-byte sector per lane.  The recorder streams
+ * are write-once per ring pass, so they bypass L1 and are marked evict-first in L2 (HS_ST256_POLICY
+ * 0 selects the default write-back policy; kept as a compile-time switch for A/B measurements). */
+#ifndef HS_ST256_POLICY
+#define HS_ST256_POLICY 1
+#endif
+__device__ __forceinline__ void hs_st256(void *p, const uint4 a, const uint4 b)
+{
+#if HS_ST256_POLICY == 1
+    asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#elif HS_ST256_POLICY == 2
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#else
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#endif
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 /* next arrival of a constant-rate profile, with the reference's "time travel" outcome
  * folded in: if the computed time is earlier than the current one the SourceEvent would be
  * popped and skipped and the Source never ticks again (INT64_MAX). */
@@ -168,12 +186,14 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     constexpr uint32_t STAGE_ROWS = (FLAGS & HS_LF_REC) ? HS_STAGE : 1;
     __shared__ int64_t sh_t[HS_DRAW_BUF][HS_LANE_THREADS];       /* arrival times A_k (ns)          */
     __shared__ double sh_svc[HS_DRAW_BUF][HS_LANE_THREADS];      /* service: Duration.to_seconds()  */
-    /* recorder staging: [slot][lane] so that lanes at different slots never conflict; full
-     * 128-byte groups are written to HBM cooperatively at the converged top of the loop.  (The flush
-     * reads one lane's 8 slots with 8 lanes, an 8-way bank conflict; padding the rows removes it but
-     * makes the per-event writes conflict instead -- measured neutral, so the simple layout stays.) */
+    /* recorder staging, [slot][lane]: a lane only ever touches its own 16-byte column, so neither the
+     * per-event writes nor the flush reads conflict, whatever slot each lane is at.  A lane that holds a
+     * full 128-byte group (8 records) writes it itself as four 256-bit stores (whole 32-byte sectors,
+     * the four sectors of one line back to back).  Sink samples (16 B) and service times (8 B) are paired /
+     * quadrupled the same way into one 32-byte sector per store. */
     __shared__ __align__(16) uint4 sh_rec[STAGE_ROWS][HS_LANE_THREADS];
-    __shared__ uint4 sh_flush[HS_LANE_THREADS / 32][(FLAGS & HS_LF_REC) ? 32 : 1];   /* {tid, stage pos, ring pos, -} per flushing lane */
+    __shared__ __align__(16) uint4 sh_smp[(FLAGS & HS_LF_REC) ? HS_LANE_THREADS : 1];        /* first Sink sample of a pair */
+    __shared__ double sh_sv[(FLAGS & HS_LF_REC) ? 3 : 1][HS_LANE_THREADS];                   /* first three service times of a quad */
     __shared__ __align__(16) hs_ring_entry sh_head[HS_LANE_THREADS];  /* next item to deliver      */
     const uint32_t tid = threadIdx.x;
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,7 +256,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     /* recorder staging cursors: st_wr staged, st_fl flushed; rec_pos = ring slot of record st_fl */
     const bool staged = (FLAGS & HS_LF_REC) && O.records && P.record_cap >= 2 * HS_FLUSH && (P.record_cap % HS_FLUSH) == 0;
     uint32_t st_wr = 0, st_fl = 0;
-    const uint32_t lane = tid & 31u, wib = tid >> 5;
+    /* sample streams: *_sync <=> every earlier entry of the 32-byte sector being filled is staged in shared memory */
+    const bool smp_pairs = (FLAGS & HS_LF_REC) && (P.sample_cap % 2u) == 0;
+    const bool svc_quads = (FLAGS & HS_LF_REC) && (P.service_cap % 4u) == 0;
+    bool smp_sync = false, svc_sync = false;
     hs_now_ev nowq[HS_NOW_CAP];
 
     hs_lane_state *S = states + r;
@@ -321,6 +344,32 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         }                                                                                    \
     } while (0)
 
+    /* Sink sample / service time into their rings, one whole 32-byte sector per global store: the first
+     * entries of a sector wait in the lane's shared-memory column, the last one completes the 256-bit
+     * store.  A sector that was begun before this launch (resume at an odd position) or rings whose
+     * capacity is not a multiple of the sector are written entry by entry. */
+#define HS_SMP_STORE(W)                                                                      \
+    do {                                                                                     \
+        const uint32_t p_ = smp_pos;                                                         \
+        if (!(p_ & 1u)) smp_sync = smp_pairs;                                                \
+        if (smp_sync) { if (!(p_ & 1u)) sh_smp[tid] = (W); else hs_st256(smp + (p_ - 1u), sh_smp[tid], (W)); } \
+        else *(uint4 *)(smp + p_) = (W);                                                     \
+        smp_pos = (p_ + 1 == P.sample_cap) ? 0u : p_ + 1;                                    \
+    } while (0)
+#define HS_SVC_STORE(V)                                                                      \
+    do {                                                                                     \
+        const uint32_t p_ = svc_pos, q_ = p_ & 3u; const double v_ = (V);                    \
+        if (q_ == 0u) svc_sync = svc_quads;                                                  \
+        if (svc_sync) {                                                                      \
+            if (q_ < 3u) sh_sv[q_][tid] = v_;                                                \
+            else { const uint64_t a_ = (uint64_t)__double_as_longlong(sh_sv[0][tid]), b_ = (uint64_t)__double_as_longlong(sh_sv[1][tid]), \
+                                  c_ = (uint64_t)__double_as_longlong(sh_sv[2][tid]), d_ = (uint64_t)__double_as_longlong(v_);            \
+                   hs_st256(svc_out + (p_ - 3u), make_uint4((uint32_t)a_, (uint32_t)(a_ >> 32), (uint32_t)b_, (uint32_t)(b_ >> 32)),      \
+                            make_uint4((uint32_t)c_, (uint32_t)(c_ >> 32), (uint32_t)d_, (uint32_t)(d_ >> 32))); }                        \
+        } else svc_out[p_] = v_;                                                             \
+        svc_pos = (p_ + 1 == P.service_cap) ? 0u : p_ + 1;                                   \
+    } while (0)
+
 #define HS_RECORD(KIND, IDX, ENT)                                                            \
     do {                                                                                     \
         if (FLAGS & HS_LF_HASH) hash = hs_hash_step(hash, now, hs_record_word1((IDX), (KIND), (uint32_t)(ENT))); \
@@ -349,7 +398,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     do {                                                                                     \
         const uint32_t k_ = (uint32_t)((uint64_t)n_svc % HS_DRAW_BUF);                       \
         const int64_t delta_ = hs_seconds_to_ns(sh_svc[k_][tid]);   /* event.py:499, temporal.py:221 */ \
-        if ((FLAGS & HS_LF_REC) && svc_out) { svc_out[svc_pos] = sh_svc[k_][tid];   /* plain store: see HS_SINK */ svc_pos = (svc_pos + 1 == P.service_cap) ? 0u : svc_pos + 1; } \
+        if ((FLAGS & HS_LF_REC) && svc_out) HS_SVC_STORE(sh_svc[k_][tid]);                     \
         n_svc++;                                                                             \
         { const double sv_ = sh_svc[k_][tid]; const uint64_t i_ = ctr + 1; ctr += 2;         \
           HS_C_PUSH(now + delta_, i_, (CREATED), sv_); }                                     \
@@ -367,11 +416,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 uint4 w_; const uint64_t lb_ = (uint64_t)__double_as_longlong(lat_);         \
                 w_.x = (uint32_t)(uint64_t)now; w_.y = (uint32_t)((uint64_t)now >> 32);      \
                 w_.z = (uint32_t)lb_; w_.w = (uint32_t)(lb_ >> 32);                          \
-                /* plain (write-back) store: the 16-byte sample and the 8-byte service time fill their 128-byte  \
-                 * lines over many events; kept in L2 until complete they reach HBM as whole lines, whereas       \
-                 * evict-first stores left partial sectors behind (read-modify-write traffic)                  */ \
-                *(uint4 *)(smp + smp_pos) = w_;                                              \
-                smp_pos = (smp_pos + 1 == P.sample_cap) ? 0u : smp_pos + 1; }                \
+                HS_SMP_STORE(w_); }                                                          \
         }                                                                                    \
     } while (0)
 
@@ -462,28 +507,112 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         if (todo == 0u) break;
         if (__any_sync(0xffffffffu, need)) HS_REFILL_ROUND();
         if (FLAGS & HS_LF_REC) {
-            /* cooperative flush: every lane holding a full 128-byte group hands it to 8 lanes,
-             * which write it as one contiguous line (4 groups per store instruction) */
-            const bool want = staged && (st_wr - st_fl) >= HS_FLUSH;
-            const unsigned fm = __ballot_sync(0xffffffffu, want);
-            if (fm) {
-                const uint32_t n_want = (uint32_t)__popc(fm);
-                if (want) sh_flush[wib][__popc(fm & ((1u << lane) - 1u))] = make_uint4(tid, st_fl, rec_pos, 0u);
-                __syncwarp();
-                const uint32_t c = lane & 7u;
-                for (uint32_t g = lane >> 3; g < n_want; g += 4) {      /* 4 groups = 512 B per store instruction */
-                    const uint4 f = sh_flush[wib][g];
-                    const uint4 w = sh_rec[(f.y + c) % HS_STAGE][f.x];
-                    hs_event_record *dst = O.records + ((size_t)(blockIdx.x * blockDim.x + f.x)) * P.record_cap + f.z + c;
-                    __stcs((uint4 *)dst, w);
-                }
-                __syncwarp();
-                if (want) { st_fl += HS_FLUSH; rec_pos = (rec_pos + HS_FLUSH == P.record_cap) ? 0u : rec_pos + HS_FLUSH; }
+            /* a lane holding a full 128-byte group writes it itself: 8 reads of its own staging column,
+             * four 256-bit stores (st_fl is a multiple of 8, so the group is rows 0-7 or 8-15) */
+            if (staged && (st_wr - st_fl) >= HS_FLUSH) {
+                const uint4 *src = &sh_rec[st_fl & (HS_STAGE - 1)][tid];
+                uint4 *dst = (uint4 *)(rec + rec_pos);
+#pragma unroll
+                for (int g = 0; g < HS_FLUSH; g += 2)
+                    hs_st256(dst + g, src[(size_t)g * HS_LANE_THREADS], src[(size_t)(g + 1) * HS_LANE_THREADS]);
+                st_fl += HS_FLUSH; rec_pos = (rec_pos + HS_FLUSH == P.record_cap) ? 0u : rec_pos + HS_FLUSH;
             }
         }
         if (finished) continue;
 
-        if (now_n == 0) {
+        if (SIMPLE && now_n == 0) {
+            /* ===== M/M/1 shape (HS_LF_SIMPLE): one converged, branch-free chain per iteration =====
+             * Both chains -- arrival TICK -> ENQUEUE [-> NOTIFY [-> POLL -> DELIVER -> WORKER]] and completion
+             * CONTINUATION -> SINK -> POLL [-> DELIVER -> WORKER] -- are the same straight-line code with
+             * per-lane selects, so the lanes of a warp never split by chain.  Everything that could make the
+             * events created at `now` NOT the next pops is tested up front, before any state changes; such a
+             * lane takes the generic one-event step below instead:
+             *   a tie between the pending tick and the continuation, a next tick that is not later than this one
+             *   (zero inter-arrival) or does not exist, the run / window end, a stop bit, the event limit, a
+             *   full device ring, and recorder staging that is not group aligned yet (first events after a resume). */
+            const bool busy = active > 0;
+            const bool pickC = busy && tC < tT;
+            const bool isA = !pickC;
+            const int64_t tn = pickC ? tC : tT;
+            const int64_t tT_next = sh_t[(arr_draws + 1) % HS_DRAW_BUF][tid];
+            bool slow = (busy && tC == tT) || (tn > fast_limit) || (tn < now) || (status & stop_bits) ||
+                        (processed + 8 > P.max_events) || (isA && (tT_next <= tn || tT_next >= HS_T_EXHAUSTED)) ||
+                        (q_len >= P.ring);
+            if ((FLAGS & HS_LF_REC) && rec) slow = slow || !(staged && (st_wr != st_fl || (rec_pos % HS_FLUSH) == 0));
+            if (!slow) {
+                now = tn;
+                const bool q_empty = (q_len == 0);
+                const bool start = isA ? (q_empty && !busy) : !q_empty;      /* a service starts in this chain */
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                const hs_ring_entry h = *my_head;                            /* next queued request (valid if !q_empty) */
+                const uint64_t c0 = ctr;
+                const uint64_t idx0 = isA ? iT : iC;
+                const uint64_t widx = isA ? c0 : h.idx;                      /* the payload WORKER carries */
+                const int64_t start_created = isA ? now : h.created;
+                const uint32_t nrec = isA ? (2u + (q_empty ? 1u : 0u) + (start ? 3u : 0u)) : (3u + (start ? 2u : 0u));
+                ctr = c0 + (isA ? (2u + (q_empty ? 1u : 0u) + (start ? 4u : 0u)) : (2u + (start ? 3u : 0u)));
+                processed += nrec;
+                if ((FLAGS & HS_LF_HASH) || ((FLAGS & HS_LF_REC) && rec)) {
+                    /* slot:   0            1        2             3              4               5
+                     * A:      TICK iT      ENQ c0   NOTIFY c0+2   POLL c0+3      DELIVER c0+4    WORKER c0
+                     * C:      CONT iC      SINK c0  POLL c0+1     DELIVER c0+2   WORKER item     -        */
+                    const uint32_t esrv = (uint32_t)M.srv_id << 16;
+                    uint32_t z[6], w[6]; bool v[6];
+                    z[0] = (uint32_t)idx0; z[1] = (uint32_t)c0; z[2] = (uint32_t)c0 + (isA ? 2u : 1u);
+                    z[3] = (uint32_t)c0 + (isA ? 3u : 2u); z[4] = isA ? (uint32_t)c0 + 4u : (uint32_t)widx; z[5] = (uint32_t)c0;
+                    w[0] = isA ? ((uint32_t)HS_EV_SOURCE_TICK | ((uint32_t)M.src_id << 16)) : ((uint32_t)HS_EV_CONTINUATION | esrv);
+                    w[1] = isA ? ((uint32_t)HS_EV_REQ_ENQUEUE | esrv) : ((uint32_t)HS_EV_REQ_SINK | ((uint32_t)M.dst_id << 16));
+                    w[2] = (isA ? (uint32_t)HS_EV_NOTIFY : (uint32_t)HS_EV_POLL) | esrv;
+                    w[3] = (isA ? (uint32_t)HS_EV_POLL : (uint32_t)HS_EV_DELIVER) | esrv;
+                    w[4] = (isA ? (uint32_t)HS_EV_DELIVER : (uint32_t)HS_EV_REQ_WORKER) | esrv;
+                    w[5] = (uint32_t)HS_EV_REQ_WORKER | esrv;
+                    v[0] = true; v[1] = true; v[2] = isA ? q_empty : true; v[3] = start; v[4] = start; v[5] = isA && start;
+                    const uint32_t nlo = (uint32_t)(uint64_t)now, nhi = (uint32_t)((uint64_t)now >> 32);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        if (v[j]) {
+                            if (FLAGS & HS_LF_HASH) hash = hs_hash_step(hash, now, (uint64_t)z[j] | ((uint64_t)(w[j] & 0xffu) << 32) | ((uint64_t)(w[j] >> 16) << 40));
+                            if ((FLAGS & HS_LF_REC) && rec) sh_rec[(st_wr + (uint32_t)j) % HS_STAGE][tid] = make_uint4(nlo, nhi, z[j], w[j]);
+                        }
+                    }
+                    if ((FLAGS & HS_LF_REC) && rec) st_wr += nrec;
+                }
+                if (isA) {
+                    /* Source: payload index c0, next SourceEvent index c0 + 1 (source.py:166-170) */
+                    arr_draws++; tT = tT_next; iT = c0 + 1;
+                    if (!start) {                                   /* Queue._handle_enqueue: the request waits */
+                        hs_ring_entry e_; e_.created = now; e_.idx = c0;
+                        ring[(q_head + q_len) & ring_mask] = e_;
+                        if (q_empty) *my_head = e_;
+                        q_len++;
+                    }
+                } else {
+                    /* Server resumes after its yield, the Sink takes the request (server.py:255-273, common.py:36-44) */
+                    total_service = HS_ADD(total_service, svc_s);
+                    HS_SINK(c_created);
+                    active = 0;
+                    if (start) {                                    /* Queue._handle_poll: pop the head, prefetch the next */
+                        q_head++; q_len--;
+                        if (q_len > 0) {
+                            const hs_ring_entry *n_ = ring + (q_head & ring_mask);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
+                                         :: "r"(my_head_s), "l"(n_) : "memory");
+                        }
+                    }
+                }
+                if (start) {
+                    /* Server.handle_queued_event up to its yield (server.py:217-253): the scheduled
+                     * ProcessContinuation takes the last index of the chain */
+                    const double sv_ = sh_svc[(uint32_t)((uint64_t)n_svc % HS_DRAW_BUF)][tid];
+                    if ((FLAGS & HS_LF_REC) && svc_out) HS_SVC_STORE(sv_);
+                    n_svc++;
+                    tC = now + hs_seconds_to_ns(sv_); iC = ctr - 1; c_created = start_created; svc_s = sv_; active = 1;
+                }
+                continue;
+            }
+        }
+
+        if (!SIMPLE && now_n == 0) {
             const bool pickC = active > 0 && (tC < tT || (tC == tT && iC < iT));
             const int64_t tn = pickC ? tC : tT;
             /* fast path <=> the chosen event is not tied, lies inside both the run and the window
@@ -678,6 +807,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             st_fl++; rec_pos = (rec_pos + 1 == P.record_cap) ? 0u : rec_pos + 1;
         }
     }
+    if (FLAGS & HS_LF_REC) {                /* entries of a sector that is not complete yet */
+        if (smp_sync && (smp_pos & 1u)) *(uint4 *)(smp + (smp_pos - 1u)) = sh_smp[tid];
+        if (svc_sync) for (uint32_t q = 0; q < (svc_pos & 3u); ++q) svc_out[svc_pos - (svc_pos & 3u) + q] = sh_sv[q][tid];
+    }
 
     /* ---- persist / publish --------------------------------------------- */
     /* derived counters: a tick is processed per consumed arrival time except the pending one;
@@ -733,6 +866,8 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
 #undef HS_NEXT_TICK
 #undef HS_SERVICE_START
 #undef HS_SINK
+#undef HS_SMP_STORE
+#undef HS_SVC_STORE
 #undef HS_Q_PUSH
 #undef HS_Q_POP
 #undef HS_PUSH_NOW

@@ -156,3 +156,56 @@ def test_event_limit_stops_a_model_whose_clock_cannot_advance(eng, engine_id):
     assert (want["summaries"]["events_processed"] == 5003).all()
     assert (want["summaries"]["status"] & hs._abi.HS_ST_EVENT_LIMIT).all()
     assert_same(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The configuration bench.py times: hash OFF (flags=0), small recorder rings that wrap many times,
+# one continuing run cut into resumed windows.  hs_lane_kernel<10> (REC|SIMPLE) and <2> (REC), and
+# with the hash on <11>/<3>; rings are compared raw (slot = item number mod cap on both sides).
+
+BENCH_CAPS = dict(record_cap=1024, sample_cap=128, service_cap=128)
+
+
+@pytest.mark.parametrize("flags", [0, hs._abi.HS_RUN_ORDER_HASH])
+@pytest.mark.parametrize("name,model_kw,end_s,n_rep", [
+    ("mm1_simple", dict(), 400.0, 160),                      # configs[1] shape -> HS_LF_SIMPLE kernels
+    ("mm1_heavy_simple", dict(rate=9.7), 300.0, 96),         # long queues: ring push/pop + prefetch path
+    ("mm1_lifo", dict(rate=9.0, lifo=True), 200.0, 64),      # not SIMPLE -> the general fused chains
+    ("mmc4", dict(rate=32.0, concurrency=4), 60.0, 64),
+])
+def test_bench_configuration_windows_and_wrapping_rings(eng, name, model_kw, end_s, n_rep, flags):
+    model = hs.mm1(**model_kw)
+    end = int(end_s * 1e9)
+    kw = dict(seed=1234, n_replicas=n_rep, flags=flags, **BENCH_CAPS)
+    want = O.oracle_run(model, O.make_params(end_ns=end, **kw))
+    assert int(want["summaries"]["events_processed"].min()) > 4 * 1024      # every ring wrapped
+    eng.upload(model)
+    cuts = [end // 7, end // 7 + 1, end // 3, end // 2 + 12345, (4 * end) // 5]
+    eng.run(engine.make_params(end_ns=end, window_end_ns=cuts[0], **kw))
+    for c in cuts[1:]:
+        eng.run(engine.make_params(end_ns=end, window_end_ns=c, resume=1, **kw))
+        # a paused state is itself comparable: the oracle paused at the same cut
+    mid = eng.read_outputs()
+    pw = O.oracle_run(model, O.make_params(end_ns=end, window_end_ns=cuts[-1], **kw))
+    assert_same(mid, pw)
+    eng.run(engine.make_params(end_ns=end, window_end_ns=-1, resume=1, **kw))
+    got = eng.read_outputs()
+    assert_same(got, want)
+    if flags == 0:
+        assert (got["summaries"]["order_hash"] == 0).all()
+
+
+@pytest.mark.parametrize("caps", [dict(record_cap=1000, sample_cap=125, service_cap=126),    # not sector multiples
+                                  dict(record_cap=24, sample_cap=2, service_cap=4),          # smallest staged rings
+                                  dict(record_cap=0, sample_cap=64, service_cap=0),
+                                  dict(record_cap=0, sample_cap=0, service_cap=64)])
+def test_recorder_ring_shapes(eng, caps):
+    """Ring capacities that are not multiples of the 32-byte store sector, minimal rings, and single streams."""
+    model = hs.mm1()
+    end = 120 * 10**9
+    kw = dict(seed=99, n_replicas=70, flags=0, **caps)
+    want = O.oracle_run(model, O.make_params(end_ns=end, **kw))
+    eng.upload(model)
+    eng.run(engine.make_params(end_ns=end, window_end_ns=37 * 10**9 + 5, **kw))
+    eng.run(engine.make_params(end_ns=end, window_end_ns=-1, resume=1, **kw))
+    assert_same(eng.read_outputs(), want)

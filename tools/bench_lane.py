@@ -5,12 +5,12 @@ sys.path[:0] = [ROOT]
 import happysim_b200 as hs
 from happysim_b200 import engine
 
-def run(name, end_s, **kw):
+def run(name, end_s, hash=False, **kw):
     eng = engine.Engine(0)
     eng.upload(hs.mm1())
     best = None
     for _ in range(4):
-        eng.run(engine.make_params(seed=1234, end_ns=int(end_s * 1e9), n_replicas=65536, flags=0, **kw))
+        eng.run(engine.make_params(seed=1234, end_ns=int(end_s * 1e9), n_replicas=65536, flags=(1 if hash else 0), **kw))
         eng.sync()
         ms = eng.last_run_ms(); best = ms if best is None else min(best, ms)
     ev = int(eng.read_outputs()["summaries"]["events_processed"].sum())
@@ -19,4 +19,4 @@ def run(name, end_s, **kw):
 
 run("summary", 2000.0)
 run("record", 2000.0, record_cap=1024, sample_cap=128, service_cap=128)
-run("hash+rec", 2000.0, record_cap=1024, sample_cap=128, service_cap=128, )
+run("hash+rec", 2000.0, record_cap=1024, sample_cap=128, service_cap=128, hash=True)

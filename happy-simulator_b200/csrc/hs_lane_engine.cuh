@@ -166,13 +166,13 @@ __device__ __forceinline__ void hs_st256(void *p, const uint4 a, const uint4 b)
  * folded in: if the computed time is earlier than the current one the SourceEvent would be
  * popped and skipped and the Source never ticks again (INT64_MAX). */
 template <bool PROFILE>
-__device__ __forceinline__ int64_t hs_lane_next_arrival(int64_t t, double target, double rate,
+__device__ __forceinline__ int64_t hs_lane_next_arrival(int64_t t, double target, double rate, double rate_recip,
                                                         const hs_profile_desc *prof)
 {
     if (t >= HS_T_EXHAUSTED) return t;              /* dead / exhausted source stays so */
     int64_t n;
     if (PROFILE) n = hs_next_arrival_profile_ns(prof, t, target);
-    else n = hs_next_arrival_ns(t, target, rate);
+    else n = hs_next_arrival_ns_r(t, target, rate, rate_recip);
     if (n == HS_T_EXHAUSTED) return n;              /* RuntimeError: no further SourceEvent object */
     return n < t ? INT64_MAX : n;
 }
@@ -215,6 +215,9 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         c_rt = M.cell_i0[(size_t)cell * M.n_entities + M.srv_id];
     }
     const double lambda = HS_DIV(1.0, mean);             /* exponential.py:36 */
+    /* reciprocals for hs_div_by: exact x / rate and x / lambda in three fp64 instructions (0.0 = general division) */
+    const double rate_recip = hs_recip_divisor_ok(rate) ? HS_DIV(1.0, rate) : 0.0;
+    const double lambda_recip = hs_recip_divisor_ok(lambda) ? HS_DIV(1.0, lambda) : 0.0;
     hs_profile_desc prof_local;
     if (FLAGS & HS_LF_PROFILE) prof_local = M.prof;
     const hs_profile_desc *profp = (FLAGS & HS_LF_PROFILE) ? &prof_local : nullptr;
@@ -300,7 +303,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     /* next arrival time from t (arrival_time_provider.py:66-82); a result < t would be
      * popped and skipped as "time travel" by the loop (simulation.py:479-489), after which the
      * Source never ticks again: INT64_MAX marks that dead source. */
-#define HS_NEXT_ARRIVAL(T, TARGET) hs_lane_next_arrival<(FLAGS & HS_LF_PROFILE) != 0>((T), (TARGET), rate, profp)
+#define HS_NEXT_ARRIVAL(T, TARGET) hs_lane_next_arrival<(FLAGS & HS_LF_PROFILE) != 0>((T), (TARGET), rate, rate_recip, profp)
 
     /* one converged refill round: each lane that has room generates the next Philox
      * pair of each stream and stores the precomputed draws */
@@ -326,12 +329,12 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             double u0_ = 0.0, u1_ = 0.0;                                                     \
             int64_t d0_ = hs_seconds_to_ns(mean), d1_ = d0_;                                 \
             if (expo && !trace_svc) { hs_uniform_pair(seed, rid, sid_svc, s_gen >> 1, &u0_, &u1_); \
-                                        d0_ = hs_exp_latency_ns(u0_, lambda); d1_ = hs_exp_latency_ns(u1_, lambda); } \
+                                        d0_ = hs_exp_latency_ns_r(u0_, lambda, lambda_recip); d1_ = hs_exp_latency_ns_r(u1_, lambda, lambda_recip); } \
             if (expo && trace_svc) {       /* Duration.from_seconds(-log(1-U) / lambda)         */ \
                 const uint64_t k_ = s_gen & ~1ull;                                           \
                 if (k_ + 1 >= P.n_trace_svc) { status |= HS_ST_TRACE_EXHAUSTED; finished = true; } \
-                else { d0_ = hs_seconds_to_ns(HS_DIV(trace_svc[(size_t)r * P.n_trace_svc + k_], lambda));  \
-                       d1_ = hs_seconds_to_ns(HS_DIV(trace_svc[(size_t)r * P.n_trace_svc + k_ + 1], lambda)); } \
+                else { d0_ = hs_seconds_to_ns(hs_div_by(trace_svc[(size_t)r * P.n_trace_svc + k_], lambda, lambda_recip));  \
+                       d1_ = hs_seconds_to_ns(hs_div_by(trace_svc[(size_t)r * P.n_trace_svc + k_ + 1], lambda, lambda_recip)); } \
             }                                                                                \
             if (!(s_gen & 1)) {                                                              \
                 const double s0_ = hs_ns_to_seconds(d0_);                                    \
@@ -436,6 +439,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         { const hs_ring_entry h_ = *my_head; (CREATED) = h_.created; (IDX) = h_.idx; }       \
         if (!lifo) q_head++;                                                                 \
         q_len--;                                                                             \
+        if (q_len == 0) q_head = 0;   /* an empty queue restarts at slot 0: the rings' hot lines stay in L2 */ \
         if (q_len > 0) {                                                                     \
             const hs_ring_entry *n_ = ring + ((lifo ? q_head + q_len - 1 : q_head) & ring_mask); \
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" \
@@ -498,6 +502,11 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     }
 
     const uint32_t stop_bits = HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW;
+    /* SIMPLE kernels: conditions that only a generic step can change, folded into one flag
+     * (a stop bit is set; recorder staging not yet group aligned after a resume) */
+#define HS_STICKY_SLOW() (((status & stop_bits) != 0) || ((FLAGS & HS_LF_REC) && rec && !(staged && (st_wr != st_fl || (rec_pos % HS_FLUSH) == 0))))
+    bool sticky_slow = HS_STICKY_SLOW();
+    const int64_t ev_fast_limit = P.max_events - 8;     /* a chain is <= 6 events: single-step near the limit */
     const int64_t fast_limit = (windowed && P.window_end_ns < P.end_ns) ? P.window_end_ns : P.end_ns;
     bool paused = false;
     while (true) {
@@ -506,6 +515,15 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
         const unsigned todo = __ballot_sync(0xffffffffu, !finished);
         if (todo == 0u) break;
         if (__any_sync(0xffffffffu, need)) HS_REFILL_ROUND();
+        /* SIMPLE: the three shared-memory operands of the next chain are requested first, so their
+         * latency is covered by the flush below: next arrival time, next service time, queue head */
+        int64_t tT_next = 0; double sv_next = 0.0; hs_ring_entry h; h.created = 0; h.idx = 0;
+        if (SIMPLE) {
+            tT_next = sh_t[(arr_draws + 1) % HS_DRAW_BUF][tid];
+            sv_next = sh_svc[(uint32_t)((uint64_t)n_svc % HS_DRAW_BUF)][tid];
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            h = *my_head;                                    /* next queued request (meaningful if q_len > 0) */
+        }
         if (FLAGS & HS_LF_REC) {
             /* a lane holding a full 128-byte group writes it itself: 8 reads of its own staging column,
              * four 256-bit stores (st_fl is a multiple of 8, so the group is rows 0-7 or 8-15) */
@@ -534,17 +552,15 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
             const bool pickC = busy && tC < tT;
             const bool isA = !pickC;
             const int64_t tn = pickC ? tC : tT;
-            const int64_t tT_next = sh_t[(arr_draws + 1) % HS_DRAW_BUF][tid];
-            bool slow = (busy && tC == tT) || (tn > fast_limit) || (tn < now) || (status & stop_bits) ||
-                        (processed + 8 > P.max_events) || (isA && (tT_next <= tn || tT_next >= HS_T_EXHAUSTED)) ||
-                        (q_len >= P.ring);
-            if ((FLAGS & HS_LF_REC) && rec) slow = slow || !(staged && (st_wr != st_fl || (rec_pos % HS_FLUSH) == 0));
+            /* (tn >= now always holds here: arrival times are generated non-decreasing -- an earlier one is
+             * stored as INT64_MAX, "time travel" -- and a continuation resumes at now + delta, delta >= 0) */
+            bool slow = sticky_slow || (busy && tC == tT) || (tn > fast_limit) || (processed > ev_fast_limit) ||
+                        (isA && tT_next <= tn) || (q_len >= P.ring);
+            if (FLAGS & HS_LF_PROFILE) slow = slow || (isA && tT_next == HS_T_EXHAUSTED);
             if (!slow) {
                 now = tn;
                 const bool q_empty = (q_len == 0);
                 const bool start = isA ? (q_empty && !busy) : !q_empty;      /* a service starts in this chain */
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                const hs_ring_entry h = *my_head;                            /* next queued request (valid if !q_empty) */
                 const uint64_t c0 = ctr;
                 const uint64_t idx0 = isA ? iT : iC;
                 const uint64_t widx = isA ? c0 : h.idx;                      /* the payload WORKER carries */
@@ -593,6 +609,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     active = 0;
                     if (start) {                                    /* Queue._handle_poll: pop the head, prefetch the next */
                         q_head++; q_len--;
+                        if (q_len == 0) q_head = 0;                 /* an empty queue restarts at slot 0 (hot lines stay in L2) */
                         if (q_len > 0) {
                             const hs_ring_entry *n_ = ring + (q_head & ring_mask);
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
@@ -603,7 +620,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 if (start) {
                     /* Server.handle_queued_event up to its yield (server.py:217-253): the scheduled
                      * ProcessContinuation takes the last index of the chain */
-                    const double sv_ = sh_svc[(uint32_t)((uint64_t)n_svc % HS_DRAW_BUF)][tid];
+                    const double sv_ = sv_next;
                     if ((FLAGS & HS_LF_REC) && svc_out) HS_SVC_STORE(sv_);
                     n_svc++;
                     tC = now + hs_seconds_to_ns(sv_); iC = ctr - 1; c_created = start_created; svc_s = sv_; active = 1;
@@ -796,8 +813,10 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 break;
             default: break;
             }
+            if (SIMPLE) sticky_slow = HS_STICKY_SLOW();
         }
     }
+#undef HS_STICKY_SLOW
 
     if (!valid) return;
     if (P.resume && S->done) return;        /* finished in an earlier window: outputs already final */

@@ -198,8 +198,38 @@ HS_HD double hs_exp1(double u) { return -hs_log(HS_SUB(1.0, u)); }
 HS_HD int64_t hs_seconds_to_ns(double seconds)          /* T1 */
 { return (int64_t)HS_D2LL(HS_MUL(seconds, HS_NS_PER_S)); }
 
+/* Correctly rounded x / b for a divisor whose correctly rounded reciprocal y = RN(1/b) is at hand:
+ *     q = RN(x * y);   r = x - q * b  (exact in one fma: q is a faithful quotient);   x / b = RN(q + r * y)
+ * (Markstein, "Computation of elementary functions on the IBM RISC System/6000 processor", IBM J. Res.
+ * Dev. 34 (1990), Theorem 8.5 -- the final step of every fma-based IEEE division, including the one nvcc
+ * emits for `/`; valid while no intermediate over-/underflows, which the magnitudes on this path -- ns
+ * counts below 2^63, targets in [2^-53, 37], rates in [1e-6, 1e12] -- never approach).  Three fp64
+ * instructions instead of the ~20 of a general division; the result is bit-identical to `x / b`
+ * (tests/test_sampler.py checks it against the C division on random and structured operands,
+ * tools/divcheck.c ran 5e9 more).  The sign of a zero quotient is not preserved (-0.0 / b gives +0.0);
+ * no caller can observe it: the quotients are added to a non-negative time or truncated to an integer. */
+HS_HD double hs_div_recip(double x, double b, double y)
+{
+    const double q = HS_MUL(x, y);
+    const double r = HS_FMA(-q, b, x);
+    return HS_FMA(r, y, q);
+}
+#define HS_NS_PER_S_RECIP 1e-9      /* the double nearest 10^-9 = RN(1 / 1e9) */
+
+/* For run-time divisors (a Source's rate, a server's lambda) the caller passes y = 1.0 / b, or 0.0 to ask for
+ * the general division: for divisors outside the comfortable range and for a significand of all ones,
+ * the one case the literature singles out for reciprocal-based division. */
+HS_HD int hs_recip_divisor_ok(double b)
+{
+    const uint64_t u = HS_D2BITS(b);
+    const uint64_t man = u & 0x000fffffffffffffULL;
+    return b >= 1e-100 && b <= 1e100 && man != 0x000fffffffffffffULL;
+}
+HS_HD double hs_div_by(double x, double b, double y)
+{ return y != 0.0 ? hs_div_recip(x, b, y) : HS_DIV(x, b); }
+
 HS_HD double hs_ns_to_seconds(int64_t ns)               /* T3 */
-{ return HS_DIV(HS_LL2D(ns), HS_NS_PER_S); }
+{ return hs_div_recip(HS_LL2D(ns), HS_NS_PER_S, HS_NS_PER_S_RECIP); }
 
 /* L2: next arrival of a constant-rate profile; target = 1.0 (constant
  * provider) or hs_exp1(u) (Poisson provider). */
@@ -209,10 +239,19 @@ HS_HD int64_t hs_next_arrival_ns(int64_t cur_ns, double target, double rate)
     return hs_seconds_to_ns(t_next);
 }
 
+/* L2 with the rate's reciprocal precomputed by the caller (rate_recip = 1.0 / rate by IEEE division, or 0.0) */
+HS_HD int64_t hs_next_arrival_ns_r(int64_t cur_ns, double target, double rate, double rate_recip)
+{
+    double t_next = HS_ADD(hs_ns_to_seconds(cur_ns), hs_div_by(target, rate, rate_recip));
+    return hs_seconds_to_ns(t_next);
+}
+
 /* D1: ExponentialLatency.get_latency -> Duration (ns). lambda = 1/mean is
  * computed once by the caller exactly as the reference does (exponential.py:36). */
 HS_HD int64_t hs_exp_latency_ns(double u, double lambda)
 { return hs_seconds_to_ns(HS_DIV(hs_exp1(u), lambda)); }
+HS_HD int64_t hs_exp_latency_ns_r(double u, double lambda, double lambda_recip)
+{ return hs_seconds_to_ns(hs_div_by(hs_exp1(u), lambda, lambda_recip)); }
 
 /* Server.handle_queued_event: service_time_s = Duration.to_seconds(); the
  * generator yields it and ProcessContinuation adds int(delay*1e9) to now

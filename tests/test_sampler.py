@@ -132,3 +132,19 @@ def test_zipf_routing_keys_follow_the_reference_inverse_transform():
     keys = [L.hs_cpu_routing_key(float(u), 100, cum.ctypes.data_as(C.POINTER(C.c_double))) for u in np.random.RandomState(3).random_sample(5000)]
     counts = np.bincount(keys, minlength=100)
     assert counts[0] > counts[1] > counts[5] > counts[50]
+
+
+def test_ns_to_seconds_is_the_ieee_division():
+    """hs_ns_to_seconds evaluates float(ns) / 1e9 as q = x * RN(1e-9), r = fma(-q, 1e9, x), fma(r, RN(1e-9), q)
+    (hs_div_recip, three fp64 instructions on the device).  It must equal the IEEE quotient the reference
+    computes (core/temporal.py:66-68) for every ns count: random magnitudes, exact multiples of 1e9 and
+    their neighbours, powers of two and their neighbours.  (tools/divcheck.c: 5e9 more operands, 0 mismatches.)"""
+    L = O.lib()
+    rng = np.random.default_rng(7)
+    vals = [int(v) >> int(s) for v, s in zip(rng.integers(0, 2**62, 120_000), rng.integers(0, 62, 120_000))]
+    vals += [m * 10**9 + k for m in rng.integers(0, 9_000_000, 20_000).tolist() for k in (-1, 0, 1)]
+    vals += [(1 << e) + k for e in range(1, 63) for k in range(-40, 41)]
+    for v in vals:
+        if v < 0:
+            continue
+        assert L.hs_cpu_ns_to_seconds(v) == float(v) / 1e9, v

@@ -554,11 +554,12 @@ class Simulation:
     """core/simulation.py:38-591 -- same constructor, ``run() -> SimulationSummary``.
 
     Extra keyword arguments (not in the reference): ``seed`` (Philox key), ``replica`` (Philox
-    replica word), ``device``."""
+    replica word), ``device``, ``queue_ring`` (first size of the device queue rings; they grow on overflow)."""
 
     def __init__(self, start_time: Instant | None = None, end_time: Instant | None = None, sources=None,
                  entities=None, probes=None, trace_recorder=None, fault_schedule=None, duration: float | None = None,
-                 *, seed: int | None = None, replica: int = 0, device: int = 0, rng: str = "philox"):
+                 *, seed: int | None = None, replica: int = 0, device: int = 0, rng: str = "philox",
+                 queue_ring: int | None = None):
         if duration is not None and end_time is not None:
             raise ValueError("Cannot specify both 'duration' and 'end_time'")
         if start_time is not None and start_time.nanoseconds != 0:
@@ -583,6 +584,8 @@ class Simulation:
         if rng not in ("philox", "stock"):
             raise ValueError("rng must be 'philox' or 'stock'")
         self._rng = rng
+        self._queue_ring = int(queue_ring) if queue_ring else 0
+        self.last_run_info: dict = {}
         self._summary: SimulationSummary | None = None
         self._instant_cls = Instant
         self.model, self.objects = lowering.lower(self._sources, self._entities, probes=self._probes)
@@ -592,69 +595,50 @@ class Simulation:
         return self._summary
 
     # -- single run -------------------------------------------------------------
-    def _caps(self, n_hint: int | None = None):
-        dur = self._end_time.to_seconds()
+    def _rate_bound(self) -> float:
         ents = self.model.entities
         rate = 0.0
         for i in self.model.ids_of(A.HS_ENT_SOURCE):
             pi = int(ents["i3"][i])
             if pi == 0:
                 rate += float(ents["d0"][i])
-            else:        # non-constant profile: bound by its largest parameter that can be a rate
-                pr = self.model.profiles[pi - 1]
-                rate += float(max(pr["p"][1:3]) if int(pr["kind"]) == A.HS_PROF_LINEAR_RAMP else max(pr["p"][0:2]))
+            else:        # non-constant profile: bound by its largest rate
+                rate += lowering.profile_max_rate(self.model.profiles[pi - 1], getattr(self.model, "profile_tables", None))
+        return rate
+
+    def _caps(self, n_hint: int | None = None):
+        dur = self._end_time.to_seconds()
+        rate = self._rate_bound()
         req = int(rate * dur * 1.3 + 6 * math.sqrt(rate * dur + 1) + 64)
         n_srv = len(self.model.ids_of(A.HS_ENT_SERVER))
         chain = 1 if (n_srv <= 1 or self.model.ids_of(A.HS_ENT_LB)) else n_srv     # tandem: one start per stage
         return dict(record_cap=0, sample_cap=req, service_cap=req * chain)
 
+    def _events_per_request(self) -> int:
+        """Upper bound of processed events per generated request: ~7 per server stage a request can pass
+        (ENQUEUE, NOTIFY, POLL, DELIVER, WORKER, CONTINUATION, completion POLL) plus tick, routing and sink."""
+        n_srv = len(self.model.ids_of(A.HS_ENT_SERVER))
+        stages = 1 if (n_srv <= 1 or self.model.ids_of(A.HS_ENT_LB)) else n_srv
+        return 8 * stages + 8 + 2 * len(self.model.ids_of(A.HS_ENT_PROBE))
+
+    def _queue_ring_hint(self) -> int:
+        """First device ring size: the backlog an overloaded model would build over the run, bounded."""
+        if self._queue_ring:
+            return int(self._queue_ring)
+        dur = self._end_time.to_seconds()
+        ents = self.model.entities
+        cap = 0.0
+        for i in self.model.ids_of(A.HS_ENT_SERVER):
+            mean = float(ents["d0"][i])
+            cap += (max(1, int(ents["i0"][i])) / mean) if mean > 0 else float("inf")
+        backlog = max(0.0, (self._rate_bound() - cap) * dur)
+        ring = 256
+        while ring < min(2.5 * backlog + 64, 1 << 22):
+            ring *= 2
+        return ring
+
     def run(self) -> SimulationSummary:
-        t0 = _time.monotonic()
-        eng = _engine(self._device)
-        eng.upload(self.model)
-        caps = self._caps()
-        eng.set_trace(None, None)
-        if getattr(self, "_rng", "philox") == "stock":
-            eng.set_trace(*stock_streams(self._seed, 1, caps["sample_cap"] * 2 + 64))
-        # per-server service-time lists / per-collector samples are demultiplexed with the event records
-        n_streams = len(self.model.ids_of(A.HS_ENT_SINK)) + len(self.model.ids_of(A.HS_ENT_PROBE))
-        need_events = len(self.model.ids_of(A.HS_ENT_SERVER)) > 1 or n_streams > 1
-        if self.model.ids_of(A.HS_ENT_PROBE):        # probe samples share the sample stream
-            dur = self._end_time.to_seconds()
-            extra = sum(int(dur * float(self.model.profiles[int(self.model.entities["i3"][i]) - 1]["p"][0])) + 8
-                        for i in self.model.ids_of(A.HS_ENT_SOURCE) if int(self.model.entities["i3"][i]) > 0)
-            caps["sample_cap"] += extra
-        for _ in range(6):
-            kw = dict(caps)
-            if need_events:
-                kw["record_cap"] = kw["service_cap"] * 12
-            eng.run(make_params(seed=self._seed, rid_base=self._replica, end_ns=self._end_time.nanoseconds,
-                                n_replicas=1, flags=0, max_events=60 * kw["sample_cap"] + 1_000_000, **kw))
-            out = eng.read_outputs()
-            s = out["summaries"][0]
-            if int(s["status"]) & A.HS_ST_TRACE_EXHAUSTED:
-                caps = {k: 2 * v for k, v in caps.items()}
-                eng.set_trace(*stock_streams(self._seed, 1, caps["sample_cap"] * 2 + 64))
-                continue
-            if int(s["status"]) & A.HS_ST_EVENT_LIMIT:
-                raise RuntimeError("event limit reached: the model's clock does not advance (a source faster than "
-                                   "one event per nanosecond never terminates in the reference either)")
-            if int(s["status"]) & (A.HS_ST_QUEUE_OVERFLOW | A.HS_ST_FEL_OVERFLOW):
-                raise RuntimeError(f"device structure overflow (status {int(s['status'])}); raise queue_ring")
-            if (int(s["n_sink_samples"]) <= kw["sample_cap"] and int(s["n_service_samples"]) <= kw["service_cap"]
-                    and (not need_events or int(s["events_processed"]) <= kw["record_cap"])):
-                break
-            caps = dict(record_cap=0, sample_cap=2 * int(s["n_sink_samples"]) + 64,
-                        service_cap=2 * int(s["n_service_samples"]) + 64)
-        self._write_back(out, 0)
-        s = out["summaries"][0]
-        duration_s = float(int(s["final_time_ns"])) / 1_000_000_000
-        n = int(s["events_processed"])
-        self._summary = SimulationSummary(duration_s=duration_s, total_events_processed=n, events_cancelled=0,
-                                          events_per_second=n / duration_s if duration_s > 0 else 0.0,
-                                          wall_clock_seconds=_time.monotonic() - t0,
-                                          entities=self._entity_summaries())
-        return self._summary
+        return _run_many([self], seed=self._seed, seed_stride=0, rid_base=self._replica, rid_stride=0)[0]
 
     def _write_back(self, out, r: int) -> None:
         """Publish replica ``r`` onto the Python objects, where the reference's callers look."""
@@ -772,18 +756,196 @@ class Simulation:
 
     # -- ensembles ----------------------------------------------------------------
     def run_ensemble(self, n_replicas: int, *, seed: int | None = None, seed_stride: int = 0, rid_base: int = 0,
-                     rid_stride: int = 1, replica_index_base: int = 0, replicas_per_cell: int = 1, **caps):
+                     rid_stride: int = 1, replica_index_base: int = 0, replicas_per_cell: int = 1,
+                     window_end_s: float | None = None, resume: bool = False, host: dict | None = None,
+                     upload: bool = True, totals: bool = True, on_overflow: str = "grow", **caps):
         """N independent replicas of this model on the device; returns the raw per-replica arrays
-        (summaries, entity_stats, optional recorder rings) and the engine's totals."""
+        (summaries, entity_stats, optional recorder rings) and the engine's totals.
+
+        ``window_end_s`` / ``resume`` cut one continuing run into windows exactly like the reference's
+        ``Simulation._run_window`` (core/simulation.py:527-541): state stays resident in HBM between calls.
+        ``host`` = caller-owned (pinned) buffers from ``Engine.alloc_host_outputs`` to read into.
+
+        Every replica's ``status`` is checked.  A device queue ring that overflowed (the reference's queues are
+        unbounded) is handled per ``on_overflow``: "grow" re-runs the ensemble with doubled rings (fresh,
+        unwindowed runs only), "raise" raises, "ignore" returns the flagged statuses to the caller."""
         eng = _engine(self._device)
-        eng.upload(self.model)
-        eng.run(make_params(seed=self._seed if seed is None else seed, seed_stride=seed_stride, rid_base=rid_base,
-                            rid_stride=rid_stride, end_ns=self._end_time.nanoseconds, n_replicas=n_replicas,
-                            replica_index_base=replica_index_base, replicas_per_cell=replicas_per_cell, **caps))
-        out = eng.read_outputs()
-        out["totals"] = eng.read_totals()
+        if upload:
+            eng.upload(self.model)
+        if not resume:
+            eng.set_trace(None, None)            # never inherit a stock-generator trace from an earlier run()
+        end_ns = self._end_time.nanoseconds
+        we = -1
+        if window_end_s is not None:
+            w = int(round(float(window_end_s) * 1e9))
+            we = w if w < end_ns else -1
+        ring = int(caps.pop("queue_ring", 0) or 0)
+        bad = A.HS_ST_QUEUE_OVERFLOW | A.HS_ST_FEL_OVERFLOW | A.HS_ST_SKETCH_OVERFLOW
+        for _ in range(12):
+            eng.run(make_params(seed=self._seed if seed is None else seed, seed_stride=seed_stride, rid_base=rid_base,
+                                rid_stride=rid_stride, end_ns=end_ns, n_replicas=n_replicas,
+                                replica_index_base=replica_index_base, replicas_per_cell=replicas_per_cell,
+                                window_end_ns=we, resume=int(bool(resume)), queue_ring=ring, **caps))
+            out = eng.read_outputs(host)
+            st = out["summaries"]["status"]
+            flagged = int((st & bad != 0).sum())
+            if not flagged or on_overflow == "ignore":
+                break
+            only_queue = not (int(np.bitwise_or.reduce(st)) & (A.HS_ST_FEL_OVERFLOW | A.HS_ST_SKETCH_OVERFLOW))
+            if on_overflow == "grow" and only_queue and not resume and we < 0 and ring < (1 << 22):
+                ring = max(512, 2 * (ring or 256))
+                continue
+            raise EnsembleStatusError(f"{flagged} of {n_replicas} replicas stopped early (status bits "
+                                      f"{int(np.bitwise_or.reduce(st))}: 1 queue ring full, 2 event list full, 32 sketch "
+                                      f"full); pass a larger queue_ring=", st.copy())
+        if "max_events" in caps and int((st & A.HS_ST_EVENT_LIMIT != 0).sum()) and on_overflow != "ignore":
+            raise EnsembleStatusError("max_events reached before end_time", st.copy())
+        out["status"] = st
+        out["queue_ring"] = ring
+        if totals:
+            out["totals"] = eng.read_totals()
         out["device_ms"] = eng.last_run_ms()
         return out
+
+
+class EnsembleStatusError(RuntimeError):
+    """Replicas of an ensemble stopped early; ``.status`` holds every replica's status word."""
+
+    def __init__(self, msg, status):
+        super().__init__(msg)
+        self.status = status
+
+
+def _same_topology(a, b) -> bool:
+    """Two lowered models that differ at most in the per-cell columns: d0 (rates, mean service times) of any
+    row and i0 (concurrency) of SERVER rows.  Such models run as cells of ONE launch (hs_model_desc.cell_d0/i0)."""
+    ea, eb = a.entities, b.entities
+    if ea.shape != eb.shape or a.n_cells or b.n_cells:
+        return False
+    for f in ea.dtype.names:
+        if f == "d0":
+            continue
+        if f == "i0":
+            srv = ea["kind"] == A.HS_ENT_SERVER
+            if not np.array_equal(ea["i0"][~srv], eb["i0"][~srv]):
+                return False
+            continue
+        if not np.array_equal(ea[f], eb[f]):
+            return False
+    for f in ("backends", "key_table", "profiles", "sketch_tables", "key_cdf"):
+        x, y = np.asarray(getattr(a, f)), np.asarray(getattr(b, f))
+        if x.shape != y.shape or x.tobytes() != y.tobytes():
+            return False
+    return True
+
+
+def _run_many(sims, *, seed: int, seed_stride: int, rid_base: int, rid_stride: int):
+    """Run ``sims`` -- Simulations of one topology (``_same_topology``), same end time and device -- as the
+    replicas of ONE device launch, replica k = sims[k] with Philox key ``seed + k * seed_stride`` and replica word
+    ``rid_base + k * rid_stride``; results are written back onto each Simulation's own objects.  A single
+    Simulation is the n = 1 case (``Simulation.run``).  Ring capacities that turn out too small (recorder
+    streams, device queues, the event limit) are doubled and the launch repeated; ``last_run_info`` records how
+    many launches that took and their wall time."""
+    t0 = _time.monotonic()
+    lead = sims[0]
+    n = len(sims)
+    eng = _engine(lead._device)
+    model = lead.model
+    if n > 1:
+        import copy
+        model = copy.copy(lead.model)
+        model.cell_d0 = np.stack([np.asarray(sm.model.entities["d0"], np.float64) for sm in sims])
+        model.cell_i0 = np.stack([np.asarray(sm.model.entities["i0"], np.int32) for sm in sims])
+    eng.upload(model)
+    caps = {k: max(sm._caps()[k] for sm in sims) for k in ("record_cap", "sample_cap", "service_cap")}
+    stock = getattr(lead, "_rng", "philox") == "stock"
+    eng.set_trace(None, None)
+    if stock:
+        eng.set_trace(*stock_streams(seed, n, caps["sample_cap"] * 2 + 64, seed_stride))
+    m = lead.model
+    # per-server service-time lists / per-collector samples are demultiplexed with the event records
+    n_streams = len(m.ids_of(A.HS_ENT_SINK)) + len(m.ids_of(A.HS_ENT_PROBE))
+    need_events = len(m.ids_of(A.HS_ENT_SERVER)) > 1 or n_streams > 1
+    if m.ids_of(A.HS_ENT_PROBE):        # probe samples share the sample stream
+        dur = lead._end_time.to_seconds()
+        caps["sample_cap"] += max(sum(int(dur * float(sm.model.profiles[int(sm.model.entities["i3"][i]) - 1]["p"][0])) + 8
+                                      for i in sm.model.ids_of(A.HS_ENT_SOURCE) if int(sm.model.entities["i3"][i]) > 0)
+                                  for sm in sims)
+    ring = max(sm._queue_ring_hint() for sm in sims)
+    per_req = max(sm._events_per_request() for sm in sims)
+    max_events = per_req * caps["sample_cap"] + 1_000_000
+    launches, prev_final = 0, None
+    for _ in range(24):
+        kw = dict(caps)
+        if need_events:
+            kw["record_cap"] = kw["service_cap"] * 12
+        eng.run(make_params(seed=seed, seed_stride=seed_stride, rid_base=rid_base, rid_stride=rid_stride,
+                            end_ns=lead._end_time.nanoseconds, n_replicas=n, replicas_per_cell=1, flags=0,
+                            max_events=max_events, queue_ring=ring, **kw))
+        launches += 1
+        out = eng.read_outputs()
+        summ = out["summaries"]
+        status = int(np.bitwise_or.reduce(summ["status"]))
+        if status & A.HS_ST_TRACE_EXHAUSTED:
+            caps = {k: 2 * v for k, v in caps.items()}
+            max_events = per_req * caps["sample_cap"] + 1_000_000
+            eng.set_trace(*stock_streams(seed, n, caps["sample_cap"] * 2 + 64, seed_stride))
+            continue
+        if status & A.HS_ST_QUEUE_OVERFLOW and not (status & A.HS_ST_FEL_OVERFLOW):
+            if ring >= (1 << 24):
+                raise RuntimeError(f"device queue ring overflow at {ring} entries per server; the queue of this model "
+                                   f"grows without bound -- pass Simulation(queue_ring=...) if that is intended")
+            ring *= 4            # the reference's queues are unbounded: grow the device rings and run again
+            continue
+        if status & (A.HS_ST_FEL_OVERFLOW | A.HS_ST_SKETCH_OVERFLOW):
+            raise RuntimeError(f"device structure overflow (status {status})")
+        if status & A.HS_ST_EVENT_LIMIT:
+            final = int(summ["final_time_ns"][summ["status"] & A.HS_ST_EVENT_LIMIT != 0].min())
+            if prev_final is not None and final <= prev_final:
+                raise RuntimeError("event limit reached: the model's clock does not advance (a source faster than "
+                                   "one event per nanosecond never terminates in the reference either)")
+            prev_final = final
+            max_events *= 4      # a valid model denser in events than estimated: raise the safety valve
+            continue
+        if (int(summ["n_sink_samples"].max()) <= kw["sample_cap"] and int(summ["n_service_samples"].max()) <= kw["service_cap"]
+                and (not need_events or int(summ["events_processed"].max()) <= kw["record_cap"])):
+            break
+        caps = dict(record_cap=0, sample_cap=2 * int(summ["n_sink_samples"].max()) + 64,
+                    service_cap=2 * int(summ["n_service_samples"].max()) + 64)
+        max_events = max(max_events, per_req * caps["sample_cap"] + 1_000_000)
+    else:
+        raise RuntimeError("could not size the device buffers for this model")
+    if stock:
+        eng.set_trace(None, None)            # the trace must not leak into a later ensemble on this engine
+    wall = _time.monotonic() - t0
+    res = []
+    for k, sm in enumerate(sims):
+        sm._write_back(out, k)
+        s = summ[k]
+        duration_s = float(int(s["final_time_ns"])) / 1_000_000_000
+        ev = int(s["events_processed"])
+        sm.last_run_info = {"launches": launches, "wall_s": wall, "queue_ring": ring, "batched_with": n,
+                            "device_ms_last_launch": eng.last_run_ms(), "status": int(s["status"])}
+        sm._summary = SimulationSummary(duration_s=duration_s, total_events_processed=ev, events_cancelled=0,
+                                        events_per_second=ev / duration_s if duration_s > 0 else 0.0,
+                                        wall_clock_seconds=wall, entities=sm._entity_summaries())
+        res.append(sm._summary)
+    return res
+
+
+def _group_by_topology(sims):
+    """Indices of ``sims`` grouped so that each group can run as one launch."""
+    groups: list[list[int]] = []
+    for i, sm in enumerate(sims):
+        for g in groups:
+            h = sims[g[0]]
+            if (h._device == sm._device and h._end_time.nanoseconds == sm._end_time.nanoseconds
+                    and getattr(h, "_rng", "philox") == getattr(sm, "_rng", "philox") and _same_topology(h.model, sm.model)):
+                g.append(i)
+                break
+        else:
+            groups.append([i])
+    return groups
 
 
 def run_lowered(ref_sim, model=None, objects=None, *, seed: int | None = None, replica: int = 0, device: int = 0):
@@ -798,6 +960,8 @@ def run_lowered(ref_sim, model=None, objects=None, *, seed: int | None = None, r
     shell._sources, shell._entities = list(ref_sim._sources), list(ref_sim._entities)
     shell._seed = default_seed if seed is None else int(seed)
     shell._replica, shell._device, shell._summary = int(replica), device, None
+    shell._rng, shell._queue_ring, shell.last_run_info = "philox", 0, {}
+    shell._probes = []
     shell._instant_cls = type(ref_sim._start_time)
     shell.model, shell.objects = model, objects
     return shell.run()
@@ -814,45 +978,93 @@ class RunConfig:
 
 @dataclass
 class ParallelResult:
-    """parallel/runner.py:57-70"""
+    """parallel/runner.py:57-70 (+ ``status``: the replica's device status word, 0 = ran to end_time)"""
     name: str
     summary: SimulationSummary
     artifacts: dict[str, Any] = field(default_factory=dict)
+    status: int = 0
+
+
+class _ReplicaResults:
+    """List-like view of an ensemble's ``ParallelResult``s.  Results are materialised on access (the
+    write-back of a replica onto the model's Python objects is O(samples)); ``len``, indexing, slicing and
+    iteration behave like the reference's list."""
+
+    def __init__(self, sim, out, wall: float):
+        self._sim, self.raw, self._wall = sim, out, wall
+
+    def __len__(self):
+        return len(self.raw["summaries"])
+
+    def _one(self, i: int) -> ParallelResult:
+        sim, out = self._sim, self.raw
+        sim._write_back(out, i)
+        s = out["summaries"][i]
+        d = float(int(s["final_time_ns"])) / 1_000_000_000
+        n = int(s["events_processed"])
+        return ParallelResult(name=f"replica_{i}", status=int(s["status"]), summary=SimulationSummary(
+            duration_s=d, total_events_processed=n, events_per_second=n / d if d > 0 else 0.0,
+            wall_clock_seconds=self._wall, entities=sim._entity_summaries()))
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._one(k) for k in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        return self._one(i)
+
+    def __iter__(self):
+        return (self._one(i) for i in range(len(self)))
+
+    @property
+    def total_events_processed(self) -> int:
+        return int(self.raw["summaries"]["events_processed"].sum())
 
 
 class ParallelRunner:
     """parallel/runner.py:82-142 -- replicas run as one device ensemble instead of a process pool.
 
     Replica i uses Philox key ``base_seed + i`` (the reference seeds ``random`` with base_seed + i),
-    so ``run_replicas(build, n, s)[i]`` equals ``Simulation(seed=s + i).run()``."""
+    so ``run_replicas(build, n, s)[i]`` equals ``Simulation(seed=s + i).run()``.  A sweep runs as one
+    launch per topology: configurations whose lowered models differ only in rates, mean service times and
+    server concurrency are the cells of one launch (hs_model_desc.cell_d0 / cell_i0)."""
 
     def __init__(self, max_workers: int | None = None, device: int = 0):
         self._max_workers = max_workers
         self._device = device
 
-    def run_replicas(self, build_fn: Callable, n_replicas: int, base_seed: int = 42) -> list[ParallelResult]:
+    def run_replicas(self, build_fn: Callable, n_replicas: int, base_seed: int = 42, **caps):
+        """Returns a list-like of ParallelResult (materialised on access).  Device queue rings that overflow
+        are grown and the ensemble re-run (``Simulation.run_ensemble``); every result carries ``status``."""
         sim = build_fn()
         t0 = _time.monotonic()
-        out = sim.run_ensemble(n_replicas, seed=base_seed, seed_stride=1, rid_base=sim._replica, rid_stride=0)
-        wall = _time.monotonic() - t0
-        res = []
-        for i in range(n_replicas):
-            sim._write_back(out, i)
-            s = out["summaries"][i]
-            d = float(int(s["final_time_ns"])) / 1_000_000_000
-            n = int(s["events_processed"])
-            res.append(ParallelResult(name=f"replica_{i}", summary=SimulationSummary(
-                duration_s=d, total_events_processed=n, events_per_second=n / d if d > 0 else 0.0,
-                wall_clock_seconds=wall, entities=sim._entity_summaries())))
-        return res
+        out = sim.run_ensemble(n_replicas, seed=base_seed, seed_stride=1, rid_base=sim._replica, rid_stride=0,
+                               queue_ring=sim._queue_ring_hint(), **caps)
+        return _ReplicaResults(sim, out, _time.monotonic() - t0)
 
     def run_sweep(self, configs: list[RunConfig]) -> list[ParallelResult]:
         if not configs:
             return []
-        out = []
+        sims = []
         for cfg in configs:
             sim = cfg.build_fn()
             if cfg.seed is not None:
                 sim._seed = int(cfg.seed)
-            out.append(ParallelResult(name=cfg.name, summary=sim.run()))
-        return out
+            sims.append(sim)
+        res: list = [None] * len(sims)
+        for g in _group_by_topology(sims):
+            seeds = [sims[i]._seed for i in g]
+            rids = [sims[i]._replica for i in g]
+            ds = {b - a for a, b in zip(seeds, seeds[1:])}
+            dr = {b - a for a, b in zip(rids, rids[1:])}
+            if len(g) > 1 and len(ds) <= 1 and len(dr) <= 1 and min(ds | {0}) >= 0 and min(dr | {0}) >= 0:
+                sums = _run_many([sims[i] for i in g], seed=seeds[0], seed_stride=(ds.pop() if ds else 0),
+                                 rid_base=rids[0], rid_stride=(dr.pop() if dr else 0))
+            else:            # seeds that are not an arithmetic progression: one launch each
+                sums = [sims[i].run() for i in g]
+            for i, sm in zip(g, sums):
+                res[i] = ParallelResult(name=configs[i].name, summary=sm, status=sims[i].last_run_info.get("status", 0))
+        return res

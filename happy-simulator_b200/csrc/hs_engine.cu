@@ -453,6 +453,21 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(E->device));
     uint32_t n = m->n_entities;
+    /* Re-uploading the model that is already resident (byte-identical tables) keeps a paused run resumable:
+     * a caller that sends its model with every window, as Simulation.run_ensemble does, still continues
+     * the same run.  Any difference starts over. */
+    auto same_bytes = [](const void *a, size_t na, const void *b, size_t nb) { return na == nb && (na == 0 || memcmp(a, b, na) == 0); };
+    const bool same_model = E->have_model && E->ents.size() == n &&
+        same_bytes(E->ents.data(), E->ents.size() * sizeof(hs_entity_desc), m->entities, (size_t)n * sizeof(hs_entity_desc)) &&
+        same_bytes(E->backends.data(), E->backends.size() * 4, m->backends, (m->backends ? (size_t)m->n_backends : 0) * 4) &&
+        same_bytes(E->key_table.data(), E->key_table.size() * 4, m->key_table, (m->key_table ? (size_t)m->key_population : 0) * 4) &&
+        E->n_cells == m->n_cells &&
+        same_bytes(E->cell_d0.data(), E->cell_d0.size() * 8, m->cell_d0, (size_t)m->n_cells * n * 8) &&
+        same_bytes(E->cell_i0.data(), E->cell_i0.size() * 4, m->cell_i0, (size_t)m->n_cells * n * 4) &&
+        same_bytes(E->profiles.data(), E->profiles.size() * sizeof(hs_profile_desc), m->profiles, (m->profiles ? (size_t)m->n_profiles : 0) * sizeof(hs_profile_desc)) &&
+        same_bytes(E->sketch_tab.data(), E->sketch_tab.size() * 4, m->sketch_tables, (m->sketch_tables ? (size_t)m->n_sketch_table : 0) * 4) &&
+        same_bytes(E->key_cdf.data(), E->key_cdf.size() * 8, m->key_cdf, (m->key_cdf ? (size_t)m->n_key_cdf : 0) * 8);
+    const bool keep_run = same_model && E->have_run;
     E->ents.assign(m->entities, m->entities + n);
     E->backends.assign(m->backends, m->backends + (m->backends ? m->n_backends : 0));
     E->key_table.assign(m->key_table, m->key_table + (m->key_table ? m->key_population : 0));
@@ -498,7 +513,7 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
     CUDA_TRY(cudaStreamSynchronize(E->stream));   /* host vectors may be reused by the caller's next upload */
     E->lane_ok = classify_lane(E);
     E->have_model = true;
-    E->have_run = false;
+    E->have_run = keep_run;
     return HS_OK;
 }
 

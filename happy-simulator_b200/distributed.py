@@ -41,27 +41,50 @@ def totals_from_outputs(model, out) -> A.Totals:
     return t
 
 
-def allreduce_totals(t: A.Totals, device=None, group=None) -> A.Totals:
-    """The single end-of-run collective.  No-op when torch.distributed is not initialised."""
+def _gather_words(words: np.ndarray, device, group):
+    """ONE collective: every rank contributes its packed int64 vector (float64 values travel as their bit
+    patterns) and receives all of them, [world, n_words].  The reduction is then done locally in rank order,
+    which makes the float sums deterministic and identical on every rank (an NCCL SUM all-reduce would also
+    need separate MIN / MAX calls for the extrema)."""
     import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return t
+    world = dist.get_world_size(group)
     dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
-    vi = torch.tensor(list(t.i), dtype=torch.int64, device=dev)
-    vf = torch.tensor(list(t.fsum), dtype=torch.float64, device=dev)
-    vmin = torch.tensor([t.fmin], dtype=torch.float64, device=dev)
-    vmax = torch.tensor([t.fmax], dtype=torch.float64, device=dev)
-    dist.all_reduce(vi, group=group)
-    dist.all_reduce(vf, group=group)
-    dist.all_reduce(vmin, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(vmax, op=dist.ReduceOp.MAX, group=group)
+    mine = torch.from_numpy(np.ascontiguousarray(words, dtype=np.int64)).to(dev)
+    allv = torch.empty(world * mine.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    return allv.cpu().numpy().reshape(world, -1)
+
+
+TOTALS_ALLREDUCE_CALLS = 1
+CELL_ALLREDUCE_CALLS = 1
+
+
+def _dist_active(group) -> bool:
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def allreduce_totals(t: A.Totals, device=None, group=None) -> A.Totals:
+    """The single end-of-run collective (one all-gather of the packed 13-word vector, reduced in rank order).
+    No-op when torch.distributed is not initialised."""
+    if not _dist_active(group):
+        return t
+    ni, nf = A.HS_TOTALS_I64, A.HS_TOTALS_F64_SUM
+    w = np.zeros(ni + nf + 2, np.int64)
+    w[:ni] = list(t.i)
+    w[ni:] = np.array(list(t.fsum) + [t.fmin, t.fmax], np.float64).view(np.int64)
+    g = _gather_words(w, device, group)
+    f = g[:, ni:].copy().view(np.float64)
     r = A.Totals()
-    for k in range(A.HS_TOTALS_I64):
-        r.i[k] = int(vi[k])
-    for k in range(A.HS_TOTALS_F64_SUM):
-        r.fsum[k] = float(vf[k])
-    r.fmin, r.fmax = float(vmin[0]), float(vmax[0])
+    for k in range(ni):
+        r.i[k] = int(g[:, k].sum())
+    for k in range(nf):
+        acc = 0.0
+        for rank in range(g.shape[0]):
+            acc += float(f[rank, k])
+        r.fsum[k] = acc
+    r.fmin, r.fmax = float(f[:, nf].min()), float(f[:, nf + 1].max())
     return r
 
 
@@ -91,29 +114,48 @@ def cell_totals_from_outputs(model, out, n_cells: int, replicas_per_cell: int, i
     return res
 
 
-def allreduce_cell_totals(cells, device=None, group=None):
-    """One collective for a sweep: every cell's totals vector and histogram, stacked (configs[4])."""
-    import torch
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return cells
-    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
-    ks = ["events_processed", "sink_events", "server_completions", "source_ticks", "dropped", "replicas",
-          "replicas_flagged", "sum_final_time_us"]
-    fs = ["sum_latency", "sum_latency_sq", "sum_service"]
-    vi = torch.tensor([[d[k] for k in ks] + [int(x) for x in h] for d, h in cells], dtype=torch.int64, device=dev)
-    vf = torch.tensor([[d[k] for k in fs] for d, _ in cells], dtype=torch.float64, device=dev)
-    vmin = torch.tensor([d["min_latency"] for d, _ in cells], dtype=torch.float64, device=dev)
-    vmax = torch.tensor([d["max_latency"] for d, _ in cells], dtype=torch.float64, device=dev)
-    dist.all_reduce(vi, group=group); dist.all_reduce(vf, group=group)
-    dist.all_reduce(vmin, op=dist.ReduceOp.MIN, group=group); dist.all_reduce(vmax, op=dist.ReduceOp.MAX, group=group)
+_CELL_INTS = ["events_processed", "sink_events", "server_completions", "source_ticks", "dropped", "replicas",
+              "replicas_flagged", "sum_final_time_us"]
+_CELL_FLOATS = ["sum_latency", "sum_latency_sq", "sum_service", "min_latency", "max_latency"]
+
+
+def pack_cell_totals(cells) -> np.ndarray:
+    """[(totals dict, uint64[64] histogram)] per cell -> int64[n_cells, 8 + 64 + 5] (floats as bit patterns)."""
+    ni, nh, nf = len(_CELL_INTS), A.HS_HISTOGRAM_BINS, len(_CELL_FLOATS)
+    w = np.zeros((len(cells), ni + nh + nf), np.int64)
+    for c, (d, h) in enumerate(cells):
+        w[c, :ni] = [d[k] for k in _CELL_INTS]
+        w[c, ni:ni + nh] = np.asarray(h, np.uint64).astype(np.int64)
+        w[c, ni + nh:] = np.array([d[k] for k in _CELL_FLOATS], np.float64).view(np.int64)
+    return w
+
+
+def reduce_cell_words(g: np.ndarray):
+    """[world, n_cells, words] -> the all-reduced cells, reduced in rank order (deterministic float sums)."""
+    ni, nh = len(_CELL_INTS), A.HS_HISTOGRAM_BINS
+    ints = g[:, :, :ni + nh].sum(axis=0)
+    f = np.ascontiguousarray(g[:, :, ni + nh:]).view(np.float64)
     out = []
-    for c in range(len(cells)):
-        d = {k: int(vi[c, j]) for j, k in enumerate(ks)}
-        d.update({k: float(vf[c, j]) for j, k in enumerate(fs)})
-        d["min_latency"], d["max_latency"] = float(vmin[c]), float(vmax[c])
-        out.append((d, vi[c, len(ks):].cpu().numpy().astype(np.uint64)))
+    for c in range(g.shape[1]):
+        d = {k: int(ints[c, j]) for j, k in enumerate(_CELL_INTS)}
+        for j, k in enumerate(_CELL_FLOATS[:3]):
+            acc = 0.0
+            for rank in range(g.shape[0]):
+                acc += float(f[rank, c, j])
+            d[k] = acc
+        d["min_latency"], d["max_latency"] = float(f[:, c, 3].min()), float(f[:, c, 4].max())
+        out.append((d, ints[c, ni:].astype(np.uint64)))
     return out
+
+
+def allreduce_cell_totals(cells, device=None, group=None):
+    """One collective for a sweep (configs[4]): every cell's totals vector and latency histogram, packed into
+    one int64 buffer, all-gathered once and reduced in rank order on every rank."""
+    if not _dist_active(group):
+        return cells
+    w = pack_cell_totals(cells)
+    g = _gather_words(w.ravel(), device, group).reshape(-1, *w.shape)
+    return reduce_cell_words(g)
 
 
 def histogram_percentile(hist, p: float) -> float:

@@ -124,6 +124,14 @@ def bloom_table(size_bits: int, num_hashes: int, seed: int | None, population: i
     return tab
 
 
+def profile_max_rate(pr, tables=None) -> float:
+    """Largest rate a lowered profile row can return (buffer sizing only)."""
+    kind = int(pr["kind"])
+    if kind == A.HS_PROF_LINEAR_RAMP:
+        return float(max(pr["p"][1:3]))
+    return float(max(pr["p"][0:2]))
+
+
 def _arrival(tp):
     """ArrivalTimeProvider -> (HS_ARR_*, rate, profile tuple or None).  The reference's built-in
     profile classes (load/profile.py) are lowered; a user-defined Profile.get_rate is a Python

@@ -589,6 +589,57 @@ int hs_oracle_run_range(const hs_model_desc *m, const hs_run_params *p, const hs
     return HS_OK;
 }
 
+/* CPU anchor for bench.py: n_threads POSIX threads pull replica indices [0, max_replicas) from a shared
+ * counter and run them until budget_s of wall time is spent (a replica in progress is finished), all inside
+ * C -- no Python call, GIL hand-over or ctypes marshalling per replica.  Every thread keeps private totals;
+ * only the summary of the replica it runs is written (into a thread-local hs_replica_summary).
+ * Returns events processed / replicas completed / wall seconds. */
+#include <pthread.h>
+#include <stdatomic.h>
+#include <time.h>
+typedef struct { const hs_model_desc *m; const hs_run_params *p; atomic_uint *next; uint32_t max_replicas;
+                 double deadline; int64_t events; uint32_t replicas; } obench_arg;
+static double obench_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+static void *obench_worker(void *v)
+{
+    obench_arg *a = (obench_arg *)v;
+    hs_run_params q = *a->p;
+    q.n_replicas = 1; q.record_cap = q.sample_cap = q.service_cap = 0;
+    const uint32_t ne = a->m->n_entities;
+    hs_replica_summary summ; hs_entity_stats *st = (hs_entity_stats *)calloc(ne ? ne : 1, sizeof *st);
+    hs_outputs o; memset(&o, 0, sizeof o); o.summaries = &summ; o.entity_stats = st;
+    while (obench_now() < a->deadline) {
+        const uint32_t k = atomic_fetch_add(a->next, 1u);
+        if (k >= a->max_replicas) break;
+        q.replica_index_base = a->p->replica_index_base + k;     /* global replica id k: its own Philox streams */
+        memset(&summ, 0, sizeof summ);
+        run_replica(a->m, &q, 0, &o, NULL);
+        a->events += summ.events_processed; a->replicas += 1;
+    }
+    free(st);
+    return NULL;
+}
+int hs_oracle_bench(const hs_model_desc *m, const hs_run_params *p, int n_threads, double budget_s, uint32_t max_replicas,
+                    int64_t *events, uint32_t *replicas, double *wall_s)
+{
+    if (!m || !p || m->abi_version != HS_ABI_VERSION || n_threads < 1 || n_threads > 4096) return HS_ERR_INVALID;
+    atomic_uint next = 0;
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof *th);
+    obench_arg *args = (obench_arg *)calloc((size_t)n_threads, sizeof *args);
+    const double t0 = obench_now();
+    for (int i = 0; i < n_threads; ++i) {
+        args[i].m = m; args[i].p = p; args[i].next = &next; args[i].max_replicas = max_replicas; args[i].deadline = t0 + budget_s;
+        pthread_create(&th[i], NULL, obench_worker, &args[i]);
+    }
+    int64_t ev = 0; uint32_t rp = 0;
+    for (int i = 0; i < n_threads; ++i) { pthread_join(th[i], NULL); ev += args[i].events; rp += args[i].replicas; }
+    if (events) *events = ev;
+    if (replicas) *replicas = rp;
+    if (wall_s) *wall_s = obench_now() - t0;
+    free(th); free(args);
+    return HS_OK;
+}
+
 /* One replica driven by externally supplied draws: arrival target areas
  * (-log(1-U), poisson_arrival.py:31) and service samples (random.expovariate,
  * exponential.py:43) captured from the reference's stock generators. */

@@ -1,5 +1,6 @@
 """bench.py's output contract: the committed line of the last GPU run carries every key the driver reads, and
-the reference arm (the oracle port on the host cores -- runs without a GPU) prints exactly one JSON line."""
+the reference arm (the unmodified Python reference from baseline/_ref when installed, else the oracle port, on the
+host cores -- runs without a GPU) prints exactly one JSON line."""
 import json
 import os
 import subprocess
@@ -31,5 +32,10 @@ def test_reference_arm_prints_one_json_line_without_a_gpu():
     assert out.returncode == 0 and len(lines) == 1, out.stderr[-500:]
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "happysimulator"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) or d["cpu_baseline"]["core_accounting"]["cgroup_quota_cpus"]
+    assert d["cpu_baseline_port"]["kind"] == "port" and d["cpu_baseline_port"]["per_core"] > 1e6
+    if have_ref:
+        assert 2e4 < d["cpu_baseline"]["per_core"] < 2e6        # CPython: ~1.5e5 events/s per core
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

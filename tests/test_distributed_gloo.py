@@ -109,3 +109,68 @@ def test_two_rank_sketch_merge_equals_single_process():
             assert set(merged) == set(want)
             for i in want:       # HLL max, CMS sum, Bloom OR over both ranks == over the whole ensemble
                 assert np.array_equal(np.asarray(merged[i], dtype=np.uint64), want[i].astype(np.uint64))
+
+
+def _cell_worker(rank, world, port, per_rank, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import happysim_b200 as hs
+    from happysim_b200 import distributed as D, engine, _abi as A
+    import oracle_lib as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = hs.mmc_sweep(cs=(1, 2, 5), rhos=(0.5, 0.9))            # 6 cells
+    rpc = 3
+    out = O.oracle_run(model, O.make_params(seed=5, end_ns=20 * 10**9, n_replicas=per_rank, replica_index_base=rank * per_rank,
+                                            replicas_per_cell=rpc, flags=A.HS_RUN_HISTOGRAM))
+    cells = [(engine.totals_to_dict(t), h) for t, h in D.cell_totals_from_outputs(model, out, model.n_cells, rpc, rank * per_rank)]
+    red = D.allreduce_cell_totals(cells)
+    q.put((rank, [(d, h.tolist()) for d, h in red]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_cell_allreduce_equals_single_process():
+    """configs[4]'s aggregation path: per-cell totals + latency histograms, one collective, equal to the
+    single-process reduction over the whole sweep (integers exactly, float sums in rank order)."""
+    import happysim_b200 as hs
+    from happysim_b200 import distributed as D, engine, _abi as A
+    import oracle_lib as O
+    per_rank, world, port = 18, 2, 33000 + os.getpid() % 2000      # 18 = one pass over 6 cells x 3 replicas per rank
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cell_worker, args=(r, world, port, per_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    model = hs.mmc_sweep(cs=(1, 2, 5), rhos=(0.5, 0.9))
+    whole = O.oracle_run(model, O.make_params(seed=5, end_ns=20 * 10**9, n_replicas=per_rank * world, replicas_per_cell=3,
+                                              flags=A.HS_RUN_HISTOGRAM))
+    want = [(engine.totals_to_dict(t), h) for t, h in D.cell_totals_from_outputs(model, whole, model.n_cells, 3, 0)]
+    assert D.CELL_ALLREDUCE_CALLS == 1
+    for rank, red in got:
+        assert len(red) == len(want) == 6
+        for (d, h), (wd, wh) in zip(red, want):
+            for k, v in wd.items():
+                if isinstance(v, float):
+                    assert v == d[k] or abs(v - d[k]) <= 1e-12 * abs(v), k
+                else:
+                    assert v == d[k], k
+            assert h == wh.tolist()
+            assert d["replicas"] == 6 and d["events_processed"] > 0
+    assert got[0][1] == got[1][1]            # identical on every rank, bit for bit
+
+
+def test_pack_and_reduce_cell_words_roundtrip():
+    from happysim_b200 import distributed as D
+    cells = [({"events_processed": 10 + c, "sink_events": 3, "server_completions": 3, "source_ticks": 4, "dropped": 0,
+               "replicas": 2, "replicas_flagged": 0, "sum_final_time_us": 99, "sum_latency": 0.1 * c, "sum_latency_sq": 0.3,
+               "sum_service": 1.5, "min_latency": 0.01 * (c + 1), "max_latency": 2.0 + c},
+              np.arange(64, dtype=np.uint64) * c) for c in range(4)]
+    w = D.pack_cell_totals(cells)
+    red = D.reduce_cell_words(np.stack([w, w]))
+    for (d, h), (d1, h1) in zip(cells, red):
+        assert d1["events_processed"] == 2 * d["events_processed"] and d1["sum_latency"] == d["sum_latency"] + d["sum_latency"]
+        assert d1["min_latency"] == d["min_latency"] and d1["max_latency"] == d["max_latency"]
+        assert (h1 == 2 * h).all()

@@ -91,10 +91,146 @@ def test_run_ensemble_totals():
     assert 0.40 < mean_lat < 0.60            # M/M/1, rho = 0.8: W = 1 / (mu - lambda) = 0.5 s
 
 
-def test_engine_errors_surface_as_exceptions():
-    sim = quickstart(seed=1, end_s=5, rate=5000)[0]       # rho = 500: the device queue ring overflows
-    with pytest.raises(RuntimeError, match="overflow"):
-        sim.run()
+def test_overloaded_model_runs_like_the_reference_unbounded_queue():
+    """rho = 500: the reference's queue is unbounded, so the run must complete; the device rings are sized
+    from the backlog estimate and grown on overflow.  Checked against the oracle with a huge ring."""
+    import oracle_lib as O
+    from happysim_b200 import engine
+    sim, source, server, sink = quickstart(seed=1, end_s=5, rate=5000)
+    summary = sim.run()
+    want = O.oracle_run(sim.model, O.make_params(seed=1, end_ns=5 * 10**9, n_replicas=1, flags=0, queue_ring=1 << 16))
+    assert summary.total_events_processed == int(want["summaries"]["events_processed"][0])
+    assert int(want["summaries"]["status"][0]) == 0 and sim.last_run_info["status"] == 0
+    assert server.stats_accepted == int(want["entity_stats"][0][1]["c0"]) > 20000
+    assert sink.events_received == int(want["entity_stats"][0][2]["c0"])
+    # a deliberately tiny first ring is grown, not reported as an error
+    sim2, _, server2, _ = quickstart(seed=1, end_s=5, rate=5000)
+    sim2._queue_ring = 64
+    assert sim2.run().total_events_processed == summary.total_events_processed
+    assert sim2.last_run_info["launches"] > 1 and sim2.last_run_info["queue_ring"] >= 32768
+
+
+def test_ensemble_status_is_checked_and_rings_grow():
+    import oracle_lib as O
+    sim = quickstart(seed=3, end_s=40, rate=30)[0]            # rho = 3: backlog ~ 800 requests per replica
+    with pytest.raises(hs.api.EnsembleStatusError) as ei:
+        sim.run_ensemble(64, flags=0, queue_ring=64, on_overflow="raise")
+    assert (ei.value.status & A.HS_ST_QUEUE_OVERFLOW).all()
+    out = sim.run_ensemble(64, flags=0, queue_ring=64)       # default: grow and re-run
+    assert (out["status"] == 0).all() and out["queue_ring"] >= 1024
+    want = O.oracle_run(sim.model, O.make_params(seed=3, end_ns=40 * 10**9, n_replicas=64, flags=0, queue_ring=1 << 14))
+    assert out["summaries"].tobytes() == want["summaries"].tobytes()
+    res = hs.ParallelRunner().run_replicas(lambda: quickstart(end_s=40, rate=30)[0], 16, base_seed=5)
+    assert len(res) == 16 and all(r.status == 0 for r in res)
+    assert res[-1].summary.total_events_processed == quickstart(seed=5 + 15, end_s=40, rate=30)[0].run().total_events_processed
+
+
+def test_spike_profile_defaults_run_without_tuning():
+    """SpikeProfile's own defaults (baseline 10, spike 150 for 15 s) against a 10 req/s server build a queue of
+    ~2100: far beyond the default device ring, fine for the reference."""
+    sink = hs.Sink()
+    server = hs.Server("Server", service_time=hs.ExponentialLatency(0.1), downstream=sink)
+    source = hs.Source.with_profile(hs.SpikeProfile(), target=server)
+    sim = hs.Simulation(end_time=hs.Instant.from_seconds(120), sources=[source], entities=[server, sink], seed=11)
+    summary = sim.run()
+    assert sim.last_run_info["status"] == 0 and summary.total_events_processed > 10000
+    assert server.stats_accepted - server.stats.requests_completed > 1500     # the backlog the spike left behind
+    import oracle_lib as O
+    want = O.oracle_run(sim.model, O.make_params(seed=11, end_ns=120 * 10**9, n_replicas=1, flags=0))
+    assert summary.total_events_processed == int(want["summaries"]["events_processed"][0])
+
+
+def test_tandem_event_budget_scales_with_depth():
+    """12 servers in series cost ~86 events per request: the event-limit safety valve must scale with the
+    topology (or be raised on retry) instead of failing a valid model."""
+    sink = hs.Sink()
+    servers = [hs.Server(f"S{i}", service_time=hs.ExponentialLatency(0.002)) for i in range(12)]
+    for a, b in zip(servers, servers[1:]):
+        a.downstream = b
+    servers[-1].downstream = sink
+    src = hs.Source.poisson(rate=100.0, target=servers[0])
+    sim = hs.Simulation(end_time=hs.Instant.from_seconds(400), sources=[src], entities=[*servers, sink], seed=2)
+    assert sim._events_per_request() >= 86
+    summary = sim.run()
+    assert summary.total_events_processed > 80 * sink.events_received > 3_000_000
+
+
+def test_stock_trace_does_not_leak_into_later_ensembles():
+    sim = quickstart(seed=42, end_s=20)[0]
+    base = sim.run_ensemble(1, flags=0)["summaries"].copy()
+    stock = hs.Simulation(end_time=hs.Instant.from_seconds(20), seed=42, rng="stock",
+                          **dict(zip(("sources", "entities"), _qs_parts())))
+    stock.run()
+    again = sim.run_ensemble(1, flags=0)["summaries"]
+    assert again.tobytes() == base.tobytes()
+    assert sim.run_ensemble(5, flags=0)["summaries"]["events_processed"][0] == base["events_processed"][0]
+
+
+def _qs_parts():
+    sink = hs.Sink()
+    server = hs.Server("Server", service_time=hs.ExponentialLatency(0.1), downstream=sink)
+    return [hs.Source.poisson(rate=8, target=server)], [server, sink]
+
+
+def test_run_sweep_is_one_launch_per_topology_and_equals_single_runs():
+    grid = [(6.0, 0.1, 1), (8.0, 0.1, 1), (30.0, 0.1, 4), (9.0, 0.05, 2)]
+
+    def build(rate, mean, c):
+        def f():
+            sink = hs.Sink()
+            server = hs.Server("Server", concurrency=c, service_time=hs.ExponentialLatency(mean), downstream=sink)
+            src = hs.Source.poisson(rate=rate, target=server)
+            return hs.Simulation(end_time=hs.Instant.from_seconds(50), sources=[src], entities=[server, sink])
+        return f
+    cfgs = [hs.RunConfig(name=f"cfg{i}", build_fn=build(*g), seed=100 + i) for i, g in enumerate(grid)]
+    # plus one configuration of another topology (a load-balanced pair)
+    def build_lb():
+        sink = hs.Sink()
+        sv = [hs.Server(f"S{i}", service_time=hs.ExponentialLatency(0.1), downstream=sink) for i in range(2)]
+        lb = hs.LoadBalancer("LB", backends=sv, strategy=hs.RoundRobin())
+        return hs.Simulation(end_time=hs.Instant.from_seconds(50), sources=[hs.Source.poisson(rate=12.0, target=lb)],
+                             entities=[*sv, sink, lb])
+    cfgs.insert(2, hs.RunConfig(name="lb", build_fn=build_lb, seed=7))
+    res = hs.ParallelRunner().run_sweep(cfgs)
+    assert [r.name for r in res] == ["cfg0", "cfg1", "lb", "cfg2", "cfg3"]
+    for cfg, r in zip(cfgs, res):
+        one = cfg.build_fn()
+        one._seed = cfg.seed
+        s = one.run()
+        assert r.summary.total_events_processed == s.total_events_processed, cfg.name
+        assert r.summary.duration_s == s.duration_s and r.status == 0
+        assert {k: v.events_handled for k, v in r.summary.entities.items()} == {k: v.events_handled for k, v in s.entities.items()}
+
+
+def test_parallel_simulation_batches_partitions_of_one_topology():
+    def part(name, rate):
+        sink = hs.Sink(f"{name}.sink")
+        server = hs.Server(f"{name}.srv", service_time=hs.ExponentialLatency(0.1), downstream=sink)
+        src = hs.Source.poisson(rate=rate, target=server, name=f"{name}.src")
+        return hs.SimulationPartition(name=name, entities=[server, sink], sources=[src]), sink
+    parts = [part("a", 5.0), part("b", 8.0), part("c", 9.0)]
+    ps = hs.ParallelSimulation([p for p, _ in parts], duration=60.0, seed=9)
+    summ = ps.run()
+    assert ps.launch_groups == [["a", "b", "c"]]
+    for k, (p, sink) in enumerate(parts):
+        sink2 = hs.Sink("x")
+        server2 = hs.Server("y", service_time=hs.ExponentialLatency(0.1), downstream=sink2)
+        src2 = hs.Source.poisson(rate=(5.0, 8.0, 9.0)[k], target=server2)
+        one = hs.Simulation(duration=60.0, sources=[src2], entities=[server2, sink2], seed=9, replica=k)
+        s = one.run()
+        assert summ.partitions[p.name].total_events_processed == s.total_events_processed
+        assert sink.latencies_s == sink2.latencies_s
+    assert summ.total_events_processed == sum(s.total_events_processed for s in summ.partitions.values())
+
+
+def test_run_ensemble_windows_equal_the_uncut_run():
+    sim = quickstart(seed=13, end_s=90)[0]
+    whole = sim.run_ensemble(256, flags=0)
+    sim.run_ensemble(256, flags=0, window_end_s=20.0)
+    sim.run_ensemble(256, flags=0, window_end_s=55.5, resume=True, upload=False)
+    cut = sim.run_ensemble(256, flags=0, window_end_s=None, resume=True, upload=False)
+    assert cut["summaries"].tobytes() == whole["summaries"].tobytes()
+    assert cut["entity_stats"].tobytes() == whole["entity_stats"].tobytes()
 
 
 def test_latency_tracker_and_throughput_tracker_collect_like_the_reference_sink():

@@ -12,6 +12,13 @@
  */
 #ifndef HS_SKETCH_H
 #define HS_SKETCH_H
+/* the two entry points of a SKETCH row (measured: as real calls on the device they cost the thread engine's hot
+ * loop registers around the call site -- 264 B of spills -- for no gain, so they stay inline) */
+#if defined(__CUDACC__)
+#define HS_SK_FN __host__ __device__ __forceinline__
+#else
+#define HS_SK_FN static inline
+#endif
 
 #include "hs_sampler.h"
 #include "../../include/hs_b200.h"
@@ -151,7 +158,7 @@ HS_HD int32_t hs_bloom_bit(uint64_t seed, int32_t i, int32_t size_bits, int32_t 
 }
 
 /* sketch.add(key): `state` is this replica's state of the row, `tab` the row's table (stride K) */
-HS_HD void hs_sketch_add(uint8_t *state, const int32_t *tab, int32_t algo, int32_t p_or_depth, int32_t width,
+HS_SK_FN void hs_sketch_add(uint8_t *state, const int32_t *tab, int32_t algo, int32_t p_or_depth, int32_t width,
                          int64_t K, int32_t key)
 {
     /* K > 0: `tab` is the per-key table.  K == 0: the hashes are evaluated here; `tab` then holds the sketch seed
@@ -249,7 +256,7 @@ HS_HD int hs_td_flush(hs_td_hdr *H, hs_td_centroid *C, double *B, double compres
 }
 
 /* TDigest.add(value) (tdigest.py:114-137); `state` is this replica's state of the row */
-HS_HD int hs_tdigest_add(uint8_t *state, double compression, uint32_t buf_size, uint32_t cap, double value)
+HS_SK_FN int hs_tdigest_add(uint8_t *state, double compression, uint32_t buf_size, uint32_t cap, double value)
 {
     hs_td_hdr *H = (hs_td_hdr *)state;
     hs_td_centroid *C = (hs_td_centroid *)(state + 32);

@@ -66,6 +66,7 @@ __host__ __device__ inline hs_thread_layout hs_thread_offsets(uint32_t ne, uint3
 
 #define HS_T_LT(T1, I1, T2, I2) ((T1) < (T2) || ((T1) == (T2) && (I1) < (I2)))
 
+
 template <int FLAGS>
 __global__ void __launch_bounds__(HS_THREAD_BLOCK, HS_T_MINBLOCKS)
 hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blocks,
@@ -200,58 +201,59 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     int64_t top_t = HS_W_EMPTY; uint64_t top_k = ~0ull;  /* the heap's root key, cached */
     if (heap_n) { const hs_tkey t0 = K[0]; top_t = t0.time; top_k = t0.k2; }
     bool paused = false;
-    while (true) {
-        const int64_t now0 = hdr.now;
-        if (!(now0 <= P.end_ns) || (hdr.status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW | HS_ST_TRACE_EXHAUSTED))) break;
-        if (hdr.processed >= P.max_events) { hdr.status |= HS_ST_EVENT_LIMIT; break; }
-        /* ---- pop: the now tier's minimum, unless the heap's root sorts first ---------- */
-        int nb = -1; int64_t nt = HS_W_EMPTY; uint64_t ni = ~0ull;
-        for (int k = 0; k < now_n; ++k) {
-            int64_t t; uint64_t ix; now_key(k, t, ix);
-            if (HS_T_LT(t, ix, nt, ni)) { nt = t; ni = ix; nb = k; }
-        }
-        hs_wnow ev;
-        if (heap_n > 0 && (nb < 0 || HS_T_LT(top_t, top_k >> 16, nt, ni))) {
-            if (windowed && top_t > P.window_end_ns) { paused = true; break; }
-            const uint32_t slot = (uint32_t)(top_k & 0xffffu);
-            const hs_tpay pp = PAY[slot];
-            ev.time = top_t; ev.idx = top_k >> 16; ev.created = pp.created; ev.aux = pp.aux;
-            ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = 0u;
-            heap_n--;
-            FREE[S - heap_n - 1] = (uint16_t)slot;
-            if (heap_n > 0) {                            /* sift-down of the last key from the root */
-                const hs_tkey last = K[heap_n];
-                uint32_t k = 0;
-                while (true) {
-                    const uint32_t c = HS_T_ARITY * k + 1;
-                    if (c >= heap_n) break;
-                    /* all children at once (one aligned line; the key array has ARITY spare entries, so positions
-                     * past the heap's end are readable -- their stale contents are masked out by index) */
-                    hs_tkey ch[HS_T_ARITY];
-#pragma unroll
-                    for (uint32_t j = 0; j < HS_T_ARITY; ++j) ch[j] = K[c + j];
-                    hs_tkey best = ch[0]; uint32_t bc = c;
-#pragma unroll
-                    for (uint32_t j = 1; j < HS_T_ARITY; ++j)
-                        if (c + j < heap_n && HS_T_LT(ch[j].time, ch[j].k2, best.time, best.k2)) { best = ch[j]; bc = c + j; }
-                    if (!HS_T_LT(best.time, best.k2, last.time, last.k2)) break;
-                    K[k] = best;
-                    if (k == 0) { top_t = best.time; top_k = best.k2; }
-                    k = bc;
-                }
-                K[k] = last;
-                if (k == 0) { top_t = last.time; top_k = last.k2; }
+
+    /* ---- phase-locked dispatch ---------------------------------------------------------------------
+     * Every replica processes ITS events in exactly the reference's order; what is arranged here is only
+     * WHEN a lane runs its next handler.  The loop body is a fixed cycle of phases, one per event kind, in
+     * the order the kinds follow each other in the model's same-timestamp chains
+     *     heap pop -> TICK | CONTINUATION -> REQ_LB -> ENQUEUE -> SINK ... -> NOTIFY -> LB_RESPONSE -> POLL -> DELIVER -> WORKER
+     * and a lane executes a phase only if its next event is of that kind.  After a heap pop all lanes of a
+     * warp walk their chains in step, so a phase's code runs once per cycle for all of them (instead of each
+     * lane dragging the warp through its own handler: 2.4 of 8 lanes active in round 1's one-switch loop).
+     * A lane whose next event is a kind whose phase has passed simply waits for the next cycle. */
+    hs_wnow ev; ev.time = 0; ev.idx = 0; ev.created = 0; ev.aux = 0; ev.m0 = 0; ev.key = -1; ev.hook = 0; ev.pad = 0;
+    int ev_kind = -1;                                    /* kind of the event held in `ev`, -1: none */
+    bool alive = true, need_heap = false;
+
+    /* choose the next event: the now tier's minimum unless the heap's root sorts first (then the heap phase pops it) */
+    auto next_event = [&]() {
+        while (true) {
+            ev_kind = -1; need_heap = false;
+            const int64_t now0 = hdr.now;
+            if (!(now0 <= P.end_ns) || (hdr.status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW | HS_ST_TRACE_EXHAUSTED))) { alive = false; return; }
+            if (hdr.processed >= P.max_events) { hdr.status |= HS_ST_EVENT_LIMIT; alive = false; return; }
+            int nb = -1; int64_t nt = HS_W_EMPTY; uint64_t ni = ~0ull;
+            for (int k = 0; k < now_n; ++k) {
+                int64_t t; uint64_t ix; now_key(k, t, ix);
+                if (HS_T_LT(t, ix, nt, ni)) { nt = t; ni = ix; nb = k; }
             }
-            if (heap_n == 0) { top_t = HS_W_EMPTY; top_k = ~0ull; }
-        } else if (nb >= 0) {
-            if (windowed && nt > P.window_end_ns) { paused = true; break; }
+            if (heap_n > 0 && (nb < 0 || HS_T_LT(top_t, top_k >> 16, nt, ni))) {
+                if (windowed && top_t > P.window_end_ns) { paused = true; alive = false; return; }
+                need_heap = true;
+                return;
+            }
+            if (nb < 0) { alive = false; return; }           /* heap exhausted */
+            if (windowed && nt > P.window_end_ns) { paused = true; alive = false; return; }
             ev = now_load(nb);
             now_n--;
             if (nb != now_n) now_store(nb, now_load(now_n));
-        } else break;                                    /* heap exhausted */
-        hdr.fel_n--;
-        if (ev.time < now0) continue;                    /* "time travel": skipped (simulation.py:479-489) */
+            hdr.fel_n--;
+            if (ev.time < now0) continue;                    /* "time travel": skipped (simulation.py:479-489) */
+            int k = (int)(ev.m0 & 0xffu);
+            if (k == (int)HS_EV_REQ_ANY) {
+                const int ek = ENTS[ev.m0 >> 8].kind;
+                k = ek == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE : ek == HS_ENT_SINK ? HS_EV_REQ_SINK :
+                    ek == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : ek == HS_ENT_PROBE ? HS_EV_PROBE :
+                    ek == HS_ENT_SKETCH ? HS_EV_REQ_SKETCH : HS_EV_REQ_LB;
+            }
+            ev_kind = k;
+            return;
+        }
+    };
 
+    /* one event of compile-time kind KC::value: the handler of hs_handlers.inc, then the insertion of the (at most
+     * one) future event it created */
+    auto process = [&](const int kind) {
         const int64_t now = ev.time;
         const uint64_t bi = ev.idx;
         const uint32_t ent = ev.m0 >> 8;
@@ -259,7 +261,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         const uint64_t e_aux = ev.aux;
         const int32_t e_key = ev.key;
         const uint32_t e_hook = ev.hook;
-        /* model row and entity state, loaded while the warp is converged; handlers work on the copy */
+        /* model row and entity state; handlers work on the copy */
         union { hs_entity_desc d; uint4 q[3]; } du;
         { const uint4 *g = (const uint4 *)&ENTS[ent]; du.q[0] = g[0]; du.q[1] = g[1]; du.q[2] = g[2]; }
         union { hs_went w; uint4 q[6]; } xu;
@@ -267,11 +269,6 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
 #pragma unroll
           for (int i = 0; i < 6; ++i) xu.q[i] = g[i]; }
         hs_went *X = &xu.w;
-        int kind = (int)(ev.m0 & 0xffu);
-        if (kind == (int)HS_EV_REQ_ANY)
-            kind = du.d.kind == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE : du.d.kind == HS_ENT_SINK ? HS_EV_REQ_SINK :
-                   du.d.kind == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : du.d.kind == HS_ENT_PROBE ? HS_EV_PROBE :
-                   du.d.kind == HS_ENT_SKETCH ? HS_EV_REQ_SKETCH : HS_EV_REQ_LB;
         const uint32_t srv_idx = (uint32_t)__double_as_longlong(du.d.d1);   /* patched in by the host, see hs_model_upload */
         hdr.now = now;
         if (FLAGS & HS_WF_HASH) hdr.hash = hs_hash_step(hdr.hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
@@ -331,6 +328,65 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 if (k == 0) { top_t = fkey.time; top_k = fkey.k2; }
                 hdr.fel_n++;
             }
+        }
+    };
+    const bool single = (P.lane_stride == 32);          /* one replica per warp: nothing to align, every pass runs the next event */
+    next_event();
+    while (alive) {
+        /* ---- heap phase: the root is the next event (SourceEvent / ProcessContinuation) -------------- */
+        if (need_heap) {
+            const int64_t now0 = hdr.now;
+            const uint32_t slot = (uint32_t)(top_k & 0xffffu);
+            const hs_tpay pp = PAY[slot];
+            ev.time = top_t; ev.idx = top_k >> 16; ev.created = pp.created; ev.aux = pp.aux;
+            ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = 0u;
+            heap_n--;
+            FREE[S - heap_n - 1] = (uint16_t)slot;
+            if (heap_n > 0) {                            /* sift-down of the last key from the root */
+                const hs_tkey last = K[heap_n];
+                uint32_t k = 0;
+                while (true) {
+                    const uint32_t c = HS_T_ARITY * k + 1;
+                    if (c >= heap_n) break;
+                    /* all children at once (one aligned line; the key array has ARITY spare entries, so positions
+                     * past the heap's end are readable -- their stale contents are masked out by index) */
+                    hs_tkey ch[HS_T_ARITY];
+#pragma unroll
+                    for (uint32_t j = 0; j < HS_T_ARITY; ++j) ch[j] = K[c + j];
+                    hs_tkey best = ch[0]; uint32_t bc = c;
+#pragma unroll
+                    for (uint32_t j = 1; j < HS_T_ARITY; ++j)
+                        if (c + j < heap_n && HS_T_LT(ch[j].time, ch[j].k2, best.time, best.k2)) { best = ch[j]; bc = c + j; }
+                    if (!HS_T_LT(best.time, best.k2, last.time, last.k2)) break;
+                    K[k] = best;
+                    if (k == 0) { top_t = best.time; top_k = best.k2; }
+                    k = bc;
+                }
+                K[k] = last;
+                if (k == 0) { top_t = last.time; top_k = last.k2; }
+            }
+            if (heap_n == 0) { top_t = HS_W_EMPTY; top_k = ~0ull; }
+            hdr.fel_n--;
+            need_heap = false;
+            if (ev.time < now0) next_event();            /* "time travel": skipped (simulation.py:479-489) */
+            else { int k = (int)(ev.m0 & 0xffu);
+                   if (k == (int)HS_EV_REQ_ANY) {
+                       const int ek = ENTS[ev.m0 >> 8].kind;
+                       k = ek == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE : ek == HS_ENT_SINK ? HS_EV_REQ_SINK :
+                           ek == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : ek == HS_ENT_PROBE ? HS_EV_PROBE :
+                           ek == HS_ENT_SKETCH ? HS_EV_REQ_SKETCH : HS_EV_REQ_LB;
+                   }
+                   ev_kind = k; }
+        }
+        /* ---- handler phases, in chain order: ONE copy of the handlers (a copy per kind was three times slower when a
+         * warp holds a single replica: 170 KB of code); `kind` is warp-uniform in every pass, so the switch inside
+         * process() is a uniform branch and the lanes that take it run the same handler.
+         * One nibble per pass, low first: TICK 0, CONTINUATION 7, PROBE 11, REQ_LB 1, ENQUEUE 2, SINK 8, COUNTER 10,
+         * SKETCH 12, NOTIFY 3, LB_RESPONSE 9, POLL 4, DELIVER 5, WORKER 6 (the HS_EV_* values of include/hs_b200.h) */
+#pragma unroll 1
+        for (int ph = 0; ph < 13; ++ph) {
+            const int kind = single ? ev_kind : (int)((0x65493ca821b70ull >> (4 * ph)) & 15ull);
+            if (alive && ev_kind >= 0 && ev_kind == kind) { process(kind); next_event(); }
         }
     }
 

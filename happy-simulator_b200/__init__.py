@@ -21,9 +21,10 @@ from .api import (  # noqa: F401,E402
     Instant, Duration, Entity, Source, SimpleEventProvider, ConstantRateProfile, ConstantArrivalTimeProvider,
     PoissonArrivalTimeProvider, ConstantLatency, ExponentialLatency, FIFOQueue, LIFOQueue, FixedConcurrency,
     Server, ServerStats, Sink, Counter, LoadBalancer, LoadBalancerStats, RoundRobin, ConsistentHash,
-    UniformKeyContext, ZipfKeyContext, Simulation, SimulationSummary, EntitySummary, QueueStats, ParallelRunner, RunConfig,
+    UniformKeyContext, ZipfKeyContext, StepProfile, Simulation, SimulationSummary, EntitySummary, QueueStats, ParallelRunner, RunConfig,
     ParallelResult, seed, run_lowered, LinearRampProfile, SpikeProfile,
 )
 from . import api  # noqa: F401,E402
 from .instrumentation import Data, BucketedData, LatencyTracker, ThroughputTracker, Probe  # noqa: F401,E402
 from .parallel import SimulationPartition, PartitionLink, ParallelSimulation, ParallelSimulationSummary  # noqa: F401,E402
+from .hook import install, uninstall, stats as install_stats  # noqa: F401,E402

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-HS_ABI_VERSION = 2
+HS_ABI_VERSION = 3
 
 HS_OK, HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_NO_DEVICE, HS_ERR_STATE, HS_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
 
@@ -15,7 +15,7 @@ HS_ARR_CONSTANT, HS_ARR_POISSON = 0, 1
 HS_SVC_CONSTANT, HS_SVC_EXPONENTIAL = 0, 1
 HS_Q_FIFO, HS_Q_LIFO = 0, 1
 HS_LB_ROUND_ROBIN, HS_LB_KEY_TABLE = 0, 1
-HS_PROF_CONSTANT, HS_PROF_LINEAR_RAMP, HS_PROF_SPIKE = 0, 1, 2
+HS_PROF_CONSTANT, HS_PROF_LINEAR_RAMP, HS_PROF_SPIKE, HS_PROF_STEP = 0, 1, 2, 3
 
 (HS_EV_SOURCE_TICK, HS_EV_REQ_LB, HS_EV_REQ_ENQUEUE, HS_EV_NOTIFY, HS_EV_POLL, HS_EV_DELIVER,
  HS_EV_REQ_WORKER, HS_EV_CONTINUATION, HS_EV_REQ_SINK, HS_EV_LB_RESPONSE, HS_EV_REQ_COUNTER,
@@ -47,7 +47,8 @@ class ModelDesc(C.Structure):
                 ("cell_d0", C.POINTER(C.c_double)), ("cell_i0", C.POINTER(C.c_int32)),
                 ("n_profiles", C.c_uint32), ("reserved2", C.c_uint32), ("profiles", C.c_void_p),
                 ("n_sketch_table", C.c_uint32), ("n_key_cdf", C.c_uint32),
-                ("sketch_tables", C.POINTER(C.c_int32)), ("key_cdf", C.POINTER(C.c_double))]
+                ("sketch_tables", C.POINTER(C.c_int32)), ("key_cdf", C.POINTER(C.c_double)),
+                ("profile_table", C.POINTER(C.c_double)), ("n_profile_table", C.c_uint64)]
 
 
 class RunParams(C.Structure):

@@ -168,6 +168,31 @@ class SpikeProfile:
         return self.baseline_rate
 
 
+@dataclass(frozen=True)
+class StepProfile:
+    """A piecewise-constant rate profile (not in the reference's load/profile.py; the reference's examples define
+    such profiles themselves, e.g. examples/queuing/m_m_1_queue.py:104-169): ``rates[k]`` applies from
+    ``breakpoints[k - 1]`` (inclusive) to ``breakpoints[k]`` (exclusive).  Lowered as HS_PROF_STEP."""
+    breakpoints: tuple = ()
+    rates: tuple = (1.0,)
+
+    def __post_init__(self):
+        if len(self.rates) != len(self.breakpoints) + 1:
+            raise ValueError("StepProfile: n breakpoints need n + 1 rates")
+        if any(b <= a for a, b in zip(self.breakpoints, self.breakpoints[1:])):
+            raise ValueError("StepProfile: breakpoints must ascend")
+
+    def get_rate(self, time) -> float:
+        import bisect
+        return float(self.rates[bisect.bisect_right(self.breakpoints, time.to_seconds())])
+
+    @classmethod
+    def from_profile(cls, profile, end_s: float, scan_step_s: float | None = None) -> "StepProfile":
+        """Tabulate any step-function ``Profile`` (exactly, see lowering.step_table_from_profile)."""
+        breaks, rates = lowering.step_table_from_profile(profile, scan_end_s=float(end_s), scan_step_s=scan_step_s)
+        return cls(tuple(breaks), tuple(rates))
+
+
 class _ArrivalTimeProvider:
     """load/arrival_time_provider.py:28-47 (constant-rate profiles only on the device)."""
 
@@ -588,7 +613,8 @@ class Simulation:
         self.last_run_info: dict = {}
         self._summary: SimulationSummary | None = None
         self._instant_cls = Instant
-        self.model, self.objects = lowering.lower(self._sources, self._entities, probes=self._probes)
+        self.model, self.objects = lowering.lower(self._sources, self._entities, probes=self._probes,
+                                                  horizon_s=self._end_time.to_seconds())
 
     @property
     def summary(self):
@@ -603,7 +629,7 @@ class Simulation:
             if pi == 0:
                 rate += float(ents["d0"][i])
             else:        # non-constant profile: bound by its largest rate
-                rate += lowering.profile_max_rate(self.model.profiles[pi - 1], getattr(self.model, "profile_tables", None))
+                rate += lowering.profile_max_rate(self.model.profiles[pi - 1], self.model.profile_table)
         return rate
 
     def _caps(self, n_hint: int | None = None):
@@ -832,14 +858,14 @@ def _same_topology(a, b) -> bool:
             continue
         if not np.array_equal(ea[f], eb[f]):
             return False
-    for f in ("backends", "key_table", "profiles", "sketch_tables", "key_cdf"):
+    for f in ("backends", "key_table", "profiles", "profile_table", "sketch_tables", "key_cdf"):
         x, y = np.asarray(getattr(a, f)), np.asarray(getattr(b, f))
         if x.shape != y.shape or x.tobytes() != y.tobytes():
             return False
     return True
 
 
-def _run_many(sims, *, seed: int, seed_stride: int, rid_base: int, rid_stride: int):
+def _run_many(sims, *, seed: int, seed_stride: int, rid_base: int, rid_stride: int, trace_fn=None):
     """Run ``sims`` -- Simulations of one topology (``_same_topology``), same end time and device -- as the
     replicas of ONE device launch, replica k = sims[k] with Philox key ``seed + k * seed_stride`` and replica word
     ``rid_base + k * rid_stride``; results are written back onto each Simulation's own objects.  A single
@@ -858,10 +884,12 @@ def _run_many(sims, *, seed: int, seed_stride: int, rid_base: int, rid_stride: i
         model.cell_i0 = np.stack([np.asarray(sm.model.entities["i0"], np.int32) for sm in sims])
     eng.upload(model)
     caps = {k: max(sm._caps()[k] for sm in sims) for k in ("record_cap", "sample_cap", "service_cap")}
-    stock = getattr(lead, "_rng", "philox") == "stock"
+    stock = getattr(lead, "_rng", "philox") == "stock" or trace_fn is not None
+    if trace_fn is None:           # the reference's two MT19937 streams for Simulation(seed=, rng="stock")
+        trace_fn = lambda n_draws: stock_streams(seed, n, n_draws, seed_stride)      # noqa: E731
     eng.set_trace(None, None)
     if stock:
-        eng.set_trace(*stock_streams(seed, n, caps["sample_cap"] * 2 + 64, seed_stride))
+        eng.set_trace(*trace_fn(caps["sample_cap"] * 2 + 64))
     m = lead.model
     # per-server service-time lists / per-collector samples are demultiplexed with the event records
     n_streams = len(m.ids_of(A.HS_ENT_SINK)) + len(m.ids_of(A.HS_ENT_PROBE))
@@ -889,7 +917,7 @@ def _run_many(sims, *, seed: int, seed_stride: int, rid_base: int, rid_stride: i
         if status & A.HS_ST_TRACE_EXHAUSTED:
             caps = {k: 2 * v for k, v in caps.items()}
             max_events = per_req * caps["sample_cap"] + 1_000_000
-            eng.set_trace(*stock_streams(seed, n, caps["sample_cap"] * 2 + 64, seed_stride))
+            eng.set_trace(*trace_fn(caps["sample_cap"] * 2 + 64))
             continue
         if status & A.HS_ST_QUEUE_OVERFLOW and not (status & A.HS_ST_FEL_OVERFLOW):
             if ring >= (1 << 24):
@@ -948,12 +976,14 @@ def _group_by_topology(sims):
     return groups
 
 
-def run_lowered(ref_sim, model=None, objects=None, *, seed: int | None = None, replica: int = 0, device: int = 0):
+def run_lowered(ref_sim, model=None, objects=None, *, seed: int | None = None, replica: int = 0, device: int = 0,
+                trace_fn=None):
     """Run a REFERENCE ``happysimulator.Simulation`` object on the device and write the results back
     onto its own entity objects (the hook shown in INTEGRATION.md section 3).  ``ref_sim`` only needs the
     reference's attributes ``_sources``, ``_entities``, ``_start_time``, ``_end_time``."""
     if model is None:
-        model, objects = lowering.lower(ref_sim._sources, ref_sim._entities)
+        model, objects = lowering.lower(ref_sim._sources, ref_sim._entities, probes=getattr(ref_sim, "_probes", None) or None,
+                                        horizon_s=float(int(ref_sim._end_time.nanoseconds)) / 1e9)
     shell = Simulation.__new__(Simulation)
     shell._start_time = Instant.Epoch
     shell._end_time = Instant(int(ref_sim._end_time.nanoseconds))
@@ -964,6 +994,8 @@ def run_lowered(ref_sim, model=None, objects=None, *, seed: int | None = None, r
     shell._probes = []
     shell._instant_cls = type(ref_sim._start_time)
     shell.model, shell.objects = model, objects
+    if trace_fn is not None:
+        return _run_many([shell], seed=shell._seed, seed_stride=0, rid_base=shell._replica, rid_stride=0, trace_fn=trace_fn)[0]
     return shell.run()
 
 

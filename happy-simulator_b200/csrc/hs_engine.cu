@@ -72,9 +72,11 @@ struct hs_engine {
     std::vector<hs_entity_desc> ents;
     std::vector<int32_t> backends, key_table;
     std::vector<double> cell_d0; std::vector<int32_t> cell_i0;
-    std::vector<hs_profile_desc> profiles;
+    std::vector<hs_profile_desc> profiles;      /* STEP rows: p[2] = device address of the row's table */
+    std::vector<hs_profile_desc> profiles_raw;  /* as uploaded, p[2] of STEP rows zeroed (for the same-model test) */
+    std::vector<double> profile_table;
     uint32_t n_cells = 0;
-    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0, d_profiles, d_sketch_tab, d_key_cdf;
+    dev_buf d_ents, d_backends, d_key_table, d_cell_d0, d_cell_i0, d_profiles, d_profile_table, d_sketch_tab, d_key_cdf;
     std::vector<int32_t> sketch_tab;
     std::vector<double> key_cdf;
     std::vector<uint64_t> sk_off, sk_moff;      /* hs_sketch_layout of the model */
@@ -111,15 +113,25 @@ static int validate_model(const hs_model_desc *m)
             if (m->entities[e.target].kind == HS_ENT_SOURCE) return fail(HS_ERR_INVALID, "entity %u: source targets a source", i);
             if (e.i3 < 0 || (uint32_t)e.i3 > m->n_profiles) return fail(HS_ERR_INVALID, "entity %u: profile index %d out of range", i, e.i3);
             if (e.i3 > 0 && !m->profiles) return fail(HS_ERR_INVALID, "profiles is NULL");
-            if (e.i3 > 0 && (m->profiles[e.i3 - 1].kind < HS_PROF_CONSTANT || m->profiles[e.i3 - 1].kind > HS_PROF_SPIKE))
+            if (e.i3 > 0 && (m->profiles[e.i3 - 1].kind < HS_PROF_CONSTANT || m->profiles[e.i3 - 1].kind > HS_PROF_STEP))
                 return fail(HS_ERR_INVALID, "entity %u: unknown profile kind", i);
             if (e.i3 > 0 && m->profiles[e.i3 - 1].kind == HS_PROF_LINEAR_RAMP && !(m->profiles[e.i3 - 1].p[0] > 0.0))
                 return fail(HS_ERR_INVALID, "entity %u: LinearRampProfile duration must be > 0", i);
             if (e.i3 > 0) {     /* a rate that reaches zero sends the reference's bracket search to times beyond int64 ns */
                 const hs_profile_desc &pr = m->profiles[e.i3 - 1];
-                const bool ok = pr.kind == HS_PROF_LINEAR_RAMP ? (pr.p[1] > 0.0 && pr.p[2] > 0.0)
-                              : pr.kind == HS_PROF_SPIKE ? (pr.p[0] > 0.0 && pr.p[1] > 0.0 && pr.p[2] >= 0.0 && pr.p[3] >= 0.0)
-                              : (pr.p[0] > 0.0);
+                bool ok = pr.kind == HS_PROF_LINEAR_RAMP ? (pr.p[1] > 0.0 && pr.p[2] > 0.0)
+                        : pr.kind == HS_PROF_SPIKE ? (pr.p[0] > 0.0 && pr.p[1] > 0.0 && pr.p[2] >= 0.0 && pr.p[3] >= 0.0)
+                        : pr.kind == HS_PROF_STEP ? true : (pr.p[0] > 0.0);
+                if (pr.kind == HS_PROF_STEP) {
+                    const double off = pr.p[0], nb = pr.p[1];
+                    if (!(off >= 0.0 && nb >= 0.0 && nb <= 65536.0) || !m->profile_table ||
+                        (uint64_t)off + 2 * (uint64_t)nb + 1 > m->n_profile_table)
+                        return fail(HS_ERR_INVALID, "entity %u: step profile table out of range", i);
+                    const double *tab = m->profile_table + (uint64_t)off;
+                    const uint64_t nbi = (uint64_t)nb;
+                    for (uint64_t k = 0; k + 1 < nbi; ++k) if (!(tab[k] < tab[k + 1])) return fail(HS_ERR_INVALID, "entity %u: step profile breakpoints must ascend", i);
+                    for (uint64_t k = 0; k <= nbi; ++k) ok = ok && tab[nbi + k] > 0.0;
+                }
                 if (!ok) return fail(HS_ERR_INVALID, "entity %u: profile rates must stay > 0", i);
             }
             if (e.i3 == 0 && !(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: source rate must be > 0 (arrival_time_provider.py:75)", i);
@@ -436,7 +448,7 @@ int hs_engine_destroy(hs_engine *E)
     cudaStreamSynchronize(E->stream);
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
                        &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
-                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_hist, &E->d_cell_totals, &E->d_conts,
+                       &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_profile_table, &E->d_hist, &E->d_cell_totals, &E->d_conts,
                        &E->d_sketch_tab, &E->d_sketch, &E->d_sketch_merged, &E->d_key_cdf};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
@@ -457,6 +469,8 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
      * a caller that sends its model with every window, as Simulation.run_ensemble does, still continues
      * the same run.  Any difference starts over. */
     auto same_bytes = [](const void *a, size_t na, const void *b, size_t nb) { return na == nb && (na == 0 || memcmp(a, b, na) == 0); };
+    std::vector<hs_profile_desc> new_raw(m->profiles, m->profiles + (m->profiles ? m->n_profiles : 0));
+    for (auto &pr : new_raw) if (pr.kind == HS_PROF_STEP) pr.p[2] = 0.0;   /* a caller-side address, not part of the model */
     const bool same_model = E->have_model && E->ents.size() == n &&
         same_bytes(E->ents.data(), E->ents.size() * sizeof(hs_entity_desc), m->entities, (size_t)n * sizeof(hs_entity_desc)) &&
         same_bytes(E->backends.data(), E->backends.size() * 4, m->backends, (m->backends ? (size_t)m->n_backends : 0) * 4) &&
@@ -464,7 +478,8 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
         E->n_cells == m->n_cells &&
         same_bytes(E->cell_d0.data(), E->cell_d0.size() * 8, m->cell_d0, (size_t)m->n_cells * n * 8) &&
         same_bytes(E->cell_i0.data(), E->cell_i0.size() * 4, m->cell_i0, (size_t)m->n_cells * n * 4) &&
-        same_bytes(E->profiles.data(), E->profiles.size() * sizeof(hs_profile_desc), m->profiles, (m->profiles ? (size_t)m->n_profiles : 0) * sizeof(hs_profile_desc)) &&
+        same_bytes(E->profiles_raw.data(), E->profiles_raw.size() * sizeof(hs_profile_desc), new_raw.data(), new_raw.size() * sizeof(hs_profile_desc)) &&
+        same_bytes(E->profile_table.data(), E->profile_table.size() * 8, m->profile_table, (m->profile_table ? (size_t)m->n_profile_table : 0) * 8) &&
         same_bytes(E->sketch_tab.data(), E->sketch_tab.size() * 4, m->sketch_tables, (m->sketch_tables ? (size_t)m->n_sketch_table : 0) * 4) &&
         same_bytes(E->key_cdf.data(), E->key_cdf.size() * 8, m->key_cdf, (m->key_cdf ? (size_t)m->n_key_cdf : 0) * 8);
     const bool keep_run = same_model && E->have_run;
@@ -472,7 +487,9 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
     E->backends.assign(m->backends, m->backends + (m->backends ? m->n_backends : 0));
     E->key_table.assign(m->key_table, m->key_table + (m->key_table ? m->key_population : 0));
     E->n_cells = m->n_cells;
-    E->profiles.assign(m->profiles, m->profiles + (m->profiles ? m->n_profiles : 0));
+    E->profiles_raw = new_raw;
+    E->profiles = new_raw;
+    E->profile_table.assign(m->profile_table, m->profile_table + (m->profile_table ? m->n_profile_table : 0));
     E->cell_d0.clear(); E->cell_i0.clear();
     if (m->n_cells) {
         E->cell_d0.assign(m->cell_d0, m->cell_d0 + (size_t)m->n_cells * n);
@@ -509,6 +526,12 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
     if ((rc = up(E->d_key_table, E->key_table.data(), E->key_table.size() * 4))) return rc;
     if ((rc = up(E->d_cell_d0, E->cell_d0.data(), E->cell_d0.size() * 8))) return rc;
     if ((rc = up(E->d_cell_i0, E->cell_i0.data(), E->cell_i0.size() * 4))) return rc;
+    if ((rc = up(E->d_profile_table, E->profile_table.data(), E->profile_table.size() * 8))) return rc;
+    for (auto &pr : E->profiles)                       /* STEP rows carry the device address of their table */
+        if (pr.kind == HS_PROF_STEP) {
+            const uint64_t a = (uint64_t)(uintptr_t)((const double *)E->d_profile_table.p + (size_t)pr.p[0]);
+            memcpy(&pr.p[2], &a, 8);
+        }
     if ((rc = up(E->d_profiles, E->profiles.data(), E->profiles.size() * sizeof(hs_profile_desc)))) return rc;
     CUDA_TRY(cudaStreamSynchronize(E->stream));   /* host vectors may be reused by the caller's next upload */
     E->lane_ok = classify_lane(E);

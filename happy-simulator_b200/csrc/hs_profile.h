@@ -41,6 +41,13 @@ HS_HD double hs_profile_rate(const hs_profile_desc *P, double t_seconds)
         const double fraction = HS_DIV(t, P->p[0]);
         return HS_ADD(P->p[1], HS_MUL(fraction, HS_SUB(P->p[2], P->p[1])));
     }
+    if (P->kind == HS_PROF_STEP) {                  /* a user-defined step function, e.g. examples/queuing/m_m_1_queue.py:137-169 */
+        const double *tab = (const double *)(uintptr_t)HS_D2BITS(P->p[2]);
+        const int n = (int)P->p[1];
+        int lo = 0, hi = n;                         /* number of breakpoints <= t (they ascend) */
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (t < tab[mid]) hi = mid; else lo = mid + 1; }
+        return tab[n + lo];
+    }
     if (P->kind == HS_PROF_SPIKE) {                 /* profile.py:98-110 */
         if (t < P->p[2]) return P->p[0];
         if (t < HS_ADD(P->p[2], P->p[3])) return P->p[1];

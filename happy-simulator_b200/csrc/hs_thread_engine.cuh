@@ -251,8 +251,234 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         }
     };
 
-    /* one event of compile-time kind KC::value: the handler of hs_handlers.inc, then the insertion of the (at most
-     * one) future event it created */
+    /* insertion of a future event (SourceEvent or ProcessContinuation) into the 4-ary key heap */
+    auto heap_insert = [&](hs_tkey fkey, const hs_tpay &fpay) {
+        if (heap_n >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; return; }
+        const uint32_t slot = FREE[S - heap_n - 1];
+        PAY[slot] = fpay;
+        fkey.k2 |= slot;
+        uint32_t k = heap_n++;
+        while (k > 0) {
+            const uint32_t p = (k - 1) >> HS_T_SHIFT;
+            hs_tkey q;
+            if (p == 0) { q.time = top_t; q.k2 = top_k; } else q = K[p];
+            if (!HS_T_LT(fkey.time, fkey.k2, q.time, q.k2)) break;
+            K[k] = q; k = p;
+        }
+        K[k] = fkey;
+        if (k == 0) { top_t = fkey.time; top_k = fkey.k2; }
+        hdr.fel_n++;
+    };
+
+    /* ---- fused same-timestamp chains -----------------------------------------------------------------------------
+     * The event just popped from the heap (`ev`, a SourceEvent or a ProcessContinuation) starts a chain of events at
+     * the same nanosecond: TICK -> [REQ_LB ->] ENQUEUE -> [NOTIFY ->] [LB_RESPONSE ->] [POLL -> DELIVER -> WORKER]
+     * or CONTINUATION -> [SINK|COUNTER ->] [POLL -> [DELIVER -> WORKER]].  When nothing else is pending at that
+     * nanosecond (empty now tier, the heap's new root strictly later, the events the chain itself schedules strictly
+     * later) every event a handler creates is the next pop -- ties among them are resolved by the creation order,
+     * which the code below follows index for index, exactly like the lane engine's fused chains -- so the whole
+     * chain runs as straight-line code on the entities' state: one load and one store per entity instead of one
+     * per event, no now-tier traffic, no per-event dispatch.  Every condition is tested BEFORE anything is
+     * changed (draws are pure functions of their index); a chain that does not qualify -- a tie, another topology
+     * (tandem, sketch or probe targets), a stop_after source, a full ring, traces, the run / window end, the event
+     * limit -- goes through the generic one-event path below, which is the oracle's.  Returns true if it ran. */
+    auto emit = [&](const int64_t now, const uint64_t idx, const int kind, const uint32_t ent) {
+        if (FLAGS & HS_WF_HASH) hdr.hash = hs_hash_step(hdr.hash, now, hs_record_word1(idx, (uint32_t)kind, ent));
+        if ((FLAGS & HS_WF_REC) && rec) {
+            hs_event_record rc; rc.time_ns = now; rc.sort_index = (uint32_t)idx; rc.kind = (uint8_t)kind;
+            rc.pad = 0; rc.entity = (uint16_t)ent;
+            rec[hdr.rec_pos] = rc; hdr.rec_pos = (hdr.rec_pos + 1 == P.record_cap) ? 0u : hdr.rec_pos + 1;
+        }
+        hdr.processed++;
+    };
+    const bool fuse_on = !P.trace_arr && !P.trace_svc;
+    auto fused_chain = [&]() -> bool {
+        const int64_t now = ev.time;
+        const int k0 = (int)(ev.m0 & 0xffu);
+        if (!fuse_on || now_n != 0 || !(top_t > now) || now > P.end_ns || hdr.processed + 10 > P.max_events) return false;
+        const uint32_t ent = ev.m0 >> 8;
+        if (k0 == HS_EV_SOURCE_TICK) {
+            const hs_entity_desc ds = ENTS[ent];
+            if (ds.l0 >= 0 && now > ds.l0) return false;                      /* stop_after reached: no payload */
+            const int t1 = ds.target;
+            const hs_entity_desc d1 = ENTS[t1];
+            hs_went *Xs = &E[ent];
+            const int64_t cur_ns = Xs->u.src.cur_ns; const uint64_t arr_draws = Xs->u.src.arr_draws, key_draws = Xs->u.src.key_draws;
+            int32_t key = -1;
+            if (ds.i1 > 0) key = hs_routing_key(hs_uniform(seed, rid, HS_STREAM_ROUTING | (ent << 8), key_draws), ds.i1,
+                                                ds.i2 > 0 ? M.key_cdf + (ds.i2 - 1) : nullptr);
+            int lb = -1, be = t1; uint64_t rr = 0; bool use_rr = false;
+            hs_went *Xl = nullptr;
+            if (d1.kind == HS_ENT_LB) {
+                if (d1.i2 <= 0) return false;
+                lb = t1; Xl = &E[lb];
+                int slot;
+                if (d1.i0 == HS_LB_KEY_TABLE && key >= 0) slot = M.key_table[key];
+                else { rr = Xl->u.lb.rr_index; slot = (int)(rr % (uint64_t)d1.i2); use_rr = true; }
+                be = BACKENDS[d1.i1 + slot];
+            } else if (d1.kind != HS_ENT_SERVER) return false;
+            const hs_entity_desc dv = ENTS[be];
+            if (dv.kind != HS_ENT_SERVER) return false;
+            hs_went *Xv = &E[be];
+            const uint32_t q_head = Xv->u.srv.q_head, q_len = Xv->u.srv.q_len; const int32_t active = Xv->u.srv.active;
+            const int32_t c_lim = Xv->i0;
+            if (q_len >= P.ring) return false;
+            /* the next SourceEvent (source.py:166-180) */
+            double target = 1.0;
+            if (Xs->i0 == HS_ARR_POISSON) target = hs_exp1(hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), arr_draws));
+            int64_t nt;
+            if ((FLAGS & HS_WF_PROFILE) && ds.i3 > 0) nt = hs_next_arrival_profile_ns(&M.profiles[ds.i3 - 1], cur_ns, target);
+            else nt = hs_next_arrival_ns(cur_ns, target, Xs->d0);
+            if (nt == HS_T_EXHAUSTED || nt <= now) return false;
+            const bool was_empty = (q_len == 0);
+            const bool drop = (dv.l0 >= 0 && (int64_t)q_len >= dv.l0);
+            const bool notify = !drop && was_empty;
+            const bool poll = notify && active < c_lim;              /* the worker is idle: POLL -> DELIVER -> WORKER follow */
+            /* the service time the WORKER event would draw (server.py:246-253) */
+            const uint64_t svc_draws = Xv->u.srv.svc_draws;
+            double svc_s = 0.0; int64_t resume_t = 0;
+            if (poll) {
+                const int64_t dur = (dv.i2 == HS_SVC_EXPONENTIAL)
+                    ? hs_seconds_to_ns(HS_DIV(hs_exp1(hs_uniform(seed, rid, HS_STREAM_SERVICE | ((uint32_t)be << 8), svc_draws)), Xv->lambda))
+                    : hs_seconds_to_ns(Xv->d0);
+                svc_s = hs_ns_to_seconds(dur);
+                resume_t = hs_resume_ns(now, svc_s);
+                if (resume_t <= now) return false;                   /* a zero-length service resumes at this very nanosecond */
+            }
+            /* ---- nothing can stop the chain any more: run it ---------------------------------------------------- */
+            hdr.now = now;
+            const uint64_t idxP = ctr, idxT = ctr + 1; ctr += 2;
+            emit(now, ev.idx, HS_EV_SOURCE_TICK, ent);
+            Xs->u.src.provider++; Xs->u.src.generated++; Xs->u.src.cur_ns = nt;
+            if (ds.i1 > 0) Xs->u.src.key_draws = key_draws + 1;
+            if (Xs->i0 == HS_ARR_POISSON) Xs->u.src.arr_draws = arr_draws + 1;
+            { hs_tkey fk; fk.time = nt; fk.k2 = idxT << 16;
+              hs_tpay fp; fp.created = 0; fp.aux = 0ull; fp.m0 = (uint32_t)HS_EV_SOURCE_TICK | (ent << 8); fp.key = -1; fp.hook = 0u; fp.pad = 0u;
+              heap_insert(fk, fp); }
+            uint64_t idxE = idxP;
+            if (lb >= 0) {                                           /* LoadBalancer._forward_request */
+                emit(now, idxP, HS_EV_REQ_LB, (uint32_t)lb);
+                idxE = ctr++;
+            }
+            emit(now, idxE, HS_EV_REQ_ENQUEUE, (uint32_t)be);        /* Queue._handle_enqueue */
+            uint64_t idxN = 0, idxR = 0;
+            if (drop) Xv->u.srv.dropped++;
+            else {
+                Xv->u.srv.accepted++;
+                if (notify) idxN = ctr++;
+            }
+            if (lb >= 0) idxR = ctr++;                               /* _lb_response hook fires at ENQUEUE time */
+            uint64_t idxPoll = 0;
+            if (notify) { emit(now, idxN, HS_EV_NOTIFY, (uint32_t)be); if (poll) idxPoll = ctr++; }
+            if (lb >= 0) {
+                emit(now, idxR, HS_EV_LB_RESPONSE, (uint32_t)lb);    /* in_flight: +1 at forward, -1 here */
+                Xl->u.lb.received++; Xl->u.lb.forwarded++; Xl->u.lb.responses++;
+                if (use_rr) Xl->u.lb.rr_index = rr + 1;
+            }
+            if (poll) {
+                /* the request is enqueued and polled at once: the ring slot is dead before anyone could read it */
+                emit(now, idxPoll, HS_EV_POLL, (uint32_t)be);
+                const uint64_t idxD = ctr++;
+                emit(now, idxD, HS_EV_DELIVER, (uint32_t)be);
+                emit(now, idxE, HS_EV_REQ_WORKER, (uint32_t)be);     /* the payload keeps its own index */
+                ctr++;                                               /* inline ProcessContinuation */
+                if (dv.i1 != HS_Q_LIFO) Xv->u.srv.q_head = q_head + 1;
+                Xv->u.srv.active = active + 1;
+                if (dv.i2 == HS_SVC_EXPONENTIAL) Xv->u.srv.svc_draws = svc_draws + 1;
+                if ((FLAGS & HS_WF_REC) && svc_out) { svc_out[hdr.svc_pos] = svc_s; hdr.svc_pos = (hdr.svc_pos + 1 == P.service_cap) ? 0u : hdr.svc_pos + 1; }
+                hdr.n_svc++;
+                const uint64_t idxC = ctr++;
+                hs_tkey fk; fk.time = resume_t; fk.k2 = idxC << 16;
+                hs_tpay fp; fp.created = now; fp.aux = (uint64_t)__double_as_longlong(svc_s);
+                fp.m0 = (uint32_t)HS_EV_CONTINUATION | ((uint32_t)be << 8); fp.key = key; fp.hook = 0x80000000u; fp.pad = 0u;
+                heap_insert(fk, fp);
+            } else if (!drop) {
+                const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1);
+                hs_wring_entry *rg = ring0 + (size_t)srv_idx * P.ring;
+                hs_wring_entry q; q.created = now; q.idx = idxE; q.key = key;
+                rg[(q_head + q_len) & ring_mask] = q;
+                Xv->u.srv.q_len = q_len + 1;
+            }
+            return true;
+        }
+        if (k0 == HS_EV_CONTINUATION) {
+            const hs_entity_desc dv = ENTS[ent];
+            const int tgt = dv.target;
+            int tkind = 0;
+            if (tgt >= 0) { tkind = ENTS[tgt].kind; if (tkind != HS_ENT_SINK && tkind != HS_ENT_COUNTER) return false; }
+            hs_went *Xv = &E[ent];
+            const uint32_t q_head = Xv->u.srv.q_head, q_len = Xv->u.srv.q_len;
+            const int32_t active = Xv->u.srv.active > 0 ? Xv->u.srv.active - 1 : 0;
+            const bool poll = (ev.hook & 0x80000000u) && active < Xv->i0;
+            const bool start = poll && q_len > 0;
+            const uint64_t svc_draws = Xv->u.srv.svc_draws;
+            double svc_s = 0.0; int64_t resume_t = 0;
+            hs_wring_entry q; q.created = 0; q.idx = 0; q.key = -1;
+            if (start) {
+                const int64_t dur = (dv.i2 == HS_SVC_EXPONENTIAL)
+                    ? hs_seconds_to_ns(HS_DIV(hs_exp1(hs_uniform(seed, rid, HS_STREAM_SERVICE | (ent << 8), svc_draws)), Xv->lambda))
+                    : hs_seconds_to_ns(Xv->d0);
+                svc_s = hs_ns_to_seconds(dur);
+                resume_t = hs_resume_ns(now, svc_s);
+                if (resume_t <= now) return false;
+                const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1);
+                const hs_wring_entry *rg = ring0 + (size_t)srv_idx * P.ring;
+                q = rg[(dv.i1 == HS_Q_LIFO ? q_head + q_len - 1 : q_head) & ring_mask];
+            }
+            hdr.now = now;
+            emit(now, ev.idx, HS_EV_CONTINUATION, ent);                /* generator resumes, server.py:255-273 */
+            Xv->u.srv.completed++;
+            Xv->u.srv.total_service = HS_ADD(Xv->u.srv.total_service, __longlong_as_double((long long)ev.aux));
+            uint64_t idxS = 0, idxPoll = 0;
+            if (tgt >= 0) idxS = ctr++;
+            if (poll) idxPoll = ctr++;
+            if (tgt >= 0) {
+                hs_went *Xk = &E[tgt];
+                if (tkind == HS_ENT_SINK) {                            /* Sink.handle_event, common.py:36-44 */
+                    emit(now, idxS, HS_EV_REQ_SINK, (uint32_t)tgt);
+                    const double lat = hs_ns_to_seconds(now - ev.created);
+                    if (O.hist) atomicAdd(O.hist + (size_t)r * HS_HIST_BINS + hs_latency_bin(now - ev.created), 1u);
+                    double sm = Xk->u.snk.sum, cp = Xk->u.snk.comp;
+                    hs_neumaier_add(&sm, &cp, lat);
+                    Xk->u.snk.sum = sm; Xk->u.snk.comp = cp;
+                    Xk->u.snk.sumsq = HS_ADD(Xk->u.snk.sumsq, HS_MUL(lat, lat));
+                    if (lat < Xk->u.snk.mn) Xk->u.snk.mn = lat;
+                    if (lat > Xk->u.snk.mx) Xk->u.snk.mx = lat;
+                    if ((FLAGS & HS_WF_REC) && smp) { hs_sink_sample qs; qs.completion_ns = now; qs.latency_s = lat; smp[hdr.smp_pos] = qs;
+                        hdr.smp_pos = (hdr.smp_pos + 1 == P.sample_cap) ? 0u : hdr.smp_pos + 1; }
+                    hdr.n_smp++;
+                } else emit(now, idxS, HS_EV_REQ_COUNTER, (uint32_t)tgt);
+                Xk->u.snk.received++;
+            }
+            int32_t act = active;
+            if (poll) {
+                emit(now, idxPoll, HS_EV_POLL, ent);                   /* Queue._handle_poll */
+                if (start) {
+                    const uint64_t idxD = ctr++;
+                    emit(now, idxD, HS_EV_DELIVER, ent);
+                    emit(now, q.idx, HS_EV_REQ_WORKER, ent);
+                    ctr++;                                             /* inline ProcessContinuation */
+                    if (dv.i1 != HS_Q_LIFO) Xv->u.srv.q_head = q_head + 1;
+                    Xv->u.srv.q_len = q_len - 1;
+                    act = active + 1;
+                    if (dv.i2 == HS_SVC_EXPONENTIAL) Xv->u.srv.svc_draws = svc_draws + 1;
+                    if ((FLAGS & HS_WF_REC) && svc_out) { svc_out[hdr.svc_pos] = svc_s; hdr.svc_pos = (hdr.svc_pos + 1 == P.service_cap) ? 0u : hdr.svc_pos + 1; }
+                    hdr.n_svc++;
+                    const uint64_t idxC = ctr++;
+                    hs_tkey fk; fk.time = resume_t; fk.k2 = idxC << 16;
+                    hs_tpay fp; fp.created = q.created; fp.aux = (uint64_t)__double_as_longlong(svc_s);
+                    fp.m0 = (uint32_t)HS_EV_CONTINUATION | (ent << 8); fp.key = (int32_t)q.key; fp.hook = 0x80000000u; fp.pad = 0u;
+                    heap_insert(fk, fp);
+                }
+            }
+            Xv->u.srv.active = act;
+            return true;
+        }
+        return false;
+    };
+
+    /* one event: the handler of hs_handlers.inc (kind is warp-uniform at every call site), then the insertion of the
+     * (at most one) future event it created */
     auto process = [&](const int kind) {
         const int64_t now = ev.time;
         const uint64_t bi = ev.idx;
@@ -309,26 +535,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         { uint4 *g = (uint4 *)&E[ent];
 #pragma unroll
           for (int i = 2; i < 6; ++i) g[i] = xu.q[i]; }
-        /* heap insertion of the future event (SourceEvent or ProcessContinuation) */
-        if (have_fut) {
-            if (heap_n >= S) hdr.status |= HS_ST_FEL_OVERFLOW;
-            else {
-                const uint32_t slot = FREE[S - heap_n - 1];
-                PAY[slot] = fpay;
-                fkey.k2 |= slot;
-                uint32_t k = heap_n++;
-                while (k > 0) {
-                    const uint32_t p = (k - 1) >> HS_T_SHIFT;
-                    hs_tkey q;
-                    if (p == 0) { q.time = top_t; q.k2 = top_k; } else q = K[p];
-                    if (!HS_T_LT(fkey.time, fkey.k2, q.time, q.k2)) break;
-                    K[k] = q; k = p;
-                }
-                K[k] = fkey;
-                if (k == 0) { top_t = fkey.time; top_k = fkey.k2; }
-                hdr.fel_n++;
-            }
-        }
+        if (have_fut) heap_insert(fkey, fpay);
     };
     const bool single = (P.lane_stride == 32);          /* one replica per warp: nothing to align, every pass runs the next event */
     next_event();
@@ -369,6 +576,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             hdr.fel_n--;
             need_heap = false;
             if (ev.time < now0) next_event();            /* "time travel": skipped (simulation.py:479-489) */
+            else if (fused_chain()) next_event();        /* the whole same-timestamp chain ran as straight-line code */
             else { int k = (int)(ev.m0 & 0xffu);
                    if (k == (int)HS_EV_REQ_ANY) {
                        const int ek = ENTS[ev.m0 >> 8].kind;

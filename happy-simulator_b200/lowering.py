@@ -129,13 +129,84 @@ def profile_max_rate(pr, tables=None) -> float:
     kind = int(pr["kind"])
     if kind == A.HS_PROF_LINEAR_RAMP:
         return float(max(pr["p"][1:3]))
+    if kind == A.HS_PROF_STEP:
+        off, n = int(pr["p"][0]), int(pr["p"][1])
+        return float(np.max(tables[off + n: off + 2 * n + 1]))
     return float(max(pr["p"][0:2]))
 
 
-def _arrival(tp):
+class _Seconds:
+    """Stand-in for an Instant when probing a user's Profile.get_rate: the reference evaluates
+    ``profile.get_rate(Instant.from_seconds(t))`` and profiles read ``time.to_seconds()`` (load/profile.py:37-110),
+    i.e. float(int(t * 1e9)) / 1e9 -- the rate is a function of the NANOSECOND count."""
+    __slots__ = ("nanoseconds",)
+
+    def __init__(self, ns: int):
+        self.nanoseconds = int(ns)
+
+    def to_seconds(self) -> float:
+        return float(self.nanoseconds) / 1_000_000_000
+
+
+def step_table_from_profile(profile, scan_end_s: float, scan_step_s: float | None = None, max_pieces: int = 4096):
+    """Tabulate a piecewise-constant ``Profile.get_rate`` exactly: (breakpoints, rates) with
+    ``rates[number of breakpoints <= t] == profile.get_rate(t)`` for every t the arrival solver can ask about.
+
+    get_rate only ever sees times of the form float(ns) / 1e9, so the function is scanned on the integer
+    nanosecond axis: a coarse grid finds the pieces, bisection on ns finds the first nanosecond of each new piece,
+    and that nanosecond's to_seconds() value is the breakpoint -- ``t >= b`` then holds for exactly the same ns
+    counts as in the user's own comparisons, whatever arithmetic they use (e.g. int((t - 65.0) / 11.0),
+    examples/queuing/m_m_1_queue.py:160-166).  Assumptions, checked where they can be: the function is constant
+    between changes (a second scan on an offset grid must agree with the table), pieces are not shorter than the
+    scan step, and the profile keeps its last value beyond ``scan_end_s``.  Raises UnsupportedModelError for
+    anything that is not a step function."""
+    step = scan_step_s or max(1e-3, scan_end_s / 400_000.0)
+    end_ns = int(scan_end_s * 1e9)
+    step_ns = max(1, int(step * 1e9))
+
+    def f(ns):
+        return float(profile.get_rate(_Seconds(ns)))
+
+    grid = list(range(0, end_ns + step_ns, step_ns))
+    vals = [f(ns) for ns in grid]
+    breaks_ns, rates = [], [vals[0]]
+    for a, b, va, vb in zip(grid, grid[1:], vals, vals[1:]):
+        if va == vb:
+            continue
+        lo, hi = a, b                         # f(lo) == va, f(hi) != va: first ns with a different value
+        while hi - lo > 1:
+            mid = (lo + hi) // 2
+            if f(mid) == va:
+                lo = mid
+            else:
+                hi = mid
+        if f(hi) != vb:
+            raise UnsupportedModelError(f"profile {_cls(profile)}: two rate changes within one scan step of {step} s "
+                                        f"near t = {a / 1e9} s (pass a smaller scan_step_s) or not a step function")
+        breaks_ns.append(hi)
+        rates.append(vb)
+        if len(rates) > max_pieces:
+            raise UnsupportedModelError(f"profile {_cls(profile)}: more than {max_pieces} pieces -- a continuously "
+                                        "varying get_rate is a Python callback and cannot run on the device")
+    breaks = [float(ns) / 1_000_000_000 for ns in breaks_ns]
+    # verification on an offset grid: the table must reproduce the function
+    import bisect
+    for ns in range(step_ns // 3, end_ns, max(step_ns, (end_ns // 50_000) or 1)):
+        if rates[bisect.bisect_right(breaks, float(ns) / 1_000_000_000)] != f(ns):
+            raise UnsupportedModelError(f"profile {_cls(profile)} is not piecewise constant at the scan resolution "
+                                        f"({step} s): table and get_rate disagree at t = {ns / 1e9} s")
+    if any(not (r > 0.0) for r in rates):
+        raise UnsupportedModelError(f"profile {_cls(profile)}: rates must stay > 0 (a zero rate sends the reference's "
+                                    "bracket search beyond the int64 nanosecond range)")
+    return breaks, rates
+
+
+def _arrival(tp, horizon_s: float | None = None):
     """ArrivalTimeProvider -> (HS_ARR_*, rate, profile tuple or None).  The reference's built-in
-    profile classes (load/profile.py) are lowered; a user-defined Profile.get_rate is a Python
-    callback and cannot run on the device."""
+    profile classes (load/profile.py) are lowered as they are; ``StepProfile`` tables directly; any other
+    user-defined Profile is tabulated as a step function over the run's horizon when it is one
+    (``step_table_from_profile``) -- a continuously varying get_rate is a Python callback and cannot run on
+    the device."""
     name = _cls(tp)
     prof = getattr(tp, "profile", None)
     pname = _cls(prof)
@@ -147,9 +218,16 @@ def _arrival(tp):
     elif pname == "SpikeProfile":
         ptuple = ("spike", float(prof.baseline_rate), float(prof.spike_rate), float(prof.warmup_s),
                   float(prof.spike_duration_s))
+    elif hasattr(prof, "breakpoints") and hasattr(prof, "rates"):           # happysim_b200.StepProfile
+        ptuple = ("step", [float(x) for x in prof.breakpoints], [float(x) for x in prof.rates])
+    elif prof is not None and hasattr(prof, "get_rate") and horizon_s is not None:
+        # the arrival solver brackets beyond the current time (arrival_time_provider.py:100-120): scan well past the run's end
+        breaks, rates = step_table_from_profile(prof, scan_end_s=2.0 * float(horizon_s) + 120.0)
+        ptuple = ("step", breaks, rates)
     else:
-        raise UnsupportedModelError(f"arrival profile {pname}: only ConstantRateProfile, LinearRampProfile and "
-                                    "SpikeProfile are lowered (a custom get_rate is a Python callback)")
+        raise UnsupportedModelError(f"arrival profile {pname}: ConstantRateProfile, LinearRampProfile, SpikeProfile and "
+                                    "step functions (StepProfile, or any piecewise-constant get_rate when the run's "
+                                    "horizon is known) are lowered; a continuously varying get_rate is a Python callback")
     if "Poisson" in name:
         return A.HS_ARR_POISSON, rate, ptuple
     if "Constant" in name:
@@ -177,7 +255,7 @@ def _queue_policy(q):
     return (A.HS_Q_LIFO if name == "LIFOQueue" else A.HS_Q_FIFO), cap
 
 
-def lower(sources, entities, *, key_population: int | None = None, probes=None):
+def lower(sources, entities, *, key_population: int | None = None, probes=None, horizon_s: float | None = None):
     """-> (FlatModel, objects) where objects[i] is the Python object of entity id i.
 
     Entity ids: sources first (in ``sources`` order, the bootstrap order of
@@ -267,7 +345,7 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None):
                                                 "device (use happysim_b200.UniformKeyContext / ZipfKeyContext)")
                 if getattr(ctx, "zipf_s", None) is not None:
                     cdf = zipf_cdf(pop, float(ctx.zipf_s))
-            kind, rate, ptuple = _arrival(o._time_provider)
+            kind, rate, ptuple = _arrival(o._time_provider, horizon_s)
             stop = prov._stop_after
             b.source(name, rate=rate, target=ids[id(prov._target)], poisson=(kind == A.HS_ARR_POISSON),
                      stop_after_ns=-1 if stop is None else _ns(stop), key_population=pop, profile=ptuple, key_cdf=cdf)

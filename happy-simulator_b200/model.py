@@ -26,6 +26,7 @@ class FlatModel:
     cell_d0: np.ndarray | None = None         # float64[n_cells, n]
     cell_i0: np.ndarray | None = None         # int32[n_cells, n]
     profiles: np.ndarray = field(default_factory=lambda: np.zeros(0, A.PROFILE_DTYPE))
+    profile_table: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))   # STEP profiles: breakpoints + rates
     sketch_tables: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     key_cdf: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))
 
@@ -145,7 +146,15 @@ class FlatModel:
             d.cell_i0 = ci.ctypes.data_as(C.POINTER(C.c_int32))
             keep += [cd, ci]
         if len(self.profiles):
-            pr = np.ascontiguousarray(self.profiles, dtype=A.PROFILE_DTYPE)
+            pr = np.array(self.profiles, dtype=A.PROFILE_DTYPE)          # a copy: p[2] of STEP rows is filled in below
+            if len(self.profile_table):
+                pt = np.ascontiguousarray(self.profile_table, dtype=np.float64)
+                d.profile_table = pt.ctypes.data_as(C.POINTER(C.c_double))
+                d.n_profile_table = pt.shape[0]
+                keep.append(pt)
+                for row in pr:                                       # host address of the row's table, for the CPU oracle
+                    if int(row["kind"]) == A.HS_PROF_STEP:
+                        row["p"][2] = np.array([pt.ctypes.data + 8 * int(row["p"][0])], np.uint64).view(np.float64)[0]
             d.n_profiles = pr.shape[0]
             d.profiles = pr.ctypes.data
             keep.append(pr)
@@ -172,6 +181,7 @@ class ModelBuilder:
         self._backends: list[int] = []
         self._key_table = np.zeros(0, np.int32)
         self._profiles: list[tuple] = []
+        self._profile_tables: list[list[float]] = []
         self._sketch_tables: list[np.ndarray] = []
         self._key_cdf: list[np.ndarray] = []
 
@@ -183,9 +193,19 @@ class ModelBuilder:
     def source(self, name="Source", *, rate=0.0, target=-1, poisson=True, stop_after_ns=-1, key_population=0,
                profile=None, key_cdf=None):
         """profile: None (ConstantRateProfile(rate)) or ("linear_ramp", duration_s, start_rate, end_rate)
-        or ("spike", baseline_rate, spike_rate, warmup_s, spike_duration_s)."""
+        or ("spike", baseline_rate, spike_rate, warmup_s, spike_duration_s) or ("step", breakpoints, rates):
+        n ascending breakpoints in seconds and n + 1 rates, rate(t) = rates[number of breakpoints <= t]."""
         i3 = 0
-        if profile is not None:
+        if profile is not None and profile[0] == "step":
+            breaks = [float(x) for x in profile[1]]
+            rates = [float(x) for x in profile[2]]
+            if len(rates) != len(breaks) + 1 or any(b <= a for a, b in zip(breaks, breaks[1:])):
+                raise ValueError("step profile: n ascending breakpoints and n + 1 rates")
+            off = sum(len(t) for t in self._profile_tables)
+            self._profile_tables.append(breaks + rates)
+            self._profiles.append((A.HS_PROF_STEP, 0, [float(off), float(len(breaks)), 0.0, 0.0]))
+            i3 = len(self._profiles)
+        elif profile is not None:
             kind = {"constant": A.HS_PROF_CONSTANT, "linear_ramp": A.HS_PROF_LINEAR_RAMP, "spike": A.HS_PROF_SPIKE}[profile[0]]
             ps = [float(x) for x in profile[1:]] + [0.0] * (5 - len(profile))
             self._profiles.append((kind, 0, ps))
@@ -299,6 +319,8 @@ class ModelBuilder:
                       key_table=self._key_table)
         if self._profiles:
             m.profiles = np.array(self._profiles, dtype=A.PROFILE_DTYPE)
+            if self._profile_tables:
+                m.profile_table = np.array([x for t in self._profile_tables for x in t], dtype=np.float64)
         if self._sketch_tables:
             m.sketch_tables = np.concatenate([t.ravel() for t in self._sketch_tables]).astype(np.int32)
         if self._key_cdf:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HS_ABI_VERSION 2u
+#define HS_ABI_VERSION 3u
 
 typedef enum hs_status {
     HS_OK = 0,
@@ -145,14 +145,23 @@ typedef struct hs_model_desc {
     /* ZipfDistribution._cum_probs of the sources whose keys are Zipf distributed (zipf.py:96-110), as the
      * host computed them; a key is bisect_left(cum_probs, u) clamped to the last index (zipf.py:112-123). */
     const double *key_cdf;
+    /* Tables of the piecewise-constant (STEP) rate profiles: for a profile with n breakpoints, n ascending
+     * breakpoints (seconds) followed by n + 1 rates; rate(t) = rates[#{breakpoints <= t}].  A user-defined
+     * Profile.get_rate that is a step function (examples/queuing/m_m_1_queue.py:104-169) lowers to one. */
+    const double *profile_table;
+    uint64_t n_profile_table;      /* total length of profile_table[]                          */
 } hs_model_desc;
 
-enum { HS_PROF_CONSTANT = 0, HS_PROF_LINEAR_RAMP = 1, HS_PROF_SPIKE = 2 };
+enum { HS_PROF_CONSTANT = 0, HS_PROF_LINEAR_RAMP = 1, HS_PROF_SPIKE = 2, HS_PROF_STEP = 3 };
 typedef struct hs_profile_desc {
     int32_t kind;      /* HS_PROF_*                                                          */
     int32_t pad;
     double p[4];       /* CONSTANT: rate | LINEAR_RAMP: duration_s, start_rate, end_rate
-                          | SPIKE: baseline_rate, spike_rate, warmup_s, spike_duration_s    */
+                          | SPIKE: baseline_rate, spike_rate, warmup_s, spike_duration_s
+                          | STEP: offset of its table in profile_table, number of breakpoints n,
+                            p[2] = the ADDRESS of that table as a bit pattern (filled in by whoever
+                            evaluates the profile: the engine writes the device address into its copy,
+                            the host layer the host address for the CPU oracle), p[3] unused          */
 } hs_profile_desc;     /* 40 bytes */
 
 /* ---- run --------------------------------------------------------------- */

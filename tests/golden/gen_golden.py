@@ -197,6 +197,33 @@ def zipf_hot_keys(K=300, s=1.1, n_servers=6):
     return b.build(), {src: s}
 
 
+def example_metastable_profile():
+    """The profile class of the reference's own example (examples/queuing/m_m_1_queue.py:104-169), imported from
+    the example file itself: a user-defined step function incl. the int((t - 65.0) / 11.0) step-down phase."""
+    import importlib.util
+    RH._import_reference()
+    path = os.path.join(RH.REFERENCE_ROOT, "examples", "queuing", "m_m_1_queue.py")
+    spec = importlib.util.spec_from_file_location("ref_example_mm1", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_example_mm1"] = mod
+    spec.loader.exec_module(mod)
+    return mod.MetastableLoadProfile()
+
+
+def step_profiled(profile_obj, end_s, mean_service_s=0.1, stop_after_s=None):
+    """Source(PoissonArrivalTimeProvider(<user step profile>)) -> Server(Exp) -> Sink, the table tabulated by
+    happysim_b200.lowering.step_table_from_profile exactly as Simulation() would."""
+    from happysim_b200 import lowering
+    breaks, rates = lowering.step_table_from_profile(profile_obj, scan_end_s=2.0 * end_s + 120.0)
+    b = hs.ModelBuilder()
+    src = b.source(profile=("step", breaks, rates), poisson=True,
+                   stop_after_ns=-1 if stop_after_s is None else int(stop_after_s * 1e9))
+    srv = b.server(mean_service_s=mean_service_s)
+    snk = b.sink()
+    b.set_target(src, srv); b.set_target(srv, snk)
+    return b.build(), {src: profile_obj}
+
+
 def philox_cases():
     c = {}
     c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
@@ -231,6 +258,9 @@ def philox_cases():
     c["sketch_tdigest"] = (sketch_quantiles(), dict(seed=29, rid=0, end_s=40))
     m, zs = zipf_hot_keys()
     c["zipf_chash_topk"] = (m, dict(seed=37, rid=5, end_s=6, chash_vnodes=30, zipf_s=zs))
+    # a user-defined step profile: the example's MetastableLoadProfile, its whole 130 s scenario
+    m, po = step_profiled(example_metastable_profile(), 130.0, stop_after_s=120.0)
+    c["step_metastable_mm1"] = (m, dict(seed=42, rid=0, end_s=130, profile_objects=po))
     return c
 
 
@@ -239,6 +269,7 @@ def save_case(path, model, ref, meta):
     np.savez_compressed(
         path,
         entities=model.entities, backends=model.backends, key_table=model.key_table, profiles=model.profiles,
+        profile_table=model.profile_table,
         names=np.array(model.names), meta=np.array([meta["seed"], meta["rid"], int(meta["end_s"] * 1e9)], dtype=np.int64),
         summaries=ref["summaries"], entity_stats=ref["entity_stats"],
         n_records=np.int64(len(rec)), records=rec[:MAX_REC],
@@ -258,7 +289,7 @@ def main():
             continue
         ref = RH.run_reference(model, seed=kw["seed"], rid=kw["rid"], end_ns=int(kw["end_s"] * 1e9),
                                chash_vnodes=kw.get("chash_vnodes"), sketch_seeds=kw.get("sketch_seeds"),
-                               zipf_s=kw.get("zipf_s"))
+                               zipf_s=kw.get("zipf_s"), profile_objects=kw.get("profile_objects"))
         save_case(os.path.join(HERE, f"philox_{name}.npz"), model, ref, kw)
         print(f"philox_{name}: {len(ref['records'])} events, hash {int(ref['summaries']['order_hash'][0]):#x}")
 

@@ -31,7 +31,7 @@ def _import_reference():
 
 
 def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, stock_rng=False,
-                  max_records=None, sketch_seeds=None, zipf_s=None):
+                  max_records=None, sketch_seeds=None, zipf_s=None, profile_objects=None):
     """Run the reference on ``model`` (a happysim_b200.FlatModel); replica word ``rid``.
 
     stock_rng=True leaves the reference's own MT19937 streams in place (seeded
@@ -198,8 +198,13 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
         if int(e["i3"]) > 0:
             pr = model.profiles[int(e["i3"]) - 1]
             pp = [float(x) for x in pr["p"]]
-            profile = (LinearRampProfile(pp[0], pp[1], pp[2]) if int(pr["kind"]) == A.HS_PROF_LINEAR_RAMP
-                       else SpikeProfile(pp[0], pp[1], pp[2], pp[3]))
+            if int(pr["kind"]) == A.HS_PROF_STEP:
+                # the user's own Profile object (the table in the model was tabulated from it): the reference runs
+                # the ORIGINAL get_rate, the oracle and the device the table
+                profile = profile_objects[i]
+            else:
+                profile = (LinearRampProfile(pp[0], pp[1], pp[2]) if int(pr["kind"]) == A.HS_PROF_LINEAR_RAMP
+                           else SpikeProfile(pp[0], pp[1], pp[2], pp[3]))
         if int(e["i0"]) == A.HS_ARR_POISSON:
             atp = (PoissonArrivalTimeProvider(profile, Instant.Epoch) if stock_rng
                    else PhiloxPoissonArrival(profile, Instant.Epoch, i))

@@ -19,6 +19,8 @@ def load(name):
                          key_table=z["key_table"])
     if "profiles" in z.files and len(z["profiles"]):
         model.profiles = z["profiles"]
+    if "profile_table" in z.files and len(z["profile_table"]):
+        model.profile_table = z["profile_table"]
     if "sketch_tables" in z.files and len(z["sketch_tables"]):
         model.sketch_tables = z["sketch_tables"]
     if "key_cdf" in z.files and len(z["key_cdf"]):

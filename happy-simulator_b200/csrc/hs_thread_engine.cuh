@@ -291,6 +291,18 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         }
         hdr.processed++;
     };
+    /* entity state as six 16-byte vectors: one burst of loads into registers, the dynamic part (vectors 2..5) stored back */
+    union went_u { hs_went w; uint4 q[6]; };
+    auto went_load = [&](const int i, went_u &x) {
+        const uint4 *g = (const uint4 *)&E[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) x.q[k] = g[k];
+    };
+    auto went_store = [&](const int i, const went_u &x) {
+        uint4 *g = (uint4 *)&E[i];
+#pragma unroll
+        for (int k = 2; k < 6; ++k) g[k] = x.q[k];
+    };
     const bool fuse_on = !P.trace_arr && !P.trace_svc;
     auto fused_chain = [&]() -> bool {
         const int64_t now = ev.time;
@@ -302,16 +314,16 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (ds.l0 >= 0 && now > ds.l0) return false;                      /* stop_after reached: no payload */
             const int t1 = ds.target;
             const hs_entity_desc d1 = ENTS[t1];
-            hs_went *Xs = &E[ent];
+            went_u xs; went_load((int)ent, xs); hs_went *Xs = &xs.w;
             const int64_t cur_ns = Xs->u.src.cur_ns; const uint64_t arr_draws = Xs->u.src.arr_draws, key_draws = Xs->u.src.key_draws;
             int32_t key = -1;
             if (ds.i1 > 0) key = hs_routing_key(hs_uniform(seed, rid, HS_STREAM_ROUTING | (ent << 8), key_draws), ds.i1,
                                                 ds.i2 > 0 ? M.key_cdf + (ds.i2 - 1) : nullptr);
             int lb = -1, be = t1; uint64_t rr = 0; bool use_rr = false;
-            hs_went *Xl = nullptr;
+            went_u xl; hs_went *Xl = &xl.w;
             if (d1.kind == HS_ENT_LB) {
                 if (d1.i2 <= 0) return false;
-                lb = t1; Xl = &E[lb];
+                lb = t1; went_load(lb, xl);
                 int slot;
                 if (d1.i0 == HS_LB_KEY_TABLE && key >= 0) slot = M.key_table[key];
                 else { rr = Xl->u.lb.rr_index; slot = (int)(rr % (uint64_t)d1.i2); use_rr = true; }
@@ -319,7 +331,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             } else if (d1.kind != HS_ENT_SERVER) return false;
             const hs_entity_desc dv = ENTS[be];
             if (dv.kind != HS_ENT_SERVER) return false;
-            hs_went *Xv = &E[be];
+            went_u xv; went_load(be, xv); hs_went *Xv = &xv.w;
             const uint32_t q_head = Xv->u.srv.q_head, q_len = Xv->u.srv.q_len; const int32_t active = Xv->u.srv.active;
             const int32_t c_lim = Xv->i0;
             if (q_len >= P.ring) return false;
@@ -399,6 +411,9 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 rg[(q_head + q_len) & ring_mask] = q;
                 Xv->u.srv.q_len = q_len + 1;
             }
+            went_store((int)ent, xs);
+            if (lb >= 0) went_store(lb, xl);
+            went_store(be, xv);
             return true;
         }
         if (k0 == HS_EV_CONTINUATION) {
@@ -406,7 +421,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             const int tgt = dv.target;
             int tkind = 0;
             if (tgt >= 0) { tkind = ENTS[tgt].kind; if (tkind != HS_ENT_SINK && tkind != HS_ENT_COUNTER) return false; }
-            hs_went *Xv = &E[ent];
+            went_u xv; went_load((int)ent, xv); hs_went *Xv = &xv.w;
             const uint32_t q_head = Xv->u.srv.q_head, q_len = Xv->u.srv.q_len;
             const int32_t active = Xv->u.srv.active > 0 ? Xv->u.srv.active - 1 : 0;
             const bool poll = (ev.hook & 0x80000000u) && active < Xv->i0;
@@ -433,7 +448,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (tgt >= 0) idxS = ctr++;
             if (poll) idxPoll = ctr++;
             if (tgt >= 0) {
-                hs_went *Xk = &E[tgt];
+                went_u xk; went_load(tgt, xk); hs_went *Xk = &xk.w;
                 if (tkind == HS_ENT_SINK) {                            /* Sink.handle_event, common.py:36-44 */
                     emit(now, idxS, HS_EV_REQ_SINK, (uint32_t)tgt);
                     const double lat = hs_ns_to_seconds(now - ev.created);
@@ -449,6 +464,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                     hdr.n_smp++;
                 } else emit(now, idxS, HS_EV_REQ_COUNTER, (uint32_t)tgt);
                 Xk->u.snk.received++;
+                went_store(tgt, xk);
             }
             int32_t act = active;
             if (poll) {
@@ -472,6 +488,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 }
             }
             Xv->u.srv.active = act;
+            went_store((int)ent, xv);
             return true;
         }
         return false;

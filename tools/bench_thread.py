@@ -21,7 +21,7 @@ def run(name, model, n, end_s, rpw=None, **kw):
     eng.close()
 
 lb = hs.lb_round_robin(64, 512.0)
-for n, rpws in ((16384, (None, 16, 32)), (65536, (None,))):
+for n, rpws in ((16384, (None, 16)), (65536, (None, 16, 8))):
     for rpw in rpws:
         run("configs[2] lb-rr64", lb, n, 10.0, rpw=rpw)
 tab = hs.consistent_hash_table([f"S{i}" for i in range(1024)], 100, 10000)

@@ -20,7 +20,7 @@ from .sketching import (HyperLogLog, CountMinSketch, BloomFilter, TopK, SketchCo
 from .api import (  # noqa: F401,E402
     Instant, Duration, Entity, Source, SimpleEventProvider, ConstantRateProfile, ConstantArrivalTimeProvider,
     PoissonArrivalTimeProvider, ConstantLatency, ExponentialLatency, FIFOQueue, LIFOQueue, FixedConcurrency,
-    Server, ServerStats, Sink, Counter, LoadBalancer, LoadBalancerStats, RoundRobin, ConsistentHash,
+    Server, ServerStats, CachingServer, CachingServerStats, Sink, Counter, LoadBalancer, LoadBalancerStats, RoundRobin, ConsistentHash,
     UniformKeyContext, ZipfKeyContext, StepProfile, Simulation, SimulationSummary, EntitySummary, QueueStats, ParallelRunner, RunConfig,
     ParallelResult, seed, run_lowered, LinearRampProfile, SpikeProfile,
 )

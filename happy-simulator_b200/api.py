@@ -428,6 +428,64 @@ class Server(Entity):
         return sum(self._service_times) / len(self._service_times) if self._service_times else 0.0
 
 
+@dataclass
+class CachingServerStats:
+    """examples/load-balancing/common.py:90-97"""
+    requests_processed: int = 0
+    cache_hits: int = 0
+    cache_misses: int = 0
+
+
+class CachingServer(Entity):
+    """examples/load-balancing/common.py:100-275: a server with a local TTL cache in front of a shared datastore.
+    Same constructor; ``datastore`` is accepted and unused (its read latency is ``datastore_read_latency_s``).
+    The request's customer id is its routing key (``UniformKeyContext`` / ``ZipfKeyContext`` on the source).
+    ``cache_capacity`` must exceed the key population: the reference class raises on its first eviction."""
+
+    def __init__(self, name: str, server_id: int = 0, datastore=None, cache_capacity: int = 100, cache_ttl_s: float = 30.0,
+                 cache_read_latency_s: float = 0.0001, datastore_read_latency_s: float = 0.005,
+                 processing_latency_s: float = 0.001):
+        super().__init__(name)
+        if cache_ttl_s <= 0:
+            raise ValueError(f"ttl must be > 0, got {cache_ttl_s}")          # eviction_policies.py:174
+        self.server_id = server_id
+        self._datastore = datastore
+        self._cache_capacity = cache_capacity
+        self._cache_ttl_s = cache_ttl_s
+        self._cache_read_latency_s = cache_read_latency_s
+        self._datastore_read_latency_s = datastore_read_latency_s
+        self._processing_latency_s = processing_latency_s
+        self._queue = _Queue(f"{name}.queue", FIFOQueue())
+        self.stats = CachingServerStats()
+        self._insert_times: dict[str, float] = {}     # TTLEviction._insert_times after the run: "customer:<id>" -> seconds
+
+    @property
+    def stats_accepted(self) -> int:
+        return self._queue.stats_accepted
+
+    @property
+    def stats_dropped(self) -> int:
+        return self._queue.stats_dropped
+
+    @property
+    def hit_rate(self) -> float:
+        total = self.stats.cache_hits + self.stats.cache_misses
+        return self.stats.cache_hits / total if total else 0.0
+
+    @property
+    def miss_rate(self) -> float:
+        total = self.stats.cache_hits + self.stats.cache_misses
+        return self.stats.cache_misses / total if total else 0.0
+
+    @property
+    def cache_size(self) -> int:
+        return len(self._insert_times)
+
+    @property
+    def requests_processed(self) -> int:
+        return self.stats.requests_processed
+
+
 class Sink(Entity):
     """components/common.py:18-76"""
 
@@ -715,6 +773,17 @@ class Simulation:
                 o._requests_completed, o._requests_rejected = int(row["c2"]), int(row["c3"])
                 o._total_service_time = float(row["f0"])
                 o._service_times = per_server[i]
+            elif k == A.HS_ENT_CACHE_SERVER:
+                o._queue.stats_accepted, o._queue.stats_dropped = int(row["c0"]), int(row["c1"])
+                o.stats.requests_processed, o.stats.cache_misses, o.stats.cache_hits = int(row["c2"]), int(row["c3"]), int(row["f0"])
+                if out.get("sketches") is not None:
+                    ins = self.model.cache_views(out["sketches"])[i][r]
+                    K = len(ins) - 1
+                    times = {("customer:unknown" if j == K else f"customer:{j}"): float(t) for j, t in enumerate(ins) if t != 0.0}
+                    if hasattr(o, "_insert_times"):
+                        o._insert_times = times
+                    elif getattr(o, "_eviction_policy", None) is not None:      # the example's own object, already initialised
+                        o._eviction_policy._insert_times = times
             elif k == A.HS_ENT_SINK and hasattr(o, "data"):          # LatencyTracker / ThroughputTracker
                 o.count = int(row["c0"])
                 sm = per_sink[i]

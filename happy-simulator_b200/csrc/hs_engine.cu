@@ -154,6 +154,13 @@ static int validate_model(const hs_model_desc *m)
             if (e.i2 == HS_SVC_EXPONENTIAL && !(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: exponential mean must be > 0", i);
             if (e.d0 < 0.0) return fail(HS_ERR_INVALID, "entity %u: negative service time", i);
             break;
+        case HS_ENT_CACHE_SERVER:
+            if (e.target != -1) return fail(HS_ERR_INVALID, "entity %u: a CachingServer forwards nothing (its generator returns [])", i);
+            if (e.i0 < 1 || e.i0 > (1 << 20)) return fail(HS_ERR_INVALID, "entity %u: key slots must be in [1, 2^20]", i);
+            if (e.i1 != HS_Q_FIFO && e.i1 != HS_Q_LIFO) return fail(HS_ERR_INVALID, "entity %u: bad queue policy", i);
+            if (e.i2 < 0 || e.i3 < 0 || e.l0 < 0) return fail(HS_ERR_INVALID, "entity %u: negative latency", i);
+            if (!(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: ttl must be > 0 (eviction_policies.py:174)", i);
+            break;
         case HS_ENT_SINK: case HS_ENT_COUNTER: break;
         case HS_ENT_SKETCH: {
             if (e.i0 < HS_SK_HLL || e.i0 > HS_SK_TDIGEST) return fail(HS_ERR_INVALID, "entity %u: unknown sketch algorithm %d", i, e.i0);
@@ -215,7 +222,7 @@ static int validate_model(const hs_model_desc *m)
                 int be = m->backends[e.i1 + b];
                 if (be < 0 || (uint32_t)be >= n) return fail(HS_ERR_INVALID, "entity %u: backend %d out of range", i, be);
                 int bk = m->entities[be].kind;
-                if (bk != HS_ENT_SERVER && bk != HS_ENT_SINK && bk != HS_ENT_COUNTER) return fail(HS_ERR_INVALID, "entity %u: backend %d must be a Server, Sink or Counter", i, be);
+                if (bk != HS_ENT_SERVER && bk != HS_ENT_CACHE_SERVER && bk != HS_ENT_SINK && bk != HS_ENT_COUNTER) return fail(HS_ERR_INVALID, "entity %u: backend %d must be a Server, CachingServer, Sink or Counter", i, be);
             }
             if (e.i0 == HS_LB_KEY_TABLE) {
                 if (!m->key_table || m->key_population == 0) return fail(HS_ERR_INVALID, "entity %u: key table missing", i);
@@ -295,6 +302,11 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
             int32_t c = e.i0;
             for (uint32_t k = 0; k < E->n_cells; ++k) c = std::max(c, E->cell_i0[(size_t)k * ne + i]);
             live += (uint64_t)c + 1;
+            srv_index[i] = (int32_t)n_servers++;
+        }
+        if (e.kind == HS_ENT_CACHE_SERVER) {      /* no concurrency limit: one pending continuation per request in service;
+                                                    64 covers 10 000 requests/s through the ~6 ms of a miss (overflow is flagged) */
+            live += 64;
             srv_index[i] = (int32_t)n_servers++;
         }
     }
@@ -514,7 +526,10 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
         int64_t k = 0;
         for (uint32_t i = 0; i < n; ++i) {
             hs_entity_desc &e = dev_ents[i];
-            const int64_t v = (e.kind == HS_ENT_SERVER) ? k++ : (e.kind == HS_ENT_SKETCH) ? (int64_t)E->sk_off[i] : -1;
+            /* SERVER: its index among the queue rings; SKETCH: the offset of its state; CACHE_SERVER: both,
+             * ring index in the low 24 bits, state offset above */
+            const int64_t v = (e.kind == HS_ENT_SERVER) ? k++ : (e.kind == HS_ENT_SKETCH) ? (int64_t)E->sk_off[i]
+                            : (e.kind == HS_ENT_CACHE_SERVER) ? ((k++) | ((int64_t)E->sk_off[i] << 24)) : -1;
             memcpy(&e.d1, &v, 8);
         }
     }

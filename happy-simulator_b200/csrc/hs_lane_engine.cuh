@@ -150,6 +150,9 @@ struct hs_lane_out {
 #ifndef HS_ST256_POLICY
 #define HS_ST256_POLICY 1
 #endif
+#ifndef HS_LANE_PREDICATED
+#define HS_LANE_PREDICATED 1    /* SIMPLE chains: state updates as selects + predicated memory operations (0: two branches) */
+#endif
 __device__ __forceinline__ void hs_st256(void *p, const uint4 a, const uint4 b)
 {
 #if HS_ST256_POLICY == 1
@@ -593,6 +596,63 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     }
                     if ((FLAGS & HS_LF_REC) && rec) st_wr += nrec;
                 }
+#if HS_LANE_PREDICATED
+                /* Every state variable is updated by a select, the memory operations are predicated: no branch,
+                 * hence no reconvergence point and no register shuffling where the two chains used to meet again. */
+                const bool isC = !isA;
+                /* Source: payload index c0, next SourceEvent index c0 + 1 (source.py:166-170) */
+                arr_draws += isA ? 1ull : 0ull;
+                tT = isA ? tT_next : tT;
+                iT = isA ? c0 + 1 : iT;
+                /* Server resumes after its yield, the Sink takes the request (server.py:255-273, common.py:36-44) */
+                {
+                    const double ts_ = HS_ADD(total_service, svc_s);
+                    total_service = isC ? ts_ : total_service;
+                    const int64_t dlat_ = now - c_created;
+                    const double lat_ = hs_ns_to_seconds(dlat_);
+                    if (isC && hist) atomicAdd(hist + hs_latency_bin(dlat_), 1u);
+                    {   /* hs_neumaier_add, branch-free: c += (hi - t) + lo with (hi, lo) = (s, x) ordered by magnitude */
+                        const double t_ = HS_ADD(sum, lat_);
+                        const bool big_ = hs_fabs(sum) >= hs_fabs(lat_);
+                        const double hi_ = big_ ? sum : lat_, lo_ = big_ ? lat_ : sum;
+                        const double c2_ = HS_ADD(comp, HS_ADD(HS_SUB(hi_, t_), lo_));
+                        sum = isC ? t_ : sum; comp = isC ? c2_ : comp;
+                    }
+                    const double q2_ = HS_ADD(sumsq, HS_MUL(lat_, lat_));
+                    sumsq = isC ? q2_ : sumsq;
+                    mn = (isC && lat_ < mn) ? lat_ : mn;
+                    mx = (isC && lat_ > mx) ? lat_ : mx;
+                    if (isC && (FLAGS & HS_LF_REC) && smp) {
+                        uint4 w_; const uint64_t lb_ = (uint64_t)__double_as_longlong(lat_);
+                        w_.x = (uint32_t)(uint64_t)now; w_.y = (uint32_t)((uint64_t)now >> 32);
+                        w_.z = (uint32_t)lb_; w_.w = (uint32_t)(lb_ >> 32);
+                        HS_SMP_STORE(w_);
+                    }
+                }
+                /* Queue: the request waits (arrival, no service start) / the head is delivered (completion with a start) */
+                const bool do_push = isA && !start, do_pop = isC && start;
+                if (do_push) {
+                    hs_ring_entry e_; e_.created = now; e_.idx = c0;
+                    ring[(q_head + q_len) & ring_mask] = e_;
+                    if (q_empty) *my_head = e_;
+                }
+                q_len = q_len + (do_push ? 1u : 0u) - (do_pop ? 1u : 0u);
+                q_head = do_pop ? (q_len == 0 ? 0u : q_head + 1u) : q_head;      /* an empty queue restarts at slot 0 */
+                if (do_pop && q_len > 0) {
+                    const hs_ring_entry *n_ = ring + (q_head & ring_mask);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
+                                 :: "r"(my_head_s), "l"(n_) : "memory");
+                }
+                /* Server.handle_queued_event up to its yield (server.py:217-253): the scheduled ProcessContinuation
+                 * takes the last index of the chain */
+                if (start && (FLAGS & HS_LF_REC) && svc_out) HS_SVC_STORE(sv_next);
+                n_svc += start ? 1 : 0;
+                tC = start ? now + hs_seconds_to_ns(sv_next) : tC;
+                iC = start ? ctr - 1 : iC;
+                c_created = start ? start_created : c_created;
+                svc_s = start ? sv_next : svc_s;
+                active = start ? 1 : (isA ? active : 0);
+#else
                 if (isA) {
                     /* Source: payload index c0, next SourceEvent index c0 + 1 (source.py:166-170) */
                     arr_draws++; tT = tT_next; iT = c0 + 1;
@@ -625,6 +685,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     n_svc++;
                     tC = now + hs_seconds_to_ns(sv_); iC = ctr - 1; c_created = start_created; svc_s = sv_; active = 1;
                 }
+#endif
                 continue;
             }
         }

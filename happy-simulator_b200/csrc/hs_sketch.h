@@ -26,6 +26,7 @@
 /* bytes of one replica's state of a SKETCH row (multiple of 16) */
 static inline uint64_t hs_sketch_row_bytes(const hs_entity_desc *d)
 {
+    if (d->kind == HS_ENT_CACHE_SERVER) return (((uint64_t)d->i0 + 1u) * 8u + 15u) / 16u * 16u;   /* double insert_s[K + 1] */
     if (d->kind != HS_ENT_SKETCH) return 0;
     if (d->i0 == HS_SK_HLL) return (uint64_t)1 << d->i2;                       /* uint8 registers[2^p], p >= 4 */
     if (d->i0 == HS_SK_BLOOM) return (((uint64_t)d->i3 + 63u) / 64u * 8u + 15u) / 16u * 16u;   /* uint64 words */
@@ -50,7 +51,7 @@ static inline void hs_sketch_layout_impl(const hs_model_desc *m, uint64_t *per_r
     uint64_t a = 0, b = 0;
     for (uint32_t i = 0; i < m->n_entities; ++i) {
         const hs_entity_desc *d = &m->entities[i];
-        if (per_replica) per_replica[i] = d->kind == HS_ENT_SKETCH ? a : 0;
+        if (per_replica) per_replica[i] = (d->kind == HS_ENT_SKETCH || d->kind == HS_ENT_CACHE_SERVER) ? a : 0;
         if (merged) merged[i] = d->kind == HS_ENT_SKETCH ? b : 0;
         a += hs_sketch_row_bytes(d);
         b += hs_sketch_row_merged_bytes(d);

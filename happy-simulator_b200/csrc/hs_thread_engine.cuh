@@ -149,6 +149,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             hs_went *e = &E[i];
             e->d0 = M.n_cells ? M.cell_d0[(size_t)cell * ne + i] : d.d0;
             e->i0 = M.n_cells ? M.cell_i0[(size_t)cell * ne + i] : d.i0;
+            if (d.kind == HS_ENT_CACHE_SERVER) e->i0 = 0x7fffffff;          /* Entity.has_capacity() is True: no limit */
             e->lambda = (d.kind == HS_ENT_SERVER && d.i2 == HS_SVC_EXPONENTIAL) ? HS_DIV(1.0, e->d0) : 0.0;
             if (d.kind == HS_ENT_SINK || d.kind == HS_ENT_PROBE) {
                 e->u.snk.mn = __longlong_as_double(0x7ff0000000000000LL);
@@ -242,7 +243,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             int k = (int)(ev.m0 & 0xffu);
             if (k == (int)HS_EV_REQ_ANY) {
                 const int ek = ENTS[ev.m0 >> 8].kind;
-                k = ek == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE : ek == HS_ENT_SINK ? HS_EV_REQ_SINK :
+                k = (ek == HS_ENT_SERVER || ek == HS_ENT_CACHE_SERVER) ? HS_EV_REQ_ENQUEUE : ek == HS_ENT_SINK ? HS_EV_REQ_SINK :
                     ek == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : ek == HS_ENT_PROBE ? HS_EV_PROBE :
                     ek == HS_ENT_SKETCH ? HS_EV_REQ_SKETCH : HS_EV_REQ_LB;
             }
@@ -405,7 +406,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 fp.m0 = (uint32_t)HS_EV_CONTINUATION | ((uint32_t)be << 8); fp.key = key; fp.hook = 0x80000000u; fp.pad = 0u;
                 heap_insert(fk, fp);
             } else if (!drop) {
-                const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1);
+                const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1) & 0xffffffu;
                 hs_wring_entry *rg = ring0 + (size_t)srv_idx * P.ring;
                 hs_wring_entry q; q.created = now; q.idx = idxE; q.key = key;
                 rg[(q_head + q_len) & ring_mask] = q;
@@ -418,6 +419,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         }
         if (k0 == HS_EV_CONTINUATION) {
             const hs_entity_desc dv = ENTS[ent];
+            if (dv.kind != HS_ENT_SERVER) return false;               /* e.g. a CachingServer's multi-yield generator */
             const int tgt = dv.target;
             int tkind = 0;
             if (tgt >= 0) { tkind = ENTS[tgt].kind; if (tkind != HS_ENT_SINK && tkind != HS_ENT_COUNTER) return false; }
@@ -436,7 +438,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 svc_s = hs_ns_to_seconds(dur);
                 resume_t = hs_resume_ns(now, svc_s);
                 if (resume_t <= now) return false;
-                const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1);
+                const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1) & 0xffffffu;
                 const hs_wring_entry *rg = ring0 + (size_t)srv_idx * P.ring;
                 q = rg[(dv.i1 == HS_Q_LIFO ? q_head + q_len - 1 : q_head) & ring_mask];
             }
@@ -512,7 +514,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
 #pragma unroll
           for (int i = 0; i < 6; ++i) xu.q[i] = g[i]; }
         hs_went *X = &xu.w;
-        const uint32_t srv_idx = (uint32_t)__double_as_longlong(du.d.d1);   /* patched in by the host, see hs_model_upload */
+        const uint32_t srv_idx = (uint32_t)__double_as_longlong(du.d.d1) & 0xffffffu;   /* patched in by the host, see hs_model_upload */
         hdr.now = now;
         if (FLAGS & HS_WF_HASH) hdr.hash = hs_hash_step(hdr.hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
         if ((FLAGS & HS_WF_REC) && rec) {
@@ -597,7 +599,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             else { int k = (int)(ev.m0 & 0xffu);
                    if (k == (int)HS_EV_REQ_ANY) {
                        const int ek = ENTS[ev.m0 >> 8].kind;
-                       k = ek == HS_ENT_SERVER ? HS_EV_REQ_ENQUEUE : ek == HS_ENT_SINK ? HS_EV_REQ_SINK :
+                       k = (ek == HS_ENT_SERVER || ek == HS_ENT_CACHE_SERVER) ? HS_EV_REQ_ENQUEUE : ek == HS_ENT_SINK ? HS_EV_REQ_SINK :
                            ek == HS_ENT_COUNTER ? HS_EV_REQ_COUNTER : ek == HS_ENT_PROBE ? HS_EV_PROBE :
                            ek == HS_ENT_SKETCH ? HS_EV_REQ_SKETCH : HS_EV_REQ_LB;
                    }
@@ -641,6 +643,8 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             case HS_ENT_SOURCE: a.c0 = e->u.src.generated; a.c1 = e->u.src.provider; break;
             case HS_ENT_SERVER: a.c0 = e->u.srv.accepted; a.c1 = e->u.srv.dropped; a.c2 = e->u.srv.completed;
                 a.c3 = e->u.srv.rejected; a.f0 = e->u.srv.total_service; break;
+            case HS_ENT_CACHE_SERVER: a.c0 = e->u.srv.accepted; a.c1 = e->u.srv.dropped; a.c2 = e->u.srv.completed;
+                a.c3 = e->u.srv.rejected; a.f0 = (double)e->u.srv.svc_draws; a.f1 = (double)e->u.srv.pad; break;   /* misses, hits, size */
             case HS_ENT_SINK: a.c0 = e->u.snk.received; a.f0 = hs_neumaier_result(e->u.snk.sum, e->u.snk.comp);
                 a.f1 = e->u.snk.sumsq; a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
             case HS_ENT_COUNTER: a.c0 = e->u.snk.received; break;

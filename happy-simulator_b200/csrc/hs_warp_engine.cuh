@@ -235,6 +235,7 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                 e->d0 = M.n_cells ? M.cell_d0[(size_t)cell * ne + i] : d.d0;
                 e->i0 = M.n_cells ? M.cell_i0[(size_t)cell * ne + i] : d.i0;
                 e->lambda = (d.kind == HS_ENT_SERVER && d.i2 == HS_SVC_EXPONENTIAL) ? HS_DIV(1.0, e->d0) : 0.0;
+                if (d.kind == HS_ENT_CACHE_SERVER) e->i0 = 0x7fffffff;      /* Entity.has_capacity() is True: no limit */
                 if (d.kind == HS_ENT_SINK || d.kind == HS_ENT_PROBE) {
                     e->u.snk.mn = __longlong_as_double(0x7ff0000000000000LL);
                     e->u.snk.mx = __longlong_as_double(0xfff0000000000000LL);
@@ -413,6 +414,8 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
                 case HS_ENT_SOURCE: a.c0 = e->u.src.generated; a.c1 = e->u.src.provider; break;
                 case HS_ENT_SERVER: a.c0 = e->u.srv.accepted; a.c1 = e->u.srv.dropped; a.c2 = e->u.srv.completed;
                     a.c3 = e->u.srv.rejected; a.f0 = e->u.srv.total_service; break;
+                case HS_ENT_CACHE_SERVER: a.c0 = e->u.srv.accepted; a.c1 = e->u.srv.dropped; a.c2 = e->u.srv.completed;
+                    a.c3 = e->u.srv.rejected; a.f0 = (double)e->u.srv.svc_draws; a.f1 = (double)e->u.srv.pad; break;   /* misses, hits, size */
                 case HS_ENT_SINK: a.c0 = e->u.snk.received; a.f0 = hs_neumaier_result(e->u.snk.sum, e->u.snk.comp);
                     a.f1 = e->u.snk.sumsq; a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
                 case HS_ENT_COUNTER: a.c0 = e->u.snk.received; break;

@@ -283,6 +283,9 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None, 
             return "probe" if _cls(o._event_provider) == "_ProbeEventProvider" else A.HS_ENT_SOURCE
         if hasattr(o, "_concurrency_model") and hasattr(o, "_service_time") and hasattr(o, "_queue"):
             return A.HS_ENT_SERVER
+        if all(hasattr(o, a) for a in ("_cache_capacity", "_cache_ttl_s", "_cache_read_latency_s",
+                                       "_datastore_read_latency_s", "_processing_latency_s", "_queue")):
+            return A.HS_ENT_CACHE_SERVER          # examples/load-balancing/common.py:100 CachingServer (or the mirror)
         if hasattr(o, "latencies_s") and hasattr(o, "events_received"):
             return A.HS_ENT_SINK
         if hasattr(o, "data") and hasattr(o, "count") and hasattr(getattr(o, "data"), "_samples") and \
@@ -296,7 +299,7 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None, 
                 and hasattr(o, "_events_processed"):
             return A.HS_ENT_SKETCH
         raise UnsupportedModelError(f"entity {getattr(o, 'name', o)!r} of type {n} cannot be lowered to the device "
-                                    "engine (supported: Source, Server, Sink, Counter, LoadBalancer, SketchCollector)")
+                                    "engine (supported: Source, Server, CachingServer, Sink, Counter, LoadBalancer, SketchCollector)")
 
     # discover downstream objects (they may be missing from entities=, as in the reference)
     i = 0
@@ -358,6 +361,23 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None, 
             ds = o._downstream
             b.server(name, concurrency=int(cm.limit), mean_service_s=mean, exponential=(skind == A.HS_SVC_EXPONENTIAL),
                      downstream=-1 if ds is None else ids[id(ds)], capacity=cap, lifo=(pol == A.HS_Q_LIFO))
+        elif k == A.HS_ENT_CACHE_SERVER:
+            pol, cap = _queue_policy(o._queue)
+            if cap >= 0:
+                raise UnsupportedModelError(f"caching server {name!r}: bounded queue")
+            pop = key_population or max((int(getattr(getattr(s_._event_provider, "_context_fn", None), "key_population", 0))
+                                         for s_ in sources or []), default=0)
+            if pop <= 0:
+                raise UnsupportedModelError(f"caching server {name!r}: the cache key is the request's customer id -- the "
+                                            "source needs a finite key population (UniformKeyContext / ZipfKeyContext)")
+            if int(o._cache_capacity) <= pop:
+                raise UnsupportedModelError(f"caching server {name!r}: cache_capacity {int(o._cache_capacity)} <= key population "
+                                            f"{pop}: the cache could fill, and the reference's CachingServer raises "
+                                            "FrozenInstanceError on its first eviction (examples/load-balancing/common.py:264)")
+            b.cache_server(name, key_slots=pop, cache_ttl_s=float(o._cache_ttl_s),
+                           cache_read_latency_s=float(o._cache_read_latency_s),
+                           datastore_read_latency_s=float(o._datastore_read_latency_s),
+                           processing_latency_s=float(o._processing_latency_s), lifo=(pol == A.HS_Q_LIFO))
         elif k == A.HS_ENT_SINK:
             b.sink(name)
         elif k == A.HS_ENT_COUNTER:

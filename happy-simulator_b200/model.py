@@ -44,6 +44,10 @@ class FlatModel:
         per, mer, a, b = [0] * self.n_entities, [0] * self.n_entities, 0, 0
         for i in range(self.n_entities):
             e = self.entities[i]
+            if int(e["kind"]) == A.HS_ENT_CACHE_SERVER:       # double insert_s[K + 1]; not merged
+                per[i], mer[i] = a, b
+                a += ((int(e["i0"]) + 1) * 8 + 15) // 16 * 16
+                continue
             if int(e["kind"]) != A.HS_ENT_SKETCH:
                 continue
             per[i], mer[i] = a, b
@@ -85,6 +89,13 @@ class FlatModel:
                 d, w = int(e["i2"]), int(e["i3"])
                 out[i] = np.ascontiguousarray(raw[:, per[i]: per[i] + d * w * 4]).view(np.uint32).reshape(-1, d, w)
         return out
+
+    def cache_views(self, raw: np.ndarray) -> dict:
+        """Per-replica TTL-cache states out of hs_outputs.sketches: {entity id: float64[n, K + 1] insertion times in
+        seconds (0 = not cached; the last slot is the key-less "unknown" customer)}."""
+        per = self.sketch_layout()[0]
+        return {i: np.ascontiguousarray(raw[:, per[i]: per[i] + 8 * (int(self.entities[i]["i0"]) + 1)]).view(np.float64)
+                for i in self.ids_of(A.HS_ENT_CACHE_SERVER)}
 
     def canonical_sketches(self, raw: np.ndarray) -> np.ndarray:
         """Copy of hs_outputs.sketches with the dead parts of TDIGEST rows zeroed (centroid slots past
@@ -225,6 +236,15 @@ class ModelBuilder:
                          A.HS_Q_LIFO if lifo else A.HS_Q_FIFO,
                          A.HS_SVC_EXPONENTIAL if exponential else A.HS_SVC_CONSTANT,
                          int(capacity), float(mean_service_s))
+
+    def cache_server(self, name="CachingServer", *, key_slots, cache_ttl_s=30.0, cache_read_latency_s=0.0001,
+                     datastore_read_latency_s=0.005, processing_latency_s=0.001, lifo=False):
+        """examples/load-balancing/common.py:100-275 CachingServer: ``key_slots`` = K cache entries for keys 0..K-1
+        (the cache must be larger than the key population, see include/hs_b200.h).  The delays are stored as the
+        nanosecond counts the reference adds to `now`: int(delay_s * 1e9) (core/temporal.py:221-222)."""
+        return self._add(name, A.HS_ENT_CACHE_SERVER, -1, int(key_slots), A.HS_Q_LIFO if lifo else A.HS_Q_FIFO,
+                         int(cache_read_latency_s * 1e9), int(datastore_read_latency_s * 1e9), float(cache_ttl_s),
+                         i3=int(processing_latency_s * 1e9))
 
     def sink(self, name="Sink"):
         return self._add(name, A.HS_ENT_SINK)

@@ -50,9 +50,22 @@ enum {
     HS_ENT_LB = 5,       /* components/load_balancer/load_balancer.py:60 LoadBalancer               */
     HS_ENT_PROBE = 6,    /* instrumentation/probe.py:81 Probe's measurement callback (the Probe's own
                             ticking is a SOURCE row with a constant profile on the general path)     */
-    HS_ENT_SKETCH = 7    /* components/sketching/sketch_collector.py:24 SketchCollector over a HyperLogLog
+    HS_ENT_SKETCH = 7,   /* components/sketching/sketch_collector.py:24 SketchCollector over a HyperLogLog
                             (sketching/hyperloglog.py:43) or CountMinSketch (count_min_sketch.py:52) whose
                             value_extractor reads the request's routing key                           */
+    HS_ENT_CACHE_SERVER = 8 /* examples/load-balancing/common.py:100-275 CachingServer: a QueuedResource without a
+                            concurrency limit (Entity.has_capacity() is True) whose generator yields the cache-read
+                            latency, on a miss the datastore latency, then the processing latency; one TTL cache
+                            entry per customer key (TTLEviction, components/datastore/eviction_policies.py:154-226).
+                            i0 = number of key slots K (keys 0..K-1; a request without a key uses slot K),
+                            i1 = HS_Q_*, i2 / i3 = int(cache_read_latency_s * 1e9) / int(processing_latency_s * 1e9),
+                            l0 = int(datastore_read_latency_s * 1e9), d0 = cache TTL (s), target = -1 (the generator
+                            returns []).  The cache must be larger than the key population: the example raises
+                            FrozenInstanceError on its first eviction (common.py:264), so eviction is not a
+                            behaviour to reproduce and the lowering rejects such models.  Per-replica state: K + 1
+                            insertion times (seconds; 0 = not cached), in the hs_outputs.sketches region.
+                            hs_entity_stats: c0 accepted, c1 dropped, c2 requests_processed, c3 cache_misses,
+                            f0 cache_hits, f1 cache_size (as doubles)                                   */
 };
 /* Sketch algorithms of a SKETCH row.  Both hash the item with SHA-256 (hyperloglog.py:128-135,
  * count_min_sketch.py:136-155); the items are the routing keys 0..population-1, so the host evaluates

@@ -63,6 +63,7 @@ typedef struct oev {
     int32_t lb_hook;     /* LoadBalancer on_complete hook: LB entity id, -1 none  */
     int32_t poll_hook;   /* QueueDriver schedule_poll hook: server id, -1 none    */
     double svc_s;        /* CONTINUATION: the service time the generator yielded  */
+    int32_t stage;       /* CONTINUATION at a CachingServer: which yield resumes (1, 2, 3) | was_in_cache << 8 */
     uint64_t payload_idx;/* DELIVER: _sort_index of the payload Event it carries  */
 } oev;
 
@@ -146,6 +147,10 @@ typedef struct oent {
     uint32_t lb_next_request_id;
     /* SKETCH */
     int64_t sk_processed, sk_added;   /* SketchCollector._events_processed, sketch._total_count */
+    /* CACHE_SERVER */
+    double *cache_ins;                /* TTLEviction._insert_times per key slot (seconds; 0 = not cached)    */
+    int64_t cache_hits, cache_misses, cache_size;
+    int cache_own;                    /* cache_ins is a private allocation (no hs_outputs.sketches buffer)   */
     uint8_t *sk_state;                /* this replica's registers / counters (in hs_outputs.sketches) */
 } oent;
 
@@ -207,7 +212,7 @@ static oev new_event(orun *R, int64_t time, int kind, int ent)   /* Event.__init
 static int request_kind_for(const orun *R, int ent)
 {
     switch (R->ents[ent].d.kind) {
-    case HS_ENT_SERVER: return HS_EV_REQ_ENQUEUE;
+    case HS_ENT_SERVER: case HS_ENT_CACHE_SERVER: return HS_EV_REQ_ENQUEUE;
     case HS_ENT_SINK: return HS_EV_REQ_SINK;
     case HS_ENT_COUNTER: return HS_EV_REQ_COUNTER;
     case HS_ENT_LB: return HS_EV_REQ_LB;
@@ -244,7 +249,7 @@ static int64_t next_arrival(orun *R, int sid, oent *s)
 static void run_poll_hook(orun *R, int server)
 {
     oent *s = &R->ents[server];
-    if (s->active < s->d.i0) {            /* target.has_capacity()                */
+    if (s->d.kind == HS_ENT_CACHE_SERVER || s->active < s->d.i0) {   /* target.has_capacity(); Entity's default is True */
         oev p = new_event(R, R->now, HS_EV_POLL, server);
         heap_push(&R->heap, &p);
     }
@@ -309,7 +314,8 @@ static void handle(orun *R, oev *e)
     }
     case HS_EV_REQ_ENQUEUE: {             /* Queue._handle_enqueue, queue.py:122-147 */
         int was_empty = (E->q_len == 0);
-        int accepted = !(E->d.l0 >= 0 && (int64_t)E->q_len >= E->d.l0);  /* queue_policy.py:94-98 */
+        const int64_t qcap = E->d.kind == HS_ENT_CACHE_SERVER ? -1 : E->d.l0;   /* CachingServer: FIFOQueue(), unbounded */
+        int accepted = !(qcap >= 0 && (int64_t)E->q_len >= qcap);        /* queue_policy.py:94-98 */
         if (!accepted) {
             E->dropped++;
         } else {
@@ -325,7 +331,7 @@ static void handle(orun *R, oev *e)
         break;
     }
     case HS_EV_NOTIFY:                    /* QueueDriver._handle_notify, :92-99  */
-        if (E->active < E->d.i0) {
+        if (E->d.kind == HS_ENT_CACHE_SERVER || E->active < E->d.i0) {
             oev p = new_event(R, R->now, HS_EV_POLL, e->ent);
             heap_push(&R->heap, &p);
         }
@@ -350,6 +356,20 @@ static void handle(orun *R, oev *e)
     }
     case HS_EV_REQ_WORKER: {              /* Server.handle_queued_event first step */
         R->counter++;                     /* inline ProcessContinuation, event.py:314-325 */
+        if (E->d.kind == HS_ENT_CACHE_SERVER) {
+            /* CachingServer.handle_queued_event up to its first yield (examples/load-balancing/common.py:197-213):
+             * was_in_cache = key in cache and not TTLEviction.is_expired(key) (eviction_policies.py:215-226, clock =
+             * self.now.to_seconds()); then `yield cache_read_latency_s` -> ProcessContinuation at now + int(delay * 1e9) */
+            E->active++;
+            const int slot = e->key >= 0 && e->key < E->d.i0 ? e->key : E->d.i0;       /* no customer id: "unknown" */
+            const double ins = E->cache_ins[slot];
+            const int was_in = ins != 0.0 && !(hs_ns_to_seconds(R->now) - ins >= E->d.d0);
+            oev c = new_event(R, R->now + (int64_t)E->d.i2, HS_EV_CONTINUATION, e->ent);
+            c.created_at = e->created_at; c.req_id = e->req_id; c.key = e->key;
+            c.poll_hook = e->poll_hook; c.stage = 1 | (was_in << 8);
+            heap_push(&R->heap, &c);
+            break;
+        }
         if (E->active >= E->d.i0) {       /* acquire failed, server.py:223-234   */
             E->rejected++;
             R->status |= HS_ST_REJECT_PATH;
@@ -379,6 +399,29 @@ static void handle(orun *R, oev *e)
         break;
     }
     case HS_EV_CONTINUATION: {            /* generator resumes, server.py:255-273 */
+        if (E->d.kind == HS_ENT_CACHE_SERVER) {               /* common.py:215-232 */
+            const int stage = e->stage & 0xff, was_in = (e->stage >> 8) & 1;
+            const int slot = e->key >= 0 && e->key < E->d.i0 ? e->key : E->d.i0;
+            int next_stage = 0; int64_t delay = 0;
+            if (stage == 1) {
+                if (was_in) { E->cache_hits++; next_stage = 3; delay = (int64_t)E->d.i3; }     /* on_access: TTL ignores it */
+                else { E->cache_misses++; next_stage = 2; delay = E->d.l0; }                  /* yield datastore latency  */
+            } else if (stage == 2) {          /* _populate_cache: cache[key] = value; on_insert(key) records the time */
+                if (E->cache_ins[slot] == 0.0) E->cache_size++;
+                E->cache_ins[slot] = hs_ns_to_seconds(R->now);
+                next_stage = 3; delay = (int64_t)E->d.i3;
+            } else {                          /* requests_processed += 1; return [] -> completion hooks */
+                E->completed++;
+                E->active = E->active > 0 ? E->active - 1 : 0;
+                if (e->poll_hook >= 0) run_poll_hook(R, e->poll_hook);
+                break;
+            }
+            oev c = new_event(R, R->now + delay, HS_EV_CONTINUATION, e->ent);
+            c.created_at = e->created_at; c.req_id = e->req_id; c.key = e->key;
+            c.poll_hook = e->poll_hook; c.stage = next_stage;
+            heap_push(&R->heap, &c);
+            break;
+        }
         E->active = E->active > 0 ? E->active - 1 : 0;    /* FixedConcurrency.release */
         E->completed++;
         E->total_service += e->svc_s;
@@ -486,8 +529,16 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
         if (out->sketches && total) {
             uint8_t *base = out->sketches + (size_t)r * total;
             memset(base, 0, total);
-            for (uint32_t i = 0; i < ne; ++i) if (R.ents[i].d.kind == HS_ENT_SKETCH) R.ents[i].sk_state = base + off[i];
+            for (uint32_t i = 0; i < ne; ++i) {
+                if (R.ents[i].d.kind == HS_ENT_SKETCH) R.ents[i].sk_state = base + off[i];
+                if (R.ents[i].d.kind == HS_ENT_CACHE_SERVER) R.ents[i].cache_ins = (double *)(base + off[i]);
+            }
         }
+        for (uint32_t i = 0; i < ne; ++i)     /* the cache is state the run needs, with or without an output buffer */
+            if (R.ents[i].d.kind == HS_ENT_CACHE_SERVER && !R.ents[i].cache_ins) {
+                R.ents[i].cache_ins = (double *)calloc((size_t)R.ents[i].d.i0 + 1, sizeof(double));
+                R.ents[i].cache_own = 1;
+            }
         free(off);
     }
     if (out->records) R.rec = out->records + (size_t)r * p->record_cap;
@@ -562,12 +613,15 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
             case HS_ENT_PROBE:
                 st->c0 = E->received; st->f0 = hs_neumaier_result(E->sum, E->comp); st->f2 = E->mn; st->f3 = E->mx; break;
             case HS_ENT_SKETCH: st->c0 = E->sk_processed; st->c1 = E->sk_added; break;
+            case HS_ENT_CACHE_SERVER:
+                st->c0 = E->accepted; st->c1 = E->dropped; st->c2 = E->completed; st->c3 = E->cache_misses;
+                st->f0 = (double)E->cache_hits; st->f1 = (double)E->cache_size; break;
             case HS_ENT_LB:
                 st->c0 = E->lb_received; st->c1 = E->lb_forwarded; st->c2 = E->lb_in_flight; st->c3 = E->lb_responses; break;
             }
         }
     }
-    for (uint32_t i = 0; i < ne; ++i) free(R.ents[i].q);
+    for (uint32_t i = 0; i < ne; ++i) { free(R.ents[i].q); if (R.ents[i].cache_own) free(R.ents[i].cache_ins); }
     free(R.ents); free(R.heap.a);
 }
 

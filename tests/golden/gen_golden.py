@@ -224,6 +224,22 @@ def step_profiled(profile_obj, end_s, mean_service_s=0.1, stop_after_s=None):
     return b.build(), {src: profile_obj}
 
 
+def cache_farm(n_servers, K, rate, ttl_s, vnodes=None, poisson=True):
+    """examples/load-balancing/consistent_hashing_basics.py:161-255: Source (customer ids ~ Uniform{0..K-1}) ->
+    LoadBalancer(ConsistentHash | RoundRobin) -> n x CachingServer(TTL cache over a shared datastore)."""
+    names = [f"Server_{i}" for i in range(n_servers)]
+    b = hs.ModelBuilder()
+    src = b.source(rate=rate, key_population=K, poisson=poisson)
+    servers = [b.cache_server(nm, key_slots=K, cache_ttl_s=ttl_s) for nm in names]
+    if n_servers == 1:
+        b.set_target(src, servers[0])
+        return b.build()
+    tab = RH.ring_table_from_reference(names, vnodes, K) if vnodes else None
+    lb = b.load_balancer(backends=servers, key_table=tab)
+    b.set_target(src, lb)
+    return b.build()
+
+
 def philox_cases():
     c = {}
     c["mm1_seed0"] = (hs.mm1(), dict(seed=0, rid=0, end_s=60))
@@ -258,6 +274,10 @@ def philox_cases():
     c["sketch_tdigest"] = (sketch_quantiles(), dict(seed=29, rid=0, end_s=40))
     m, zs = zipf_hot_keys()
     c["zipf_chash_topk"] = (m, dict(seed=37, rid=5, end_s=6, chash_vnodes=30, zipf_s=zs))
+    # SURVEY 8(f) row 4, second half: CachingServer / TTL cache behind the two load-balancing strategies
+    c["cache_direct_ttl"] = (cache_farm(1, 3, 10.0, 0.5, poisson=False), dict(seed=5, rid=0, end_s=6))
+    c["cache_chash5"] = (cache_farm(5, 40, 200.0, 0.8, vnodes=30), dict(seed=41, rid=2, end_s=6, chash_vnodes=30))
+    c["cache_rr5"] = (cache_farm(5, 40, 200.0, 0.8), dict(seed=41, rid=2, end_s=6))
     # a user-defined step profile: the example's MetastableLoadProfile, its whole 130 s scenario
     m, po = step_profiled(example_metastable_profile(), 130.0, stop_after_s=120.0)
     c["step_metastable_mm1"] = (m, dict(seed=42, rid=0, end_s=130, profile_objects=po))

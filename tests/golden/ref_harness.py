@@ -69,6 +69,17 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     from happysimulator.components.sketching.topk_collector import TopKCollector
     from happysimulator.components.sketching.quantile_estimator import QuantileEstimator
 
+    CachingServer = KVStore = None
+    if (model.entities["kind"] == A.HS_ENT_CACHE_SERVER).any():
+        # the example's own class, imported from the example file (examples/load-balancing/common.py:100-275)
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_lb_common", os.path.join(REFERENCE_ROOT, "examples", "load-balancing", "common.py"))
+        lbmod = importlib.util.module_from_spec(spec)
+        sys.modules["ref_lb_common"] = lbmod
+        spec.loader.exec_module(lbmod)
+        CachingServer = lbmod.CachingServer
+        from happysimulator.components.datastore.kv_store import KVStore
+
     L = O.lib()
     ents = model.entities
     n = model.n_entities
@@ -121,6 +132,20 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             else:
                 sk = CountMinSketch(width=int(e["i3"]), depth=int(e["i2"]), seed=sk_seed)
             objs[i] = SketchCollector(names[i], sketch=sk, value_extractor=extract)
+    datastore = None
+    for i in range(n):
+        if int(ents["kind"][i]) != A.HS_ENT_CACHE_SERVER:
+            continue
+        e = ents[i]
+        if datastore is None:
+            datastore = KVStore(name="SharedDatastore", read_latency=0.005, write_latency=0.010)
+        lat = [int(e["i2"]) / 1e9, int(e["l0"]) / 1e9, int(e["i3"]) / 1e9]
+        assert [int(x * 1e9) for x in lat] == [int(e["i2"]), int(e["l0"]), int(e["i3"])], "delays must round-trip through seconds"
+        assert int(e["i1"]) == A.HS_Q_FIFO
+        # capacity K + 1 > key population K: the example cannot evict (common.py:264 raises on its first eviction)
+        objs[i] = CachingServer(names[i], server_id=i, datastore=datastore, cache_capacity=int(e["i0"]) + 1,
+                                cache_ttl_s=float(e["d0"]), cache_read_latency_s=lat[0], datastore_read_latency_s=lat[1],
+                                processing_latency_s=lat[2])
     for i in range(n):
         if int(ents["kind"][i]) != A.HS_ENT_SERVER:
             continue
@@ -225,7 +250,7 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     oid = {}
     for i, o in enumerate(objs):
         oid[id(o)] = i
-        if int(ents["kind"][i]) == A.HS_ENT_SERVER:
+        if int(ents["kind"][i]) in (A.HS_ENT_SERVER, A.HS_ENT_CACHE_SERVER):
             oid[id(o.queue)] = i
             oid[id(o.driver)] = i
             oid[id(o.worker)] = i
@@ -253,7 +278,7 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             return A.HS_EV_LB_RESPONSE
         if isinstance(t, _QueuedResourceWorkerAdapter):
             return A.HS_EV_REQ_WORKER
-        if isinstance(t, Server):
+        if isinstance(t, Server) or (CachingServer is not None and isinstance(t, CachingServer)):
             return A.HS_EV_REQ_ENQUEUE
         if isinstance(t, Sink):
             return A.HS_EV_REQ_SINK
@@ -315,6 +340,10 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             stats[i]["c0"], stats[i]["c1"] = o.stats_accepted, o.stats_dropped
             stats[i]["c2"], stats[i]["c3"], stats[i]["f0"] = st.requests_completed, st.requests_rejected, st.total_service_time
             per_server_service[i] = list(o._service_times)
+        elif k == A.HS_ENT_CACHE_SERVER:
+            stats[i]["c0"], stats[i]["c1"] = o.stats_accepted, o.stats_dropped
+            stats[i]["c2"], stats[i]["c3"] = o.stats.requests_processed, o.stats.cache_misses
+            stats[i]["f0"], stats[i]["f1"] = float(o.stats.cache_hits), float(o.cache_size)
         elif k == A.HS_ENT_SINK:
             stats[i]["c0"] = o.events_received
             s2 = 0.0
@@ -348,8 +377,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
             merged.append((by_id[ent][0][c], by_id[ent][1][c]))
             cursors[ent] = c + 1
         elif kind == A.HS_EV_REQ_WORKER:
-            c = svc_cursor[ent]
-            if c < len(per_server_service[ent]):
+            c = svc_cursor.get(ent, 0)
+            if ent in per_server_service and c < len(per_server_service[ent]):
                 svc_merged.append(per_server_service[ent][c])
                 svc_cursor[ent] = c + 1
     smp = np.zeros(len(merged), A.SAMPLE_DTYPE)
@@ -368,6 +397,16 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
     if total:
         img = np.zeros(total, np.uint8)
         for i, o in enumerate(objs):
+            if int(ents["kind"][i]) == A.HS_ENT_CACHE_SERVER:     # TTLEviction._insert_times, one slot per customer key
+                K = int(ents["i0"][i])
+                ins = np.zeros(K + 1, np.float64)
+                pol = o._eviction_policy
+                for key, t in (pol._insert_times.items() if pol is not None else ()):
+                    cid = key.split(":", 1)[1]
+                    ins[K if cid == "unknown" else int(cid)] = t
+                assert set(o._cache._cache) == set(pol._insert_times) if pol is not None else True
+                img[per[i]: per[i] + ins.size * 8] = ins.view(np.uint8)
+                continue
             if int(ents["kind"][i]) != A.HS_ENT_SKETCH:
                 continue
             algo = int(ents["i0"][i])

@@ -63,5 +63,5 @@ def test_model_validation_errors(lib):
     with pytest.raises(engine.EngineError, match="out of range"):
         engine.validate_model(bad)
     bad = hs.lb_round_robin(4, 32.0); bad.backends[2] = 0           # a Source as backend
-    with pytest.raises(engine.EngineError, match="must be a Server, Sink or Counter"):
+    with pytest.raises(engine.EngineError, match="must be a Server, CachingServer, Sink or Counter"):
         engine.validate_model(bad)

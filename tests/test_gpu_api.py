@@ -333,3 +333,27 @@ def test_probes_sample_queue_depth_like_the_reference():
     assert [round(t * 1e9) for t in depth.times()[:4]] == [100000000, 200000000, 299999999, 399999998]
     assert seen.raw_values() == sorted(seen.raw_values()) and seen.raw_values()[-1] <= sink.events_received
     assert p1.generated_count == int(st[1]["c0"])
+
+
+@pytest.mark.parametrize("fixture,strategy", [("philox_cache_chash5", "chash"), ("philox_cache_rr5", "rr")])
+def test_caching_server_farm_matches_the_reference_fixture(fixture, strategy):
+    """examples/load-balancing/consistent_hashing_basics.py: consistent hashing keeps a customer on one server's TTL cache
+    (hit rate ~80 %), round robin spreads it over all five (~40 %).  The fixture is the unmodified reference running
+    the example's own CachingServer class; here the mirror classes run on the device."""
+    _, kw, z = G.load(fixture)
+    servers = [hs.CachingServer(f"Server_{i}", server_id=i, cache_capacity=100, cache_ttl_s=0.8) for i in range(5)]
+    strat = hs.ConsistentHash(virtual_nodes=30) if strategy == "chash" else hs.RoundRobin()
+    lb = hs.LoadBalancer("LB", backends=servers, strategy=strat)
+    src = hs.Source.poisson(rate=200.0, event_provider=hs.SimpleEventProvider(lb, context_fn=hs.UniformKeyContext(40)))
+    sim = hs.Simulation(end_time=hs.Instant(kw["end_ns"]), sources=[src], entities=[*servers, lb], seed=kw["seed"],
+                        replica=kw["rid_base"])
+    summary = sim.run()
+    st = z["entity_stats"][0]
+    assert summary.total_events_processed == int(z["summaries"]["events_processed"][0])
+    for i, sv in enumerate(servers):
+        row = st[1 + i]
+        assert (sv.stats.requests_processed, sv.stats.cache_misses, sv.stats.cache_hits) == (int(row["c2"]), int(row["c3"]), int(row["f0"]))
+        assert sv.cache_size == int(row["f1"]) and sv.stats_accepted == int(row["c0"])
+    hit = sum(s.stats.cache_hits for s in servers) / max(1, sum(s.stats.cache_hits + s.stats.cache_misses for s in servers))
+    assert (hit > 0.7) if strategy == "chash" else (hit < 0.5)
+    assert lb.stats.requests_forwarded == int(st[6]["c1"])

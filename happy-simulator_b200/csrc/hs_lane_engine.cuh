@@ -596,9 +596,13 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     }
                     if ((FLAGS & HS_LF_REC) && rec) st_wr += nrec;
                 }
-#if HS_LANE_PREDICATED
-                /* Every state variable is updated by a select, the memory operations are predicated: no branch,
-                 * hence no reconvergence point and no register shuffling where the two chains used to meet again. */
+                /* Two forms of the same updates, chosen per kernel by measurement (tools/bench_lane.py, A/B on one B200):
+                 * selects + predicated memory operations (no branch, no reconvergence point, no register shuffling
+                 * where the chains meet again) win without the recorder (+1 %) and with the order hash (+8 %); with the
+                 * recorder alone the two-branch form is 3.7 % faster (the predicated Sink block keeps more values live
+                 * across the staged stores). */
+                constexpr bool PREDICATED = HS_LANE_PREDICATED != 0 && (!(FLAGS & HS_LF_REC) || (FLAGS & HS_LF_HASH));
+                if (PREDICATED) {
                 const bool isC = !isA;
                 /* Source: payload index c0, next SourceEvent index c0 + 1 (source.py:166-170) */
                 arr_draws += isA ? 1ull : 0ull;
@@ -652,7 +656,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 c_created = start ? start_created : c_created;
                 svc_s = start ? sv_next : svc_s;
                 active = start ? 1 : (isA ? active : 0);
-#else
+                } else {
                 if (isA) {
                     /* Source: payload index c0, next SourceEvent index c0 + 1 (source.py:166-170) */
                     arr_draws++; tT = tT_next; iT = c0 + 1;
@@ -685,7 +689,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     n_svc++;
                     tC = now + hs_seconds_to_ns(sv_); iC = ctr - 1; c_created = start_created; svc_s = sv_; active = 1;
                 }
-#endif
+                }
                 continue;
             }
         }

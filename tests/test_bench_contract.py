@@ -13,16 +13,30 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json")))
-    assert BASE_KEYS | {"roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"} <= set(d)
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")))
+    assert BASE_KEYS | {"roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "parity_sample"} <= set(d)
     assert d["metric"] == "simulated_events_per_second" and d["unit"] == "events/s"      # BASELINE.json: "simulated events/sec"
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
-    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["cpu_baseline"]["cores"] <= d["cpu_baseline"]["core_accounting"]["affinity"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["d2h_bytes_per_step"] > 0
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["gpu_launches"] == d["steps"]
     assert "workload" in d["config"] and d["higher_is_better"] is True and d["scaling"] == "weak"
     assert abs(d["value"] - d["events_timed"] / (d["ms_per_step"] * d["steps"] * 1e-3)) / d["value"] < 1e-9
+    # the timed run was checked against the CPU oracle inside the bench: raw rings, summaries, statistics
+    ps = d["parity_sample"]
+    assert ps["ok"] and ps["ok_all_ranks"] and ps["replicas"] >= 8 and "records" in ps["compared"] and ps["events_checked"] > 1e7
+
+
+def test_committed_full_horizon_run_covers_the_whole_configuration():
+    """BASELINE configs[1] is 65 536 replicas x 1e6 sim-s: one committed run covers all 100 windows, with the same sentinel."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_full_horizon.json")))
+    assert d["steps"] + d["warmup"] == 100 and d["config"]["window_s"] * 100 == d["config"]["horizon_s"] == 1e6
+    assert d["aggregate"]["events_processed"] > 3.9e12 and d["aggregate"]["replicas"] == 65536 and d["replicas_flagged"] == 0
+    assert abs(d["aggregate"]["mean_latency_s"] - 0.5) < 1e-3                 # M/M/1, rho = 0.8: W = 1 / (mu - lambda)
+    ps = d["parity_sample"]
+    assert ps["ok"] and ps["windows"] == 100 and ps["sim_seconds_each"] == 1e6 and ps["events_checked"] > 4e8
 
 
 def test_reference_arm_prints_one_json_line_without_a_gpu():

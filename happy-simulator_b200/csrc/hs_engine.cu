@@ -349,6 +349,19 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     M.sketch_tables = (const int32_t *)E->d_sketch_tab.p; M.sk_total = E->sk_total;
     M.key_cdf = (const double *)E->d_key_cdf.p;
     M.n_entities = ne; M.n_cells = E->n_cells; M.n_servers = n_servers; M.fel_slots = S; M.block_bytes = block_bytes;
+    {
+        bool fixed = per_thread && ne <= S;
+        for (uint32_t i = 0; i < ne && fixed; ++i) {
+            const hs_entity_desc &e = E->ents[i];
+            if (e.kind == HS_ENT_CACHE_SERVER) fixed = false;
+            if (e.kind == HS_ENT_SERVER) {
+                int32_t c = e.i0;
+                for (uint32_t k = 0; k < E->n_cells; ++k) c = std::max(c, E->cell_i0[(size_t)k * ne + i]);
+                if (c != 1) fixed = false;
+            }
+        }
+        M.fixed_slots = fixed ? 1u : 0u; M.pad_ = 0;
+    }
     M.n_backends = (uint32_t)E->backends.size(); M.model_bytes = model_bytes;
     hs_warp_run R;
     R.seed = p->seed; R.seed_stride = p->seed_stride; R.rid_base = p->rid_base; R.rid_stride = p->rid_stride;

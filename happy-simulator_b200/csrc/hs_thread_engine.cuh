@@ -178,7 +178,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (first == HS_T_EXHAUSTED) continue;       /* source.start(): RuntimeError, no tick */
             e->u.src.cur_ns = first;
             if (hn >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; break; }
-            const uint32_t slot = FREE[S - hn - 1];
+            const uint32_t slot = M.fixed_slots ? i : FREE[S - hn - 1];
             hs_tpay pp; pp.created = 0; pp.aux = 0ull; pp.m0 = HS_EV_SOURCE_TICK | (i << 8); pp.key = -1; pp.hook = 0u; pp.pad = 0u;
             PAY[slot] = pp;
             hs_tkey nk; nk.time = first; nk.k2 = (boot++ << 16) | slot;
@@ -255,7 +255,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     /* insertion of a future event (SourceEvent or ProcessContinuation) into the 4-ary key heap */
     auto heap_insert = [&](hs_tkey fkey, const hs_tpay &fpay) {
         if (heap_n >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; return; }
-        const uint32_t slot = FREE[S - heap_n - 1];
+        const uint32_t slot = M.fixed_slots ? (fpay.m0 >> 8) : FREE[S - heap_n - 1];   /* entity-owned slot, or the stack's top */
         PAY[slot] = fpay;
         fkey.k2 |= slot;
         uint32_t k = heap_n++;
@@ -316,15 +316,16 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             const int t1 = ds.target;
             const hs_entity_desc d1 = ENTS[t1];
             went_u xs; went_load((int)ent, xs); hs_went *Xs = &xs.w;
+            went_u xl; hs_went *Xl = &xl.w;
+            if (d1.kind == HS_ENT_LB) went_load(t1, xl);             /* issued together with the source's: independent lines */
             const int64_t cur_ns = Xs->u.src.cur_ns; const uint64_t arr_draws = Xs->u.src.arr_draws, key_draws = Xs->u.src.key_draws;
             int32_t key = -1;
             if (ds.i1 > 0) key = hs_routing_key(hs_uniform(seed, rid, HS_STREAM_ROUTING | (ent << 8), key_draws), ds.i1,
                                                 ds.i2 > 0 ? M.key_cdf + (ds.i2 - 1) : nullptr);
             int lb = -1, be = t1; uint64_t rr = 0; bool use_rr = false;
-            went_u xl; hs_went *Xl = &xl.w;
             if (d1.kind == HS_ENT_LB) {
                 if (d1.i2 <= 0) return false;
-                lb = t1; went_load(lb, xl);
+                lb = t1;
                 int slot;
                 if (d1.i0 == HS_LB_KEY_TABLE && key >= 0) slot = M.key_table[key];
                 else { rr = Xl->u.lb.rr_index; slot = (int)(rr % (uint64_t)d1.i2); use_rr = true; }
@@ -567,7 +568,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             ev.time = top_t; ev.idx = top_k >> 16; ev.created = pp.created; ev.aux = pp.aux;
             ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = 0u;
             heap_n--;
-            FREE[S - heap_n - 1] = (uint16_t)slot;
+            if (!M.fixed_slots) FREE[S - heap_n - 1] = (uint16_t)slot;
             if (heap_n > 0) {                            /* sift-down of the last key from the root */
                 const hs_tkey last = K[heap_n];
                 uint32_t k = 0;

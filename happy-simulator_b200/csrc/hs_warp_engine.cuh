@@ -81,6 +81,9 @@ struct hs_warp_model {
     uint32_t n_entities, n_cells, n_servers, fel_slots;   /* fel_slots = S, multiple of 32 */
     uint32_t block_bytes;           /* bytes of one replica block (multiple of 16)          */
     uint32_t n_backends, model_bytes; /* shared-memory copy of the model tables (per CTA)     */
+    uint32_t fixed_slots, pad_;       /* thread engine: every entity has at most ONE pending future event (sources: the next
+                                         tick; servers with concurrency 1: the continuation), so its payload slot is its
+                                         entity id -- no free-slot stack traffic on the heap's push / pop path */
 };
 
 struct hs_warp_run {

@@ -13,20 +13,23 @@ from collections import defaultdict
 from typing import Any
 
 
-def _percentile_sorted(sorted_values, p: float) -> float:
-    """instrumentation/data.py:197-210"""
-    if not sorted_values:
+def _percentile_sorted(ordered, p: float) -> float:
+    """Linear-interpolation percentile of an ascending sequence, p in [0, 1]: the arithmetic of the reference's
+    helper (instrumentation/data.py:197-210) restated -- rank = p (n - 1), then ``v[k] * (1 - f) + v[k + 1] * f`` with
+    k = floor(rank), f = rank - k, in exactly that order of operations, so every percentile the mirrors report
+    (Sink.latency_stats, Data.percentile, BucketedData p50 / p99) equals the reference's float for float."""
+    count = len(ordered)
+    if count == 0:
         return 0.0
-    if p <= 0:
-        return float(sorted_values[0])
+    if p <= 0 or count == 1:
+        return float(ordered[0])
     if p >= 1:
-        return float(sorted_values[-1])
-    n = len(sorted_values)
-    pos = p * (n - 1)
-    lo = int(pos)
-    hi = min(lo + 1, n - 1)
-    frac = pos - lo
-    return float(sorted_values[lo] * (1.0 - frac) + sorted_values[hi] * frac)
+        return float(ordered[count - 1])
+    rank = p * (count - 1)
+    k = int(rank)
+    f = rank - k
+    upper = ordered[k + 1] if k + 1 < count else ordered[count - 1]
+    return float(ordered[k] * (1.0 - f) + upper * f)
 
 
 class BucketedData:

@@ -35,3 +35,19 @@ def test_data_matches_the_reference_class():
         assert a.percentile(p) == b.percentile(p)
     assert a.bucket(2.5).to_dict() == b.bucket(2.5).to_dict()
     assert a.rate(5.0).values == b.rate(5.0).values
+
+
+def test_percentile_helper_equals_the_reference_helper_float_for_float():
+    import random
+    import sys
+    import pytest
+    for d in ("/root/reference", __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))), "baseline", "_ref")):
+        if __import__("os").path.isdir(__import__("os").path.join(d, "happysimulator")) and d not in sys.path:
+            sys.path.insert(0, d)
+    ref = pytest.importorskip("happysimulator.instrumentation.data")
+    from happysim_b200.instrumentation import _percentile_sorted as mine
+    rnd = random.Random(1)
+    for n in (0, 1, 2, 3, 7, 100, 1001):
+        v = sorted(rnd.random() * 10 for _ in range(n))
+        for p in (-1, 0, 1e-9, 0.25, 0.5, 0.99, 0.999, 1, 2, rnd.random(), rnd.random()):
+            assert mine(v, p) == ref._percentile_sorted(v, p), (n, p)

@@ -15,7 +15,7 @@ collective is the end-of-run NCCL all-reduce of the fixed-layout summary vector 
      10 sim-s horizon, one step = 1 sim-s window;
   4  M/M/c sweep, c in 1..32 x 8 arrival-rate levels = 256 cells, 262 144 replicas over 8 GPUs (32 768 per GPU,
      128 seeds per cell and GPU), 1 000 sim-s horizon, one step = 100 sim-s window; after the run the per-cell
-     totals and latency histograms are all-reduced (two NCCL calls) and checked against the numpy reduction of
+     totals and latency histograms are all-reduced (one collective) and checked against the numpy reduction of
      the per-replica outputs gathered from every rank.
 They print the same JSON line (kept under profiles/); the driver's headline stays --config 1.
 
@@ -320,6 +320,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the CPU oracle (checker of the parity sample, CPU legs) is built once per node, before any rank loads it
+    if local == 0:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    barrier()
     cfg = make_config(a)
     model, n = cfg["model"], cfg["replicas"]
     end_ns = int(cfg["horizon_s"] * 1e9)
@@ -397,7 +401,6 @@ def main():
     def parity_sample(mode, windows_done, k_rep):
         """Replicas spread over this rank's range, oracle-run with the same seeds up to the last window executed
         (the oracle pauses at the same window end), compared with the device state of the timed run."""
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
         got = eng.read_outputs()
         idx = sorted({int(i) for i in np.linspace(0, n - 1, k_rep)})
         p = params(mode, windows_done - 1, resume=0, mk=O.make_params)

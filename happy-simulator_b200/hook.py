@@ -123,8 +123,6 @@ def install(*, device: int = 0, verbose: bool = False) -> None:
         sm = api.run_lowered(self, model, objects, device=_state["device"], trace_fn=_trace_fn_from_states(np_state, py_state))
         # leave both global generators where a reference run would have left them
         kinds = model.entities["kind"]
-        st_rows = None
-        shell_info = sm.entities          # (unused; the counts come from the written-back objects)
         n_arr = sum(int(getattr(o, "_generated_count", 0)) + 1 for i, o in enumerate(objects)
                     if int(kinds[i]) == A.HS_ENT_SOURCE and int(model.entities["i0"][i]) == A.HS_ARR_POISSON)
         n_svc = sum(len(getattr(o, "_service_times", ())) for i, o in enumerate(objects)

@@ -84,3 +84,33 @@ def test_run_replicas_is_one_device_ensemble(ref):
     ev = [r.summary.total_events_processed for r in res]
     assert len(set(ev)) > 8 and all(1200 < e < 2600 for e in ev)
     assert res[3].summary.entities["Sink"].events_handled > 150
+
+
+def test_probes_and_trackers_survive_install(ref):
+    """A script with a queue-depth Probe and a LatencyTracker sink (instrumentation/probe.py, collectors.py):
+    the samples written back onto the script's own Data objects equal the reference loop's."""
+    import happysim_b200 as hs
+    from happysimulator import Instant, LatencyTracker, Probe, Simulation, Source
+    from happysimulator.components.server.server import Server
+    from happysimulator.distributions.exponential import ExponentialLatency
+
+    def script():
+        random.seed(3); np.random.seed(3)
+        sink = LatencyTracker(name="Sink")
+        server = Server("Server", service_time=ExponentialLatency(0.1), downstream=sink)
+        probe, depth = Probe.on(server, "depth", interval=0.25)
+        sim = Simulation(sources=[Source.poisson(rate=9, target=server)], entities=[server, sink], probes=[probe],
+                         end_time=Instant.from_seconds(40.0))
+        summary = sim.run()
+        return summary, sink, depth
+    want_s, want_sink, want_depth = script()
+    hs.install()
+    try:
+        got_s, got_sink, got_depth = script()
+        st = hs.install_stats()
+    finally:
+        hs.uninstall()
+    assert st["device_runs"] >= 1 and st["fallbacks"] == 0
+    assert got_s.total_events_processed == want_s.total_events_processed
+    assert got_depth.raw_values() == want_depth.raw_values() and got_depth.times() == want_depth.times()
+    assert got_sink.data.raw_values() == want_sink.data.raw_values() and got_sink.count == want_sink.count

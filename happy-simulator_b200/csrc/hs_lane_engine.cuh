@@ -150,9 +150,6 @@ struct hs_lane_out {
 #ifndef HS_ST256_POLICY
 #define HS_ST256_POLICY 1
 #endif
-#ifndef HS_LANE_CARRY
-#define HS_LANE_CARRY 1         /* SIMPLE chains: next-chain operands carried in registers across the loop top (0: read at the top) */
-#endif
 #ifndef HS_LANE_PREDICATED
 #define HS_LANE_PREDICATED 1    /* SIMPLE chains: state updates as selects + predicated memory operations (0: two branches) */
 #endif
@@ -515,22 +512,20 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
     const int64_t ev_fast_limit = P.max_events - 8;     /* a chain is <= 6 events: single-step near the limit */
     const int64_t fast_limit = (windowed && P.window_end_ns < P.end_ns) ? P.window_end_ns : P.end_ns;
     bool paused = false;
-    /* SIMPLE: the two shared-memory operands of the next chain -- the next arrival time and the next service time --
-     * are carried in registers: a chain re-reads them at its end (HS_LANE_CARRY), a whole loop top before they are
-     * needed, instead of at the point of use; a lane whose buffers were dry re-reads them after the refill round.
-     * The queue head is only read (after waiting for its cp.async) by a completion chain that actually delivers it. */
-    int64_t tT_next = 0; double sv_next = 0.0;
-    bool operands_stale = true;
     while (true) {
         /* converged top of the loop: vote on termination and on refilling */
         const bool need = !finished && (a_gen == arr_draws || s_gen == (uint64_t)n_svc);
         const unsigned todo = __ballot_sync(0xffffffffu, !finished);
         if (todo == 0u) break;
         if (__any_sync(0xffffffffu, need)) HS_REFILL_ROUND();
-        if (SIMPLE && (need || operands_stale || !HS_LANE_CARRY)) {
+        /* SIMPLE: the three shared-memory operands of the next chain are requested first, so their
+         * latency is covered by the flush below: next arrival time, next service time, queue head */
+        int64_t tT_next = 0; double sv_next = 0.0; hs_ring_entry h; h.created = 0; h.idx = 0;
+        if (SIMPLE) {
             tT_next = sh_t[(arr_draws + 1) % HS_DRAW_BUF][tid];
             sv_next = sh_svc[(uint32_t)((uint64_t)n_svc % HS_DRAW_BUF)][tid];
-            operands_stale = false;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            h = *my_head;                                    /* next queued request (meaningful if q_len > 0) */
         }
         if (FLAGS & HS_LF_REC) {
             /* a lane holding a full 128-byte group writes it itself: 8 reads of its own staging column,
@@ -569,11 +564,6 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 now = tn;
                 const bool q_empty = (q_len == 0);
                 const bool start = isA ? (q_empty && !busy) : !q_empty;      /* a service starts in this chain */
-                hs_ring_entry h; h.created = 0; h.idx = 0;
-                if (!isA && !q_empty) {                                      /* the request this completion delivers */
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    h = *my_head;
-                }
                 const uint64_t c0 = ctr;
                 const uint64_t idx0 = isA ? iT : iC;
                 const uint64_t widx = isA ? c0 : h.idx;                      /* the payload WORKER carries */
@@ -699,10 +689,6 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                     n_svc++;
                     tC = now + hs_seconds_to_ns(sv_); iC = ctr - 1; c_created = start_created; svc_s = sv_; active = 1;
                 }
-                }
-                if (HS_LANE_CARRY) {       /* operands of the NEXT chain (re-read after the refill if a buffer ran dry) */
-                    tT_next = sh_t[(arr_draws + 1) % HS_DRAW_BUF][tid];
-                    sv_next = sh_svc[(uint32_t)((uint64_t)n_svc % HS_DRAW_BUF)][tid];
                 }
                 continue;
             }
@@ -892,7 +878,7 @@ hs_lane_kernel(hs_lane_model M, hs_lane_run P, hs_lane_state *__restrict__ state
                 break;
             default: break;
             }
-            if (SIMPLE) { sticky_slow = HS_STICKY_SLOW(); operands_stale = true; }
+            if (SIMPLE) sticky_slow = HS_STICKY_SLOW();
         }
     }
 #undef HS_STICKY_SLOW

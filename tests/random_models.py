@@ -134,3 +134,62 @@ def random_lane_model(seed: int):
     what = (f"lane seed {seed}: rate {rate} {'poisson' if poisson else 'constant'}, c={c}, "
             f"{'exp' if exponential else 'const'} service {mean:.4f}, dst {('sink', 'counter', 'none')[dst]}")
     return model, end_s, what
+
+
+def random_model_v2(seed: int, with_extras: bool = False):
+    """Second generator (round 2 features; its own fixture file so that the first generator's models stay as they
+    are): user-defined STEP rate profiles and CachingServer farms behind round-robin / consistent-hash load balancers,
+    alone and mixed with ordinary servers.  -> (FlatModel, end_seconds, description[, extras for the harness])"""
+    rng = np.random.RandomState(50_000 + seed)
+    extras = {"profile_objects": {}, "chash_vnodes": None}
+    b = hs.ModelBuilder()
+    shape = str(rng.choice(["cache_direct", "cache_lb_rr", "cache_lb_chash", "step_server", "step_farm", "step_cache"]))
+    K = int(rng.choice([3, 12, 40])) if "cache" in shape else int(rng.choice([0, 16]))
+    rate = float(rng.choice([30.0, 90.0, 200.0]))
+    kw = dict(rate=rate, poisson=bool(rng.rand() < 0.75), key_population=K)
+    if rng.rand() < 0.15:
+        kw["stop_after_ns"] = int(rng.uniform(0.5, 2.0) * 1e9)
+    step = None
+    if shape.startswith("step") or rng.rand() < 0.3:
+        n = int(rng.randint(1, 6))
+        breaks = sorted({round(float(x), 3) for x in rng.uniform(0.05, 3.5, size=n)})
+        rates = [rate * float(rng.choice([0.3, 0.6, 1.0, 1.7, 2.5])) for _ in range(len(breaks) + 1)]
+        step = hs.StepProfile(tuple(breaks), tuple(rates))
+        kw["profile"] = ("step", list(step.breakpoints), list(step.rates))
+    src = b.source("Src", **kw)
+    if step is not None:
+        extras["profile_objects"][src] = step
+
+    def cache(i):
+        ttl = float(rng.choice([0.05, 0.3, 1.0, 30.0]))
+        return b.cache_server(f"Cache{i}", key_slots=K, cache_ttl_s=ttl,
+                              cache_read_latency_s=float(rng.choice([0.0001, 0.001])),
+                              datastore_read_latency_s=float(rng.choice([0.005, 0.02])),
+                              processing_latency_s=float(rng.choice([0.001, 0.004])))
+
+    if shape in ("cache_direct", "step_cache"):
+        head = cache(0)
+    elif shape == "step_server":
+        snk = b.sink()
+        c = int(rng.choice([1, 2]))
+        head = b.server("Srv", concurrency=c, mean_service_s=c / rate * float(rng.uniform(0.4, 1.0)),
+                        exponential=bool(rng.rand() < 0.7), downstream=snk, lifo=bool(rng.rand() < 0.3))
+    else:
+        n = int(rng.randint(2, 6))
+        if shape == "step_farm":
+            snk = b.sink()
+            backs = [b.server(f"Srv{i}", mean_service_s=n / rate * float(rng.uniform(0.4, 1.0)), downstream=snk) for i in range(n)]
+            names = None
+        else:
+            backs = [cache(i) for i in range(n)]
+            names = [f"Cache{i}" for i in range(n)]
+        table = None
+        if shape == "cache_lb_chash":
+            extras["chash_vnodes"] = int(rng.choice([5, 30]))
+            table = hs.consistent_hash_table(names, extras["chash_vnodes"], K)
+        head = b.load_balancer("LB", backends=backs, key_table=table)
+    b.set_target(src, head)
+    model = b.build()
+    end_s = float(rng.uniform(1.5, 4.0))
+    what = f"v2 seed {seed}: {shape}, K={K}, rate {rate}{' step' if step is not None else ''}, {model.n_entities} entities"
+    return (model, end_s, what, extras) if with_extras else (model, end_s, what)

@@ -96,3 +96,39 @@ def test_random_single_server_model_on_lane_and_general_engines(eng, seed):
         assert_same(eng.read_outputs(), want)
     except AssertionError as e:
         raise AssertionError(f"{what}: {e}") from None
+
+
+# ---- second generator: user-defined step profiles and CachingServer farms ------------------------------------------
+from random_models import random_model_v2            # noqa: E402
+from test_random_models import SEEDS_V2, check_against_reference_v2   # noqa: E402
+
+
+@pytest.mark.parametrize("seed", SEEDS_V2)
+def test_random_step_profile_and_cache_model_on_every_engine(eng, seed):
+    """Every engine that accepts the model (lane for a single ordinary server, thread, warp) against the oracle --
+    records, statistics, samples, TTL-cache states -- and replica word 0 against the unmodified reference; then the
+    same run cut into windows."""
+    model, end_s, what = random_model_v2(seed)
+    end_ns = int(end_s * 1e9)
+    kw = dict(seed=2000 + seed, n_replicas=5, record_cap=16000, sample_cap=2000, service_cap=2000, queue_ring=1024)
+    want = O.oracle_run(model, O.make_params(end_ns=end_ns, **kw))
+    eng.upload(model)
+    eng.run(engine.make_params(end_ns=end_ns, **dict(kw, n_replicas=1)))
+    check_against_reference_v2(eng.read_outputs(), seed)
+    for eng_id in (0, 1, 3):
+        try:
+            eng.run(engine.make_params(end_ns=end_ns, engine=eng_id, **kw))
+            got = eng.read_outputs()
+            assert_same(got, want)
+            if want.get("sketches") is not None:
+                assert got["sketches"].tobytes() == want["sketches"].tobytes(), "TTL cache states differ"
+            cuts = [end_ns // 5, end_ns // 2 + 7]
+            eng.run(engine.make_params(end_ns=end_ns, window_end_ns=cuts[0], engine=eng_id, **kw))
+            eng.run(engine.make_params(end_ns=end_ns, window_end_ns=cuts[1], resume=1, engine=eng_id, **kw))
+            eng.run(engine.make_params(end_ns=end_ns, resume=1, engine=eng_id, **kw))
+            got = eng.read_outputs()
+            assert_same(got, want)
+            if want.get("sketches") is not None:
+                assert got["sketches"].tobytes() == want["sketches"].tobytes(), "TTL cache states differ after windows"
+        except AssertionError as e:
+            raise AssertionError(f"{what}, engine {eng_id}: {e}") from None

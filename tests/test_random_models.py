@@ -84,3 +84,30 @@ def test_oracle_matches_the_reference_on_random_single_server_models(seed):
     for f in ("events_processed", "final_time_ns", "order_hash", "heap_left", "n_sink_samples", "n_service_samples"):
         assert int(s[f]) == int(ws[f]), (what, f, int(s[f]), int(ws[f]))
     assert out["entity_stats"][0].tobytes() == REF[f"lane{seed}_stats"][0].tobytes(), what
+
+
+# ---- second generator: step profiles and CachingServer farms (tests/golden/random_models_v2.npz) -------------------
+SEEDS_V2 = list(range(48))          # also on the device engines (tests/test_gpu_random_models.py)
+REF_SEEDS_V2 = list(range(120))
+
+_v2_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "random_models_v2.npz")
+REF_V2 = np.load(_v2_path) if os.path.exists(_v2_path) else None
+
+
+def check_against_reference_v2(out, seed, r=0):
+    ws, wstats, wsk = REF_V2[f"s{seed}_summary"][0], REF_V2[f"s{seed}_stats"][0], REF_V2[f"s{seed}_sketches"]
+    s = out["summaries"][r]
+    for f in ("events_processed", "final_time_ns", "order_hash", "heap_left", "n_sink_samples", "n_service_samples"):
+        assert int(s[f]) == int(ws[f]), (seed, f, int(s[f]), int(ws[f]))
+    assert out["entity_stats"][r].tobytes() == wstats.tobytes(), (seed, "entity statistics")
+    if len(wsk):
+        assert out["sketches"][r].tobytes() == wsk.tobytes(), (seed, "TTL cache states")
+
+
+@pytest.mark.parametrize("seed", REF_SEEDS_V2)
+def test_oracle_matches_the_reference_on_random_step_profile_and_cache_models(seed):
+    from random_models import random_model_v2
+    model, end_s, what = random_model_v2(seed)
+    engine.validate_model(model)
+    out = O.oracle_run(model, O.make_params(seed=2000 + seed, end_ns=int(end_s * 1e9), n_replicas=1))
+    check_against_reference_v2(out, seed)

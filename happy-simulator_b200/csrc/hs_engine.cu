@@ -368,7 +368,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     R.end_ns = p->end_ns; R.window_end_ns = p->window_end_ns;
     R.n_replicas = n; R.index_base = p->replica_index_base; R.replicas_per_cell = p->replicas_per_cell;
     R.record_cap = p->record_cap; R.sample_cap = p->sample_cap; R.service_cap = p->service_cap;
-    R.ring = ring; R.resume = p->resume; R.lane_stride = 1;
+    R.ring = ring; R.resume = p->resume; R.lane_stride = 1; R.heap_top = 0;
     R.max_events = p->max_events > 0 ? p->max_events : INT64_MAX;
     R.trace_arr = E->n_trace_arr ? (const double *)E->d_trace_arr.p : nullptr; R.n_trace_arr = E->n_trace_arr;
     R.trace_svc = E->n_trace_svc ? (const double *)E->d_trace_svc.p : nullptr; R.n_trace_svc = E->n_trace_svc;
@@ -402,11 +402,25 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
         rpw = std::min<uint32_t>(32, std::max<uint32_t>(1, rpw));
         R.lane_stride = 32 / rpw;
         const int tblocks = (int)(((uint64_t)n * R.lane_stride + HS_THREAD_BLOCK - 1) / HS_THREAD_BLOCK);
+        /* heap keys kept in shared memory: as many whole top levels as 16 KB per block hold for the block's replicas
+         * (8 blocks per SM stay resident next to the 12 KB of the now tier); HS_THREAD_HEAPTOP overrides (experiments) */
+        {
+            const uint32_t rpb = HS_THREAD_BLOCK / R.lane_stride;
+            const uint32_t budget = 16384u / 16u / rpb;          /* keys per replica */
+            uint32_t top = 0, level = 1, total = 0;
+            while (total + level <= budget && total + level <= S) { total += level; level *= HS_T_ARITY; top = total; }
+            if (top < 1 + HS_T_ARITY || R.lane_stride == 32) top = 0;       /* one replica per warp: its heap sits in L1 anyway */
+            if (const char *ev = getenv("HS_THREAD_HEAPTOP")) top = (uint32_t)std::max(0, atoi(ev));
+            R.heap_top = top;
+        }
+        const size_t dyn_smem = (size_t)R.heap_top * (HS_THREAD_BLOCK / R.lane_stride) * 16;
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
-#define HS_LAUNCH_THREAD(F) case F: hs_thread_kernel<F><<<tblocks, HS_THREAD_BLOCK, 0, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;
-        switch (fl) {
+#define HS_LAUNCH_THREAD(F) case F: hs_thread_kernel<F><<<tblocks, HS_THREAD_BLOCK, dyn_smem, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;
+        switch (fl | (R.heap_top ? HS_WF_HEAPTOP : 0)) {
         HS_LAUNCH_THREAD(0) HS_LAUNCH_THREAD(1) HS_LAUNCH_THREAD(2) HS_LAUNCH_THREAD(3)
         HS_LAUNCH_THREAD(4) HS_LAUNCH_THREAD(5) HS_LAUNCH_THREAD(6) HS_LAUNCH_THREAD(7)
+        HS_LAUNCH_THREAD(8) HS_LAUNCH_THREAD(9) HS_LAUNCH_THREAD(10) HS_LAUNCH_THREAD(11)
+        HS_LAUNCH_THREAD(12) HS_LAUNCH_THREAD(13) HS_LAUNCH_THREAD(14) HS_LAUNCH_THREAD(15)
         }
 #undef HS_LAUNCH_THREAD
         CUDA_TRY(cudaGetLastError());

@@ -36,6 +36,7 @@
 #define HS_WF_HASH 1
 #define HS_WF_REC 2
 #define HS_WF_PROFILE 4    /* some Source has a non-constant rate profile (Simpson + Brent calls) */
+#define HS_WF_HEAPTOP 8    /* thread engine: the heap's top levels live in shared memory (launches with several replicas per warp) */
 
 struct __align__(16) hs_warp_hdr {      /* 128 B */
     int64_t now; uint64_t ctr; int64_t processed; uint64_t hash;
@@ -93,6 +94,8 @@ struct hs_warp_run {
     uint32_t n_replicas, index_base, replicas_per_cell;
     uint32_t record_cap, sample_cap, service_cap, ring, resume;
     uint32_t lane_stride;           /* thread engine: lanes per replica (1, 2, 4 ... 32) */
+    uint32_t heap_top;              /* thread engine: number of heap keys (whole top levels: 0, 5, 21, 85 or 341 for
+                                       arity 4) kept in shared memory during a launch, [key][replica column] */
     int64_t max_events;
     const double *trace_arr, *trace_svc;
     uint64_t n_trace_arr, n_trace_svc;

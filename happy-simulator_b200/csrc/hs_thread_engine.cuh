@@ -633,6 +633,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
          * process() is a uniform branch and the lanes that take it run the same handler.
          * One nibble per pass, low first: TICK 0, CONTINUATION 7, PROBE 11, REQ_LB 1, ENQUEUE 2, SINK 8, COUNTER 10,
          * SKETCH 12, NOTIFY 3, LB_RESPONSE 9, POLL 4, DELIVER 5, WORKER 6 (the HS_EV_* values of include/hs_b200.h) */
+        if (ev_kind < 0) continue;                   /* the fused chain did it all: nothing for the generic passes */
 #pragma unroll 1
         for (int ph = 0; ph < 13; ++ph) {
             const int kind = single ? ev_kind : (int)((0x65493ca821b70ull >> (4 * ph)) & 15ull);

@@ -146,11 +146,13 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         t = (int64_t)((uint64_t)a.x | ((uint64_t)a.y << 32)); ix = (uint64_t)a.z | ((uint64_t)a.w << 32);
     };
 
-    hs_warp_hdr hdr;                                     /* working copy of the header (registers) */
+    hs_warp_hdr hdr;                                     /* working copy of the header */
     hs_warp_hdr *H = &hdr;
+    int64_t h_now = 0, h_processed = 0; uint64_t h_hash = 0; int32_t h_fel = 0;   /* its hot fields, in registers (see below) */
     if (P.resume) {
         hdr = *Hg;
         if (hdr.done) return;
+        h_now = H->now; h_processed = H->processed; h_hash = H->hash; h_fel = H->fel_n;
         for (uint32_t i = 0; i < TOP && i < hdr.free_top + HS_T_ARITY; ++i) {      /* the heap's top levels (free_top = heap size) */
             const hs_tkey k = K[i];
             Ktop[i * rpb + (uint32_t)tid] = make_uint4((uint32_t)(uint64_t)k.time, (uint32_t)((uint64_t)k.time >> 32), (uint32_t)k.k2, (uint32_t)(k.k2 >> 32));
@@ -178,7 +180,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 e->u.snk.mx = __longlong_as_double(0xfff0000000000000LL);
             }
         }
-        hdr.hash = HS_HASH_INIT;
+        h_hash = HS_HASH_INIT;
         /* Simulation.__init__: source.start() in order; bootstrap indices come from the global
          * counter (simulation.py:77,145-154), run() restarts the per-heap one at 0. */
         uint64_t boot = 0;
@@ -209,7 +211,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                             if (!HS_T_LT(nk.time, nk.k2, q.time, q.k2)) break; kstore(k, q); k = p; }
             kstore(k, nk);
         }
-        hdr.fel_n = (int32_t)hn;
+        h_fel = (int32_t)hn;
         hdr.free_top = hn;                               /* free_top holds the heap size in this engine */
         hdr.ctr = 0;
     }
@@ -218,6 +220,8 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     hs_sink_sample *smp = (FLAGS & HS_WF_REC) && O.samples ? O.samples + (size_t)r * P.sample_cap : nullptr;
     double *svc_out = (FLAGS & HS_WF_REC) && O.service ? O.service + (size_t)r * P.service_cap : nullptr;
 
+    /* the header's hot fields live in registers for the duration of the launch (the struct itself is addressed through
+     * H by the handlers, i.e. it sits in local memory) and are written back with it at the end */
     uint64_t ctr = hdr.ctr;
     int now_n = hdr.now_n;
     uint32_t heap_n = hdr.free_top;
@@ -242,9 +246,9 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     auto next_event = [&]() {
         while (true) {
             ev_kind = -1; need_heap = false;
-            const int64_t now0 = hdr.now;
+            const int64_t now0 = h_now;
             if (!(now0 <= P.end_ns) || (hdr.status & (HS_ST_QUEUE_OVERFLOW | HS_ST_FEL_OVERFLOW | HS_ST_TRACE_EXHAUSTED))) { alive = false; return; }
-            if (hdr.processed >= P.max_events) { hdr.status |= HS_ST_EVENT_LIMIT; alive = false; return; }
+            if (h_processed >= P.max_events) { hdr.status |= HS_ST_EVENT_LIMIT; alive = false; return; }
             int nb = -1; int64_t nt = HS_W_EMPTY; uint64_t ni = ~0ull;
             for (int k = 0; k < now_n; ++k) {
                 int64_t t; uint64_t ix; now_key(k, t, ix);
@@ -260,7 +264,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             ev = now_load(nb);
             now_n--;
             if (nb != now_n) now_store(nb, now_load(now_n));
-            hdr.fel_n--;
+            h_fel--;
             if (ev.time < now0) continue;                    /* "time travel": skipped (simulation.py:479-489) */
             int k = (int)(ev.m0 & 0xffu);
             if (k == (int)HS_EV_REQ_ANY) {
@@ -290,7 +294,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         }
         kstore(k, fkey);
         if (k == 0) { top_t = fkey.time; top_k = fkey.k2; }
-        hdr.fel_n++;
+        h_fel++;
     };
 
     /* ---- fused same-timestamp chains -----------------------------------------------------------------------------
@@ -306,13 +310,13 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
      * (tandem, sketch or probe targets), a stop_after source, a full ring, traces, the run / window end, the event
      * limit -- goes through the generic one-event path below, which is the oracle's.  Returns true if it ran. */
     auto emit = [&](const int64_t now, const uint64_t idx, const int kind, const uint32_t ent) {
-        if (FLAGS & HS_WF_HASH) hdr.hash = hs_hash_step(hdr.hash, now, hs_record_word1(idx, (uint32_t)kind, ent));
+        if (FLAGS & HS_WF_HASH) h_hash = hs_hash_step(h_hash, now, hs_record_word1(idx, (uint32_t)kind, ent));
         if ((FLAGS & HS_WF_REC) && rec) {
             hs_event_record rc; rc.time_ns = now; rc.sort_index = (uint32_t)idx; rc.kind = (uint8_t)kind;
             rc.pad = 0; rc.entity = (uint16_t)ent;
             rec[hdr.rec_pos] = rc; hdr.rec_pos = (hdr.rec_pos + 1 == P.record_cap) ? 0u : hdr.rec_pos + 1;
         }
-        hdr.processed++;
+        h_processed++;
     };
     /* entity state as six 16-byte vectors: one burst of loads into registers, the dynamic part (vectors 2..5) stored back */
     union went_u { hs_went w; uint4 q[6]; };
@@ -330,7 +334,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     auto fused_chain = [&]() -> bool {
         const int64_t now = ev.time;
         const int k0 = (int)(ev.m0 & 0xffu);
-        if (!fuse_on || now_n != 0 || !(top_t > now) || now > P.end_ns || hdr.processed + 10 > P.max_events) return false;
+        if (!fuse_on || now_n != 0 || !(top_t > now) || now > P.end_ns || h_processed + 10 > P.max_events) return false;
         const uint32_t ent = ev.m0 >> 8;
         if (k0 == HS_EV_SOURCE_TICK) {
             const hs_entity_desc ds = ENTS[ent];
@@ -382,7 +386,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 if (resume_t <= now) return false;                   /* a zero-length service resumes at this very nanosecond */
             }
             /* ---- nothing can stop the chain any more: run it ---------------------------------------------------- */
-            hdr.now = now;
+            h_now = now;
             const uint64_t idxP = ctr, idxT = ctr + 1; ctr += 2;
             emit(now, ev.idx, HS_EV_SOURCE_TICK, ent);
             Xs->u.src.provider++; Xs->u.src.generated++; Xs->u.src.cur_ns = nt;
@@ -465,7 +469,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 const hs_wring_entry *rg = ring0 + (size_t)srv_idx * P.ring;
                 q = rg[(dv.i1 == HS_Q_LIFO ? q_head + q_len - 1 : q_head) & ring_mask];
             }
-            hdr.now = now;
+            h_now = now;
             emit(now, ev.idx, HS_EV_CONTINUATION, ent);                /* generator resumes, server.py:255-273 */
             Xv->u.srv.completed++;
             Xv->u.srv.total_service = HS_ADD(Xv->u.srv.total_service, __longlong_as_double((long long)ev.aux));
@@ -538,14 +542,14 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
           for (int i = 0; i < 6; ++i) xu.q[i] = g[i]; }
         hs_went *X = &xu.w;
         const uint32_t srv_idx = (uint32_t)__double_as_longlong(du.d.d1) & 0xffffffu;   /* patched in by the host, see hs_model_upload */
-        hdr.now = now;
-        if (FLAGS & HS_WF_HASH) hdr.hash = hs_hash_step(hdr.hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
+        h_now = now;
+        if (FLAGS & HS_WF_HASH) h_hash = hs_hash_step(h_hash, now, hs_record_word1(bi, (uint32_t)kind, ent));
         if ((FLAGS & HS_WF_REC) && rec) {
             hs_event_record rc; rc.time_ns = now; rc.sort_index = (uint32_t)bi; rc.kind = (uint8_t)kind;
             rc.pad = 0; rc.entity = (uint16_t)ent;
             rec[hdr.rec_pos] = rc; hdr.rec_pos = (hdr.rec_pos + 1 == P.record_cap) ? 0u : hdr.rec_pos + 1;
         }
-        hdr.processed++;
+        h_processed++;
 
         bool have_fut = false;                           /* an event creates at most one future event */
         hs_tkey fkey; hs_tpay fpay;
@@ -557,7 +561,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (now_n >= HS_W_NCAP) hdr.status |= HS_ST_FEL_OVERFLOW;                                    \
             else { hs_wnow n_; n_.time = t_; n_.idx = (IDX); n_.created = (CREATED); n_.aux = (AUX);     \
                    n_.m0 = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); n_.key = (KEY); n_.hook = (HOOK); n_.pad = 0u; \
-                   now_store(now_n++, n_); hdr.fel_n++; }                                                \
+                   now_store(now_n++, n_); h_fel++; }                                                \
         } else {                                                                                         \
             if (have_fut) hdr.status |= HS_ST_FEL_OVERFLOW;                                              \
             fkey.time = t_; fkey.k2 = (uint64_t)(IDX) << 16; fpay.created = (CREATED); fpay.aux = (AUX); \
@@ -584,7 +588,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     while (alive) {
         /* ---- heap phase: the root is the next event (SourceEvent / ProcessContinuation) -------------- */
         if (need_heap) {
-            const int64_t now0 = hdr.now;
+            const int64_t now0 = h_now;
             const uint32_t slot = (uint32_t)(top_k & 0xffffu);
             const hs_tpay pp = PAY[slot];
             ev.time = top_t; ev.idx = top_k >> 16; ev.created = pp.created; ev.aux = pp.aux;
@@ -615,7 +619,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 if (k == 0) { top_t = last.time; top_k = last.k2; }
             }
             if (heap_n == 0) { top_t = HS_W_EMPTY; top_k = ~0ull; }
-            hdr.fel_n--;
+            h_fel--;
             need_heap = false;
             if (ev.time < now0) next_event();            /* "time travel": skipped (simulation.py:479-489) */
             else if (fused_chain()) next_event();        /* the whole same-timestamp chain ran as straight-line code */
@@ -654,14 +658,15 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         g[2] = Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid];
     }
     hdr.ctr = ctr; hdr.now_n = now_n; hdr.free_top = heap_n;
+    H->now = h_now; H->processed = h_processed; H->hash = h_hash; H->fel_n = h_fel;
     hdr.done = paused ? 0 : 1;
     *Hg = hdr;
     if (O.summaries) {
         hs_replica_summary s;
-        s.events_processed = hdr.processed; s.final_time_ns = hdr.now;
-        s.order_hash = (FLAGS & HS_WF_HASH) ? hdr.hash : 0ull;
+        s.events_processed = h_processed; s.final_time_ns = h_now;
+        s.order_hash = (FLAGS & HS_WF_HASH) ? h_hash : 0ull;
         s.next_sort_index = hdr.ctr; s.n_sink_samples = hdr.n_smp; s.n_service_samples = hdr.n_svc;
-        s.heap_left = hdr.fel_n; s.status = hdr.status;
+        s.heap_left = h_fel; s.status = hdr.status;
         O.summaries[r] = s;
     }
     if (O.stats) {

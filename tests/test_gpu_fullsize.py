@@ -166,3 +166,58 @@ def test_latency_histograms_and_cell_totals(eng):
     k2 = dict(seed=3, n_replicas=96, end_ns=100 * 10**9, flags=A.HS_RUN_HISTOGRAM)
     eng.run(engine.make_params(**k2))
     assert eng.read_outputs()["histograms"].tobytes() == O.oracle_run(m1, O.make_params(**k2))["histograms"].tobytes()
+
+
+def test_config3_full_size_one_gpus_share(eng):
+    """BASELINE configs[3] as one GPU of the four sees it: 1 024 replicas of the 1 024-node ring (global replica ids of
+    rank 2), 2 sim-s in two windows; a sample of replicas against the oracle, routing conservation on all of them."""
+    n, base = 1024, 2 * 1024
+    table = hs.consistent_hash_table([f"S{i}" for i in range(1024)], 100, 10000)
+    model = hs.lb_key_table(table, 1024, rate=8192.0)
+    end = 2 * 10**9
+    kw = dict(seed=1234, n_replicas=n, replica_index_base=base, end_ns=end, flags=0)
+    eng.upload(model)
+    eng.run(engine.make_params(window_end_ns=end // 2, **kw))
+    eng.run(engine.make_params(resume=1, **kw))
+    out = eng.read_outputs()
+    s, st = out["summaries"], out["entity_stats"]
+    assert (s["status"] == 0).all() and (s["final_time_ns"] > end).all()
+    for r in (0, 1, 511, 1023):
+        w = O.oracle_run(model, O.make_params(seed=1234, end_ns=end, n_replicas=1, replica_index_base=base + r, flags=0))
+        assert s[r].tobytes() == w["summaries"][0].tobytes(), r
+        assert st[r].tobytes() == w["entity_stats"][0].tobytes(), r
+    src, servers, snk, lb = st[:, 0], st[:, 1:1025], st[:, 1025], st[:, 1026]
+    arrivals = (servers["c0"] + servers["c1"]).sum(axis=1)
+    assert ((lb["c1"] - arrivals >= 0) & (lb["c1"] - arrivals <= 1)).all()          # forwarded == enqueued (+ one in flight)
+    assert ((src["c1"] - lb["c0"] >= 0) & (src["c1"] - lb["c0"] <= 1)).all()
+    assert ((servers["c2"].sum(axis=1) - snk["c0"]) >= 0).all()
+    assert 1.5e4 < float(src["c1"].mean()) < 1.8e4                                   # 8 192 requests/s for 2 s
+
+
+def test_config4_full_size_one_gpus_share(eng):
+    """BASELINE configs[4] as one GPU of the eight sees it: 32 768 replicas = 256 (c, rho) cells x 128 seeds (global ids
+    of rank 5), 100 sim-s; oracle sample, per-cell device reduction == numpy, utilisation per cell == rho."""
+    model = hs.mmc_sweep()
+    n, per_cell, base = 32768, 128, 5 * 32768
+    end = 100 * 10**9
+    kw = dict(seed=1234, n_replicas=n, replica_index_base=base, replicas_per_cell=per_cell, end_ns=end,
+              flags=A.HS_RUN_HISTOGRAM, queue_ring=4096)
+    eng.upload(model)
+    eng.run(engine.make_params(**kw))
+    out = eng.read_outputs()
+    assert (out["summaries"]["status"] == 0).all()
+    for r in (0, 127, 128, 7 * 128 + 5, 255 * 128 + 127):          # incl. the slowest cell (c = 1, rho = 0.99) and the last one
+        w = O.oracle_run(model, O.make_params(**dict(kw, n_replicas=1, replica_index_base=base + r)))
+        assert out["summaries"][r].tobytes() == w["summaries"][0].tobytes(), r
+        assert out["entity_stats"][r].tobytes() == w["entity_stats"][0].tobytes(), r
+        assert out["histograms"][r].tobytes() == w["histograms"][0].tobytes(), r
+    cells = eng.read_cell_totals(256)
+    ref = D.cell_totals_from_outputs(model, out, 256, per_cell, index_base=base)
+    for c, ((d, h), (t, hh)) in enumerate(zip(cells, ref)):
+        assert d["events_processed"] == t.i[0] and d["replicas"] == per_cell and d["sink_events"] == t.i[1], c
+        assert d["min_latency"] == t.fmin and d["max_latency"] == t.fmax
+        assert np.allclose([d["sum_latency"], d["sum_latency_sq"], d["sum_service"]], list(t.fsum), rtol=1e-12)
+        assert np.array_equal(h, hh)
+        cc, rho = model.cells[c]
+        util = d["sum_service"] / (per_cell * 100.0 * cc)
+        assert abs(util - rho) < 0.05, (cc, rho, util)

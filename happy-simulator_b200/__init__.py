@@ -15,7 +15,7 @@ from .model import FlatModel, ModelBuilder, mm1, lb_round_robin, lb_key_table, m
 __version__ = "0.1.0"
 
 from .lowering import lower, consistent_hash_table, hll_table, cms_table, bloom_table, zipf_cdf, UnsupportedModelError  # noqa: F401,E402
-from .sketching import (HyperLogLog, CountMinSketch, BloomFilter, TopK, SketchCollector, TopKCollector,  # noqa: F401,E402
+from .sketching import (HyperLogLog, CountMinSketch, BloomFilter, TopK, ReservoirSampler, SketchCollector, TopKCollector,  # noqa: F401,E402
                         KeyExtractor, FrequencyEstimate, TDigest, QuantileEstimator, LatencyExtractor)  # noqa: F401,E402
 from .api import (  # noqa: F401,E402
     Instant, Duration, Entity, Source, SimpleEventProvider, ConstantRateProfile, ConstantArrivalTimeProvider,

@@ -9,7 +9,7 @@ HS_OK, HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_NO_DEVICE, HS_ERR_STATE, HS_ERR_OVERF
 
 HS_ENT_SOURCE, HS_ENT_SERVER, HS_ENT_SINK, HS_ENT_COUNTER, HS_ENT_LB, HS_ENT_PROBE, HS_ENT_SKETCH = 1, 2, 3, 4, 5, 6, 7
 HS_ENT_CACHE_SERVER = 8
-HS_SK_HLL, HS_SK_CMS, HS_SK_BLOOM, HS_SK_TOPK, HS_SK_TDIGEST = 1, 2, 3, 4, 5
+HS_SK_HLL, HS_SK_CMS, HS_SK_BLOOM, HS_SK_TOPK, HS_SK_TDIGEST, HS_SK_RESERVOIR = 1, 2, 3, 4, 5, 6
 METRICS = {"depth": 0, "active_requests": 1, "utilization": 2, "available_capacity": 3, "stats_accepted": 4,
            "stats_dropped": 5, "events_received": 6, "total": 7, "generated_count": 8}
 HS_ARR_CONSTANT, HS_ARR_POISSON = 0, 1

@@ -822,7 +822,9 @@ class Simulation:
                         import sys as _sys
                         from . import sketching as _sk
                         mod = _sys.modules[type(sk).__module__]
-                        if algo == A.HS_SK_TOPK:
+                        if algo == A.HS_SK_RESERVOIR:
+                            _sk.load_reservoir_state(sk, state)
+                        elif algo == A.HS_SK_TOPK:
                             t = _sk.TopK(int(self.model.entities["i2"][i])); t._load_device_state(state, int(row["c1"]))
                             sk._counters = {it: mod._Counter(item=it, count=c[0], error=c[1]) for it, c in t._counters.items()}
                         else:

@@ -163,7 +163,7 @@ static int validate_model(const hs_model_desc *m)
             break;
         case HS_ENT_SINK: case HS_ENT_COUNTER: break;
         case HS_ENT_SKETCH: {
-            if (e.i0 < HS_SK_HLL || e.i0 > HS_SK_TDIGEST) return fail(HS_ERR_INVALID, "entity %u: unknown sketch algorithm %d", i, e.i0);
+            if (e.i0 < HS_SK_HLL || e.i0 > HS_SK_RESERVOIR) return fail(HS_ERR_INVALID, "entity %u: unknown sketch algorithm %d", i, e.i0);
             if (e.l0 < 0 || e.l0 > INT32_MAX) return fail(HS_ERR_INVALID, "entity %u: sketch key population must be >= 0", i);
             if (e.l0 == 0 && (e.i0 == HS_SK_HLL || e.i0 == HS_SK_CMS || e.i0 == HS_SK_BLOOM)) {    /* hashed on the device */
                 const uint64_t words = e.i0 == HS_SK_CMS ? 2u * (uint64_t)e.i2 : 2u;
@@ -171,6 +171,13 @@ static int validate_model(const hs_model_desc *m)
                 if (e.i0 != HS_SK_HLL && (e.i2 < 1 || e.i3 < 1)) return fail(HS_ERR_INVALID, "entity %u: sketch dimensions must be >= 1", i);
                 if (e.i1 < 0 || !m->sketch_tables || (uint64_t)e.i1 + words > m->n_sketch_table)
                     return fail(HS_ERR_INVALID, "entity %u: sketch seed words out of range", i);
+                break;
+            }
+            if (e.i0 == HS_SK_RESERVOIR) {
+                if (e.i2 < 1) return fail(HS_ERR_INVALID, "entity %u: size must be positive (reservoir.py:68)", i);
+                if (e.i1 < 0 || !m->sketch_tables || (uint64_t)e.i1 + 625u > m->n_sketch_table)
+                    return fail(HS_ERR_INVALID, "entity %u: generator state (625 words) out of range", i);
+                if ((uint32_t)m->sketch_tables[e.i1 + 624] > 624u) return fail(HS_ERR_INVALID, "entity %u: generator index must be <= 624", i);
                 break;
             }
             if (e.l0 == 0 && e.i0 == HS_SK_TOPK) { if (e.i2 < 1) return fail(HS_ERR_INVALID, "entity %u: k must be positive (topk.py:79)", i); break; }
@@ -790,7 +797,7 @@ int hs_read_sketches(hs_engine *E, void *merged, uint64_t merged_bytes)
         } else if (e.i0 == HS_SK_BLOOM) {
             const uint32_t words = (uint32_t)(hs_sketch_row_bytes(&e) / 4u);
             hs_sketch_merge_or_kernel<<<(words + 127) / 128, 128, 0, E->stream>>>(src, E->sk_total, n, words, (uint32_t *)dst);
-        } else if (e.i0 == HS_SK_TOPK || e.i0 == HS_SK_TDIGEST) {
+        } else if (e.i0 == HS_SK_TOPK || e.i0 == HS_SK_TDIGEST || e.i0 == HS_SK_RESERVOIR) {
             continue;                                   /* no merged image: these merges are sequential, done by the host layer */
         } else {
             const uint32_t cells = (uint32_t)e.i2 * (uint32_t)e.i3;

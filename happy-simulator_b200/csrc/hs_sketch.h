@@ -32,6 +32,7 @@ static inline uint64_t hs_sketch_row_bytes(const hs_entity_desc *d)
     if (d->i0 == HS_SK_BLOOM) return (((uint64_t)d->i3 + 63u) / 64u * 8u + 15u) / 16u * 16u;   /* uint64 words */
     if (d->i0 == HS_SK_TOPK) return (16u + (uint64_t)d->i2 * 12u + 15u) / 16u * 16u;           /* n, pad, k slots */
     if (d->i0 == HS_SK_TDIGEST) return 32u + (uint64_t)d->i3 * 16u + ((uint64_t)d->i2 * 8u + 15u) / 16u * 16u;
+    if (d->i0 == HS_SK_RESERVOIR) return 16u + 624u * 4u + ((uint64_t)d->i2 * 4u + 15u) / 16u * 16u;   /* hdr, mt[624], items[size] */
     return ((uint64_t)d->i2 * (uint64_t)d->i3 * 4u + 15u) / 16u * 16u;         /* uint32 counters[depth][width] */
 }
 
@@ -41,7 +42,7 @@ static inline uint64_t hs_sketch_row_merged_bytes(const hs_entity_desc *d)
     if (d->kind != HS_ENT_SKETCH) return 0;
     if (d->i0 == HS_SK_HLL) return (uint64_t)1 << d->i2;
     if (d->i0 == HS_SK_BLOOM) return hs_sketch_row_bytes(d);
-    if (d->i0 == HS_SK_TOPK || d->i0 == HS_SK_TDIGEST) return 0;               /* merged on the host */
+    if (d->i0 == HS_SK_TOPK || d->i0 == HS_SK_TDIGEST || d->i0 == HS_SK_RESERVOIR) return 0;   /* merged on the host */
     return ((uint64_t)d->i2 * (uint64_t)d->i3 * 8u + 15u) / 16u * 16u;
 }
 
@@ -158,6 +159,50 @@ HS_HD int32_t hs_bloom_bit(uint64_t seed, int32_t i, int32_t size_bits, int32_t 
     return (int32_t)((h1 % mm + ((uint64_t)i % mm) * (h2 % mm)) % mm);
 }
 
+/* ---- ReservoirSampler (sketching/reservoir.py:30): Algorithm R driven by a private random.Random(seed), i.e.
+ * CPython's MT19937.  State of one replica: {uint32 n_items, uint32 mti, uint64 total_count}, uint32 mt[624],
+ * int32 items[size].  The row's table holds the generator state the collector was built with (mt[624], mti). */
+typedef struct hs_rs_hdr { uint32_t n_items, mti; uint64_t total; } hs_rs_hdr;   /* 16 B */
+
+/* genrand_uint32 of CPython's _randommodule.c (the MT19937 reference algorithm): all 624 words are regenerated
+ * when the index runs out, then one tempered word is handed out */
+HS_HD uint32_t hs_mt_next(uint32_t *mt, uint32_t *mti)
+{
+    if (*mti >= 624u) {
+        for (uint32_t k = 0; k < 624u; ++k) {
+            const uint32_t y = (mt[k] & 0x80000000u) | (mt[k + 1u < 624u ? k + 1u : 0u] & 0x7fffffffu);
+            mt[k] = mt[k + 397u < 624u ? k + 397u : k - 227u] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        *mti = 0;
+    }
+    uint32_t y = mt[(*mti)++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+
+/* ReservoirSampler._add_one (reservoir.py:100-111): the first `size` items fill the list; after that
+ * j = randint(0, total - 1) = Random._randbelow_with_getrandbits(total): k = total.bit_length(),
+ * r = getrandbits(k) = genrand_uint32() >> (32 - k), redrawn while r >= total; the item replaces slot j < size. */
+HS_SK_FN void hs_reservoir_add(uint8_t *state, const int32_t *tab, uint32_t size, int32_t key)
+{
+    hs_rs_hdr *H = (hs_rs_hdr *)state;
+    uint32_t *mt = (uint32_t *)(state + 16);
+    int32_t *items = (int32_t *)(state + 16 + 624 * 4);
+    if (H->total == 0) {                          /* first add of this replica: the collector's own generator state */
+        for (uint32_t k = 0; k < 624u; ++k) mt[k] = (uint32_t)tab[k];
+        H->mti = (uint32_t)tab[624];
+    }
+    H->total += 1;
+    if (H->n_items < size) { items[H->n_items++] = key; return; }
+    const uint32_t total = (uint32_t)H->total;    /* < 2^32: a replica never processes that many events */
+    int bits = 0;
+    for (uint32_t t = total; t; t >>= 1) ++bits;          /* total.bit_length() */
+    uint32_t mti = H->mti, r;
+    do r = hs_mt_next(mt, &mti) >> (32 - bits); while (r >= total);
+    H->mti = mti;
+    if (r < size) items[r] = key;
+}
+
 /* sketch.add(key): `state` is this replica's state of the row, `tab` the row's table (stride K) */
 HS_SK_FN void hs_sketch_add(uint8_t *state, const int32_t *tab, int32_t algo, int32_t p_or_depth, int32_t width,
                          int64_t K, int32_t key)
@@ -183,6 +228,8 @@ HS_SK_FN void hs_sketch_add(uint8_t *state, const int32_t *tab, int32_t algo, in
             w[bit >> 6] |= 1ull << (bit & 63u);
         }
 #undef HS_SK_SEED64
+    } else if (algo == HS_SK_RESERVOIR) {
+        hs_reservoir_add(state, tab, (uint32_t)p_or_depth, key);
     } else {                                      /* Space-Saving over k counters kept in dict (insertion) order */
         uint32_t *hdr = (uint32_t *)state;
         int32_t *slot = (int32_t *)(state + 16);  /* {item, count, error} x k */

@@ -178,7 +178,7 @@ def merge_sketch_states(model, raw: np.ndarray) -> dict:
     """Host restatement of Engine.read_sketches for per-replica states (hs_outputs.sketches of any
     party): HyperLogLog.merge = register max, CountMinSketch.merge = counter sum, BloomFilter.merge = OR
     over the replicas; TOPK rows (no device image) become a ``TopK`` object merged in replica order."""
-    from .sketching import TDigest, TopK
+    from .sketching import ReservoirSampler, TDigest, TopK
     out = {}
     for i, v in model.sketch_views(raw).items():
         algo = int(model.entities["i0"][i])
@@ -192,6 +192,16 @@ def merge_sketch_states(model, raw: np.ndarray) -> dict:
                 o = TDigest(acc.compression)
                 o._load_device_state(v[r])
                 acc.merge(o)
+            out[i] = acc
+        elif algo == A.HS_SK_RESERVOIR:      # ReservoirSampler.merge draws from the accumulator's generator: replica
+            acc = ReservoirSampler(int(model.entities["i2"][i]))      # order, starting from replica 0's own state
+            for r in range(v.shape[0]):
+                o = ReservoirSampler(acc.capacity)
+                o._load_device_state(v[r], 0)
+                if r == 0:
+                    acc = o
+                else:
+                    acc.merge(o)
             out[i] = acc
         elif algo == A.HS_SK_TOPK:           # TopK.merge is sequential and order dependent: replica 0, 1, 2 ...
             acc = TopK(int(model.entities["i2"][i]))
@@ -217,7 +227,7 @@ def allreduce_sketches(model, merged: dict, device=None, group=None) -> dict:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return merged
     dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
-    host_only = (A.HS_SK_TOPK, A.HS_SK_TDIGEST)
+    host_only = (A.HS_SK_TOPK, A.HS_SK_TDIGEST, A.HS_SK_RESERVOIR)
     ids = sorted(i for i in merged if int(model.entities["i0"][i]) not in host_only)
     hll = [i for i in ids if int(model.entities["i0"][i]) == A.HS_SK_HLL]
     blm = [i for i in ids if int(model.entities["i0"][i]) == A.HS_SK_BLOOM]

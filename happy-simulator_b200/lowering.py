@@ -414,9 +414,13 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None, 
             elif _cls(sk) == "CountMinSketch":
                 b.sketch_cms(name, width=int(sk._width), depth=int(sk._depth), seed=sk._seed,
                              table=None if on_device else cms_table(sk._width, sk._depth, sk._seed, pop))
+            elif _cls(sk) == "ReservoirSampler":     # starts from the state the sampler's own generator is in now
+                if sk._reservoir or sk._total_count:
+                    raise UnsupportedModelError(f"sketch collector {name!r}: the reservoir already holds items")
+                b.sketch_reservoir(name, size=int(sk._size), key_population=pop, state=sk._rng.getstate()[1])
             else:
                 raise UnsupportedModelError(f"sketch collector {name!r}: sketch {_cls(sk)} (supported: HyperLogLog, "
-                                            "CountMinSketch, BloomFilter, TopK)")
+                                            "CountMinSketch, BloomFilter, TopK, ReservoirSampler)")
         elif k == A.HS_ENT_LB:
             strat = o._strategy
             backs = [info.backend for info in o._backends.values() if info.is_healthy]

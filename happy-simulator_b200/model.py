@@ -60,6 +60,8 @@ class FlatModel:
                 a += (16 + int(e["i2"]) * 12 + 15) // 16 * 16          # merged on the host: no merged image
             elif int(e["i0"]) == A.HS_SK_TDIGEST:
                 a += 32 + int(e["i3"]) * 16 + (int(e["i2"]) * 8 + 15) // 16 * 16
+            elif int(e["i0"]) == A.HS_SK_RESERVOIR:                      # hdr, mt[624], items[size]; host-merged
+                a += 16 + 624 * 4 + (int(e["i2"]) * 4 + 15) // 16 * 16
             else:
                 cells = int(e["i2"]) * int(e["i3"])
                 a += (cells * 4 + 15) // 16 * 16; b += (cells * 8 + 15) // 16 * 16
@@ -67,7 +69,8 @@ class FlatModel:
 
     def sketch_views(self, raw: np.ndarray) -> dict:
         """Per-replica states out of hs_outputs.sketches: {entity id: HLL uint8[n, 2^p] | CMS uint32[n, depth,
-        width] | BLOOM uint64[n, words] | TOPK int64[n, 1 + 3 k] = (tracked, then item, count, error per slot)}."""
+        width] | BLOOM uint64[n, words] | TOPK int64[n, 1 + 3 k] = (tracked, then item, count, error per slot) |
+        RESERVOIR int64[n, 3 + 624 + size] = (items held, generator index, items seen, mt[624], the sample slots)}."""
         per = self.sketch_layout()[0]
         out = {}
         for i in self.ids_of(A.HS_ENT_SKETCH):
@@ -85,6 +88,13 @@ class FlatModel:
                 hdr = np.ascontiguousarray(raw[:, per[i]: per[i] + 4]).view(np.uint32).astype(np.int64)
                 sl = np.ascontiguousarray(raw[:, per[i] + 16: per[i] + 16 + 12 * k]).view(np.int32).astype(np.int64)
                 out[i] = np.concatenate([hdr, sl], axis=1)
+            elif int(e["i0"]) == A.HS_SK_RESERVOIR:
+                size = int(e["i2"])
+                hdr = np.ascontiguousarray(raw[:, per[i]: per[i] + 8]).view(np.uint32).astype(np.int64)
+                tot = np.ascontiguousarray(raw[:, per[i] + 8: per[i] + 16]).view(np.int64)
+                mt = np.ascontiguousarray(raw[:, per[i] + 16: per[i] + 16 + 2496]).view(np.uint32).astype(np.int64)
+                it = np.ascontiguousarray(raw[:, per[i] + 2512: per[i] + 2512 + 4 * size]).view(np.int32).astype(np.int64)
+                out[i] = np.concatenate([hdr, tot, mt, it], axis=1)
             else:
                 d, w = int(e["i2"]), int(e["i3"])
                 out[i] = np.ascontiguousarray(raw[:, per[i]: per[i] + d * w * 4]).view(np.uint32).reshape(-1, d, w)
@@ -124,7 +134,7 @@ class FlatModel:
             elif int(e["i0"]) == A.HS_SK_BLOOM:
                 nw = (int(e["i3"]) + 63) // 64
                 out[i] = img[mer[i]: mer[i] + nw * 8].copy().view(np.uint64)
-            elif int(e["i0"]) in (A.HS_SK_TOPK, A.HS_SK_TDIGEST):
+            elif int(e["i0"]) in (A.HS_SK_TOPK, A.HS_SK_TDIGEST, A.HS_SK_RESERVOIR):
                 continue
             else:
                 d, w = int(e["i2"]), int(e["i3"])
@@ -319,6 +329,19 @@ class ModelBuilder:
     def sketch_topk(self, name="TopK", *, k, key_population):
         """TopKCollector(k) / SketchCollector(TopK(k)) on the routing key (Space-Saving; no table)."""
         return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_TOPK, 0, int(k), int(key_population))
+
+    def sketch_reservoir(self, name="Reservoir", *, size, key_population, seed=None, state=None):
+        """SketchCollector(ReservoirSampler(size, seed)) on the routing key (reservoir.py:30).  The row's table is
+        the MT19937 state the sampler starts from: ``state`` = random.Random.getstate()[1] (625 words), or the
+        state of random.Random(seed)."""
+        if state is None:
+            import random
+            state = random.Random(seed).getstate()[1]
+        words = np.array([int(x) for x in state], dtype=np.uint32).view(np.int32)
+        assert words.size == 625
+        off = sum(t.size for t in self._sketch_tables)
+        self._sketch_tables.append(words)
+        return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_RESERVOIR, off, int(size), int(key_population))
 
     def load_balancer(self, name="LB", *, backends, key_table=None):
         off = len(self._backends)

@@ -368,6 +368,89 @@ class TopK:
         self._total_count = int(item_count)
 
 
+class ReservoirSampler:
+    """sketching/reservoir.py:30: a uniform sample of ``size`` stream items (Algorithm R), driven by the sampler's
+    own ``random.Random(seed)``.  On the device the same MT19937 stream runs per replica (csrc/hs_sketch.h,
+    hs_reservoir_add); the state it ends in is written back here, generator included."""
+
+    def __init__(self, size: int, seed: int | None = None):
+        import random
+        if size <= 0:
+            raise ValueError(f"size must be positive, got {size}")
+        self._size = size
+        self._reservoir: list = []
+        self._total_count = 0
+        self._rng = random.Random(seed)
+
+    capacity = property(lambda self: self._size)
+    item_count = property(lambda self: self._total_count)
+    sample_size = property(lambda self: len(self._reservoir))
+    is_full = property(lambda self: len(self._reservoir) >= self._size)
+
+    def add(self, item, count: int = 1) -> None:
+        if count < 0:
+            raise ValueError(f"count must be non-negative, got {count}")
+        for _ in range(count):
+            self._total_count += 1
+            if len(self._reservoir) < self._size:
+                self._reservoir.append(item)
+            else:                                         # kept with probability size / items seen
+                j = self._rng.randint(0, self._total_count - 1)
+                if j < self._size:
+                    self._reservoir[j] = item
+
+    def sample(self) -> list:
+        return list(self._reservoir)
+
+    def __iter__(self):
+        return iter(self._reservoir)
+
+    def __len__(self) -> int:
+        return len(self._reservoir)
+
+    def __getitem__(self, index):
+        return self._reservoir[index]
+
+    def merge(self, other: "ReservoirSampler") -> None:
+        """reservoir.py:140-184: each slot of the new sample is drawn from self with probability
+        seen(self) / seen(both), else from other -- with this sampler's generator."""
+        if not isinstance(other, ReservoirSampler):
+            raise TypeError(f"Can only merge with ReservoirSampler, got {type(other).__name__}")
+        if other._size != self._size:
+            raise ValueError(f"Cannot merge: capacity differs ({self._size} vs {other._size})")
+        combined = self._total_count + other._total_count
+        if combined == 0:
+            return
+        fresh = []
+        for _ in range(min(self._size, combined)):
+            src = self if self._rng.random() < self._total_count / combined else other
+            if src._reservoir:
+                fresh.append(src._reservoir[self._rng.randint(0, len(src._reservoir) - 1)])
+        self._reservoir = fresh[: self._size]
+        self._total_count = combined
+
+    def clear(self) -> None:
+        self._reservoir.clear()
+        self._total_count = 0
+
+    def __repr__(self):
+        return f"ReservoirSampler(capacity={self._size}, sampled={len(self._reservoir)}, seen={self._total_count})"
+
+    def _load_device_state(self, row: np.ndarray, item_count: int) -> None:
+        load_reservoir_state(self, row)
+
+
+def load_reservoir_state(sampler, row) -> None:
+    """Fill a ReservoirSampler (this module's or the reference's: same private fields) from one replica's row of
+    FlatModel.sketch_views: (items held, generator index, items seen, mt[624], sample slots).  A replica that saw no
+    item never started its generator: the sampler's own state stays."""
+    n, mti, total = int(row[0]), int(row[1]), int(row[2])
+    sampler._reservoir = [int(x) for x in row[3 + 624: 3 + 624 + n]]
+    sampler._total_count = total
+    if total:
+        sampler._rng.setstate((3, tuple(int(x) for x in row[3: 3 + 624]) + (mti,), None))
+
+
 class TopKCollector:
     """components/sketching/topk_collector.py:22: SketchCollector specialised to TopK."""
 

@@ -73,8 +73,10 @@ enum {
 enum { HS_SK_HLL = 1, HS_SK_CMS = 2,
        HS_SK_BLOOM = 3,   /* sketching/bloom_filter.py:57 BloomFilter (bit positions per key on the host)      */
        HS_SK_TOPK = 4,    /* sketching/topk.py:37 TopK, Space-Saving (no hashing: pure counter bookkeeping)     */
-       HS_SK_TDIGEST = 5 }; /* sketching/tdigest.py:47 TDigest behind components/sketching/quantile_estimator.py:35;
+       HS_SK_TDIGEST = 5,   /* sketching/tdigest.py:47 TDigest behind components/sketching/quantile_estimator.py:35;
                              the value is the request's latency in seconds (Sink's, common.py:39-41)       */
+       HS_SK_RESERVOIR = 6 }; /* sketching/reservoir.py:30 ReservoirSampler (Algorithm R on its own MT19937): i2 = size,
+                             i1 = offset in sketch_tables of the generator state it starts from (mt[624], index) */
 /* Probe metrics (getattr(target, metric), probe.py:55-62). */
 enum { HS_METRIC_DEPTH = 0, HS_METRIC_ACTIVE_REQUESTS = 1, HS_METRIC_UTILIZATION = 2, HS_METRIC_AVAILABLE_CAPACITY = 3,
        HS_METRIC_STATS_ACCEPTED = 4, HS_METRIC_STATS_DROPPED = 5, HS_METRIC_EVENTS_RECEIVED = 6, HS_METRIC_TOTAL = 7,

@@ -181,6 +181,29 @@ def sketch_quantiles():
     return b.build()
 
 
+def sketch_reservoirs(K=500):
+    """Source -> LoadBalancer -> 3 servers -> ReservoirSampler collectors of size 16, 700 and 5: every sampler
+    goes through several 624-word refills of its MT19937 and plenty of rejected draws (randint -> _randbelow);
+    a key-less source feeds a fourth sampler directly (value None: counted, never sampled)."""
+    import random
+    b = hs.ModelBuilder()
+    src = b.source("Keyed", rate=200.0, key_population=K)
+    plain = b.source("Plain", rate=3.0, poisson=False)
+    servers = [b.server(f"S{i}", concurrency=2, mean_service_s=0.01) for i in range(3)]
+    started = random.Random(99)
+    for _ in range(1000):                       # a generator that is already mid-stream when the run starts
+        started.random()
+    rs = [b.sketch_reservoir("r16", size=16, seed=7, key_population=K),
+          b.sketch_reservoir("r700", size=700, seed=123, key_population=K),
+          b.sketch_reservoir("r5", size=5, state=started.getstate()[1], key_population=K)]
+    idle = b.sketch_reservoir("idle", size=4, seed=1, key_population=K)
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb); b.set_target(plain, idle)
+    for sv, dst in zip(servers, rs):
+        b.set_target(sv, dst)
+    return b.build()
+
+
 def zipf_hot_keys(K=300, s=1.1, n_servers=6):
     """client_id ~ Zipf(s) -> LoadBalancer(ConsistentHash) -> servers -> TopKCollector: hot keys pile on a few
     ring nodes and Space-Saving has real heavy hitters to find (distributions/zipf.py:27-123)."""
@@ -272,6 +295,7 @@ def philox_cases():
     m, seeds = sketch_members()
     c["sketch_bloom_topk"] = (m, dict(seed=23, rid=2, end_s=5, sketch_seeds=seeds))
     c["sketch_tdigest"] = (sketch_quantiles(), dict(seed=29, rid=0, end_s=40))
+    c["sketch_reservoir"] = (sketch_reservoirs(), dict(seed=43, rid=1, end_s=20))
     m, zs = zipf_hot_keys()
     c["zipf_chash_topk"] = (m, dict(seed=37, rid=5, end_s=6, chash_vnodes=30, zipf_s=zs))
     # SURVEY 8(f) row 4, second half: CachingServer / TTL cache behind the two load-balancing strategies

@@ -125,6 +125,13 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
                 objs[i] = QuantileEstimator(names[i], compression=float(e["d0"]),
                                             value_extractor=lambda ev: (ev.time - ev.context["created_at"]).to_seconds())
                 continue
+            if int(e["i0"]) == A.HS_SK_RESERVOIR:    # starts from the generator state in the row's table
+                from happysimulator.sketching.reservoir import ReservoirSampler
+                sk = ReservoirSampler(size=int(e["i2"]))
+                words = model.sketch_tables[int(e["i1"]): int(e["i1"]) + 625].view(np.uint32)
+                sk._rng.setstate((3, tuple(int(x) for x in words), None))
+                objs[i] = SketchCollector(names[i], sketch=sk, value_extractor=extract)
+                continue
             if int(e["i0"]) == A.HS_SK_HLL:
                 sk = HyperLogLog(precision=int(e["i2"]), seed=sk_seed)
             elif int(e["i0"]) == A.HS_SK_BLOOM:
@@ -432,6 +439,15 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
                     bb = np.array(td._buffer, dtype=np.float64)
                     off = per[i] + 32 + cap * 16
                     img[off: off + bb.size * 8] = bb.view(np.uint8)
+            elif algo == A.HS_SK_RESERVOIR:     # {items held, generator index, items seen}, mt[624], items
+                rs = o.sketch
+                st = rs._rng.getstate()[1]
+                if rs._total_count:             # a sampler that saw nothing never touched its generator on the device
+                    img[per[i]: per[i] + 8] = np.array([len(rs._reservoir), st[624]], dtype=np.uint32).view(np.uint8)
+                    img[per[i] + 8: per[i] + 16] = np.array([rs._total_count], dtype=np.int64).view(np.uint8)
+                    img[per[i] + 16: per[i] + 2512] = np.array(st[:624], dtype=np.uint32).view(np.uint8)
+                    it = np.array(rs._reservoir, dtype=np.int32)
+                    img[per[i] + 2512: per[i] + 2512 + it.size * 4] = it.view(np.uint8)
             elif algo == A.HS_SK_TOPK:          # dict order = insertion order (topk.py:116-128)
                 cs = list(o._topk._counters.values())
                 hdr = np.array([len(cs), 0, 0, 0], dtype=np.uint32)
@@ -460,6 +476,8 @@ def run_reference(model, *, seed, rid=0, end_ns, names=None, chash_vnodes=None, 
                 vals = [o.quantile(q) for q in qs] + [o.cdf(v) for v in (0.0, 0.01, 0.05, 0.1, 0.3, 1.0, 5.0)] + \
                        [float(o._tdigest.centroid_count)]
                 ans[i] = np.array(vals, dtype=np.float64).view(np.int64)
+            elif algo == A.HS_SK_RESERVOIR: # the sample, then what the sampler's generator hands out next
+                ans[i] = np.array(o.sketch.sample() + [o.sketch.item_count, o.sketch._rng.getrandbits(32)], dtype=np.int64)
             elif algo == A.HS_SK_TOPK:      # top(): (item, count, error) rows, then max_error and the threshold
                 ans[i] = np.array([v for fe in o.top() for v in (fe.item, fe.count, fe.error)] +
                                   [o.max_error(), o.guaranteed_threshold()], dtype=np.int64)

@@ -213,3 +213,62 @@ def test_api_mirror_writes_the_device_state_back():
     assert abs(hll.cardinality() - len(np.unique(np.nonzero(views[iu][0])[0]))) >= 0            # sanity: runs
     assert 200 < hll.cardinality() < 400
     assert cms.estimate(0) <= freq.events_processed
+
+
+@pytest.mark.parametrize("eng_id", [1, 3])
+def test_reservoir_ensemble_matches_oracle(eng, eng_id):
+    """ReservoirSampler rows: every replica runs its own copy of the sampler's MT19937 (624-word refills, rejected
+    draws of randint); sample, count and generator state equal the oracle's byte for byte -- and through the
+    fixture philox_sketch_reservoir the reference's.  The merge over replicas is the class's own, on the host."""
+    K = 2000
+    b = hs.ModelBuilder()
+    src = b.source(rate=900.0, key_population=K)
+    servers = [b.server(f"S{i}", concurrency=2, mean_service_s=0.004) for i in range(4)]
+    rs = [b.sketch_reservoir("r8", size=8, seed=3, key_population=K), b.sketch_reservoir("r300", size=300, seed=4, key_population=K)]
+    lb = b.load_balancer(backends=servers)
+    b.set_target(src, lb)
+    for k, sv in enumerate(servers):
+        b.set_target(sv, rs[k % 2])
+    model = b.build()
+    kw = dict(seed=51, end_ns=4 * 10**9, n_replicas=23, record_cap=40000, sample_cap=16, service_cap=4000)
+    eng.upload(model)
+    eng.run(engine.make_params(engine=eng_id, **kw))
+    got = eng.read_outputs()
+    want = O.oracle_run(model, O.make_params(**kw))
+    assert_same(got, want)
+    assert got["sketches"].tobytes() == want["sketches"].tobytes()
+    views = model.sketch_views(got["sketches"])
+    assert int(views[rs[0]][:, 2].min()) > 1500 and (views[rs[0]][:, 0] == 8).all() and (views[rs[1]][:, 0] == 300).all()
+    assert len({tuple(v[3 + 624:]) for v in views[rs[0]]}) == 23            # different key streams, different samples
+    assert eng.read_sketches() == {}                                        # host-merged rows only
+    merged = D.merge_sketch_states(model, got["sketches"])[rs[0]]
+    assert merged.item_count == int(got["entity_stats"][:, rs[0]]["c1"].sum()) and len(merged) == 8
+    pool = {int(x) for v in views[rs[0]] for x in v[3 + 624:]}
+    assert set(merged.sample()) <= pool
+
+
+def test_reservoir_fixture_runs_in_windows(eng):
+    model, kw, z = G.load("philox_sketch_reservoir")
+    caps = dict(G.caps(z), n_replicas=1, seed=kw["seed"], rid_base=kw["rid_base"])
+    eng.upload(model)
+    eng.run(engine.make_params(end_ns=kw["end_ns"], window_end_ns=3 * 10**9, **caps))
+    eng.run(engine.make_params(end_ns=kw["end_ns"], window_end_ns=11 * 10**9 + 1, resume=1, **caps))
+    eng.run(engine.make_params(end_ns=kw["end_ns"], resume=1, **caps))
+    G.check_against(z, eng.read_outputs())
+
+
+def test_api_mirror_reservoir_sampler_continues_its_generator():
+    import random
+    K = 700
+    sampler = hs.ReservoirSampler(10, seed=77)
+    coll = hs.SketchCollector("sample", sampler)
+    src = hs.Source.poisson(rate=500.0, event_provider=hs.SimpleEventProvider(coll, context_fn=hs.UniformKeyContext(K)))
+    sim = hs.Simulation(end_time=hs.Instant.from_seconds(3.0), sources=[src], entities=[coll], seed=5)
+    sim.run()
+    n = coll.events_processed
+    twin = hs.ReservoirSampler(10, seed=77)
+    L = O.lib()
+    for j in range(n):
+        twin.add(int(L.hs_cpu_uniform(5, 0, A.HS_STREAM_ROUTING | (sim.objects.index(src) << 8), j) * K))
+    assert n > 1200 and sampler.item_count == n and sampler.sample() == twin.sample()
+    assert sampler._rng.getstate() == twin._rng.getstate() != random.Random(77).getstate()

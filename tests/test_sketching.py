@@ -64,6 +64,16 @@ def test_mirror_classes_give_the_reference_answers(name):
                    [float(sk.centroid_count)]
             assert np.array(vals, dtype=np.float64).view(np.int64).tolist() == [int(x) for x in want]   # bit for bit
             assert sk.percentile(50) == sk.quantile(0.5) and sk.min <= sk.quantile(0.5) <= sk.max
+        elif int(e["i0"]) == A.HS_SK_RESERVOIR:
+            sk = hs.ReservoirSampler(size=int(e["i2"]))
+            untouched = sk._rng.getstate()
+            sk._load_device_state(state[0], added)
+            assert sk.sample() == [int(x) for x in want[:-2]] and sk.item_count == added == int(want[-2])
+            assert len(sk) == min(added, sk.capacity) and sk.is_full == (added >= sk.capacity)
+            if added:                       # the generator continues where the reference's own would
+                assert sk._rng.getrandbits(32) == int(want[-1])
+            else:
+                assert sk._rng.getstate() == untouched
         elif int(e["i0"]) == A.HS_SK_TOPK:
             sk = hs.TopK(k=int(e["i2"]))
             sk._load_device_state(state[0], added)

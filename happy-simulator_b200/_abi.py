@@ -3,12 +3,13 @@ from __future__ import annotations
 
 import ctypes as C
 
-HS_ABI_VERSION = 3
+HS_ABI_VERSION = 4
 
 HS_OK, HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_NO_DEVICE, HS_ERR_STATE, HS_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
 
 HS_ENT_SOURCE, HS_ENT_SERVER, HS_ENT_SINK, HS_ENT_COUNTER, HS_ENT_LB, HS_ENT_PROBE, HS_ENT_SKETCH = 1, 2, 3, 4, 5, 6, 7
 HS_ENT_CACHE_SERVER = 8
+HS_ENT_REMOTE = 9
 HS_SK_HLL, HS_SK_CMS, HS_SK_BLOOM, HS_SK_TOPK, HS_SK_TDIGEST, HS_SK_RESERVOIR = 1, 2, 3, 4, 5, 6
 METRICS = {"depth": 0, "active_requests": 1, "utilization": 2, "available_capacity": 3, "stats_accepted": 4,
            "stats_dropped": 5, "events_received": 6, "total": 7, "generated_count": 8}
@@ -27,8 +28,9 @@ EVENT_KIND_NAMES = ["SOURCE_TICK", "REQ_LB", "REQ_ENQUEUE", "NOTIFY", "POLL", "D
 
 HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH, HS_ST_TRACE_EXHAUSTED, HS_ST_EVENT_LIMIT = 1, 2, 4, 8, 16
 HS_ST_SKETCH_OVERFLOW = 32
+HS_ST_LINK_OVERFLOW = 64
 
-HS_STREAM_ARRIVAL, HS_STREAM_SERVICE, HS_STREAM_ROUTING = 0, 1, 2
+HS_STREAM_ARRIVAL, HS_STREAM_SERVICE, HS_STREAM_ROUTING, HS_STREAM_LINK_LOSS, HS_STREAM_LINK_LATENCY = 0, 1, 2, 3, 4
 
 HS_TOTALS_I64, HS_TOTALS_F64_SUM = 8, 3
 
@@ -44,12 +46,17 @@ class ModelDesc(C.Structure):
                 ("entities", C.POINTER(EntityDesc)),
                 ("n_backends", C.c_uint32), ("key_population", C.c_uint32),
                 ("backends", C.POINTER(C.c_int32)), ("key_table", C.POINTER(C.c_int32)),
-                ("n_cells", C.c_uint32), ("reserved", C.c_uint32),
+                ("n_cells", C.c_uint32), ("outbox_cap", C.c_uint32),
                 ("cell_d0", C.POINTER(C.c_double)), ("cell_i0", C.POINTER(C.c_int32)),
-                ("n_profiles", C.c_uint32), ("reserved2", C.c_uint32), ("profiles", C.c_void_p),
+                ("n_profiles", C.c_uint32), ("inbox_cap", C.c_uint32), ("profiles", C.c_void_p),
                 ("n_sketch_table", C.c_uint32), ("n_key_cdf", C.c_uint32),
                 ("sketch_tables", C.POINTER(C.c_int32)), ("key_cdf", C.POINTER(C.c_double)),
                 ("profile_table", C.POINTER(C.c_double)), ("n_profile_table", C.c_uint64)]
+
+
+class LinkDesc(C.Structure):
+    _fields_ = [("latency_kind", C.c_int32), ("stream", C.c_int32), ("latency_mean_s", C.c_double),
+                ("packet_loss", C.c_double)]
 
 
 class RunParams(C.Structure):
@@ -122,6 +129,8 @@ STATS_DTYPE = _np.dtype([("c0", "<i8"), ("c1", "<i8"), ("c2", "<i8"), ("c3", "<i
 RECORD_DTYPE = _np.dtype([("time_ns", "<i8"), ("sort_index", "<u4"), ("kind", "u1"), ("pad", "u1"),
                           ("entity", "<u2")])
 SAMPLE_DTYPE = _np.dtype([("completion_ns", "<i8"), ("latency_s", "<f8")])
+XEVENT_DTYPE = _np.dtype([("time_ns", "<i8"), ("sort_index", "<u8"), ("created_ns", "<i8"), ("aux", "<u8"), ("key", "<i4"),
+                          ("ent", "<i4")])        # hs_xevent, 40 bytes
 ENTITY_DTYPE = _np.dtype([("kind", "<i4"), ("target", "<i4"), ("i0", "<i4"), ("i1", "<i4"), ("i2", "<i4"),
                           ("i3", "<i4"), ("l0", "<i8"), ("d0", "<f8"), ("d1", "<f8")])
 assert SUMMARY_DTYPE.itemsize == 56 and STATS_DTYPE.itemsize == 64 and RECORD_DTYPE.itemsize == 16

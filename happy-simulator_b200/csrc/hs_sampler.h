@@ -102,6 +102,8 @@ HS_HD hs_u32x4 hs_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t 
 #define HS_STREAM_ARRIVAL 0u
 #define HS_STREAM_SERVICE 1u
 #define HS_STREAM_ROUTING 2u
+#define HS_STREAM_LINK_LOSS 3u      /* WindowedCoordinator._rng.random(), coordinator.py:204 */
+#define HS_STREAM_LINK_LATENCY 4u   /* PartitionLink.latency.sample(), coordinator.py:209 (| latency object id << 8) */
 
 /* 53-bit uniform in [0,1) from two 32-bit words, the genrand_res53 recipe both
  * reference generators use (CPython random.random(), numpy legacy

@@ -29,6 +29,8 @@ class FlatModel:
     profile_table: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))   # STEP profiles: breakpoints + rates
     sketch_tables: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     key_cdf: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))
+    outbox_cap: int = 0                       # linked partitions: cross-partition events a replica can emit per window
+    inbox_cap: int = 0                        # ... and receive per barrier
 
     @property
     def n_entities(self) -> int:
@@ -152,6 +154,7 @@ class FlatModel:
         d = A.ModelDesc()
         d.abi_version = A.HS_ABI_VERSION
         d.n_entities = self.n_entities
+        d.outbox_cap, d.inbox_cap = int(self.outbox_cap), int(self.inbox_cap)
         d.entities = ents.ctypes.data_as(C.POINTER(A.EntityDesc))
         d.n_backends = be.shape[0]
         d.key_population = kt.shape[0]
@@ -342,6 +345,11 @@ class ModelBuilder:
         off = sum(t.size for t in self._sketch_tables)
         self._sketch_tables.append(words)
         return self._add(name, A.HS_ENT_SKETCH, -1, A.HS_SK_RESERVOIR, off, int(size), int(key_population))
+
+    def remote(self, name="Remote", *, link, dest_entity):
+        """Stand-in for an entity of another partition (HS_ENT_REMOTE): events sent to it leave through the
+        partition's outgoing link number ``link`` and arrive at entity ``dest_entity`` of the link's destination."""
+        return self._add(name, A.HS_ENT_REMOTE, -1, int(link), int(dest_entity))
 
     def load_balancer(self, name="LB", *, backends, key_table=None):
         off = len(self._backends)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HS_ABI_VERSION 3u
+#define HS_ABI_VERSION 4u
 
 typedef enum hs_status {
     HS_OK = 0,
@@ -53,7 +53,7 @@ enum {
     HS_ENT_SKETCH = 7,   /* components/sketching/sketch_collector.py:24 SketchCollector over a HyperLogLog
                             (sketching/hyperloglog.py:43) or CountMinSketch (count_min_sketch.py:52) whose
                             value_extractor reads the request's routing key                           */
-    HS_ENT_CACHE_SERVER = 8 /* examples/load-balancing/common.py:100-275 CachingServer: a QueuedResource without a
+    HS_ENT_CACHE_SERVER = 8, /* examples/load-balancing/common.py:100-275 CachingServer: a QueuedResource without a
                             concurrency limit (Entity.has_capacity() is True) whose generator yields the cache-read
                             latency, on a miss the datastore latency, then the processing latency; one TTL cache
                             entry per customer key (TTLEviction, components/datastore/eviction_policies.py:154-226).
@@ -66,6 +66,13 @@ enum {
                             insertion times (seconds; 0 = not cached), in the hs_outputs.sketches region.
                             hs_entity_stats: c0 accepted, c1 dropped, c2 requests_processed, c3 cache_misses,
                             f0 cache_hits, f1 cache_size (as doubles)                                   */
+    HS_ENT_REMOTE = 9    /* stand-in for an entity that lives in ANOTHER partition of a ParallelSimulation
+                            (parallel/simulation.py:31, parallel/routing.py:17-63): an event whose target is this row
+                            is never scheduled here -- the partition's router puts it, with its send time, into the
+                            partition's outbox, and the coordinator delivers it at the next window barrier
+                            (parallel/coordinator.py:182-227).  i0 = slot of the outgoing link in the hs_link_desc
+                            array handed to hs_coordinator_exchange, i1 = the entity's id in the destination
+                            partition's model.  hs_entity_stats: c0 = events sent through it                 */
 };
 /* Sketch algorithms of a SKETCH row.  Both hash the item with SHA-256 (hyperloglog.py:128-135,
  * count_min_sketch.py:136-155); the items are the routing keys 0..population-1, so the host evaluates
@@ -138,13 +145,15 @@ typedef struct hs_model_desc {
     /* Parameter sweep ("cells"): replica r belongs to cell r / replicas_per_cell; a cell
      * overrides d0 / i0 of every entity.  NULL = no override.                                 */
     uint32_t n_cells;
-    uint32_t reserved;
+    uint32_t outbox_cap;           /* linked partitions: cross-partition events one replica can emit per window
+                                      (0: the model has no REMOTE rows)                                        */
     const double *cell_d0;         /* [n_cells][n_entities] or NULL */
     const int32_t *cell_i0;        /* [n_cells][n_entities] or NULL */
     /* Non-constant rate profiles (load/profile.py LinearRampProfile, SpikeProfile): arrival times
      * come from the reference's adaptive-Simpson + Brent path (arrival_time_provider.py:84-144). */
     uint32_t n_profiles;
-    uint32_t reserved2;
+    uint32_t inbox_cap;            /* linked partitions: cross-partition events one replica can receive per
+                                      barrier (0: no link ends in this partition)                            */
     const struct hs_profile_desc *profiles;   /* 40 bytes each, see below */
     /* Per-key hash results of the SKETCH rows (row i0/i1/i2/i3/l0: algorithm, table offset, p | depth,
      * CMS width, K).  HLL: [2][K] = register index (hash >> (64 - p)) and run length (leading zeros of
@@ -225,6 +234,7 @@ typedef struct hs_run_params {
 #define HS_ST_TRACE_EXHAUSTED 8u  /* ran out of externally supplied draws    */
 #define HS_ST_EVENT_LIMIT 16u     /* hs_run_params.max_events reached        */
 #define HS_ST_SKETCH_OVERFLOW 32u /* a TDigest outgrew its centroid capacity */
+#define HS_ST_LINK_OVERFLOW 64u   /* a partition's outbox or inbox filled up */
 
 typedef struct hs_replica_summary {
     int64_t events_processed;  /* SimulationSummary.total_events_processed (simulation.py:553) */
@@ -381,6 +391,48 @@ int hs_read_cell_totals(hs_engine *e, hs_cell_totals *out, uint32_t n_cells);
 /* Merge the last run's per-replica sketches on the device (layout: hs_sketch_layout's merged image)
  * and copy the image to the host; what a multi-GPU run all-reduces (max for HLL bytes, sum for CMS). */
 int hs_read_sketches(hs_engine *e, void *merged, uint64_t merged_bytes);
+
+/* ---- linked partitions (parallel/coordinator.py:28-227) --------------------------------------------
+ * A ParallelSimulation with PartitionLinks is one engine per partition (each with the same replicas) plus one
+ * coordinator.  Per window the host layer runs every partition with hs_run(end_ns = window end, resume = window > 0)
+ * -- Simulation._run_window = _execute_until(window_end), core/simulation.py:527-541: the loop test is on the LAST
+ * processed time, so a partition also processes its first event beyond the window end -- and then calls
+ * hs_coordinator_exchange once per partition, in partition order (WindowedCoordinator._exchange_events walks the
+ * outboxes in that order).  An event delivered earlier than the destination's clock is "time travel" and is
+ * skipped, uncounted, exactly as the reference's loop skips it (core/simulation.py:479-489). */
+typedef struct hs_xevent {        /* one cross-partition event, 40 bytes */
+    int64_t time_ns;              /* outbox: send time (the sender's clock); inbox: arrival time            */
+    uint64_t sort_index;          /* Event._sort_index, from the SENDER's per-heap counter (event_heap.py:48) */
+    int64_t created_ns;           /* context["created_at"]                                                   */
+    uint64_t aux;                 /* reserved (0)                                                            */
+    int32_t key;                  /* context["metadata"]["client_id"], -1 if none                            */
+    int32_t ent;                  /* outbox: the REMOTE row it was sent to; inbox: target entity id          */
+} hs_xevent;
+
+typedef struct hs_link_desc {     /* parallel/link.py:18 PartitionLink with a latency override               */
+    int32_t latency_kind;         /* HS_SVC_CONSTANT | HS_SVC_EXPONENTIAL: event.time = send_time + sample()  */
+    int32_t stream;               /* id of the latency OBJECT: links that share one object share its draws    */
+    double latency_mean_s;
+    double packet_loss;           /* in [0, 1): one coordinator draw per event when > 0 (coordinator.py:204)  */
+} hs_link_desc;
+
+typedef struct hs_coordinator hs_coordinator;
+/* Per-replica coordinator state on `device`: the draw counters of the loss stream and of n_streams latency
+ * streams, delivered / lost totals.  Philox key and replica word of replica r as in hs_run_params. */
+int hs_coordinator_create(int device, void *cuda_stream, uint32_t n_replicas, uint32_t n_streams,
+                          uint64_t seed, uint64_t seed_stride, uint32_t rid_base, uint32_t rid_stride,
+                          uint32_t replica_index_base, hs_coordinator **out);
+void hs_coordinator_destroy(hs_coordinator *c);
+/* Drain src's outboxes: every event goes through its REMOTE row's link links[row.i0] (loss draw, then
+ * time = send time + latency sample) into the inbox of dsts[row.i0] with target row.i1; the next hs_run of that
+ * engine pushes its inbox into the replicas' heaps before the first pop (Simulation.schedule, :195-206). */
+int hs_coordinator_exchange(hs_coordinator *c, hs_engine *src, uint32_t n_links, const hs_link_desc *links,
+                            hs_engine *const *dsts);
+/* totals over all replicas since create: events delivered into inboxes, events lost */
+int hs_coordinator_read(hs_coordinator *c, uint64_t *delivered, uint64_t *lost);
+/* Copy the current outboxes / inboxes to the host: buf[n_replicas][cap], counts[n_replicas] (tests, debugging). */
+int hs_read_outbox(hs_engine *e, hs_xevent *buf, uint32_t *counts);
+int hs_read_inbox(hs_engine *e, hs_xevent *buf, uint32_t *counts);
 
 /* Device pointer/size of the last run's totals (for the NCCL allreduce done by
  * the host layer on torch.distributed; layout = hs_totals). */

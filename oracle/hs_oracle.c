@@ -173,6 +173,11 @@ typedef struct orun {
     hs_sink_sample *smp; int64_t n_smp;
     uint32_t *hist;
     double *svc; int64_t n_svc;
+    int64_t processed; uint64_t hash;     /* events processed so far, running order hash               */
+    /* linked partitions: this partition's outbox (routing.py:17-63), drained by the coordinator at every barrier */
+    hs_xevent *outbox; uint32_t outbox_n, outbox_cap;
+    uint32_t r;                           /* replica slot in the outputs                                */
+    const hs_outputs *out;
 } orun;
 
 static void q_push(oent *s, const oreq *r)
@@ -428,7 +433,16 @@ static void handle(orun *R, oev *e)
         if (E->d.target >= 0) {           /* Entity.forward, entity.py:83-105     */
             oev f = new_event(R, R->now, request_kind_for(R, E->d.target), E->d.target);
             f.created_at = e->created_at; f.req_id = e->req_id; f.key = e->key;
-            heap_push(&R->heap, &f);
+            if (R->ents[E->d.target].d.kind == HS_ENT_REMOTE) {
+                /* the partition's event router (routing.py:40-61): a target outside this partition -> the event,
+                 * already constructed (its sort index is spent), goes to the outbox with the current time */
+                R->ents[E->d.target].received++;
+                if (R->outbox_n < R->outbox_cap) {
+                    hs_xevent *x = &R->outbox[R->outbox_n++];
+                    x->time_ns = R->now; x->sort_index = f.idx; x->created_ns = f.created_at; x->aux = 0;
+                    x->key = f.key; x->ent = E->d.target;
+                } else R->status |= HS_ST_LINK_OVERFLOW;
+            } else heap_push(&R->heap, &f);
         }
         if (e->poll_hook >= 0) run_poll_hook(R, e->poll_hook);
         break;
@@ -500,11 +514,13 @@ static void handle(orun *R, oev *e)
 
 typedef struct { const double *targets; uint64_t n_targets; const double *service; uint64_t n_service; } otrace;
 
-static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t r,
-                        const hs_outputs *out, const otrace *tr)
+/* Simulation.__init__ of one replica: entity state, output cursors, the sources' first ticks */
+static void orun_init(orun *Rp, const hs_model_desc *m, const hs_run_params *p, uint32_t r,
+                      const hs_outputs *out, const otrace *tr)
 {
-    orun R; memset(&R, 0, sizeof R);
-    R.m = m; R.p = p;
+#define R (*Rp)
+    memset(&R, 0, sizeof R);
+    R.m = m; R.p = p; R.r = r; R.out = out;
     if (tr) { R.trace_targets = tr->targets; R.n_trace_targets = tr->n_targets;
               R.trace_service = tr->service; R.n_trace_service = tr->n_service; }
     uint32_t ne = m->n_entities;
@@ -566,32 +582,43 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
     /* run(): _active_sim_context installs the per-heap counter, again from 0
      * (event_heap.py:48, sim_future.py:64-73). */
     R.counter = 0;
+    R.processed = 0;
+    R.hash = HS_HASH_INIT;
+#undef R
+}
 
-    int64_t processed = 0;
-    uint64_t h = HS_HASH_INIT;
-    /* _execute_until, simulation.py:472: the test is on the LAST processed time. */
-    int windowed = (p->window_end_ns >= 0 && p->window_end_ns < p->end_ns);
-    while (R.heap.n && R.now <= p->end_ns) {
-        /* windowed run (core/simulation.py:527-541 cut at event boundaries): pause
-         * before the first event later than the window end; resume is not modelled
-         * here -- a paused prefix is compared against the device's paused prefix. */
-        if (windowed && R.heap.a[0].time > p->window_end_ns) break;
-        if (p->max_events > 0 && processed >= p->max_events) { R.status |= HS_ST_EVENT_LIMIT; break; }
+/* _execute_until(end_ns) (simulation.py:449-505): the test is on the LAST processed time, so the first event
+ * beyond end_ns is still processed.  cut_ns >= 0: stop before the first event later than cut_ns instead (a run cut
+ * at an event boundary, hs_run_params.window_end_ns). */
+static void orun_until(orun *Rp, int64_t end_ns, int64_t cut_ns)
+{
+#define R (*Rp)
+    const hs_run_params *p = R.p;
+    while (R.heap.n && R.now <= end_ns) {
+        if (cut_ns >= 0 && R.heap.a[0].time > cut_ns) break;
+        if (p->max_events > 0 && R.processed >= p->max_events) { R.status |= HS_ST_EVENT_LIMIT; break; }
         oev e = heap_pop(&R.heap);
         if (e.time < R.now) continue;     /* "time travel": skipped, not counted (simulation.py:479-489) */
         R.now = e.time;
         uint64_t w1 = hs_record_word1(e.idx, (uint32_t)e.kind, (uint32_t)e.ent);
-        h = hs_hash_step(h, e.time, w1);
+        R.hash = hs_hash_step(R.hash, e.time, w1);
         if (R.rec && p->record_cap) {
-            hs_event_record *rc = &R.rec[processed % (int64_t)p->record_cap];
+            hs_event_record *rc = &R.rec[R.processed % (int64_t)p->record_cap];
             rc->time_ns = e.time; rc->sort_index = (uint32_t)e.idx;
             rc->kind = (uint8_t)e.kind; rc->pad = 0; rc->entity = (uint16_t)e.ent;
         }
-        if (!(p->flags & HS_RUN_ORDER_HASH)) h = 0;
-        processed++;
+        if (!(p->flags & HS_RUN_ORDER_HASH)) R.hash = 0;
+        R.processed++;
         handle(&R, &e);
     }
+#undef R
+}
 
+static void orun_finish(orun *Rp)
+{
+#define R (*Rp)
+    const hs_outputs *out = R.out; const uint32_t r = R.r; const uint32_t ne = R.m->n_entities;
+    const int64_t processed = R.processed; const uint64_t h = R.hash;
     if (out->summaries) {
         hs_replica_summary *s = &out->summaries[r];
         s->events_processed = processed; s->final_time_ns = R.now; s->order_hash = h;
@@ -609,7 +636,7 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
                 st->f0 = E->total_service; break;
             case HS_ENT_SINK:
                 st->c0 = E->received; st->f0 = hs_neumaier_result(E->sum, E->comp); st->f1 = E->sumsq; st->f2 = E->mn; st->f3 = E->mx; break;
-            case HS_ENT_COUNTER: st->c0 = E->received; break;
+            case HS_ENT_COUNTER: case HS_ENT_REMOTE: st->c0 = E->received; break;
             case HS_ENT_PROBE:
                 st->c0 = E->received; st->f0 = hs_neumaier_result(E->sum, E->comp); st->f2 = E->mn; st->f3 = E->mx; break;
             case HS_ENT_SKETCH: st->c0 = E->sk_processed; st->c1 = E->sk_added; break;
@@ -623,6 +650,19 @@ static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t
     }
     for (uint32_t i = 0; i < ne; ++i) { free(R.ents[i].q); if (R.ents[i].cache_own) free(R.ents[i].cache_ins); }
     free(R.ents); free(R.heap.a);
+#undef R
+}
+
+static void run_replica(const hs_model_desc *m, const hs_run_params *p, uint32_t r,
+                        const hs_outputs *out, const otrace *tr)
+{
+    orun R;
+    orun_init(&R, m, p, r, out, tr);
+    /* windowed run (core/simulation.py:527-541 cut at event boundaries): pause before the first event later
+     * than the window end; resume is not modelled here -- a paused prefix is compared against the device's. */
+    const int windowed = (p->window_end_ns >= 0 && p->window_end_ns < p->end_ns);
+    orun_until(&R, p->end_ns, windowed ? p->window_end_ns : -1);
+    orun_finish(&R);
 }
 
 /* ---- exported --------------------------------------------------------- */
@@ -631,6 +671,72 @@ int hs_oracle_run(const hs_model_desc *m, const hs_run_params *p, const hs_outpu
 {
     if (!m || !p || !out || m->abi_version != HS_ABI_VERSION) return HS_ERR_INVALID;
     for (uint32_t r = 0; r < p->n_replicas; ++r) run_replica(m, p, r, out, NULL);
+    return HS_OK;
+}
+
+/* ---- linked partitions: ParallelSimulation with PartitionLinks (parallel/simulation.py:31-284) ------------
+ * One orun per partition; WindowedCoordinator.run (coordinator.py:75-172): for every window, every partition runs
+ * _run_window(window_end) = _execute_until(window_end) -- the per-heap sort-index counters make the partitions'
+ * results independent of the order the thread pool runs them in (event_heap.py:46-48) -- then _exchange_events
+ * (coordinator.py:182-227) walks the outboxes in partition order: one loss draw from the coordinator's generator
+ * when the link loses packets, event.time = send_time + link.latency.sample(), Simulation.schedule() = heap push.
+ * links[p][k] / link_dst[p][k]: the link a REMOTE row with i0 = k of partition p sends through, and the partition
+ * it ends in.  window_ends: the coordinator's window ends in ns (computed in float seconds by the host layer,
+ * coordinator.py:88-95).  The coordinator's draws: HS_STREAM_LINK_LOSS / HS_STREAM_LINK_LATENCY | stream << 8 of
+ * Philox key cseed + g * cseed_stride, replica word crid_base + g * crid_stride (g = global replica index). */
+int hs_oracle_run_linked(uint32_t n_parts, const hs_model_desc *const *models, const hs_run_params *const *params,
+                         const hs_outputs *const *outs, const hs_link_desc *const *links, const uint32_t *const *link_dst,
+                         const int64_t *window_ends, uint32_t n_windows, uint32_t n_streams,
+                         uint64_t cseed, uint64_t cseed_stride, uint32_t crid_base, uint32_t crid_stride,
+                         uint64_t *delivered, uint64_t *lost)
+{
+    if (!n_parts || !models || !params || !outs || !window_ends) return HS_ERR_INVALID;
+    for (uint32_t q = 0; q < n_parts; ++q)
+        if (!models[q] || models[q]->abi_version != HS_ABI_VERSION || params[q]->n_replicas != params[0]->n_replicas) return HS_ERR_INVALID;
+    const uint32_t n = params[0]->n_replicas;
+    orun *R = (orun *)calloc(n_parts, sizeof(orun));
+    uint64_t *lat_draws = (uint64_t *)calloc(n_streams ? n_streams : 1, sizeof(uint64_t));
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint32_t g = params[0]->replica_index_base + r;
+        const uint64_t seed = cseed + (uint64_t)g * cseed_stride;
+        const uint32_t rid = crid_base + g * crid_stride;
+        uint64_t loss_draws = 0, n_del = 0, n_lost = 0;
+        memset(lat_draws, 0, (n_streams ? n_streams : 1) * sizeof(uint64_t));
+        for (uint32_t q = 0; q < n_parts; ++q) {
+            orun_init(&R[q], models[q], params[q], r, outs[q], NULL);
+            R[q].outbox_cap = models[q]->outbox_cap;
+            R[q].outbox = (hs_xevent *)calloc(R[q].outbox_cap ? R[q].outbox_cap : 1, sizeof(hs_xevent));
+        }
+        for (uint32_t w = 0; w < n_windows; ++w) {
+            for (uint32_t q = 0; q < n_parts; ++q) orun_until(&R[q], window_ends[w], -1);      /* 1. EXECUTE */
+            for (uint32_t q = 0; q < n_parts; ++q) {                                            /* 2. EXCHANGE */
+                for (uint32_t k = 0; k < R[q].outbox_n; ++k) {
+                    const hs_xevent *x = &R[q].outbox[k];
+                    const hs_entity_desc *rem = &models[q]->entities[x->ent];
+                    const hs_link_desc *lk = &links[q][rem->i0];
+                    orun *D = &R[link_dst[q][rem->i0]];
+                    if (lk->packet_loss > 0.0 &&
+                        hs_uniform(seed, rid, HS_STREAM_LINK_LOSS, loss_draws++) < lk->packet_loss) { n_lost++; continue; }
+                    int64_t lat;
+                    if (lk->latency_kind == HS_SVC_EXPONENTIAL) {
+                        const double u = hs_uniform(seed, rid, HS_STREAM_LINK_LATENCY | ((uint32_t)lk->stream << 8), lat_draws[lk->stream]++);
+                        lat = hs_exp_latency_ns(u, 1.0 / lk->latency_mean_s);
+                    } else lat = hs_seconds_to_ns(lk->latency_mean_s);
+                    oev e; memset(&e, 0, sizeof e);
+                    e.time = x->time_ns + lat; e.idx = x->sort_index; e.ent = rem->i1;
+                    e.kind = request_kind_for(D, rem->i1);
+                    e.created_at = x->created_ns; e.key = x->key; e.lb_hook = -1; e.poll_hook = -1;
+                    heap_push(&D->heap, &e);
+                    n_del++;
+                }
+                R[q].outbox_n = 0;
+            }
+        }
+        for (uint32_t q = 0; q < n_parts; ++q) { free(R[q].outbox); orun_finish(&R[q]); }
+        if (delivered) delivered[r] = n_del;
+        if (lost) lost[r] = n_lost;
+    }
+    free(lat_draws); free(R);
     return HS_OK;
 }
 

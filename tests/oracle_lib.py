@@ -118,6 +118,36 @@ def oracle_run(model: happysim_b200.FlatModel, p: A.RunParams, r0=None, r1=None)
     return bufs
 
 
+def oracle_run_linked(lm, params: list, *, end_ns, cseed, cseed_stride=0, crid_base=None, crid_stride=None):
+    """A linked run (happysim_b200.linked.LinkedModel) on the oracle: per partition the usual output buffers,
+    plus per-replica counts of delivered / lost cross-partition events."""
+    L = lib()
+    nP = lm.n_partitions
+    descs = [m.desc() for m in lm.models]
+    outs = [alloc_outputs(m.n_entities, p, m.sketch_layout()[2]) for m, p in zip(lm.models, params)]
+    ends = np.array(lm.window_ends(end_ns), dtype=np.int64)
+    link_arrs, dst_arrs = [], []
+    for q in range(nP):
+        arr, dst = lm.link_descs(q)
+        link_arrs.append(arr)
+        dst_arrs.append((C.c_uint32 * max(1, len(dst)))(*dst))
+    PP = lambda T, xs: (C.POINTER(T) * nP)(*[C.cast(C.pointer(x) if not isinstance(x, C.Array) else x, C.POINTER(T)) for x in xs])
+    n = params[0].n_replicas
+    delivered, lost = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    L.hs_oracle_run_linked.restype = C.c_int
+    L.hs_oracle_run_linked.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_int64), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
+                                       C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    rc = L.hs_oracle_run_linked(nP, PP(A.ModelDesc, descs), PP(A.RunParams, params), PP(A.Outputs, [o for _, o in outs]),
+                                PP(A.LinkDesc, link_arrs), PP(C.c_uint32, dst_arrs),
+                                ends.ctypes.data_as(C.POINTER(C.c_int64)), len(ends), lm.n_streams,
+                                cseed, cseed_stride, nP if crid_base is None else crid_base,
+                                nP + 1 if crid_stride is None else crid_stride,
+                                delivered.ctypes.data_as(C.POINTER(C.c_uint64)), lost.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert rc == 0, rc
+    return [b for b, _ in outs], delivered, lost, ends
+
+
 def oracle_run_trace(model, p: A.RunParams, targets, service):
     """One replica fed with externally captured draws (the reference's stock RNG outputs)."""
     d = model.desc()

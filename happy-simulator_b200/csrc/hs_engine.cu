@@ -93,6 +93,10 @@ struct hs_engine {
     dev_buf d_conts, d_hist, d_cell_totals; bool hist_on = false;
     dev_buf d_trace_arr, d_trace_svc; uint64_t n_trace_arr = 0, n_trace_svc = 0; uint32_t trace_replicas = 0;
     dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals, d_srv_index, d_counter;
+    /* linked partitions */
+    uint32_t outbox_cap = 0, inbox_cap = 0;
+    dev_buf d_outbox, d_outbox_n, d_inbox, d_inbox_n;
+    uint32_t link_replicas = 0;                 /* replicas the outbox / inbox buffers are sized for */
 };
 
 /* ---- validation ----------------------------------------------------------- */
@@ -110,6 +114,7 @@ static int validate_model(const hs_model_desc *m)
         case HS_ENT_SOURCE:
             n_src++;
             if (e.target < 0 || (uint32_t)e.target >= n) return fail(HS_ERR_INVALID, "entity %u: source target %d out of range", i, e.target);
+            if (m->entities[e.target].kind == HS_ENT_REMOTE) return fail(HS_ERR_INVALID, "entity %u: a source's target must be in its own partition (parallel/validation.py:53-71)", i);
             if (m->entities[e.target].kind == HS_ENT_SOURCE) return fail(HS_ERR_INVALID, "entity %u: source targets a source", i);
             if (e.i3 < 0 || (uint32_t)e.i3 > m->n_profiles) return fail(HS_ERR_INVALID, "entity %u: profile index %d out of range", i, e.i3);
             if (e.i3 > 0 && !m->profiles) return fail(HS_ERR_INVALID, "profiles is NULL");
@@ -162,6 +167,10 @@ static int validate_model(const hs_model_desc *m)
             if (!(e.d0 > 0.0)) return fail(HS_ERR_INVALID, "entity %u: ttl must be > 0 (eviction_policies.py:174)", i);
             break;
         case HS_ENT_SINK: case HS_ENT_COUNTER: break;
+        case HS_ENT_REMOTE:
+            if (e.i0 < 0 || e.i0 >= 16 || e.i1 < 0) return fail(HS_ERR_INVALID, "entity %u: REMOTE row needs a link slot in 0..15 and a destination entity id", i);
+            if (m->outbox_cap == 0) return fail(HS_ERR_INVALID, "entity %u: a model with REMOTE rows needs outbox_cap > 0", i);
+            break;
         case HS_ENT_SKETCH: {
             if (e.i0 < HS_SK_HLL || e.i0 > HS_SK_RESERVOIR) return fail(HS_ERR_INVALID, "entity %u: unknown sketch algorithm %d", i, e.i0);
             if (e.l0 < 0 || e.l0 > INT32_MAX) return fail(HS_ERR_INVALID, "entity %u: sketch key population must be >= 0", i);
@@ -317,6 +326,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
             srv_index[i] = (int32_t)n_servers++;
         }
     }
+    live += E->inbox_cap;                            /* what a barrier can deliver is scheduled at once */
     const uint32_t S = (uint32_t)((live + 31) / 32) * 32;
     if (S > 65535) return fail(HS_ERR_INVALID, "model needs %u future-event slots (limit 65535)", S);
     /* thread engine: 4-ary key heap + payload slots instead of the warp engine's SoA slot table */
@@ -357,7 +367,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     M.key_cdf = (const double *)E->d_key_cdf.p;
     M.n_entities = ne; M.n_cells = E->n_cells; M.n_servers = n_servers; M.fel_slots = S; M.block_bytes = block_bytes;
     {
-        bool fixed = per_thread && ne <= S;
+        bool fixed = per_thread && ne <= S && E->inbox_cap == 0;      /* delivered events need slots of their own */
         for (uint32_t i = 0; i < ne && fixed; ++i) {
             const hs_entity_desc &e = E->ents[i];
             if (e.kind == HS_ENT_CACHE_SERVER) fixed = false;
@@ -368,6 +378,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
             }
         }
         M.fixed_slots = fixed ? 1u : 0u; M.pad_ = 0;
+        M.outbox_cap = E->outbox_cap; M.inbox_cap = E->inbox_cap;
     }
     M.n_backends = (uint32_t)E->backends.size(); M.model_bytes = model_bytes;
     hs_warp_run R;
@@ -376,6 +387,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     R.n_replicas = n; R.index_base = p->replica_index_base; R.replicas_per_cell = p->replicas_per_cell;
     R.record_cap = p->record_cap; R.sample_cap = p->sample_cap; R.service_cap = p->service_cap;
     R.ring = ring; R.resume = p->resume; R.lane_stride = 1; R.heap_top = 0;
+    R.linked = (p->flags & HS_RUN_LINKED) ? 1u : 0u;
     R.max_events = p->max_events > 0 ? p->max_events : INT64_MAX;
     R.trace_arr = E->n_trace_arr ? (const double *)E->d_trace_arr.p : nullptr; R.n_trace_arr = E->n_trace_arr;
     R.trace_svc = E->n_trace_svc ? (const double *)E->d_trace_svc.p : nullptr; R.n_trace_svc = E->n_trace_svc;
@@ -386,6 +398,10 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     O.service = p->service_cap ? (double *)E->d_svc.p : nullptr;
     O.hist = want_hist ? (uint32_t *)E->d_hist.p : nullptr;
     O.sketch = (uint8_t *)E->d_sketch.p;
+    O.outbox = (hs_xevent *)E->d_outbox.p; O.outbox_n = (uint32_t *)E->d_outbox_n.p;
+    O.inbox = (hs_xevent *)E->d_inbox.p; O.inbox_n = (uint32_t *)E->d_inbox_n.p;
+    if ((E->outbox_cap || E->inbox_cap || R.linked) && !per_thread)
+        return fail(HS_ERR_INVALID, "linked partitions run on the thread engine (engine 3)");
 
     auto launch = [&](auto kern) -> int {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -495,7 +511,8 @@ int hs_engine_destroy(hs_engine *E)
     dev_buf *bufs[] = {&E->d_ents, &E->d_backends, &E->d_key_table, &E->d_cell_d0, &E->d_cell_i0, &E->d_state,
                        &E->d_rings, &E->d_summ, &E->d_stats, &E->d_rec, &E->d_smp, &E->d_svc, &E->d_partials, &E->d_totals,
                        &E->d_srv_index, &E->d_counter, &E->d_trace_arr, &E->d_trace_svc, &E->d_profiles, &E->d_profile_table, &E->d_hist, &E->d_cell_totals, &E->d_conts,
-                       &E->d_sketch_tab, &E->d_sketch, &E->d_sketch_merged, &E->d_key_cdf};
+                       &E->d_sketch_tab, &E->d_sketch, &E->d_sketch_merged, &E->d_key_cdf,
+                       &E->d_outbox, &E->d_outbox_n, &E->d_inbox, &E->d_inbox_n};
     for (dev_buf *b : bufs) b->release();
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
@@ -528,7 +545,8 @@ int hs_model_upload(hs_engine *E, const hs_model_desc *m)
         same_bytes(E->profile_table.data(), E->profile_table.size() * 8, m->profile_table, (m->profile_table ? (size_t)m->n_profile_table : 0) * 8) &&
         same_bytes(E->sketch_tab.data(), E->sketch_tab.size() * 4, m->sketch_tables, (m->sketch_tables ? (size_t)m->n_sketch_table : 0) * 4) &&
         same_bytes(E->key_cdf.data(), E->key_cdf.size() * 8, m->key_cdf, (m->key_cdf ? (size_t)m->n_key_cdf : 0) * 8);
-    const bool keep_run = same_model && E->have_run;
+    const bool keep_run = same_model && E->have_run && E->outbox_cap == m->outbox_cap && E->inbox_cap == m->inbox_cap;
+    E->outbox_cap = m->outbox_cap; E->inbox_cap = m->inbox_cap;
     E->ents.assign(m->entities, m->entities + n);
     E->backends.assign(m->backends, m->backends + (m->backends ? m->n_backends : 0));
     E->key_table.assign(m->key_table, m->key_table + (m->key_table ? m->key_population : 0));
@@ -644,6 +662,17 @@ int hs_run(hs_engine *E, const hs_run_params *p)
         if (!p->resume) CUDA_TRY(cudaMemsetAsync(E->d_hist.p, 0, (size_t)n * HS_HISTOGRAM_BINS * sizeof(uint32_t), E->stream));
     }
     E->hist_on = want_hist;
+    if (E->outbox_cap || E->inbox_cap) {             /* linked partitions: per-replica outboxes / inboxes */
+        if ((rc = E->d_outbox.ensure((size_t)n * std::max(1u, E->outbox_cap) * sizeof(hs_xevent)))) return rc;
+        if ((rc = E->d_inbox.ensure((size_t)n * std::max(1u, E->inbox_cap) * sizeof(hs_xevent)))) return rc;
+        if ((rc = E->d_outbox_n.ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = E->d_inbox_n.ensure((size_t)n * 4 + 16))) return rc;
+        if (!p->resume) {
+            CUDA_TRY(cudaMemsetAsync(E->d_outbox_n.p, 0, (size_t)n * 4, E->stream));
+            CUDA_TRY(cudaMemsetAsync(E->d_inbox_n.p, 0, (size_t)n * 4, E->stream));
+        }
+        E->link_replicas = n;
+    }
     const bool want_hash = (p->flags & HS_RUN_ORDER_HASH) != 0;
     const bool want_rec = (p->record_cap | p->sample_cap | p->service_cap) != 0;
 
@@ -870,5 +899,149 @@ int hs_totals_device_ptr(hs_engine *E, void **ptr)
     *ptr = E->d_totals.p;
     return HS_OK;
 }
+
+/* ---- linked partitions: the window barrier (parallel/coordinator.py:182-227) ---------------------------- */
+#define HS_MAX_LINKS_ 16
+struct hs_link_dev { int32_t kind, stream; double mean_s, loss; hs_xevent *inbox; uint32_t *inbox_n; uint32_t inbox_cap, pad; };
+struct hs_links_dev { hs_link_dev l[HS_MAX_LINKS_]; };
+
+struct hs_coordinator {
+    int device = 0; cudaStream_t stream = nullptr;
+    uint32_t n = 0, n_streams = 1;
+    uint64_t seed = 0, seed_stride = 0; uint32_t rid_base = 0, rid_stride = 0, index_base = 0;
+    dev_buf d_loss_draws, d_lat_draws, d_counts;      /* uint64[n], uint64[n][n_streams], uint64[3][n] */
+};
+
+/* one thread per replica: its outbox in emission order -- one loss draw when the link loses packets, then
+ * event.time = send_time + latency.sample(), then Simulation.schedule(event) = a slot of the destination's inbox */
+__global__ void hs_exchange_kernel(const hs_xevent *__restrict__ outbox, uint32_t *__restrict__ outbox_n, uint32_t ocap,
+                                   const hs_entity_desc *__restrict__ src_ents, hs_links_dev LK, uint32_t n, uint32_t n_streams,
+                                   uint64_t seed0, uint64_t seed_stride, uint32_t rid_base, uint32_t rid_stride, uint32_t index_base,
+                                   uint64_t *__restrict__ loss_draws, uint64_t *__restrict__ lat_draws, uint64_t *__restrict__ counts)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t g = index_base + r;
+    const uint64_t seed = seed0 + (uint64_t)g * seed_stride;
+    const uint32_t rid = rid_base + g * rid_stride;
+    const uint32_t cnt = outbox_n[r];
+    uint64_t nl = loss_draws[r], delivered = 0, lost = 0, over = 0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const hs_xevent x = outbox[(size_t)r * ocap + k];
+        const hs_entity_desc row = src_ents[x.ent];
+        const hs_link_dev &L = LK.l[row.i0];
+        if (L.loss > 0.0 && hs_uniform(seed, rid, HS_STREAM_LINK_LOSS, nl++) < L.loss) { lost++; continue; }
+        int64_t lat;
+        if (L.kind == HS_SVC_EXPONENTIAL) {
+            const uint64_t d = lat_draws[(size_t)r * n_streams + L.stream]++;
+            lat = hs_exp_latency_ns(hs_uniform(seed, rid, HS_STREAM_LINK_LATENCY | ((uint32_t)L.stream << 8), d), HS_DIV(1.0, L.mean_s));
+        } else lat = hs_seconds_to_ns(L.mean_s);
+        const uint32_t m = L.inbox_n[r];
+        if (m >= L.inbox_cap) { over++; continue; }
+        hs_xevent y = x; y.time_ns = x.time_ns + lat; y.ent = row.i1;
+        L.inbox[(size_t)r * L.inbox_cap + m] = y;
+        L.inbox_n[r] = m + 1u;
+        delivered++;
+    }
+    outbox_n[r] = 0u;
+    loss_draws[r] = nl;
+    counts[r] += delivered; counts[(size_t)n + r] += lost; counts[2 * (size_t)n + r] += over;
+}
+
+int hs_coordinator_create(int device, void *cuda_stream, uint32_t n_replicas, uint32_t n_streams,
+                          uint64_t seed, uint64_t seed_stride, uint32_t rid_base, uint32_t rid_stride,
+                          uint32_t replica_index_base, hs_coordinator **out)
+{
+    if (!out || !n_replicas) return fail(HS_ERR_INVALID, "hs_coordinator_create: bad arguments");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(HS_ERR_NO_DEVICE, "no CUDA device available");
+    if (device < 0 || device >= count) return fail(HS_ERR_INVALID, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    hs_coordinator *c = new hs_coordinator();
+    c->device = device; c->stream = (cudaStream_t)cuda_stream; c->n = n_replicas; c->n_streams = n_streams ? n_streams : 1u;
+    c->seed = seed; c->seed_stride = seed_stride; c->rid_base = rid_base; c->rid_stride = rid_stride; c->index_base = replica_index_base;
+    int rc;
+    if ((rc = c->d_loss_draws.ensure((size_t)n_replicas * 8)) || (rc = c->d_lat_draws.ensure((size_t)n_replicas * c->n_streams * 8)) ||
+        (rc = c->d_counts.ensure((size_t)n_replicas * 24))) { delete c; return rc; }
+    CUDA_TRY(cudaMemsetAsync(c->d_loss_draws.p, 0, (size_t)n_replicas * 8, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_lat_draws.p, 0, (size_t)n_replicas * c->n_streams * 8, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_counts.p, 0, (size_t)n_replicas * 24, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return HS_OK;
+}
+
+void hs_coordinator_destroy(hs_coordinator *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->d_loss_draws.release(); c->d_lat_draws.release(); c->d_counts.release();
+    delete c;
+}
+
+int hs_coordinator_exchange(hs_coordinator *c, hs_engine *src, uint32_t n_links, const hs_link_desc *links, hs_engine *const *dsts)
+{
+    if (!c || !src) return fail(HS_ERR_INVALID, "hs_coordinator_exchange: NULL handle");
+    if (n_links > HS_MAX_LINKS_ || (n_links && (!links || !dsts))) return fail(HS_ERR_INVALID, "hs_coordinator_exchange: at most %d links", HS_MAX_LINKS_);
+    if (!src->have_run || !src->outbox_cap) return HS_OK;              /* nothing can have been sent */
+    if (src->link_replicas != c->n) return fail(HS_ERR_STATE, "the coordinator was created for %u replicas, the partition ran %u", c->n, src->link_replicas);
+    CUDA_TRY(cudaSetDevice(c->device));
+    hs_links_dev LK; memset(&LK, 0, sizeof LK);
+    for (const hs_entity_desc &e : src->ents)
+        if (e.kind == HS_ENT_REMOTE && (uint32_t)e.i0 >= n_links) return fail(HS_ERR_INVALID, "a REMOTE row uses link slot %d of %u", e.i0, n_links);
+    for (uint32_t k = 0; k < n_links; ++k) {
+        hs_engine *D = dsts[k];
+        if (!D || D == src) return fail(HS_ERR_INVALID, "link %u: bad destination engine", k);
+        if (D->device != src->device) return fail(HS_ERR_INVALID, "link %u: the partitions of one replica set live on one device", k);
+        if (!D->inbox_cap || !D->have_run || D->link_replicas != c->n) return fail(HS_ERR_STATE, "link %u: the destination has no inbox or has not run these replicas", k);
+        if (links[k].latency_kind != HS_SVC_CONSTANT && links[k].latency_kind != HS_SVC_EXPONENTIAL) return fail(HS_ERR_INVALID, "link %u: bad latency kind", k);
+        if (!(links[k].latency_mean_s >= 0.0) || !(links[k].packet_loss >= 0.0 && links[k].packet_loss < 1.0)) return fail(HS_ERR_INVALID, "link %u: latency must be >= 0 and packet_loss in [0, 1) (parallel/link.py:45-52)", k);
+        if (links[k].stream < 0 || (uint32_t)links[k].stream >= c->n_streams) return fail(HS_ERR_INVALID, "link %u: latency stream %d of %u", k, links[k].stream, c->n_streams);
+        for (const hs_entity_desc &e : src->ents)
+            if (e.kind == HS_ENT_REMOTE && (uint32_t)e.i0 == k) {
+                if ((size_t)e.i1 >= D->ents.size()) return fail(HS_ERR_INVALID, "link %u: destination entity %d out of range", k, e.i1);
+                const int dk = D->ents[e.i1].kind;
+                if (dk == HS_ENT_SOURCE || dk == HS_ENT_PROBE || dk == HS_ENT_REMOTE) return fail(HS_ERR_INVALID, "link %u: destination entity %d cannot receive requests", k, e.i1);
+            }
+        LK.l[k].kind = links[k].latency_kind; LK.l[k].stream = links[k].stream; LK.l[k].mean_s = links[k].latency_mean_s;
+        LK.l[k].loss = links[k].packet_loss; LK.l[k].inbox = (hs_xevent *)D->d_inbox.p; LK.l[k].inbox_n = (uint32_t *)D->d_inbox_n.p;
+        LK.l[k].inbox_cap = D->inbox_cap;
+        if (D->stream != c->stream) CUDA_TRY(cudaStreamSynchronize(D->stream));
+    }
+    if (src->stream != c->stream) CUDA_TRY(cudaStreamSynchronize(src->stream));
+    const uint32_t threads = 128, blocks = (c->n + threads - 1) / threads;
+    hs_exchange_kernel<<<blocks, threads, 0, c->stream>>>((const hs_xevent *)src->d_outbox.p, (uint32_t *)src->d_outbox_n.p, src->outbox_cap,
+        (const hs_entity_desc *)src->d_ents.p, LK, c->n, c->n_streams, c->seed, c->seed_stride, c->rid_base, c->rid_stride, c->index_base,
+        (uint64_t *)c->d_loss_draws.p, (uint64_t *)c->d_lat_draws.p, (uint64_t *)c->d_counts.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));      /* the partitions' streams may differ from the coordinator's */
+    src->launches += 1;
+    return HS_OK;
+}
+
+int hs_coordinator_read(hs_coordinator *c, uint64_t *delivered, uint64_t *lost, uint64_t *overflowed)
+{
+    if (!c) return fail(HS_ERR_INVALID, "hs_coordinator_read: NULL handle");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t nb = (size_t)c->n * 8;
+    if (delivered) CUDA_TRY(cudaMemcpyAsync(delivered, c->d_counts.p, nb, cudaMemcpyDeviceToHost, c->stream));
+    if (lost) CUDA_TRY(cudaMemcpyAsync(lost, (const uint8_t *)c->d_counts.p + nb, nb, cudaMemcpyDeviceToHost, c->stream));
+    if (overflowed) CUDA_TRY(cudaMemcpyAsync(overflowed, (const uint8_t *)c->d_counts.p + 2 * nb, nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HS_OK;
+}
+
+static int read_box(hs_engine *E, const dev_buf &box, const dev_buf &cnt, uint32_t cap, hs_xevent *buf, uint32_t *counts)
+{
+    if (!E || !E->have_run) return fail(HS_ERR_STATE, "no run to read");
+    CUDA_TRY(cudaSetDevice(E->device));
+    if (!cap) return HS_OK;
+    if (buf) CUDA_TRY(cudaMemcpyAsync(buf, box.p, (size_t)E->link_replicas * cap * sizeof(hs_xevent), cudaMemcpyDeviceToHost, E->stream));
+    if (counts) CUDA_TRY(cudaMemcpyAsync(counts, cnt.p, (size_t)E->link_replicas * 4, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    return HS_OK;
+}
+int hs_read_outbox(hs_engine *E, hs_xevent *buf, uint32_t *counts) { return read_box(E, E->d_outbox, E->d_outbox_n, E ? E->outbox_cap : 0, buf, counts); }
+int hs_read_inbox(hs_engine *E, hs_xevent *buf, uint32_t *counts) { return read_box(E, E->d_inbox, E->d_inbox_n, E ? E->inbox_cap : 0, buf, counts); }
 
 } /* extern "C" */

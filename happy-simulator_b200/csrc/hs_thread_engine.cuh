@@ -151,7 +151,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     int64_t h_now = 0, h_processed = 0; uint64_t h_hash = 0; int32_t h_fel = 0;   /* its hot fields, in registers (see below) */
     if (P.resume) {
         hdr = *Hg;
-        if (hdr.done) return;
+        if (hdr.done && !P.linked) return;       /* a linked partition's next window: the end time has moved on, events may have arrived */
         h_now = H->now; h_processed = H->processed; h_hash = H->hash; h_fel = H->fel_n;
         for (uint32_t i = 0; i < TOP && i < hdr.free_top + HS_T_ARITY; ++i) {      /* the heap's top levels (free_top = heap size) */
             const hs_tkey k = K[i];
@@ -523,6 +523,18 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         return false;
     };
 
+    /* linked partitions: the partition's event router (parallel/routing.py:40-61) -- an event whose target lives in
+     * another partition is constructed (its sort index is spent) but never scheduled here: it goes, with the current
+     * time, to this replica's outbox, which hs_coordinator_exchange drains at the window barrier */
+    auto outbox_send = [&](const uint64_t idx, const int64_t created, const int32_t key, const uint32_t rem, const int64_t now) {
+        E[rem].u.snk.received++;
+        const uint32_t n = O.outbox_n[r];
+        if (n >= M.outbox_cap) { hdr.status |= HS_ST_LINK_OVERFLOW; return; }
+        hs_xevent x; x.time_ns = now; x.sort_index = idx; x.created_ns = created; x.aux = 0ull; x.key = key; x.ent = (int32_t)rem;
+        O.outbox[(size_t)r * M.outbox_cap + n] = x;
+        O.outbox_n[r] = n + 1u;
+    };
+
     /* one event: the handler of hs_handlers.inc (kind is warp-uniform at every call site), then the insertion of the
      * (at most one) future event it created */
     auto process = [&](const int kind) {
@@ -557,7 +569,9 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
 #define HS_W_PUSH(TIME, IDX, KIND, ENT, CREATED, AUX, KEY, HOOK)                                         \
     do {                                                                                                 \
         const int64_t t_ = (TIME);                                                                       \
-        if (t_ <= now) {                                                                                 \
+        if ((KIND) == HS_EV_REQ_ANY && M.outbox_cap && ENTS[(ENT)].kind == HS_ENT_REMOTE)                \
+            outbox_send((IDX), (CREATED), (KEY), (uint32_t)(ENT), now);                                  \
+        else if (t_ <= now) {                                                                                 \
             if (now_n >= HS_W_NCAP) hdr.status |= HS_ST_FEL_OVERFLOW;                                    \
             else { hs_wnow n_; n_.time = t_; n_.idx = (IDX); n_.created = (CREATED); n_.aux = (AUX);     \
                    n_.m0 = (uint32_t)(KIND) | ((uint32_t)(ENT) << 8); n_.key = (KEY); n_.hook = (HOOK); n_.pad = 0u; \
@@ -583,6 +597,20 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
           for (int i = 2; i < 6; ++i) g[i] = xu.q[i]; }
         if (have_fut) heap_insert(fkey, fpay);
     };
+    /* linked partitions: what the coordinator delivered at the last barrier is scheduled before the first pop
+     * (WindowedCoordinator._exchange_events -> Simulation.schedule = heap push, core/simulation.py:195-206); an event
+     * that lies behind this replica's clock is dropped by the time-travel test when it is popped */
+    if (M.inbox_cap && O.inbox_n) {
+        const uint32_t n_in = O.inbox_n[r];
+        for (uint32_t k = 0; k < n_in; ++k) {
+            const hs_xevent x = O.inbox[(size_t)r * M.inbox_cap + k];
+            hs_tkey fk; fk.time = x.time_ns; fk.k2 = x.sort_index << 16;
+            hs_tpay fp; fp.created = x.created_ns; fp.aux = 0ull; fp.m0 = (uint32_t)HS_EV_REQ_ANY | ((uint32_t)x.ent << 8);
+            fp.key = x.key; fp.hook = 0u; fp.pad = 0u;
+            heap_insert(fk, fp);
+        }
+        O.inbox_n[r] = 0u;
+    }
     const bool single = (P.lane_stride == 32);          /* one replica per warp: nothing to align, every pass runs the next event */
     next_event();
     while (alive) {
@@ -681,7 +709,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 a.c3 = e->u.srv.rejected; a.f0 = (double)e->u.srv.svc_draws; a.f1 = (double)e->u.srv.pad; break;   /* misses, hits, size */
             case HS_ENT_SINK: a.c0 = e->u.snk.received; a.f0 = hs_neumaier_result(e->u.snk.sum, e->u.snk.comp);
                 a.f1 = e->u.snk.sumsq; a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
-            case HS_ENT_COUNTER: a.c0 = e->u.snk.received; break;
+            case HS_ENT_COUNTER: case HS_ENT_REMOTE: a.c0 = e->u.snk.received; break;
             case HS_ENT_PROBE: a.c0 = e->u.snk.received; a.f0 = hs_neumaier_result(e->u.snk.sum, e->u.snk.comp);
                 a.f2 = e->u.snk.mn; a.f3 = e->u.snk.mx; break;
             case HS_ENT_LB: a.c0 = e->u.lb.received; a.c1 = e->u.lb.forwarded; a.c2 = e->u.lb.in_flight;

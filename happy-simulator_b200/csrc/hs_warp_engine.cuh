@@ -82,6 +82,7 @@ struct hs_warp_model {
     uint32_t n_entities, n_cells, n_servers, fel_slots;   /* fel_slots = S, multiple of 32 */
     uint32_t block_bytes;           /* bytes of one replica block (multiple of 16)          */
     uint32_t n_backends, model_bytes; /* shared-memory copy of the model tables (per CTA)     */
+    uint32_t outbox_cap, inbox_cap;   /* linked partitions (HS_ENT_REMOTE rows / link destination), else 0 */
     uint32_t fixed_slots, pad_;       /* thread engine: every entity has at most ONE pending future event (sources: the next
                                          tick; servers with concurrency 1: the continuation), so its payload slot is its
                                          entity id -- no free-slot stack traffic on the heap's push / pop path */
@@ -93,6 +94,7 @@ struct hs_warp_run {
     int64_t end_ns, window_end_ns;
     uint32_t n_replicas, index_base, replicas_per_cell;
     uint32_t record_cap, sample_cap, service_cap, ring, resume;
+    uint32_t linked;                /* HS_RUN_LINKED: a window of a linked partition -- finished replicas continue */
     uint32_t lane_stride;           /* thread engine: lanes per replica (1, 2, 4 ... 32) */
     uint32_t heap_top;              /* thread engine: number of heap keys (whole top levels: 0, 5, 21, 85 or 341 for
                                        arity 4) kept in shared memory during a launch, [key][replica column] */
@@ -109,6 +111,8 @@ struct hs_warp_out {
     double *service;
     uint32_t *hist;
     uint8_t *sketch;                /* [replica][sk_total] */
+    hs_xevent *outbox; uint32_t *outbox_n;   /* [replica][outbox_cap], entries used (linked partitions) */
+    hs_xevent *inbox; uint32_t *inbox_n;     /* [replica][inbox_cap], entries waiting to be scheduled   */
 };
 
 /* ---- PTX helpers: mbarrier + TMA 1-D bulk copies ------------------------- */

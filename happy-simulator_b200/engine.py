@@ -28,7 +28,8 @@ _lib = None
 EXPORTED_SYMBOLS = ["hs_version", "hs_last_error", "hs_engine_create", "hs_engine_destroy", "hs_model_upload",
                     "hs_model_validate", "hs_run", "hs_set_trace", "hs_sync", "hs_last_run_ms", "hs_launch_count",
                     "hs_read_outputs", "hs_read_totals", "hs_read_cell_totals", "hs_totals_device_ptr",
-                    "hs_sketch_layout", "hs_read_sketches"]
+                    "hs_sketch_layout", "hs_read_sketches", "hs_coordinator_create", "hs_coordinator_destroy",
+                    "hs_coordinator_exchange", "hs_coordinator_read", "hs_read_outbox", "hs_read_inbox"]
 
 
 def load_library(path: str | None = None):
@@ -60,6 +61,13 @@ def load_library(path: str | None = None):
         "hs_sketch_layout": ([C.POINTER(A.ModelDesc), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
         "hs_read_sketches": ([H, C.c_void_p, C.c_uint64], C.c_int),
+        "hs_coordinator_create": ([C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                   C.c_uint32, C.POINTER(H)], C.c_int),
+        "hs_coordinator_destroy": ([H], None),
+        "hs_coordinator_exchange": ([H, H, C.c_uint32, C.POINTER(A.LinkDesc), C.POINTER(H)], C.c_int),
+        "hs_coordinator_read": ([H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
+        "hs_read_outbox": ([H, C.c_void_p, C.POINTER(C.c_uint32)], C.c_int),
+        "hs_read_inbox": ([H, C.c_void_p, C.POINTER(C.c_uint32)], C.c_int),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)
@@ -96,6 +104,42 @@ def make_params(*, seed=1234, end_ns, n_replicas=1, seed_stride=0, rid_base=0, r
     p.window_end_ns, p.resume, p.flags = int(window_end_ns), resume, flags
     p.max_events = int(max_events)
     return p
+
+
+class Coordinator:
+    """The window barrier of a linked run (hs_coordinator_*, parallel/coordinator.py:182-227): per-replica draw
+    counters of the loss stream and the links' latency streams, delivery totals."""
+
+    def __init__(self, device: int, n_replicas: int, n_streams: int, *, seed, seed_stride=0, rid_base, rid_stride,
+                 replica_index_base=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        self.n_replicas = int(n_replicas)
+        _check(self._L, self._L.hs_coordinator_create(device, None, n_replicas, n_streams, seed, seed_stride, rid_base,
+                                                      rid_stride, replica_index_base, C.byref(self._h)))
+
+    def exchange(self, src: "Engine", links, dsts) -> None:
+        """Drain ``src``'s outboxes through its outgoing ``links`` (ctypes hs_link_desc array) into the inboxes of the
+        engines ``dsts`` (one per link slot)."""
+        arr = (C.c_void_p * max(1, len(dsts)))(*[d._h for d in dsts])
+        _check(self._L, self._L.hs_coordinator_exchange(self._h, src._h, len(dsts), links, arr))
+
+    def read(self):
+        """(delivered, lost, overflowed) uint64[n_replicas] since creation."""
+        out = [np.zeros(self.n_replicas, np.uint64) for _ in range(3)]
+        _check(self._L, self._L.hs_coordinator_read(self._h, *[o.ctypes.data_as(C.POINTER(C.c_uint64)) for o in out]))
+        return tuple(out)
+
+    def close(self):
+        if self._h:
+            self._L.hs_coordinator_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:
@@ -135,6 +179,15 @@ class Engine:
         assert a.ndim == 2 and s.ndim == 2 and a.shape[0] == s.shape[0]
         _check(self._L, self._L.hs_set_trace(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[1],
                                              s.ctypes.data_as(C.POINTER(C.c_double)), s.shape[1], a.shape[0]))
+
+    def read_box(self, which: str = "outbox"):
+        """(entries XEVENT_DTYPE[n_replicas, cap], counts uint32[n_replicas]) of the partition's outbox / inbox."""
+        cap = int(self._model.outbox_cap if which == "outbox" else self._model.inbox_cap)
+        n = int(self._params.n_replicas)
+        buf, cnt = np.zeros((n, max(1, cap)), A.XEVENT_DTYPE), np.zeros(n, np.uint32)
+        fn = self._L.hs_read_outbox if which == "outbox" else self._L.hs_read_inbox
+        _check(self._L, fn(self._h, buf.ctypes.data, cnt.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return buf, cnt
 
     def run(self, params: A.RunParams) -> None:
         _check(self._L, self._L.hs_run(self._h, C.byref(params)))

@@ -83,3 +83,54 @@ class LinkedModel:
                                      f"{self.names[self.links[p][slot].dest]!r}, which cannot receive requests")
             if m.ids_of(A.HS_ENT_REMOTE) and m.outbox_cap <= 0:
                 raise ValueError(f"partition {self.names[p]!r} has REMOTE rows but no outbox")
+
+
+class LinkedRun:
+    """A LinkedModel on one GPU: one engine per partition (the same replicas in each), one coordinator.
+
+    ``run()`` is WindowedCoordinator.run (coordinator.py:75-172): for every window, every partition runs
+    ``hs_run(end_ns=window end, resume=window > 0, HS_RUN_LINKED)``, then ``hs_coordinator_exchange`` drains the
+    partitions' outboxes in partition order.  Replica r of partition q draws from the Philox replica word
+    ``q + g * (P + 1)`` (g = global replica index), the coordinator from ``P + g * (P + 1)``."""
+
+    def __init__(self, lm: LinkedModel, *, device: int = 0):
+        from . import engine as _engine
+        lm.validate()
+        self.lm, self.device = lm, device
+        self.engines = [_engine.Engine(device) for _ in lm.models]
+        for e, m in zip(self.engines, lm.models):
+            e.upload(m)
+        self.coordinator = None
+        self.windows = 0
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        if self.coordinator is not None:
+            self.coordinator.close()
+
+    def run(self, *, seed, end_ns, n_replicas=1, replica_index_base=0, caps=None, flags=A.HS_RUN_ORDER_HASH, queue_ring=0):
+        """caps: per-partition dicts of record_cap / sample_cap / service_cap (or one dict for all).  Returns the
+        per-partition outputs (Engine.read_outputs) and (delivered, lost, overflowed) per replica."""
+        from . import engine as _engine
+        lm, nP = self.lm, self.lm.n_partitions
+        if self.coordinator is not None:
+            self.coordinator.close()
+        self.coordinator = _engine.Coordinator(self.device, n_replicas, lm.n_streams, seed=seed, rid_base=nP,
+                                               rid_stride=nP + 1, replica_index_base=replica_index_base)
+        caps = caps or {}
+        link_args = [lm.link_descs(q) for q in range(nP)]
+        ends = lm.window_ends(end_ns)
+        for w, wend in enumerate(ends):
+            for q, e in enumerate(self.engines):
+                c = caps[q] if isinstance(caps, (list, tuple)) else caps
+                e.run(_engine.make_params(seed=seed, end_ns=wend, n_replicas=n_replicas, rid_base=q, rid_stride=nP + 1,
+                                          replica_index_base=replica_index_base, engine=3, resume=1 if w else 0,
+                                          flags=flags | A.HS_RUN_LINKED, queue_ring=queue_ring, **c))
+            for q, e in enumerate(self.engines):
+                arr, dst = link_args[q]
+                if dst:
+                    self.coordinator.exchange(e, arr, [self.engines[d] for d in dst])
+        self.windows = len(ends)
+        outs = [e.read_outputs() for e in self.engines]
+        return outs, self.coordinator.read()

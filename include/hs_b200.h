@@ -70,7 +70,7 @@ enum {
                             (parallel/simulation.py:31, parallel/routing.py:17-63): an event whose target is this row
                             is never scheduled here -- the partition's router puts it, with its send time, into the
                             partition's outbox, and the coordinator delivers it at the next window barrier
-                            (parallel/coordinator.py:182-227).  i0 = slot of the outgoing link in the hs_link_desc
+                            (parallel/coordinator.py:182-227).  i0 = slot (0..15) of the outgoing link in the hs_link_desc
                             array handed to hs_coordinator_exchange, i1 = the entity's id in the destination
                             partition's model.  hs_entity_stats: c0 = events sent through it                 */
 };
@@ -225,6 +225,9 @@ typedef struct hs_run_params {
 
 #define HS_RUN_ORDER_HASH 1u   /* maintain hs_replica_summary.order_hash (off: hash = 0)  */
 #define HS_RUN_HISTOGRAM 2u    /* per-replica 64-bin latency histogram of all Sink events  */
+#define HS_RUN_LINKED 4u       /* a window of a linked partition (hs_coordinator_*): with resume = 1, replicas that
+                                  had finished (clock past the previous end_ns, or nothing pending) run on -- end_ns
+                                  is the new window end and the barrier may have delivered events               */
 #define HS_HISTOGRAM_BINS 64   /* log-spaced over integer ns, see hs_latency_bin()         */
 
 /* Replica status bits. */
@@ -428,8 +431,9 @@ void hs_coordinator_destroy(hs_coordinator *c);
  * engine pushes its inbox into the replicas' heaps before the first pop (Simulation.schedule, :195-206). */
 int hs_coordinator_exchange(hs_coordinator *c, hs_engine *src, uint32_t n_links, const hs_link_desc *links,
                             hs_engine *const *dsts);
-/* totals over all replicas since create: events delivered into inboxes, events lost */
-int hs_coordinator_read(hs_coordinator *c, uint64_t *delivered, uint64_t *lost);
+/* per-replica totals since create ([n_replicas] each, any pointer may be NULL): events delivered into inboxes,
+ * events lost on lossy links, events that found the destination's inbox full (a sizing error: raise inbox_cap) */
+int hs_coordinator_read(hs_coordinator *c, uint64_t *delivered, uint64_t *lost, uint64_t *overflowed);
 /* Copy the current outboxes / inboxes to the host: buf[n_replicas][cap], counts[n_replicas] (tests, debugging). */
 int hs_read_outbox(hs_engine *e, hs_xevent *buf, uint32_t *counts);
 int hs_read_inbox(hs_engine *e, hs_xevent *buf, uint32_t *counts);

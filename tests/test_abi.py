@@ -21,7 +21,7 @@ def lib():
 def declared_functions():
     src = open(os.path.join(ROOT, "include", "hs_b200.h")).read()
     body = src[src.index("/* ---- entry points"):]
-    return sorted(set(re.findall(r"^(?:int|uint32_t)\s+(hs_\w+)\s*\(", body, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|uint32_t|void)\s+(hs_\w+)\s*\(", body, flags=re.M)))
 
 
 def test_every_declared_entry_point_is_exported(lib):
@@ -38,6 +38,7 @@ def test_version_and_struct_layouts(lib):
     assert "hs_entity_desc;      /* 48 bytes */" in src and C.sizeof(A.EntityDesc) == 48
     assert C.sizeof(A.ReplicaSummary) == 56 and C.sizeof(A.EntityStats) == 64
     assert C.sizeof(A.EventRecord) == 16 and C.sizeof(A.SinkSample) == 16
+    assert C.sizeof(A.LinkDesc) == 24 and A.XEVENT_DTYPE.itemsize == 40          # hs_link_desc, hs_xevent
     assert C.sizeof(A.Totals) == 8 * (A.HS_TOTALS_I64 + A.HS_TOTALS_F64_SUM + 2)
 
 

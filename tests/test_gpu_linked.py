@@ -1,0 +1,95 @@
+"""SURVEY 8(f) row 4, first half on the device: partitions joined by PartitionLinks -- one engine per partition,
+hs_run per window (HS_RUN_LINKED), hs_coordinator_exchange at every barrier -- against the fixtures produced by the
+unmodified reference's ParallelSimulation / WindowedCoordinator and, for ensembles, against the oracle."""
+import numpy as np
+import pytest
+
+import golden_lib as G
+import oracle_lib as O
+from happysim_b200 import _abi as A, engine
+from happysim_b200.linked import LinkedRun
+from test_gpu_lane_parity import assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", G.case_names("linked_"))
+def test_linked_fixture_on_the_device(name):
+    lm, kw, z = G.load_linked(name)
+    run = LinkedRun(lm)
+    try:
+        outs, (delivered, lost, over) = run.run(seed=kw["seed"], end_ns=kw["end_ns"],
+                                                caps=[G.linked_caps(z, q) for q in range(lm.n_partitions)])
+    finally:
+        run.close()
+    assert run.windows == int(z["total_windows"]) and int(delivered[0]) == int(z["cross_events"]) and int(over[0]) == 0
+    for q in range(lm.n_partitions):
+        G.check_linked_partition(z, q, outs[q])
+
+
+@pytest.mark.parametrize("name", ["linked_lossy_fanout", "linked_aligned_ring"])
+def test_linked_ensemble_matches_the_oracle(name):
+    lm, kw, z = G.load_linked(name)
+    nP, n = lm.n_partitions, 41
+    caps = [dict(record_cap=6000, sample_cap=600, service_cap=1200) for _ in range(nP)]
+    run = LinkedRun(lm)
+    try:
+        outs, (delivered, lost, over) = run.run(seed=kw["seed"], end_ns=kw["end_ns"], n_replicas=n, replica_index_base=3, caps=caps)
+    finally:
+        run.close()
+    ps = [O.make_params(seed=kw["seed"], end_ns=kw["end_ns"], n_replicas=n, rid_base=q, rid_stride=nP + 1,
+                        replica_index_base=3, **caps[q]) for q in range(nP)]
+    want, wd, wl, _ = O.oracle_run_linked(lm, ps, end_ns=kw["end_ns"], cseed=kw["seed"])
+    assert np.array_equal(delivered, wd) and np.array_equal(lost, wl) and not over.any()
+    for q in range(nP):
+        assert_same(outs[q], want[q])
+        if want[q].get("sketches") is not None:
+            assert outs[q]["sketches"].tobytes() == want[q]["sketches"].tobytes()
+    assert len({int(x) for x in outs[0]["summaries"]["order_hash"]}) == (1 if name == "linked_aligned_ring" else n)
+
+
+def test_outbox_and_inbox_between_windows():
+    """After the first window and before its barrier the sender's outbox holds what its servers forwarded; the
+    barrier moves it, delayed by the link latency, into the receiver's inbox; the next window schedules it."""
+    lm, kw, z = G.load_linked("linked_tandem_const")
+    run = LinkedRun(lm)
+    try:
+        a, b = run.engines
+        ends = lm.window_ends(kw["end_ns"])
+        mk = lambda q, w: engine.make_params(seed=kw["seed"], end_ns=ends[w], rid_base=q, rid_stride=3, engine=3,
+                                             resume=1 if w else 0, flags=A.HS_RUN_ORDER_HASH | A.HS_RUN_LINKED)
+        coord = engine.Coordinator(0, 1, 1, seed=kw["seed"], rid_base=2, rid_stride=3)
+        sent_total = 0
+        for w in range(6):
+            a.run(mk(0, w)); b.run(mk(1, w))
+            box, cnt = a.read_box("outbox")
+            inbox_before = int(b.read_box("inbox")[1][0])
+            assert inbox_before == 0                                   # drained by the run that just ended
+            arr, dst = lm.link_descs(0)
+            coord.exchange(a, arr, [b])
+            ib, icnt = b.read_box("inbox")
+            assert int(a.read_box("outbox")[1][0]) == 0 and int(icnt[0]) == int(cnt[0])
+            k = int(cnt[0])
+            assert np.array_equal(ib[0][:k]["time_ns"], box[0][:k]["time_ns"] + 50_000_000)
+            assert np.array_equal(ib[0][:k]["sort_index"], box[0][:k]["sort_index"]) and (ib[0][:k]["ent"] == 0).all()
+            assert (box[0][:k]["ent"] == 2).all() and (np.diff(box[0][:k]["time_ns"]) >= 0).all()
+            sent_total += k
+        assert sent_total > 5 and int(coord.read()[0][0]) == sent_total
+        coord.close()
+    finally:
+        run.close()
+
+
+def test_linked_models_need_the_thread_engine_and_an_outbox():
+    lm, kw, z = G.load_linked("linked_tandem_const")
+    e = engine.Engine(0)
+    try:
+        e.upload(lm.models[0])
+        with pytest.raises(engine.EngineError, match="thread engine"):
+            e.run(engine.make_params(seed=1, end_ns=10**8, engine=1))
+        m = lm.models[0]
+        m.outbox_cap = 0
+        with pytest.raises(engine.EngineError, match="outbox_cap"):
+            e.upload(m)
+    finally:
+        e.close()

@@ -30,6 +30,7 @@ HS_ST_QUEUE_OVERFLOW, HS_ST_FEL_OVERFLOW, HS_ST_REJECT_PATH, HS_ST_TRACE_EXHAUST
 HS_ST_SKETCH_OVERFLOW = 32
 HS_RUN_LINKED = 4
 HS_ST_LINK_OVERFLOW = 64
+HS_ST_LINK_TIE = 128
 
 HS_STREAM_ARRIVAL, HS_STREAM_SERVICE, HS_STREAM_ROUTING, HS_STREAM_LINK_LOSS, HS_STREAM_LINK_LATENCY = 0, 1, 2, 3, 4
 

@@ -240,6 +240,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
      * A lane whose next event is a kind whose phase has passed simply waits for the next cycle. */
     hs_wnow ev; ev.time = 0; ev.idx = 0; ev.created = 0; ev.aux = 0; ev.m0 = 0; ev.key = -1; ev.hook = 0; ev.pad = 0;
     int ev_kind = -1;                                    /* kind of the event held in `ev`, -1: none */
+    int64_t prev_t = -1; uint64_t prev_i = ~0ull; uint32_t prev_x = 0u;   /* the previous pop (linked partitions: tie detection) */
     bool alive = true, need_heap = false;
 
     /* choose the next event: the now tier's minimum unless the heap's root sorts first (then the heap phase pops it) */
@@ -262,6 +263,10 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (nb < 0) { alive = false; return; }           /* heap exhausted */
             if (windowed && nt > P.window_end_ns) { paused = true; alive = false; return; }
             ev = now_load(nb);
+            if (M.inbox_cap) {
+                if (ev.time == prev_t && ev.idx == prev_i && prev_x) hdr.status |= HS_ST_LINK_TIE;
+                prev_t = ev.time; prev_i = ev.idx; prev_x = 0u;
+            }
             now_n--;
             if (nb != now_n) now_store(nb, now_load(now_n));
             h_fel--;
@@ -606,7 +611,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             const hs_xevent x = O.inbox[(size_t)r * M.inbox_cap + k];
             hs_tkey fk; fk.time = x.time_ns; fk.k2 = x.sort_index << 16;
             hs_tpay fp; fp.created = x.created_ns; fp.aux = 0ull; fp.m0 = (uint32_t)HS_EV_REQ_ANY | ((uint32_t)x.ent << 8);
-            fp.key = x.key; fp.hook = 0u; fp.pad = 0u;
+            fp.key = x.key; fp.hook = 0u; fp.pad = 1u;               /* pad = 1: came over a link (tie detection) */
             heap_insert(fk, fp);
         }
         O.inbox_n[r] = 0u;
@@ -620,7 +625,11 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             const uint32_t slot = (uint32_t)(top_k & 0xffffu);
             const hs_tpay pp = PAY[slot];
             ev.time = top_t; ev.idx = top_k >> 16; ev.created = pp.created; ev.aux = pp.aux;
-            ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = 0u;
+            ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = pp.pad;
+            if (M.inbox_cap) {                           /* a delivered event that ties on (time, sort index): see HS_ST_LINK_TIE */
+                if (ev.time == prev_t && ev.idx == prev_i && (ev.pad | prev_x)) hdr.status |= HS_ST_LINK_TIE;
+                prev_t = ev.time; prev_i = ev.idx; prev_x = ev.pad;
+            }
             heap_n--;
             if (!M.fixed_slots) FREE[S - heap_n - 1] = (uint16_t)slot;
             if (heap_n > 0) {                            /* sift-down of the last key from the root */

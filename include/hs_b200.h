@@ -238,6 +238,10 @@ typedef struct hs_run_params {
 #define HS_ST_EVENT_LIMIT 16u     /* hs_run_params.max_events reached        */
 #define HS_ST_SKETCH_OVERFLOW 32u /* a TDigest outgrew its centroid capacity */
 #define HS_ST_LINK_OVERFLOW 64u   /* a partition's outbox or inbox filled up */
+#define HS_ST_LINK_TIE 128u       /* linked partitions: an event delivered over a link tied with another event on BOTH time
+                                     and sort index (the indices come from different partitions' counters).  The reference
+                                     orders such a pair by the accident of heapq's array layout; the engines order it by
+                                     their own heap's, so this replica's event order may differ from the reference's      */
 
 typedef struct hs_replica_summary {
     int64_t events_processed;  /* SimulationSummary.total_events_processed (simulation.py:553) */

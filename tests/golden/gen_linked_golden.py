@@ -39,11 +39,14 @@ def tandem_over_a_link(loss=0.0, kind=CONST, latency=0.05):
     return LinkedModel([ma, mb], ["A", "B"], [[LinkSpec(1, kind, latency, loss, 0)], []], window_s=0.05)
 
 
-def aligned_ring():
+def aligned_ring(pumps=False):
     """Three partitions in a ring, everything on a 5 ms grid (constant sources, constant service times, constant link
     latencies): cross-partition requests and local ones land on the same nanosecond all the time and are ordered by
     sort indices that come from DIFFERENT partitions' counters (event_heap.py:46-48).
-    A: Source(100/s) -> S_A -> B.S_B;  B: Source(50/s) -> S_B -> C.S_C;  C: S_C -> A.counter;  A also counts."""
+    A: Source(100/s) -> S_A -> B.S_B;  B: Source(50/s) -> S_B -> C.S_C;  C: S_C -> A.counter;  A also counts.
+    Without ``pumps`` the three counters grow at about the same pace and a few delivered events tie with a local one
+    on time AND index -- the reference then orders the pair by the accident of heapq's array layout.  With ``pumps``
+    (a fast local Source -> Counter in B and in C) the counters spread apart: same-nanosecond ties only."""
     a = hs.ModelBuilder()
     sa_src = a.source("A.src", rate=100.0, poisson=False)
     s_a = a.server("A.server", concurrency=2, mean_service_s=0.01, exponential=False)
@@ -56,11 +59,15 @@ def aligned_ring():
     s_b = b.server("B.server", concurrency=4, mean_service_s=0.01, exponential=False)
     to_c = b.remote("C.server@B", link=0, dest_entity=0)
     b.set_target(sb_src, s_b); b.set_target(s_b, to_c)
+    if pumps:
+        b.set_target(b.source("B.pump", rate=400.0, poisson=False), b.counter("B.pumped"))
     mb = b.build(); mb.outbox_cap, mb.inbox_cap = 64, 64
     c = hs.ModelBuilder()
     s_c = c.server("C.server", concurrency=1, mean_service_s=0.005, exponential=False, capacity=3)
     to_a = c.remote("A.counter@C", link=0, dest_entity=2)
     c.set_target(s_c, to_a)
+    if pumps:
+        c.set_target(c.source("C.pump", rate=3000.0, poisson=False), c.counter("C.pumped"))
     mc = c.build(); mc.outbox_cap, mc.inbox_cap = 64, 64
     links = [[LinkSpec(1, CONST, 0.02, 0.0, 0)], [LinkSpec(2, CONST, 0.03, 0.0, 1)], [LinkSpec(0, CONST, 0.02, 0.0, 0)]]
     return LinkedModel([ma, mb, mc], ["A", "B", "C"], links, window_s=0.02, n_streams=2)
@@ -97,6 +104,7 @@ def cases():
         "tandem_const": (tandem_over_a_link(), dict(seed=5, end_s=4.0)),
         "tandem_lossy_exp": (tandem_over_a_link(loss=0.2, kind=EXPO), dict(seed=7, end_s=4.0)),
         "aligned_ring": (aligned_ring(), dict(seed=1, end_s=1.5)),
+        "aligned_ring_spread": (aligned_ring(pumps=True), dict(seed=1, end_s=1.5)),
         "lossy_fanout": (lossy_fanout(), dict(seed=11, end_s=3.0)),
     }
 

@@ -22,12 +22,19 @@ def test_linked_fixture_on_the_device(name):
                                                 caps=[G.linked_caps(z, q) for q in range(lm.n_partitions)])
     finally:
         run.close()
-    assert run.windows == int(z["total_windows"]) and int(delivered[0]) == int(z["cross_events"]) and int(over[0]) == 0
+    assert run.windows == int(z["total_windows"]) and int(over[0]) == 0
+    if name == "linked_aligned_ring":
+        # a few delivered events tie with a local one on time AND sort index (indices of two partitions' counters): the
+        # reference orders such a pair by the accident of heapq's array layout; the device says so instead of guessing
+        st = [int(o["summaries"]["status"][0]) for o in outs]
+        assert any(x & A.HS_ST_LINK_TIE for x in st) and not any(x & ~A.HS_ST_LINK_TIE for x in st)
+        return
+    assert int(delivered[0]) == int(z["cross_events"])
     for q in range(lm.n_partitions):
         G.check_linked_partition(z, q, outs[q])
 
 
-@pytest.mark.parametrize("name", ["linked_lossy_fanout", "linked_aligned_ring"])
+@pytest.mark.parametrize("name", ["linked_lossy_fanout", "linked_aligned_ring_spread"])
 def test_linked_ensemble_matches_the_oracle(name):
     lm, kw, z = G.load_linked(name)
     nP, n = lm.n_partitions, 41
@@ -45,7 +52,7 @@ def test_linked_ensemble_matches_the_oracle(name):
         assert_same(outs[q], want[q])
         if want[q].get("sketches") is not None:
             assert outs[q]["sketches"].tobytes() == want[q]["sketches"].tobytes()
-    assert len({int(x) for x in outs[0]["summaries"]["order_hash"]}) == (1 if name == "linked_aligned_ring" else n)
+    assert len({int(x) for x in outs[0]["summaries"]["order_hash"]}) == (1 if name == "linked_aligned_ring_spread" else n)
 
 
 def test_outbox_and_inbox_between_windows():

@@ -45,11 +45,17 @@ def test_the_fixtures_exercise_time_travel_loss_and_cross_counter_ties():
     lm, kw, z = G.load_linked("linked_lossy_fanout")
     outs, delivered, lost, _ = run_oracle(lm, kw, z)
     assert int(lost[0]) > 20 and int(delivered[0]) > 200
-    lm, kw, z = G.load_linked("linked_aligned_ring")
-    rec = z["p1_records"]
-    req = rec[rec["kind"] == A.HS_EV_REQ_ENQUEUE]
-    t, c = np.unique(req["time_ns"], return_counts=True)
-    assert (c > 1).sum() > 20                                                             # same-nanosecond requests at B.server
+    for name, exact in (("linked_aligned_ring", True), ("linked_aligned_ring_spread", False)):
+        lm, kw, z = G.load_linked(name)
+        rec = z["p1_records"]
+        req = rec[rec["kind"] == A.HS_EV_REQ_ENQUEUE]
+        t, c = np.unique(req["time_ns"], return_counts=True)
+        assert (c > 1).sum() > 20                                                         # same-nanosecond requests at B.server
+        # ties on time AND index between two different events (the payload a worker takes over keeps its index, and
+        # the bootstrap tick and the first run-time event both carry index 0: neither is a pair of rivals)
+        other = rec[(rec["kind"] != A.HS_EV_REQ_WORKER) & (rec["sort_index"] > 0)]
+        _, cc = np.unique(np.stack([other["time_ns"], other["sort_index"].astype(np.int64)], axis=1), axis=0, return_counts=True)
+        assert ((cc > 1).sum() > 0) == exact
 
 
 def test_replicas_are_independent_and_keyed_by_their_global_index():

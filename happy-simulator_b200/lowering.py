@@ -255,8 +255,13 @@ def _queue_policy(q):
     return (A.HS_Q_LIFO if name == "LIFOQueue" else A.HS_Q_FIFO), cap
 
 
-def lower(sources, entities, *, key_population: int | None = None, probes=None, horizon_s: float | None = None):
+def lower(sources, entities, *, key_population: int | None = None, probes=None, horizon_s: float | None = None,
+          remote: dict | None = None):
     """-> (FlatModel, objects) where objects[i] is the Python object of entity id i.
+
+    ``remote``: {id(object): link slot} for objects that live in ANOTHER partition of a ParallelSimulation: a Server
+    may name one as its downstream; it becomes an HS_ENT_REMOTE row (its destination entity id is filled in by the
+    caller once the other partition is lowered, parallel.py).
 
     Entity ids: sources first (in ``sources`` order, the bootstrap order of
     Simulation.__init__), then every entity reachable from them, in ``entities`` order
@@ -277,8 +282,12 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None, 
     for e in entities or []:
         add(e)
 
+    remote = remote or {}
+
     def kind_of(o):
         n = _cls(o)
+        if id(o) in remote:
+            return A.HS_ENT_REMOTE
         if hasattr(o, "_event_provider") and hasattr(o, "_time_provider"):
             return "probe" if _cls(o._event_provider) == "_ProbeEventProvider" else A.HS_ENT_SOURCE
         if hasattr(o, "_concurrency_model") and hasattr(o, "_service_time") and hasattr(o, "_queue"):
@@ -312,12 +321,17 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None, 
             t = getattr(o._event_provider, "_target", None)
             if t is None:
                 raise UnsupportedModelError(f"source {o.name!r}: event provider {_cls(o._event_provider)} has no target")
+            if id(t) in remote:        # parallel/validation.py:53-71
+                raise ValueError(f"Source {o.name!r} targets entity {getattr(t, 'name', t)!r} of another partition")
             add(t)
         elif k == A.HS_ENT_SERVER:
             if o._downstream is not None:
                 add(o._downstream)
         elif k == A.HS_ENT_LB:
             for info in o._backends.values():
+                if id(info.backend) in remote:
+                    raise UnsupportedModelError(f"load balancer {o.name!r}: backend {getattr(info.backend, 'name', '?')!r} lives in "
+                                                "another partition (only a Server's downstream may cross a PartitionLink)")
                 add(info.backend)
         i += 1
 
@@ -327,6 +341,9 @@ def lower(sources, entities, *, key_population: int | None = None, probes=None, 
     for o in objs:
         k = kind_of(o)
         name = getattr(o, "name", _cls(o))
+        if k == A.HS_ENT_REMOTE:
+            b.remote(f"{name}@remote", link=int(remote[id(o)]), dest_entity=0)
+            continue
         if k == "probe":
             ep = o._event_provider
             if ep.metric not in A.METRICS:

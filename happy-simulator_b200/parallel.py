@@ -2,9 +2,9 @@
 
 ``ParallelSimulation`` without links runs every partition as its own Simulation (own heap,
 own creation counter -- parallel/simulation.py:170-195) and aggregates the summaries exactly
-as the reference's ``_build_summary`` does.  Partitions connected by ``PartitionLink``s need the
-windowed coordinator (parallel/coordinator.py:75-227); that logical-process mode is SURVEY.md
-8(f) row 4 and is rejected here rather than approximated."""
+as the reference's ``_build_summary`` does.  Partitions connected by ``PartitionLink``s run under the
+windowed coordinator (parallel/coordinator.py:75-227) on the device: one engine per partition, one
+``hs_run`` per window and partition, ``hs_coordinator_exchange`` at every barrier (linked.py)."""
 from __future__ import annotations
 
 import time as _time
@@ -28,7 +28,11 @@ class SimulationPartition:
 
 @dataclass(frozen=True)
 class PartitionLink:
-    """parallel/link.py:18-79 (validation only; linked execution is not lowered yet)."""
+    """parallel/link.py:18-79.  ``latency``: a ConstantLatency / ExponentialLatency (this package's or the
+    reference's): the coordinator overrides every cross-partition event's time with send time + a sample of it
+    (coordinator.py:207-210).  Without it the reference insists on ``event.time - send_time >= min_latency``
+    (coordinator.py:211-221), which no stock component can satisfy -- Entity.forward stamps the event with the current
+    time -- so such a link cannot carry a lowered model's events."""
     source_partition: str
     dest_partition: str
     min_latency: float
@@ -63,6 +67,15 @@ class ParallelSimulationSummary:
     coordination_efficiency: float = 1.0
 
 
+def _events_bound(model, end_ns: int) -> float:
+    """Upper estimate of the Sink samples / service starts one replica of ``model`` produces (ring sizing)."""
+    from . import _abi as A
+    rate = 0.0
+    for i in model.ids_of(A.HS_ENT_SOURCE):
+        rate += float(model.entities["d0"][i])
+    return (rate * 4 + 50.0) * (end_ns / 1e9 + 1.0) + 4.0 * max(model.inbox_cap, 0)
+
+
 class ParallelSimulation:
     """parallel/simulation.py:31-284"""
 
@@ -75,12 +88,15 @@ class ParallelSimulation:
         names = [p.name for p in partitions]
         if len(set(names)) != len(names):
             raise ValueError("Partition names must be unique")       # parallel/validation.py
-        if links:
-            raise UnsupportedModelError("partitions connected by PartitionLinks need the windowed coordinator "
-                                        "(logical-process mode, SURVEY.md 8(f) row 4)")
         self._seed = seed
         self._partitions = partitions
+        self._device = device
+        self._links = list(links or [])
         self._simulations: dict[str, Simulation] = {}
+        self._linked = None
+        if self._links:
+            self._init_linked(start_time, end_time, duration, window_size)
+            return
         for k, p in enumerate(partitions):
             self._simulations[p.name] = Simulation(start_time=start_time, end_time=end_time, duration=duration,
                                                    sources=p.sources or None, entities=p.entities or None,
@@ -92,7 +108,158 @@ class ParallelSimulation:
     def simulations(self) -> dict[str, Simulation]:
         return dict(self._simulations)
 
+    # ---- partitions joined by links --------------------------------------------------------------------------
+    def _init_linked(self, start_time, end_time, duration, window_size):
+        """parallel/validation.py:19-110 + parallel/simulation.py:84-150: check the declarations, find the events that
+        cross partitions (a Server whose downstream lives elsewhere) and lower every partition to a model of its own."""
+        from . import _abi as A
+        from .api import Instant
+        from .linked import LinkedModel, LinkSpec
+        from .lowering import _service, lower
+        parts = self._partitions
+        names = [p.name for p in parts]
+        if start_time is not None and int(start_time.nanoseconds) != 0:
+            raise UnsupportedModelError("linked partitions start at Instant.Epoch")
+        if duration is not None:
+            end_time = Instant.Epoch + duration
+        if end_time is None:
+            raise UnsupportedModelError("linked partitions need an end time (auto-termination cannot end a Source)")
+        self._end_ns = int(end_time.nanoseconds)
+        index = {n: k for k, n in enumerate(names)}
+        for l in self._links:                                    # validation.py:73-84
+            if l.source_partition not in index:
+                raise ValueError(f"PartitionLink references unknown source partition '{l.source_partition}'")
+            if l.dest_partition not in index:
+                raise ValueError(f"PartitionLink references unknown dest partition '{l.dest_partition}'")
+        min_lat = min(l.min_latency for l in self._links)
+        if window_size is not None and window_size > min_lat:    # validation.py:103-110
+            raise ValueError(f"window_size ({window_size}s) must be <= min(link.min_latency) ({min_lat}s)")
+        window = float(window_size if window_size is not None else min_lat)
+        owner: dict[int, int] = {}
+        for k, p in enumerate(parts):                            # validation.py:40-51
+            for e in list(p.entities) + list(p.sources) + list(p.probes):
+                if id(e) in owner and owner[id(e)] != k:
+                    raise ValueError(f"Entity '{getattr(e, 'name', e)}' is in partitions '{names[owner[id(e)]]}' and '{p.name}'")
+                owner[id(e)] = k
+        streams: dict[int, int] = {}
+        out_links: list[list] = [[] for _ in parts]
+        slot_of: list[dict[int, int]] = [dict() for _ in parts]    # destination partition -> link slot
+        for l in self._links:
+            if l.latency is None:
+                raise UnsupportedModelError(
+                    f"PartitionLink {l.source_partition}->{l.dest_partition} has no latency override: the reference then "
+                    "requires event.time - send_time >= min_latency (coordinator.py:211-221), and every stock component "
+                    "forwards with the current time, so the reference itself raises on the first cross-partition event")
+            kind, mean = _service(l.latency)
+            s = streams.setdefault(id(l.latency), len(streams))
+            q, d = index[l.source_partition], index[l.dest_partition]
+            slot_of[q][d] = len(out_links[q])
+            out_links[q].append(LinkSpec(d, kind, mean, float(l.packet_loss), s))
+        models, objects = [], []
+        hidden = lambda ents: {id(getattr(o, a)) for o in ents for a in ("queue", "driver", "worker")
+                               if hasattr(o, "_concurrency_model") and hasattr(o, a)}
+        for k, p in enumerate(parts):
+            skip = hidden(p.entities)       # a reference script has to list a Server's hidden parts for its router
+            ents = [e for e in p.entities if id(e) not in skip]
+            remote = {}
+            for e in ents:                  # the only edge that may leave a partition: Server -> downstream
+                t = getattr(e, "_downstream", None) if hasattr(e, "_concurrency_model") else None
+                if t is not None and id(t) in owner and owner[id(t)] != k:
+                    d = owner[id(t)]
+                    if d not in slot_of[k]:
+                        raise ValueError(f"Entity '{getattr(e, 'name', e)}' in partition '{p.name}' references entity "
+                                         f"'{getattr(t, 'name', t)}' in partition '{names[d]}' without a PartitionLink "
+                                         f"('{p.name}' -> '{names[d]}')")       # validation.py:160-200
+                    remote[id(t)] = slot_of[k][d]
+            m, objs = lower(p.sources or [], ents, probes=p.probes or None, horizon_s=self._end_ns / 1e9, remote=remote)
+            models.append(m)
+            objects.append(objs)
+        for k, m in enumerate(models):      # REMOTE rows: the entity's id over there
+            m.entities = m.entities.copy()
+            for i in m.ids_of(A.HS_ENT_REMOTE):
+                d = out_links[k][int(m.entities["i0"][i])].dest
+                where = [j for j, o in enumerate(objects[d]) if o is objects[k][i]]
+                if not where:
+                    raise UnsupportedModelError(f"'{getattr(objects[k][i], 'name', '?')}' is not an entity of partition '{names[d]}'")
+                m.entities["i1"][i] = where[0]
+            if m.ids_of(A.HS_ENT_REMOTE):
+                m.outbox_cap = self.link_buffer
+        for q in range(len(parts)):
+            for l in out_links[q]:
+                models[l.dest].inbox_cap = self.link_buffer * max(1, sum(1 for qq in range(len(parts)) for x in out_links[qq] if x.dest == l.dest))
+        self._linked = LinkedModel(models, names, out_links, window_s=window, n_streams=max(1, len(streams)), objects=objects)
+        self._linked.validate()
+
+    link_buffer = 256        # cross-partition events one replica may emit per window (class default; overflow is reported)
+
+    def _run_linked(self, n_replicas: int = 1):
+        from . import _abi as A
+        from .api import Instant
+        from .linked import LinkedRun
+        lm = self._linked
+        t0 = _time.monotonic()
+        run = LinkedRun(lm, device=self._device)
+        try:
+            caps = []
+            for m in lm.models:
+                ev = max(64, int(_events_bound(m, self._end_ns)))
+                many = len(m.ids_of(A.HS_ENT_SINK)) + len(m.ids_of(A.HS_ENT_PROBE)) > 1 or len(m.ids_of(A.HS_ENT_SERVER)) > 1
+                caps.append(dict(sample_cap=ev, service_cap=ev, record_cap=8 * ev if many else 0))   # records tell the sinks / servers apart
+            outs, (delivered, lost, over) = run.run(seed=self._seed, end_ns=self._end_ns, n_replicas=n_replicas, caps=caps, flags=0)
+        finally:
+            run.close()
+        wall = _time.monotonic() - t0
+        bad = [(lm.names[q], int(s)) for q, o in enumerate(outs) for s in o["summaries"]["status"] if int(s) & ~A.HS_ST_LINK_TIE]
+        if bad or over.any():
+            raise RuntimeError(f"linked run did not complete cleanly: partition status {bad[:4]}, inbox overflows {int(over.sum())} "
+                               f"(raise ParallelSimulation.link_buffer, now {self.link_buffer})")
+        self.link_ties = int(sum(int(s) & A.HS_ST_LINK_TIE != 0 for o in outs for s in o["summaries"]["status"]))
+        self.last_outputs, self.last_delivered, self.last_lost = outs, delivered, lost
+        return outs, delivered, lost, wall, run.windows
+
     def run(self) -> ParallelSimulationSummary:
+        if self._linked is not None:
+            return self._summarise_linked(*self._run_linked(1))
+        return self._run_independent()
+
+    def _summarise_linked(self, outs, delivered, lost, wall, windows) -> ParallelSimulationSummary:
+        """coordinator.py:123-172: per-partition summaries from the partitions' final state, the aggregate like
+        _build_summary; results are written back onto the script's own objects (replica 0)."""
+        from .api import Instant
+        lm = self._linked
+        summaries = {}
+        for q, name in enumerate(lm.names):
+            shell = Simulation.__new__(Simulation)
+            shell.model, shell.objects, shell._instant_cls = lm.models[q], lm.objects[q], Instant
+            shell._entities = [o for o in self._partitions[q].entities if any(o is x for x in lm.objects[q])]
+            shell._write_back(outs[q], 0)
+            s = outs[q]["summaries"][0]
+            d = float(int(s["final_time_ns"])) / 1e9
+            ev = int(s["events_processed"])
+            summaries[name] = SimulationSummary(duration_s=d, total_events_processed=ev, events_per_second=ev / d if d > 0 else 0.0,
+                                                wall_clock_seconds=wall, entities=shell._entity_summaries())
+        total = sum(s.total_events_processed for s in summaries.values())
+        duration_s = max((s.duration_s for s in summaries.values()), default=0.0)
+        merged = {}
+        for s in summaries.values():
+            merged.update(s.entities)
+        n = len(summaries)
+        return ParallelSimulationSummary(
+            duration_s=duration_s, total_events_processed=total, events_per_second=total / duration_s if duration_s > 0 else 0.0,
+            wall_clock_seconds=wall, partitions=summaries, entities=merged,
+            partition_wall_times={nm: wall / n for nm in summaries}, speedup=1.0, parallelism_efficiency=1.0 / n if n else 1.0,
+            total_windows=windows, total_cross_partition_events=int(delivered[0]), window_size_s=lm.window_s)
+
+    def run_ensemble(self, n_replicas: int):
+        """Linked partitions only: n replicas of the whole ParallelSimulation in one set of launches.  Returns
+        {partition name: per-replica outputs (Engine.read_outputs)}, delivered and lost cross-partition events per
+        replica."""
+        if self._linked is None:
+            raise UnsupportedModelError("run_ensemble is for partitions joined by PartitionLinks")
+        outs, delivered, lost, wall, windows = self._run_linked(n_replicas)
+        return {n: o for n, o in zip(self._linked.names, outs)}, delivered, lost
+
+    def _run_independent(self) -> ParallelSimulationSummary:
         """Independent partitions (parallel/simulation.py:170-195).  Partitions whose lowered models share a
         topology (``api._same_topology``: they differ at most in rates, mean service times and concurrency) are
         the replicas of ONE device launch, replica word = partition index as in the sequential case; the others

@@ -100,3 +100,26 @@ def test_linked_models_need_the_thread_engine_and_an_outbox():
             e.upload(m)
     finally:
         e.close()
+
+
+def test_api_parallel_simulation_with_a_link_equals_the_reference_fixture():
+    """hs.ParallelSimulation(partitions, links=[...]).run(): the numbers the unmodified reference's ParallelSimulation
+    produced for the same declaration (fixture linked_tandem_const), on the script's own objects."""
+    import happysim_b200 as hs
+    from test_parallel_linked import tandem
+    parts, link, (src, sa, sb, sink) = tandem()
+    ps = hs.ParallelSimulation(parts, duration=4.0, links=[link], seed=5)
+    summ = ps.run()
+    lm, kw, z = G.load_linked("linked_tandem_const")
+    assert summ.total_windows == int(z["total_windows"]) and summ.total_cross_partition_events == int(z["cross_events"])
+    assert summ.total_events_processed == int(z["total_events"]) and summ.window_size_s == 0.05
+    assert [s.total_events_processed for s in summ.partitions.values()] == [int(z[f"p{q}_summaries"]["events_processed"][0]) for q in range(2)]
+    assert sink.latencies_s == [float(x) for x in z["p1_sink_samples"]["latency_s"]]
+    assert [t.nanoseconds for t in sink.completion_times] == [int(x) for x in z["p1_sink_samples"]["completion_ns"]]
+    assert sa.stats.requests_completed == int(z["p0_entity_stats"][0][1]["c2"]) > 100
+    assert sb.stats.requests_completed == int(z["p1_entity_stats"][0][0]["c2"]) > 100
+    assert src.generated_count == int(z["p0_entity_stats"][0][0]["c0"]) and ps.link_ties == 0
+    assert set(summ.entities) >= {"A.server", "B.server", "B.sink"}
+    ens, delivered, lost = ps.run_ensemble(24)
+    assert int(delivered[0]) == int(z["cross_events"]) and not lost.any() and len(set(int(x) for x in delivered)) > 3
+    assert int(ens["B"]["summaries"]["events_processed"][0]) == int(z["p1_summaries"]["events_processed"][0])

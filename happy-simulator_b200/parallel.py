@@ -192,7 +192,7 @@ class ParallelSimulation:
 
     link_buffer = 256        # cross-partition events one replica may emit per window (class default; overflow is reported)
 
-    def _run_linked(self, n_replicas: int = 1):
+    def _run_linked(self, n_replicas: int = 1, replica_index_base: int = 0):
         from . import _abi as A
         from .api import Instant
         from .linked import LinkedRun
@@ -205,7 +205,8 @@ class ParallelSimulation:
                 ev = max(64, int(_events_bound(m, self._end_ns)))
                 many = len(m.ids_of(A.HS_ENT_SINK)) + len(m.ids_of(A.HS_ENT_PROBE)) > 1 or len(m.ids_of(A.HS_ENT_SERVER)) > 1
                 caps.append(dict(sample_cap=ev, service_cap=ev, record_cap=8 * ev if many else 0))   # records tell the sinks / servers apart
-            outs, (delivered, lost, over) = run.run(seed=self._seed, end_ns=self._end_ns, n_replicas=n_replicas, caps=caps, flags=0)
+            outs, (delivered, lost, over) = run.run(seed=self._seed, end_ns=self._end_ns, n_replicas=n_replicas, replica_index_base=replica_index_base,
+                                                    caps=caps, flags=0)
         finally:
             run.close()
         wall = _time.monotonic() - t0
@@ -250,13 +251,13 @@ class ParallelSimulation:
             partition_wall_times={nm: wall / n for nm in summaries}, speedup=1.0, parallelism_efficiency=1.0 / n if n else 1.0,
             total_windows=windows, total_cross_partition_events=int(delivered[0]), window_size_s=lm.window_s)
 
-    def run_ensemble(self, n_replicas: int):
+    def run_ensemble(self, n_replicas: int, replica_index_base: int = 0):
         """Linked partitions only: n replicas of the whole ParallelSimulation in one set of launches.  Returns
         {partition name: per-replica outputs (Engine.read_outputs)}, delivered and lost cross-partition events per
         replica."""
         if self._linked is None:
             raise UnsupportedModelError("run_ensemble is for partitions joined by PartitionLinks")
-        outs, delivered, lost, wall, windows = self._run_linked(n_replicas)
+        outs, delivered, lost, wall, windows = self._run_linked(n_replicas, replica_index_base)     # a rank's shard: base = rank * n
         return {n: o for n, o in zip(self._linked.names, outs)}, delivered, lost
 
     def _run_independent(self) -> ParallelSimulationSummary:

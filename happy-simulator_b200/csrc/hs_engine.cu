@@ -439,11 +439,16 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
         const size_t dyn_smem = (size_t)R.heap_top * (HS_THREAD_BLOCK / R.lane_stride) * 16;
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
 #define HS_LAUNCH_THREAD(F) case F: hs_thread_kernel<F><<<tblocks, HS_THREAD_BLOCK, dyn_smem, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;
-        switch (fl | (R.heap_top ? HS_WF_HEAPTOP : 0)) {
+        const bool linked_model = E->outbox_cap || E->inbox_cap || R.linked;
+        if (linked_model && (fl & HS_WF_PROFILE)) return fail(HS_ERR_INVALID, "linked partitions with non-constant rate profiles are not compiled in");
+        switch (fl | (R.heap_top ? HS_WF_HEAPTOP : 0) | (linked_model ? HS_WF_LINKED : 0)) {
         HS_LAUNCH_THREAD(0) HS_LAUNCH_THREAD(1) HS_LAUNCH_THREAD(2) HS_LAUNCH_THREAD(3)
         HS_LAUNCH_THREAD(4) HS_LAUNCH_THREAD(5) HS_LAUNCH_THREAD(6) HS_LAUNCH_THREAD(7)
         HS_LAUNCH_THREAD(8) HS_LAUNCH_THREAD(9) HS_LAUNCH_THREAD(10) HS_LAUNCH_THREAD(11)
         HS_LAUNCH_THREAD(12) HS_LAUNCH_THREAD(13) HS_LAUNCH_THREAD(14) HS_LAUNCH_THREAD(15)
+        HS_LAUNCH_THREAD(16) HS_LAUNCH_THREAD(17) HS_LAUNCH_THREAD(18) HS_LAUNCH_THREAD(19)        /* LINKED (no PROFILE) */
+        HS_LAUNCH_THREAD(24) HS_LAUNCH_THREAD(25) HS_LAUNCH_THREAD(26) HS_LAUNCH_THREAD(27)
+        default: return fail(HS_ERR_STATE, "no thread kernel for flags %d", fl);
         }
 #undef HS_LAUNCH_THREAD
         CUDA_TRY(cudaGetLastError());

@@ -151,7 +151,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     int64_t h_now = 0, h_processed = 0; uint64_t h_hash = 0; int32_t h_fel = 0;   /* its hot fields, in registers (see below) */
     if (P.resume) {
         hdr = *Hg;
-        if (hdr.done && !P.linked) return;       /* a linked partition's next window: the end time has moved on, events may have arrived */
+        if (hdr.done && !((FLAGS & HS_WF_LINKED) && P.linked)) return;       /* a linked partition's next window: the end time has moved on, events may have arrived */
         h_now = H->now; h_processed = H->processed; h_hash = H->hash; h_fel = H->fel_n;
         for (uint32_t i = 0; i < TOP && i < hdr.free_top + HS_T_ARITY; ++i) {      /* the heap's top levels (free_top = heap size) */
             const hs_tkey k = K[i];
@@ -263,7 +263,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (nb < 0) { alive = false; return; }           /* heap exhausted */
             if (windowed && nt > P.window_end_ns) { paused = true; alive = false; return; }
             ev = now_load(nb);
-            if (M.inbox_cap) {
+            if ((FLAGS & HS_WF_LINKED) && M.inbox_cap) {
                 if (ev.time == prev_t && ev.idx == prev_i && prev_x) hdr.status |= HS_ST_LINK_TIE;
                 prev_t = ev.time; prev_i = ev.idx; prev_x = 0u;
             }
@@ -574,7 +574,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
 #define HS_W_PUSH(TIME, IDX, KIND, ENT, CREATED, AUX, KEY, HOOK)                                         \
     do {                                                                                                 \
         const int64_t t_ = (TIME);                                                                       \
-        if ((KIND) == HS_EV_REQ_ANY && M.outbox_cap && ENTS[(ENT)].kind == HS_ENT_REMOTE)                \
+        if ((FLAGS & HS_WF_LINKED) && (KIND) == HS_EV_REQ_ANY && M.outbox_cap && ENTS[(ENT)].kind == HS_ENT_REMOTE)                \
             outbox_send((IDX), (CREATED), (KEY), (uint32_t)(ENT), now);                                  \
         else if (t_ <= now) {                                                                                 \
             if (now_n >= HS_W_NCAP) hdr.status |= HS_ST_FEL_OVERFLOW;                                    \
@@ -605,7 +605,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     /* linked partitions: what the coordinator delivered at the last barrier is scheduled before the first pop
      * (WindowedCoordinator._exchange_events -> Simulation.schedule = heap push, core/simulation.py:195-206); an event
      * that lies behind this replica's clock is dropped by the time-travel test when it is popped */
-    if (M.inbox_cap && O.inbox_n) {
+    if ((FLAGS & HS_WF_LINKED) && M.inbox_cap && O.inbox_n) {
         const uint32_t n_in = O.inbox_n[r];
         for (uint32_t k = 0; k < n_in; ++k) {
             const hs_xevent x = O.inbox[(size_t)r * M.inbox_cap + k];
@@ -625,8 +625,8 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             const uint32_t slot = (uint32_t)(top_k & 0xffffu);
             const hs_tpay pp = PAY[slot];
             ev.time = top_t; ev.idx = top_k >> 16; ev.created = pp.created; ev.aux = pp.aux;
-            ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = pp.pad;
-            if (M.inbox_cap) {                           /* a delivered event that ties on (time, sort index): see HS_ST_LINK_TIE */
+            ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = (FLAGS & HS_WF_LINKED) ? pp.pad : 0u;
+            if ((FLAGS & HS_WF_LINKED) && M.inbox_cap) {         /* a delivered event that ties on (time, sort index): see HS_ST_LINK_TIE */
                 if (ev.time == prev_t && ev.idx == prev_i && (ev.pad | prev_x)) hdr.status |= HS_ST_LINK_TIE;
                 prev_t = ev.time; prev_i = ev.idx; prev_x = ev.pad;
             }

@@ -37,6 +37,8 @@
 #define HS_WF_REC 2
 #define HS_WF_PROFILE 4    /* some Source has a non-constant rate profile (Simpson + Brent calls) */
 #define HS_WF_HEAPTOP 8    /* thread engine: the heap's top levels live in shared memory (launches with several replicas per warp) */
+#define HS_WF_LINKED 16    /* thread engine: a partition of a linked ParallelSimulation (REMOTE rows -> outbox, inbox drained at
+                              launch, finished replicas run on, tie detection); compiled out of every other launch */
 
 struct __align__(16) hs_warp_hdr {      /* 128 B */
     int64_t now; uint64_t ctr; int64_t processed; uint64_t hash;

@@ -275,7 +275,7 @@ def test_parallel_simulation_independent_partitions():
     alone = hs.Simulation(duration=40.0, sources=pa2.sources, entities=pa2.entities, seed=5, replica=0).run()
     assert alone.total_events_processed == summ.partitions["a"].total_events_processed
     assert sa2.latencies_s == sa.latencies_s and sb.events_received > sa.events_received
-    with pytest.raises(hs.UnsupportedModelError, match="windowed coordinator"):
+    with pytest.raises(hs.UnsupportedModelError, match="no latency override"):      # linked runs: tests/test_gpu_linked.py
         hs.ParallelSimulation([pa, pb], duration=1.0, links=[hs.PartitionLink("a", "b", min_latency=0.1)])
     with pytest.raises(ValueError, match="min_latency must be > 0"):
         hs.PartitionLink("a", "b", min_latency=0.0)

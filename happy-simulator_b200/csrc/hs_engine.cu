@@ -95,6 +95,7 @@ struct hs_engine {
     dev_buf d_state, d_rings, d_summ, d_stats, d_rec, d_smp, d_svc, d_partials, d_totals, d_srv_index, d_counter;
     /* linked partitions */
     uint32_t outbox_cap = 0, inbox_cap = 0;
+    std::vector<int32_t> srv_index_host;        /* what d_srv_index holds */
     dev_buf d_outbox, d_outbox_n, d_inbox, d_inbox_n;
     uint32_t link_replicas = 0;                 /* replicas the outbox / inbox buffers are sized for */
 };
@@ -353,8 +354,11 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
     if ((rc = E->d_rings.ensure(std::max<size_t>(16, (size_t)n * n_servers * ring * sizeof(hs_wring_entry))))) return rc;
     if ((rc = E->d_srv_index.ensure(ne * 4 + 16))) return rc;
     if ((rc = E->d_counter.ensure(16))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(E->d_srv_index.p, srv_index.data(), ne * 4, cudaMemcpyHostToDevice, E->stream));
-    CUDA_TRY(cudaStreamSynchronize(E->stream));     /* srv_index is a local */
+    if (E->srv_index_host != srv_index) {            /* uploaded once per model: the window loop of a linked run stays asynchronous */
+        E->srv_index_host = srv_index;
+        CUDA_TRY(cudaMemcpyAsync(E->d_srv_index.p, E->srv_index_host.data(), ne * 4, cudaMemcpyHostToDevice, E->stream));
+        CUDA_TRY(cudaStreamSynchronize(E->stream));
+    }
     CUDA_TRY(cudaMemsetAsync(E->d_counter.p, 0, 16, E->stream));
 
     hs_warp_model M;
@@ -992,6 +996,7 @@ int hs_coordinator_exchange(hs_coordinator *c, hs_engine *src, uint32_t n_links,
     if (src->link_replicas != c->n) return fail(HS_ERR_STATE, "the coordinator was created for %u replicas, the partition ran %u", c->n, src->link_replicas);
     CUDA_TRY(cudaSetDevice(c->device));
     hs_links_dev LK; memset(&LK, 0, sizeof LK);
+    bool foreign = src->stream != c->stream;          /* everything on one stream: the window loop needs no host synchronisation */
     for (const hs_entity_desc &e : src->ents)
         if (e.kind == HS_ENT_REMOTE && (uint32_t)e.i0 >= n_links) return fail(HS_ERR_INVALID, "a REMOTE row uses link slot %d of %u", e.i0, n_links);
     for (uint32_t k = 0; k < n_links; ++k) {
@@ -1011,7 +1016,7 @@ int hs_coordinator_exchange(hs_coordinator *c, hs_engine *src, uint32_t n_links,
         LK.l[k].kind = links[k].latency_kind; LK.l[k].stream = links[k].stream; LK.l[k].mean_s = links[k].latency_mean_s;
         LK.l[k].loss = links[k].packet_loss; LK.l[k].inbox = (hs_xevent *)D->d_inbox.p; LK.l[k].inbox_n = (uint32_t *)D->d_inbox_n.p;
         LK.l[k].inbox_cap = D->inbox_cap;
-        if (D->stream != c->stream) CUDA_TRY(cudaStreamSynchronize(D->stream));
+        if (D->stream != c->stream) { foreign = true; CUDA_TRY(cudaStreamSynchronize(D->stream)); }
     }
     if (src->stream != c->stream) CUDA_TRY(cudaStreamSynchronize(src->stream));
     const uint32_t threads = 128, blocks = (c->n + threads - 1) / threads;
@@ -1019,7 +1024,7 @@ int hs_coordinator_exchange(hs_coordinator *c, hs_engine *src, uint32_t n_links,
         (const hs_entity_desc *)src->d_ents.p, LK, c->n, c->n_streams, c->seed, c->seed_stride, c->rid_base, c->rid_stride, c->index_base,
         (uint64_t *)c->d_loss_draws.p, (uint64_t *)c->d_lat_draws.p, (uint64_t *)c->d_counts.p);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(c->stream));      /* the partitions' streams may differ from the coordinator's */
+    if (foreign) CUDA_TRY(cudaStreamSynchronize(c->stream));      /* a partition on another stream must not run ahead of the barrier */
     src->launches += 1;
     return HS_OK;
 }

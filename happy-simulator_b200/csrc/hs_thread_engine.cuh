@@ -263,8 +263,10 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (nb < 0) { alive = false; return; }           /* heap exhausted */
             if (windowed && nt > P.window_end_ns) { paused = true; alive = false; return; }
             ev = now_load(nb);
-            if ((FLAGS & HS_WF_LINKED) && M.inbox_cap) {
-                if (ev.time == prev_t && ev.idx == prev_i && prev_x) hdr.status |= HS_ST_LINK_TIE;
+            if ((FLAGS & HS_WF_LINKED) && M.inbox_cap) {      /* remembered for the tie test at the next heap pop.  An event of
+                                                                  * this tier that repeats the key of the delivered event popped just
+                                                                  * before it is that event's own child (had it been pending already,
+                                                                  * it would have been popped first): no rival, no flag */
                 prev_t = ev.time; prev_i = ev.idx; prev_x = 0u;
             }
             now_n--;

@@ -111,11 +111,11 @@ class Coordinator:
     counters of the loss stream and the links' latency streams, delivery totals."""
 
     def __init__(self, device: int, n_replicas: int, n_streams: int, *, seed, seed_stride=0, rid_base, rid_stride,
-                 replica_index_base=0):
+                 replica_index_base=0, stream: int | None = None):
         self._L = load_library()
         self._h = C.c_void_p()
         self.n_replicas = int(n_replicas)
-        _check(self._L, self._L.hs_coordinator_create(device, None, n_replicas, n_streams, seed, seed_stride, rid_base,
+        _check(self._L, self._L.hs_coordinator_create(device, C.c_void_p(stream or 0), n_replicas, n_streams, seed, seed_stride, rid_base,
                                                       rid_stride, replica_index_base, C.byref(self._h)))
 
     def exchange(self, src: "Engine", links, dsts) -> None:

@@ -95,9 +95,15 @@ class LinkedRun:
 
     def __init__(self, lm: LinkedModel, *, device: int = 0):
         from . import engine as _engine
+        import torch
         lm.validate()
         self.lm, self.device = lm, device
-        self.engines = [_engine.Engine(device) for _ in lm.models]
+        # one CUDA stream for every partition and the coordinator: the window loop (partitions x windows launches plus the
+        # barrier kernels) is queued without a host synchronisation in between
+        self._stream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None
+        sp = self._stream.cuda_stream if self._stream is not None else None
+        self._stream_ptr = sp
+        self.engines = [_engine.Engine(device, stream=sp) for _ in lm.models]
         for e, m in zip(self.engines, lm.models):
             e.upload(m)
         self.coordinator = None
@@ -117,7 +123,7 @@ class LinkedRun:
         if self.coordinator is not None:
             self.coordinator.close()
         self.coordinator = _engine.Coordinator(self.device, n_replicas, lm.n_streams, seed=seed, rid_base=nP,
-                                               rid_stride=nP + 1, replica_index_base=replica_index_base)
+                                               rid_stride=nP + 1, replica_index_base=replica_index_base, stream=self._stream_ptr)
         caps = caps or {}
         link_args = [lm.link_descs(q) for q in range(nP)]
         ends = lm.window_ends(end_ns)

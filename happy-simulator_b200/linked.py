@@ -50,7 +50,10 @@ class LinkedModel:
                 w = end_s
             nxt = int(w * 1_000_000_000)
             if nxt <= cur:
-                raise ValueError(f"window of {self.window_s} s does not advance the clock at {cur} ns")
+                # e.g. an end time whose nanoseconds do not survive the trip through float seconds: the clamped window
+                # ends 1 ns short of it, for ever -- the reference's coordinator never returns from such a run
+                raise ValueError(f"window of {self.window_s} s does not advance the clock at {cur} ns (end {end_ns} ns): "
+                                 "the reference's WindowedCoordinator would loop for ever")
             ends.append(nxt)
             cur = nxt
         return ends

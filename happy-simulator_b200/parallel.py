@@ -189,6 +189,7 @@ class ParallelSimulation:
                 models[l.dest].inbox_cap = self.link_buffer * max(1, sum(1 for qq in range(len(parts)) for x in out_links[qq] if x.dest == l.dest))
         self._linked = LinkedModel(models, names, out_links, window_s=window, n_streams=max(1, len(streams)), objects=objects)
         self._linked.validate()
+        self._linked.window_ends(self._end_ns)      # raises if the coordinator's clock could not reach the end time
 
     link_buffer = 256        # cross-partition events one replica may emit per window (class default; overflow is reported)
 

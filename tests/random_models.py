@@ -5,6 +5,7 @@ and on the device engines and compare every output bit for bit."""
 import numpy as np
 
 import happysim_b200 as hs
+from happysim_b200 import _abi as A
 
 
 def random_model(seed: int, with_extras: bool = False):
@@ -193,3 +194,108 @@ def random_model_v2(seed: int, with_extras: bool = False):
     end_s = float(rng.uniform(1.5, 4.0))
     what = f"v2 seed {seed}: {shape}, K={K}, rate {rate}{' step' if step is not None else ''}, {model.n_entities} entities"
     return (model, end_s, what, extras) if with_extras else (model, end_s, what)
+
+
+def random_linked_model(seed: int):
+    """Random ParallelSimulation with PartitionLinks: 2-4 partitions, each an optional source, an
+    entry (a server, a two-server chain or a load balancer over two servers), a sink and a counter; the last server of a
+    partition forwards to its own sink / counter / key sketch, to the entry of a LATER partition, or back into an EARLIER
+    partition's sink or counter.  Links: constant or exponential latency between 1x and 3x the window (exponential:
+    plenty of time travel), some lossy, some sharing one latency object.  About a third of the seeds put everything on
+    a grid (constant sources, service times and latencies) so that cross-partition events tie with local ones on the
+    nanosecond.  -> (LinkedModel, end_seconds, description)"""
+    from happysim_b200.linked import LinkedModel, LinkSpec
+    rng = np.random.RandomState(70_000 + seed)
+    nP = int(rng.randint(2, 5))
+    W = float(rng.choice([0.02, 0.05, 0.1]))
+    grid = bool(rng.rand() < 0.35)
+    K = int(rng.choice([0, 0, 20]))
+    builders, info = [], []
+    for p in range(nP):
+        b = hs.ModelBuilder()
+        ids = {}
+        has_src = p == 0 or rng.rand() < 0.55
+        rate = float(rng.choice([50.0, 100.0])) if grid else float(rng.choice([20.0, 60.0, 150.0]))
+        if has_src:
+            ids["src"] = b.source(f"P{p}.src", rate=rate, poisson=(not grid) and bool(rng.rand() < 0.75), key_population=K)
+
+        def server(name, n_par=1):
+            c = int(rng.choice([1, 1, 2, 3]))
+            if grid:
+                svc, expo = float(rng.choice([0.005, 0.01])), False
+            else:
+                svc, expo = c * n_par / (rate * 1.6) * float(rng.uniform(0.5, 1.1)), bool(rng.rand() < 0.7)
+            return b.server(name, concurrency=c, mean_service_s=svc, exponential=expo,
+                            capacity=int(rng.choice([-1, -1, 2, 6])), lifo=bool(rng.rand() < 0.25))
+        shape = str(rng.choice(["one", "chain", "lb"]))
+        if shape == "one":
+            tail = [server(f"P{p}.s0")]
+            ids["entry"] = tail[0]
+        elif shape == "chain":
+            s0, s1 = server(f"P{p}.s0"), server(f"P{p}.s1")
+            b.set_target(s0, s1)
+            ids["entry"], tail = s0, [s1]
+        else:
+            tail = [server(f"P{p}.s0", 2), server(f"P{p}.s1", 2)]
+            ids["entry"] = b.load_balancer(f"P{p}.lb", backends=tail)
+        ids["sink"], ids["counter"] = b.sink(f"P{p}.sink"), b.counter(f"P{p}.counter")
+        if K:
+            ids["sketch"] = b.sketch_topk(f"P{p}.heavy", k=5, key_population=K)
+        if has_src:
+            b.set_target(ids["src"], ids["entry"])
+        builders.append(b)
+        info.append((ids, tail))
+    links: list[list] = [[] for _ in range(nP)]
+    shared = {}
+    rems = {}
+    any_link = False
+    for p in range(nP):
+        ids, tail = info[p]
+        for k, sv in enumerate(tail):
+            must = (p == 0 and k == 0 and not any_link)
+            choice = "fwd" if must else str(rng.choice(["sink", "counter", "sketch", "fwd", "fwd", "back"]))
+            if choice == "sketch" and not K:
+                choice = "sink"
+            if choice == "fwd" and p == nP - 1:
+                choice = "back"
+            if choice == "back" and p == 0:
+                choice = "counter"
+            if choice in ("sink", "counter", "sketch"):
+                builders[p].set_target(sv, ids[choice])
+                continue
+            q = int(rng.randint(p + 1, nP)) if choice == "fwd" else int(rng.randint(0, p))
+            dest = info[q][0]["entry"] if choice == "fwd" else info[q][0][str(rng.choice(["sink", "counter"]))]
+            slot = next((s for s, l in enumerate(links[p]) if l.dest == q), None)
+            if slot is None:
+                if grid:
+                    kind, mean = A.HS_SVC_CONSTANT, W * float(rng.choice([1.0, 2.0]))
+                else:
+                    kind = A.HS_SVC_EXPONENTIAL if rng.rand() < 0.4 else A.HS_SVC_CONSTANT
+                    mean = W * float(rng.choice([1.0, 1.5, 3.0]))
+                stream = shared.setdefault((kind, mean), len(shared))
+                slot = len(links[p])
+                links[p].append(LinkSpec(q, kind, mean, float(rng.choice([0.0, 0.0, 0.1, 0.3])) if not grid else 0.0, stream))
+            rem = rems.get((p, q, dest))          # one REMOTE row per remote entity, as the lowering produces them
+            if rem is None:
+                rem = rems[(p, q, dest)] = builders[p].remote(f"P{q}.{dest}@P{p}", link=slot, dest_entity=dest)
+            builders[p].set_target(sv, rem)
+            any_link = True
+    models = [b.build() for b in builders]
+    for p, m in enumerate(models):
+        m.outbox_cap = 256 if m.ids_of(A.HS_ENT_REMOTE) else 0
+        m.inbox_cap = 256 if any(l.dest == p for ls in links for l in ls) else 0
+    lm = LinkedModel(models, [f"P{p}" for p in range(nP)], links, window_s=W, n_streams=max(1, len(shared)))
+    lm.validate()
+    end_s = round(float(rng.uniform(1.0, 2.5)), 2)
+    while True:          # an end time that does not survive ns -> float seconds -> ns sends the reference's coordinator into
+        try:             # an endless loop (the clamped last window ends 1 ns short, coordinator.py:88-95): not a test case
+            lm.window_ends(int(end_s * 1e9))
+            break
+        except ValueError:
+            end_s = round(end_s + 0.01, 2)
+    what = f"linked seed {seed}: {nP} partitions, window {W}, {'grid' if grid else 'continuous'}, K={K}, " \
+           f"{sum(len(l) for l in links)} links, {sum(m.n_entities for m in models)} entities"
+    return lm, end_s, what
+
+
+LINKED_SEEDS = 72

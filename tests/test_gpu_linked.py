@@ -123,3 +123,41 @@ def test_api_parallel_simulation_with_a_link_equals_the_reference_fixture():
     ens, delivered, lost = ps.run_ensemble(24)
     assert int(delivered[0]) == int(z["cross_events"]) and not lost.any() and len(set(int(x) for x in delivered)) > 3
     assert int(ens["B"]["summaries"]["events_processed"][0]) == int(z["p1_summaries"]["events_processed"][0])
+
+
+def test_random_linked_models_on_the_device():
+    """The 72 random linked ParallelSimulations (tests/random_models.random_linked_model; oracle == reference on all of
+    them, tests/test_random_linked.py): 6 replicas each on the device against the oracle.  A replica in which a delivered
+    event tied with another on time AND index is flagged (HS_ST_LINK_TIE; only the grid models can) and is left out."""
+    import random_models as RM
+    flagged = compared = 0
+    for seed in range(RM.LINKED_SEEDS):
+        lm, end_s, what = RM.random_linked_model(seed)
+        end_ns, nP, n = int(end_s * 1e9), lm.n_partitions, 6
+        caps = [dict(record_cap=512, sample_cap=64, service_cap=64) for _ in range(nP)]
+        run = LinkedRun(lm)
+        try:
+            outs, (delivered, lost, over) = run.run(seed=1000 + seed, end_ns=end_ns, n_replicas=n, caps=caps)
+        finally:
+            run.close()
+        ps = [O.make_params(seed=1000 + seed, end_ns=end_ns, n_replicas=n, rid_base=q, rid_stride=nP + 1, **caps[q]) for q in range(nP)]
+        want, wd, wl, _ = O.oracle_run_linked(lm, ps, end_ns=end_ns, cseed=1000 + seed)
+        assert not over.any(), what
+        tie = np.zeros(n, bool)
+        for o in outs:
+            tie |= (o["summaries"]["status"] & A.HS_ST_LINK_TIE) != 0
+        assert "grid" in what or not tie.any(), what
+        flagged += int(tie.sum())
+        for r in np.nonzero(~tie)[0]:
+            compared += 1
+            assert (int(delivered[r]), int(lost[r])) == (int(wd[r]), int(wl[r])), (what, r)
+            for q in range(nP):
+                g, w = outs[q]["summaries"][r], want[q]["summaries"][r]
+                for f in ("events_processed", "final_time_ns", "order_hash", "heap_left", "n_sink_samples", "n_service_samples"):
+                    assert int(g[f]) == int(w[f]), (what, q, int(r), f, int(g[f]), int(w[f]))
+                assert int(g["status"]) & ~A.HS_ST_LINK_TIE == int(w["status"]), (what, q, int(r))
+                assert outs[q]["entity_stats"][r].tobytes() == want[q]["entity_stats"][r].tobytes(), (what, q, int(r))
+                assert outs[q]["records"][r].tobytes() == want[q]["records"][r].tobytes(), (what, q, int(r))
+                if want[q].get("sketches") is not None:
+                    assert outs[q]["sketches"][r].tobytes() == want[q]["sketches"][r].tobytes(), (what, q, int(r))
+    assert compared > 300 and flagged < 120, (compared, flagged)

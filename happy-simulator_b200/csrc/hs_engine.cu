@@ -802,7 +802,16 @@ int hs_read_outputs(hs_engine *E, const hs_outputs *out)
     if (out->histograms && E->hist_on) CUDA_TRY(cudaMemcpyAsync(out->histograms, E->d_hist.p, n * HS_HISTOGRAM_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, E->stream));
     if (out->service_samples && p.service_cap) CUDA_TRY(cudaMemcpyAsync(out->service_samples, E->d_svc.p, n * p.service_cap * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
     if (out->sketches && E->sk_total) CUDA_TRY(cudaMemcpyAsync(out->sketches, E->d_sketch.p, n * E->sk_total, cudaMemcpyDeviceToHost, E->stream));
+    /* linked partitions: what the last barrier delivered is scheduled on the receiver (Simulation.schedule = heap push,
+     * coordinator.py:222) whether or not another window follows -- those events wait in the inbox here and are part of
+     * the pending-event count like everything else in the reference's heap */
+    std::vector<uint32_t> inbox_n;
+    if (out->summaries && E->inbox_cap && E->link_replicas == n) {
+        inbox_n.resize(n);
+        CUDA_TRY(cudaMemcpyAsync(inbox_n.data(), E->d_inbox_n.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, E->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(E->stream));
+    for (size_t r = 0; r < inbox_n.size(); ++r) out->summaries[r].heap_left += (int32_t)inbox_n[r];
     return HS_OK;
 }
 

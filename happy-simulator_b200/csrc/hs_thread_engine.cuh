@@ -4,7 +4,7 @@
  * The warp engine gives a replica a whole warp but its handlers are scalar control flow, so 31
  * lanes idle; here every lane runs its own replica.  A replica's state cannot live in registers
  * (a 64-server farm is ~10 KB), so it stays in a contiguous per-replica block in HBM
- *     [ header 128 B | entity state n x 96 B | heap keys S x 16 B | payloads S x 32 B |
+ *     [ header 128 B | entities n x 128 B (state 96 B + own payload 32 B) | heap keys S x 16 B | payloads S x 32 B |
  *       free-slot stack S x 2 B | now-tier overflow 24 x 48 B ]
  * that only this thread touches (nothing to stage or synchronise; a paused window resumes from the
  * same bytes).  Pending events are kept in two tiers that together order exactly like the
@@ -51,12 +51,19 @@
 struct __align__(16) hs_tkey { int64_t time; uint64_t k2; };                 /* k2 = sort_index << 16 | slot */
 struct __align__(16) hs_tpay { int64_t created; uint64_t aux; uint32_t m0; int32_t key; uint32_t hook, pad; };
 
+/* One 128-byte line per entity: its state and, next to it, the payload of ITS pending future event (entity-owned slots,
+ * hs_warp_model.fixed_slots: a source's next tick, a concurrency-1 server's continuation).  A pop then finds the payload
+ * and the state of the entity it is for in the same line -- one miss instead of two or three (a 96-byte state at a
+ * 96-byte stride straddles two lines half of the time) -- and these misses are what the kernel waits for. */
+struct __align__(16) hs_tent { hs_went w; hs_tpay pay; };
+static_assert(sizeof(hs_tent) == 128, "one line per entity");
+
 struct hs_thread_layout { uint32_t keys, pay, free_, spill, total; };
 
 __host__ __device__ inline hs_thread_layout hs_thread_offsets(uint32_t ne, uint32_t S)
 {
     hs_thread_layout L;
-    L.keys = ((uint32_t)sizeof(hs_warp_hdr) + ne * (uint32_t)sizeof(hs_went) + 127u) / 128u * 128u;
+    L.keys = (uint32_t)sizeof(hs_warp_hdr) + ne * (uint32_t)sizeof(hs_tent);      /* the header is one line too */
     L.pay = L.keys + (HS_T_LEAD + (S + HS_T_ARITY) * 16u + 127u) / 128u * 128u;   /* the children ARITY k + 1 .. ARITY k + ARITY share one aligned line */
     L.free_ = L.pay + S * 32u;
     L.spill = L.free_ + (S * 2u + 15u) / 16u * 16u;
@@ -65,6 +72,13 @@ __host__ __device__ inline hs_thread_layout hs_thread_offsets(uint32_t ne, uint3
 }
 
 #define HS_T_LT(T1, I1, T2, I2) ((T1) < (T2) || ((T1) == (T2) && (I1) < (I2)))
+
+/* experiment switches (HS_B200_DEFS="-DHS_T_...=0" builds the A/B variants; the defaults are the measured winners) */
+#ifndef HS_T_PREFETCH
+#define HS_T_PREFETCH 1             /* the next chain's payload / entity lines are requested while the current chain runs */
+#endif
+
+__device__ __forceinline__ void hs_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 
 template <int FLAGS>
@@ -87,9 +101,10 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
 
     unsigned char *blk = blocks + (size_t)r * M.block_bytes;
     hs_warp_hdr *Hg = (hs_warp_hdr *)blk;
-    hs_went *E = (hs_went *)(blk + sizeof(hs_warp_hdr));
+    hs_tent *E = (hs_tent *)(blk + sizeof(hs_warp_hdr));
     hs_tkey *K = (hs_tkey *)(blk + L.keys + HS_T_LEAD);
     hs_tpay *PAY = (hs_tpay *)(blk + L.pay);
+    auto pay_at = [&](const uint32_t slot) -> hs_tpay * { return M.fixed_slots ? &E[slot].pay : &PAY[slot]; };
     uint16_t *FREE = (uint16_t *)(blk + L.free_);
     hs_wnow *Ng = (hs_wnow *)(blk + L.spill);
 
@@ -170,7 +185,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         const uint32_t cell = M.n_cells ? (gidx / P.replicas_per_cell) % M.n_cells : 0u;
         for (uint32_t i = 0; i < ne; ++i) {
             const hs_entity_desc d = ENTS[i];
-            hs_went *e = &E[i];
+            hs_went *e = &E[i].w;
             e->d0 = M.n_cells ? M.cell_d0[(size_t)cell * ne + i] : d.d0;
             e->i0 = M.n_cells ? M.cell_i0[(size_t)cell * ne + i] : d.i0;
             if (d.kind == HS_ENT_CACHE_SERVER) e->i0 = 0x7fffffff;          /* Entity.has_capacity() is True: no limit */
@@ -187,7 +202,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         uint32_t hn = 0;
         for (uint32_t i = 0; i < ne; ++i) {
             if (ENTS[i].kind != HS_ENT_SOURCE) continue;
-            hs_went *e = &E[i];
+            hs_went *e = &E[i].w;
             double target = 1.0;
             if (e->i0 == HS_ARR_POISSON && P.trace_arr) {
                 if (hdr.np_cursor >= P.n_trace_arr) { hdr.status |= HS_ST_TRACE_EXHAUSTED; break; }
@@ -204,7 +219,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (hn >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; break; }
             const uint32_t slot = M.fixed_slots ? i : FREE[S - hn - 1];
             hs_tpay pp; pp.created = 0; pp.aux = 0ull; pp.m0 = HS_EV_SOURCE_TICK | (i << 8); pp.key = -1; pp.hook = 0u; pp.pad = 0u;
-            PAY[slot] = pp;
+            *pay_at(slot) = pp;
             hs_tkey nk; nk.time = first; nk.k2 = (boot++ << 16) | slot;
             uint32_t k = hn++;
             while (k > 0) { const uint32_t p = (k - 1) >> HS_T_SHIFT; const hs_tkey q = kload(p);
@@ -285,11 +300,14 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         }
     };
 
-    /* insertion of a future event (SourceEvent or ProcessContinuation) into the 4-ary key heap */
+    /* insertion of a future event (SourceEvent or ProcessContinuation) into the 4-ary key heap.  (Measured and dropped,
+     * round 2: a "lazy" pop that leaves a hole at the root for the chain's first insertion to fill -- heapreplace, one
+     * walk instead of two.  It moves the sift-down out of the heap phase, where all lanes of a warp run it together, into
+     * the chains, where the tick lanes and the completion lanes each run their own: configs[2] 7.6e9 -> 4.7e9 events/s.) */
     auto heap_insert = [&](hs_tkey fkey, const hs_tpay &fpay) {
         if (heap_n >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; return; }
         const uint32_t slot = M.fixed_slots ? (fpay.m0 >> 8) : FREE[S - heap_n - 1];   /* entity-owned slot, or the stack's top */
-        PAY[slot] = fpay;
+        *pay_at(slot) = fpay;
         fkey.k2 |= slot;
         uint32_t k = heap_n++;
         while (k > 0) {
@@ -315,7 +333,11 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
      * per event, no now-tier traffic, no per-event dispatch.  Every condition is tested BEFORE anything is
      * changed (draws are pure functions of their index); a chain that does not qualify -- a tie, another topology
      * (tandem, sketch or probe targets), a stop_after source, a full ring, traces, the run / window end, the event
-     * limit -- goes through the generic one-event path below, which is the oracle's.  Returns true if it ran. */
+     * limit -- goes through the generic one-event path below, which is the oracle's.  Returns true if it ran.
+     * (Measured and dropped, round 2: ONE instruction stream for the tick and the completion lanes where their work is
+     * the same -- server-state load, service draw, continuation insert, server-state store -- with the per-kind parts
+     * in between.  Fewer warp instructions, but the tick chain's arrival draw no longer overlaps the load of the
+     * server's state, and exposed load latency is what bounds this kernel: configs[2] 7.8e9 -> 6.9e9 events/s.) */
     auto emit = [&](const int64_t now, const uint64_t idx, const int kind, const uint32_t ent) {
         if (FLAGS & HS_WF_HASH) h_hash = hs_hash_step(h_hash, now, hs_record_word1(idx, (uint32_t)kind, ent));
         if ((FLAGS & HS_WF_REC) && rec) {
@@ -328,12 +350,12 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     /* entity state as six 16-byte vectors: one burst of loads into registers, the dynamic part (vectors 2..5) stored back */
     union went_u { hs_went w; uint4 q[6]; };
     auto went_load = [&](const int i, went_u &x) {
-        const uint4 *g = (const uint4 *)&E[i];
+        const uint4 *g = (const uint4 *)&E[i].w;
 #pragma unroll
         for (int k = 0; k < 6; ++k) x.q[k] = g[k];
     };
     auto went_store = [&](const int i, const went_u &x) {
-        uint4 *g = (uint4 *)&E[i];
+        uint4 *g = (uint4 *)&E[i].w;
 #pragma unroll
         for (int k = 2; k < 6; ++k) g[k] = x.q[k];
     };
@@ -341,7 +363,8 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     auto fused_chain = [&]() -> bool {
         const int64_t now = ev.time;
         const int k0 = (int)(ev.m0 & 0xffu);
-        if (!fuse_on || now_n != 0 || !(top_t > now) || now > P.end_ns || h_processed + 10 > P.max_events) return false;
+        if (!fuse_on || now_n != 0 || now > P.end_ns || h_processed + 10 > P.max_events) return false;
+        if (!(top_t > now)) return false;                       /* the heap's new root must be strictly later */
         const uint32_t ent = ev.m0 >> 8;
         if (k0 == HS_EV_SOURCE_TICK) {
             const hs_entity_desc ds = ENTS[ent];
@@ -355,11 +378,10 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             int32_t key = -1;
             if (ds.i1 > 0) key = hs_routing_key(hs_uniform(seed, rid, HS_STREAM_ROUTING | (ent << 8), key_draws), ds.i1,
                                                 ds.i2 > 0 ? M.key_cdf + (ds.i2 - 1) : nullptr);
-            int lb = -1, be = t1; uint64_t rr = 0; bool use_rr = false;
+            int lb = -1, be = t1, slot = 0; uint64_t rr = 0; bool use_rr = false;
             if (d1.kind == HS_ENT_LB) {
                 if (d1.i2 <= 0) return false;
                 lb = t1;
-                int slot;
                 if (d1.i0 == HS_LB_KEY_TABLE && key >= 0) slot = M.key_table[key];
                 else { rr = Xl->u.lb.rr_index; slot = (int)(rr % (uint64_t)d1.i2); use_rr = true; }
                 be = BACKENDS[d1.i1 + slot];
@@ -393,6 +415,14 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 if (resume_t <= now) return false;                   /* a zero-length service resumes at this very nanosecond */
             }
             /* ---- nothing can stop the chain any more: run it ---------------------------------------------------- */
+            if (HS_T_PREFETCH && use_rr) {
+                /* round robin: the backend of the NEXT request is the next slot, so its state -- the one load of the next
+                 * tick chain that depends on another load -- is requested now.  (A key-table balancer's next backend is
+                 * known too, the routing key being a pure function of its draw index, but the extra Philox evaluation
+                 * cost more than the request saved: configs[3] 2.16e9 -> 2.02e9 events/s at 4 096 replicas.) */
+                const int s2 = slot + 1;
+                hs_prefetch(&E[BACKENDS[d1.i1 + (s2 == d1.i2 ? 0 : s2)]]);
+            }
             h_now = now;
             const uint64_t idxP = ctr, idxT = ctr + 1; ctr += 2;
             emit(now, ev.idx, HS_EV_SOURCE_TICK, ent);
@@ -458,6 +488,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             int tkind = 0;
             if (tgt >= 0) { tkind = ENTS[tgt].kind; if (tkind != HS_ENT_SINK && tkind != HS_ENT_COUNTER) return false; }
             went_u xv; went_load((int)ent, xv); hs_went *Xv = &xv.w;
+            if (HS_T_PREFETCH && tgt >= 0) hs_prefetch(&E[tgt]);     /* the sink's line: wanted after the draw */
             const uint32_t q_head = Xv->u.srv.q_head, q_len = Xv->u.srv.q_len;
             const int32_t active = Xv->u.srv.active > 0 ? Xv->u.srv.active - 1 : 0;
             const bool poll = (ev.hook & 0x80000000u) && active < Xv->i0;
@@ -466,15 +497,16 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             double svc_s = 0.0; int64_t resume_t = 0;
             hs_wring_entry q; q.created = 0; q.idx = 0; q.key = -1;
             if (start) {
+                /* the waiting request first: its load (a miss, as a rule) is in flight while the service time is drawn */
+                const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1) & 0xffffffu;
+                const hs_wring_entry *rg = ring0 + (size_t)srv_idx * P.ring;
+                q = rg[(dv.i1 == HS_Q_LIFO ? q_head + q_len - 1 : q_head) & ring_mask];
                 const int64_t dur = (dv.i2 == HS_SVC_EXPONENTIAL)
                     ? hs_seconds_to_ns(HS_DIV(hs_exp1(hs_uniform(seed, rid, HS_STREAM_SERVICE | (ent << 8), svc_draws)), Xv->lambda))
                     : hs_seconds_to_ns(Xv->d0);
                 svc_s = hs_ns_to_seconds(dur);
                 resume_t = hs_resume_ns(now, svc_s);
                 if (resume_t <= now) return false;
-                const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1) & 0xffffffu;
-                const hs_wring_entry *rg = ring0 + (size_t)srv_idx * P.ring;
-                q = rg[(dv.i1 == HS_Q_LIFO ? q_head + q_len - 1 : q_head) & ring_mask];
             }
             h_now = now;
             emit(now, ev.idx, HS_EV_CONTINUATION, ent);                /* generator resumes, server.py:255-273 */
@@ -534,7 +566,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
      * another partition is constructed (its sort index is spent) but never scheduled here: it goes, with the current
      * time, to this replica's outbox, which hs_coordinator_exchange drains at the window barrier */
     auto outbox_send = [&](const uint64_t idx, const int64_t created, const int32_t key, const uint32_t rem, const int64_t now) {
-        E[rem].u.snk.received++;
+        E[rem].w.u.snk.received++;
         const uint32_t n = O.outbox_n[r];
         if (n >= M.outbox_cap) { hdr.status |= HS_ST_LINK_OVERFLOW; return; }
         hs_xevent x; x.time_ns = now; x.sort_index = idx; x.created_ns = created; x.aux = 0ull; x.key = key; x.ent = (int32_t)rem;
@@ -556,7 +588,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         union { hs_entity_desc d; uint4 q[3]; } du;
         { const uint4 *g = (const uint4 *)&ENTS[ent]; du.q[0] = g[0]; du.q[1] = g[1]; du.q[2] = g[2]; }
         union { hs_went w; uint4 q[6]; } xu;
-        { const uint4 *g = (const uint4 *)&E[ent];
+        { const uint4 *g = (const uint4 *)&E[ent].w;
 #pragma unroll
           for (int i = 0; i < 6; ++i) xu.q[i] = g[i]; }
         hs_went *X = &xu.w;
@@ -593,13 +625,15 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
 #define HS_W_REQ_KIND(TGT) HS_EV_REQ_ANY
 #define HS_W_D (du.d)
 #define HS_W_SRVIDX srv_idx
+#define HS_W_ENT(I) (&E[(I)].w)
 #include "hs_handlers.inc"
+#undef HS_W_ENT
 #undef HS_W_SRVIDX
 #undef HS_W_D
 #undef HS_W_REQ_KIND
 #undef HS_W_PUSH
         /* write the entity's dynamic state back (the union; d0 / lambda / i0 never change) */
-        { uint4 *g = (uint4 *)&E[ent];
+        { uint4 *g = (uint4 *)&E[ent].w;
 #pragma unroll
           for (int i = 2; i < 6; ++i) g[i] = xu.q[i]; }
         if (have_fut) heap_insert(fkey, fpay);
@@ -625,7 +659,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         if (need_heap) {
             const int64_t now0 = h_now;
             const uint32_t slot = (uint32_t)(top_k & 0xffffu);
-            const hs_tpay pp = PAY[slot];
+            const hs_tpay pp = *pay_at(slot);
             ev.time = top_t; ev.idx = top_k >> 16; ev.created = pp.created; ev.aux = pp.aux;
             ev.m0 = pp.m0; ev.key = pp.key; ev.hook = pp.hook; ev.pad = (FLAGS & HS_WF_LINKED) ? pp.pad : 0u;
             if ((FLAGS & HS_WF_LINKED) && M.inbox_cap) {         /* a delivered event that ties on (time, sort index): see HS_ST_LINK_TIE */
@@ -656,12 +690,19 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 }
                 kstore(k, last);
                 if (k == 0) { top_t = last.time; top_k = last.k2; }
+                if (HS_T_PREFETCH) {
+                    /* the new root is (unless this chain schedules something sooner) the NEXT pop: its payload and, with
+                     * entity-owned slots, its entity's state are requested now, a whole chain ahead of their use */
+                    const uint32_t ns = (uint32_t)(top_k & 0xffffu);
+                    hs_prefetch(M.fixed_slots ? (const void *)&E[ns] : (const void *)&PAY[ns]);   /* entity-owned slot: ONE line holds both */
+                }
             }
             if (heap_n == 0) { top_t = HS_W_EMPTY; top_k = ~0ull; }
             h_fel--;
             need_heap = false;
-            if (ev.time < now0) next_event();            /* "time travel": skipped (simulation.py:479-489) */
-            else if (fused_chain()) next_event();        /* the whole same-timestamp chain ran as straight-line code */
+            int chain_done = 0;
+            if (ev.time < now0) chain_done = 1;          /* "time travel": skipped (simulation.py:479-489) */
+            else if (fused_chain()) chain_done = 1;      /* the whole same-timestamp chain ran as straight-line code */
             else { int k = (int)(ev.m0 & 0xffu);
                    if (k == (int)HS_EV_REQ_ANY) {
                        const int ek = ENTS[ev.m0 >> 8].kind;
@@ -670,6 +711,9 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                            ek == HS_ENT_SKETCH ? HS_EV_REQ_SKETCH : HS_EV_REQ_LB;
                    }
                    ev_kind = k; }
+            asm volatile("" : "+r"(chain_done));         /* ONE copy of next_event() for the tick and the completion lanes, after they
+                                                          * have reconverged (the compiler would otherwise thread it into both chains) */
+            if (chain_done) next_event();
         }
         /* ---- handler phases, in chain order: ONE copy of the handlers (a copy per kind was three times slower when a
          * warp holds a single replica: 170 KB of code); `kind` is warp-uniform in every pass, so the switch inside
@@ -710,7 +754,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
     }
     if (O.stats) {
         for (uint32_t i = 0; i < ne; ++i) {
-            const hs_went *e = &E[i];
+            const hs_went *e = &E[i].w;
             hs_entity_stats a; a.c0 = a.c1 = a.c2 = a.c3 = 0; a.f0 = a.f1 = a.f2 = a.f3 = 0.0;
             switch (ENTS[i].kind) {
             case HS_ENT_SOURCE: a.c0 = e->u.src.generated; a.c1 = e->u.src.provider; break;

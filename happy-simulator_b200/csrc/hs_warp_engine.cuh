@@ -381,7 +381,9 @@ hs_warp_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ block
         }                                                                                                \
     } while (0)
 #define HS_W_D (ENTS[ent])
+#define HS_W_ENT(I) (&E[(I)])
 #include "hs_handlers.inc"
+#undef HS_W_ENT
 #undef HS_W_D
 #undef HS_W_PUSH
                 }

@@ -250,7 +250,7 @@ typedef struct hs_replica_summary {
     uint64_t next_sort_index;  /* value of the per-heap creation counter at the end            */
     int64_t n_sink_samples;    /* Sink samples produced (all sinks); ring position = n % cap   */
     int64_t n_service_samples; /* service starts (Server._service_times appends)               */
-    int32_t heap_left;         /* events still pending                                         */
+    int32_t heap_left;         /* events still pending (linked partitions: incl. delivered, not yet taken) */
     uint32_t status;           /* HS_ST_* bits, 0 = clean                                      */
 } hs_replica_summary;          /* 56 bytes */
 

@@ -137,7 +137,8 @@ def test_random_linked_models_on_the_device():
         caps = [dict(record_cap=512, sample_cap=64, service_cap=64) for _ in range(nP)]
         run = LinkedRun(lm)
         try:
-            outs, (delivered, lost, over) = run.run(seed=1000 + seed, end_ns=end_ns, n_replicas=n, caps=caps)
+            # queue_ring: the reference's queues are unbounded; some of the random models run overloaded for a while
+            outs, (delivered, lost, over) = run.run(seed=1000 + seed, end_ns=end_ns, n_replicas=n, caps=caps, queue_ring=2048)
         finally:
             run.close()
         ps = [O.make_params(seed=1000 + seed, end_ns=end_ns, n_replicas=n, rid_base=q, rid_stride=nP + 1, **caps[q]) for q in range(nP)]

@@ -443,8 +443,20 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
         const size_t dyn_smem = (size_t)R.heap_top * (HS_THREAD_BLOCK / R.lane_stride) * 16;
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
 #define HS_LAUNCH_THREAD(F) case F: hs_thread_kernel<F><<<tblocks, HS_THREAD_BLOCK, dyn_smem, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;
+#define HS_LAUNCH_THREAD_WIDE(F) case F: hs_thread_kernel_wide<F><<<tblocks, HS_THREAD_BLOCK, dyn_smem, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;
         const bool linked_model = E->outbox_cap || E->inbox_cap || R.linked;
         if (linked_model && (fl & HS_WF_PROFILE)) return fail(HS_ERR_INVALID, "linked partitions with non-constant rate profiles are not compiled in");
+        /* small launches (every block resident at 4 blocks per SM, no shared-memory heap top, not linked): the spill-free
+         * instantiation, see hs_thread_kernel_wide; HS_THREAD_WIDE=0/1 overrides (experiments) */
+        bool wide = !R.heap_top && !linked_model && tblocks <= E->sm_count * HS_T_WIDE_BLOCKS;
+        if (const char *ev = getenv("HS_THREAD_WIDE")) wide = atoi(ev) != 0 && !R.heap_top && !linked_model;
+        if (wide) {
+            switch (fl) {
+            HS_LAUNCH_THREAD_WIDE(0) HS_LAUNCH_THREAD_WIDE(1) HS_LAUNCH_THREAD_WIDE(2) HS_LAUNCH_THREAD_WIDE(3)
+            HS_LAUNCH_THREAD_WIDE(4) HS_LAUNCH_THREAD_WIDE(5) HS_LAUNCH_THREAD_WIDE(6) HS_LAUNCH_THREAD_WIDE(7)
+            default: return fail(HS_ERR_STATE, "no wide thread kernel for flags %d", fl);
+            }
+        } else
         switch (fl | (R.heap_top ? HS_WF_HEAPTOP : 0) | (linked_model ? HS_WF_LINKED : 0)) {
         HS_LAUNCH_THREAD(0) HS_LAUNCH_THREAD(1) HS_LAUNCH_THREAD(2) HS_LAUNCH_THREAD(3)
         HS_LAUNCH_THREAD(4) HS_LAUNCH_THREAD(5) HS_LAUNCH_THREAD(6) HS_LAUNCH_THREAD(7)
@@ -455,6 +467,7 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
         default: return fail(HS_ERR_STATE, "no thread kernel for flags %d", fl);
         }
 #undef HS_LAUNCH_THREAD
+#undef HS_LAUNCH_THREAD_WIDE
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
         E->launches += 1;

@@ -78,13 +78,17 @@ __host__ __device__ inline hs_thread_layout hs_thread_offsets(uint32_t ne, uint3
 #define HS_T_PREFETCH 1             /* the next chain's payload / entity lines are requested while the current chain runs */
 #endif
 
+#ifndef HS_T_TAILINS
+#define HS_T_TAILINS 1              /* fused chains: heap insertions in ONE place, after tick and completion lanes reconverged */
+#endif
+
 __device__ __forceinline__ void hs_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 
 template <int FLAGS>
-__global__ void __launch_bounds__(HS_THREAD_BLOCK, HS_T_MINBLOCKS)
-hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blocks,
-                 hs_wring_entry *__restrict__ rings, hs_warp_out O)
+__device__ __forceinline__ void
+hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__restrict__ blocks,
+               hs_wring_entry *__restrict__ rings, const hs_warp_out &O)
 {
     __shared__ uint4 Ns[HS_T_KS * 3 * HS_THREAD_BLOCK];
     extern __shared__ uint4 Ktop[];                      /* the heap's top levels: [key index][replica column of the block] */
@@ -304,11 +308,14 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
      * round 2: a "lazy" pop that leaves a hole at the root for the chain's first insertion to fill -- heapreplace, one
      * walk instead of two.  It moves the sift-down out of the heap phase, where all lanes of a warp run it together, into
      * the chains, where the tick lanes and the completion lanes each run their own: configs[2] 7.6e9 -> 4.7e9 events/s.) */
-    auto heap_insert = [&](hs_tkey fkey, const hs_tpay &fpay) {
-        if (heap_n >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; return; }
-        const uint32_t slot = M.fixed_slots ? (fpay.m0 >> 8) : FREE[S - heap_n - 1];   /* entity-owned slot, or the stack's top */
+    auto heap_slot_store = [&](hs_tkey &fkey, const hs_tpay &fpay, const uint32_t pending) -> bool {   /* the payload goes to its slot at once */
+        if (heap_n + pending >= S) { hdr.status |= HS_ST_FEL_OVERFLOW; return false; }
+        const uint32_t slot = M.fixed_slots ? (fpay.m0 >> 8) : FREE[S - (heap_n + pending) - 1];   /* entity-owned slot, or the stack's top */
         *pay_at(slot) = fpay;
         fkey.k2 |= slot;
+        return true;
+    };
+    auto heap_push_key = [&](const hs_tkey fkey) {                       /* the key sifts up */
         uint32_t k = heap_n++;
         while (k > 0) {
             const uint32_t p = (k - 1) >> HS_T_SHIFT;
@@ -320,6 +327,20 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
         kstore(k, fkey);
         if (k == 0) { top_t = fkey.time; top_k = fkey.k2; }
         h_fel++;
+    };
+    auto heap_insert = [&](hs_tkey fkey, const hs_tpay &fpay) {
+        if (heap_slot_store(fkey, fpay, 0u)) heap_push_key(fkey);
+    };
+    /* The fused chains do not sift their (at most two) new keys up themselves: they park them here, and the heap phase
+     * inserts them after the tick lanes and the completion lanes of the warp have come together again -- one copy of the
+     * sift-up loop, run by all lanes at once, instead of three copies inside the divergent chains. */
+    hs_tkey pk0, pk1; pk0.time = pk1.time = 0; pk0.k2 = pk1.k2 = 0ull;
+    int n_pk = 0;
+    auto chain_insert = [&](hs_tkey fkey, const hs_tpay &fpay) {
+        if (!HS_T_TAILINS) { heap_insert(fkey, fpay); return; }
+        if (!heap_slot_store(fkey, fpay, (uint32_t)n_pk)) return;
+        if (n_pk == 0) pk0 = fkey; else pk1 = fkey;
+        n_pk++;
     };
 
     /* ---- fused same-timestamp chains -----------------------------------------------------------------------------
@@ -337,7 +358,9 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
      * (Measured and dropped, round 2: ONE instruction stream for the tick and the completion lanes where their work is
      * the same -- server-state load, service draw, continuation insert, server-state store -- with the per-kind parts
      * in between.  Fewer warp instructions, but the tick chain's arrival draw no longer overlaps the load of the
-     * server's state, and exposed load latency is what bounds this kernel: configs[2] 7.8e9 -> 6.9e9 events/s.) */
+     * server's state, and exposed load latency is what bounds this kernel: configs[2] 7.8e9 -> 6.9e9 events/s.
+     * Also dropped: keeping the second uniform of a Philox block in the entity's spare bytes for the stream's next draw
+     * (half of the Philox evaluations) -- the extra live state spills at 128 registers: 8.3e9 -> 7.6e9.) */
     auto emit = [&](const int64_t now, const uint64_t idx, const int kind, const uint32_t ent) {
         if (FLAGS & HS_WF_HASH) h_hash = hs_hash_step(h_hash, now, hs_record_word1(idx, (uint32_t)kind, ent));
         if ((FLAGS & HS_WF_REC) && rec) {
@@ -431,7 +454,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             if (Xs->i0 == HS_ARR_POISSON) Xs->u.src.arr_draws = arr_draws + 1;
             { hs_tkey fk; fk.time = nt; fk.k2 = idxT << 16;
               hs_tpay fp; fp.created = 0; fp.aux = 0ull; fp.m0 = (uint32_t)HS_EV_SOURCE_TICK | (ent << 8); fp.key = -1; fp.hook = 0u; fp.pad = 0u;
-              heap_insert(fk, fp); }
+              chain_insert(fk, fp); }
             uint64_t idxE = idxP;
             if (lb >= 0) {                                           /* LoadBalancer._forward_request */
                 emit(now, idxP, HS_EV_REQ_LB, (uint32_t)lb);
@@ -468,7 +491,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                 hs_tkey fk; fk.time = resume_t; fk.k2 = idxC << 16;
                 hs_tpay fp; fp.created = now; fp.aux = (uint64_t)__double_as_longlong(svc_s);
                 fp.m0 = (uint32_t)HS_EV_CONTINUATION | ((uint32_t)be << 8); fp.key = key; fp.hook = 0x80000000u; fp.pad = 0u;
-                heap_insert(fk, fp);
+                chain_insert(fk, fp);
             } else if (!drop) {
                 const uint32_t srv_idx = (uint32_t)__double_as_longlong(dv.d1) & 0xffffffu;
                 hs_wring_entry *rg = ring0 + (size_t)srv_idx * P.ring;
@@ -552,7 +575,7 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                     hs_tkey fk; fk.time = resume_t; fk.k2 = idxC << 16;
                     hs_tpay fp; fp.created = q.created; fp.aux = (uint64_t)__double_as_longlong(svc_s);
                     fp.m0 = (uint32_t)HS_EV_CONTINUATION | (ent << 8); fp.key = (int32_t)q.key; fp.hook = 0x80000000u; fp.pad = 0u;
-                    heap_insert(fk, fp);
+                    chain_insert(fk, fp);
                 }
             }
             Xv->u.srv.active = act;
@@ -677,8 +700,17 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                     /* all children at once (one aligned line; the key array has ARITY spare entries, so positions
                      * past the heap's end are readable -- their stale contents are masked out by index) */
                     hs_tkey ch[HS_T_ARITY];
+                    if ((FLAGS & HS_WF_HEAPTOP) && c < TOP) {           /* TOP is whole levels: c + j < TOP for all j or for none */
+                        const uint4 *b = &Ktop[c * rpb + (uint32_t)tid];
 #pragma unroll
-                    for (uint32_t j = 0; j < HS_T_ARITY; ++j) ch[j] = kload(c + j);   /* c + j < TOP for all j or for none: whole levels */
+                        for (uint32_t j = 0; j < HS_T_ARITY; ++j) {
+                            const uint4 q = b[j * rpb];
+                            ch[j].time = (int64_t)((uint64_t)q.x | ((uint64_t)q.y << 32)); ch[j].k2 = (uint64_t)q.z | ((uint64_t)q.w << 32);
+                        }
+                    } else {
+#pragma unroll
+                        for (uint32_t j = 0; j < HS_T_ARITY; ++j) ch[j] = K[c + j];
+                    }
                     hs_tkey best = ch[0]; uint32_t bc = c;
 #pragma unroll
                     for (uint32_t j = 1; j < HS_T_ARITY; ++j)
@@ -711,8 +743,13 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
                            ek == HS_ENT_SKETCH ? HS_EV_REQ_SKETCH : HS_EV_REQ_LB;
                    }
                    ev_kind = k; }
-            asm volatile("" : "+r"(chain_done));         /* ONE copy of next_event() for the tick and the completion lanes, after they
-                                                          * have reconverged (the compiler would otherwise thread it into both chains) */
+            asm volatile("" : "+r"(chain_done), "+r"(n_pk));   /* ONE copy of what follows for the tick and the completion lanes, after
+                                                                 * they have reconverged (the compiler would otherwise thread it into both chains) */
+            if (HS_T_TAILINS) {
+#pragma unroll 1
+                for (int i = 0; i < n_pk; ++i) heap_push_key(i == 0 ? pk0 : pk1);
+                n_pk = 0;
+            }
             if (chain_done) next_event();
         }
         /* ---- handler phases, in chain order: ONE copy of the handlers (a copy per kind was three times slower when a
@@ -774,6 +811,29 @@ hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blo
             O.stats[(size_t)r * ne + i] = a;
         }
     }
+}
+
+/* Two entry points around the one body.  hs_thread_kernel: 128 registers per thread, 8 blocks of 64 threads per SM -- the
+ * register file holds 16 warps per SM, which is what an ensemble of thousands of replicas needs to hide its loads; ptxas
+ * spills ~130 bytes per thread to get there.  hs_thread_kernel_wide: the same code with the registers it asks for (~208,
+ * no spills) at 4 blocks per SM, for launches whose blocks all fit at that occupancy (small ensembles, one replica per
+ * warp): every spill reload sits on the one dependent-instruction chain a warp has there.  configs[3] at one GPU's 1 024
+ * replicas: 1.125e9 -> 1.25e9 events/s; at 16 384 replicas of configs[2] the wide form would lose a quarter (second wave). */
+template <int FLAGS>
+__global__ void __launch_bounds__(HS_THREAD_BLOCK, HS_T_MINBLOCKS)
+hs_thread_kernel(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blocks,
+                 hs_wring_entry *__restrict__ rings, hs_warp_out O)
+{
+    hs_thread_body<FLAGS>(M, P, blocks, rings, O);
+}
+
+#define HS_T_WIDE_BLOCKS 4
+template <int FLAGS>
+__global__ void __launch_bounds__(HS_THREAD_BLOCK, HS_T_WIDE_BLOCKS)
+hs_thread_kernel_wide(hs_warp_model M, hs_warp_run P, unsigned char *__restrict__ blocks,
+                      hs_wring_entry *__restrict__ rings, hs_warp_out O)
+{
+    hs_thread_body<FLAGS>(M, P, blocks, rings, O);
 }
 
 #endif /* HS_THREAD_ENGINE_CUH */

@@ -482,7 +482,7 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
                 emit(now, idxD, HS_EV_DELIVER, (uint32_t)be);
                 emit(now, idxE, HS_EV_REQ_WORKER, (uint32_t)be);     /* the payload keeps its own index */
                 ctr++;                                               /* inline ProcessContinuation */
-                if (dv.i1 != HS_Q_LIFO) Xv->u.srv.q_head = q_head + 1;
+                Xv->u.srv.q_head = 0;                                /* the queue is empty again: it restarts at slot 0 (see POLL in hs_handlers.inc) */
                 Xv->u.srv.active = active + 1;
                 if (dv.i2 == HS_SVC_EXPONENTIAL) Xv->u.srv.svc_draws = svc_draws + 1;
                 if ((FLAGS & HS_WF_REC) && svc_out) { svc_out[hdr.svc_pos] = svc_s; hdr.svc_pos = (hdr.svc_pos + 1 == P.service_cap) ? 0u : hdr.svc_pos + 1; }
@@ -565,7 +565,7 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
                     emit(now, idxD, HS_EV_DELIVER, ent);
                     emit(now, q.idx, HS_EV_REQ_WORKER, ent);
                     ctr++;                                             /* inline ProcessContinuation */
-                    if (dv.i1 != HS_Q_LIFO) Xv->u.srv.q_head = q_head + 1;
+                    Xv->u.srv.q_head = (q_len == 1) ? 0u : (dv.i1 != HS_Q_LIFO ? q_head + 1 : q_head);   /* empty: restart at slot 0 */
                     Xv->u.srv.q_len = q_len - 1;
                     act = active + 1;
                     if (dv.i2 == HS_SVC_EXPONENTIAL) Xv->u.srv.svc_draws = svc_draws + 1;

@@ -357,8 +357,10 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
      * limit -- goes through the generic one-event path below, which is the oracle's.  Returns true if it ran.
      * (Measured and dropped, round 2: ONE instruction stream for the tick and the completion lanes where their work is
      * the same -- server-state load, service draw, continuation insert, server-state store -- with the per-kind parts
-     * in between.  Fewer warp instructions, but the tick chain's arrival draw no longer overlaps the load of the
-     * server's state, and exposed load latency is what bounds this kernel: configs[2] 7.8e9 -> 6.9e9 events/s.
+     * in between, in two orders (the arrival draw after the service draw; the arrival draw between the request for the
+     * server's state and its first use).  Fewer warp instructions, but more values live across the shared pieces than 128
+     * registers hold (spill reloads sit on the critical path) and more reconvergence points: configs[2] 7.8e9 -> 6.9e9 and
+     * 9.0e9 -> 6.8e9 events/s.
      * Also dropped: keeping the second uniform of a Philox block in the entity's spare bytes for the stream's next draw
      * (half of the Philox evaluations) -- the extra live state spills at 128 registers: 8.3e9 -> 7.6e9.) */
     auto emit = [&](const int64_t now, const uint64_t idx, const int kind, const uint32_t ent) {
@@ -411,10 +413,8 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
             } else if (d1.kind != HS_ENT_SERVER) return false;
             const hs_entity_desc dv = ENTS[be];
             if (dv.kind != HS_ENT_SERVER) return false;
-            went_u xv; went_load(be, xv); hs_went *Xv = &xv.w;
-            const uint32_t q_head = Xv->u.srv.q_head, q_len = Xv->u.srv.q_len; const int32_t active = Xv->u.srv.active;
-            const int32_t c_lim = Xv->i0;
-            if (q_len >= P.ring) return false;
+            went_u xv; went_load(be, xv); hs_went *Xv = &xv.w;       /* requested here, first looked at after the arrival draw below:
+                                                                      * the load (a miss, as a rule) has ~200 instructions to arrive */
             /* the next SourceEvent (source.py:166-180) */
             double target = 1.0;
             if (Xs->i0 == HS_ARR_POISSON) target = hs_exp1(hs_uniform(seed, rid, HS_STREAM_ARRIVAL | (ent << 8), arr_draws));
@@ -422,6 +422,9 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
             if ((FLAGS & HS_WF_PROFILE) && ds.i3 > 0) nt = hs_next_arrival_profile_ns(&M.profiles[ds.i3 - 1], cur_ns, target);
             else nt = hs_next_arrival_ns(cur_ns, target, Xs->d0);
             if (nt == HS_T_EXHAUSTED || nt <= now) return false;
+            const uint32_t q_head = Xv->u.srv.q_head, q_len = Xv->u.srv.q_len; const int32_t active = Xv->u.srv.active;
+            const int32_t c_lim = Xv->i0;
+            if (q_len >= P.ring) return false;
             const bool was_empty = (q_len == 0);
             const bool drop = (dv.l0 >= 0 && (int64_t)q_len >= dv.l0);
             const bool notify = !drop && was_empty;

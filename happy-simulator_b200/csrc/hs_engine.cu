@@ -429,18 +429,22 @@ static int hs_warp_launch(hs_engine *E, const hs_run_params *p, uint32_t ring, b
         rpw = std::min<uint32_t>(32, std::max<uint32_t>(1, rpw));
         R.lane_stride = 32 / rpw;
         const int tblocks = (int)(((uint64_t)n * R.lane_stride + HS_THREAD_BLOCK - 1) / HS_THREAD_BLOCK);
-        /* heap keys kept in shared memory: as many whole top levels as 16 KB per block hold for the block's replicas
-         * (8 blocks per SM stay resident next to the 12 KB of the now tier); HS_THREAD_HEAPTOP overrides (experiments) */
+        /* shared memory of a block: the now tier (HS_T_KS entries x 48 B per replica column) and, next to it, whole top
+         * levels of the key heap: at most three (1 + 4 + 16 keys) and at most 20 KB per block together.  Shared memory is
+         * carved out of the L1 the replicas' state lives in, and deep levels are read at scattered indices (bank
+         * conflicts): on the 64-server farm at 8 replicas per warp, 5 / 21 / 85 keys per replica in shared memory run at
+         * 8.99e9 / 9.25e9 / 8.71e9 events/s (tools/scan_heaptop.py).  HS_THREAD_HEAPTOP overrides (experiments). */
+        const uint32_t rpb = HS_THREAD_BLOCK / R.lane_stride;
         {
-            const uint32_t rpb = HS_THREAD_BLOCK / R.lane_stride;
-            const uint32_t budget = 16384u / 16u / rpb;          /* keys per replica */
+            const uint32_t budget = std::min<uint32_t>(21u, (20480u / 16u - HS_T_KS * 3u * rpb) / rpb);          /* keys per replica */
             uint32_t top = 0, level = 1, total = 0;
             while (total + level <= budget && total + level <= S) { total += level; level *= HS_T_ARITY; top = total; }
             if (top < 1 + HS_T_ARITY || R.lane_stride == 32) top = 0;       /* one replica per warp: its heap sits in L1 anyway */
             if (const char *ev = getenv("HS_THREAD_HEAPTOP")) top = (uint32_t)std::max(0, atoi(ev));
             R.heap_top = top;
         }
-        const size_t dyn_smem = (size_t)R.heap_top * (HS_THREAD_BLOCK / R.lane_stride) * 16;
+        const size_t dyn_smem = (size_t)(HS_T_KS * 3u + R.heap_top) * rpb * 16;
+        if (dyn_smem > 48u * 1024u) return fail(HS_ERR_INVALID, "thread engine: %zu bytes of shared memory per block (HS_THREAD_HEAPTOP too large)", dyn_smem);
         CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
 #define HS_LAUNCH_THREAD(F) case F: hs_thread_kernel<F><<<tblocks, HS_THREAD_BLOCK, dyn_smem, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;
 #define HS_LAUNCH_THREAD_WIDE(F) case F: hs_thread_kernel_wide<F><<<tblocks, HS_THREAD_BLOCK, dyn_smem, E->stream>>>(M, R, (unsigned char *)E->d_state.p, (hs_wring_entry *)E->d_rings.p, O); break;

@@ -90,8 +90,14 @@ __device__ __forceinline__ void
 hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__restrict__ blocks,
                hs_wring_entry *__restrict__ rings, const hs_warp_out &O)
 {
-    __shared__ uint4 Ns[HS_T_KS * 3 * HS_THREAD_BLOCK];
-    extern __shared__ uint4 Ktop[];                      /* the heap's top levels: [key index][replica column of the block] */
+    /* dynamic shared memory of a block: [ now tier: HS_T_KS x 3 chunks x rpb columns | heap top: P.heap_top keys x rpb columns ],
+     * rpb = replicas (columns) of the block.  The now tier is sized by the columns in use (it was 64 wide whatever the
+     * launch): shared memory is carved out of L1, and L1 is where the replicas' state lives -- configs[3] at one replica per
+     * warp 1.30e9 -> 1.37e9 events/s, configs[2] at 8 per warp 9.0e9 -> 9.25e9 from this alone. */
+    extern __shared__ uint4 hs_t_dyn[];
+    const uint32_t rpb = HS_THREAD_BLOCK / P.lane_stride;            /* replica columns per block */
+    uint4 *const Ns = hs_t_dyn;
+    uint4 *const Ktop = hs_t_dyn + HS_T_KS * 3 * rpb;    /* the heap's top levels: [key index][replica column of the block] */
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid % P.lane_stride) return;                    /* surplus lanes (see above) */
     const int tid = (int)(threadIdx.x / P.lane_stride);  /* this replica's column of the shared now tier */
@@ -118,7 +124,6 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
      * Compiled in (HS_WF_HEAPTOP) for launches with several replicas per warp: measured +5-7 % on the 64-server farm;
      * with one replica per warp the few resident heaps already sit in L1 and the extra addressing costs 10 %. */
     const uint32_t TOP = (FLAGS & HS_WF_HEAPTOP) ? P.heap_top : 0u;
-    const uint32_t rpb = HS_THREAD_BLOCK / P.lane_stride;            /* replica columns per block */
     auto kload = [&](const uint32_t i) -> hs_tkey {
         if ((FLAGS & HS_WF_HEAPTOP) && i < TOP) { const uint4 q = Ktop[i * rpb + (uint32_t)tid]; hs_tkey k;
                        k.time = (int64_t)((uint64_t)q.x | ((uint64_t)q.y << 32)); k.k2 = (uint64_t)q.z | ((uint64_t)q.w << 32); return k; }
@@ -142,9 +147,9 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
     auto now_store = [&](int k, const hs_wnow &v) {
         now_u u; u.e = v;
         if (k < HS_T_KS) {
-            Ns[(k * 3 + 0) * HS_THREAD_BLOCK + tid] = u.q[0];
-            Ns[(k * 3 + 1) * HS_THREAD_BLOCK + tid] = u.q[1];
-            Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid] = u.q[2];
+            Ns[(k * 3 + 0) * rpb + tid] = u.q[0];
+            Ns[(k * 3 + 1) * rpb + tid] = u.q[1];
+            Ns[(k * 3 + 2) * rpb + tid] = u.q[2];
         } else {
             uint4 *g = (uint4 *)&Ng[k]; g[0] = u.q[0]; g[1] = u.q[1]; g[2] = u.q[2];
         }
@@ -152,16 +157,16 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
     auto now_load = [&](int k) -> hs_wnow {
         now_u u;
         if (k < HS_T_KS) {
-            u.q[0] = Ns[(k * 3 + 0) * HS_THREAD_BLOCK + tid];
-            u.q[1] = Ns[(k * 3 + 1) * HS_THREAD_BLOCK + tid];
-            u.q[2] = Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid];
+            u.q[0] = Ns[(k * 3 + 0) * rpb + tid];
+            u.q[1] = Ns[(k * 3 + 1) * rpb + tid];
+            u.q[2] = Ns[(k * 3 + 2) * rpb + tid];
         } else {
             const uint4 *g = (const uint4 *)&Ng[k]; u.q[0] = g[0]; u.q[1] = g[1]; u.q[2] = g[2];
         }
         return u.e;
     };
     auto now_key = [&](int k, int64_t &t, uint64_t &ix) {
-        const uint4 a = (k < HS_T_KS) ? Ns[(k * 3) * HS_THREAD_BLOCK + tid] : *(const uint4 *)&Ng[k];
+        const uint4 a = (k < HS_T_KS) ? Ns[(k * 3) * rpb + tid] : *(const uint4 *)&Ng[k];
         t = (int64_t)((uint64_t)a.x | ((uint64_t)a.y << 32)); ix = (uint64_t)a.z | ((uint64_t)a.w << 32);
     };
 
@@ -178,9 +183,9 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
         }
         for (int k = 0; k < hdr.now_n && k < HS_T_KS; ++k) {
             const uint4 *g = (const uint4 *)&Ng[k];
-            Ns[(k * 3 + 0) * HS_THREAD_BLOCK + tid] = g[0];
-            Ns[(k * 3 + 1) * HS_THREAD_BLOCK + tid] = g[1];
-            Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid] = g[2];
+            Ns[(k * 3 + 0) * rpb + tid] = g[0];
+            Ns[(k * 3 + 1) * rpb + tid] = g[1];
+            Ns[(k * 3 + 2) * rpb + tid] = g[2];
         }
     } else {
         for (uint32_t i = 0; i < L.keys / 16; ++i) ((uint4 *)blk)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -776,9 +781,9 @@ hs_thread_body(const hs_warp_model &M, const hs_warp_run &P, unsigned char *__re
     }
     for (int k = 0; k < now_n && k < HS_T_KS; ++k) {     /* park the shared-memory part of the now tier */
         uint4 *g = (uint4 *)&Ng[k];
-        g[0] = Ns[(k * 3 + 0) * HS_THREAD_BLOCK + tid];
-        g[1] = Ns[(k * 3 + 1) * HS_THREAD_BLOCK + tid];
-        g[2] = Ns[(k * 3 + 2) * HS_THREAD_BLOCK + tid];
+        g[0] = Ns[(k * 3 + 0) * rpb + tid];
+        g[1] = Ns[(k * 3 + 1) * rpb + tid];
+        g[2] = Ns[(k * 3 + 2) * rpb + tid];
     }
     hdr.ctr = ctr; hdr.now_n = now_n; hdr.free_top = heap_n;
     H->now = h_now; H->processed = h_processed; H->hash = h_hash; H->fel_n = h_fel;

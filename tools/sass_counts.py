@@ -15,10 +15,10 @@ for line in out.splitlines():
         op = m.group(1)
         base = op.split(".")[0]
         cnt[cur][base] += 1
-        if base in ("STG", "LDG", "LDGSTS", "UBLKCP", "STS", "LDS", "SYNCS", "REDG", "ATOMG", "SHFL", "MUFU", "UTMALDG", "UTMASTG"):
+        if base in ("CCTL", "STG", "LDG", "LDGSTS", "UBLKCP", "STS", "LDS", "SYNCS", "REDG", "ATOMG", "SHFL", "MUFU", "UTMALDG", "UTMASTG"):
             cnt[cur][op] += 1
 KEYS = ["STG.E.NA.EFL2.256", "STG.E.ENL2.256", "STG.E.128", "STG.E.64", "STG.E", "LDG.E.128", "LDG.E.64", "LDG.E", "LDGSTS.E.128", "LDGSTS",
-        "UBLKCP", "SYNCS", "SHFL", "REDG", "ATOMG", "STS.128", "LDS.128", "DFMA", "DMUL", "DADD", "MUFU", "IMAD", "BRA", "BSSY"]
+        "UBLKCP", "CCTL.E.PF1", "SYNCS", "SHFL", "REDG", "ATOMG", "STS.128", "LDS.128", "DFMA", "DMUL", "DADD", "MUFU", "IMAD", "BRA", "BSSY"]
 print(f"# {os.path.relpath(lib, ROOT)}: SASS mnemonic counts per kernel (cuobjdump -sass, sm_100a)")
 for fn in sorted(cnt):
     if "hs_" not in fn:

@@ -26,8 +26,10 @@
  * long as the sum of the distinct paths its lanes take: the launch spreads the replicas over as many
  * warps as fit (P.lane_stride lanes per replica, the surplus lanes exit at once).
  *
- * Bound (ncu, profiles/r01_ncu_thread_lb64.txt): issue slots and dependent-instruction latency -- 39 % issue
- * active at 8 replicas per warp, 2.4 of those 8 lanes active on average -- not memory: DRAM runs at 0.19 TB/s.
+ * Bound (ncu, profiles/r02c_ncu_thread_lb64.txt, the 64-server farm at 8 replicas per warp): exposed load latency and
+ * dependent-instruction latency at 128 registers -- 2.4 long-scoreboard + 2.5 fixed-latency stall cycles per issued
+ * instruction, 43 % issue active, 4.3 of the 8 lanes active on average, 50 warp-instructions per event (round 1: 136 at
+ * 2.4 lanes) -- not bandwidth: DRAM runs at 0.43 TB/s.
  * Sort indices are packed above a 16-bit slot number in the heap keys: at most 2^48 events per replica and
  * 65 535 concurrently pending future events.
  */

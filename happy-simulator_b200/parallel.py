@@ -8,6 +8,8 @@ windowed coordinator (parallel/coordinator.py:75-227) on the device: one engine 
 from __future__ import annotations
 
 import time as _time
+
+import numpy as np
 from dataclasses import dataclass, field
 from typing import Any
 
@@ -192,6 +194,7 @@ class ParallelSimulation:
         self._linked.window_ends(self._end_ns)      # raises if the coordinator's clock could not reach the end time
 
     link_buffer = 256        # cross-partition events one replica may emit per window (class default; overflow is reported)
+    queue_ring = 0           # device slots per server queue of a linked run (0: the engine's default); grown and re-run on overflow
 
     def _run_linked(self, n_replicas: int = 1, replica_index_base: int = 0):
         from . import _abi as A
@@ -206,15 +209,37 @@ class ParallelSimulation:
                 ev = max(64, int(_events_bound(m, self._end_ns)))
                 many = len(m.ids_of(A.HS_ENT_SINK)) + len(m.ids_of(A.HS_ENT_PROBE)) > 1 or len(m.ids_of(A.HS_ENT_SERVER)) > 1
                 caps.append(dict(sample_cap=ev, service_cap=ev, record_cap=8 * ev if many else 0))   # records tell the sinks / servers apart
-            outs, (delivered, lost, over) = run.run(seed=self._seed, end_ns=self._end_ns, n_replicas=n_replicas, replica_index_base=replica_index_base,
-                                                    caps=caps, flags=0)
+            # The reference's queues are unbounded, the device's are rings: a replica whose ring filled up stopped early
+            # (HS_ST_QUEUE_OVERFLOW).  Like Simulation.run(), grow the ring and run the whole thing again (every window
+            # starts from scratch: resume = 0 at window 0, a fresh coordinator) instead of handing that to the caller.
+            ring = int(getattr(self, "queue_ring", 0) or 0)
+            for _attempt in range(6):
+                outs, (delivered, lost, over) = run.run(seed=self._seed, end_ns=self._end_ns, n_replicas=n_replicas,
+                                                        replica_index_base=replica_index_base, caps=caps, flags=0, queue_ring=ring)
+                status = 0
+                for o in outs:
+                    status |= int(np.bitwise_or.reduce(o["summaries"]["status"])) if len(o["summaries"]) else 0
+                if not (status & A.HS_ST_QUEUE_OVERFLOW) or (status & ~(A.HS_ST_QUEUE_OVERFLOW | A.HS_ST_LINK_TIE)) or over.any():
+                    break
+                ring = max(512, 4 * ring)
+            self.last_queue_ring = ring
         finally:
             run.close()
         wall = _time.monotonic() - t0
         bad = [(lm.names[q], int(s)) for q, o in enumerate(outs) for s in o["summaries"]["status"] if int(s) & ~A.HS_ST_LINK_TIE]
         if bad or over.any():
-            raise RuntimeError(f"linked run did not complete cleanly: partition status {bad[:4]}, inbox overflows {int(over.sum())} "
-                               f"(raise ParallelSimulation.link_buffer, now {self.link_buffer})")
+            bits = 0
+            for _, s_ in bad:
+                bits |= s_
+            why = []
+            if bits & A.HS_ST_QUEUE_OVERFLOW:
+                why.append(f"a server queue outgrew {ring} device slots (ParallelSimulation.queue_ring)")
+            if (bits & A.HS_ST_LINK_OVERFLOW) or over.any():
+                why.append(f"an outbox / inbox outgrew ParallelSimulation.link_buffer = {self.link_buffer}")
+            if bits & ~(A.HS_ST_QUEUE_OVERFLOW | A.HS_ST_LINK_OVERFLOW):
+                why.append(f"status bits {bits & ~(A.HS_ST_QUEUE_OVERFLOW | A.HS_ST_LINK_OVERFLOW):#x}")
+            raise RuntimeError(f"linked run did not complete cleanly: partition status {bad[:4]}, inbox overflows {int(over.sum())}: "
+                               + "; ".join(why))
         self.link_ties = int(sum(int(s) & A.HS_ST_LINK_TIE != 0 for o in outs for s in o["summaries"]["status"]))
         self.last_outputs, self.last_delivered, self.last_lost = outs, delivered, lost
         return outs, delivered, lost, wall, run.windows

@@ -96,3 +96,40 @@ def test_the_references_own_objects_lower_the_same_way():
     lm, kw, z = G.load_linked("linked_tandem_const")
     for q in range(2):
         assert ps._linked.models[q].entities.tobytes() == lm.models[q].entities.tobytes()
+
+
+def test_a_full_device_queue_ring_is_grown_and_the_linked_run_repeated(monkeypatch):
+    """The reference's queues are unbounded; a device queue ring that filled up (HS_ST_QUEUE_OVERFLOW) is not the
+    caller's problem: the whole linked run is repeated with a larger ring (host logic, no device: LinkedRun is stubbed)."""
+    import numpy as np
+    from happysim_b200 import linked as L, parallel as P
+    rings = []
+
+    class StubRun:
+        def __init__(self, lm, *, device=0):
+            self.lm, self.windows = lm, 0
+        def run(self, *, seed, end_ns, n_replicas=1, replica_index_base=0, caps=None, flags=0, queue_ring=0):
+            rings.append(queue_ring)
+            st = np.zeros(n_replicas, dtype=[("status", "<u4")])
+            if queue_ring < 2048:
+                st["status"][0] = A.HS_ST_QUEUE_OVERFLOW
+            self.windows = 80
+            z = np.zeros(n_replicas, np.uint64)
+            return [{"summaries": st.copy()} for _ in self.lm.models], (z, z.copy(), z.copy())
+        def close(self):
+            pass
+
+    monkeypatch.setattr(L, "LinkedRun", StubRun)
+    parts, link, _ = tandem()
+    ps = hs.ParallelSimulation(parts, duration=4.0, links=[link], seed=5)
+    outs, delivered, lost, wall, windows = ps._run_linked(3)
+    assert rings == [0, 512, 2048] and ps.last_queue_ring == 2048 and windows == 80
+    # a caller's own starting size is respected, and a ring that never suffices ends in an error that names the cause
+    rings.clear()
+    ps.queue_ring = 4096
+    ps._run_linked(1)
+    assert rings == [4096]
+    StubRun.run = lambda self, **kw: ([{"summaries": np.array([(A.HS_ST_QUEUE_OVERFLOW,)], dtype=[("status", "<u4")])} for _ in self.lm.models],
+                                      (np.zeros(1, np.uint64),) * 3)
+    with pytest.raises(RuntimeError, match="queue_ring"):
+        ps._run_linked(1)
